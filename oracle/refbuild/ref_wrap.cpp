@@ -1,0 +1,520 @@
+// oracle/_ref wrapper — TEST INFRASTRUCTURE ONLY (never linked into the product library).
+//
+// A flat C interface over the *unmodified* vendored SEAL-4.1-bs of the reference
+// (/root/reference/thirdparty/SEAL-4.1-bs/native/src/seal, compiled where it lies by
+// oracle/refbuild/Makefile) so that Python tests can
+//   * pin oracle/ckks_oracle.c (the C restatement) against the real implementation, and
+//   * compare the CUDA path bit-for-bit on identical keys / randomness / inputs.
+// Every buffer is raw uint64 residues in SEAL's own layout [poly][limb][coeff]
+// (S/ciphertext.h:339-370).  Nothing here re-implements arithmetic: each entry point loads the
+// raw residues into seal:: value types and calls the reference's public API.
+#include "seal/seal.h"
+#include <cstdint>
+#include <cstring>
+#include <complex>
+#include <memory>
+#include <vector>
+#include <map>
+#include <string>
+#include <chrono>
+#include <omp.h>
+
+using namespace seal;
+using namespace std;
+
+namespace
+{
+    struct Ref
+    {
+        unique_ptr<SEALContext> ctx;
+        unique_ptr<KeyGenerator> keygen;
+        unique_ptr<CKKSEncoder> encoder;
+        unique_ptr<Evaluator> evaluator;
+        unique_ptr<Encryptor> encryptor;
+        unique_ptr<Decryptor> decryptor;
+        SecretKey sk;
+        PublicKey pk;
+        RelinKeys rlk;
+        GaloisKeys glk;
+        bool have_rlk = false;
+        size_t n = 0;
+        size_t n_data_limbs = 0; // limbs at the first (fresh-ciphertext) level
+        string err;
+    };
+
+    parms_id_type parms_for_limbs(const Ref &r, size_t limbs)
+    {
+        auto cd = r.ctx->first_context_data();
+        while (cd && cd->parms().coeff_modulus().size() != limbs)
+        {
+            cd = cd->next_context_data();
+        }
+        if (!cd)
+        {
+            throw invalid_argument("no level with that many limbs");
+        }
+        return cd->parms_id();
+    }
+
+    void load_ct(const Ref &r, const uint64_t *raw, size_t size, size_t limbs, double scale, Ciphertext &ct)
+    {
+        ct.resize(*r.ctx, parms_for_limbs(r, limbs), size);
+        ct.is_ntt_form() = true;
+        ct.scale() = scale;
+        memcpy(ct.data(), raw, size * limbs * r.n * sizeof(uint64_t));
+    }
+
+    void store_ct(const Ref &r, const Ciphertext &ct, uint64_t *raw)
+    {
+        memcpy(raw, ct.data(), ct.size() * ct.coeff_modulus_size() * r.n * sizeof(uint64_t));
+    }
+
+    void load_pt(const Ref &r, const uint64_t *raw, size_t limbs, double scale, Plaintext &pt)
+    {
+        pt.parms_id() = parms_id_zero;
+        pt.resize(limbs * r.n);
+        memcpy(pt.data(), raw, limbs * r.n * sizeof(uint64_t));
+        pt.parms_id() = parms_for_limbs(r, limbs);
+        pt.scale() = scale;
+    }
+} // namespace
+
+#define REF_TRY(r) try {
+#define REF_CATCH(r)                                                                                                   \
+    }                                                                                                                  \
+    catch (const exception &e)                                                                                         \
+    {                                                                                                                  \
+        (r)->err = e.what();                                                                                           \
+        return -1;                                                                                                     \
+    }                                                                                                                  \
+    return 0;
+
+extern "C"
+{
+    // Build the CKKS context the way M/test/test_full_scheme.hpp:381-389 does:
+    // CoeffModulus::Create(N, bits), sparse ternary secret of the given Hamming weight (0 = dense),
+    // SEALContext(parms, true, sec_level_type::none).  `seed` makes all SEAL randomness deterministic.
+    void *ref_create(int log_n, const int *bits, int n_bits, int hamming_weight, uint64_t seed)
+    {
+        auto r = new Ref();
+        try
+        {
+            EncryptionParameters parms(scheme_type::ckks);
+            size_t n = size_t(1) << log_n;
+            parms.set_poly_modulus_degree(n);
+            vector<int> bv(bits, bits + n_bits);
+            parms.set_coeff_modulus(CoeffModulus::Create(n, bv));
+            parms.set_secret_key_hamming_weight(size_t(hamming_weight));
+            prng_seed_type s;
+            for (size_t i = 0; i < s.size(); i++)
+            {
+                s[i] = seed + 0x9E3779B97F4A7C15ULL * (i + 1);
+            }
+            parms.set_random_generator(make_shared<Blake2xbPRNGFactory>(s));
+            r->ctx = make_unique<SEALContext>(parms, true, sec_level_type::none);
+            if (!r->ctx->parameters_set())
+            {
+                throw invalid_argument(string("bad parameters: ") + r->ctx->parameter_error_message());
+            }
+            r->n = n;
+            r->n_data_limbs = r->ctx->first_context_data()->parms().coeff_modulus().size();
+            r->keygen = make_unique<KeyGenerator>(*r->ctx);
+            r->sk = r->keygen->secret_key();
+            r->keygen->create_public_key(r->pk);
+            r->encoder = make_unique<CKKSEncoder>(*r->ctx);
+            r->evaluator = make_unique<Evaluator>(*r->ctx, *r->encoder);
+            r->encryptor = make_unique<Encryptor>(*r->ctx, r->pk);
+            r->decryptor = make_unique<Decryptor>(*r->ctx, r->sk);
+        }
+        catch (const exception &e)
+        {
+            r->err = e.what();
+        }
+        return r;
+    }
+
+    void ref_destroy(void *h)
+    {
+        delete static_cast<Ref *>(h);
+    }
+
+    const char *ref_error(void *h)
+    {
+        return static_cast<Ref *>(h)->err.c_str();
+    }
+
+    int ref_ok(void *h)
+    {
+        return static_cast<Ref *>(h)->ctx && static_cast<Ref *>(h)->err.empty() ? 1 : 0;
+    }
+
+    // All primes of the key level (data primes then the special prime).
+    int ref_n_key_limbs(void *h)
+    {
+        auto r = static_cast<Ref *>(h);
+        return int(r->ctx->key_context_data()->parms().coeff_modulus().size());
+    }
+
+    void ref_primes(void *h, uint64_t *out)
+    {
+        auto r = static_cast<Ref *>(h);
+        auto &cm = r->ctx->key_context_data()->parms().coeff_modulus();
+        for (size_t i = 0; i < cm.size(); i++)
+        {
+            out[i] = cm[i].value();
+        }
+    }
+
+    // NTT tables of key-level limb `limb`: root powers (operand, quotient) in SEAL's stored order,
+    // S/util/ntt.cpp:254-296.
+    void ref_ntt_tables(void *h, int limb, uint64_t *root_op, uint64_t *root_quo, uint64_t *inv_root_op,
+                        uint64_t *inv_root_quo, uint64_t *inv_n_op_quo)
+    {
+        auto r = static_cast<Ref *>(h);
+        auto &t = r->ctx->key_context_data()->small_ntt_tables()[limb];
+        for (size_t i = 0; i < r->n; i++)
+        {
+            root_op[i] = t.get_from_root_powers(i).operand;
+            root_quo[i] = t.get_from_root_powers(i).quotient;
+            inv_root_op[i] = t.get_from_inv_root_powers(i).operand;
+            inv_root_quo[i] = t.get_from_inv_root_powers(i).quotient;
+        }
+        inv_n_op_quo[0] = t.inv_degree_modulo().operand;
+        inv_n_op_quo[1] = t.inv_degree_modulo().quotient;
+    }
+
+    // In-place forward / inverse negacyclic NTT of `count` consecutive polynomials for limb `limb`.
+    void ref_ntt(void *h, int limb, uint64_t *data, int count)
+    {
+        auto r = static_cast<Ref *>(h);
+        auto &t = r->ctx->key_context_data()->small_ntt_tables()[limb];
+        for (int c = 0; c < count; c++)
+        {
+            util::ntt_negacyclic_harvey(data + size_t(c) * r->n, t);
+        }
+    }
+
+    void ref_intt(void *h, int limb, uint64_t *data, int count)
+    {
+        auto r = static_cast<Ref *>(h);
+        auto &t = r->ctx->key_context_data()->small_ntt_tables()[limb];
+        for (int c = 0; c < count; c++)
+        {
+            util::inverse_ntt_negacyclic_harvey(data + size_t(c) * r->n, t);
+        }
+    }
+
+    // ---- keys -------------------------------------------------------------------------------
+    // Secret key in NTT form at the key level: [limb][N].
+    void ref_secret_key(void *h, uint64_t *out)
+    {
+        auto r = static_cast<Ref *>(h);
+        memcpy(out, r->sk.data().data(), size_t(ref_n_key_limbs(h)) * r->n * sizeof(uint64_t));
+    }
+
+    // Public key: [2][key limbs][N].
+    void ref_public_key(void *h, uint64_t *out)
+    {
+        auto r = static_cast<Ref *>(h);
+        memcpy(out, r->pk.data().data(), 2 * size_t(ref_n_key_limbs(h)) * r->n * sizeof(uint64_t));
+    }
+
+    int ref_make_relin_key(void *h)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        r->keygen->create_relin_keys(r->rlk);
+        r->have_rlk = true;
+        REF_CATCH(r)
+    }
+
+    // Adds Galois keys for the given rotation steps (0 is ignored by SEAL; conjugation is requested
+    // with `with_conjugate`).
+    int ref_make_galois_keys(void *h, const int *steps, int n_steps, int with_conjugate)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        vector<uint32_t> elts;
+        auto gt = r->ctx->key_context_data()->galois_tool();
+        for (int i = 0; i < n_steps; i++)
+        {
+            if (steps[i] != 0)
+            {
+                elts.push_back(gt->get_elt_from_step(steps[i]));
+            }
+        }
+        if (with_conjugate)
+        {
+            elts.push_back(gt->get_elt_from_step(0));
+        }
+        GaloisKeys add;
+        r->keygen->create_galois_keys(elts, add);
+        // merge into r->glk
+        auto &dst = r->glk.data();
+        auto &src = add.data();
+        if (dst.size() < src.size())
+        {
+            dst.resize(src.size());
+        }
+        for (size_t i = 0; i < src.size(); i++)
+        {
+            if (!src[i].empty())
+            {
+                dst[i] = src[i];
+            }
+        }
+        r->glk.parms_id() = add.parms_id();
+        REF_CATCH(r)
+    }
+
+    uint32_t ref_galois_elt_from_step(void *h, int step)
+    {
+        auto r = static_cast<Ref *>(h);
+        return r->ctx->key_context_data()->galois_tool()->get_elt_from_step(step);
+    }
+
+    int ref_has_galois_key(void *h, uint32_t elt)
+    {
+        auto r = static_cast<Ref *>(h);
+        return r->glk.has_key(elt) ? 1 : 0;
+    }
+
+    // One key-switching key as [digit][poly(2)][key limb][N]  (S/kswitchkeys.h:335-340).
+    // kind 0 = relin key, kind 1 = Galois key for element `elt`.
+    int ref_export_kswitch_key(void *h, int kind, uint32_t elt, uint64_t *out)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        const vector<PublicKey> *k = nullptr;
+        if (kind == 0)
+        {
+            k = &r->rlk.key(2);
+        }
+        else
+        {
+            k = &r->glk.key(elt);
+        }
+        size_t kl = size_t(ref_n_key_limbs(h));
+        size_t per = 2 * kl * r->n;
+        for (size_t j = 0; j < k->size(); j++)
+        {
+            memcpy(out + j * per, (*k)[j].data().data(), per * sizeof(uint64_t));
+        }
+        REF_CATCH(r)
+    }
+
+    // ---- client side -------------------------------------------------------------------------
+    // encode(vector<complex>) at `limbs` limbs.  values: interleaved re,im, `n_vals` complex numbers.
+    int ref_encode_complex(void *h, const double *values, int n_vals, int limbs, double scale, uint64_t *out)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        vector<complex<double>> v(n_vals);
+        for (int i = 0; i < n_vals; i++)
+        {
+            v[i] = complex<double>(values[2 * i], values[2 * i + 1]);
+        }
+        Plaintext pt;
+        r->encoder->encode(v, parms_for_limbs(*r, limbs), scale, pt);
+        memcpy(out, pt.data(), size_t(limbs) * r->n * sizeof(uint64_t));
+        REF_CATCH(r)
+    }
+
+    int ref_encode_real(void *h, const double *values, int n_vals, int limbs, double scale, uint64_t *out)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        vector<double> v(values, values + n_vals);
+        Plaintext pt;
+        r->encoder->encode(v, parms_for_limbs(*r, limbs), scale, pt);
+        memcpy(out, pt.data(), size_t(limbs) * r->n * sizeof(uint64_t));
+        REF_CATCH(r)
+    }
+
+    int ref_encode_scalar(void *h, double value, int limbs, double scale, uint64_t *out)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        Plaintext pt;
+        r->encoder->encode(value, parms_for_limbs(*r, limbs), scale, pt);
+        memcpy(out, pt.data(), size_t(limbs) * r->n * sizeof(uint64_t));
+        REF_CATCH(r)
+    }
+
+    // decode a plaintext given as raw residues -> n/2 complex values (interleaved)
+    int ref_decode(void *h, const uint64_t *raw, int limbs, double scale, double *out)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        Plaintext pt;
+        load_pt(*r, raw, limbs, scale, pt);
+        vector<complex<double>> v;
+        r->encoder->decode(pt, v);
+        for (size_t i = 0; i < v.size(); i++)
+        {
+            out[2 * i] = v[i].real();
+            out[2 * i + 1] = v[i].imag();
+        }
+        REF_CATCH(r)
+    }
+
+    // Encrypt a raw plaintext (public-key encryption, S/encryptor.cpp) -> size-2 ct at `limbs`.
+    int ref_encrypt(void *h, const uint64_t *pt_raw, int limbs, double scale, uint64_t *out)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        Plaintext pt;
+        load_pt(*r, pt_raw, limbs, scale, pt);
+        Ciphertext ct;
+        r->encryptor->encrypt(pt, ct);
+        store_ct(*r, ct, out);
+        REF_CATCH(r)
+    }
+
+    // Decrypt raw ct -> raw plaintext residues [limbs][N] (NTT form).
+    int ref_decrypt(void *h, const uint64_t *ct_raw, int size, int limbs, double scale, uint64_t *out)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        Ciphertext ct;
+        load_ct(*r, ct_raw, size, limbs, scale, ct);
+        Plaintext pt;
+        r->decryptor->decrypt(ct, pt);
+        memcpy(out, pt.data(), size_t(limbs) * r->n * sizeof(uint64_t));
+        REF_CATCH(r)
+    }
+
+    // ---- Evaluator ops on raw ciphertexts ----------------------------------------------------
+    enum
+    {
+        OP_ADD = 0,
+        OP_SUB = 1,
+        OP_MULTIPLY = 2,
+        OP_SQUARE = 3,
+        OP_RELINEARIZE = 4,
+        OP_RESCALE = 5,
+        OP_MOD_SWITCH = 6,
+        OP_ROTATE = 7,
+        OP_CONJUGATE = 8,
+        OP_MULTIPLY_PLAIN = 9,
+        OP_ADD_PLAIN = 10,
+        OP_SUB_PLAIN = 11,
+        OP_NEGATE = 12,
+        OP_MULTIPLY_CONST = 13,
+        OP_ADD_CONST = 14,
+        OP_DOUBLE = 15,
+        OP_ADD_REDUCED_ERROR = 16,
+        OP_SUB_REDUCED_ERROR = 17,
+        OP_MULTIPLY_REDUCED_ERROR = 18,
+        OP_MULTIPLY_VECTOR_REDUCED_ERROR = 19,
+    };
+
+    // Generic entry: a (size_a, limbs_a, scale_a), optional b (ct or plain raw, limbs_b, scale_b),
+    // integer arg `iarg` (rotation steps), double arg `darg` (constant), vector arg for
+    // multiply_vector (complex interleaved, n/2 values).  Output written to out; *out_size,
+    // *out_limbs, *out_scale filled.
+    int ref_eval(void *h, int op, const uint64_t *a, int size_a, int limbs_a, double scale_a, const uint64_t *b,
+                 int size_b, int limbs_b, double scale_b, int iarg, double darg, const double *varg, uint64_t *out,
+                 int *out_size, int *out_limbs, double *out_scale)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        Ciphertext ca, cb, res;
+        Plaintext pb;
+        load_ct(*r, a, size_a, limbs_a, scale_a, ca);
+        auto &ev = *r->evaluator;
+        switch (op)
+        {
+        case OP_ADD:
+            load_ct(*r, b, size_b, limbs_b, scale_b, cb);
+            ev.add(ca, cb, res);
+            break;
+        case OP_SUB:
+            load_ct(*r, b, size_b, limbs_b, scale_b, cb);
+            ev.sub(ca, cb, res);
+            break;
+        case OP_MULTIPLY:
+            load_ct(*r, b, size_b, limbs_b, scale_b, cb);
+            ev.multiply(ca, cb, res);
+            break;
+        case OP_SQUARE:
+            ev.square(ca, res);
+            break;
+        case OP_RELINEARIZE:
+            ev.relinearize(ca, r->rlk, res);
+            break;
+        case OP_RESCALE:
+            ev.rescale_to_next(ca, res);
+            break;
+        case OP_MOD_SWITCH:
+            ev.mod_switch_to_next(ca, res);
+            break;
+        case OP_ROTATE:
+            ev.rotate_vector(ca, iarg, r->glk, res);
+            break;
+        case OP_CONJUGATE:
+            ev.complex_conjugate(ca, r->glk, res);
+            break;
+        case OP_MULTIPLY_PLAIN:
+            load_pt(*r, b, limbs_b, scale_b, pb);
+            ev.multiply_plain(ca, pb, res);
+            break;
+        case OP_ADD_PLAIN:
+            load_pt(*r, b, limbs_b, scale_b, pb);
+            ev.add_plain(ca, pb, res);
+            break;
+        case OP_SUB_PLAIN:
+            load_pt(*r, b, limbs_b, scale_b, pb);
+            ev.sub_plain(ca, pb, res);
+            break;
+        case OP_NEGATE:
+            ev.negate(ca, res);
+            break;
+        case OP_MULTIPLY_CONST:
+            ev.multiply_const(ca, darg, res);
+            break;
+        case OP_ADD_CONST:
+            ev.add_const(ca, darg, res);
+            break;
+        case OP_DOUBLE:
+            res = ca;
+            ev.double_inplace(res);
+            break;
+        case OP_ADD_REDUCED_ERROR:
+            load_ct(*r, b, size_b, limbs_b, scale_b, cb);
+            ev.add_reduced_error(ca, cb, res);
+            break;
+        case OP_SUB_REDUCED_ERROR:
+            load_ct(*r, b, size_b, limbs_b, scale_b, cb);
+            ev.sub_reduced_error(ca, cb, res);
+            break;
+        case OP_MULTIPLY_REDUCED_ERROR:
+            load_ct(*r, b, size_b, limbs_b, scale_b, cb);
+            ev.multiply_reduced_error(ca, cb, r->rlk, res);
+            break;
+        case OP_MULTIPLY_VECTOR_REDUCED_ERROR:
+        {
+            vector<complex<double>> v(r->n / 2);
+            for (size_t i = 0; i < v.size(); i++)
+            {
+                v[i] = complex<double>(varg[2 * i], varg[2 * i + 1]);
+            }
+            res = ca;
+            ev.multiply_vector_inplace_reduced_error(res, v);
+            break;
+        }
+        default:
+            throw invalid_argument("unknown op");
+        }
+        store_ct(*r, res, out);
+        *out_size = int(res.size());
+        *out_limbs = int(res.coeff_modulus_size());
+        *out_scale = res.scale();
+        REF_CATCH(r)
+    }
+
+    int ref_omp_threads()
+    {
+        return omp_get_max_threads();
+    }
+}

@@ -1,0 +1,33 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+SMALL_BITS = [40, 30, 30, 30, 40]  # small chain used by the fast parity cases (logN = 12)
+SMALL_LOGN = 12
+
+
+@pytest.fixture(scope="session")
+def oracle_small():
+    from oracle import Oracle
+    return Oracle(SMALL_LOGN, SMALL_BITS)
+
+
+@pytest.fixture(scope="session")
+def sealref_small():
+    from oracle import SealRef, have_ref
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    r = SealRef(SMALL_LOGN, SMALL_BITS, hamming_weight=0, seed=7)
+    r.make_relin_key()
+    r.make_galois_keys([1, 2, 4, -1, 256], conjugate=True)
+    return r
