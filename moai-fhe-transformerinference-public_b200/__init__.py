@@ -1,0 +1,281 @@
+"""moai-fhe-transformerinference-public_b200 — B200-native CKKS evaluation backend (host-side Python mirror).
+
+The product is ``libmoai_b200.so`` (hand-written sm_100a CUDA behind the C ABI of
+``include/moai_b200.h``).  This module is the thin Python host side used by the tests and
+``bench.py``: it loads the library with ctypes and mirrors the reference's ``seal::Evaluator``
+method names (S/evaluator.h:93-1386) on *batches* of ciphertexts held in torch CUDA tensors
+(torch only provides device memory, streams and ``torch.distributed`` plumbing).
+
+There is NO CPU fallback: constructing :class:`Backend` without a CUDA device, or without the
+built extension, raises.  Nothing here imports ``oracle/``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmoai_b200.so")
+
+MOAI_BITS = [51] + [46] * 20 + [51] * 14 + [58]  # M/test/test_full_scheme.hpp:356-378
+MOAI_LOG_N = 16
+
+_u64p = C.POINTER(C.c_uint64)
+_lib = None
+
+
+class MoaiError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libmoai_b200 status %d: %s" % (code, msg))
+        self.code = code
+
+
+def load_library():
+    """dlopen the in-tree CUDA extension; fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libmoai_b200.so is missing: run `python __graft_entry__.py` (build()) first; "
+                              "there is no CPU fallback")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.moai_last_error.restype = C.c_char_p
+    return _lib
+
+
+def exported_symbols():
+    """Every entry point include/moai_b200.h declares (checked by the CPU test-suite)."""
+    import re
+    hdr = open(os.path.join(_HERE, "..", "include", "moai_b200.h")).read()
+    hdr += open(os.path.join(_HERE, "..", "include", "moai_b200_modules.h")).read() \
+        if os.path.exists(os.path.join(_HERE, "..", "include", "moai_b200_modules.h")) else ""
+    return sorted(set(re.findall(r"\b(moai_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def to_device(a, device="cuda"):
+    """numpy uint64 array -> torch int64 CUDA tensor holding the same bits."""
+    import torch
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return torch.from_numpy(a.view(np.int64)).to(device)
+
+
+def to_host(t):
+    return t.detach().cpu().numpy().view(np.uint64)
+
+
+class Backend:
+    """One CKKS context on one GPU.  Tensors are int64 CUDA tensors carrying uint64 residues,
+    shaped [batch, size, limbs, n] (ciphertexts) or [limbs, n] (plaintexts)."""
+
+    def __init__(self, log_n, primes, device=0):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("moai_b200 needs a CUDA device (no CPU fallback)")
+        self.torch = torch
+        self.lib = load_library()
+        self.log_n, self.n = log_n, 1 << log_n
+        self.primes = [int(p) for p in primes]
+        self.kl = len(self.primes)
+        self.device = torch.device("cuda", device)
+        arr = (C.c_uint64 * self.kl)(*self.primes)
+        h = C.c_void_p()
+        self._chk(self.lib.moai_context_create(C.c_int32(log_n), arr, C.c_int32(self.kl), C.c_int32(device),
+                                               C.byref(h)))
+        self.h = h
+        self.use_torch_stream()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.moai_context_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise MoaiError(rc, self.lib.moai_last_error().decode())
+
+    def use_torch_stream(self):
+        """Launch on torch's current stream so torch.cuda.Event timing sees the kernels."""
+        s = self.torch.cuda.current_stream(self.device).cuda_stream
+        self._chk(self.lib.moai_set_stream(self.h, C.c_void_p(s)))
+
+    def synchronize(self):
+        self._chk(self.lib.moai_synchronize(self.h))
+
+    def empty(self, *shape):
+        return self.torch.empty(shape, dtype=self.torch.int64, device=self.device)
+
+    # ---- NTT (A1/A2)
+    def ntt_forward_(self, x):
+        b, p, l, n = x.shape
+        self._chk(self.lib.moai_ntt_forward(self.h, _ptr(x), C.c_int64(b), C.c_int32(p), C.c_int32(l)))
+        return x
+
+    def ntt_inverse_(self, x):
+        b, p, l, n = x.shape
+        self._chk(self.lib.moai_ntt_inverse(self.h, _ptr(x), C.c_int64(b), C.c_int32(p), C.c_int32(l)))
+        return x
+
+    def ntt_forward_limb_(self, x, limb):
+        self._chk(self.lib.moai_ntt_forward_limb(self.h, _ptr(x), C.c_int64(x.numel() // self.n), C.c_int32(limb)))
+        return x
+
+    def ntt_inverse_limb_(self, x, limb):
+        self._chk(self.lib.moai_ntt_inverse_limb(self.h, _ptr(x), C.c_int64(x.numel() // self.n), C.c_int32(limb)))
+        return x
+
+    # ---- element-wise (A3-A5, A10)
+    def _bin(self, fn, a, b, out=None):
+        bt, p, l, n = a.shape
+        out = self.torch.empty_like(a) if out is None else out
+        self._chk(fn(self.h, _ptr(a), _ptr(b), _ptr(out), C.c_int64(bt), C.c_int32(p), C.c_int32(l)))
+        return out
+
+    def add(self, a, b, out=None):
+        return self._bin(self.lib.moai_add, a, b, out)
+
+    def sub(self, a, b, out=None):
+        return self._bin(self.lib.moai_sub, a, b, out)
+
+    def negate(self, a, out=None):
+        bt, p, l, n = a.shape
+        out = self.torch.empty_like(a) if out is None else out
+        self._chk(self.lib.moai_negate(self.h, _ptr(a), _ptr(out), C.c_int64(bt), C.c_int32(p), C.c_int32(l)))
+        return out
+
+    def _plain(self, fn, ct, pt, out=None):
+        bt, p, l, n = ct.shape
+        stride = 0 if pt.dim() == 2 else l * n
+        out = self.torch.empty_like(ct) if out is None else out
+        self._chk(fn(self.h, _ptr(ct), _ptr(pt), _ptr(out), C.c_int64(bt), C.c_int32(p), C.c_int32(l),
+                     C.c_int64(stride)))
+        return out
+
+    def add_plain(self, ct, pt, out=None):
+        return self._plain(self.lib.moai_add_plain, ct, pt, out)
+
+    def sub_plain(self, ct, pt, out=None):
+        return self._plain(self.lib.moai_sub_plain, ct, pt, out)
+
+    def multiply_plain(self, ct, pt, out=None):
+        return self._plain(self.lib.moai_multiply_plain, ct, pt, out)
+
+    def multiply(self, a, b, out=None, accumulate=False):
+        bt, p, l, n = a.shape
+        out = self.empty(bt, 3, l, n) if out is None else out
+        self._chk(self.lib.moai_multiply(self.h, _ptr(a), _ptr(b), _ptr(out), C.c_int64(bt), C.c_int32(l),
+                                         C.c_int32(int(accumulate))))
+        return out
+
+    def square(self, a, out=None):
+        bt, p, l, n = a.shape
+        out = self.empty(bt, 3, l, n) if out is None else out
+        self._chk(self.lib.moai_square(self.h, _ptr(a), _ptr(out), C.c_int64(bt), C.c_int32(l)))
+        return out
+
+    # ---- level changes (A8, A9, C1)
+    def rescale_to_next(self, a, out=None):
+        bt, p, l, n = a.shape
+        out = self.empty(bt, p, l - 1, n) if out is None else out
+        self._chk(self.lib.moai_rescale_to_next(self.h, _ptr(a), _ptr(out), C.c_int64(bt), C.c_int32(p), C.c_int32(l)))
+        return out
+
+    def mod_switch_to(self, a, limbs_out, out=None):
+        bt, p, l, n = a.shape
+        out = self.empty(bt, p, limbs_out, n) if out is None else out
+        self._chk(self.lib.moai_mod_switch_to(self.h, _ptr(a), _ptr(out), C.c_int64(bt), C.c_int32(p), C.c_int32(l),
+                                              C.c_int32(limbs_out)))
+        return out
+
+    def mod_switch_to_next(self, a):
+        return self.mod_switch_to(a, a.shape[2] - 1)
+
+    def mod_raise(self, a, limbs_out):
+        bt, p, l, n = a.shape
+        assert l == 1
+        out = self.empty(bt, p, limbs_out, n)
+        self._chk(self.lib.moai_mod_raise(self.h, _ptr(a), _ptr(out), C.c_int64(bt), C.c_int32(p),
+                                          C.c_int32(limbs_out)))
+        return out
+
+    # ---- key switching (A6, A7)
+    def galois_elt_from_step(self, step):
+        e = C.c_uint32()
+        self._chk(self.lib.moai_galois_elt_from_step(self.h, C.c_int32(step), C.byref(e)))
+        return e.value
+
+    def rotate_naf_steps(self, steps):
+        out = (C.c_int32 * 64)()
+        cnt = C.c_int32()
+        self._chk(self.lib.moai_rotate_naf_steps(self.h, C.c_int32(steps), out, C.byref(cnt)))
+        return [out[i] for i in range(cnt.value)]
+
+    def apply_galois(self, a, elt, ksk, out=None):
+        bt, p, l, n = a.shape
+        out = self.torch.empty_like(a) if out is None else out
+        self._chk(self.lib.moai_apply_galois(self.h, _ptr(a), _ptr(out), C.c_int64(bt), C.c_int32(l), C.c_uint32(elt),
+                                             _ptr(ksk)))
+        return out
+
+    def rotate_vector(self, a, steps, galois_keys):
+        """Evaluator::rotate_vector incl. the NAF fallback for missing keys
+        (S/evaluator.cpp:2667-2722).  galois_keys: dict galois_elt -> device key tensor."""
+        if steps == 0:
+            return a
+        elt = self.galois_elt_from_step(steps)
+        if elt in galois_keys:
+            return self.apply_galois(a, elt, galois_keys[elt])
+        if abs(steps) & (abs(steps) - 1) == 0:  # NAF has a single term: nothing to decompose into
+            raise MoaiError(1, "Galois key not present")
+        terms = self.rotate_naf_steps(steps)
+        for s in terms:
+            a = self.rotate_vector(a, s, galois_keys)
+        return a
+
+    def complex_conjugate(self, a, galois_keys):
+        elt = self.galois_elt_from_step(0)
+        if elt not in galois_keys:
+            raise MoaiError(1, "Galois key not present")
+        return self.apply_galois(a, elt, galois_keys[elt])
+
+    def relinearize(self, a3, relin_key, out=None):
+        bt, p, l, n = a3.shape
+        out = self.empty(bt, 2, l, n) if out is None else out
+        self._chk(self.lib.moai_relinearize(self.h, _ptr(a3), _ptr(out), C.c_int64(bt), C.c_int32(l), _ptr(relin_key)))
+        return out
+
+    def switch_key_(self, ct, target, ksk):
+        bt, p, l, n = ct.shape
+        self._chk(self.lib.moai_switch_key(self.h, _ptr(ct), _ptr(target), C.c_int64(bt), C.c_int32(l), _ptr(ksk)))
+        return ct
+
+    # ---- scalar plaintexts (A11, A13)
+    def encode_scalar_consts(self, value, scale, limbs):
+        out = (C.c_uint64 * limbs)()
+        self._chk(self.lib.moai_encode_scalar_consts(self.h, C.c_double(value), C.c_double(scale), C.c_int32(limbs),
+                                                     out))
+        return np.array(list(out), dtype=np.uint64)
+
+    def multiply_const(self, a, value, scale, out=None):
+        bt, p, l, n = a.shape
+        k = self.encode_scalar_consts(value, scale, l)
+        out = self.torch.empty_like(a) if out is None else out
+        self._chk(self.lib.moai_multiply_scalar(self.h, _ptr(a), k.ctypes.data_as(_u64p), _ptr(out), C.c_int64(bt),
+                                                C.c_int32(p), C.c_int32(l)))
+        return out
+
+    def add_const(self, a, value, scale, out=None):
+        bt, p, l, n = a.shape
+        k = self.encode_scalar_consts(value, scale, l)
+        out = self.torch.empty_like(a) if out is None else out
+        self._chk(self.lib.moai_add_scalar(self.h, _ptr(a), k.ctypes.data_as(_u64p), _ptr(out), C.c_int64(bt),
+                                           C.c_int32(p), C.c_int32(l)))
+        return out

@@ -1,0 +1,420 @@
+// C ABI of libmoai_b200.so (declared in include/moai_b200.h).  Thin: argument checks with the
+// reference's error semantics, then the stream-ordered launchers of ops.cuh / ntt.cuh.
+#include "../../include/moai_b200.h"
+#include "ntt.cuh"
+#include "ops.cuh"
+#include <cmath>
+
+using namespace moai;
+
+struct moai_context
+{
+    Context *c;
+};
+
+#define API_BEGIN                                                                                                      \
+    try                                                                                                                \
+    {
+#define API_END                                                                                                        \
+    }                                                                                                                  \
+    catch (const StatusError &e)                                                                                       \
+    {                                                                                                                  \
+        set_last_error(e.msg);                                                                                         \
+        return e.code;                                                                                                 \
+    }                                                                                                                  \
+    catch (const std::exception &e)                                                                                    \
+    {                                                                                                                  \
+        set_last_error(e.what());                                                                                      \
+        return MOAI_LOGIC_ERROR;                                                                                       \
+    }                                                                                                                  \
+    return MOAI_OK;
+
+static Context *get(moai_context *ctx)
+{
+    if (!ctx || !ctx->c)
+    {
+        throw StatusError{ INVALID_ARGUMENT, "null context" };
+    }
+    MOAI_CUDA_CHECK(cudaSetDevice(ctx->c->device));
+    return ctx->c;
+}
+
+static void check_shape(Context *c, long long batch, int size, int limbs)
+{
+    MOAI_REQUIRE(batch >= 0, "negative batch");
+    MOAI_REQUIRE(size >= 1 && size <= 3, "ciphertext size must be 1..3");
+    MOAI_REQUIRE(limbs >= 1 && limbs <= c->kl, "encrypted is not valid for encryption parameters");
+}
+
+extern "C"
+{
+    const char *moai_last_error(void)
+    {
+        return last_error().c_str();
+    }
+
+    int32_t moai_version(void)
+    {
+        return 100;
+    }
+
+    int32_t moai_context_create(int32_t log_n, const uint64_t *primes, int32_t n_key_limbs, int32_t device,
+                                moai_context **out)
+    {
+        API_BEGIN
+        MOAI_REQUIRE(primes && out, "null argument");
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+        {
+            throw StatusError{ CUDA_ERROR, "no CUDA device: libmoai_b200 has no CPU fallback" };
+        }
+        Context *c = context_create(log_n, reinterpret_cast<const u64 *>(primes), n_key_limbs, device);
+        *out = new moai_context{ c };
+        API_END
+    }
+
+    int32_t moai_context_destroy(moai_context *ctx)
+    {
+        API_BEGIN
+        if (ctx)
+        {
+            if (ctx->c)
+            {
+                cudaSetDevice(ctx->c->device);
+                cudaDeviceSynchronize();
+                delete ctx->c;
+            }
+            delete ctx;
+        }
+        API_END
+    }
+
+    int32_t moai_set_stream(moai_context *ctx, void *cuda_stream)
+    {
+        API_BEGIN
+        get(ctx)->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+        API_END
+    }
+
+    int32_t moai_synchronize(moai_context *ctx)
+    {
+        API_BEGIN
+        MOAI_CUDA_CHECK(cudaStreamSynchronize(get(ctx)->stream));
+        API_END
+    }
+
+    int32_t moai_malloc(moai_context *ctx, uint64_t bytes, void **out)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(out, "null argument");
+        MOAI_CUDA_CHECK(cudaMallocAsync(out, bytes ? bytes : 8, c->stream));
+        API_END
+    }
+
+    int32_t moai_free(moai_context *ctx, void *ptr)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        if (ptr)
+        {
+            MOAI_CUDA_CHECK(cudaFreeAsync(ptr, c->stream));
+        }
+        API_END
+    }
+
+    int32_t moai_memcpy_h2d(moai_context *ctx, void *dst, const void *src, uint64_t bytes)
+    {
+        API_BEGIN
+        MOAI_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, get(ctx)->stream));
+        API_END
+    }
+
+    int32_t moai_memcpy_d2h(moai_context *ctx, void *dst, const void *src, uint64_t bytes)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+        MOAI_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        API_END
+    }
+
+    int32_t moai_memcpy_d2d(moai_context *ctx, void *dst, const void *src, uint64_t bytes)
+    {
+        API_BEGIN
+        MOAI_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, get(ctx)->stream));
+        API_END
+    }
+
+    int32_t moai_ntt_forward(moai_context *ctx, uint64_t *data, int64_t batch, int32_t polys, int32_t limbs)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, batch, polys, limbs);
+        ntt_forward(c, reinterpret_cast<u64 *>(data), batch * polys * limbs, c->d_ids, limbs);
+        API_END
+    }
+
+    int32_t moai_ntt_inverse(moai_context *ctx, uint64_t *data, int64_t batch, int32_t polys, int32_t limbs)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, batch, polys, limbs);
+        ntt_inverse(c, reinterpret_cast<u64 *>(data), batch * polys * limbs, c->d_ids, limbs);
+        API_END
+    }
+
+    int32_t moai_ntt_forward_limb(moai_context *ctx, uint64_t *data, int64_t count, int32_t limb)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(limb >= 0 && limb < c->kl, "limb out of range");
+        ntt_forward(c, reinterpret_cast<u64 *>(data), count, c->d_ids + limb, 1);
+        API_END
+    }
+
+    int32_t moai_ntt_inverse_limb(moai_context *ctx, uint64_t *data, int64_t count, int32_t limb)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(limb >= 0 && limb < c->kl, "limb out of range");
+        ntt_inverse(c, reinterpret_cast<u64 *>(data), count, c->d_ids + limb, 1);
+        API_END
+    }
+
+#define U(p) reinterpret_cast<u64 *>(p)
+#define CU(p) reinterpret_cast<const u64 *>(p)
+
+    int32_t moai_add(moai_context *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, int64_t batch,
+                     int32_t size, int32_t limbs)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, batch, size, limbs);
+        ew_addsub(c, EW_ADD, CU(a), CU(b), U(out), batch, size, limbs);
+        API_END
+    }
+
+    int32_t moai_sub(moai_context *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, int64_t batch,
+                     int32_t size, int32_t limbs)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, batch, size, limbs);
+        ew_addsub(c, EW_SUB, CU(a), CU(b), U(out), batch, size, limbs);
+        API_END
+    }
+
+    int32_t moai_negate(moai_context *ctx, const uint64_t *a, uint64_t *out, int64_t batch, int32_t size,
+                        int32_t limbs)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, batch, size, limbs);
+        ew_addsub(c, EW_NEG, CU(a), CU(a), U(out), batch, size, limbs);
+        API_END
+    }
+
+    int32_t moai_add_plain(moai_context *ctx, const uint64_t *ct, const uint64_t *pt, uint64_t *out, int64_t batch,
+                           int32_t size, int32_t limbs, int64_t pt_stride)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, batch, size, limbs);
+        ew_addsub_plain(c, EW_ADD, CU(ct), CU(pt), U(out), batch, size, limbs, pt_stride);
+        API_END
+    }
+
+    int32_t moai_sub_plain(moai_context *ctx, const uint64_t *ct, const uint64_t *pt, uint64_t *out, int64_t batch,
+                           int32_t size, int32_t limbs, int64_t pt_stride)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, batch, size, limbs);
+        ew_addsub_plain(c, EW_SUB, CU(ct), CU(pt), U(out), batch, size, limbs, pt_stride);
+        API_END
+    }
+
+    int32_t moai_multiply_plain(moai_context *ctx, const uint64_t *ct, const uint64_t *pt, uint64_t *out,
+                                int64_t batch, int32_t size, int32_t limbs, int64_t pt_stride)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, batch, size, limbs);
+        ew_multiply_plain(c, CU(ct), CU(pt), U(out), batch, size, limbs, pt_stride);
+        API_END
+    }
+
+    int32_t moai_multiply(moai_context *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, int64_t batch,
+                          int32_t limbs, int32_t accumulate)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, batch, 2, limbs);
+        ew_multiply(c, CU(a), CU(b), U(out), batch, limbs, accumulate != 0);
+        API_END
+    }
+
+    int32_t moai_square(moai_context *ctx, const uint64_t *a, uint64_t *out, int64_t batch, int32_t limbs)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, batch, 2, limbs);
+        ew_square(c, CU(a), U(out), batch, limbs);
+        API_END
+    }
+
+    int32_t moai_rescale_to_next(moai_context *ctx, const uint64_t *in, uint64_t *out, int64_t batch, int32_t size,
+                                 int32_t limbs)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, batch, size, limbs);
+        MOAI_REQUIRE(limbs <= c->kl - 1, "encrypted is not valid for encryption parameters");
+        rescale(c, CU(in), U(out), batch, size, limbs);
+        API_END
+    }
+
+    int32_t moai_mod_switch_to(moai_context *ctx, const uint64_t *in, uint64_t *out, int64_t batch, int32_t size,
+                               int32_t limbs_in, int32_t limbs_out)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, batch, size, limbs_in);
+        mod_switch_drop(c, CU(in), U(out), batch, size, limbs_in, limbs_out);
+        API_END
+    }
+
+    int32_t moai_galois_elt_from_step(moai_context *ctx, int32_t step, uint32_t *elt)
+    {
+        API_BEGIN
+        MOAI_REQUIRE(elt, "null argument");
+        *elt = get(ctx)->elt_from_step(step);
+        API_END
+    }
+
+    int32_t moai_rotate_naf_steps(moai_context *ctx, int32_t steps, int32_t *out_steps, int32_t *out_count)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(out_steps && out_count, "null argument");
+        // non-adjacent form, least significant term first (S/util/numth.h:22-42)
+        const bool neg = steps < 0;
+        long long v = neg ? -(long long)steps : steps;
+        int cnt = 0;
+        for (int i = 0; v; i++)
+        {
+            int zi = (v & 1) ? 2 - (int)(v & 3) : 0;
+            v = (v - zi) >> 1;
+            if (zi)
+            {
+                long long term = (long long)(neg ? -zi : zi) * (1LL << i);
+                long long mag = term < 0 ? -term : term;
+                if ((size_t)mag != (c->n >> 1)) // a term of N/2 slots is the identity rotation
+                {
+                    out_steps[cnt++] = (int32_t)term;
+                }
+            }
+        }
+        *out_count = cnt;
+        API_END
+    }
+
+    int32_t moai_apply_galois(moai_context *ctx, const uint64_t *in, uint64_t *out, int64_t batch, int32_t limbs,
+                              uint32_t galois_elt, const uint64_t *ksk)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, batch, 2, limbs);
+        MOAI_REQUIRE(limbs <= c->kl - 1, "encrypted is not valid for encryption parameters");
+        MOAI_REQUIRE(ksk, "Galois key not present");
+        apply_galois(c, CU(in), U(out), batch, limbs, galois_elt, CU(ksk));
+        API_END
+    }
+
+    int32_t moai_relinearize(moai_context *ctx, const uint64_t *in3, uint64_t *out2, int64_t batch, int32_t limbs,
+                             const uint64_t *ksk)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, batch, 3, limbs);
+        MOAI_REQUIRE(limbs <= c->kl - 1, "encrypted is not valid for encryption parameters");
+        MOAI_REQUIRE(ksk, "not enough relinearization keys");
+        relinearize(c, CU(in3), U(out2), batch, limbs, CU(ksk));
+        API_END
+    }
+
+    int32_t moai_switch_key(moai_context *ctx, uint64_t *ct, const uint64_t *target, int64_t batch, int32_t limbs,
+                            const uint64_t *ksk)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, batch, 2, limbs);
+        MOAI_REQUIRE(limbs <= c->kl - 1, "encrypted is not valid for encryption parameters");
+        switch_key(c, U(ct), CU(target), batch, limbs, CU(ksk));
+        API_END
+    }
+
+    int32_t moai_encode_scalar_consts(moai_context *ctx, double value, double scale, int32_t limbs,
+                                      uint64_t *host_out)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(limbs >= 1 && limbs <= c->kl && host_out, "bad arguments");
+        MOAI_REQUIRE(scale > 0, "scale out of bounds");
+        // CKKSEncoder::encode_internal(double): round(value*scale), sign-magnitude, residue per limb
+        double v = value * scale;
+        int bit_count = (int)(std::log2(std::fabs(v))) + 2;
+        double r = std::round(v);
+        const bool neg = std::signbit(r);
+        r = std::fabs(r);
+        MOAI_REQUIRE(bit_count <= 128, "encoded value is too large");
+        unsigned __int128 mag;
+        if (bit_count <= 64)
+        {
+            mag = (u64)r;
+        }
+        else
+        {
+            const double two64 = std::pow(2.0, 64);
+            mag = (((unsigned __int128)(u64)(r / two64)) << 64) | (u64)std::fmod(r, two64);
+        }
+        for (int l = 0; l < limbs; l++)
+        {
+            u64 res = (u64)(mag % c->q[l]);
+            host_out[l] = neg ? (res ? c->q[l] - res : 0) : res;
+        }
+        API_END
+    }
+
+    int32_t moai_multiply_scalar(moai_context *ctx, const uint64_t *ct, const uint64_t *host_consts, uint64_t *out,
+                                 int64_t batch, int32_t size, int32_t limbs)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, batch, size, limbs);
+        ew_multiply_scalar(c, CU(ct), CU(host_consts), U(out), batch, size, limbs);
+        API_END
+    }
+
+    int32_t moai_add_scalar(moai_context *ctx, const uint64_t *ct, const uint64_t *host_consts, uint64_t *out,
+                            int64_t batch, int32_t size, int32_t limbs)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, batch, size, limbs);
+        ew_add_scalar(c, CU(ct), CU(host_consts), U(out), batch, size, limbs);
+        API_END
+    }
+
+    int32_t moai_mod_raise(moai_context *ctx, const uint64_t *in, uint64_t *out, int64_t batch, int32_t size,
+                           int32_t limbs_out)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, batch, size, limbs_out);
+        mod_raise(c, CU(in), U(out), batch, size, limbs_out);
+        API_END
+    }
+}

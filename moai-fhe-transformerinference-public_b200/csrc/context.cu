@@ -1,0 +1,333 @@
+// Context construction: derives every table the kernels need from (log N, prime chain).
+// The caller passes the primes of its SEALContext key level (data primes then the special
+// prime); the tables below are the same mathematical objects SEAL builds in
+// NTTTables::initialize (S/util/ntt.cpp:241-300), RNSTool::initialize (S/util/rns.cpp:578-787),
+// GaloisTool (S/util/galois.cpp:18-95) and CKKSEncoder::CKKSEncoder (S/ckks.cpp:20-75).
+#include "context.hpp"
+#include <cmath>
+#include <complex>
+#include <cstring>
+
+namespace moai
+{
+    namespace
+    {
+        typedef unsigned __int128 u128h;
+
+        thread_local std::string g_last_error;
+
+        u64 h_mulmod(u64 a, u64 b, u64 q)
+        {
+            return (u64)(((u128h)a * b) % q);
+        }
+
+        u64 h_powmod(u64 a, u64 e, u64 q)
+        {
+            u64 r = 1;
+            a %= q;
+            for (; e; e >>= 1)
+            {
+                if (e & 1)
+                {
+                    r = h_mulmod(r, a, q);
+                }
+                a = h_mulmod(a, a, q);
+            }
+            return r;
+        }
+
+        u64 h_invmod(u64 a, u64 q)
+        {
+            return h_powmod(a % q, q - 2, q);
+        }
+
+        u64 h_shoup(u64 w, u64 q)
+        {
+            return (u64)((((u128h)w) << 64) / q);
+        }
+
+        u64 bitrev(u64 x, int bits)
+        {
+            u64 r = 0;
+            for (int i = 0; i < bits; i++)
+            {
+                r = (r << 1) | ((x >> i) & 1);
+            }
+            return r;
+        }
+
+        // Smallest primitive 2N-th root of unity mod q (what SEAL's try_minimal_primitive_root
+        // selects, S/util/numth.cpp:385-413): take any primitive root and scan its odd powers.
+        u64 minimal_primitive_root(u64 two_n, u64 q)
+        {
+            u64 cofactor = (q - 1) / two_n;
+            u64 g = 0;
+            for (u64 a = 2;; a++)
+            {
+                g = h_powmod(a, cofactor, q);
+                if (h_powmod(g, two_n >> 1, q) == q - 1)
+                {
+                    break;
+                }
+            }
+            u64 g2 = h_mulmod(g, g, q), cur = g, best = g;
+            for (u64 i = 0; i < two_n; i += 2)
+            {
+                best = cur < best ? cur : best;
+                cur = h_mulmod(cur, g2, q);
+            }
+            return best;
+        }
+
+        template <class T>
+        T *to_device(const std::vector<T> &h)
+        {
+            T *d = nullptr;
+            MOAI_CUDA_CHECK(cudaMalloc(&d, h.size() * sizeof(T)));
+            MOAI_CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+            return d;
+        }
+    } // namespace
+
+    void set_last_error(const std::string &msg)
+    {
+        g_last_error = msg;
+    }
+
+    const std::string &last_error()
+    {
+        return g_last_error;
+    }
+
+    Scratch::Scratch(size_t bytes, cudaStream_t stream) : s(stream)
+    {
+        if (bytes)
+        {
+            MOAI_CUDA_CHECK(cudaMallocAsync(&p, bytes, stream));
+        }
+    }
+
+    Scratch::~Scratch()
+    {
+        if (p)
+        {
+            cudaFreeAsync(p, s);
+        }
+    }
+
+    Context::~Context()
+    {
+        cudaFree(d_limb);
+        cudaFree(d_fwd);
+        cudaFree(d_inv);
+        cudaFree(d_inv_last);
+        cudaFree(d_half_mod);
+        cudaFree(d_two64);
+        cudaFree(d_ids);
+        cudaFree(d_ids_ks);
+        cudaFree(d_fft_inv_roots);
+        cudaFree(d_index_map);
+        for (auto &kv : galois_tables)
+        {
+            cudaFree(kv.second);
+        }
+    }
+
+    uint32_t Context::elt_from_step(int step) const
+    {
+        // generator 5 (fork: S/util/galois.h:169); step 0 = complex conjugation (2N - 1)
+        uint64_t m = (uint64_t)n << 1;
+        if (step == 0)
+        {
+            return (uint32_t)(m - 1);
+        }
+        uint32_t pos = (uint32_t)(step < 0 ? -(int64_t)step : step);
+        if (pos >= (n >> 1))
+        {
+            throw StatusError{ INVALID_ARGUMENT, "step count too large" };
+        }
+        uint32_t e = step < 0 ? (uint32_t)(n >> 1) - pos : pos;
+        uint64_t g = 1;
+        while (e--)
+        {
+            g = (g * 5) & (m - 1);
+        }
+        return (uint32_t)g;
+    }
+
+    const uint32_t *Context::galois_table(uint32_t elt)
+    {
+        std::lock_guard<std::mutex> lk(galois_mu);
+        auto it = galois_tables.find(elt);
+        if (it != galois_tables.end())
+        {
+            return it->second;
+        }
+        if (!(elt & 1) || elt >= 2 * n)
+        {
+            throw StatusError{ INVALID_ARGUMENT, "Galois element is not valid" };
+        }
+        // NTT-domain automorphism as an index permutation (S/util/galois.cpp:36-43)
+        std::vector<uint32_t> h(n);
+        for (size_t i = 0; i < n; i++)
+        {
+            u64 rev = bitrev(n + i, log_n + 1);
+            u64 idx = (((u64)elt * rev) >> 1) & (n - 1);
+            h[i] = (uint32_t)bitrev(idx, log_n);
+        }
+        uint32_t *d = to_device(h);
+        galois_tables[elt] = d;
+        return d;
+    }
+
+    Context *context_create(int log_n, const u64 *primes, int kl, int device)
+    {
+        MOAI_REQUIRE(log_n >= 12 && log_n <= 16, "log_n must be in [12, 16]");
+        MOAI_REQUIRE(kl >= 2 && kl <= 64, "need 2..64 primes (data primes + special prime)");
+        MOAI_CUDA_CHECK(cudaSetDevice(device));
+        Context *c = new Context();
+        c->device = device;
+        c->log_n = log_n;
+        c->n = (size_t)1 << log_n;
+        c->kl = kl;
+        c->q.assign(primes, primes + kl);
+        size_t n = c->n;
+        cudaDeviceProp prop;
+        MOAI_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        c->sm_count = prop.multiProcessorCount;
+
+        std::vector<Twiddle> fwd((size_t)kl * n), inv((size_t)kl * n);
+        c->h_limb.resize(kl);
+        for (int l = 0; l < kl; l++)
+        {
+            u64 q = primes[l];
+            MOAI_REQUIRE(q > 2 && (q >> 61) == 0 && (q - 1) % (2 * n) == 0, "prime must be < 2^61 and = 1 mod 2N");
+            u64 psi = minimal_primitive_root(2 * n, q);
+            u64 ipsi = h_invmod(psi, q);
+            Twiddle *f = fwd.data() + (size_t)l * n, *g = inv.data() + (size_t)l * n;
+            u64 pw = psi, ipw = ipsi;
+            f[0] = Twiddle{ 1, h_shoup(1, q) };
+            g[0] = Twiddle{ 1, h_shoup(1, q) };
+            for (size_t i = 1; i < n; i++)
+            {
+                f[bitrev(i, log_n)] = Twiddle{ pw, h_shoup(pw, q) };
+                g[bitrev(i - 1, log_n) + 1] = Twiddle{ ipw, h_shoup(ipw, q) };
+                pw = h_mulmod(pw, psi, q);
+                ipw = h_mulmod(ipw, ipsi, q);
+            }
+            LimbConst &lc = c->h_limb[l];
+            lc.q = q;
+            lc.two_q = q << 1;
+            int bits = 64 - __builtin_clzll(q);
+            lc.bar_shift = (u32)(bits - 1);
+            lc.bar_m = (u64)((((u128h)1) << (64 + bits - 1)) / q);
+            lc.pad = 0;
+            lc.inv_n = h_invmod((u64)n % q, q);
+            lc.inv_n_quo = h_shoup(lc.inv_n, q);
+            lc.inv_n_w = h_mulmod(g[n - 1].w, lc.inv_n, q); // last GS stage root times N^-1
+            lc.inv_n_w_quo = h_shoup(lc.inv_n_w, q);
+            lc.q0_mod = primes[0] % q;
+        }
+        c->d_fwd = to_device(fwd);
+        c->d_inv = to_device(inv);
+        c->d_limb = to_device(c->h_limb);
+
+        std::vector<Twiddle> inv_last((size_t)kl * kl), two64(kl);
+        std::vector<u64> half_mod((size_t)kl * kl);
+        for (int last = 0; last < kl; last++)
+        {
+            for (int i = 0; i < kl; i++)
+            {
+                Twiddle t{ 0, 0 };
+                if (i != last)
+                {
+                    t.w = h_invmod(primes[last] % primes[i], primes[i]);
+                    t.wq = h_shoup(t.w, primes[i]);
+                }
+                inv_last[(size_t)last * kl + i] = t;
+                half_mod[(size_t)last * kl + i] = (primes[last] >> 1) % primes[i];
+            }
+        }
+        for (int i = 0; i < kl; i++)
+        {
+            u64 r = (u64)((((u128h)1) << 64) % primes[i]);
+            two64[i] = Twiddle{ r, h_shoup(r, primes[i]) };
+        }
+        c->d_inv_last = to_device(inv_last);
+        c->d_half_mod = to_device(half_mod);
+        c->d_two64 = to_device(two64);
+
+        std::vector<int> ids(kl), ids_ks((size_t)kl * (kl + 1), 0);
+        for (int i = 0; i < kl; i++)
+        {
+            ids[i] = i;
+        }
+        for (int l = 1; l < kl; l++)
+        {
+            for (int i = 0; i < l; i++)
+            {
+                ids_ks[(size_t)l * (kl + 1) + i] = i;
+            }
+            ids_ks[(size_t)l * (kl + 1) + l] = kl - 1;
+        }
+        c->d_ids = to_device(ids);
+        c->d_ids_ks = to_device(ids_ks);
+
+        // CKKS encoder tables: index map (generator 5 orbit, S/ckks.cpp:36-52) and the inverse
+        // FFT roots conj(zeta^{bitrev(i-1)+1}) (S/ckks.cpp:56-66, S/util/croots.cpp:17-72).
+        size_t slots = n >> 1;
+        u64 m = (u64)n << 1;
+        c->h_index_map.resize(n);
+        u64 pos = 1;
+        for (size_t i = 0; i < slots; i++)
+        {
+            c->h_index_map[i] = (uint32_t)bitrev((pos - 1) >> 1, log_n);
+            c->h_index_map[slots | i] = (uint32_t)bitrev((m - pos - 1) >> 1, log_n);
+            pos = (pos * 5) & (m - 1);
+        }
+        // Octant table + symmetries, evaluated exactly like the reference so that the doubles
+        // agree bit for bit with std::polar on the same libm.
+        std::vector<std::complex<double>> oct(m / 8 + 1);
+        const double PI = 3.1415926535897932384626433832795028842;
+        for (size_t i = 0; i <= m / 8; i++)
+        {
+            oct[i] = std::polar<double>(1.0, 2 * PI * static_cast<double>(i) / static_cast<double>(m));
+        }
+        std::function<std::complex<double>(size_t)> root = [&](size_t index) -> std::complex<double> {
+            index &= m - 1;
+            if (index <= m / 8)
+            {
+                return oct[index];
+            }
+            else if (index <= m / 4)
+            {
+                auto a = oct[m / 4 - index];
+                return { a.imag(), a.real() };
+            }
+            else if (index <= m / 2)
+            {
+                return -std::conj(root(m / 2 - index));
+            }
+            else if (index <= 3 * m / 4)
+            {
+                return -root(index - m / 2);
+            }
+            return std::conj(root(m - index));
+        };
+        c->h_fft_inv_roots.assign(n, double2{ 0, 0 });
+        for (size_t i = 1; i < n; i++)
+        {
+            auto z = std::conj(root(bitrev(i - 1, log_n) + 1));
+            c->h_fft_inv_roots[i] = double2{ z.real(), z.imag() };
+        }
+        c->d_fft_inv_roots = to_device(c->h_fft_inv_roots);
+        c->d_index_map = to_device(c->h_index_map);
+
+        // keep freed scratch memory cached in the stream-ordered pool
+        cudaMemPool_t pool;
+        MOAI_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t thresh = UINT64_MAX;
+        MOAI_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+        return c;
+    }
+} // namespace moai

@@ -1,0 +1,117 @@
+// Host-side context of the B200 CKKS evaluation backend.
+//
+// Mirrors what the reference keeps per SEALContext::ContextData (S/context.h) for the hot
+// path: the prime chain, per-prime NTT tables (S/util/ntt.cpp:241-300), the rescale / mod-down
+// constants inv_q_last_mod_q (S/util/rns.cpp:578-787), Galois permutation tables
+// (S/util/galois.cpp:18-51) and the CKKS encoder tables (S/ckks.cpp:20-75) — all resident in
+// HBM and built eagerly at creation.
+#pragma once
+#include "modarith.cuh"
+#include <cuda_runtime.h>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace moai
+{
+    enum Status : int
+    {
+        OK = 0,
+        INVALID_ARGUMENT = 1, // maps to std::invalid_argument in the C++ facade
+        LOGIC_ERROR = 2,      // maps to std::logic_error
+        CUDA_ERROR = 3,
+        OUT_OF_MEMORY = 4,
+    };
+
+    struct StatusError
+    {
+        int code;
+        std::string msg;
+    };
+
+    void set_last_error(const std::string &msg);
+    const std::string &last_error();
+
+#define MOAI_CUDA_CHECK(expr)                                                                                          \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        cudaError_t _e = (expr);                                                                                       \
+        if (_e != cudaSuccess)                                                                                         \
+        {                                                                                                              \
+            throw ::moai::StatusError{ _e == cudaErrorMemoryAllocation ? ::moai::OUT_OF_MEMORY : ::moai::CUDA_ERROR,   \
+                                       std::string(#expr) + ": " + cudaGetErrorString(_e) };                           \
+        }                                                                                                              \
+    } while (0)
+
+#define MOAI_REQUIRE(cond, msg)                                                                                        \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        if (!(cond))                                                                                                   \
+        {                                                                                                              \
+            throw ::moai::StatusError{ ::moai::INVALID_ARGUMENT, std::string(msg) };                                   \
+        }                                                                                                              \
+    } while (0)
+
+    // Twiddle entry: Shoup pair, one 16-byte load in the kernels.
+    struct __align__(16) Twiddle
+    {
+        u64 w;
+        u64 wq;
+    };
+
+    struct Context
+    {
+        int device = 0;
+        int log_n = 0;
+        size_t n = 0;
+        int kl = 0; // key-level limb count (data primes + special prime)
+        std::vector<u64> q;
+        cudaStream_t stream = nullptr;
+        int sm_count = 148;
+
+        // device tables
+        LimbConst *d_limb = nullptr;   // [kl]
+        Twiddle *d_fwd = nullptr;      // [kl][n]  psi powers, bit-reversed order
+        Twiddle *d_inv = nullptr;      // [kl][n]  psi^-1 powers, scrambled order
+        Twiddle *d_inv_last = nullptr; // [kl][kl] inv_last[last][i] = q_last^-1 mod q_i (i != last)
+        u64 *d_half_mod = nullptr;     // [kl][kl] half_mod[last][i] = (q_last >> 1) mod q_i
+        Twiddle *d_two64 = nullptr;    // [kl] 2^64 mod q_i
+        int *d_ids = nullptr;          // [kl] identity limb ids 0..kl-1
+        int *d_ids_ks = nullptr;       // [kl][kl+1]: row l = {0..l-1, kl-1} target moduli of a key switch at l limbs
+
+        // CKKS encoder tables
+        double2 *d_fft_inv_roots = nullptr; // [n]
+        uint32_t *d_index_map = nullptr;    // [n]
+        std::vector<double2> h_fft_inv_roots;
+        std::vector<uint32_t> h_index_map;
+
+        std::vector<LimbConst> h_limb;
+
+        std::mutex galois_mu;
+        std::map<uint32_t, uint32_t *> galois_tables; // elt -> device [n]
+
+        ~Context();
+        const uint32_t *galois_table(uint32_t elt);
+        uint32_t elt_from_step(int step) const;
+    };
+
+    Context *context_create(int log_n, const u64 *primes, int kl, int device);
+
+    // stream-ordered scratch allocation
+    struct Scratch
+    {
+        void *p = nullptr;
+        cudaStream_t s;
+        Scratch(size_t bytes, cudaStream_t stream);
+        ~Scratch();
+        template <class T>
+        T *as()
+        {
+            return reinterpret_cast<T *>(p);
+        }
+        Scratch(const Scratch &) = delete;
+        Scratch &operator=(const Scratch &) = delete;
+    };
+} // namespace moai

@@ -1,0 +1,594 @@
+// Element-wise, rescale / mod-switch / mod-raise and key-switching kernels.
+// Reference behaviour (canonical residues, SEAL layout) per SURVEY Appendix D:
+//   add/sub/negate      S/util/polyarithsmallmod.h:77-300, S/evaluator.cpp:130-350
+//   multiply_plain      S/evaluator.cpp:2336-2373
+//   multiply / square   S/evaluator.cpp:770-909, 1223-1282
+//   rescale             S/util/rns.cpp:830-901 (divide_and_round_q_last_ntt_inplace)
+//   mod-switch          S/evaluator.cpp:1483-1546
+//   key switch          S/evaluator.cpp:2724-3021
+//   Galois (NTT form)   S/util/galois.cpp:192-218
+//   ModRaise            M/source/bootstrapping/Bootstrapper.cpp:2938-2992
+// All kernels are HBM-streaming: flat 1-D grids, 16-byte vector accesses, one limb constant
+// lookup per thread (limb index is uniform per 2-element vector because n is even).
+#include "ntt.cuh"
+#include "ops.cuh"
+
+namespace moai
+{
+    namespace
+    {
+        constexpr int EW_THREADS = 256;
+
+        inline unsigned grid_for(long long work_items)
+        {
+            return (unsigned)((work_items + EW_THREADS - 1) / EW_THREADS);
+        }
+
+        // ------------------------------------------------------------------ add / sub / negate
+        __global__ void k_addsub(int op, const ulonglong2 *__restrict__ a, const ulonglong2 *__restrict__ b,
+                                 ulonglong2 *__restrict__ out, long long total2, int log_n2, int limbs,
+                                 const LimbConst *__restrict__ lcs)
+        {
+            long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= total2)
+            {
+                return;
+            }
+            const int limb = (int)((i >> log_n2) % limbs);
+            const u64 q = lcs[limb].q;
+            ulonglong2 x = a[i], r;
+            if (op == EW_NEG)
+            {
+                r.x = negmod(x.x, q);
+                r.y = negmod(x.y, q);
+            }
+            else
+            {
+                ulonglong2 y = b[i];
+                if (op == EW_ADD)
+                {
+                    r.x = addmod(x.x, y.x, q);
+                    r.y = addmod(x.y, y.y, q);
+                }
+                else
+                {
+                    r.x = submod(x.x, y.x, q);
+                    r.y = submod(x.y, y.y, q);
+                }
+            }
+            out[i] = r;
+        }
+
+        // ct[b][p][l][i] (op) pt[b*stride][l][i] on poly 0, copy on the others
+        __global__ void k_addsub_plain(int op, const ulonglong2 *__restrict__ ct, const ulonglong2 *__restrict__ pt,
+                                       ulonglong2 *__restrict__ out, long long total2, int log_n2, int polys, int limbs,
+                                       long long pt_stride2, const LimbConst *__restrict__ lcs)
+        {
+            long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= total2)
+            {
+                return;
+            }
+            const long long lp = i >> log_n2; // (b * polys + p) * limbs + l
+            const int limb = (int)(lp % limbs);
+            const long long bp = lp / limbs;
+            const int p = (int)(bp % polys);
+            ulonglong2 x = ct[i];
+            if (p == 0)
+            {
+                const long long b = bp / polys;
+                const u64 q = lcs[limb].q;
+                const long long within = i & (((long long)1 << log_n2) - 1);
+                ulonglong2 y = pt[b * pt_stride2 + ((long long)limb << log_n2) + within];
+                if (op == EW_ADD)
+                {
+                    x.x = addmod(x.x, y.x, q);
+                    x.y = addmod(x.y, y.y, q);
+                }
+                else
+                {
+                    x.x = submod(x.x, y.x, q);
+                    x.y = submod(x.y, y.y, q);
+                }
+            }
+            out[i] = x;
+        }
+
+        __global__ void k_multiply_plain(const ulonglong2 *__restrict__ ct, const ulonglong2 *__restrict__ pt,
+                                         ulonglong2 *__restrict__ out, long long total2, int log_n2, int polys,
+                                         int limbs, long long pt_stride2, const LimbConst *__restrict__ lcs)
+        {
+            long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= total2)
+            {
+                return;
+            }
+            const long long lp = i >> log_n2;
+            const int limb = (int)(lp % limbs);
+            const long long b = lp / limbs / polys;
+            const LimbConst lc = lcs[limb];
+            const long long within = i & (((long long)1 << log_n2) - 1);
+            ulonglong2 x = ct[i];
+            ulonglong2 y = pt[b * pt_stride2 + ((long long)limb << log_n2) + within];
+            x.x = mulmod(x.x, y.x, lc);
+            x.y = mulmod(x.y, y.y, lc);
+            out[i] = x;
+        }
+
+        // mode 0: out = ct * k[l] (all polys);  mode 1: out = ct + k[l] on poly 0
+        __global__ void k_scalar(int mode, const ulonglong2 *__restrict__ ct, const Twiddle *__restrict__ consts,
+                                 ulonglong2 *__restrict__ out, long long total2, int log_n2, int polys, int limbs,
+                                 const LimbConst *__restrict__ lcs)
+        {
+            long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= total2)
+            {
+                return;
+            }
+            const long long lp = i >> log_n2;
+            const int limb = (int)(lp % limbs);
+            const int p = (int)((lp / limbs) % polys);
+            const u64 q = lcs[limb].q;
+            const Twiddle k = consts[limb];
+            ulonglong2 x = ct[i];
+            if (mode == 0)
+            {
+                x.x = mul_shoup(x.x, k.w, k.wq, q);
+                x.y = mul_shoup(x.y, k.w, k.wq, q);
+            }
+            else if (p == 0)
+            {
+                x.x = addmod(x.x, k.w, q);
+                x.y = addmod(x.y, k.w, q);
+            }
+            out[i] = x;
+        }
+
+        // (a0, a1) x (b0, b1) -> (a0 b0, a0 b1 + a1 b0, a1 b1); one thread per coefficient pair of a limb
+        __global__ void k_multiply(const ulonglong2 *__restrict__ a, const ulonglong2 *__restrict__ b,
+                                   ulonglong2 *__restrict__ out, long long total2, int log_n2, int limbs,
+                                   const LimbConst *__restrict__ lcs, int accumulate, int square)
+        {
+            long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; // over [batch][limbs][n/2]
+            if (i >= total2)
+            {
+                return;
+            }
+            const long long lb = i >> log_n2; // b * limbs + l
+            const int limb = (int)(lb % limbs);
+            const long long bt = lb / limbs;
+            const LimbConst lc = lcs[limb];
+            const long long within = i & (((long long)1 << log_n2) - 1);
+            const long long poly2 = (long long)limbs << log_n2;
+            const long long off_in = bt * 2 * poly2 + ((long long)limb << log_n2) + within;
+            const long long off_out = bt * 3 * poly2 + ((long long)limb << log_n2) + within;
+            ulonglong2 a0 = a[off_in], a1 = a[off_in + poly2];
+            ulonglong2 b0 = square ? a0 : b[off_in], b1 = square ? a1 : b[off_in + poly2];
+            ulonglong2 r0, r1, r2;
+            r0.x = mulmod(a0.x, b0.x, lc);
+            r0.y = mulmod(a0.y, b0.y, lc);
+            r2.x = mulmod(a1.x, b1.x, lc);
+            r2.y = mulmod(a1.y, b1.y, lc);
+            u128 m;
+            m = mul_wide(a0.x, b1.x);
+            mac_wide(m, a1.x, b0.x);
+            r1.x = barrett_reduce_wide(m, lc);
+            m = mul_wide(a0.y, b1.y);
+            mac_wide(m, a1.y, b0.y);
+            r1.y = barrett_reduce_wide(m, lc);
+            if (accumulate)
+            {
+                ulonglong2 o0 = out[off_out], o1 = out[off_out + poly2], o2 = out[off_out + 2 * poly2];
+                r0.x = addmod(r0.x, o0.x, lc.q);
+                r0.y = addmod(r0.y, o0.y, lc.q);
+                r1.x = addmod(r1.x, o1.x, lc.q);
+                r1.y = addmod(r1.y, o1.y, lc.q);
+                r2.x = addmod(r2.x, o2.x, lc.q);
+                r2.y = addmod(r2.y, o2.y, lc.q);
+            }
+            out[off_out] = r0;
+            out[off_out + poly2] = r1;
+            out[off_out + 2 * poly2] = r2;
+        }
+
+        // ------------------------------------------------------------------ divide-and-round by the last limb
+        // in:  [P][limbs_in][n] with the divisor limb last (prime index `last_id`), targets 0..limbs_in-2
+        // step 1 (host): t[P][n] = INTT_last(in[.][limbs_in-1])
+        // step 2: u[P][limbs_in-1][n] = ((t + half) mod q_last) mod q_i + (q_i - half mod q_i)     (< 2 q_i)
+        __global__ void k_divround_expand(const ulonglong2 *__restrict__ t, ulonglong2 *__restrict__ u, long long total2,
+                                          int log_n2, int targets, int last_id, int kl,
+                                          const LimbConst *__restrict__ lcs, const u64 *__restrict__ half_mod)
+        {
+            long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; // over [P][targets][n/2]
+            if (i >= total2)
+            {
+                return;
+            }
+            const long long lp = i >> log_n2;
+            const int limb = (int)(lp % targets);
+            const long long p = lp / targets;
+            const long long within = i & (((long long)1 << log_n2) - 1);
+            const LimbConst lq = lcs[last_id];
+            const LimbConst lc = lcs[limb];
+            const u64 half = lq.q >> 1;
+            const u64 fix = lc.q - half_mod[(size_t)last_id * kl + limb];
+            ulonglong2 v = t[(p << log_n2) + within];
+            v.x = addmod(v.x, half, lq.q);
+            v.y = addmod(v.y, half, lq.q);
+            ulonglong2 r;
+            r.x = reduce64(v.x, lc) + fix;
+            r.y = reduce64(v.y, lc) + fix;
+            u[i] = r;
+        }
+
+        // step 4: out[P][targets][n] = (in[P][limbs_in][n](limb i) - u) * q_last^-1 mod q_i  (+ addend)
+        __global__ void k_divround_finish(const ulonglong2 *__restrict__ in, const ulonglong2 *__restrict__ u,
+                                          const ulonglong2 *addend, ulonglong2 *out, // may alias each other
+                                          long long total2, int log_n2, int targets, int limbs_in, int last_id, int kl,
+                                          const LimbConst *__restrict__ lcs, const Twiddle *__restrict__ inv_last)
+        {
+            long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; // over [P][targets][n/2]
+            if (i >= total2)
+            {
+                return;
+            }
+            const long long lp = i >> log_n2;
+            const int limb = (int)(lp % targets);
+            const long long p = lp / targets;
+            const long long within = i & (((long long)1 << log_n2) - 1);
+            const u64 q = lcs[limb].q;
+            const Twiddle inv = inv_last[(size_t)last_id * kl + limb];
+            ulonglong2 x = in[((p * limbs_in + limb) << log_n2) + within];
+            ulonglong2 y = u[i];
+            ulonglong2 r;
+            r.x = mul_shoup(submod(x.x, y.x, q), inv.w, inv.wq, q);
+            r.y = mul_shoup(submod(x.y, y.y, q), inv.w, inv.wq, q);
+            if (addend)
+            {
+                ulonglong2 z = addend[i];
+                r.x = addmod(r.x, z.x, q);
+                r.y = addmod(r.y, z.y, q);
+            }
+            out[i] = r;
+        }
+
+        // in [P][limbs_in][n] -> out [P][limbs_in-1][n] (+= addend of the same shape when given)
+        void divide_round_last(Context *c, const u64 *in, long long P, int limbs_in, int last_id, const u64 *addend,
+                               u64 *out)
+        {
+            const size_t n = c->n;
+            const int targets = limbs_in - 1;
+            Scratch t(P * n * sizeof(u64), c->stream);
+            Scratch u((size_t)P * targets * n * sizeof(u64), c->stream);
+            MOAI_CUDA_CHECK(cudaMemcpy2DAsync(t.p, n * sizeof(u64), in + (size_t)targets * n,
+                                              (size_t)limbs_in * n * sizeof(u64), n * sizeof(u64), (size_t)P,
+                                              cudaMemcpyDeviceToDevice, c->stream));
+            ntt_inverse(c, t.as<u64>(), P, c->d_ids + last_id, 1);
+            const long long total2 = P * targets * (long long)(n / 2);
+            k_divround_expand<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
+                t.as<ulonglong2>(), u.as<ulonglong2>(), total2, c->log_n - 1, targets, last_id, c->kl, c->d_limb,
+                c->d_half_mod);
+            ntt_forward(c, u.as<u64>(), P * targets, c->d_ids, targets);
+            k_divround_finish<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
+                reinterpret_cast<const ulonglong2 *>(in), u.as<ulonglong2>(),
+                reinterpret_cast<const ulonglong2 *>(addend), reinterpret_cast<ulonglong2 *>(out), total2, c->log_n - 1,
+                targets, limbs_in, last_id, c->kl, c->d_limb, c->d_inv_last);
+            MOAI_CUDA_CHECK(cudaGetLastError());
+        }
+
+        // ------------------------------------------------------------------ mod raise
+        // d[P][n] (coefficients mod q0) -> out[P][limbs][n]: centred lift into every prime
+        __global__ void k_modraise_expand(const ulonglong2 *__restrict__ d, ulonglong2 *__restrict__ out,
+                                          long long total2, int log_n2, int limbs, const LimbConst *__restrict__ lcs)
+        {
+            long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= total2)
+            {
+                return;
+            }
+            const long long lp = i >> log_n2;
+            const int limb = (int)(lp % limbs);
+            const long long p = lp / limbs;
+            const long long within = i & (((long long)1 << log_n2) - 1);
+            const LimbConst lc = lcs[limb];
+            const u64 q0 = lcs[0].q, half = q0 >> 1;
+            const u64 corr = lc.q - lc.q0_mod; // -(q0) mod q_j
+            ulonglong2 v = d[(p << log_n2) + within], r;
+            r.x = reduce64(v.x, lc);
+            r.y = reduce64(v.y, lc);
+            if (v.x > half)
+            {
+                r.x = addmod(r.x, corr, lc.q);
+            }
+            if (v.y > half)
+            {
+                r.y = addmod(r.y, corr, lc.q);
+            }
+            out[i] = r;
+        }
+
+        // ------------------------------------------------------------------ Galois permutation
+        __global__ void k_galois(const u64 *__restrict__ in, u64 *__restrict__ out, long long total, int log_n,
+                                 const uint32_t *__restrict__ table)
+        {
+            long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= total)
+            {
+                return;
+            }
+            const long long within = i & (((long long)1 << log_n) - 1);
+            out[i] = in[i - within + table[within]];
+        }
+
+        // ------------------------------------------------------------------ key switch pieces
+        // ext[b][I][J][n] = d[b][J][n] mod m_I   (I over {q_0..q_{l-1}, p})
+        __global__ void k_ks_expand(const ulonglong2 *__restrict__ d, ulonglong2 *__restrict__ ext, long long total2,
+                                    int log_n2, int limbs, const int *__restrict__ ids_ks,
+                                    const LimbConst *__restrict__ lcs)
+        {
+            long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; // over [b][I][J][n/2]
+            if (i >= total2)
+            {
+                return;
+            }
+            const long long lp = i >> log_n2;
+            const int J = (int)(lp % limbs);
+            const long long bi = lp / limbs;
+            const int I = (int)(bi % (limbs + 1));
+            const long long b = bi / (limbs + 1);
+            const long long within = i & (((long long)1 << log_n2) - 1);
+            const LimbConst lc = lcs[ids_ks[I]];
+            ulonglong2 v = d[((b * limbs + J) << log_n2) + within];
+            ulonglong2 r;
+            r.x = reduce64(v.x, lc);
+            r.y = reduce64(v.y, lc);
+            ext[i] = r;
+        }
+
+        // acc[b][k][I][n] = sum_J ext[b][I][J][n] * ksk[J][k][ids_ks[I]][n] mod m_I
+        __global__ void k_ks_mac(const ulonglong2 *__restrict__ ext, const ulonglong2 *__restrict__ ksk,
+                                 ulonglong2 *__restrict__ acc, long long batch, int log_n2, int limbs, int kl,
+                                 const int *__restrict__ ids_ks, const LimbConst *__restrict__ lcs,
+                                 const Twiddle *__restrict__ two64)
+        {
+            // grid: x = n/2 / blockDim, y = I, z = batch chunk
+            const long long within = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            const int I = blockIdx.y;
+            const long long b = blockIdx.z;
+            const int key_limb = ids_ks[I];
+            const LimbConst lc = lcs[key_limb];
+            const Twiddle t64 = two64[key_limb];
+            const long long n2 = (long long)1 << log_n2;
+            const ulonglong2 *e = ext + ((b * (limbs + 1) + I) * limbs << log_n2) + within;
+            u128 a0x{ 0, 0 }, a0y{ 0, 0 }, a1x{ 0, 0 }, a1y{ 0, 0 };
+            for (int J = 0; J < limbs; J++)
+            {
+                const ulonglong2 v = e[(long long)J << log_n2];
+                const ulonglong2 k0 = __ldg(ksk + (((long long)J * 2 + 0) * kl + key_limb) * n2 + within);
+                const ulonglong2 k1 = __ldg(ksk + (((long long)J * 2 + 1) * kl + key_limb) * n2 + within);
+                mac_wide(a0x, v.x, k0.x);
+                mac_wide(a0y, v.y, k0.y);
+                mac_wide(a1x, v.x, k1.x);
+                mac_wide(a1y, v.y, k1.y);
+            }
+            ulonglong2 r0, r1;
+            r0.x = barrett_reduce_acc(a0x, lc, t64.w, t64.wq);
+            r0.y = barrett_reduce_acc(a0y, lc, t64.w, t64.wq);
+            r1.x = barrett_reduce_acc(a1x, lc, t64.w, t64.wq);
+            r1.y = barrett_reduce_acc(a1y, lc, t64.w, t64.wq);
+            acc[(((b * 2 + 0) * (limbs + 1) + I) << log_n2) + within] = r0;
+            acc[(((b * 2 + 1) * (limbs + 1) + I) << log_n2) + within] = r1;
+        }
+    } // namespace
+
+    // ====================================================================== launchers
+    void ew_addsub(Context *c, int op, const u64 *a, const u64 *b, u64 *out, long long batch, int polys, int limbs)
+    {
+        const long long total2 = batch * polys * limbs * (long long)(c->n / 2);
+        if (!total2)
+        {
+            return;
+        }
+        k_addsub<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
+            op, reinterpret_cast<const ulonglong2 *>(a), reinterpret_cast<const ulonglong2 *>(b),
+            reinterpret_cast<ulonglong2 *>(out), total2, c->log_n - 1, limbs, c->d_limb);
+        MOAI_CUDA_CHECK(cudaGetLastError());
+    }
+
+    void ew_addsub_plain(Context *c, int op, const u64 *ct, const u64 *pt, u64 *out, long long batch, int polys,
+                         int limbs, long long pt_stride)
+    {
+        const long long total2 = batch * polys * limbs * (long long)(c->n / 2);
+        if (!total2)
+        {
+            return;
+        }
+        k_addsub_plain<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
+            op, reinterpret_cast<const ulonglong2 *>(ct), reinterpret_cast<const ulonglong2 *>(pt),
+            reinterpret_cast<ulonglong2 *>(out), total2, c->log_n - 1, polys, limbs, pt_stride / 2, c->d_limb);
+        MOAI_CUDA_CHECK(cudaGetLastError());
+    }
+
+    void ew_multiply_plain(Context *c, const u64 *ct, const u64 *pt, u64 *out, long long batch, int polys, int limbs,
+                           long long pt_stride)
+    {
+        const long long total2 = batch * polys * limbs * (long long)(c->n / 2);
+        if (!total2)
+        {
+            return;
+        }
+        k_multiply_plain<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
+            reinterpret_cast<const ulonglong2 *>(ct), reinterpret_cast<const ulonglong2 *>(pt),
+            reinterpret_cast<ulonglong2 *>(out), total2, c->log_n - 1, polys, limbs, pt_stride / 2, c->d_limb);
+        MOAI_CUDA_CHECK(cudaGetLastError());
+    }
+
+    static void scalar_op(Context *c, int mode, const u64 *ct, const u64 *h_consts, u64 *out, long long batch,
+                          int polys, int limbs)
+    {
+        const long long total2 = batch * polys * limbs * (long long)(c->n / 2);
+        if (!total2)
+        {
+            return;
+        }
+        std::vector<Twiddle> h(limbs);
+        for (int l = 0; l < limbs; l++)
+        {
+            MOAI_REQUIRE(h_consts[l] < c->q[l], "scalar constant must be reduced");
+            h[l].w = h_consts[l];
+            h[l].wq = (u64)((((unsigned __int128)h_consts[l]) << 64) / c->q[l]);
+        }
+        Scratch d(limbs * sizeof(Twiddle), c->stream);
+        MOAI_CUDA_CHECK(cudaMemcpyAsync(d.p, h.data(), limbs * sizeof(Twiddle), cudaMemcpyHostToDevice, c->stream));
+        // h is pageable: the copy is staged before returning, so it may go out of scope
+        k_scalar<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(mode, reinterpret_cast<const ulonglong2 *>(ct),
+                                                                 d.as<Twiddle>(), reinterpret_cast<ulonglong2 *>(out),
+                                                                 total2, c->log_n - 1, polys, limbs, c->d_limb);
+        MOAI_CUDA_CHECK(cudaGetLastError());
+    }
+
+    void ew_multiply_scalar(Context *c, const u64 *ct, const u64 *h_consts, u64 *out, long long batch, int polys,
+                            int limbs)
+    {
+        scalar_op(c, 0, ct, h_consts, out, batch, polys, limbs);
+    }
+
+    void ew_add_scalar(Context *c, const u64 *ct, const u64 *h_consts, u64 *out, long long batch, int polys, int limbs)
+    {
+        scalar_op(c, 1, ct, h_consts, out, batch, polys, limbs);
+    }
+
+    void ew_multiply(Context *c, const u64 *a, const u64 *b, u64 *out3, long long batch, int limbs, bool accumulate)
+    {
+        const long long total2 = batch * limbs * (long long)(c->n / 2);
+        if (!total2)
+        {
+            return;
+        }
+        k_multiply<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
+            reinterpret_cast<const ulonglong2 *>(a), reinterpret_cast<const ulonglong2 *>(b),
+            reinterpret_cast<ulonglong2 *>(out3), total2, c->log_n - 1, limbs, c->d_limb, accumulate ? 1 : 0, 0);
+        MOAI_CUDA_CHECK(cudaGetLastError());
+    }
+
+    void ew_square(Context *c, const u64 *a, u64 *out3, long long batch, int limbs)
+    {
+        const long long total2 = batch * limbs * (long long)(c->n / 2);
+        if (!total2)
+        {
+            return;
+        }
+        k_multiply<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
+            reinterpret_cast<const ulonglong2 *>(a), reinterpret_cast<const ulonglong2 *>(a),
+            reinterpret_cast<ulonglong2 *>(out3), total2, c->log_n - 1, limbs, c->d_limb, 0, 1);
+        MOAI_CUDA_CHECK(cudaGetLastError());
+    }
+
+    void rescale(Context *c, const u64 *in, u64 *out, long long batch, int polys, int limbs)
+    {
+        MOAI_REQUIRE(limbs >= 2, "end of modulus switching chain reached");
+        divide_round_last(c, in, batch * polys, limbs, limbs - 1, nullptr, out);
+    }
+
+    void mod_switch_drop(Context *c, const u64 *in, u64 *out, long long batch, int polys, int limbs_in, int limbs_out)
+    {
+        MOAI_REQUIRE(limbs_out >= 1 && limbs_out <= limbs_in, "end of modulus switching chain reached");
+        const size_t n = c->n;
+        MOAI_CUDA_CHECK(cudaMemcpy2DAsync(out, (size_t)limbs_out * n * sizeof(u64), in,
+                                          (size_t)limbs_in * n * sizeof(u64), (size_t)limbs_out * n * sizeof(u64),
+                                          (size_t)(batch * polys), cudaMemcpyDeviceToDevice, c->stream));
+    }
+
+    void mod_raise(Context *c, const u64 *in, u64 *out, long long batch, int polys, int limbs_out)
+    {
+        const size_t n = c->n;
+        const long long P = batch * polys;
+        Scratch d(P * n * sizeof(u64), c->stream);
+        MOAI_CUDA_CHECK(cudaMemcpyAsync(d.p, in, P * n * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+        ntt_inverse(c, d.as<u64>(), P, c->d_ids, 1);
+        const long long total2 = P * limbs_out * (long long)(n / 2);
+        k_modraise_expand<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
+            d.as<ulonglong2>(), reinterpret_cast<ulonglong2 *>(out), total2, c->log_n - 1, limbs_out, c->d_limb);
+        MOAI_CUDA_CHECK(cudaGetLastError());
+        ntt_forward(c, out, P * limbs_out, c->d_ids, limbs_out);
+    }
+
+    void apply_galois_ntt(Context *c, const u64 *in, u64 *out, long long count_polys_limbs, uint32_t elt)
+    {
+        const uint32_t *table = c->galois_table(elt);
+        const long long total = count_polys_limbs * (long long)c->n;
+        if (!total)
+        {
+            return;
+        }
+        k_galois<<<grid_for(total), EW_THREADS, 0, c->stream>>>(in, out, total, c->log_n, table);
+        MOAI_CUDA_CHECK(cudaGetLastError());
+    }
+
+    void switch_key(Context *c, u64 *ct, const u64 *target, long long batch, int limbs, const u64 *ksk)
+    {
+        MOAI_REQUIRE(limbs >= 1 && limbs <= c->kl - 1, "limb count out of range");
+        const size_t n = c->n;
+        const int rns = limbs + 1;
+        const int *ids_ks = c->d_ids_ks + (size_t)limbs * (c->kl + 1);
+        // bound the extended-digit workspace (batch chunking); ~2 GiB
+        const size_t ext_per_ct = (size_t)rns * limbs * n * sizeof(u64);
+        long long chunk = (long long)(((size_t)2 << 30) / ext_per_ct);
+        chunk = chunk < 1 ? 1 : (chunk > batch ? batch : chunk);
+        Scratch d((size_t)chunk * limbs * n * sizeof(u64), c->stream);
+        Scratch ext((size_t)chunk * ext_per_ct, c->stream);
+        Scratch acc((size_t)chunk * 2 * rns * n * sizeof(u64), c->stream);
+        for (long long b0 = 0; b0 < batch; b0 += chunk)
+        {
+            const long long nb = (batch - b0) < chunk ? (batch - b0) : chunk;
+            const u64 *tg = target + (size_t)b0 * limbs * n;
+            u64 *ctb = ct + (size_t)b0 * 2 * limbs * n;
+            MOAI_CUDA_CHECK(cudaMemcpyAsync(d.p, tg, (size_t)nb * limbs * n * sizeof(u64), cudaMemcpyDeviceToDevice,
+                                            c->stream));
+            ntt_inverse(c, d.as<u64>(), nb * limbs, c->d_ids, limbs);
+            const long long total2 = nb * rns * limbs * (long long)(n / 2);
+            k_ks_expand<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(d.as<ulonglong2>(), ext.as<ulonglong2>(), total2,
+                                                                        c->log_n - 1, limbs, ids_ks, c->d_limb);
+            // NTT_I(d_I mod q_I) reproduces the target limb itself, so the I == J digits need no
+            // special case (S/evaluator.cpp:2831-2836 takes the NTT-form input there: same residues)
+            ntt_forward(c, ext.as<u64>(), nb * rns * limbs, ids_ks, rns, limbs);
+            dim3 grid((unsigned)((n / 2) / EW_THREADS), (unsigned)rns, (unsigned)nb);
+            k_ks_mac<<<grid, EW_THREADS, 0, c->stream>>>(ext.as<ulonglong2>(), reinterpret_cast<const ulonglong2 *>(ksk),
+                                                         acc.as<ulonglong2>(), nb, c->log_n - 1, limbs, c->kl, ids_ks,
+                                                         c->d_limb, c->d_two64);
+            MOAI_CUDA_CHECK(cudaGetLastError());
+            // mod-down by the special prime and add into the ciphertext (S/evaluator.cpp:2962-3018)
+            divide_round_last(c, acc.as<u64>(), nb * 2, rns, c->kl - 1, ctb, ctb);
+        }
+    }
+
+    void relinearize(Context *c, const u64 *in3, u64 *out2, long long batch, int limbs, const u64 *ksk)
+    {
+        const size_t n = c->n;
+        const size_t poly = (size_t)limbs * n;
+        // out2 <- (c0, c1) ; target <- c2
+        MOAI_CUDA_CHECK(cudaMemcpy2DAsync(out2, 2 * poly * sizeof(u64), in3, 3 * poly * sizeof(u64),
+                                          2 * poly * sizeof(u64), (size_t)batch, cudaMemcpyDeviceToDevice, c->stream));
+        Scratch tg((size_t)batch * poly * sizeof(u64), c->stream);
+        MOAI_CUDA_CHECK(cudaMemcpy2DAsync(tg.p, poly * sizeof(u64), in3 + 2 * poly, 3 * poly * sizeof(u64),
+                                          poly * sizeof(u64), (size_t)batch, cudaMemcpyDeviceToDevice, c->stream));
+        switch_key(c, out2, tg.as<u64>(), batch, limbs, ksk);
+    }
+
+    void apply_galois(Context *c, const u64 *in, u64 *out, long long batch, int limbs, uint32_t elt, const u64 *ksk)
+    {
+        const size_t n = c->n;
+        const size_t poly = (size_t)limbs * n;
+        MOAI_REQUIRE(in != out, "apply_galois is out of place");
+        // permute both polys into a scratch pair, then out = (sigma(c0), 0) + keyswitch(sigma(c1))
+        Scratch perm((size_t)batch * 2 * poly * sizeof(u64), c->stream);
+        apply_galois_ntt(c, in, perm.as<u64>(), batch * 2 * limbs, elt);
+        Scratch tg((size_t)batch * poly * sizeof(u64), c->stream);
+        MOAI_CUDA_CHECK(cudaMemcpy2DAsync(tg.p, poly * sizeof(u64), perm.as<u64>() + poly, 2 * poly * sizeof(u64),
+                                          poly * sizeof(u64), (size_t)batch, cudaMemcpyDeviceToDevice, c->stream));
+        MOAI_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)batch * 2 * poly * sizeof(u64), c->stream));
+        MOAI_CUDA_CHECK(cudaMemcpy2DAsync(out, 2 * poly * sizeof(u64), perm.p, 2 * poly * sizeof(u64),
+                                          poly * sizeof(u64), (size_t)batch, cudaMemcpyDeviceToDevice, c->stream));
+        switch_key(c, out, tg.as<u64>(), batch, limbs, ksk);
+    }
+} // namespace moai

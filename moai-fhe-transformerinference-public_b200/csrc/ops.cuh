@@ -1,0 +1,37 @@
+// Host-callable launchers of the evaluation kernels (all stream-ordered on Context::stream).
+// Buffers are device pointers in SEAL's layout: a batch of B ciphertexts is
+// [B][polys][limbs][n] uint64, a plaintext [limbs][n].
+#pragma once
+#include "context.hpp"
+
+namespace moai
+{
+    enum EwOp
+    {
+        EW_ADD = 0,
+        EW_SUB = 1,
+        EW_NEG = 2,
+    };
+
+    void ew_addsub(Context *c, int op, const u64 *a, const u64 *b, u64 *out, long long batch, int polys, int limbs);
+    // ct (+/-) pt on poly 0; pt_stride = elements between the plaintexts of consecutive batch items (0 = broadcast)
+    void ew_addsub_plain(Context *c, int op, const u64 *ct, const u64 *pt, u64 *out, long long batch, int polys,
+                         int limbs, long long pt_stride);
+    void ew_multiply_plain(Context *c, const u64 *ct, const u64 *pt, u64 *out, long long batch, int polys, int limbs,
+                           long long pt_stride);
+    // per-limb scalar constants: out = ct * k[l]  (scalar-encoded plaintext, S/ckks.cpp:131-153)
+    void ew_multiply_scalar(Context *c, const u64 *ct, const u64 *h_consts, u64 *out, long long batch, int polys,
+                            int limbs);
+    void ew_add_scalar(Context *c, const u64 *ct, const u64 *h_consts, u64 *out, long long batch, int polys, int limbs);
+    void ew_multiply(Context *c, const u64 *a, const u64 *b, u64 *out3, long long batch, int limbs, bool accumulate);
+    void ew_square(Context *c, const u64 *a, u64 *out3, long long batch, int limbs);
+
+    void rescale(Context *c, const u64 *in, u64 *out, long long batch, int polys, int limbs);
+    void mod_switch_drop(Context *c, const u64 *in, u64 *out, long long batch, int polys, int limbs_in, int limbs_out);
+    void mod_raise(Context *c, const u64 *in, u64 *out, long long batch, int polys, int limbs_out);
+
+    void apply_galois_ntt(Context *c, const u64 *in, u64 *out, long long count_polys_limbs, uint32_t elt);
+    void switch_key(Context *c, u64 *ct, const u64 *target, long long batch, int limbs, const u64 *ksk);
+    void relinearize(Context *c, const u64 *in3, u64 *out2, long long batch, int limbs, const u64 *ksk);
+    void apply_galois(Context *c, const u64 *in, u64 *out, long long batch, int limbs, uint32_t elt, const u64 *ksk);
+} // namespace moai

@@ -31,3 +31,30 @@ def sealref_small():
     r.make_relin_key()
     r.make_galois_keys([1, 2, 4, -1, 256], conjugate=True)
     return r
+
+
+def load_pkg():
+    """The product package (its directory name is not a valid identifier, hence importlib)."""
+    import importlib
+    return importlib.import_module("moai-fhe-transformerinference-public_b200")
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    return load_pkg()
+
+
+@pytest.fixture(scope="session")
+def backend_small(pkg, oracle_small):
+    return pkg.Backend(SMALL_LOGN, oracle_small.q)
+
+
+@pytest.fixture(scope="session")
+def oracle_moai():
+    from oracle import Oracle, MOAI_BITS
+    return Oracle(16, MOAI_BITS)
+
+
+@pytest.fixture(scope="session")
+def backend_moai(pkg, oracle_moai):
+    return pkg.Backend(16, oracle_moai.q)

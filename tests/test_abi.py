@@ -1,0 +1,44 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/*.h declares, and fails loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+
+import pytest
+
+from conftest import load_pkg, ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    pkg = load_pkg()
+    lib = pkg.load_library()
+    names = pkg.exported_symbols()
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.moai_version() >= 100
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    pkg = load_pkg()
+    lib = pkg.load_library()
+    primes = (C.c_uint64 * 2)(1099511480321, 1099511390209)
+    h = C.c_void_p()
+    rc = lib.moai_context_create(C.c_int32(12), primes, C.c_int32(2), C.c_int32(0), C.byref(h))
+    assert rc == 3  # MOAI_CUDA_ERROR
+    assert b"no CPU fallback" in lib.moai_last_error()
+    with pytest.raises(RuntimeError):
+        pkg.Backend(12, [1099511480321, 1099511390209])
+
+
+def test_product_never_imports_oracle():
+    """The product package and its CUDA sources must not reference oracle/ (③)."""
+    pkg_dir = os.path.join(ROOT, "moai-fhe-transformerinference-public_b200")
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+                assert "ckks_oracle" not in text and "libsealref" not in text, f
