@@ -49,6 +49,13 @@ int32_t moai_context_destroy(moai_context *ctx);
 int32_t moai_set_stream(moai_context *ctx, void *cuda_stream);
 int32_t moai_synchronize(moai_context *ctx);
 
+/* ---- measurement hooks used by bench.py ----------------------------------------------------
+ * profile: when enabled, named device phases (e.g. "ctpt_gemm") are bracketed by CUDA events on
+ * the launching stream and their elapsed ms accumulated; launch_count: kernels launched so far. */
+int32_t moai_profile_enable(moai_context *ctx, int32_t on);
+int32_t moai_profile_get(moai_context *ctx, const char *name, double *ms, int64_t *count);
+int32_t moai_launch_count(moai_context *ctx, uint64_t *count);
+
 /* ---- device memory (plumbing for hosts without their own allocator) ------------------------ */
 int32_t moai_malloc(moai_context *ctx, uint64_t bytes, void **out);
 int32_t moai_free(moai_context *ctx, void *ptr);

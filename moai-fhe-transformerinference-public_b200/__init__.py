@@ -107,6 +107,19 @@ class Backend:
         s = self.torch.cuda.current_stream(self.device).cuda_stream
         self._chk(self.lib.moai_set_stream(self.h, C.c_void_p(s)))
 
+    def profile(self, on):
+        self._chk(self.lib.moai_profile_enable(self.h, C.c_int32(int(on))))
+
+    def profile_get(self, name):
+        ms, cnt = C.c_double(), C.c_int64()
+        self._chk(self.lib.moai_profile_get(self.h, name.encode(), C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
+
+    def launch_count(self):
+        v = C.c_uint64()
+        self._chk(self.lib.moai_launch_count(self.h, C.byref(v)))
+        return v.value
+
     def synchronize(self):
         self._chk(self.lib.moai_synchronize(self.h))
 
@@ -279,3 +292,20 @@ class Backend:
         self._chk(self.lib.moai_add_scalar(self.h, _ptr(a), k.ctypes.data_as(_u64p), _ptr(out), C.c_int64(bt),
                                            C.c_int32(p), C.c_int32(l)))
         return out
+
+    # ---- fused modules (B1/B2)
+    def ct_pt_matrix_mul_wo_pre(self, enc_X, W, scale, out=None):
+        """ct_pt_matrix_mul_wo_pre / _wo_pre_large (M/source/matrix_mul/Ct_pt_matrix_mul.hpp:4-101).
+        enc_X: [K, 2, limbs, n] device tensor; W: K x C float64 (host).  Returns [C, 2, limbs-1, n]."""
+        K, p, l, n = enc_X.shape
+        W = np.ascontiguousarray(W, dtype=np.float64)
+        if W.shape[0] != K:
+            raise MoaiError(1, "bad dimensions of X or W")
+        Cc = W.shape[1]
+        out = self.empty(Cc, 2, l - 1, n) if out is None else out
+        self._chk(self.lib.moai_ct_pt_matrix_mul_wo_pre(
+            self.h, _ptr(enc_X), W.ctypes.data_as(C.POINTER(C.c_double)), C.c_int32(K), C.c_int32(Cc), C.c_int32(K),
+            C.c_int32(l), C.c_double(scale), _ptr(out)))
+        return out
+
+    ct_pt_matrix_mul_wo_pre_large = ct_pt_matrix_mul_wo_pre

@@ -1,6 +1,7 @@
 // C ABI of libmoai_b200.so (declared in include/moai_b200.h).  Thin: argument checks with the
 // reference's error semantics, then the stream-ordered launchers of ops.cuh / ntt.cuh.
 #include "../../include/moai_b200.h"
+#include "../../include/moai_b200_modules.h"
 #include "ntt.cuh"
 #include "ops.cuh"
 #include <cmath>
@@ -101,6 +102,37 @@ extern "C"
     {
         API_BEGIN
         MOAI_CUDA_CHECK(cudaStreamSynchronize(get(ctx)->stream));
+        API_END
+    }
+
+    int32_t moai_profile_enable(moai_context *ctx, int32_t on)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        c->profiling = on != 0;
+        if (on)
+        {
+            c->prof.clear();
+        }
+        API_END
+    }
+
+    int32_t moai_profile_get(moai_context *ctx, const char *name, double *ms, int64_t *count)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(name && ms && count, "null argument");
+        auto it = c->prof.find(name);
+        *ms = it == c->prof.end() ? 0.0 : it->second.first;
+        *count = it == c->prof.end() ? 0 : it->second.second;
+        API_END
+    }
+
+    int32_t moai_launch_count(moai_context *ctx, uint64_t *count)
+    {
+        API_BEGIN
+        MOAI_REQUIRE(count, "null argument");
+        *count = get(ctx)->launches;
         API_END
     }
 
@@ -415,6 +447,18 @@ extern "C"
         Context *c = get(ctx);
         check_shape(c, batch, size, limbs_out);
         mod_raise(c, CU(in), U(out), batch, size, limbs_out);
+        API_END
+    }
+
+    int32_t moai_ct_pt_matrix_mul_wo_pre(moai_context *ctx, const uint64_t *enc_X, const double *W, int32_t col_X,
+                                         int32_t col_W, int32_t row_W, int32_t limbs, double scale, uint64_t *out)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        // "ERROR: bad dimensions of X or W" (Ct_pt_matrix_mul.hpp:11-14)
+        MOAI_REQUIRE(col_X == row_W, "bad dimensions of X or W");
+        MOAI_REQUIRE(enc_X && W && out, "null argument");
+        ct_pt_matmul_scalar(c, CU(enc_X), W, row_W, col_W, limbs, scale, U(out));
         API_END
     }
 }

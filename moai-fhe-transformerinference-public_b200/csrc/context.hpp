@@ -89,6 +89,11 @@ namespace moai
 
         std::vector<LimbConst> h_limb;
 
+        // bookkeeping for bench.py: kernels launched, and (when profiling) per-phase device time
+        unsigned long long launches = 0;
+        bool profiling = false;
+        std::map<std::string, std::pair<double, long long>> prof; // name -> (ms, count)
+
         std::mutex galois_mu;
         std::map<uint32_t, uint32_t *> galois_tables; // elt -> device [n]
 
@@ -98,6 +103,39 @@ namespace moai
     };
 
     Context *context_create(int log_n, const u64 *primes, int kl, int device);
+
+    // RAII device timer around a kernel (only active when Context::profiling is set): records
+    // CUDA events on the launching stream and accumulates the elapsed time under `name`.
+    struct PhaseTimer
+    {
+        Context *c;
+        const char *name;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        PhaseTimer(Context *ctx, const char *nm) : c(ctx), name(nm)
+        {
+            if (c->profiling)
+            {
+                cudaEventCreate(&e0);
+                cudaEventCreate(&e1);
+                cudaEventRecord(e0, c->stream);
+            }
+        }
+        ~PhaseTimer()
+        {
+            if (e0)
+            {
+                cudaEventRecord(e1, c->stream);
+                cudaEventSynchronize(e1);
+                float ms = 0;
+                cudaEventElapsedTime(&ms, e0, e1);
+                auto &slot = c->prof[name];
+                slot.first += ms;
+                slot.second += 1;
+                cudaEventDestroy(e0);
+                cudaEventDestroy(e1);
+            }
+        }
+    };
 
     // stream-ordered scratch allocation
     struct Scratch

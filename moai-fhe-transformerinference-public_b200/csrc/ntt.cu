@@ -335,6 +335,7 @@ namespace moai
         case 16: launch_fwd<8>(a, c->stream); break;
         default: throw StatusError{ INVALID_ARGUMENT, "unsupported log_n" };
         }
+        c->launches += 2;
         MOAI_CUDA_CHECK(cudaGetLastError());
     }
 
@@ -354,6 +355,7 @@ namespace moai
         case 16: launch_inv<8>(a, c->stream); break;
         default: throw StatusError{ INVALID_ARGUMENT, "unsupported log_n" };
         }
+        c->launches += 2;
         MOAI_CUDA_CHECK(cudaGetLastError());
     }
 } // namespace moai

@@ -268,11 +268,13 @@ namespace moai
             k_divround_expand<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
                 t.as<ulonglong2>(), u.as<ulonglong2>(), total2, c->log_n - 1, targets, last_id, c->kl, c->d_limb,
                 c->d_half_mod);
+        c->launches += 1;
             ntt_forward(c, u.as<u64>(), P * targets, c->d_ids, targets);
             k_divround_finish<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
                 reinterpret_cast<const ulonglong2 *>(in), u.as<ulonglong2>(),
                 reinterpret_cast<const ulonglong2 *>(addend), reinterpret_cast<ulonglong2 *>(out), total2, c->log_n - 1,
                 targets, limbs_in, last_id, c->kl, c->d_limb, c->d_inv_last);
+        c->launches += 1;
             MOAI_CUDA_CHECK(cudaGetLastError());
         }
 
@@ -392,6 +394,7 @@ namespace moai
         k_addsub<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
             op, reinterpret_cast<const ulonglong2 *>(a), reinterpret_cast<const ulonglong2 *>(b),
             reinterpret_cast<ulonglong2 *>(out), total2, c->log_n - 1, limbs, c->d_limb);
+        c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
     }
 
@@ -406,6 +409,7 @@ namespace moai
         k_addsub_plain<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
             op, reinterpret_cast<const ulonglong2 *>(ct), reinterpret_cast<const ulonglong2 *>(pt),
             reinterpret_cast<ulonglong2 *>(out), total2, c->log_n - 1, polys, limbs, pt_stride / 2, c->d_limb);
+        c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
     }
 
@@ -420,6 +424,7 @@ namespace moai
         k_multiply_plain<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
             reinterpret_cast<const ulonglong2 *>(ct), reinterpret_cast<const ulonglong2 *>(pt),
             reinterpret_cast<ulonglong2 *>(out), total2, c->log_n - 1, polys, limbs, pt_stride / 2, c->d_limb);
+        c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
     }
 
@@ -444,6 +449,7 @@ namespace moai
         k_scalar<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(mode, reinterpret_cast<const ulonglong2 *>(ct),
                                                                  d.as<Twiddle>(), reinterpret_cast<ulonglong2 *>(out),
                                                                  total2, c->log_n - 1, polys, limbs, c->d_limb);
+        c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
     }
 
@@ -468,6 +474,7 @@ namespace moai
         k_multiply<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
             reinterpret_cast<const ulonglong2 *>(a), reinterpret_cast<const ulonglong2 *>(b),
             reinterpret_cast<ulonglong2 *>(out3), total2, c->log_n - 1, limbs, c->d_limb, accumulate ? 1 : 0, 0);
+        c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
     }
 
@@ -481,6 +488,7 @@ namespace moai
         k_multiply<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
             reinterpret_cast<const ulonglong2 *>(a), reinterpret_cast<const ulonglong2 *>(a),
             reinterpret_cast<ulonglong2 *>(out3), total2, c->log_n - 1, limbs, c->d_limb, 0, 1);
+        c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
     }
 
@@ -509,6 +517,7 @@ namespace moai
         const long long total2 = P * limbs_out * (long long)(n / 2);
         k_modraise_expand<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
             d.as<ulonglong2>(), reinterpret_cast<ulonglong2 *>(out), total2, c->log_n - 1, limbs_out, c->d_limb);
+        c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
         ntt_forward(c, out, P * limbs_out, c->d_ids, limbs_out);
     }
@@ -522,6 +531,7 @@ namespace moai
             return;
         }
         k_galois<<<grid_for(total), EW_THREADS, 0, c->stream>>>(in, out, total, c->log_n, table);
+        c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
     }
 
@@ -549,6 +559,7 @@ namespace moai
             const long long total2 = nb * rns * limbs * (long long)(n / 2);
             k_ks_expand<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(d.as<ulonglong2>(), ext.as<ulonglong2>(), total2,
                                                                         c->log_n - 1, limbs, ids_ks, c->d_limb);
+        c->launches += 1;
             // NTT_I(d_I mod q_I) reproduces the target limb itself, so the I == J digits need no
             // special case (S/evaluator.cpp:2831-2836 takes the NTT-form input there: same residues)
             ntt_forward(c, ext.as<u64>(), nb * rns * limbs, ids_ks, rns, limbs);
@@ -556,6 +567,7 @@ namespace moai
             k_ks_mac<<<grid, EW_THREADS, 0, c->stream>>>(ext.as<ulonglong2>(), reinterpret_cast<const ulonglong2 *>(ksk),
                                                          acc.as<ulonglong2>(), nb, c->log_n - 1, limbs, c->kl, ids_ks,
                                                          c->d_limb, c->d_two64);
+        c->launches += 1;
             MOAI_CUDA_CHECK(cudaGetLastError());
             // mod-down by the special prime and add into the ciphertext (S/evaluator.cpp:2962-3018)
             divide_round_last(c, acc.as<u64>(), nb * 2, rns, c->kl - 1, ctb, ctb);

@@ -34,4 +34,8 @@ namespace moai
     void switch_key(Context *c, u64 *ct, const u64 *target, long long batch, int limbs, const u64 *ksk);
     void relinearize(Context *c, const u64 *in3, u64 *out2, long long batch, int limbs, const u64 *ksk);
     void apply_galois(Context *c, const u64 *in, u64 *out, long long batch, int limbs, uint32_t elt, const u64 *ksk);
+
+    // fused module: out[C][2][limbs-1][n] = rescale(sum_j X[j] * encode_scalar(W[j][i]))
+    void ct_pt_matmul_scalar(Context *c, const u64 *X, const double *h_W, int K, int C, int limbs, double scale,
+                             u64 *out);
 } // namespace moai

@@ -21,7 +21,6 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ORACLE_SO = os.path.join(_HERE, "libckks_oracle.so")
 _REF_SO = os.path.join(_HERE, "_ref", "libsealref.so")
-_REF_MODULES_SO = os.path.join(_HERE, "_ref", "libmoairef.so")
 REFERENCE_ROOT = "/root/reference"
 
 u64p = C.POINTER(C.c_uint64)
@@ -47,7 +46,8 @@ def build_ref(force=False):
     """Compile the reference's SEAL-4.1-bs into oracle/_ref (only where /root/reference exists)."""
     if not os.path.isdir(REFERENCE_ROOT):
         return _REF_SO if os.path.exists(_REF_SO) else None
-    if force or not os.path.exists(_REF_SO) or not os.path.exists(_REF_MODULES_SO):
+    wrap = os.path.join(_HERE, "refbuild", "ref_wrap.cpp")
+    if force or not os.path.exists(_REF_SO) or os.path.getmtime(_REF_SO) < os.path.getmtime(wrap):
         subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(_HERE, "refbuild")])
     return _REF_SO
 
@@ -416,3 +416,20 @@ class SealRef:
                                     bb, C.c_int(size_b), C.c_int(limbs_b), C.c_double(scale_b), C.c_int(iarg),
                                     C.c_double(darg), vv, _p(out), C.byref(osz), C.byref(olm), C.byref(osc)))
         return out[: osz.value * olm.value * self.n].copy(), osz.value, olm.value, osc.value
+
+    def omp_threads(self):
+        return int(self.lib.ref_omp_threads())
+
+    def ct_pt_matmul(self, variant, X, W, mask, K, Cc, limbs, scale):
+        """The reference's ct_pt_matrix_mul_* (M/source/matrix_mul/Ct_pt_matrix_mul.hpp) on raw buffers.
+        Returns (out, seconds)."""
+        W = np.ascontiguousarray(W, dtype=np.float64)
+        out = np.zeros(Cc * 2 * (limbs - 1) * self.n, dtype=np.uint64)
+        sec = C.c_double(0)
+        m = None
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.int32)
+            m = _p(mask, i32p)
+        self._chk(self.lib.ref_ct_pt_matmul(self.h, C.c_int(variant), _p(X), _p(W, f64p), m, C.c_int(K), C.c_int(Cc),
+                                            C.c_int(limbs), C.c_double(scale), _p(out), C.byref(sec)))
+        return out, sec.value

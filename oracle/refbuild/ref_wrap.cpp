@@ -18,6 +18,10 @@
 #include <string>
 #include <chrono>
 #include <omp.h>
+#include <iostream>
+
+// The reference's own module code, unmodified (M/source/matrix_mul/Ct_pt_matrix_mul.hpp).
+#include "source/matrix_mul/Ct_pt_matrix_mul.hpp"
 
 using namespace seal;
 using namespace std;
@@ -510,6 +514,102 @@ extern "C"
         *out_size = int(res.size());
         *out_limbs = int(res.coeff_modulus_size());
         *out_scale = res.scale();
+        REF_CATCH(r)
+    }
+
+    // ---- MOAI module level: the reference's ct-pt matmuls ----------------
+    // variant 0: ct_pt_matrix_mul_wo_pre          (Ct_pt_matrix_mul.hpp:4-49)
+    // variant 1: ct_pt_matrix_mul_wo_pre_large    (:51-101, col_W must be a multiple of 128)
+    // variant 2: ct_pt_matrix_mul_wo_pre_w_mask   (:103-170, col_W must be a multiple of 128)
+    // variant 3: the loop body of variant 2 (:124-165) over an arbitrary number of columns, one
+    //            column per OpenMP iteration — used to time a bounded sample on small hosts.
+    // X: [K][2][limbs][n]; W row-major K x C; mask: n/2 ints (variants 2, 3); out [C][2][limbs-1][n].
+    int ref_ct_pt_matmul(void *h, int variant, const uint64_t *X, const double *W, const int *mask, int K, int C,
+                         int limbs, double scale, uint64_t *out, double *seconds)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        size_t ctsz = size_t(2) * limbs * r->n;
+        vector<Ciphertext> enc_X(K);
+        for (int j = 0; j < K; j++)
+        {
+            load_ct(*r, X + size_t(j) * ctsz, 2, limbs, scale, enc_X[j]);
+        }
+        vector<vector<double>> Wm(K, vector<double>(C));
+        for (int j = 0; j < K; j++)
+        {
+            for (int i = 0; i < C; i++)
+            {
+                Wm[j][i] = W[size_t(j) * C + i];
+            }
+        }
+        vector<int> bias_vec;
+        if (mask)
+        {
+            bias_vec.assign(mask, mask + r->n / 2);
+        }
+        vector<Ciphertext> res;
+        auto t0 = chrono::steady_clock::now();
+        if (variant == 0)
+        {
+            res = ct_pt_matrix_mul_wo_pre(enc_X, Wm, K, C, K, *r->ctx);
+        }
+        else if (variant == 1)
+        {
+            res = ct_pt_matrix_mul_wo_pre_large(enc_X, Wm, K, C, K, *r->ctx);
+        }
+        else if (variant == 2)
+        {
+            res = ct_pt_matrix_mul_wo_pre_w_mask(enc_X, Wm, bias_vec, K, C, K, *r->ctx);
+        }
+        else
+        {
+            res.resize(C);
+            size_t slot_count = r->encoder->slot_count();
+#pragma omp parallel for schedule(dynamic)
+            for (int i = 0; i < C; i++)
+            {
+                for (int j = 0; j < K; j++)
+                {
+                    vector<double> tempw(slot_count, 0);
+                    for (size_t kk = 0; kk < slot_count; ++kk)
+                    {
+                        if (bias_vec[kk] == 1)
+                        {
+                            tempw[kk] = Wm[j][i];
+                        }
+                    }
+                    Plaintext ecd;
+                    r->encoder->encode(tempw, enc_X[j].parms_id(), enc_X[j].scale(), ecd);
+                    if (j == 0)
+                    {
+                        r->evaluator->multiply_plain(enc_X[0], ecd, res[i]);
+                    }
+                    else
+                    {
+                        Ciphertext tempx;
+                        r->evaluator->multiply_plain(enc_X[j], ecd, tempx);
+                        r->evaluator->add_inplace(res[i], tempx);
+                    }
+                }
+                r->evaluator->rescale_to_next_inplace(res[i]);
+                res[i].scale() = scale;
+            }
+        }
+        auto t1 = chrono::steady_clock::now();
+        if (seconds)
+        {
+            *seconds = chrono::duration<double>(t1 - t0).count();
+        }
+        size_t outsz = size_t(2) * (limbs - 1) * r->n;
+        for (int i = 0; i < C; i++)
+        {
+            if (res[i].size() != 2 || res[i].coeff_modulus_size() != size_t(limbs - 1))
+            {
+                throw logic_error("unexpected output shape");
+            }
+            memcpy(out + size_t(i) * outsz, res[i].data(), outsz * sizeof(uint64_t));
+        }
         REF_CATCH(r)
     }
 

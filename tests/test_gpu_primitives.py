@@ -238,7 +238,7 @@ def test_rotate_semantics_with_real_keys(pkg, backend_small, oracle_small):
     ct = o.encrypt_sym(sk, 1, o.encode(z, scale, limbs), limbs)
     dct = pkg.to_device(ct.reshape(1, 2, limbs, o.n))
     keys = {}
-    for i, s in enumerate((1, 2, 4, 8, 0)):
+    for i, s in enumerate((1, -1, 2, 4, 8, 0)):
         e = o.elt_from_step(s)
         keys[e] = pkg.to_device(o.gen_galois_key(sk, 100 + i, e))
     rlk = pkg.to_device(o.gen_relin_key(sk, 7))
