@@ -128,6 +128,12 @@ int32_t moai_multiply_scalar(moai_context *ctx, const uint64_t *ct, const uint64
 int32_t moai_add_scalar(moai_context *ctx, const uint64_t *ct, const uint64_t *host_consts, uint64_t *out,
                         int64_t batch, int32_t size, int32_t limbs);
 
+/* ---- A12: CKKSEncoder::encode(vector<complex<double>>) (S/ckks.h:457-638), batched ---------
+ * values: DEVICE [count][n_vals] complex numbers (interleaved re, im), n_vals <= N/2 (remaining
+ * slots are zero); out: [count][limbs][N] NTT form.  Bit-identical to SEAL (same FFT order).    */
+int32_t moai_encode_vector(moai_context *ctx, const double *values, int64_t count, int32_t n_vals, double scale,
+                           int32_t limbs, uint64_t *out);
+
 /* ---- C1: Bootstrapper::modraise_inplace (M/source/bootstrapping/Bootstrapper.cpp:2938-2992) -
  * in [batch][size][1][N] (limb q0) -> out [batch][size][limbs_out][N]                           */
 int32_t moai_mod_raise(moai_context *ctx, const uint64_t *in, uint64_t *out, int64_t batch, int32_t size,

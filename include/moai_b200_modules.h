@@ -22,6 +22,14 @@ extern "C" {
 int32_t moai_ct_pt_matrix_mul_wo_pre(moai_context *ctx, const uint64_t *enc_X, const double *W, int32_t col_X,
                                      int32_t col_W, int32_t row_W, int32_t limbs, double scale, uint64_t *out);
 
+/* B3: ct_pt_matrix_mul_wo_pre_w_mask (M/source/matrix_mul/Ct_pt_matrix_mul.hpp:103-170):
+ * the plaintext of weight w is encode(w * mask) with mask = bias_vec (HOST, N/2 ints, 1 = valid
+ * token slot).  An all-ones mask takes the scalar path above (bit-identical); any other mask is
+ * evaluated exactly: one device FFT + `limbs` NTTs per weight.                                   */
+int32_t moai_ct_pt_matrix_mul_wo_pre_w_mask(moai_context *ctx, const uint64_t *enc_X, const double *W,
+                                            const int32_t *bias_vec, int32_t col_X, int32_t col_W, int32_t row_W,
+                                            int32_t limbs, double scale, uint64_t *out);
+
 #ifdef __cplusplus
 }
 #endif

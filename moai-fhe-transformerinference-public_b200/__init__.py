@@ -309,3 +309,32 @@ class Backend:
         return out
 
     ct_pt_matrix_mul_wo_pre_large = ct_pt_matrix_mul_wo_pre
+
+    def ct_pt_matrix_mul_wo_pre_w_mask(self, enc_X, W, bias_vec, scale, out=None):
+        """ct_pt_matrix_mul_wo_pre_w_mask (M/source/matrix_mul/Ct_pt_matrix_mul.hpp:103-170)."""
+        K, p, l, n = enc_X.shape
+        W = np.ascontiguousarray(W, dtype=np.float64)
+        mask = np.ascontiguousarray(bias_vec, dtype=np.int32)
+        if W.shape[0] != K or mask.size != n // 2:
+            raise MoaiError(1, "bad dimensions of X or W")
+        Cc = W.shape[1]
+        out = self.empty(Cc, 2, l - 1, n) if out is None else out
+        self._chk(self.lib.moai_ct_pt_matrix_mul_wo_pre_w_mask(
+            self.h, _ptr(enc_X), W.ctypes.data_as(C.POINTER(C.c_double)), mask.ctypes.data_as(C.POINTER(C.c_int32)),
+            C.c_int32(K), C.c_int32(Cc), C.c_int32(K), C.c_int32(l), C.c_double(scale), _ptr(out)))
+        return out
+
+    # ---- vector encoder (A12)
+    def encode(self, values, scale, limbs):
+        """CKKSEncoder::encode for a batch: values [count, n_vals] (or [n_vals]) real/complex ->
+        device plaintexts [count, limbs, n] (or [limbs, n])."""
+        v = np.asarray(values)
+        single = v.ndim == 1
+        v = np.atleast_2d(v).astype(np.complex128)
+        count, n_vals = v.shape
+        ri = np.ascontiguousarray(np.stack([v.real, v.imag], axis=-1))
+        d = self.torch.from_numpy(ri).to(self.device)
+        out = self.empty(count, limbs, self.n)
+        self._chk(self.lib.moai_encode_vector(self.h, _ptr(d), C.c_int64(count), C.c_int32(n_vals), C.c_double(scale),
+                                              C.c_int32(limbs), _ptr(out)))
+        return out[0] if single else out

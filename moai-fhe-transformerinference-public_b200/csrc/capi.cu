@@ -461,4 +461,40 @@ extern "C"
         ct_pt_matmul_scalar(c, CU(enc_X), W, row_W, col_W, limbs, scale, U(out));
         API_END
     }
+
+    int32_t moai_ct_pt_matrix_mul_wo_pre_w_mask(moai_context *ctx, const uint64_t *enc_X, const double *W,
+                                                const int32_t *bias_vec, int32_t col_X, int32_t col_W, int32_t row_W,
+                                                int32_t limbs, double scale, uint64_t *out)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(col_X == row_W, "bad dimensions of X or W");
+        MOAI_REQUIRE(enc_X && W && bias_vec && out, "null argument");
+        bool all_ones = true;
+        for (size_t s = 0; s < c->n / 2 && all_ones; s++)
+        {
+            all_ones = bias_vec[s] == 1;
+        }
+        if (all_ones)
+        {
+            // encode(vector of a constant) == encode(scalar) exactly
+            ct_pt_matmul_scalar(c, CU(enc_X), W, row_W, col_W, limbs, scale, U(out));
+        }
+        else
+        {
+            ct_pt_matmul_masked(c, CU(enc_X), W, reinterpret_cast<const int *>(bias_vec), row_W, col_W, limbs, scale,
+                                U(out));
+        }
+        API_END
+    }
+
+    int32_t moai_encode_vector(moai_context *ctx, const double *values, int64_t count, int32_t n_vals, double scale,
+                               int32_t limbs, uint64_t *out)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(limbs >= 1 && limbs <= c->kl && out, "bad arguments");
+        encode_vector(c, values, count, n_vals, scale, limbs, U(out));
+        API_END
+    }
 }

@@ -28,7 +28,7 @@ namespace moai
 
         // Wc[l][j][i] = residue of round(W[j][i] * scale) mod q_l (sign-magnitude like SEAL)
         __global__ void k_encode_weights(const double *__restrict__ W, u64 *__restrict__ Wc, long long kc, int limbs,
-                                         double scale, const LimbConst *__restrict__ lcs)
+                                         double scale, const LimbConst *__restrict__ lcs, int split26)
         {
             long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
             if (i >= kc)
@@ -42,7 +42,9 @@ namespace moai
             {
                 const LimbConst lc = lcs[l];
                 u64 r = reduce64(mag, lc);
-                Wc[(long long)l * kc + i] = neg ? negmod(r, lc.q) : r;
+                r = neg ? negmod(r, lc.q) : r;
+                // split26: low 26 bits in the low word, the rest in the high word (see k_ctpt_gemm26)
+                Wc[(long long)l * kc + i] = split26 ? (((r >> 26) << 32) | (r & 0x3FFFFFFull)) : r;
             }
         }
 
@@ -114,6 +116,125 @@ namespace moai
                 }
             }
         }
+
+        // Same GEMM for primes below 2^52 (all data primes of the repo's chain are <= 51 bits).
+        // Residues are split at 26 bits: x = x1 * 2^26 + x0, w = w1 * 2^26 + w0 (the weights arrive
+        // pre-split, one half per 32-bit word).  The three columns
+        //      c0 += x0 w0,   c1 += x0 w1 + x1 w0,   c2 += x1 w1
+        // are plain 64-bit accumulators: every product is < 2^52, so up to 1024 terms fit without a
+        // carry chain.  One MAC = exactly four IMAD.WIDE.U32 with accumulate and nothing else —
+        // the integer pipe's minimum for a 52x52-bit product; the carries are paid once per 1024 j.
+        constexpr int MM_FOLD = 1024;
+        __global__ void __launch_bounds__(MM_THREADS)
+            k_ctpt_gemm26(const ulonglong2 *__restrict__ X, const u64 *__restrict__ Wc, ulonglong2 *__restrict__ Y,
+                          int K, int C, int limbs, int log_n2, const LimbConst *__restrict__ lcs,
+                          const Twiddle *__restrict__ two64)
+        {
+            __shared__ u64 ws[MM_KC * MM_TN];
+            const int tiles_i = (C + MM_TN - 1) / MM_TN;
+            const int tiles_t = (1 << log_n2) / MM_THREADS;
+            const int tile_i = blockIdx.x % tiles_i;
+            const int rest = blockIdx.x / tiles_i;
+            const int tile_t = rest % tiles_t;
+            const int pl = rest / tiles_t; // p * limbs + l
+            const int l = pl % limbs;
+            const LimbConst lc = lcs[l];
+            const Twiddle t64 = two64[l];
+            const long long ct_stride2 = (long long)2 * limbs << log_n2;
+            const long long off = ((long long)pl << log_n2) + (long long)tile_t * MM_THREADS + threadIdx.x;
+            const int i0 = tile_i * MM_TN;
+
+            u64 c0[2][MM_TN], c1[2][MM_TN], c2[2][MM_TN];
+            u64 part[2][MM_TN]; // canonical partial sums of the folded chunks
+#pragma unroll
+            for (int c = 0; c < MM_TN; c++)
+            {
+#pragma unroll
+                for (int e = 0; e < 2; e++)
+                {
+                    c0[e][c] = c1[e][c] = c2[e][c] = 0;
+                    part[e][c] = 0;
+                }
+            }
+            auto fold = [&]() {
+#pragma unroll
+                for (int c = 0; c < MM_TN; c++)
+                {
+#pragma unroll
+                    for (int e = 0; e < 2; e++)
+                    {
+                        // part += (c0 + c1 * 2^26 + c2 * 2^52) mod q
+                        u64 lo = c0[e][c], hi = 0;
+                        u64 t = c1[e][c] << 26;
+                        lo += t;
+                        hi += (lo < t) + (c1[e][c] >> 38);
+                        t = c2[e][c] << 52;
+                        lo += t;
+                        hi += (lo < t) + (c2[e][c] >> 12);
+                        part[e][c] = addmod(part[e][c], barrett_reduce_acc(u128{ lo, hi }, lc, t64.w, t64.wq), lc.q);
+                        c0[e][c] = c1[e][c] = c2[e][c] = 0;
+                    }
+                }
+            };
+            const u64 *wl = Wc + (long long)l * K * C;
+            for (int j0 = 0; j0 < K; j0 += MM_KC)
+            {
+                const int jn = min(MM_KC, K - j0);
+                __syncthreads();
+                for (int e = threadIdx.x; e < jn * MM_TN; e += MM_THREADS)
+                {
+                    const int jj = e / MM_TN, cc = e % MM_TN;
+                    ws[e] = (i0 + cc < C) ? wl[(long long)(j0 + jj) * C + i0 + cc] : 0;
+                }
+                __syncthreads();
+                if (j0 && (j0 % MM_FOLD) == 0)
+                {
+                    fold();
+                }
+                const ulonglong2 *xp = X + (long long)j0 * ct_stride2 + off;
+#pragma unroll 2
+                for (int jj = 0; jj < jn; jj++)
+                {
+                    const ulonglong2 x = xp[(long long)jj * ct_stride2];
+                    const u32 xa0 = (u32)x.x & 0x3FFFFFFu, xa1 = (u32)(x.x >> 26);
+                    const u32 xb0 = (u32)x.y & 0x3FFFFFFu, xb1 = (u32)(x.y >> 26);
+                    const uint4 *wrow = reinterpret_cast<const uint4 *>(ws + jj * MM_TN);
+#pragma unroll
+                    for (int c = 0; c < MM_TN; c += 2)
+                    {
+                        const uint4 w = wrow[c >> 1]; // (w0, w1) of column c, (w0, w1) of column c+1
+                        c0[0][c] += (u64)xa0 * w.x;
+                        c1[0][c] += (u64)xa0 * w.y;
+                        c1[0][c] += (u64)xa1 * w.x;
+                        c2[0][c] += (u64)xa1 * w.y;
+                        c0[1][c] += (u64)xb0 * w.x;
+                        c1[1][c] += (u64)xb0 * w.y;
+                        c1[1][c] += (u64)xb1 * w.x;
+                        c2[1][c] += (u64)xb1 * w.y;
+                        c0[0][c + 1] += (u64)xa0 * w.z;
+                        c1[0][c + 1] += (u64)xa0 * w.w;
+                        c1[0][c + 1] += (u64)xa1 * w.z;
+                        c2[0][c + 1] += (u64)xa1 * w.w;
+                        c0[1][c + 1] += (u64)xb0 * w.z;
+                        c1[1][c + 1] += (u64)xb0 * w.w;
+                        c1[1][c + 1] += (u64)xb1 * w.z;
+                        c2[1][c + 1] += (u64)xb1 * w.w;
+                    }
+                }
+            }
+            fold();
+#pragma unroll
+            for (int c = 0; c < MM_TN; c++)
+            {
+                if (i0 + c < C)
+                {
+                    ulonglong2 r;
+                    r.x = part[0][c];
+                    r.y = part[1][c];
+                    Y[(long long)(i0 + c) * ct_stride2 + off] = r;
+                }
+            }
+        }
     } // namespace
 
     // X: [K][2][limbs][n] device; W: host row-major K x C doubles; out: [C][2][limbs-1][n] device
@@ -135,19 +256,126 @@ namespace moai
         Scratch dWc((size_t)limbs * kc * sizeof(u64), c->stream);
         Scratch Y((size_t)C * 2 * limbs * n * sizeof(u64), c->stream);
         MOAI_CUDA_CHECK(cudaMemcpyAsync(dW.p, h_W, kc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        bool narrow = true; // every limb prime below 2^52 -> carry-free 26-bit split kernel
+        for (int l = 0; l < limbs; l++)
+        {
+            narrow = narrow && (c->q[l] >> 52) == 0;
+        }
         k_encode_weights<<<(unsigned)((kc + 255) / 256), 256, 0, c->stream>>>(dW.as<double>(), dWc.as<u64>(), kc, limbs,
-                                                                            scale, c->d_limb);
+                                                                            scale, c->d_limb, narrow ? 1 : 0);
         c->launches += 2;
         const int tiles_i = (C + MM_TN - 1) / MM_TN;
         const int tiles_t = (int)((n / 2) / MM_THREADS);
         const long long ctas = (long long)2 * limbs * tiles_t * tiles_i;
         {
             PhaseTimer pt(c, "ctpt_gemm");
-            k_ctpt_gemm<<<(unsigned)ctas, MM_THREADS, 0, c->stream>>>(reinterpret_cast<const ulonglong2 *>(X),
-                                                                     dWc.as<u64>(), Y.as<ulonglong2>(), K, C, limbs,
-                                                                     c->log_n - 1, c->d_limb, c->d_two64);
+            if (narrow)
+            {
+                k_ctpt_gemm26<<<(unsigned)ctas, MM_THREADS, 0, c->stream>>>(
+                    reinterpret_cast<const ulonglong2 *>(X), dWc.as<u64>(), Y.as<ulonglong2>(), K, C, limbs,
+                    c->log_n - 1, c->d_limb, c->d_two64);
+            }
+            else
+            {
+                k_ctpt_gemm<<<(unsigned)ctas, MM_THREADS, 0, c->stream>>>(
+                    reinterpret_cast<const ulonglong2 *>(X), dWc.as<u64>(), Y.as<ulonglong2>(), K, C, limbs,
+                    c->log_n - 1, c->d_limb, c->d_two64);
+            }
         }
         MOAI_CUDA_CHECK(cudaGetLastError());
+        rescale(c, Y.as<u64>(), out, C, 2, limbs);
+    }
+
+    namespace
+    {
+        // acc[i][p][l][t] (+)= X[j][p][l][t] * pt[(jj * CC + ii)][l][t]  for the j-chunk [j0, j0+KC), columns [i0, i0+CC)
+        __global__ void k_masked_mac(const ulonglong2 *__restrict__ X, const ulonglong2 *__restrict__ pt,
+                                     ulonglong2 *__restrict__ acc, int KCn, int CCn, int limbs, int log_n2, int first,
+                                     const LimbConst *__restrict__ lcs, const Twiddle *__restrict__ two64)
+        {
+            // grid: x over [2*limbs][n/2 / 256], y = ii
+            const int tiles_t = (1 << log_n2) / MM_THREADS;
+            const int tile_t = blockIdx.x % tiles_t;
+            const int pl = blockIdx.x / tiles_t;
+            const int l = pl % limbs;
+            const int ii = blockIdx.y;
+            const LimbConst lc = lcs[l];
+            const Twiddle t64 = two64[l];
+            const long long within = (long long)tile_t * MM_THREADS + threadIdx.x;
+            const long long ct_stride2 = (long long)2 * limbs << log_n2;
+            const long long pt_stride2 = (long long)limbs << log_n2;
+            u128 ax{ 0, 0 }, ay{ 0, 0 };
+            for (int jj = 0; jj < KCn; jj++)
+            {
+                const ulonglong2 x = X[(long long)jj * ct_stride2 + ((long long)pl << log_n2) + within];
+                const ulonglong2 m = pt[((long long)jj * CCn + ii) * pt_stride2 + ((long long)l << log_n2) + within];
+                mac_wide(ax, x.x, m.x);
+                mac_wide(ay, x.y, m.y);
+            }
+            ulonglong2 r;
+            r.x = barrett_reduce_acc(ax, lc, t64.w, t64.wq);
+            r.y = barrett_reduce_acc(ay, lc, t64.w, t64.wq);
+            ulonglong2 *dst = acc + (long long)ii * ct_stride2 + ((long long)pl << log_n2) + within;
+            if (!first)
+            {
+                const ulonglong2 o = *dst;
+                r.x = addmod(r.x, o.x, lc.q);
+                r.y = addmod(r.y, o.y, lc.q);
+            }
+            *dst = r;
+        }
+    } // namespace
+
+    // ct_pt_matrix_mul_wo_pre_w_mask (M/source/matrix_mul/Ct_pt_matrix_mul.hpp:103-170), exact for any
+    // 0/1 mask: every plaintext encode_vector(W[j][i] * mask) is produced on the device with the
+    // reference's FFT (bit-identical), then multiplied and accumulated; K*C FFTs + K*C*limbs NTTs.
+    void ct_pt_matmul_masked(Context *c, const u64 *X, const double *h_W, const int *h_mask, int K, int C, int limbs,
+                             double scale, u64 *out)
+    {
+        MOAI_REQUIRE(K >= 1 && C >= 1, "bad dimensions of X or W");
+        MOAI_REQUIRE(limbs >= 2 && limbs <= c->kl - 1, "end of modulus switching chain reached");
+        const size_t n = c->n;
+        // chunking: KC x CC plaintexts at a time (bounded workspace ~ 1.5 GiB incl. the FFT buffers)
+        const size_t per_pt = n * sizeof(double2) + (size_t)limbs * n * sizeof(u64);
+        long long budget = (long long)(((size_t)3 << 29) / per_pt);
+        budget = budget < 1 ? 1 : budget;
+        int CC = (int)(budget < C ? budget : C);
+        int KC = (int)(budget / CC);
+        KC = KC < 1 ? 1 : (KC > K ? K : KC);
+        Scratch dmask((n / 2) * sizeof(int), c->stream);
+        Scratch dw((size_t)KC * CC * sizeof(double), c->stream);
+        Scratch pts((size_t)KC * CC * limbs * n * sizeof(u64), c->stream);
+        Scratch Y((size_t)C * 2 * limbs * n * sizeof(u64), c->stream);
+        MOAI_CUDA_CHECK(cudaMemcpyAsync(dmask.p, h_mask, (n / 2) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        std::vector<double> hw((size_t)KC * CC);
+        const int tiles_t = (int)((n / 2) / MM_THREADS);
+        for (int i0 = 0; i0 < C; i0 += CC)
+        {
+            const int cn = std::min(CC, C - i0);
+            for (int j0 = 0; j0 < K; j0 += KC)
+            {
+                const int kn = std::min(KC, K - j0);
+                for (int jj = 0; jj < kn; jj++)
+                {
+                    for (int ii = 0; ii < cn; ii++)
+                    {
+                        hw[(size_t)jj * cn + ii] = h_W[(size_t)(j0 + jj) * C + i0 + ii];
+                    }
+                }
+                MOAI_CUDA_CHECK(cudaMemcpyAsync(dw.p, hw.data(), (size_t)kn * cn * sizeof(double),
+                                                cudaMemcpyHostToDevice, c->stream));
+                MOAI_CUDA_CHECK(cudaStreamSynchronize(c->stream)); // hw is reused by the next chunk
+                encode_masked_weights(c, dw.as<double>(), dmask.as<int>(), (long long)kn * cn, scale, limbs,
+                                      pts.as<u64>());
+                dim3 grid((unsigned)(2 * limbs * tiles_t), (unsigned)cn);
+                k_masked_mac<<<grid, MM_THREADS, 0, c->stream>>>(
+                    reinterpret_cast<const ulonglong2 *>(X + (size_t)j0 * 2 * limbs * n), pts.as<ulonglong2>(),
+                    Y.as<ulonglong2>() + (size_t)i0 * limbs * n, kn, cn, limbs, c->log_n - 1, j0 == 0 ? 1 : 0,
+                    c->d_limb, c->d_two64);
+                c->launches += 1;
+                MOAI_CUDA_CHECK(cudaGetLastError());
+            }
+        }
         rescale(c, Y.as<u64>(), out, C, 2, limbs);
     }
 } // namespace moai

@@ -38,4 +38,13 @@ namespace moai
     // fused module: out[C][2][limbs-1][n] = rescale(sum_j X[j] * encode_scalar(W[j][i]))
     void ct_pt_matmul_scalar(Context *c, const u64 *X, const double *h_W, int K, int C, int limbs, double scale,
                              u64 *out);
+
+    // CKKSEncoder::encode(vector) on the device; values: DEVICE [count][n_vals] complex (re, im)
+    void encode_vector(Context *c, const double *d_values, long long count, int n_vals, double scale, int limbs,
+                       u64 *out);
+    void encode_masked_weights(Context *c, const double *d_w, const int *d_mask, long long count, double scale,
+                               int limbs, u64 *out);
+    // out[C][2][limbs-1][n] = rescale(sum_j X[j] * encode_vector(W[j][i] * mask))  (exact general-mask path)
+    void ct_pt_matmul_masked(Context *c, const u64 *X, const double *h_W, const int *h_mask, int K, int C, int limbs,
+                             double scale, u64 *out);
 } // namespace moai
