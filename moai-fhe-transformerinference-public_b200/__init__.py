@@ -338,3 +338,75 @@ class Backend:
         self._chk(self.lib.moai_encode_vector(self.h, _ptr(d), C.c_int64(count), C.c_int32(n_vals), C.c_double(scale),
                                               C.c_int32(limbs), _ptr(out)))
         return out[0] if single else out
+
+    # ---- evaluation keys + MOAI modules (B4-B9)
+    def make_keys(self, relin=None, galois=None):
+        """relin: device key tensor; galois: dict galois_elt -> device key tensor.  The returned
+        handle keeps the tensors alive."""
+        h = C.c_void_p()
+        self._chk(self.lib.moai_keys_create(self.h, C.byref(h)))
+        keep = []
+        if relin is not None:
+            self._chk(self.lib.moai_keys_set_relin(h, _ptr(relin)))
+            keep.append(relin)
+        for elt, t in (galois or {}).items():
+            self._chk(self.lib.moai_keys_add_galois(h, C.c_uint32(elt), _ptr(t)))
+            keep.append(t)
+        return _KeysHandle(self.lib, h, keep)
+
+    def _module(self, fn, x, scale, *extra, out_count=None):
+        bt, p, l, n = x.shape
+        cnt = bt if out_count is None else out_count
+        buf = self.empty(cnt, 2, l, n)
+        ol, osc = C.c_int32(), C.c_double()
+        self._chk(fn(*extra, _ptr(buf), C.byref(ol), C.byref(osc)))
+        flat = buf.reshape(-1)[: cnt * 2 * ol.value * n]
+        return flat.reshape(cnt, 2, ol.value, n), osc.value
+
+    def gelu_v2(self, keys, x, scale):
+        bt, p, l, n = x.shape
+        return self._module(self.lib.moai_gelu_v2, x, scale, self.h, keys.h, _ptr(x), C.c_int64(bt), C.c_int32(l),
+                            C.c_double(scale))
+
+    def layernorm(self, keys, x, scale, gamma, beta, bias_vec, variant=1):
+        bt, p, l, n = x.shape
+        g = np.ascontiguousarray(gamma, dtype=np.float64)
+        b = np.ascontiguousarray(beta, dtype=np.float64)
+        bv = np.ascontiguousarray(bias_vec, dtype=np.int32)
+        dp = C.POINTER(C.c_double)
+        return self._module(self.lib.moai_layernorm, x, scale, self.h, keys.h, _ptr(x), C.c_int32(bt), C.c_int32(l),
+                            C.c_double(scale), g.ctypes.data_as(dp), b.ctypes.data_as(dp),
+                            bv.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int32(variant))
+
+    def exp(self, keys, x, scale):
+        bt, p, l, n = x.shape
+        return self._module(self.lib.moai_exp, x, scale, self.h, keys.h, _ptr(x), C.c_int64(bt), C.c_int32(l),
+                            C.c_double(scale))
+
+    def inverse(self, keys, x, scale, iters):
+        bt, p, l, n = x.shape
+        return self._module(self.lib.moai_inverse, x, scale, self.h, keys.h, _ptr(x), C.c_int64(bt), C.c_int32(l),
+                            C.c_double(scale), C.c_int32(iters))
+
+    def ct_ct_matrix_mul_colpacking(self, keys, X, W, scale_X, scale_W, col_X, row_X, col_W, row_W, num_batch):
+        l = X.shape[2]
+        return self._module(self.lib.moai_ct_ct_matrix_mul_colpacking, X, scale_X, self.h, keys.h, _ptr(X), _ptr(W),
+                            C.c_int32(l), C.c_double(scale_X), C.c_double(scale_W), C.c_int32(col_X), C.c_int32(row_X),
+                            C.c_int32(col_W), C.c_int32(row_W), C.c_int32(num_batch), out_count=row_X)
+
+    def ct_ct_matrix_mul_diagpacking(self, keys, X, W, scale_X, scale_W, col_X, row_X, col_W, row_W, num_batch):
+        l = X.shape[2]
+        return self._module(self.lib.moai_ct_ct_matrix_mul_diagpacking, X, scale_X, self.h, keys.h, _ptr(X), _ptr(W),
+                            C.c_int32(l), C.c_double(scale_X), C.c_double(scale_W), C.c_int32(col_X), C.c_int32(row_X),
+                            C.c_int32(col_W), C.c_int32(row_W), C.c_int32(num_batch), out_count=col_W)
+
+
+class _KeysHandle:
+    def __init__(self, lib, h, keep):
+        self.lib, self.h, self.keep = lib, h, keep
+
+    def __del__(self):
+        try:
+            self.lib.moai_keys_destroy(self.h)
+        except Exception:
+            pass

@@ -3,6 +3,7 @@
 #include "../../include/moai_b200.h"
 #include "../../include/moai_b200_modules.h"
 #include "ntt.cuh"
+#include "modules.hpp"
 #include "ops.cuh"
 #include <cmath>
 
@@ -11,6 +12,11 @@ using namespace moai;
 struct moai_context
 {
     Context *c;
+};
+
+struct moai_keys
+{
+    Keys k;
 };
 
 #define API_BEGIN                                                                                                      \
@@ -495,6 +501,160 @@ extern "C"
         Context *c = get(ctx);
         MOAI_REQUIRE(limbs >= 1 && limbs <= c->kl && out, "bad arguments");
         encode_vector(c, values, count, n_vals, scale, limbs, U(out));
+        API_END
+    }
+
+    // ---- key handles ---------------------------------------------------------------------------
+    int32_t moai_keys_create(moai_context *ctx, moai_keys **out)
+    {
+        API_BEGIN
+        get(ctx);
+        MOAI_REQUIRE(out, "null argument");
+        *out = new moai_keys();
+        API_END
+    }
+
+    int32_t moai_keys_destroy(moai_keys *keys)
+    {
+        API_BEGIN
+        delete keys;
+        API_END
+    }
+
+    int32_t moai_keys_set_relin(moai_keys *keys, const uint64_t *ksk)
+    {
+        API_BEGIN
+        MOAI_REQUIRE(keys, "null argument");
+        keys->k.relin = CU(ksk);
+        API_END
+    }
+
+    int32_t moai_keys_add_galois(moai_keys *keys, uint32_t galois_elt, const uint64_t *ksk)
+    {
+        API_BEGIN
+        MOAI_REQUIRE(keys && ksk, "null argument");
+        keys->k.galois[galois_elt] = CU(ksk);
+        API_END
+    }
+
+    static const Keys &getk(moai_keys *keys)
+    {
+        if (!keys)
+        {
+            throw StatusError{ INVALID_ARGUMENT, "null keys" };
+        }
+        return keys->k;
+    }
+
+    static void emit(Context *c, const Ct &r, uint64_t *out, int64_t out_capacity_cts, int32_t *out_limbs,
+                     double *out_scale)
+    {
+        MOAI_REQUIRE(out && out_limbs && out_scale, "null argument");
+        MOAI_REQUIRE(out_capacity_cts >= r.batch, "output buffer too small");
+        MOAI_CUDA_CHECK(cudaMemcpyAsync(out, r.d, (size_t)r.batch * r.size * r.limbs * c->n * sizeof(u64),
+                                        cudaMemcpyDeviceToDevice, c->stream));
+        *out_limbs = r.limbs;
+        *out_scale = r.scale;
+        MOAI_CUDA_CHECK(cudaStreamSynchronize(c->stream)); // r's storage is released on return
+    }
+
+    int32_t moai_rotate_vector(moai_context *ctx, moai_keys *keys, const uint64_t *in, uint64_t *out, int64_t batch,
+                               int32_t limbs, int32_t steps)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, batch, 2, limbs);
+        Evaluator ev(c);
+        Ct a = ev.wrap(const_cast<u64 *>(CU(in)), batch, 2, limbs, 1.0);
+        Ct r = ev.rotate_vector(a, steps, getk(keys));
+        MOAI_CUDA_CHECK(cudaMemcpyAsync(out, r.d, (size_t)batch * 2 * limbs * c->n * sizeof(u64),
+                                        cudaMemcpyDeviceToDevice, c->stream));
+        MOAI_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        API_END
+    }
+
+    int32_t moai_gelu_v2(moai_context *ctx, moai_keys *keys, const uint64_t *x, int64_t batch, int32_t limbs,
+                         double scale, uint64_t *out, int32_t *out_limbs, double *out_scale)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, batch, 2, limbs);
+        Evaluator ev(c);
+        Ct r = gelu_v2(ev, ev.wrap(const_cast<u64 *>(CU(x)), batch, 2, limbs, scale), getk(keys));
+        emit(c, r, out, batch, out_limbs, out_scale);
+        API_END
+    }
+
+    int32_t moai_layernorm(moai_context *ctx, moai_keys *keys, const uint64_t *x, int32_t num_ct, int32_t limbs,
+                           double scale, const double *gamma, const double *beta, const int32_t *bias_vec,
+                           int32_t variant, uint64_t *out, int32_t *out_limbs, double *out_scale)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, num_ct, 2, limbs);
+        MOAI_REQUIRE(gamma && beta && bias_vec, "null argument");
+        MOAI_REQUIRE(variant == 1 || variant == 2, "variant must be 1 (layernorm) or 2 (layernorm2)");
+        Evaluator ev(c);
+        std::vector<double> g(gamma, gamma + num_ct), b(beta, beta + num_ct);
+        std::vector<int> bv(bias_vec, bias_vec + c->n / 2);
+        Ct r = layernorm(ev, ev.wrap(const_cast<u64 *>(CU(x)), num_ct, 2, limbs, scale), g, b, bv, getk(keys), variant);
+        emit(c, r, out, num_ct, out_limbs, out_scale);
+        API_END
+    }
+
+    int32_t moai_exp(moai_context *ctx, moai_keys *keys, const uint64_t *x, int64_t batch, int32_t limbs, double scale,
+                     uint64_t *out, int32_t *out_limbs, double *out_scale)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, batch, 2, limbs);
+        Evaluator ev(c);
+        Ct r = exp_128(ev, ev.wrap(const_cast<u64 *>(CU(x)), batch, 2, limbs, scale), getk(keys));
+        emit(c, r, out, batch, out_limbs, out_scale);
+        API_END
+    }
+
+    int32_t moai_inverse(moai_context *ctx, moai_keys *keys, const uint64_t *x, int64_t batch, int32_t limbs,
+                         double scale, int32_t iter, uint64_t *out, int32_t *out_limbs, double *out_scale)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, batch, 2, limbs);
+        Evaluator ev(c);
+        Ct r = inverse(ev, ev.wrap(const_cast<u64 *>(CU(x)), batch, 2, limbs, scale), getk(keys), iter);
+        emit(c, r, out, batch, out_limbs, out_scale);
+        API_END
+    }
+
+    int32_t moai_ct_ct_matrix_mul_colpacking(moai_context *ctx, moai_keys *keys, const uint64_t *enc_X,
+                                             const uint64_t *enc_W, int32_t limbs, double scale_X, double scale_W,
+                                             int32_t col_X, int32_t row_X, int32_t col_W, int32_t row_W,
+                                             int32_t num_batch, uint64_t *out, int32_t *out_limbs, double *out_scale)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, col_X, 2, limbs);
+        Evaluator ev(c);
+        Ct X = ev.wrap(const_cast<u64 *>(CU(enc_X)), col_X, 2, limbs, scale_X);
+        Ct W = ev.wrap(const_cast<u64 *>(CU(enc_W)), col_W, 2, limbs, scale_W);
+        Ct r = ct_ct_matrix_mul_colpacking(ev, X, W, getk(keys), col_X, row_X, col_W, row_W, num_batch);
+        emit(c, r, out, row_X, out_limbs, out_scale);
+        API_END
+    }
+
+    int32_t moai_ct_ct_matrix_mul_diagpacking(moai_context *ctx, moai_keys *keys, const uint64_t *enc_X,
+                                              const uint64_t *enc_W, int32_t limbs, double scale_X, double scale_W,
+                                              int32_t col_X, int32_t row_X, int32_t col_W, int32_t row_W,
+                                              int32_t num_batch, uint64_t *out, int32_t *out_limbs, double *out_scale)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, row_X, 2, limbs);
+        Evaluator ev(c);
+        Ct X = ev.wrap(const_cast<u64 *>(CU(enc_X)), row_X, 2, limbs, scale_X);
+        Ct W = ev.wrap(const_cast<u64 *>(CU(enc_W)), col_W, 2, limbs, scale_W);
+        Ct r = ct_ct_matrix_mul_diagpacking(ev, X, W, getk(keys), col_X, row_X, col_W, row_W, num_batch);
+        emit(c, r, out, col_W, out_limbs, out_scale);
         API_END
     }
 }

@@ -1,0 +1,159 @@
+// Host-side C++ evaluator over batches of device ciphertexts.
+//
+// Mirrors the call surface and the metadata rules of the reference's seal::Evaluator /
+// seal::CKKSEncoder (S/evaluator.h:93-1386, S/ckks.h:148-432) — same method names, same scale
+// arithmetic in doubles, same argument checks and exception kinds — but every object is a BATCH
+// of independent ciphertexts resident in HBM, because that is the only parallelism the
+// reference has (`#pragma omp parallel for` over ciphertexts).  The MOAI module functions
+// (csrc/modules.cu) are written against this class the way the reference's are written against
+// seal::Evaluator.
+#pragma once
+#include "ntt.cuh"
+#include "ops.cuh"
+#include <cmath>
+#include <complex>
+#include <map>
+#include <memory>
+#include <vector>
+
+namespace moai
+{
+    struct DevBuf
+    {
+        void *p = nullptr;
+        cudaStream_t s;
+        DevBuf(size_t bytes, cudaStream_t stream) : s(stream)
+        {
+            MOAI_CUDA_CHECK(cudaMallocAsync(&p, bytes ? bytes : 8, stream));
+        }
+        ~DevBuf()
+        {
+            if (p)
+            {
+                cudaFreeAsync(p, s);
+            }
+        }
+        DevBuf(const DevBuf &) = delete;
+        DevBuf &operator=(const DevBuf &) = delete;
+    };
+
+    // `batch` ciphertexts of identical shape/level/scale: [batch][size][limbs][n].
+    // Copies are shallow handles (shared buffer); clone() deep-copies like seal::Ciphertext's
+    // copy-assignment does.
+    struct Ct
+    {
+        std::shared_ptr<DevBuf> buf;
+        u64 *d = nullptr;
+        long long batch = 0;
+        int size = 2;
+        int limbs = 0;
+        double scale = 1.0;
+        bool empty() const
+        {
+            return d == nullptr;
+        }
+    };
+
+    // Plaintext: either a polynomial per batch item / broadcast ([count][limbs][n], count = 1 or
+    // batch) or a scalar encoding = one constant per limb (S/ckks.cpp:131-153).
+    struct Pt
+    {
+        std::shared_ptr<DevBuf> buf;
+        u64 *d = nullptr;
+        long long count = 0;
+        int limbs = 0;
+        double scale = 1.0;
+        bool is_scalar = false;
+        std::vector<u64> consts;
+    };
+
+    // Device key material: SEAL's RelinKeys / GaloisKeys as raw device pointers.
+    struct Keys
+    {
+        const u64 *relin = nullptr;
+        std::map<uint32_t, const u64 *> galois;
+    };
+
+    class Evaluator
+    {
+    public:
+        Context *c;
+        explicit Evaluator(Context *ctx) : c(ctx)
+        {}
+
+        size_t n() const
+        {
+            return c->n;
+        }
+
+        // ---- storage -------------------------------------------------------------------------
+        Ct alloc(long long batch, int size, int limbs, double scale) const;
+        Ct wrap(u64 *d, long long batch, int size, int limbs, double scale) const; // caller-owned memory
+        Ct view(const Ct &a, long long b0, long long count) const;                 // sub-batch, shared storage
+        Ct clone(const Ct &a) const;
+        void copy_into(const Ct &src, Ct &dst, long long dst_b0) const;            // dst[dst_b0 ...] = src
+        Ct concat(const std::vector<Ct> &parts) const;
+        Ct repeat(const Ct &a, long long times) const;                            // batch-1 -> batch-`times`
+
+        // ---- S/evaluator.h surface ------------------------------------------------------------
+        Ct add(const Ct &a, const Ct &b) const;          // b.batch == 1 broadcasts over a's batch
+        Ct sub(const Ct &a, const Ct &b) const;
+        void add_inplace(Ct &a, const Ct &b) const;
+        void sub_inplace(Ct &a, const Ct &b) const;
+        Ct negate(const Ct &a) const;
+        Ct add_plain(const Ct &a, const Pt &p) const;
+        Ct sub_plain(const Ct &a, const Pt &p) const;
+        Ct multiply_plain(const Ct &a, const Pt &p) const;
+        Ct multiply(const Ct &a, const Ct &b) const;     // size 2 x size 2 -> size 3
+        Ct square(const Ct &a) const;
+        void multiply_accumulate(Ct &acc3, const Ct &a, const Ct &b) const; // acc3 += a x b (size 3)
+        Ct relinearize(const Ct &a3, const Keys &k) const;
+        Ct rescale_to_next(const Ct &a) const;
+        Ct mod_switch_to(const Ct &a, int limbs) const;
+        Ct mod_switch_to_next(const Ct &a) const
+        {
+            return mod_switch_to(a, a.limbs - 1);
+        }
+        Ct rotate_vector(const Ct &a, int steps, const Keys &k) const;
+        Ct complex_conjugate(const Ct &a, const Keys &k) const;
+        Ct sum_batch(const Ct &a) const; // one ciphertext = sum over the batch (modular)
+        Ct inner_product(const Ct &a, const Ct &b) const;      // size-3 sum_j a[j] x b[j]
+        Ct sum_sub_square(const Ct &a, const Ct &m) const;     // size-3 sum_j (a[j] - m)^2, m one ciphertext
+
+        // ---- S/ckks.h surface -----------------------------------------------------------------
+        Pt encode(double value, int limbs, double scale) const;
+        Pt encode(const std::vector<std::complex<double>> &values, int limbs, double scale) const;
+        Pt encode(const std::vector<double> &values, int limbs, double scale) const;
+        // `count` plaintexts from one host array [count][n_vals] of complex values
+        Pt encode_batch(const std::complex<double> *values, long long count, int n_vals, int limbs,
+                        double scale) const;
+
+        // ---- fork-only ops (S/evaluator.cpp:395-594, S/evaluator.h:1300-1386) ------------------
+        Ct multiply_const(const Ct &a, double value) const;
+        Ct add_const(const Ct &a, double value) const;
+        Ct multiply_vector_reduced_error(const Ct &a, const std::vector<std::complex<double>> &v) const;
+        Ct add_reduced_error(const Ct &a, const Ct &b) const;
+        Ct sub_reduced_error(const Ct &a, const Ct &b) const;
+        Ct multiply_reduced_error(const Ct &a, const Ct &b, const Keys &k) const;
+        void double_inplace(Ct &a) const;
+
+        // ---- Bootstrapper::modraise_inplace -----------------------------------------------------
+        Ct mod_raise(const Ct &a, int limbs_out) const;
+
+        double last_prime(int limbs) const
+        {
+            return static_cast<double>(c->q[limbs - 1]);
+        }
+
+    private:
+        void check_same(const Ct &a, const Ct &b, bool need_scale) const;
+        Ct reduced_error_adjust(const Ct &hi, const Ct &lo) const;
+    };
+
+    // SEAL's util::are_close (S/util/common.h:569-573)
+    inline bool are_close(double v1, double v2)
+    {
+        double sf = std::max(std::max(std::fabs(v1), std::fabs(v2)), 1.0);
+        return std::fabs(v1 - v2) < std::numeric_limits<double>::epsilon() * sf;
+    }
+} // namespace moai

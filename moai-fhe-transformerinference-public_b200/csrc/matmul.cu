@@ -17,6 +17,8 @@
 #include "ntt.cuh"
 #include "ops.cuh"
 #include <cmath>
+#include <cstdlib>
+#include <type_traits>
 
 namespace moai
 {
@@ -125,11 +127,17 @@ namespace moai
         // carry chain.  One MAC = exactly four IMAD.WIDE.U32 with accumulate and nothing else —
         // the integer pipe's minimum for a 52x52-bit product; the carries are paid once per 1024 j.
         constexpr int MM_FOLD = 1024;
-        __global__ void __launch_bounds__(MM_THREADS)
-            k_ctpt_gemm26(const ulonglong2 *__restrict__ X, const u64 *__restrict__ Wc, ulonglong2 *__restrict__ Y,
-                          int K, int C, int limbs, int log_n2, const LimbConst *__restrict__ lcs,
+        template <int TM>
+        __global__ void __launch_bounds__(MM_THREADS, TM == 1 ? 2 : 1)
+            k_ctpt_gemm26(const u64 *__restrict__ Xw, const u64 *__restrict__ Wc, u64 *__restrict__ Yw,
+                          int K, int C, int limbs, int log_n, const LimbConst *__restrict__ lcs,
                           const Twiddle *__restrict__ two64)
         {
+            // TM consecutive coefficients per thread; strides below are in units of TM words
+            typedef typename std::conditional<TM == 2, ulonglong2, u64>::type vec_t;
+            const vec_t *X = reinterpret_cast<const vec_t *>(Xw);
+            vec_t *Y = reinterpret_cast<vec_t *>(Yw);
+            const int log_n2 = log_n - (TM == 2 ? 1 : 0);
             __shared__ u64 ws[MM_KC * MM_TN];
             const int tiles_i = (C + MM_TN - 1) / MM_TN;
             const int tiles_t = (1 << log_n2) / MM_THREADS;
@@ -144,13 +152,13 @@ namespace moai
             const long long off = ((long long)pl << log_n2) + (long long)tile_t * MM_THREADS + threadIdx.x;
             const int i0 = tile_i * MM_TN;
 
-            u64 c0[2][MM_TN], c1[2][MM_TN], c2[2][MM_TN];
-            u64 part[2][MM_TN]; // canonical partial sums of the folded chunks
+            u64 c0[TM][MM_TN], c1[TM][MM_TN], c2[TM][MM_TN];
+            u64 part[TM][MM_TN]; // canonical partial sums of the folded chunks
 #pragma unroll
             for (int c = 0; c < MM_TN; c++)
             {
 #pragma unroll
-                for (int e = 0; e < 2; e++)
+                for (int e = 0; e < TM; e++)
                 {
                     c0[e][c] = c1[e][c] = c2[e][c] = 0;
                     part[e][c] = 0;
@@ -161,7 +169,7 @@ namespace moai
                 for (int c = 0; c < MM_TN; c++)
                 {
 #pragma unroll
-                    for (int e = 0; e < 2; e++)
+                    for (int e = 0; e < TM; e++)
                     {
                         // part += (c0 + c1 * 2^26 + c2 * 2^52) mod q
                         u64 lo = c0[e][c], hi = 0;
@@ -191,34 +199,37 @@ namespace moai
                 {
                     fold();
                 }
-                const ulonglong2 *xp = X + (long long)j0 * ct_stride2 + off;
+                const vec_t *xp = X + (long long)j0 * ct_stride2 + off;
 #pragma unroll 2
                 for (int jj = 0; jj < jn; jj++)
                 {
-                    const ulonglong2 x = xp[(long long)jj * ct_stride2];
-                    const u32 xa0 = (u32)x.x & 0x3FFFFFFu, xa1 = (u32)(x.x >> 26);
-                    const u32 xb0 = (u32)x.y & 0x3FFFFFFu, xb1 = (u32)(x.y >> 26);
-                    const uint4 *wrow = reinterpret_cast<const uint4 *>(ws + jj * MM_TN);
-#pragma unroll
-                    for (int c = 0; c < MM_TN; c += 2)
+                    const vec_t xv = xp[(long long)jj * ct_stride2];
+                    u32 x0[TM], x1[TM];
+                    if constexpr (TM == 2)
                     {
-                        const uint4 w = wrow[c >> 1]; // (w0, w1) of column c, (w0, w1) of column c+1
-                        c0[0][c] += (u64)xa0 * w.x;
-                        c1[0][c] += (u64)xa0 * w.y;
-                        c1[0][c] += (u64)xa1 * w.x;
-                        c2[0][c] += (u64)xa1 * w.y;
-                        c0[1][c] += (u64)xb0 * w.x;
-                        c1[1][c] += (u64)xb0 * w.y;
-                        c1[1][c] += (u64)xb1 * w.x;
-                        c2[1][c] += (u64)xb1 * w.y;
-                        c0[0][c + 1] += (u64)xa0 * w.z;
-                        c1[0][c + 1] += (u64)xa0 * w.w;
-                        c1[0][c + 1] += (u64)xa1 * w.z;
-                        c2[0][c + 1] += (u64)xa1 * w.w;
-                        c0[1][c + 1] += (u64)xb0 * w.z;
-                        c1[1][c + 1] += (u64)xb0 * w.w;
-                        c1[1][c + 1] += (u64)xb1 * w.z;
-                        c2[1][c + 1] += (u64)xb1 * w.w;
+                        x0[0] = (u32)xv.x & 0x3FFFFFFu;
+                        x1[0] = (u32)(xv.x >> 26);
+                        x0[1] = (u32)xv.y & 0x3FFFFFFu;
+                        x1[1] = (u32)(xv.y >> 26);
+                    }
+                    else
+                    {
+                        x0[0] = (u32)xv & 0x3FFFFFFu;
+                        x1[0] = (u32)(xv >> 26);
+                    }
+                    const uint2 *wrow = reinterpret_cast<const uint2 *>(ws + jj * MM_TN);
+#pragma unroll
+                    for (int c = 0; c < MM_TN; c++)
+                    {
+                        const uint2 w = wrow[c]; // (w0, w1): low 26 bits, remaining bits
+#pragma unroll
+                        for (int e = 0; e < TM; e++)
+                        {
+                            c0[e][c] += (u64)x0[e] * w.x;
+                            c1[e][c] += (u64)x0[e] * w.y;
+                            c1[e][c] += (u64)x1[e] * w.x;
+                            c2[e][c] += (u64)x1[e] * w.y;
+                        }
                     }
                 }
             }
@@ -228,10 +239,17 @@ namespace moai
             {
                 if (i0 + c < C)
                 {
-                    ulonglong2 r;
-                    r.x = part[0][c];
-                    r.y = part[1][c];
-                    Y[(long long)(i0 + c) * ct_stride2 + off] = r;
+                    if constexpr (TM == 2)
+                    {
+                        ulonglong2 r;
+                        r.x = part[0][c];
+                        r.y = part[1][c];
+                        Y[(long long)(i0 + c) * ct_stride2 + off] = r;
+                    }
+                    else
+                    {
+                        Y[(long long)(i0 + c) * ct_stride2 + off] = part[0][c];
+                    }
                 }
             }
         }
@@ -262,18 +280,23 @@ namespace moai
             narrow = narrow && (c->q[l] >> 52) == 0;
         }
         k_encode_weights<<<(unsigned)((kc + 255) / 256), 256, 0, c->stream>>>(dW.as<double>(), dWc.as<u64>(), kc, limbs,
-                                                                            scale, c->d_limb, narrow ? 1 : 0);
+                                                                            scale, c->d_limb, narrow && !(getenv("MOAI_GEMM_VARIANT") && atoi(getenv("MOAI_GEMM_VARIANT")) == 0) ? 1 : 0);
         c->launches += 2;
         const int tiles_i = (C + MM_TN - 1) / MM_TN;
         const int tiles_t = (int)((n / 2) / MM_THREADS);
         const long long ctas = (long long)2 * limbs * tiles_t * tiles_i;
         {
             PhaseTimer pt(c, "ctpt_gemm");
-            if (narrow)
+            static const int variant = getenv("MOAI_GEMM_VARIANT") ? atoi(getenv("MOAI_GEMM_VARIANT")) : 2;
+            if (narrow && variant == 2)
             {
-                k_ctpt_gemm26<<<(unsigned)ctas, MM_THREADS, 0, c->stream>>>(
-                    reinterpret_cast<const ulonglong2 *>(X), dWc.as<u64>(), Y.as<ulonglong2>(), K, C, limbs,
-                    c->log_n - 1, c->d_limb, c->d_two64);
+                k_ctpt_gemm26<1><<<(unsigned)(2 * ctas), MM_THREADS, 0, c->stream>>>(
+                    X, dWc.as<u64>(), Y.as<u64>(), K, C, limbs, c->log_n, c->d_limb, c->d_two64);
+            }
+            else if (narrow && variant == 1)
+            {
+                k_ctpt_gemm26<2><<<(unsigned)ctas, MM_THREADS, 0, c->stream>>>(
+                    X, dWc.as<u64>(), Y.as<u64>(), K, C, limbs, c->log_n, c->d_limb, c->d_two64);
             }
             else
             {

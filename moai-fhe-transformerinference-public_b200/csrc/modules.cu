@@ -1,0 +1,357 @@
+// MOAI module layer as batched device pipelines.
+//
+// Each function computes exactly what the reference's free function of the same name computes —
+// the same sequence of SEAL-level operations per ciphertext, hence bit-identical residues — but the
+// loops the reference runs under `#pragma omp parallel for` (one ciphertext per iteration) become
+// the batch dimension of single kernel launches, and reductions over ciphertexts are fused
+// (Evaluator::sum_batch / inner_product / sum_sub_square).
+#include "modules.hpp"
+#include <algorithm>
+
+namespace moai
+{
+    namespace
+    {
+        // a 0/1 slot mask times a value, as the reference builds its masked vectors
+        std::vector<std::complex<double>> masked(const std::vector<int> &bias_vec, double value)
+        {
+            std::vector<std::complex<double>> v(bias_vec.size(), 0.0);
+            for (size_t i = 0; i < bias_vec.size(); i++)
+            {
+                if (bias_vec[i] == 1)
+                {
+                    v[i] = value;
+                }
+            }
+            return v;
+        }
+    } // namespace
+
+    // ------------------------------------------------------------------------------------ GELU
+    // gelu_v2: M/source/non_linear_func/gelu_others.hpp:4-154 — degree-24 polynomial in 0.1*x.
+    Ct gelu_v2(const Evaluator &ev, const Ct &x, const Keys &keys)
+    {
+        const double scale = x.scale;
+        double coeff[25] = { 3.18006986e-24,  5.70792114e-22,  3.97205561e-20,  1.31854608e-18,  1.64153184e-17,
+                             -2.33052347e-16, -9.78309547e-15, -6.72238500e-14, 1.43093357e-12,  2.41129634e-11,
+                             -4.00991558e-11, -3.06661368e-09, -1.00479838e-08, 2.05368974e-07,  1.25666834e-06,
+                             -7.76703686e-06, -6.75419265e-05, 1.62401656e-04,  1.97100905e-03,  -1.70511673e-03,
+                             -3.22621248e-02, 7.22135066e-03,  3.39374355e-01,  4.92938360e-01,  1.21149468e-02 };
+        const double s0 = 0.1, inv_s0 = 1 / s0;
+        double t = inv_s0;
+        for (int i = 23; i >= 0; --i)
+        {
+            coeff[i] *= t;
+            t *= inv_s0;
+        }
+        std::vector<Ct> p(25);
+        p[1] = ev.rescale_to_next(ev.multiply_plain(x, ev.encode(s0, x.limbs, x.scale)));
+        auto sq = [&](const Ct &a) { return ev.rescale_to_next(ev.relinearize(ev.square(a), keys)); };
+        auto mul = [&](const Ct &a, const Ct &b) {
+            // mod_switch the first factor to the second's level, multiply, relinearize, rescale
+            return ev.rescale_to_next(ev.relinearize(ev.multiply(ev.mod_switch_to(a, b.limbs), b), keys));
+        };
+        p[2] = sq(p[1]);
+        p[4] = sq(p[2]);
+        p[8] = sq(p[4]);
+        p[16] = sq(p[8]);
+        // the reference switches x_n[k] down in place before each product (gelu_others.hpp:52-121);
+        // later products therefore see the already-lowered copy
+        for (int i = 2; i < 17; i *= 2)
+        {
+            p[1] = ev.mod_switch_to(p[1], p[i].limbs);
+            p[i + 1] = mul(p[1], p[i]);
+        }
+        for (int k = 2; k <= 3; k++)
+        {
+            for (int i = 4; i < 17; i *= 2)
+            {
+                p[k] = ev.mod_switch_to(p[k], p[i].limbs);
+                p[i + k] = mul(p[k], p[i]);
+            }
+        }
+        for (int k = 4; k <= 7; k++)
+        {
+            for (int i = 8; i < 17; i *= 2)
+            {
+                p[k] = ev.mod_switch_to(p[k], p[i].limbs);
+                p[i + k] = mul(p[k], p[i]);
+            }
+        }
+        p[8] = ev.mod_switch_to(p[8], p[16].limbs);
+        p[24] = mul(p[8], p[16]);
+        Ct res;
+        for (int i = 1; i < 25; ++i)
+        {
+            Ct xi = ev.mod_switch_to(p[i], p[24].limbs);
+            xi = ev.rescale_to_next(ev.multiply_plain(xi, ev.encode(coeff[24 - i], xi.limbs, xi.scale)));
+            xi.scale = scale;
+            if (i == 1)
+            {
+                res = xi;
+            }
+            else
+            {
+                ev.add_inplace(res, xi);
+            }
+        }
+        return ev.add_plain(res, ev.encode(coeff[24], res.limbs, res.scale));
+    }
+
+    // ------------------------------------------------------------------------------------ LayerNorm
+    namespace
+    {
+        // evalLine / initGuess: M/source/non_linear_func/layernorm.hpp:4-24
+        Ct eval_line(const Evaluator &ev, const Ct &x, double m, double cst)
+        {
+            const double scale = x.scale;
+            Ct r = ev.rescale_to_next(ev.multiply_plain(x, ev.encode(m, x.limbs, scale)));
+            r.scale = scale;
+            return ev.add_plain(r, ev.encode(cst, r.limbs, scale));
+        }
+
+        // newtonIter: layernorm.hpp:26-78
+        Ct newton_iter(const Evaluator &ev, const Ct &x, Ct res, int iter, const Keys &keys)
+        {
+            const double scale = x.scale;
+            for (int i = 0; i < iter; ++i)
+            {
+                Ct res_sq = ev.rescale_to_next(ev.relinearize(ev.square(res), keys));
+                Ct res_x = ev.rescale_to_next(ev.multiply_plain(x, ev.encode(-0.5, x.limbs, scale)));
+                if (res.limbs < res_x.limbs)
+                {
+                    res_x = ev.mod_switch_to(res_x, res.limbs);
+                }
+                else
+                {
+                    res = ev.mod_switch_to(res, res_x.limbs);
+                }
+                res_x = ev.rescale_to_next(ev.relinearize(ev.multiply(res_x, res), keys));
+                res_sq = ev.mod_switch_to(res_sq, res_x.limbs);
+                res_x = ev.rescale_to_next(ev.relinearize(ev.multiply(res_x, res_sq), keys));
+                res = ev.rescale_to_next(ev.multiply_plain(res, ev.encode(1.5, res.limbs, scale)));
+                res = ev.mod_switch_to(res, res_x.limbs);
+                res_x.scale = scale;
+                res.scale = scale;
+                res = ev.add(res, res_x);
+            }
+            return res;
+        }
+
+        // goldSchmidtIter: layernorm.hpp:80-143
+        Ct goldschmidt_iter(const Evaluator &ev, Ct v, const Ct &y, int d, const Keys &keys)
+        {
+            const double scale = y.scale;
+            v = ev.mod_switch_to(v, y.limbs);
+            Ct x = ev.rescale_to_next(ev.relinearize(ev.multiply(v, y), keys));
+            Ct h = ev.rescale_to_next(ev.multiply_plain(y, ev.encode(0.5, y.limbs, scale)));
+            for (int i = 0; i < d; ++i)
+            {
+                Ct r = ev.rescale_to_next(ev.relinearize(ev.multiply(x, h), keys));
+                r.scale = scale;
+                r = ev.add_plain(ev.negate(r), ev.encode(0.5, r.limbs, scale));
+                // x = x + x*r
+                x = ev.mod_switch_to(x, r.limbs);
+                Ct tmp = ev.rescale_to_next(ev.relinearize(ev.multiply(x, r), keys));
+                x.scale = scale;
+                tmp.scale = scale;
+                x = ev.mod_switch_to(x, tmp.limbs);
+                x = ev.add(x, tmp);
+                // h = h + h*r
+                h = ev.mod_switch_to(h, r.limbs);
+                tmp = ev.rescale_to_next(ev.relinearize(ev.multiply(h, r), keys));
+                h.scale = scale;
+                tmp.scale = scale;
+                h = ev.mod_switch_to(h, tmp.limbs);
+                h = ev.add(h, tmp);
+            }
+            return ev.rescale_to_next(ev.multiply_plain(h, ev.encode(2.0, h.limbs, scale)));
+        }
+
+        // invert_sqrt: layernorm.hpp:145-155
+        Ct invert_sqrt(const Evaluator &ev, const Ct &x, int d_newt, int d_gold, const Keys &keys)
+        {
+            Ct res = eval_line(ev, x, -1.29054537e-04, 1.29054537e-01);
+            Ct y = newton_iter(ev, x, res, d_newt, keys);
+            return goldschmidt_iter(ev, x, y, d_gold, keys);
+        }
+    } // namespace
+
+    // layernorm / layernorm2: M/source/non_linear_func/layernorm.hpp:157-351, 353-547.  variant 1
+    // uses 1/768^2 and gamma/sqrt(768); variant 2 uses 1/768^3 and gamma/768 (:271,329 vs :467,525).
+    Ct layernorm(const Evaluator &ev, const Ct &x, const std::vector<double> &gamma, const std::vector<double> &beta,
+                 const std::vector<int> &bias_vec, const Keys &keys, int variant)
+    {
+        MOAI_REQUIRE(x.size == 2, "layernorm expects size-2 ciphertexts");
+        MOAI_REQUIRE((long long)gamma.size() == x.batch && (long long)beta.size() == x.batch,
+                     "gamma/beta size must equal the number of ciphertexts");
+        MOAI_REQUIRE(bias_vec.size() == ev.n() / 2, "bias_vec must have one entry per slot");
+        const double scale = x.scale;
+        const long long num_ct = x.batch;
+        const double nd = 768.0; // the reference hard-codes 768 in every constant
+        Ct ave_x = ev.sum_batch(x);
+        Ct nx = ev.rescale_to_next(ev.multiply_plain(x, ev.encode(masked(bias_vec, nd), x.limbs, x.scale)));
+        nx.scale = scale;
+        ave_x = ev.mod_switch_to(ave_x, nx.limbs);
+        ave_x.scale = scale;
+        // var = sum_i (nx_i - u)^2 accumulated at size 3, ONE relinearization (layernorm.hpp:245-266)
+        Ct var = ev.rescale_to_next(ev.relinearize(ev.sum_sub_square(nx, ave_x), keys));
+        const double inv_n = variant == 1 ? 1 / (nd * nd) : 1 / (nd * nd * nd);
+        var = ev.rescale_to_next(ev.multiply_plain(var, ev.encode(masked(bias_vec, inv_n), var.limbs, var.scale)));
+        Ct inv_sqrt_var = invert_sqrt(ev, var, 4, 2, keys);
+        ave_x = ev.mod_switch_to(ave_x, inv_sqrt_var.limbs);
+        Ct out = ev.sub(ev.mod_switch_to(nx, inv_sqrt_var.limbs), ave_x);
+        out = ev.rescale_to_next(ev.relinearize(ev.multiply(out, inv_sqrt_var), keys));
+        // per-ciphertext masked gamma' and beta plaintexts, encoded as one batch
+        const size_t slots = bias_vec.size();
+        std::vector<std::complex<double>> vals((size_t)num_ct * slots, 0.0);
+        for (long long i = 0; i < num_ct; i++)
+        {
+            const double g = variant == 1 ? gamma[i] / std::sqrt(nd) : gamma[i] / nd;
+            for (size_t j = 0; j < slots; j++)
+            {
+                if (bias_vec[j] == 1)
+                {
+                    vals[(size_t)i * slots + j] = g;
+                }
+            }
+        }
+        out = ev.rescale_to_next(
+            ev.multiply_plain(out, ev.encode_batch(vals.data(), num_ct, (int)slots, out.limbs, out.scale)));
+        for (long long i = 0; i < num_ct; i++)
+        {
+            for (size_t j = 0; j < slots; j++)
+            {
+                vals[(size_t)i * slots + j] = bias_vec[j] == 1 ? beta[i] : 0.0;
+            }
+        }
+        return ev.add_plain(out, ev.encode_batch(vals.data(), num_ct, (int)slots, out.limbs, out.scale));
+    }
+
+    // ------------------------------------------------------------------------------------ softmax pieces
+    // exp: M/source/non_linear_func/softmax.hpp:9-47 — (1 + x/128)^128
+    Ct exp_128(const Evaluator &ev, const Ct &x, const Keys &keys)
+    {
+        Ct out = ev.rescale_to_next(ev.multiply_plain(x, ev.encode(0.0078125, x.limbs, x.scale)));
+        out = ev.add_plain(out, ev.encode(1.0, out.limbs, out.scale));
+        for (int i = 0; i < 7; ++i) // i < log2(128)
+        {
+            out = ev.rescale_to_next(ev.relinearize(ev.square(out), keys));
+        }
+        return out;
+    }
+
+    // inverse: softmax.hpp:49-82 — Goldschmidt product prod (1 + y^(2^i)), y = 1 - x
+    Ct inverse(const Evaluator &ev, const Ct &x, const Keys &keys, int iter)
+    {
+        Pt one = ev.encode(1.0, x.limbs, x.scale);
+        Ct y = ev.negate(ev.sub_plain(x, one));
+        Ct res = ev.add_plain(y, one);
+        for (int i = 0; i < iter; ++i)
+        {
+            y = ev.rescale_to_next(ev.relinearize(ev.square(y), keys));
+            Ct tmp = ev.add_plain(y, ev.encode(1.0, y.limbs, y.scale));
+            res = ev.mod_switch_to(res, tmp.limbs);
+            res = ev.rescale_to_next(ev.relinearize(ev.multiply(res, tmp), keys));
+        }
+        return res;
+    }
+
+    // ------------------------------------------------------------------------------------ ct-ct matmuls
+    // ct_ct_matrix_mul_colpacking: M/source/matrix_mul/Ct_ct_matrix_mul.hpp:5-55
+    //   out[i] = rescale(relin( sum_j X[j] (x) rot(W[j], i * num_batch) )), i < row_X, j < col_X
+    Ct ct_ct_matrix_mul_colpacking(const Evaluator &ev, const Ct &X, const Ct &W, const Keys &keys, int col_X, int row_X,
+                                   int col_W, int row_W, int num_batch)
+    {
+        MOAI_REQUIRE(col_X == col_W && row_X == row_W, "bad dimensions of X or W");
+        MOAI_REQUIRE(X.batch == col_X && W.batch == col_X, "bad dimensions of X or W");
+        const double scale = X.scale;
+        Ct acc = ev.alloc(row_X, 3, X.limbs, X.scale * W.scale);
+        for (int i = 0; i < row_X; ++i)
+        {
+            Ct w = i > 0 ? ev.rotate_vector(W, i * num_batch, keys) : W; // all col_X columns in one batch
+            Ct s = ev.inner_product(X, w);
+            ev.copy_into(s, acc, i);
+        }
+        Ct out = ev.rescale_to_next(ev.relinearize(acc, keys));
+        out.scale = scale;
+        return out;
+    }
+
+    // ct_ct_matrix_mul_diagpacking: Ct_ct_matrix_mul.hpp:57-156 — baby-step/giant-step product of the
+    // diagonal-packed X (row_X ciphertexts) with the column-packed W (col_W ciphertexts).
+    Ct ct_ct_matrix_mul_diagpacking(const Evaluator &ev, const Ct &X, const Ct &W, const Keys &keys, int col_X,
+                                    int row_X, int col_W, int row_W, int num_batch)
+    {
+        MOAI_REQUIRE(X.batch == row_X && W.batch == col_W, "bad dimensions of X or W");
+        (void)row_W;
+        const double scale = X.scale;
+        int g = (int)std::sqrt((double)col_X);
+        if (g * g < col_X)
+        {
+            g++;
+        }
+        int b = col_X / g;
+        if (b * g < col_X)
+        {
+            b++;
+        }
+        // rotate X: group i (g consecutive diagonals) is rotated by (col_X - i*g) * num_batch
+        Ct rotX = ev.alloc(row_X, 2, X.limbs, X.scale);
+        for (int i = 0; i < b; ++i)
+        {
+            const int first = i * g;
+            if (first >= row_X)
+            {
+                break;
+            }
+            const int cnt = std::min(g, row_X - first);
+            Ct grp = ev.view(X, first, cnt);
+            const int rot_ind = (col_X - i * g) * num_batch;
+            Ct r = rot_ind != col_X * num_batch ? ev.rotate_vector(grp, rot_ind, keys) : grp;
+            ev.copy_into(r, rotX, first);
+        }
+        // baby steps of every output column at once: c_g[k] = rot(W, k * num_batch), batch = col_W
+        std::vector<Ct> c_g(g);
+        c_g[0] = W;
+        for (int k = 1; k < g; ++k)
+        {
+            c_g[k] = ev.rotate_vector(W, k * num_batch, keys);
+        }
+        // giant steps: out[j] = sum_k c_g[k] (x) rotX[j*g + k]   (size 3, one relin + rescale per j)
+        Ct output;
+        for (int j = 0; j < b; ++j)
+        {
+            Ct acc;
+            for (int k = 0; k < g; ++k)
+            {
+                const int index = j * g + k;
+                if (index >= col_X)
+                {
+                    break;
+                }
+                Ct xk = ev.view(rotX, index, 1);
+                if (k == 0)
+                {
+                    acc = ev.multiply(c_g[k], xk);
+                }
+                else
+                {
+                    ev.multiply_accumulate(acc, c_g[k], xk);
+                }
+            }
+            Ct o = ev.rescale_to_next(ev.relinearize(acc, keys));
+            o.scale = scale;
+            if (j == 0)
+            {
+                output = o;
+            }
+            else
+            {
+                o = ev.rotate_vector(o, j * g * num_batch, keys);
+                ev.add_inplace(output, o);
+            }
+        }
+        return output;
+    }
+} // namespace moai

@@ -25,9 +25,8 @@ namespace moai
         }
 
         // ------------------------------------------------------------------ add / sub / negate
-        __global__ void k_addsub(int op, const ulonglong2 *__restrict__ a, const ulonglong2 *__restrict__ b,
-                                 ulonglong2 *__restrict__ out, long long total2, int log_n2, int limbs,
-                                 const LimbConst *__restrict__ lcs)
+        __global__ void k_addsub(int op, const ulonglong2 *a, const ulonglong2 *__restrict__ b, ulonglong2 *out, long long total2, int log_n2, int limbs,
+                                 const LimbConst *__restrict__ lcs, long long b_period2)
         {
             long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
             if (i >= total2)
@@ -44,7 +43,7 @@ namespace moai
             }
             else
             {
-                ulonglong2 y = b[i];
+                ulonglong2 y = b[b_period2 ? i % b_period2 : i];
                 if (op == EW_ADD)
                 {
                     r.x = addmod(x.x, y.x, q);
@@ -147,7 +146,7 @@ namespace moai
         // (a0, a1) x (b0, b1) -> (a0 b0, a0 b1 + a1 b0, a1 b1); one thread per coefficient pair of a limb
         __global__ void k_multiply(const ulonglong2 *__restrict__ a, const ulonglong2 *__restrict__ b,
                                    ulonglong2 *__restrict__ out, long long total2, int log_n2, int limbs,
-                                   const LimbConst *__restrict__ lcs, int accumulate, int square)
+                                   const LimbConst *__restrict__ lcs, int accumulate, int square, int b_bcast)
         {
             long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; // over [batch][limbs][n/2]
             if (i >= total2)
@@ -163,7 +162,8 @@ namespace moai
             const long long off_in = bt * 2 * poly2 + ((long long)limb << log_n2) + within;
             const long long off_out = bt * 3 * poly2 + ((long long)limb << log_n2) + within;
             ulonglong2 a0 = a[off_in], a1 = a[off_in + poly2];
-            ulonglong2 b0 = square ? a0 : b[off_in], b1 = square ? a1 : b[off_in + poly2];
+            const long long off_b = b_bcast ? ((long long)limb << log_n2) + within : off_in;
+            ulonglong2 b0 = square ? a0 : b[off_b], b1 = square ? a1 : b[off_b + poly2];
             ulonglong2 r0, r1, r2;
             r0.x = mulmod(a0.x, b0.x, lc);
             r0.y = mulmod(a0.y, b0.y, lc);
@@ -322,6 +322,99 @@ namespace moai
             out[i] = in[i - within + table[within]];
         }
 
+        // out[per_ct] = sum over the batch of a[b][per_ct]  (modular; lazy 64-bit partial sums)
+        __global__ void k_sum_batch(const ulonglong2 *__restrict__ a, ulonglong2 *__restrict__ out, long long per_ct2,
+                                    long long batch, int log_n2, int limbs, const LimbConst *__restrict__ lcs)
+        {
+            long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= per_ct2)
+            {
+                return;
+            }
+            const int limb = (int)((i >> log_n2) % limbs);
+            const LimbConst lc = lcs[limb];
+            u64 sx = 0, sy = 0;
+            for (long long b = 0; b < batch; b++)
+            {
+                const ulonglong2 v = a[b * per_ct2 + i];
+                sx += v.x; // q < 2^61: up to 8 canonical residues fit in 64 bits
+                sy += v.y;
+                if ((b & 7) == 7)
+                {
+                    sx = reduce64(sx, lc);
+                    sy = reduce64(sy, lc);
+                }
+            }
+            ulonglong2 r;
+            r.x = reduce64(sx, lc);
+            r.y = reduce64(sy, lc);
+            out[i] = r;
+        }
+
+        // out3 = sum_j a[j] (x) b[j]  (size-2 x size-2 -> size-3, summed over the batch): the inner loop
+        // of ct_ct_matrix_mul_colpacking (M/source/matrix_mul/Ct_ct_matrix_mul.hpp:33-41) without
+        // materialising the 64 size-3 products.  128-bit lazy sums: 2 * batch * q^2 must stay < 2^128.
+        // mode 1: b is ONE ciphertext m and the terms are (a[j] - m)^2  (LayerNorm's variance sum,
+        // M/source/non_linear_func/layernorm.hpp:245-260).
+        __global__ void k_inner_product(const ulonglong2 *__restrict__ a, const ulonglong2 *__restrict__ b,
+                                        ulonglong2 *__restrict__ out, long long batch, int log_n2, int limbs, int mode,
+                                        const LimbConst *__restrict__ lcs, const Twiddle *__restrict__ two64)
+        {
+            long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; // over [limbs][n/2]
+            const int limb = (int)(i >> log_n2);
+            if (limb >= limbs)
+            {
+                return;
+            }
+            const LimbConst lc = lcs[limb];
+            const Twiddle t64 = two64[limb];
+            const long long poly2 = (long long)limbs << log_n2;
+            u128 s0x{ 0, 0 }, s0y{ 0, 0 }, s1x{ 0, 0 }, s1y{ 0, 0 }, s2x{ 0, 0 }, s2y{ 0, 0 };
+            ulonglong2 m0, m1;
+            if (mode == 1)
+            {
+                m0 = b[i];
+                m1 = b[i + poly2];
+            }
+            for (long long j = 0; j < batch; j++)
+            {
+                ulonglong2 a0 = a[j * 2 * poly2 + i], a1 = a[j * 2 * poly2 + poly2 + i];
+                ulonglong2 b0, b1;
+                if (mode == 1)
+                {
+                    a0.x = submod(a0.x, m0.x, lc.q);
+                    a0.y = submod(a0.y, m0.y, lc.q);
+                    a1.x = submod(a1.x, m1.x, lc.q);
+                    a1.y = submod(a1.y, m1.y, lc.q);
+                    b0 = a0;
+                    b1 = a1;
+                }
+                else
+                {
+                    b0 = b[j * 2 * poly2 + i];
+                    b1 = b[j * 2 * poly2 + poly2 + i];
+                }
+                mac_wide(s0x, a0.x, b0.x);
+                mac_wide(s0y, a0.y, b0.y);
+                mac_wide(s1x, a0.x, b1.x);
+                mac_wide(s1x, a1.x, b0.x);
+                mac_wide(s1y, a0.y, b1.y);
+                mac_wide(s1y, a1.y, b0.y);
+                mac_wide(s2x, a1.x, b1.x);
+                mac_wide(s2y, a1.y, b1.y);
+            }
+            ulonglong2 r;
+            r.x = barrett_reduce_acc(s0x, lc, t64.w, t64.wq);
+            r.y = barrett_reduce_acc(s0y, lc, t64.w, t64.wq);
+            out[i] = r;
+            r.x = barrett_reduce_acc(s1x, lc, t64.w, t64.wq);
+            r.y = barrett_reduce_acc(s1y, lc, t64.w, t64.wq);
+            out[i + poly2] = r;
+            r.x = barrett_reduce_acc(s2x, lc, t64.w, t64.wq);
+            r.y = barrett_reduce_acc(s2y, lc, t64.w, t64.wq);
+            out[i + 2 * poly2] = r;
+        }
+
         // ------------------------------------------------------------------ key switch pieces
         // ext[b][I][J][n] = d[b][J][n] mod m_I   (I over {q_0..q_{l-1}, p})
         __global__ void k_ks_expand(const ulonglong2 *__restrict__ d, ulonglong2 *__restrict__ ext, long long total2,
@@ -384,7 +477,8 @@ namespace moai
     } // namespace
 
     // ====================================================================== launchers
-    void ew_addsub(Context *c, int op, const u64 *a, const u64 *b, u64 *out, long long batch, int polys, int limbs)
+    void ew_addsub(Context *c, int op, const u64 *a, const u64 *b, u64 *out, long long batch, int polys, int limbs,
+                   bool b_broadcast)
     {
         const long long total2 = batch * polys * limbs * (long long)(c->n / 2);
         if (!total2)
@@ -393,7 +487,8 @@ namespace moai
         }
         k_addsub<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
             op, reinterpret_cast<const ulonglong2 *>(a), reinterpret_cast<const ulonglong2 *>(b),
-            reinterpret_cast<ulonglong2 *>(out), total2, c->log_n - 1, limbs, c->d_limb);
+            reinterpret_cast<ulonglong2 *>(out), total2, c->log_n - 1, limbs, c->d_limb,
+            b_broadcast ? (long long)polys * limbs * (long long)(c->n / 2) : 0);
         c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
     }
@@ -464,7 +559,8 @@ namespace moai
         scalar_op(c, 1, ct, h_consts, out, batch, polys, limbs);
     }
 
-    void ew_multiply(Context *c, const u64 *a, const u64 *b, u64 *out3, long long batch, int limbs, bool accumulate)
+    void ew_multiply(Context *c, const u64 *a, const u64 *b, u64 *out3, long long batch, int limbs, bool accumulate,
+                     bool b_broadcast)
     {
         const long long total2 = batch * limbs * (long long)(c->n / 2);
         if (!total2)
@@ -473,7 +569,8 @@ namespace moai
         }
         k_multiply<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
             reinterpret_cast<const ulonglong2 *>(a), reinterpret_cast<const ulonglong2 *>(b),
-            reinterpret_cast<ulonglong2 *>(out3), total2, c->log_n - 1, limbs, c->d_limb, accumulate ? 1 : 0, 0);
+            reinterpret_cast<ulonglong2 *>(out3), total2, c->log_n - 1, limbs, c->d_limb, accumulate ? 1 : 0, 0,
+            b_broadcast ? 1 : 0);
         c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
     }
@@ -487,7 +584,28 @@ namespace moai
         }
         k_multiply<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
             reinterpret_cast<const ulonglong2 *>(a), reinterpret_cast<const ulonglong2 *>(a),
-            reinterpret_cast<ulonglong2 *>(out3), total2, c->log_n - 1, limbs, c->d_limb, 0, 1);
+            reinterpret_cast<ulonglong2 *>(out3), total2, c->log_n - 1, limbs, c->d_limb, 0, 1, 0);
+        c->launches += 1;
+        MOAI_CUDA_CHECK(cudaGetLastError());
+    }
+
+    void sum_batch(Context *c, const u64 *a, u64 *out, long long batch, int polys, int limbs)
+    {
+        const long long per_ct2 = (long long)polys * limbs * (long long)(c->n / 2);
+        k_sum_batch<<<grid_for(per_ct2), EW_THREADS, 0, c->stream>>>(reinterpret_cast<const ulonglong2 *>(a),
+                                                                   reinterpret_cast<ulonglong2 *>(out), per_ct2, batch,
+                                                                   c->log_n - 1, limbs, c->d_limb);
+        c->launches += 1;
+        MOAI_CUDA_CHECK(cudaGetLastError());
+    }
+
+    void inner_product(Context *c, const u64 *a, const u64 *b, u64 *out3, long long batch, int limbs, int mode)
+    {
+        MOAI_REQUIRE(batch <= 1024, "inner product batch too large for the lazy accumulator");
+        const long long total2 = (long long)limbs * (long long)(c->n / 2);
+        k_inner_product<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
+            reinterpret_cast<const ulonglong2 *>(a), reinterpret_cast<const ulonglong2 *>(b),
+            reinterpret_cast<ulonglong2 *>(out3), batch, c->log_n - 1, limbs, mode, c->d_limb, c->d_two64);
         c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
     }

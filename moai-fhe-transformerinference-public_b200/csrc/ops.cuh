@@ -13,7 +13,12 @@ namespace moai
         EW_NEG = 2,
     };
 
-    void ew_addsub(Context *c, int op, const u64 *a, const u64 *b, u64 *out, long long batch, int polys, int limbs);
+    // b_broadcast: b is ONE ciphertext applied to every batch item of a
+    void ew_addsub(Context *c, int op, const u64 *a, const u64 *b, u64 *out, long long batch, int polys, int limbs,
+                   bool b_broadcast = false);
+    void sum_batch(Context *c, const u64 *a, u64 *out, long long batch, int polys, int limbs);
+    // mode 0: out3 = sum_j a[j] (x) b[j];  mode 1: out3 = sum_j (a[j] - b)^2 with b one ciphertext
+    void inner_product(Context *c, const u64 *a, const u64 *b, u64 *out3, long long batch, int limbs, int mode);
     // ct (+/-) pt on poly 0; pt_stride = elements between the plaintexts of consecutive batch items (0 = broadcast)
     void ew_addsub_plain(Context *c, int op, const u64 *ct, const u64 *pt, u64 *out, long long batch, int polys,
                          int limbs, long long pt_stride);
@@ -23,7 +28,8 @@ namespace moai
     void ew_multiply_scalar(Context *c, const u64 *ct, const u64 *h_consts, u64 *out, long long batch, int polys,
                             int limbs);
     void ew_add_scalar(Context *c, const u64 *ct, const u64 *h_consts, u64 *out, long long batch, int polys, int limbs);
-    void ew_multiply(Context *c, const u64 *a, const u64 *b, u64 *out3, long long batch, int limbs, bool accumulate);
+    void ew_multiply(Context *c, const u64 *a, const u64 *b, u64 *out3, long long batch, int limbs, bool accumulate,
+                     bool b_broadcast = false);
     void ew_square(Context *c, const u64 *a, u64 *out3, long long batch, int limbs);
 
     void rescale(Context *c, const u64 *in, u64 *out, long long batch, int polys, int limbs);

@@ -433,3 +433,35 @@ class SealRef:
         self._chk(self.lib.ref_ct_pt_matmul(self.h, C.c_int(variant), _p(X), _p(W, f64p), m, C.c_int(K), C.c_int(Cc),
                                             C.c_int(limbs), C.c_double(scale), _p(out), C.byref(sec)))
         return out, sec.value
+
+    def galois_elts(self):
+        buf = (C.c_uint32 * 4096)()
+        k = self.lib.ref_galois_elts(self.h, buf, C.c_int(4096))
+        return [int(buf[i]) for i in range(k)]
+
+    def gelu_v2(self, x, count, limbs, scale):
+        out = np.zeros(count * 2 * limbs * self.n, dtype=np.uint64)
+        ol, osc = C.c_int(0), C.c_double(0)
+        self._chk(self.lib.ref_gelu_v2(self.h, _p(x), C.c_int(count), C.c_int(limbs), C.c_double(scale), _p(out),
+                                       C.byref(ol), C.byref(osc)))
+        return out[: count * 2 * ol.value * self.n].copy(), ol.value, osc.value
+
+    def layernorm(self, variant, x, num_ct, limbs, scale, gamma, beta, bias_vec):
+        out = np.zeros(num_ct * 2 * limbs * self.n, dtype=np.uint64)
+        ol, osc = C.c_int(0), C.c_double(0)
+        g = np.ascontiguousarray(gamma, dtype=np.float64)
+        b = np.ascontiguousarray(beta, dtype=np.float64)
+        bv = np.ascontiguousarray(bias_vec, dtype=np.int32)
+        self._chk(self.lib.ref_layernorm(self.h, C.c_int(variant), _p(x), C.c_int(num_ct), C.c_int(limbs),
+                                         C.c_double(scale), _p(g, f64p), _p(b, f64p), _p(bv, i32p), _p(out),
+                                         C.byref(ol), C.byref(osc)))
+        return out[: num_ct * 2 * ol.value * self.n].copy(), ol.value, osc.value
+
+    def ct_ct_matmul(self, which, X, nX, W, nW, limbs, scale_X, scale_W, col_X, row_X, col_W, row_W, num_batch):
+        out = np.zeros(max(row_X, col_W) * 2 * limbs * self.n, dtype=np.uint64)
+        oc, ol, osc = C.c_int(0), C.c_int(0), C.c_double(0)
+        self._chk(self.lib.ref_ct_ct_matmul(self.h, C.c_int(which), _p(X), C.c_int(nX), _p(W), C.c_int(nW),
+                                            C.c_int(limbs), C.c_double(scale_X), C.c_double(scale_W), C.c_int(col_X),
+                                            C.c_int(row_X), C.c_int(col_W), C.c_int(row_W), C.c_int(num_batch),
+                                            _p(out), C.byref(oc), C.byref(ol), C.byref(osc)))
+        return out[: oc.value * 2 * ol.value * self.n].copy(), oc.value, ol.value, osc.value

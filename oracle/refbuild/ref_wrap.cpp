@@ -22,6 +22,10 @@
 
 // The reference's own module code, unmodified (M/source/matrix_mul/Ct_pt_matrix_mul.hpp).
 #include "source/matrix_mul/Ct_pt_matrix_mul.hpp"
+#include "source/matrix_mul/Ct_ct_matrix_mul.hpp"
+#include "source/non_linear_func/layernorm.hpp"
+#include "source/non_linear_func/gelu_others.hpp"
+#include <sstream>
 
 using namespace seal;
 using namespace std;
@@ -611,6 +615,117 @@ extern "C"
             memcpy(out + size_t(i) * outsz, res[i].data(), outsz * sizeof(uint64_t));
         }
         REF_CATCH(r)
+    }
+
+    // The reference's modules print debug decryptions to std::cout; silence them while they run.
+    struct CoutMute
+    {
+        std::streambuf *old;
+        std::ostringstream sink;
+        CoutMute() : old(std::cout.rdbuf(sink.rdbuf()))
+        {}
+        ~CoutMute()
+        {
+            std::cout.rdbuf(old);
+        }
+    };
+
+    // gelu_v2 (M/source/non_linear_func/gelu_others.hpp:4-154) on `count` ciphertexts [count][2][limbs][n]
+    int ref_gelu_v2(void *h, const uint64_t *x, int count, int limbs, double scale, uint64_t *out, int *out_limbs,
+                    double *out_scale)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        CoutMute mute;
+        size_t ctsz = size_t(2) * limbs * r->n;
+        for (int i = 0; i < count; i++)
+        {
+            Ciphertext ct;
+            load_ct(*r, x + size_t(i) * ctsz, 2, limbs, scale, ct);
+            Ciphertext res = gelu_v2(ct, *r->ctx, r->rlk, r->sk);
+            *out_limbs = int(res.coeff_modulus_size());
+            *out_scale = res.scale();
+            memcpy(out + size_t(i) * 2 * res.coeff_modulus_size() * r->n, res.data(),
+                   2 * res.coeff_modulus_size() * r->n * sizeof(uint64_t));
+        }
+        REF_CATCH(r)
+    }
+
+    // layernorm / layernorm2 (M/source/non_linear_func/layernorm.hpp:157-547); variant 1 or 2
+    int ref_layernorm(void *h, int variant, const uint64_t *x, int num_ct, int limbs, double scale, const double *gamma,
+                      const double *beta, const int *bias_vec, uint64_t *out, int *out_limbs, double *out_scale)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        CoutMute mute;
+        size_t ctsz = size_t(2) * limbs * r->n;
+        vector<Ciphertext> xs(num_ct);
+        for (int i = 0; i < num_ct; i++)
+        {
+            load_ct(*r, x + size_t(i) * ctsz, 2, limbs, scale, xs[i]);
+        }
+        vector<double> g(gamma, gamma + num_ct), b(beta, beta + num_ct);
+        vector<int> bv(bias_vec, bias_vec + r->n / 2);
+        vector<Ciphertext> res = variant == 1 ? layernorm(xs, g, b, bv, *r->ctx, r->rlk, r->sk)
+                                              : layernorm2(xs, g, b, bv, *r->ctx, r->rlk, r->sk);
+        for (int i = 0; i < num_ct; i++)
+        {
+            *out_limbs = int(res[i].coeff_modulus_size());
+            *out_scale = res[i].scale();
+            memcpy(out + size_t(i) * 2 * res[i].coeff_modulus_size() * r->n, res[i].data(),
+                   2 * res[i].coeff_modulus_size() * r->n * sizeof(uint64_t));
+        }
+        REF_CATCH(r)
+    }
+
+    // ct_ct_matrix_mul_colpacking (which = 0) / _diagpacking (which = 1)
+    // (M/source/matrix_mul/Ct_ct_matrix_mul.hpp:5-156)
+    int ref_ct_ct_matmul(void *h, int which, const uint64_t *X, int nX, const uint64_t *W, int nW, int limbs,
+                         double scale_X, double scale_W, int col_X, int row_X, int col_W, int row_W, int num_batch,
+                         uint64_t *out, int *out_count, int *out_limbs, double *out_scale)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        CoutMute mute;
+        size_t ctsz = size_t(2) * limbs * r->n;
+        vector<Ciphertext> xs(nX), ws(nW);
+        for (int i = 0; i < nX; i++)
+        {
+            load_ct(*r, X + size_t(i) * ctsz, 2, limbs, scale_X, xs[i]);
+        }
+        for (int i = 0; i < nW; i++)
+        {
+            load_ct(*r, W + size_t(i) * ctsz, 2, limbs, scale_W, ws[i]);
+        }
+        vector<Ciphertext> res =
+            which == 0 ? ct_ct_matrix_mul_colpacking(xs, ws, r->glk, r->rlk, *r->ctx, col_X, row_X, col_W, row_W, num_batch)
+                       : ct_ct_matrix_mul_diagpacking(xs, ws, r->glk, r->rlk, *r->ctx, col_X, row_X, col_W, row_W,
+                                                      num_batch);
+        *out_count = int(res.size());
+        for (size_t i = 0; i < res.size(); i++)
+        {
+            *out_limbs = int(res[i].coeff_modulus_size());
+            *out_scale = res[i].scale();
+            memcpy(out + i * 2 * res[i].coeff_modulus_size() * r->n, res[i].data(),
+                   2 * res[i].coeff_modulus_size() * r->n * sizeof(uint64_t));
+        }
+        REF_CATCH(r)
+    }
+
+    // all Galois elements currently present (so the same key set can be uploaded to the GPU)
+    int ref_galois_elts(void *h, uint32_t *out, int cap)
+    {
+        auto r = static_cast<Ref *>(h);
+        int k = 0;
+        auto &d = r->glk.data();
+        for (size_t i = 0; i < d.size(); i++)
+        {
+            if (!d[i].empty() && k < cap)
+            {
+                out[k++] = uint32_t(2 * i + 1);
+            }
+        }
+        return k;
     }
 
     int ref_omp_threads()
