@@ -58,3 +58,34 @@ def oracle_moai():
 @pytest.fixture(scope="session")
 def backend_moai(pkg, oracle_moai):
     return pkg.Backend(16, oracle_moai.q)
+
+
+DEEP_BITS = [40] + [30] * 20 + [40]  # 21 data primes: enough depth for LayerNorm (20 levels) at logN = 12
+
+
+@pytest.fixture(scope="session")
+def sealref_deep():
+    """Real SEAL with a 21-level chain, relinearization key and every power-of-two Galois key
+    (what KeyGenerator::create_galois_keys() without arguments provides, S/util/galois.cpp:106-131)."""
+    from oracle import SealRef, have_ref
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    r = SealRef(SMALL_LOGN, DEEP_BITS, hamming_weight=64, seed=21)
+    r.make_relin_key()
+    steps = []
+    for k in range(0, 11):
+        steps += [1 << k, -(1 << k)]
+    r.make_galois_keys(steps, conjugate=True)
+    return r
+
+
+@pytest.fixture(scope="session")
+def backend_deep(pkg, sealref_deep):
+    return pkg.Backend(SMALL_LOGN, sealref_deep.q)
+
+
+@pytest.fixture(scope="session")
+def keys_deep(pkg, backend_deep, sealref_deep):
+    r, be = sealref_deep, backend_deep
+    gal = {e: pkg.to_device(r.export_galois_key(e)) for e in r.galois_elts()}
+    return be.make_keys(relin=pkg.to_device(r.export_relin_key()), galois=gal)
