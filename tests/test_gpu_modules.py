@@ -42,10 +42,11 @@ def test_gelu_v2_vs_reference(pkg, backend_deep, sealref_deep, keys_deep):
 def test_layernorm_vs_reference(pkg, backend_deep, sealref_deep, keys_deep, variant):
     r, be = sealref_deep, backend_deep
     rng = np.random.default_rng(10 + variant)
-    limbs, num_ct = 21, 6
+    limbs, num_ct = 21, 768                 # the reference hard-codes 768 = 48 x 16 (layernorm.hpp:242-262)
     mask = np.zeros(r.n // 2, dtype=np.int32)
     mask[::16][:5] = 1                      # 5 valid token slots, like the reference run
-    x, _ = encrypt_batch(r, rng, num_ct, limbs, sigma=0.3, mask=mask)
+    x16, _ = encrypt_batch(r, rng, 16, limbs, sigma=0.3, mask=mask)
+    x = np.ascontiguousarray(np.tile(x16, (num_ct // 16, 1, 1, 1)))   # 16 distinct encryptions, tiled
     gamma, beta = rng.normal(size=num_ct), rng.normal(size=num_ct) * 0.1
     exp, el, es = r.layernorm(variant, x.reshape(-1), num_ct, limbs, SCALE, gamma, beta, mask)
     got, gs = be.layernorm(keys_deep, pkg.to_device(x), SCALE, gamma, beta, mask, variant=variant)
