@@ -69,6 +69,26 @@ int32_t moai_ct_ct_matrix_mul_diagpacking(moai_context *ctx, moai_keys *keys, co
                                           int32_t col_X, int32_t row_X, int32_t col_W, int32_t row_W,
                                           int32_t num_batch, uint64_t *out, int32_t *out_limbs, double *out_scale);
 
+/* ---- C1-C5: Bootstrapper (M/source/bootstrapping/Bootstrapper.{h,cpp}) --------------------------
+ * create = constructor + prepare_mod_polynomial + generate_LT_coefficient_3 (Bootstrapper.h:15-221;
+ * driver: M/test/test_full_scheme.hpp:413-448): total_limbs = data limbs after ModRaise (35),
+ * final_scale = 2^46, boundary_K = 25, deg = 59, double_angles = scale_factor = 2, log_width = loge = 10.
+ * required_steps = addLeftRotKeys_Linear_to_vector_3 (Bootstrapper.cpp:89-185): the rotation steps
+ * whose Galois keys make the linear transforms run without SEAL's NAF fallback.
+ * moai_bootstrap = Bootstrapper::bootstrap_3 (Bootstrapper.cpp:3496-3502) on a batch: in
+ * [batch][2][1][N] at chain_index 0 -> out [batch][2][total_limbs-14][N], *out_scale = final_scale. */
+typedef struct moai_bootstrapper moai_bootstrapper;
+int32_t moai_bootstrapper_create(moai_context *ctx, int32_t total_limbs, double final_scale, int32_t boundary_K,
+                                 int32_t deg, int32_t double_angles, int32_t log_width, moai_bootstrapper **out);
+int32_t moai_bootstrapper_destroy(moai_bootstrapper *b);
+int32_t moai_bootstrapper_required_steps(moai_bootstrapper *b, int32_t *steps, int32_t capacity, int32_t *count);
+int32_t moai_bootstrap(moai_context *ctx, moai_bootstrapper *b, moai_keys *keys, const uint64_t *in, int64_t batch,
+                       double scale, uint64_t *out, int32_t *out_limbs, double *out_scale);
+/* host-only inspection of the plan (no GPU): one linear stage's diagonals and the cosine coefficients */
+int32_t moai_bootstrap_plan_debug(int32_t log_n, const uint64_t *primes, int32_t n_key_limbs, int32_t total_limbs,
+                                  int32_t dir, int32_t stage, int32_t *n_diags, int32_t *offsets, double *diag_values,
+                                  double *cheb, int32_t *n_cheb);
+
 #ifdef __cplusplus
 }
 #endif

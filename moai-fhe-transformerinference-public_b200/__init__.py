@@ -401,6 +401,42 @@ class Backend:
                             C.c_int32(col_W), C.c_int32(row_W), C.c_int32(num_batch), out_count=col_W)
 
 
+class Bootstrapper:
+    """Bootstrapper (M/source/bootstrapping/Bootstrapper.h:15-221) bound to one Backend."""
+
+    def __init__(self, be, total_limbs, final_scale=2.0 ** 46, boundary_K=25, deg=59, double_angles=2, log_width=10):
+        self.be = be
+        h = C.c_void_p()
+        be._chk(be.lib.moai_bootstrapper_create(be.h, C.c_int32(total_limbs), C.c_double(final_scale),
+                                                C.c_int32(boundary_K), C.c_int32(deg), C.c_int32(double_angles),
+                                                C.c_int32(log_width), C.byref(h)))
+        self.h = h
+        self.total_limbs = total_limbs
+
+    def required_steps(self):
+        buf = (C.c_int32 * 1024)()
+        cnt = C.c_int32()
+        self.be._chk(self.be.lib.moai_bootstrapper_required_steps(self.h, buf, C.c_int32(1024), C.byref(cnt)))
+        return [int(buf[i]) for i in range(cnt.value)]
+
+    def bootstrap_3(self, keys, x, scale):
+        """x: [batch, 2, 1, n] at chain_index 0 -> ([batch, 2, total_limbs - 14, n], final_scale)."""
+        be = self.be
+        bt, p, l, n = x.shape
+        out = be.empty(bt, 2, self.total_limbs - 14, n)
+        ol, osc = C.c_int32(), C.c_double()
+        be._chk(be.lib.moai_bootstrap(be.h, self.h, keys.h, _ptr(x), C.c_int64(bt), C.c_double(scale), _ptr(out),
+                                      C.byref(ol), C.byref(osc)))
+        assert ol.value == self.total_limbs - 14
+        return out, osc.value
+
+    def __del__(self):
+        try:
+            self.be.lib.moai_bootstrapper_destroy(self.h)
+        except Exception:
+            pass
+
+
 class _KeysHandle:
     def __init__(self, lib, h, keep):
         self.lib, self.h, self.keep = lib, h, keep

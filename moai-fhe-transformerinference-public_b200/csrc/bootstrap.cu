@@ -1,0 +1,620 @@
+// Full-slot CKKS bootstrapping (see bootstrap.hpp for the design and the reference pointers).
+#include "bootstrap.hpp"
+#include <algorithm>
+#include <set>
+
+namespace moai
+{
+    namespace
+    {
+        const double PI = 3.14159265358979323846264338327950288;
+
+        typedef std::map<int, std::vector<cd>> DiagMat; // offset (mod n, in [0,n)) -> diagonal
+
+        // (A * B)[p] : out = A (B in);  diag_{a+b}[p] += A_a[p] * B_b[(p + a) mod n]
+        DiagMat mat_mul(const DiagMat &A, const DiagMat &B, int n)
+        {
+            DiagMat R;
+            for (auto &ka : A)
+            {
+                for (auto &kb : B)
+                {
+                    const int a = ka.first, b = kb.first;
+                    const int d = (a + b) % n;
+                    auto &dst = R[d];
+                    if (dst.empty())
+                    {
+                        dst.assign(n, cd(0, 0));
+                    }
+                    const auto &va = ka.second;
+                    const auto &vb = kb.second;
+                    for (int p = 0; p < n; p++)
+                    {
+                        dst[p] += va[p] * vb[(p + a) % n];
+                    }
+                }
+            }
+            // drop numerically empty diagonals
+            for (auto it = R.begin(); it != R.end();)
+            {
+                double mx = 0;
+                for (auto &z : it->second)
+                {
+                    mx = std::max(mx, std::abs(z));
+                }
+                it = mx == 0 ? R.erase(it) : std::next(it);
+            }
+            return R;
+        }
+
+        // One radix-2 level of the CKKS special FFT on n slots with block length len.
+        //   forward (SlotToCoeff direction):  out[i+j] = u + ksi v, out[i+j+len/2] = u - ksi v
+        //   inverse (CoeffToSlot direction):  out[i+j] = (u + v)/2, out[i+j+len/2] = (u - v) conj(ksi)/2
+        // ksi_j = exp(2 pi i (5^j mod 4 len) / (4 len))   (slot j <-> root zeta^{5^j}, S/ckks.cpp:36-52)
+        DiagMat fft_level(int n, int len, bool inverse)
+        {
+            const int lenh = len / 2, lenq = len * 4;
+            std::vector<cd> ksi(lenh);
+            long long pw = 1;
+            for (int j = 0; j < lenh; j++)
+            {
+                const double ang = 2 * PI * (double)(pw % lenq) / (double)lenq;
+                ksi[j] = cd(std::cos(ang), std::sin(ang));
+                pw = (pw * 5) % lenq; // 5^j mod 4 len
+            }
+            DiagMat M;
+            auto &d0 = M[0];
+            d0.assign(n, cd(0, 0));
+            const int up = lenh % n, dn = (n - lenh) % n;
+            auto &dup = M[up];
+            if (dup.empty())
+            {
+                dup.assign(n, cd(0, 0));
+            }
+            auto &ddn = M[dn];
+            if (ddn.empty())
+            {
+                ddn.assign(n, cd(0, 0));
+            }
+            for (int p = 0; p < n; p++)
+            {
+                const int j = p % len;
+                if (j < lenh)
+                {
+                    if (!inverse)
+                    {
+                        M[0][p] += cd(1, 0);
+                        M[up][p] += ksi[j];
+                    }
+                    else
+                    {
+                        M[0][p] += cd(0.5, 0);
+                        M[up][p] += cd(0.5, 0);
+                    }
+                }
+                else
+                {
+                    const cd k = ksi[j - lenh];
+                    if (!inverse)
+                    {
+                        M[dn][p] += cd(1, 0);
+                        M[0][p] += -k;
+                    }
+                    else
+                    {
+                        M[dn][p] += std::conj(k) * 0.5;
+                        M[0][p] += -std::conj(k) * 0.5;
+                    }
+                }
+            }
+            return M;
+        }
+
+        void scale_mat(DiagMat &M, double f)
+        {
+            for (auto &kv : M)
+            {
+                for (auto &z : kv.second)
+                {
+                    z *= f;
+                }
+            }
+        }
+
+        // Householder least squares (double precision is ample here: the fitted coefficients are O(1))
+        std::vector<double> lstsq(std::vector<double> A, std::vector<double> b, int m, int ncol)
+        {
+            auto at = [&](int r, int cc) -> double & { return A[(size_t)r * ncol + cc]; };
+            for (int k = 0; k < ncol; k++)
+            {
+                double nv = 0;
+                for (int r = k; r < m; r++)
+                {
+                    nv += at(r, k) * at(r, k);
+                }
+                nv = std::sqrt(nv);
+                if (nv == 0)
+                {
+                    continue;
+                }
+                std::vector<double> v(m - k);
+                for (int r = k; r < m; r++)
+                {
+                    v[r - k] = at(r, k);
+                }
+                v[0] += v[0] >= 0 ? nv : -nv;
+                double vn = 0;
+                for (double t : v)
+                {
+                    vn += t * t;
+                }
+                vn = std::sqrt(vn);
+                for (double &t : v)
+                {
+                    t /= vn;
+                }
+                for (int cc = k; cc < ncol; cc++)
+                {
+                    double dot = 0;
+                    for (int r = k; r < m; r++)
+                    {
+                        dot += v[r - k] * at(r, cc);
+                    }
+                    for (int r = k; r < m; r++)
+                    {
+                        at(r, cc) -= 2 * v[r - k] * dot;
+                    }
+                }
+                double dot = 0;
+                for (int r = k; r < m; r++)
+                {
+                    dot += v[r - k] * b[r];
+                }
+                for (int r = k; r < m; r++)
+                {
+                    b[r] -= 2 * v[r - k] * dot;
+                }
+            }
+            std::vector<double> x(ncol, 0.0);
+            for (int k = ncol - 1; k >= 0; k--)
+            {
+                double s = b[k];
+                for (int cc = k + 1; cc < ncol; cc++)
+                {
+                    s -= at(k, cc) * x[cc];
+                }
+                x[k] = s / at(k, k);
+            }
+            return x;
+        }
+    } // namespace
+
+    // ------------------------------------------------------------------------------------ set-up
+    Bootstrapper::Bootstrapper(Context *ctx, const BootParams &p) : prm(p), c_(ctx)
+    {
+        MOAI_REQUIRE(p.total_limbs >= 15 && p.total_limbs <= ctx->kl - 1, "bootstrapping needs at least 15 data limbs");
+        MOAI_REQUIRE(p.deg >= 15 && p.deg <= 63, "cosine degree must be in [15, 63]");
+        build_matrices();
+        fit_cosine();
+    }
+
+    void Bootstrapper::build_matrices()
+    {
+        const int n = slots();
+        int logn = 0;
+        while ((1 << logn) < n)
+        {
+            logn++;
+        }
+        // levels per stage like the reference's 3-way split (Bootstrapper.cpp:90-92)
+        const int d1 = logn / 3, d2 = (logn - d1) / 2, d3 = logn - d1 - d2;
+        const int grp[3] = { d1, d2, d3 };
+        // CoeffToSlot: inverse levels applied len = n, n/2, ..., 2 ; the first applied factor is rightmost
+        {
+            int len = n;
+            for (int s = 0; s < 3; s++)
+            {
+                DiagMat M;
+                for (int k = 0; k < grp[s]; k++, len >>= 1)
+                {
+                    DiagMat Lm = fft_level(n, len, true);
+                    M = M.empty() ? Lm : mat_mul(Lm, M, n);
+                }
+                // fold 1/(2K): 1/2 for the real/imaginary extraction, 1/K to land in [-1, 1]
+                scale_mat(M, std::cbrt(1.0 / (2.0 * prm.boundary_K)));
+                cts_[s].diags.clear();
+                for (auto &kv : M)
+                {
+                    const int off = kv.first > n / 2 ? kv.first - n : kv.first;
+                    cts_[s].diags[off] = kv.second;
+                }
+                cts_[s].limbs = prm.total_limbs - s;
+                plan_bsgs(cts_[s]);
+            }
+        }
+        // SlotToCoeff: forward levels applied len = 2, 4, ..., n (constants folded at encode time)
+        {
+            int len = 2;
+            for (int s = 0; s < 3; s++)
+            {
+                DiagMat M;
+                for (int k = 0; k < grp[2 - s]; k++, len <<= 1)
+                {
+                    DiagMat Lm = fft_level(n, len, false);
+                    M = M.empty() ? Lm : mat_mul(Lm, M, n);
+                }
+                stc_[s].diags.clear();
+                for (auto &kv : M)
+                {
+                    const int off = kv.first > n / 2 ? kv.first - n : kv.first;
+                    stc_[s].diags[off] = kv.second;
+                }
+                stc_[s].limbs = prm.total_limbs - 3 - (6 + prm.double_angles) - s;
+                plan_bsgs(stc_[s]);
+            }
+        }
+    }
+
+    void Bootstrapper::plan_bsgs(LinearStage &st) const
+    {
+        // every offset is a multiple of the smallest non-zero |offset|
+        int stride = 0;
+        for (auto &kv : st.diags)
+        {
+            if (kv.first != 0)
+            {
+                const int a = std::abs(kv.first);
+                stride = stride == 0 ? a : std::min(stride, a);
+            }
+        }
+        stride = stride == 0 ? 1 : stride;
+        for (auto &kv : st.diags)
+        {
+            MOAI_REQUIRE(kv.first % stride == 0, "diagonal offsets are not multiples of a common stride");
+        }
+        const int cnt = (int)st.diags.size();
+        int g = 1;
+        while (g * g < cnt)
+        {
+            g++;
+        }
+        st.stride = stride;
+        st.giant = g;
+        std::set<int> bs, gs;
+        for (auto &kv : st.diags)
+        {
+            const int e = kv.first / stride;
+            const int i = (int)std::floor((double)e / g);
+            const int j = e - i * g;
+            bs.insert(j);
+            gs.insert(i);
+        }
+        st.baby.assign(bs.begin(), bs.end());
+        st.giants.assign(gs.begin(), gs.end());
+    }
+
+    std::vector<int> Bootstrapper::required_steps() const
+    {
+        const int n = slots();
+        std::set<int> steps;
+        for (int dir = 0; dir < 2; dir++)
+        {
+            for (int s = 0; s < 3; s++)
+            {
+                const LinearStage &st = dir == 0 ? cts_[s] : stc_[s];
+                for (int j : st.baby)
+                {
+                    if (j)
+                    {
+                        steps.insert(((j * st.stride) % n + n) % n);
+                    }
+                }
+                for (int i : st.giants)
+                {
+                    if (i)
+                    {
+                        steps.insert(((long long)i * st.giant * st.stride % n + n) % n);
+                    }
+                }
+            }
+        }
+        return std::vector<int>(steps.begin(), steps.end());
+    }
+
+    void Bootstrapper::encode_stage(const Evaluator &ev, LinearStage &st, double pt_scale)
+    {
+        const int n = slots();
+        st.pts.clear();
+        st.pt_scale = pt_scale;
+        // all pre-rotated diagonals of the stage in one batched device encode
+        std::vector<std::pair<int, int>> keys;
+        std::vector<cd> vals;
+        for (auto &kv : st.diags)
+        {
+            const int e = kv.first / st.stride;
+            const int i = (int)std::floor((double)e / st.giant);
+            const int j = e - i * st.giant;
+            const long long G = (long long)i * st.giant * st.stride;
+            keys.push_back({ i, j });
+            // P[p] = diag[(p - G) mod n]
+            for (int p = 0; p < n; p++)
+            {
+                vals.push_back(kv.second[(((long long)p - G) % n + n) % n]);
+            }
+        }
+        Pt all = ev.encode_batch(vals.data(), (long long)keys.size(), n, st.limbs, pt_scale);
+        for (size_t k = 0; k < keys.size(); k++)
+        {
+            Pt one = all;
+            one.d = all.d + k * (size_t)st.limbs * c_->n;
+            one.count = 1;
+            st.pts[keys[k]] = one;
+        }
+    }
+
+    void Bootstrapper::fit_cosine()
+    {
+        // least squares on Chebyshev nodes of every interval [i - w, i + w], |i| < K, y = x / K
+        const int K = prm.boundary_K, deg = prm.deg, pts_per = 8;
+        const double w = std::ldexp(1.0, -prm.log_width);
+        const int m = (2 * K - 1) * pts_per, ncol = deg + 1;
+        std::vector<double> A((size_t)m * ncol), b(m);
+        int row = 0;
+        for (int i = -(K - 1); i <= K - 1; i++)
+        {
+            for (int t = 0; t < pts_per; t++, row++)
+            {
+                const double x = i + w * std::cos(PI * (t + 0.5) / pts_per);
+                const double y = x / K;
+                double t0 = 1, t1 = y;
+                A[(size_t)row * ncol] = 1;
+                A[(size_t)row * ncol + 1] = y;
+                for (int k = 2; k <= deg; k++)
+                {
+                    const double t2 = 2 * y * t1 - t0;
+                    A[(size_t)row * ncol + k] = t2;
+                    t0 = t1;
+                    t1 = t2;
+                }
+                b[row] = std::cos(2 * PI * (x - 0.25) / std::ldexp(1.0, prm.double_angles));
+            }
+        }
+        cheb_ = lstsq(A, b, m, ncol);
+    }
+
+    // ------------------------------------------------------------------------------------ linear transforms
+    Ct Bootstrapper::linear_transform(const Evaluator &ev, const Ct &ct, LinearStage &st, const Keys &keys) const
+    {
+        MOAI_REQUIRE(ct.limbs == st.limbs, "linear stage applied at the wrong level");
+        const long long n = slots();
+        auto norm = [&](long long step) { return (int)(((step % n) + n) % n); }; // left rotation in [0, slots)
+        std::map<int, Ct> rots;
+        for (int j : st.baby)
+        {
+            const int step = norm((long long)j * st.stride);
+            rots[j] = step == 0 ? ct : ev.rotate_vector(ct, step, keys);
+        }
+        Ct acc;
+        for (int i : st.giants)
+        {
+            Ct inner;
+            for (int j : st.baby)
+            {
+                auto it = st.pts.find({ i, j });
+                if (it == st.pts.end())
+                {
+                    continue;
+                }
+                Ct term = ev.multiply_plain(rots[j], it->second);
+                if (inner.empty())
+                {
+                    inner = term;
+                }
+                else
+                {
+                    ev.add_inplace(inner, term);
+                }
+            }
+            if (inner.empty())
+            {
+                continue;
+            }
+            const int gstep = norm((long long)i * st.giant * st.stride);
+            if (gstep != 0)
+            {
+                inner = ev.rotate_vector(inner, gstep, keys);
+            }
+            if (acc.empty())
+            {
+                acc = inner;
+            }
+            else
+            {
+                ev.add_inplace(acc, inner);
+            }
+        }
+        return ev.rescale_to_next(acc);
+    }
+
+    // ------------------------------------------------------------------------------------ EvalMod
+    // Chebyshev series sum coef[k] T_k evaluated to exactly (target_limbs, target_scale).
+    Ct Bootstrapper::eval_cheb(const Evaluator &ev, const std::vector<double> &coef, int target_limbs,
+                               double target_scale, const std::map<int, Ct> &T, const Keys &keys) const
+    {
+        int d = (int)coef.size() - 1;
+        while (d > 0 && coef[d] == 0.0)
+        {
+            d--;
+        }
+        const int kbaby = 8;
+        if (d < kbaby)
+        {
+            // leaf: sum_j c_j T_j, every term brought to (target_limbs + 1) and scaled so that the
+            // rescale lands exactly on target_scale
+            const int lv = target_limbs + 1;
+            const double ql = ev.last_prime(lv);
+            Ct acc;
+            for (int j = 1; j <= d; j++)
+            {
+                if (coef[j] == 0.0)
+                {
+                    continue;
+                }
+                Ct tj = ev.mod_switch_to(T.at(j), lv);
+                Pt cj = ev.encode(coef[j], lv, target_scale * ql / tj.scale);
+                Ct term = ev.multiply_plain(tj, cj);
+                term.scale = target_scale * ql;
+                if (acc.empty())
+                {
+                    acc = term;
+                }
+                else
+                {
+                    ev.add_inplace(acc, term);
+                }
+            }
+            MOAI_REQUIRE(!acc.empty(), "degenerate polynomial leaf");
+            Ct r = ev.rescale_to_next(acc);
+            r.scale = target_scale;
+            return ev.add_plain(r, ev.encode(coef[0], r.limbs, target_scale));
+        }
+        // split at the largest giant g = 8 * 2^m <= d :  p = q * T_g + r
+        int g = kbaby;
+        while (g * 2 <= d)
+        {
+            g *= 2;
+        }
+        std::vector<double> q(d - g + 1, 0.0), r(g, 0.0);
+        for (int i = 0; i < g; i++)
+        {
+            r[i] = coef[i];
+        }
+        q[0] = coef[g];
+        for (int i = g + 1; i <= d; i++)
+        {
+            q[i - g] = 2 * coef[i];          // T_i = 2 T_g T_{i-g} - T_{2g-i}
+            r[2 * g - i] -= coef[i];
+        }
+        const int lv = target_limbs + 1;
+        const double ql = ev.last_prime(lv);
+        Ct tg = ev.mod_switch_to(T.at(g), lv);
+        bool q_const = true;
+        for (size_t i = 1; i < q.size(); i++)
+        {
+            q_const = q_const && q[i] == 0.0;
+        }
+        Ct prod;
+        if (q_const)
+        {
+            prod = ev.rescale_to_next(ev.multiply_plain(tg, ev.encode(q[0], lv, target_scale * ql / tg.scale)));
+        }
+        else
+        {
+            Ct qc = eval_cheb(ev, q, lv, target_scale * ql / tg.scale, T, keys);
+            prod = ev.rescale_to_next(ev.relinearize(ev.multiply(qc, tg), keys));
+        }
+        prod.scale = target_scale;
+        Ct rc = eval_cheb(ev, r, target_limbs, target_scale, T, keys);
+        return ev.add(prod, rc);
+    }
+
+    Ct Bootstrapper::eval_mod(const Evaluator &ev, const Ct &y, const Keys &keys) const
+    {
+        // Chebyshev basis T_1..T_7 (baby) and T_8, T_16, T_32 (giant) of y = x / K
+        std::map<int, Ct> T;
+        T[1] = y;
+        auto dbl_minus_one = [&](const Ct &sq) {
+            Ct r = ev.rescale_to_next(ev.relinearize(sq, keys));
+            ev.double_inplace(r);
+            return ev.add_const(r, -1.0);
+        };
+        auto t_even = [&](int a) { return dbl_minus_one(ev.square(T.at(a))); }; // T_2a = 2 T_a^2 - 1
+        auto t_sum = [&](int a, int b) {                                       // T_{a+b} = 2 T_a T_b - T_{a-b}, a > b
+            Ct ta = T.at(a), tb = T.at(b);
+            const int lv = std::min(ta.limbs, tb.limbs);
+            Ct p = ev.rescale_to_next(ev.relinearize(ev.multiply(ev.mod_switch_to(ta, lv), ev.mod_switch_to(tb, lv)), keys));
+            ev.double_inplace(p);
+            return ev.sub_reduced_error(p, T.at(a - b));
+        };
+        T[2] = t_even(1);
+        T[3] = t_sum(2, 1);
+        T[4] = t_even(2);
+        T[5] = t_sum(3, 2);
+        T[6] = t_even(3);
+        T[7] = t_sum(4, 3);
+        T[8] = t_even(4);
+        T[16] = t_even(8);
+        T[32] = t_even(16);
+        Ct cosv = eval_cheb(ev, cheb_, y.limbs - 6, y.scale, T, keys);
+        for (int i = 0; i < prm.double_angles; i++)
+        {
+            cosv = dbl_minus_one(ev.square(cosv)); // cos(2a) = 2 cos(a)^2 - 1
+        }
+        return cosv;
+    }
+
+    // ------------------------------------------------------------------------------------ bootstrap
+    Ct Bootstrapper::bootstrap(const Evaluator &ev, const Ct &in, const Keys &keys)
+    {
+        MOAI_REQUIRE(in.size == 2 && in.limbs == 1, "bootstrap expects size-2 ciphertexts at the last level");
+        const int n = slots();
+        const double q0 = (double)c_->q[0];
+        // plaintexts of the linear stages: encoded once per (stage, input scale)
+        if (cts_[0].pts.empty())
+        {
+            for (int s = 0; s < 3; s++)
+            {
+                encode_stage(ev, cts_[s], ev.last_prime(cts_[s].limbs));
+            }
+        }
+        // 1. ModRaise; the plaintext is now t = m + q0 I, declared at scale q0
+        Ct ct = ev.mod_raise(in, prm.total_limbs);
+        const double initial_scale = in.scale;
+        ct.scale = q0;
+        // 2. CoeffToSlot: slots <- (c_lo + i c_hi) / (2 K q0)   (bit-reversed order)
+        for (int s = 0; s < 3; s++)
+        {
+            ct = linear_transform(ev, ct, cts_[s], keys);
+        }
+        Ct conj = ev.complex_conjugate(ct, keys);
+        Ct re = ev.add(ct, conj);                 // c_lo / (K q0)
+        Ct im = ev.sub(ct, conj);                 // 2 i c_hi / (2 K q0)
+        std::vector<cd> minus_i((size_t)n, cd(0, -1)), plus_i((size_t)n, cd(0, 1));
+        im = ev.multiply_plain(im, ev.encode(minus_i, im.limbs, 1.0)); // exact monomial, no level
+        // 3. EvalMod on both halves as one batch: sin(2 pi t / q0) ~ 2 pi m / q0
+        Ct both = eval_mod(ev, ev.concat({ re, im }), keys);
+        re = ev.view(both, 0, in.batch);
+        im = ev.view(both, in.batch, in.batch);
+        // 4. SlotToCoeff on re + i im, constants q0 / (2 pi initial_scale) folded into the diagonals
+        Ct w = ev.add(re, ev.multiply_plain(im, ev.encode(plus_i, im.limbs, 1.0)));
+        if (stc_encoded_for_scale_ != initial_scale || stc_[0].pts.empty())
+        {
+            const double f = std::cbrt(q0 / (2 * PI * initial_scale));
+            for (int s = 0; s < 3; s++)
+            {
+                LinearStage tmp = stc_[s];
+                for (auto &kv : tmp.diags)
+                {
+                    for (auto &z : kv.second)
+                    {
+                        z *= f;
+                    }
+                }
+                // the last stage's plaintext scale makes the final rescale land exactly on final_scale;
+                // w.scale is invariant through the first two stages (plaintext scale = dropped prime)
+                const double ps = s < 2 ? ev.last_prime(tmp.limbs) : prm.final_scale * ev.last_prime(tmp.limbs) / w.scale;
+                encode_stage(ev, tmp, ps);
+                stc_[s].pts = tmp.pts;
+                stc_[s].pt_scale = ps;
+            }
+            stc_encoded_for_scale_ = initial_scale;
+        }
+        MOAI_REQUIRE(w.limbs == stc_[0].limbs, "level budget mismatch before SlotToCoeff");
+        for (int s = 0; s < 3; s++)
+        {
+            w = linear_transform(ev, w, stc_[s], keys);
+        }
+        w.scale = prm.final_scale;
+        return w;
+    }
+} // namespace moai

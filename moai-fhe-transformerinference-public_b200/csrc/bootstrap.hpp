@@ -1,0 +1,92 @@
+// Full-slot CKKS bootstrapping for the batched Evaluator.
+//
+// Same pipeline and level budget as the reference's Bootstrapper::bootstrap_full_3
+// (M/source/bootstrapping/Bootstrapper.cpp:3231-3251): ModRaise (1 -> L limbs) -> CoeffToSlot
+// (3 levels) -> EvalMod on the real and imaginary halves (cosine polynomial of degree 59 in 6
+// levels + 2 double-angle steps) -> SlotToCoeff (3 levels); 14 levels in total, output scale =
+// final_scale.  Results depend on FP64 polynomial coefficients, so parity with the reference is
+// by tolerance, not bit-exact (BASELINE.json north_star).
+//
+// The implementation is our own (not a transcription of Bootstrapper.cpp):
+//  * CoeffToSlot / SlotToCoeff matrices are built from the radix-2 factors of the CKKS "special
+//    FFT" (slot j <-> root zeta^{5^j}), log2(slots) butterfly levels merged into 3 sparse-diagonal
+//    matrices; the bit-reversal permutations of the two directions cancel and are never applied.
+//  * Every diagonal is pre-rotated for baby-step/giant-step evaluation and ENCODED ONCE per
+//    (stage, level) on the device at set-up (the reference re-encodes ~318 vectors per call,
+//    Bootstrapper.cpp:2026-2027); plaintext scales are chosen so that every rescale is exact.
+//  * EvalMod: least-squares Chebyshev fit of cos(2 pi (x - 1/4) / 2^r) on the union of the
+//    intervals [i - 2^-w, i + 2^-w], |i| < K (the domain the reference's multi-interval Remez
+//    uses, M/source/bootstrapping/RemezCos.h:11-16), evaluated by a depth-optimal recursive
+//    Chebyshev division (59 = 32 + 16 + 8 + 3 -> 6 levels) with exact target scales.
+//  * Everything is batched over independent ciphertexts.
+#pragma once
+#include "evaluator.hpp"
+
+namespace moai
+{
+    typedef std::complex<double> cd;
+
+    struct BootParams
+    {
+        int boundary_K = 25;  // |t / q0| < K            (test_full_scheme.hpp:346)
+        int deg = 59;         // cosine polynomial degree (:347)
+        int double_angles = 2; // scale_factor r          (:348)
+        int log_width = 10;   // loge                     (:352)
+        int total_limbs = 35; // data limbs after ModRaise (:368)
+        double final_scale = 70368744177664.0; // 2^46
+    };
+
+    // one sparse-diagonal matrix, prepared for BSGS evaluation at a fixed level
+    struct LinearStage
+    {
+        int limbs = 0;                    // level (limb count) at which the stage is applied
+        std::map<int, std::vector<cd>> diags; // signed offset -> diagonal (length n slots)
+        int stride = 1, giant = 1;        // offsets are stride * (giant * i + j)
+        std::vector<int> baby;            // j values present (0 first)
+        std::vector<int> giants;          // i values present
+        // encoded, pre-rotated diagonals on the device: key (i, j)
+        std::map<std::pair<int, int>, Pt> pts;
+        double pt_scale = 0;              // scale the plaintexts were encoded with
+    };
+
+    class Bootstrapper
+    {
+    public:
+        Bootstrapper(Context *ctx, const BootParams &p);
+        std::vector<int> required_steps() const; // rotation steps (normalised to [0, slots)) the BSGS plans use
+        // in: batch of size-2 ciphertexts at 1 limb (chain_index 0); returns them at
+        // total_limbs - 14 limbs with scale final_scale
+        Ct bootstrap(const Evaluator &ev, const Ct &in, const Keys &keys);
+
+        // host-side artefacts, exposed for the CPU test-suite
+        const std::vector<double> &cheb_coeffs() const
+        {
+            return cheb_;
+        }
+        const LinearStage &stage(int dir, int idx) const
+        {
+            return dir == 0 ? cts_[idx] : stc_[idx];
+        }
+        int slots() const
+        {
+            return (int)(c_->n / 2);
+        }
+
+        BootParams prm;
+
+    private:
+        Context *c_;
+        LinearStage cts_[3], stc_[3];
+        std::vector<double> cheb_;
+        double stc_encoded_for_scale_ = 0; // input scale the SlotToCoeff constants were folded for
+
+        void build_matrices();
+        void plan_bsgs(LinearStage &st) const;
+        void encode_stage(const Evaluator &ev, LinearStage &st, double pt_scale);
+        void fit_cosine();
+        Ct linear_transform(const Evaluator &ev, const Ct &ct, LinearStage &st, const Keys &keys) const;
+        Ct eval_mod(const Evaluator &ev, const Ct &y, const Keys &keys) const;
+        Ct eval_cheb(const Evaluator &ev, const std::vector<double> &coef, int target_limbs, double target_scale,
+                     const std::map<int, Ct> &T, const Keys &keys) const;
+    };
+} // namespace moai

@@ -3,6 +3,7 @@
 #include "../../include/moai_b200.h"
 #include "../../include/moai_b200_modules.h"
 #include "ntt.cuh"
+#include "bootstrap.hpp"
 #include "modules.hpp"
 #include "ops.cuh"
 #include <cmath>
@@ -17,6 +18,11 @@ struct moai_context
 struct moai_keys
 {
     Keys k;
+};
+
+struct moai_bootstrapper
+{
+    Bootstrapper *b;
 };
 
 #define API_BEGIN                                                                                                      \
@@ -655,6 +661,112 @@ extern "C"
         Ct W = ev.wrap(const_cast<u64 *>(CU(enc_W)), col_W, 2, limbs, scale_W);
         Ct r = ct_ct_matrix_mul_diagpacking(ev, X, W, getk(keys), col_X, row_X, col_W, row_W, num_batch);
         emit(c, r, out, col_W, out_limbs, out_scale);
+        API_END
+    }
+
+    // ---- bootstrapping ---------------------------------------------------------------------------
+    int32_t moai_bootstrapper_create(moai_context *ctx, int32_t total_limbs, double final_scale, int32_t boundary_K,
+                                     int32_t deg, int32_t double_angles, int32_t log_width, moai_bootstrapper **out)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(out, "null argument");
+        BootParams p;
+        p.total_limbs = total_limbs;
+        p.final_scale = final_scale;
+        p.boundary_K = boundary_K;
+        p.deg = deg;
+        p.double_angles = double_angles;
+        p.log_width = log_width;
+        *out = new moai_bootstrapper{ new Bootstrapper(c, p) };
+        API_END
+    }
+
+    int32_t moai_bootstrapper_destroy(moai_bootstrapper *b)
+    {
+        API_BEGIN
+        if (b)
+        {
+            delete b->b;
+            delete b;
+        }
+        API_END
+    }
+
+    int32_t moai_bootstrapper_required_steps(moai_bootstrapper *b, int32_t *steps, int32_t capacity, int32_t *count)
+    {
+        API_BEGIN
+        MOAI_REQUIRE(b && steps && count, "null argument");
+        auto v = b->b->required_steps();
+        MOAI_REQUIRE((int)v.size() <= capacity, "steps buffer too small");
+        for (size_t i = 0; i < v.size(); i++)
+        {
+            steps[i] = v[i];
+        }
+        *count = (int32_t)v.size();
+        API_END
+    }
+
+    int32_t moai_bootstrap(moai_context *ctx, moai_bootstrapper *b, moai_keys *keys, const uint64_t *in, int64_t batch,
+                           double scale, uint64_t *out, int32_t *out_limbs, double *out_scale)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(b && in && out, "null argument");
+        check_shape(c, batch, 2, 1);
+        Evaluator ev(c);
+        Ct r = b->b->bootstrap(ev, ev.wrap(const_cast<u64 *>(CU(in)), batch, 2, 1, scale), getk(keys));
+        MOAI_REQUIRE(out_limbs && out_scale, "null argument");
+        MOAI_CUDA_CHECK(cudaMemcpyAsync(out, r.d, (size_t)r.batch * 2 * r.limbs * c->n * sizeof(u64),
+                                        cudaMemcpyDeviceToDevice, c->stream));
+        *out_limbs = r.limbs;
+        *out_scale = r.scale;
+        MOAI_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        API_END
+    }
+
+    // Host-only view of the bootstrapping plan (no GPU needed): the sparse-diagonal matrix of one
+    // linear stage (dir 0 = CoeffToSlot, 1 = SlotToCoeff; stage 0..2) and the cosine coefficients.
+    // Call with diag_values == NULL to query *n_diags.
+    int32_t moai_bootstrap_plan_debug(int32_t log_n, const uint64_t *primes, int32_t n_key_limbs, int32_t total_limbs,
+                                      int32_t dir, int32_t stage, int32_t *n_diags, int32_t *offsets,
+                                      double *diag_values, double *cheb, int32_t *n_cheb)
+    {
+        API_BEGIN
+        MOAI_REQUIRE(primes && n_diags && stage >= 0 && stage < 3, "bad arguments");
+        Context host; // tables are not needed for the plan: only n and the prime list
+        host.log_n = log_n;
+        host.n = (size_t)1 << log_n;
+        host.kl = n_key_limbs;
+        host.q.assign(primes, primes + n_key_limbs);
+        BootParams p;
+        p.total_limbs = total_limbs;
+        Bootstrapper b(&host, p);
+        const LinearStage &st = b.stage(dir, stage);
+        *n_diags = (int32_t)st.diags.size();
+        if (diag_values && offsets)
+        {
+            size_t k = 0;
+            const size_t n = host.n / 2;
+            for (auto &kv : st.diags)
+            {
+                offsets[k] = kv.first;
+                for (size_t i = 0; i < n; i++)
+                {
+                    diag_values[(k * n + i) * 2] = kv.second[i].real();
+                    diag_values[(k * n + i) * 2 + 1] = kv.second[i].imag();
+                }
+                k++;
+            }
+        }
+        if (cheb && n_cheb)
+        {
+            *n_cheb = (int32_t)b.cheb_coeffs().size();
+            for (size_t i = 0; i < b.cheb_coeffs().size(); i++)
+            {
+                cheb[i] = b.cheb_coeffs()[i];
+            }
+        }
         API_END
     }
 }

@@ -1190,10 +1190,11 @@ void orc_gen_kswitch_key(const orc_ctx *c, const u64 *sk, u64 seed, const u64 *n
     int idx[ORC_MAX_LIMBS];
     for (int j = 0; j < kl; j++)
         idx[j] = j;
-    u64 st = seed * 0x9E3779B97F4A7C15ULL + 11;
     u64 p = c->q[kl - 1];
+#pragma omp parallel for schedule(dynamic)
     for (int J = 0; J < digits; J++)
     {
+        u64 st = (seed * 0x9E3779B97F4A7C15ULL + 11) ^ ((u64)(J + 1) * 0xD1B54A32D192ED03ULL);
         u64 *c0 = out + ((size_t)J * 2) * kl * n, *c1 = c0 + (size_t)kl * n;
         enc_zero_sym(c, sk, &st, idx, kl, c0, c1);
         u64 q = c->q[J];

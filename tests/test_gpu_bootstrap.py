@@ -1,0 +1,63 @@
+"""GPU checks of full-slot bootstrapping (BASELINE config 3).  The reference
+Bootstrapper has no tests and does not compile here without NTL, and its result depends on FP64
+polynomial coefficients, so parity is by TOLERANCE on the property that defines bootstrapping:
+decrypt(bootstrap(ct)) ~ decrypt(ct), output at chain_index total-15 with scale 2^46.
+Stated tolerance: max-abs slot error < 2e-3 (the survey measured 9e-4 for the reference pipeline
+with a stub polynomial)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def boot_small(pkg):
+    from oracle import Oracle
+    bits = [51] + [46] * 2 + [51] * 14 + [58]        # same shape as the repo's chain, 17 data limbs
+    o = Oracle(12, bits)
+    be = pkg.Backend(12, o.q)
+    boot = pkg.Bootstrapper(be, total_limbs=17)
+    sk = o.gen_secret(3, hamming_weight=64)
+    gal = {}
+    for i, st in enumerate(boot.required_steps() + [0]):
+        e = o.elt_from_step(st)
+        gal[e] = pkg.to_device(o.gen_galois_key(sk, 1000 + i, e))
+    keys = be.make_keys(relin=pkg.to_device(o.gen_relin_key(sk, 5)), galois=gal)
+    return o, be, boot, sk, keys
+
+
+def test_bootstrap_preserves_message(pkg, boot_small):
+    o, be, boot, sk, keys = boot_small
+    rng = np.random.default_rng(1)
+    scale = 2.0 ** 46
+    B = 3
+    zs = (rng.normal(size=(B, o.n // 2)) + 1j * rng.normal(size=(B, o.n // 2))) * 0.1
+    zs[2] = 0.0
+    cts = np.stack([o.encrypt_sym(sk, 50 + i, o.encode(zs[i], scale, 1), 1) for i in range(B)])
+    out, out_scale = boot.bootstrap_3(keys, pkg.to_device(cts.reshape(B, 2, 1, o.n)), scale)
+    assert out.shape[2] == 3 and out_scale == scale
+    res = pkg.to_host(out)
+    for i in range(B):
+        dec = o.decode(o.decrypt(sk, res[i].reshape(-1), 2, 3), 3, out_scale)
+        assert np.abs(dec - zs[i]).max() < 2e-3, (i, np.abs(dec - zs[i]).max())
+
+
+def test_bootstrap_with_power_of_two_keys_only(pkg, boot_small):
+    """Missing rotation keys fall back to SEAL's NAF decomposition (S/evaluator.cpp:2699-2721): the
+    reference driver's default key set (powers of two) is enough, only slower."""
+    o, be, boot, sk, _ = boot_small
+    rng = np.random.default_rng(2)
+    scale = 2.0 ** 46
+    gal = {}
+    for k in range(11):
+        for st in (1 << k, -(1 << k)):
+            e = o.elt_from_step(st)
+            gal[e] = pkg.to_device(o.gen_galois_key(sk, 2000 + len(gal), e))
+    e = o.elt_from_step(0)
+    gal[e] = pkg.to_device(o.gen_galois_key(sk, 2999, e))
+    keys = be.make_keys(relin=pkg.to_device(o.gen_relin_key(sk, 5)), galois=gal)
+    z = (rng.normal(size=o.n // 2) + 1j * rng.normal(size=o.n // 2)) * 0.1
+    ct = o.encrypt_sym(sk, 60, o.encode(z, scale, 1), 1)
+    out, out_scale = boot.bootstrap_3(keys, pkg.to_device(ct.reshape(1, 2, 1, o.n)), scale)
+    dec = o.decode(o.decrypt(sk, pkg.to_host(out).reshape(-1), 2, 3), 3, out_scale)
+    assert np.abs(dec - z).max() < 2e-3
