@@ -354,4 +354,139 @@ namespace moai
         }
         return output;
     }
+
+    // ------------------------------------------------------------------------------------ attention
+    Ct ct_pt_matrix_mul_wo_pre(const Evaluator &ev, const Ct &X, const std::vector<double> &W, int col_W)
+    {
+        // M/source/matrix_mul/Ct_pt_matrix_mul.hpp:4-49 (scale forced back to the input scale, :41)
+        MOAI_REQUIRE((long long)W.size() == X.batch * col_W, "bad dimensions of X or W");
+        Ct out = ev.alloc(col_W, 2, X.limbs - 1, X.scale);
+        ct_pt_matmul_scalar(ev.c, X.d, W.data(), (int)X.batch, col_W, X.limbs, X.scale, out.d);
+        return out;
+    }
+
+    namespace
+    {
+        // x[i] += encode(b[i] * mask) with both scales forced to `scale` (single_att_block.hpp:32-45)
+        Ct add_masked_bias(const Evaluator &ev, Ct x, const std::vector<double> &b, const std::vector<int> &bias_vec,
+                           double scale)
+        {
+            const size_t slots = bias_vec.size();
+            std::vector<std::complex<double>> vals((size_t)x.batch * slots, 0.0);
+            for (long long i = 0; i < x.batch; i++)
+            {
+                for (size_t j = 0; j < slots; j++)
+                {
+                    if (bias_vec[j] == 1)
+                    {
+                        vals[(size_t)i * slots + j] = b[i];
+                    }
+                }
+            }
+            Pt p = ev.encode_batch(vals.data(), x.batch, (int)slots, x.limbs, x.scale);
+            x.scale = scale;
+            p.scale = scale;
+            return ev.add_plain(x, p);
+        }
+    } // namespace
+
+    // softmax_boot: M/source/non_linear_func/softmax.hpp:308-581
+    Ct softmax_boot(const Evaluator &ev, const Ct &X, const std::vector<int> &bias_vec, int input_num, const Keys &keys,
+                    int iter, Bootstrapper &boot, int layer_id)
+    {
+        const int num = (int)X.batch;
+        const double scale = X.scale;
+        const int slot_count = (int)bias_vec.size();
+        const int num_batch = slot_count / 128;
+        static const double minus_index_vec[12] = { 7.5, 9.9, 13.6, 13.3, 9.5, 8, 10.3, 9, 9, 9, 11, 7 };
+        MOAI_REQUIRE(layer_id >= 0 && layer_id < 12, "layer_id out of range");
+        const double minus_index = minus_index_vec[layer_id];
+        // per-ciphertext slot pattern of the valid (row, column) pairs of generalized diagonal i
+        // (softmax.hpp:340-391): value v on the selected slots, 0 elsewhere
+        auto pattern = [&](double v) {
+            std::vector<std::complex<double>> vals((size_t)num * slot_count, 0.0);
+            for (int i = 0; i < num; i++)
+            {
+                std::complex<double> *row = vals.data() + (size_t)i * slot_count;
+                if (i == 0)
+                {
+                    for (int s = 0; s < slot_count; s++)
+                    {
+                        row[s] = bias_vec[s] == 1 ? v : 0.0;
+                    }
+                }
+                else if (i > input_num && i <= num - input_num)
+                {
+                    // all-padding diagonal: zero pattern
+                }
+                else if (i <= input_num)
+                {
+                    const int index = num_batch * (input_num - i);
+                    for (int s = 0; s < slot_count; s++)
+                    {
+                        row[s] = (bias_vec[s] == 1 && s < index) ? v : 0.0;
+                    }
+                }
+                else
+                {
+                    const int index = (num - i) * num_batch;
+                    for (int s = 0; s < slot_count; s++)
+                    {
+                        row[s] = (bias_vec[s] == 1 && s >= index) ? v : 0.0;
+                    }
+                }
+            }
+            return vals;
+        };
+        // x - max on the valid slots
+        auto minus = pattern(minus_index);
+        Ct x_minus = ev.sub_plain(X, ev.encode_batch(minus.data(), num, slot_count, X.limbs, X.scale));
+        // exp, then zero the invalid slots
+        Ct exp_x = exp_128(ev, x_minus, keys);
+        auto ones = pattern(1.0);
+        exp_x = ev.rescale_to_next(
+            ev.multiply_plain(exp_x, ev.encode_batch(ones.data(), num, slot_count, exp_x.limbs, exp_x.scale)));
+        exp_x.scale = scale;
+        // sum, + 1e-5, down to the last level, bootstrap
+        Ct sum = ev.sum_batch(exp_x);
+        sum = ev.add_plain(sum, ev.encode(0.00001, sum.limbs, sum.scale));
+        sum.scale = scale;
+        sum = ev.mod_switch_to(sum, 1);
+        Ct rtn = boot.bootstrap(ev, sum, keys);
+        if (rtn.limbs > iter + 1 + 3 + 1)
+        {
+            rtn = ev.mod_switch_to(rtn, iter + 1 + 3 + 1); // chain_index <= iter + 1 + 3
+        }
+        Ct inv_sum = inverse(ev, rtn, keys, iter);
+        inv_sum.scale = scale;
+        if (exp_x.limbs < inv_sum.limbs)
+        {
+            inv_sum = ev.mod_switch_to(inv_sum, exp_x.limbs);
+        }
+        if (exp_x.limbs > inv_sum.limbs)
+        {
+            exp_x = ev.mod_switch_to(exp_x, inv_sum.limbs);
+        }
+        Ct out = ev.rescale_to_next(ev.relinearize(ev.multiply(exp_x, inv_sum), keys));
+        out.scale = scale;
+        return out;
+    }
+
+    // single_att_block: M/source/att_block/single_att_block.hpp:10-207.  Weights are row-major
+    // num_col x col_W doubles.
+    Ct single_att_block(const Evaluator &ev, const Ct &X, const std::vector<double> &WQ, const std::vector<double> &WK,
+                        const std::vector<double> &WV, const std::vector<double> &bQ, const std::vector<double> &bK,
+                        const std::vector<double> &bV, const std::vector<int> &bias_vec, int input_num,
+                        const Keys &keys, Bootstrapper &boot, int num_batch, int iter, int layer_id)
+    {
+        const double scale = X.scale;
+        const int col_W = (int)bQ.size();
+        Ct Q = add_masked_bias(ev, ct_pt_matrix_mul_wo_pre(ev, X, WQ, col_W), bQ, bias_vec, scale);
+        Ct K = add_masked_bias(ev, ct_pt_matrix_mul_wo_pre(ev, X, WK, col_W), bK, bias_vec, scale);
+        Ct Xv = X.limbs > 4 ? ev.mod_switch_to(X, 4) : X; // chain_index <= 3
+        Ct V = add_masked_bias(ev, ct_pt_matrix_mul_wo_pre(ev, Xv, WV, col_W), bV, bias_vec, scale);
+        Ct QK = ct_ct_matrix_mul_colpacking(ev, Q, K, keys, col_W, 128, col_W, 128, num_batch);
+        Ct sm = softmax_boot(ev, QK, bias_vec, input_num, keys, iter, boot, layer_id);
+        return ct_ct_matrix_mul_diagpacking(ev, sm, V, keys, 128, 128, col_W, 128, num_batch);
+    }
 } // namespace moai
