@@ -89,6 +89,40 @@ int32_t moai_bootstrap_plan_debug(int32_t log_n, const uint64_t *primes, int32_t
                                   int32_t dir, int32_t stage, int32_t *n_diags, int32_t *offsets, double *diag_values,
                                   double *cheb, int32_t *n_cheb);
 
+/* ---- B7/B6: softmax_boot (M/source/non_linear_func/softmax.hpp:308-581) and single_att_block
+ * (M/source/att_block/single_att_block.hpp:10-207); weights row-major num_col x col_W doubles.     */
+int32_t moai_softmax_boot(moai_context *ctx, moai_keys *keys, moai_bootstrapper *b, const uint64_t *enc_X,
+                          int32_t num, int32_t limbs, double scale, const int32_t *bias_vec, int32_t input_num,
+                          int32_t iter, int32_t layer_id, uint64_t *out, int32_t *out_limbs, double *out_scale);
+int32_t moai_single_att_block(moai_context *ctx, moai_keys *keys, moai_bootstrapper *b, const uint64_t *enc_X,
+                              int32_t num_col, int32_t limbs, double scale, const double *WQ, const double *WK,
+                              const double *WV, const double *bQ, const double *bK, const double *bV, int32_t col_W,
+                              const int32_t *bias_vec, int32_t input_num, int32_t num_batch, int32_t iter,
+                              int32_t layer_id, uint64_t *out, int32_t *out_limbs, double *out_scale);
+
+/* ---- one encoder layer of all_layer_test (M/test/test_full_scheme.hpp:484-1087): attention
+ * (12 heads) -> self-output matmul -> bootstrap -> residual + LayerNorm -> bootstrap ->
+ * intermediate matmul -> GELU -> final matmul -> bootstrap -> residual + LayerNorm2 -> bootstrap.
+ * x: [hidden][2][limbs][N] at chain_index 20; out: the next layer's input at chain_index 20.
+ * All weight pointers are HOST row-major [in][out] doubles as the driver reads them (:94-337).    */
+typedef struct moai_layer_weights
+{
+    int32_t hidden, heads, head_dim, inter;
+    const double *WQ, *WK, *WV;          /* [heads][hidden][head_dim] */
+    const double *bQ, *bK, *bV;          /* [heads][head_dim] */
+    const double *selfoutput, *selfoutput_bias;
+    const double *ln1_gamma, *ln1_beta;
+    const double *inter_weight, *inter_bias;
+    const double *final_weight, *final_bias;
+    const double *ln2_gamma, *ln2_beta;
+} moai_layer_weights;
+int32_t moai_encoder_layer(moai_context *ctx, moai_keys *keys, moai_bootstrapper *b, const uint64_t *x, int32_t limbs,
+                           double scale, const moai_layer_weights *w, const int32_t *bias_vec, int32_t input_num,
+                           int32_t num_batch, int32_t layer_id, int64_t boot_chunk, uint64_t *out,
+                           int32_t *out_limbs, double *out_scale);
+/* "name:ms:count;" for every profiled phase (see moai_profile_enable) */
+int32_t moai_profile_dump(moai_context *ctx, char *buf, int32_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -115,6 +115,16 @@ class Backend:
         self._chk(self.lib.moai_profile_get(self.h, name.encode(), C.byref(ms), C.byref(cnt)))
         return ms.value, cnt.value
 
+    def profile_dump(self):
+        buf = C.create_string_buffer(1 << 16)
+        self._chk(self.lib.moai_profile_dump(self.h, buf, C.c_int32(1 << 16)))
+        out = {}
+        for item in buf.value.decode().split(";"):
+            if item:
+                name, ms, cnt = item.rsplit(":", 2)
+                out[name] = (float(ms), int(cnt))
+        return out
+
     def launch_count(self):
         v = C.c_uint64()
         self._chk(self.lib.moai_launch_count(self.h, C.byref(v)))
@@ -401,6 +411,13 @@ class Backend:
                             C.c_int32(col_W), C.c_int32(row_W), C.c_int32(num_batch), out_count=col_W)
 
 
+class LayerWeightsC(C.Structure):
+    _fields_ = [("hidden", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32), ("inter", C.c_int32)] + \
+        [(k, C.POINTER(C.c_double)) for k in ("WQ", "WK", "WV", "bQ", "bK", "bV", "selfoutput", "selfoutput_bias",
+                                              "ln1_gamma", "ln1_beta", "inter_weight", "inter_bias", "final_weight",
+                                              "final_bias", "ln2_gamma", "ln2_beta")]
+
+
 class Bootstrapper:
     """Bootstrapper (M/source/bootstrapping/Bootstrapper.h:15-221) bound to one Backend."""
 
@@ -429,6 +446,41 @@ class Bootstrapper:
                                       C.byref(ol), C.byref(osc)))
         assert ol.value == self.total_limbs - 14
         return out, osc.value
+
+    def softmax_boot(self, keys, x, scale, bias_vec, input_num, iters=16, layer_id=0):
+        be = self.be
+        bt, p, l, n = x.shape
+        bv = np.ascontiguousarray(bias_vec, dtype=np.int32)
+        return be._module(be.lib.moai_softmax_boot, x, scale, be.h, keys.h, self.h, _ptr(x), C.c_int32(bt), C.c_int32(l),
+                          C.c_double(scale), bv.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int32(input_num),
+                          C.c_int32(iters), C.c_int32(layer_id))
+
+    def single_att_block(self, keys, x, scale, WQ, WK, WV, bQ, bK, bV, bias_vec, input_num, num_batch, iters=16,
+                         layer_id=0):
+        be = self.be
+        bt, p, l, n = x.shape
+        dp = C.POINTER(C.c_double)
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (WQ, WK, WV, bQ, bK, bV)]
+        bv = np.ascontiguousarray(bias_vec, dtype=np.int32)
+        col_W = arrs[3].size
+        return be._module(be.lib.moai_single_att_block, x, scale, be.h, keys.h, self.h, _ptr(x), C.c_int32(bt),
+                          C.c_int32(l), C.c_double(scale), *[a.ctypes.data_as(dp) for a in arrs], C.c_int32(col_W),
+                          bv.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int32(input_num), C.c_int32(num_batch),
+                          C.c_int32(iters), C.c_int32(layer_id), out_count=col_W)
+
+    def encoder_layer(self, keys, x, scale, weights, bias_vec, input_num, num_batch, layer_id=0, boot_chunk=32):
+        """weights: dict with the fields of moai_layer_weights (numpy float64 arrays)."""
+        be = self.be
+        bt, p, l, n = x.shape
+        dp = C.POINTER(C.c_double)
+        keep = {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in weights.items()
+                if k not in ("hidden", "heads", "head_dim", "inter")}
+        w = LayerWeightsC(hidden=weights["hidden"], heads=weights["heads"], head_dim=weights["head_dim"],
+                          inter=weights["inter"], **{k: v.ctypes.data_as(dp) for k, v in keep.items()})
+        bv = np.ascontiguousarray(bias_vec, dtype=np.int32)
+        return be._module(be.lib.moai_encoder_layer, x, scale, be.h, keys.h, self.h, _ptr(x), C.c_int32(l),
+                          C.c_double(scale), C.byref(w), bv.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int32(input_num),
+                          C.c_int32(num_batch), C.c_int32(layer_id), C.c_int64(boot_chunk))
 
     def __del__(self):
         try:

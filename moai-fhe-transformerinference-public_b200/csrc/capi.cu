@@ -7,6 +7,7 @@
 #include "modules.hpp"
 #include "ops.cuh"
 #include <cmath>
+#include <cstring>
 
 using namespace moai;
 
@@ -767,6 +768,103 @@ extern "C"
                 cheb[i] = b.cheb_coeffs()[i];
             }
         }
+        API_END
+    }
+
+    // ---- attention / encoder layer ----------------------------------------------------------------
+    int32_t moai_softmax_boot(moai_context *ctx, moai_keys *keys, moai_bootstrapper *b, const uint64_t *enc_X,
+                              int32_t num, int32_t limbs, double scale, const int32_t *bias_vec, int32_t input_num,
+                              int32_t iter, int32_t layer_id, uint64_t *out, int32_t *out_limbs, double *out_scale)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, num, 2, limbs);
+        MOAI_REQUIRE(b && bias_vec, "null argument");
+        Evaluator ev(c);
+        std::vector<int> bv(bias_vec, bias_vec + c->n / 2);
+        Ct r = softmax_boot(ev, ev.wrap(const_cast<u64 *>(CU(enc_X)), num, 2, limbs, scale), bv, input_num, getk(keys),
+                            iter, *b->b, layer_id);
+        emit(c, r, out, num, out_limbs, out_scale);
+        API_END
+    }
+
+    int32_t moai_single_att_block(moai_context *ctx, moai_keys *keys, moai_bootstrapper *b, const uint64_t *enc_X,
+                                  int32_t num_col, int32_t limbs, double scale, const double *WQ, const double *WK,
+                                  const double *WV, const double *bQ, const double *bK, const double *bV, int32_t col_W,
+                                  const int32_t *bias_vec, int32_t input_num, int32_t num_batch, int32_t iter,
+                                  int32_t layer_id, uint64_t *out, int32_t *out_limbs, double *out_scale)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, num_col, 2, limbs);
+        MOAI_REQUIRE(b && bias_vec && WQ && WK && WV && bQ && bK && bV, "null argument");
+        Evaluator ev(c);
+        std::vector<int> bv(bias_vec, bias_vec + c->n / 2);
+        const size_t wn = (size_t)num_col * col_W;
+        std::vector<double> wq(WQ, WQ + wn), wk(WK, WK + wn), wv(WV, WV + wn);
+        std::vector<double> q(bQ, bQ + col_W), k(bK, bK + col_W), v(bV, bV + col_W);
+        Ct r = single_att_block(ev, ev.wrap(const_cast<u64 *>(CU(enc_X)), num_col, 2, limbs, scale), wq, wk, wv, q, k, v,
+                                bv, input_num, getk(keys), *b->b, num_batch, iter, layer_id);
+        emit(c, r, out, col_W, out_limbs, out_scale);
+        API_END
+    }
+
+    int32_t moai_encoder_layer(moai_context *ctx, moai_keys *keys, moai_bootstrapper *b, const uint64_t *x,
+                               int32_t limbs, double scale, const moai_layer_weights *w, const int32_t *bias_vec,
+                               int32_t input_num, int32_t num_batch, int32_t layer_id, int64_t boot_chunk,
+                               uint64_t *out, int32_t *out_limbs, double *out_scale)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(b && w && bias_vec, "null argument");
+        check_shape(c, w->hidden, 2, limbs);
+        MOAI_REQUIRE(w->hidden == w->heads * w->head_dim, "hidden must equal heads * head_dim");
+        Evaluator ev(c);
+        LayerWeights lw;
+        lw.hidden = w->hidden;
+        lw.heads = w->heads;
+        lw.head_dim = w->head_dim;
+        lw.inter = w->inter;
+        const size_t hw = (size_t)w->hidden * w->head_dim;
+        for (int h = 0; h < w->heads; h++)
+        {
+            lw.WQ.emplace_back(w->WQ + h * hw, w->WQ + (h + 1) * hw);
+            lw.WK.emplace_back(w->WK + h * hw, w->WK + (h + 1) * hw);
+            lw.WV.emplace_back(w->WV + h * hw, w->WV + (h + 1) * hw);
+            lw.bQ.emplace_back(w->bQ + (size_t)h * w->head_dim, w->bQ + (size_t)(h + 1) * w->head_dim);
+            lw.bK.emplace_back(w->bK + (size_t)h * w->head_dim, w->bK + (size_t)(h + 1) * w->head_dim);
+            lw.bV.emplace_back(w->bV + (size_t)h * w->head_dim, w->bV + (size_t)(h + 1) * w->head_dim);
+        }
+        const size_t H = w->hidden, I = w->inter;
+        lw.selfoutput.assign(w->selfoutput, w->selfoutput + H * H);
+        lw.selfoutput_bias.assign(w->selfoutput_bias, w->selfoutput_bias + H);
+        lw.ln1_gamma.assign(w->ln1_gamma, w->ln1_gamma + H);
+        lw.ln1_beta.assign(w->ln1_beta, w->ln1_beta + H);
+        lw.inter_weight.assign(w->inter_weight, w->inter_weight + H * I);
+        lw.inter_bias.assign(w->inter_bias, w->inter_bias + I);
+        lw.final_weight.assign(w->final_weight, w->final_weight + I * H);
+        lw.final_bias.assign(w->final_bias, w->final_bias + H);
+        lw.ln2_gamma.assign(w->ln2_gamma, w->ln2_gamma + H);
+        lw.ln2_beta.assign(w->ln2_beta, w->ln2_beta + H);
+        std::vector<int> bv(bias_vec, bias_vec + c->n / 2);
+        Ct r = encoder_layer(ev, ev.wrap(const_cast<u64 *>(CU(x)), w->hidden, 2, limbs, scale), lw, bv, input_num,
+                             getk(keys), *b->b, num_batch, layer_id, boot_chunk > 0 ? boot_chunk : 32);
+        emit(c, r, out, w->hidden, out_limbs, out_scale);
+        API_END
+    }
+
+    int32_t moai_profile_dump(moai_context *ctx, char *buf, int32_t capacity)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(buf && capacity > 0, "bad arguments");
+        std::string s;
+        for (auto &kv : c->prof)
+        {
+            s += kv.first + ":" + std::to_string(kv.second.first) + ":" + std::to_string(kv.second.second) + ";";
+        }
+        MOAI_REQUIRE((int)s.size() < capacity, "buffer too small");
+        std::memcpy(buf, s.c_str(), s.size() + 1);
         API_END
     }
 }

@@ -489,4 +489,121 @@ namespace moai
         Ct sm = softmax_boot(ev, QK, bias_vec, input_num, keys, iter, boot, layer_id);
         return ct_ct_matrix_mul_diagpacking(ev, sm, V, keys, 128, 128, col_W, 128, num_batch);
     }
+
+    // ------------------------------------------------------------------------------------ encoder layer
+    namespace
+    {
+        Ct masked_matmul(const Evaluator &ev, const Ct &X, const std::vector<double> &W, const std::vector<int> &bias_vec,
+                         int col_W)
+        {
+            // ct_pt_matrix_mul_wo_pre_w_mask (Ct_pt_matrix_mul.hpp:103-170)
+            bool all_ones = true;
+            for (int v : bias_vec)
+            {
+                all_ones = all_ones && v == 1;
+            }
+            Ct out = ev.alloc(col_W, 2, X.limbs - 1, X.scale);
+            if (all_ones)
+            {
+                ct_pt_matmul_scalar(ev.c, X.d, W.data(), (int)X.batch, col_W, X.limbs, X.scale, out.d);
+            }
+            else
+            {
+                ct_pt_matmul_masked(ev.c, X.d, W.data(), bias_vec.data(), (int)X.batch, col_W, X.limbs, X.scale, out.d);
+            }
+            return out;
+        }
+
+        // 768 independent bootstrappings (test_full_scheme.hpp:654-660), chunked to bound the workspace
+        Ct bootstrap_all(const Evaluator &ev, const Ct &x, const Keys &keys, Bootstrapper &boot, long long chunk)
+        {
+            Ct in = ev.mod_switch_to(x, 1);
+            Ct out = ev.alloc(x.batch, 2, boot.prm.total_limbs - 14, boot.prm.final_scale);
+            for (long long b0 = 0; b0 < x.batch; b0 += chunk)
+            {
+                const long long nb = std::min(chunk, x.batch - b0);
+                Ct r = boot.bootstrap(ev, ev.view(in, b0, nb), keys);
+                ev.copy_into(r, out, b0);
+            }
+            return out;
+        }
+    } // namespace
+
+    Ct encoder_layer(const Evaluator &ev, const Ct &x, const LayerWeights &w, const std::vector<int> &bias_vec,
+                     int input_num, const Keys &keys, Bootstrapper &boot, int num_batch, int layer_id,
+                     long long boot_chunk)
+    {
+        const double scale = x.scale;
+        const int hidden = w.hidden;
+        MOAI_REQUIRE(x.batch == hidden && x.size == 2, "layer input must be one ciphertext per hidden column");
+        MOAI_REQUIRE(x.limbs == boot.prm.total_limbs - 14, "layer input must be at the post-bootstrapping level");
+        Context *c = ev.c;
+        // ---- attention (chain_index 14), heads processed one after the other like the reference
+        Ct att_out = ev.alloc(hidden, 2, 2, scale);
+        {
+            PhaseTimer t(c, "attention");
+            Ct x_att = ev.mod_switch_to(x, x.limbs - 6);
+            for (int h = 0; h < w.heads; h++)
+            {
+                Ct o = single_att_block(ev, x_att, w.WQ[h], w.WK[h], w.WV[h], w.bQ[h], w.bK[h], w.bV[h], bias_vec,
+                                        input_num, keys, boot, num_batch, 16, layer_id);
+                MOAI_REQUIRE(o.limbs == 2 && o.batch == w.head_dim, "attention head output shape");
+                ev.copy_into(o, att_out, (long long)h * w.head_dim);
+            }
+        }
+        Ct rtn;
+        {
+            PhaseTimer t(c, "selfoutput_matmul");
+            Ct so = add_masked_bias(ev, masked_matmul(ev, att_out, w.selfoutput, bias_vec, hidden), w.selfoutput_bias,
+                                    bias_vec, scale);
+            att_out = Ct();
+            rtn = so;
+        }
+        {
+            PhaseTimer t(c, "bootstrap_1");
+            rtn = bootstrap_all(ev, rtn, keys, boot, boot_chunk);
+        }
+        Ct ln1;
+        {
+            PhaseTimer t(c, "layernorm_1");
+            ev.add_inplace(rtn, ev.mod_switch_to(x, rtn.limbs)); // residual
+            ln1 = layernorm(ev, rtn, w.ln1_gamma, w.ln1_beta, bias_vec, keys, 1);
+        }
+        Ct boot_layer;
+        {
+            PhaseTimer t(c, "bootstrap_2");
+            boot_layer = bootstrap_all(ev, ln1, keys, boot, boot_chunk);
+            ln1 = Ct();
+        }
+        Ct inter;
+        {
+            PhaseTimer t(c, "intermediate_matmul");
+            Ct lowered = ev.mod_switch_to(boot_layer, boot_layer.limbs - 11);
+            inter = add_masked_bias(ev, ct_pt_matrix_mul_wo_pre(ev, lowered, w.inter_weight, w.inter), w.inter_bias,
+                                    bias_vec, scale);
+        }
+        {
+            PhaseTimer t(c, "gelu");
+            inter = gelu_v2(ev, inter, keys);
+        }
+        Ct fin;
+        {
+            PhaseTimer t(c, "final_matmul");
+            fin = add_masked_bias(ev, masked_matmul(ev, inter, w.final_weight, bias_vec, hidden), w.final_bias, bias_vec,
+                                  scale);
+            inter = Ct();
+        }
+        {
+            PhaseTimer t(c, "bootstrap_3");
+            fin = bootstrap_all(ev, fin, keys, boot, boot_chunk);
+        }
+        Ct ln2;
+        {
+            PhaseTimer t(c, "layernorm_2");
+            ev.add_inplace(fin, ev.mod_switch_to(boot_layer, fin.limbs)); // residual with the LN1 output
+            ln2 = layernorm(ev, fin, w.ln2_gamma, w.ln2_beta, bias_vec, keys, 2);
+        }
+        PhaseTimer t(c, "bootstrap_4");
+        return bootstrap_all(ev, ln2, keys, boot, boot_chunk);
+    }
 } // namespace moai

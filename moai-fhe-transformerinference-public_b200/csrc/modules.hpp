@@ -22,4 +22,25 @@ namespace moai
                         const std::vector<double> &WV, const std::vector<double> &bQ, const std::vector<double> &bK,
                         const std::vector<double> &bV, const std::vector<int> &bias_vec, int input_num,
                         const Keys &keys, Bootstrapper &boot, int num_batch, int iter, int layer_id);
+
+    // Weights of one BERT-base encoder layer as the reference driver reads them
+    // (M/test/test_full_scheme.hpp:94-337): all matrices row-major [in][out] doubles.
+    struct LayerWeights
+    {
+        int hidden = 768, heads = 12, head_dim = 64, inter = 3072;
+        std::vector<std::vector<double>> WQ, WK, WV; // [heads] each hidden x head_dim
+        std::vector<std::vector<double>> bQ, bK, bV; // [heads] each head_dim
+        std::vector<double> selfoutput, selfoutput_bias;     // hidden x hidden, hidden
+        std::vector<double> ln1_gamma, ln1_beta;             // hidden
+        std::vector<double> inter_weight, inter_bias;        // hidden x inter, inter
+        std::vector<double> final_weight, final_bias;        // inter x hidden, hidden
+        std::vector<double> ln2_gamma, ln2_beta;             // hidden
+    };
+
+    // One encoder layer of all_layer_test (M/test/test_full_scheme.hpp:484-1087): x = 768 column
+    // ciphertexts at chain_index 20; returns the layer output at chain_index 20 (after the 4th
+    // bootstrapping), ready to be the next layer's input.
+    Ct encoder_layer(const Evaluator &ev, const Ct &x, const LayerWeights &w, const std::vector<int> &bias_vec,
+                     int input_num, const Keys &keys, Bootstrapper &boot, int num_batch, int layer_id,
+                     long long boot_chunk);
 } // namespace moai
