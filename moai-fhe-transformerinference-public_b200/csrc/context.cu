@@ -7,6 +7,7 @@
 #include <cmath>
 #include <complex>
 #include <cstring>
+#include <cstdlib>
 
 namespace moai
 {
@@ -120,6 +121,8 @@ namespace moai
         cudaFree(d_limb);
         cudaFree(d_fwd);
         cudaFree(d_inv);
+        cudaFree(d_fwd_fp);
+        cudaFree(d_inv_fp);
         cudaFree(d_inv_last);
         cudaFree(d_half_mod);
         cudaFree(d_two64);
@@ -197,7 +200,14 @@ namespace moai
         c->sm_count = prop.multiProcessorCount;
 
         std::vector<Twiddle> fwd((size_t)kl * n), inv((size_t)kl * n);
+        std::vector<double> fwd_fp((size_t)kl * n), inv_fp((size_t)kl * n);
         c->h_limb.resize(kl);
+        // NTT arithmetic selection (see csrc/ntt.cuh).  MOAI_NTT_FP=0 forces the integer path;
+        // MOAI_NTT_WIDE_FP_EVERY=k sends every k-th 48..51-bit prime through the FP64 path too, the
+        // others stay on the integer pipe so that both pipes of an SM are busy in mixed batches.
+        const bool use_fp = !(getenv("MOAI_NTT_FP") && atoi(getenv("MOAI_NTT_FP")) == 0);
+        const int wide_every = getenv("MOAI_NTT_WIDE_FP_EVERY") ? atoi(getenv("MOAI_NTT_WIDE_FP_EVERY")) : 0;
+        int wide_seen = 0;
         for (int l = 0; l < kl; l++)
         {
             u64 q = primes[l];
@@ -227,7 +237,33 @@ namespace moai
             lc.inv_n_w = h_mulmod(g[n - 1].w, lc.inv_n, q); // last GS stage root times N^-1
             lc.inv_n_w_quo = h_shoup(lc.inv_n_w, q);
             lc.q0_mod = primes[0] % q;
+            auto sym = [&](u64 v) { return v > q / 2 ? -(double)(q - v) : (double)v; };
+            lc.pd = (double)q;
+            lc.pinv = 1.0 / (double)q;
+            lc.inv_n_d = sym(lc.inv_n);
+            lc.inv_n_w_d = sym(lc.inv_n_w);
+            lc.fp_class = 0;
+            lc.pad2 = 0;
+            if (use_fp && (q >> 48) == 0)
+            {
+                lc.fp_class = 1;
+            }
+            else if (use_fp && 2 * q + 64 < ((u64)1 << 52))
+            {
+                wide_seen++;
+                if (wide_every > 0 && wide_seen % wide_every == 0)
+                {
+                    lc.fp_class = 2;
+                }
+            }
+            for (size_t i = 0; i < n; i++)
+            {
+                fwd_fp[(size_t)l * n + i] = sym(f[i].w);
+                inv_fp[(size_t)l * n + i] = sym(g[i].w);
+            }
         }
+        c->d_fwd_fp = to_device(fwd_fp);
+        c->d_inv_fp = to_device(inv_fp);
         c->d_fwd = to_device(fwd);
         c->d_inv = to_device(inv);
         c->d_limb = to_device(c->h_limb);

@@ -75,6 +75,8 @@ namespace moai
         LimbConst *d_limb = nullptr;   // [kl]
         Twiddle *d_fwd = nullptr;      // [kl][n]  psi powers, bit-reversed order
         Twiddle *d_inv = nullptr;      // [kl][n]  psi^-1 powers, scrambled order
+        double *d_fwd_fp = nullptr;    // [kl][n]  the same roots as symmetric doubles (FP64 NTT path)
+        double *d_inv_fp = nullptr;    // [kl][n]
         Twiddle *d_inv_last = nullptr; // [kl][kl] inv_last[last][i] = q_last^-1 mod q_i (i != last)
         u64 *d_half_mod = nullptr;     // [kl][kl] half_mod[last][i] = (q_last >> 1) mod q_i
         Twiddle *d_two64 = nullptr;    // [kl] 2^64 mod q_i

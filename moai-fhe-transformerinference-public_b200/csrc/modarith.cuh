@@ -29,6 +29,11 @@ namespace moai
         u64 inv_n_w;   // (last inverse-NTT root * N^-1) mod q
         u64 inv_n_w_quo;
         u64 q0_mod;    // q_0 mod q  (ModRaise correction)
+        // FP64 NTT path (csrc/ntt.cu): 0 = integer path, 1 = p < 2^48, 2 = p < 2^51
+        double pd, pinv;
+        double inv_n_d, inv_n_w_d; // symmetric representatives of inv_n, inv_n_w
+        int fp_class;
+        int pad2;
     };
 
     struct u128

@@ -8,84 +8,265 @@ namespace moai
         constexpr int ROWS = 16;     // rows per pass-B CTA
         constexpr int ROW_PAD = 272; // 256 + 16: padded row, conflict-free stride-17 access
 
-        template <int COUNT>
-        __device__ __forceinline__ void load_tw(Twiddle (&tw)[8], const Twiddle *__restrict__ src)
+        // =====================================================================================
+        // Arithmetic policies.  A policy owns the per-limb constants and defines the element type
+        // kept in registers, how elements enter/leave global memory at the outer boundary
+        // (canonical uint64) and between the two passes (policy-private), and the butterflies.
+        // =====================================================================================
+
+        // ---- integer Harvey / Shoup (any prime < 2^61): values lazy in [0, 4q) forward, [0, 2q) inverse
+        struct IntField
         {
-#pragma unroll
-            for (int j = 0; j < COUNT; j++)
+            typedef u64 elem;
+            typedef Twiddle tw_t;
+            u64 q, two_q;
+            u64 inv_n, inv_n_quo, inv_n_w, inv_n_w_quo;
+            const Twiddle *__restrict__ tab;
+
+            __device__ IntField(const NttArgs &a, int limb, const LimbConst &lc)
+                : q(lc.q), two_q(lc.two_q), inv_n(lc.inv_n), inv_n_quo(lc.inv_n_quo), inv_n_w(lc.inv_n_w),
+                  inv_n_w_quo(lc.inv_n_w_quo), tab(a.tw + ((size_t)limb << a.log_n))
+            {}
+            __device__ __forceinline__ tw_t tw(size_t idx) const
             {
-                const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(src + j));
-                tw[j].w = v.x;
-                tw[j].wq = v.y;
+                const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(tab + idx));
+                return Twiddle{ v.x, v.y };
             }
-        }
+            __device__ __forceinline__ elem in_outer(u64 v) const { return v; }
+            __device__ __forceinline__ elem in_mid(u64 v) const { return v; }
+            __device__ __forceinline__ u64 out_mid(elem x) const { return x; }
+            __device__ __forceinline__ u64 out_fwd(elem x) const { return csub(csub(x, two_q), q); } // [0,4q)->[0,q)
+            __device__ __forceinline__ u64 out_inv(elem x) const { return csub(x, q); }              // [0,2q)->[0,q)
+            __device__ __forceinline__ void phase_begin_fwd(elem (&)[16]) const {}
+            __device__ __forceinline__ void phase_begin_inv(elem (&)[16]) const {}
+            __device__ __forceinline__ void ct(elem &x, elem &y, const tw_t &w) const
+            {
+                const u64 u = csub(x, two_q);
+                const u64 v = mul_shoup_lazy(y, w.w, w.wq, q);
+                x = u + v;
+                y = u + two_q - v;
+            }
+            __device__ __forceinline__ void gs(elem &x, elem &y, const tw_t &w) const
+            {
+                const u64 u = x, v = y;
+                x = csub(u + v, two_q);
+                y = mul_shoup_lazy(u + two_q - v, w.w, w.wq, q);
+            }
+            __device__ __forceinline__ void gs_last(elem &x, elem &y) const
+            {
+                const u64 u = x, v = y;
+                x = mul_shoup_lazy(csub(u + v, two_q), inv_n, inv_n_quo, q);
+                y = mul_shoup_lazy(u + two_q - v, inv_n_w, inv_n_w_quo, q);
+            }
+        };
 
-        // ------------------------------------------------------------------ forward, pass A
-        template <int LOGR>
-        __global__ void __launch_bounds__((1 << LOGR) / 16 * TB) ntt_fwd_pass_a(NttArgs a)
+        // ---- exact FP64 path for primes p < 2^51.
+        // Residues are integer-valued doubles.  With M = 1.5 * 2^52, rnd(x) = (x + M) - M is
+        // round-to-nearest-integer for |x| < 2^51.
+        //   red(x)      = x - rnd(x/p) p                 : |x| < 2^53  ->  |red| <= p/2 + 1
+        //   mul(a, w)   : h = fl(a w), l = fma(a, w, -h) (so a w = h + l exactly),
+        //                 r = fma(-rnd(h/p), p, h) + l   : needs |a| < 2^52, |w| <= p/2;
+        //                 |r| <= 1.125 p for p < 2^51 and <= 0.52 p for p < 2^48 (error terms: rounding of
+        //                 h/p, of 1/p, and |l| <= ulp(h)/2); r is an exact integer because h - t p is an
+        //                 integer below 2^53.
+        // WIDE  (2^48 <= p, 2p + 64 < 2^52): mul() is followed by red() so |v| <= p/2 + 1; the 16
+        //        registers are reduced at the start of each 4-stage phase, so the multiplier input
+        //        grows 0.5p -> 1.0p -> 1.5p -> 2.0p (< 2^52) and sums stay below 2.5p < 2^53.
+        // NARROW (p < 2^48): 32p of headroom below 2^53; no intermediate reductions in the forward
+        //        transform (|x| <= 2p + 8 * 0.52p per pass); in the inverse, sums double for at most 4
+        //        stages between the phase reductions.
+        template <bool WIDE>
+        struct FpField
         {
-            constexpr int R = 1 << LOGR, T1 = R / 16;
-            __shared__ u64 sm[R * TB];
-            const int tb = threadIdx.x & (TB - 1), t = threadIdx.x >> 4;
-            const long long poly = blockIdx.x / (256 / TB);
-            const int tile = blockIdx.x % (256 / TB);
-            const int limb = a.limb_ids[(poly / a.div) % a.period];
-            const LimbConst lc = a.limb[limb];
-            const Twiddle *__restrict__ tw_tab = a.tw + ((size_t)limb << a.log_n);
-            u64 *base = a.data + ((size_t)poly << a.log_n) + tile * TB + tb;
-            const u64 q = lc.q, two_q = lc.two_q;
+            typedef double elem;
+            typedef double tw_t;
+            double p, pinv, inv_n, inv_n_w;
+            const double *__restrict__ tab;
 
-            u64 x[16];
-            Twiddle tw[8];
+            __device__ FpField(const NttArgs &a, int limb, const LimbConst &lc)
+                : p(lc.pd), pinv(lc.pinv), inv_n(lc.inv_n_d), inv_n_w(lc.inv_n_w_d),
+                  tab(a.tw_fp + ((size_t)limb << a.log_n))
+            {}
+            __device__ __forceinline__ tw_t tw(size_t idx) const { return __ldg(tab + idx); }
+            static __device__ __forceinline__ double rnd(double x)
+            {
+                const double M = 6755399441055744.0;
+                return __dadd_rn(__dadd_rn(x, M), -M);
+            }
+            __device__ __forceinline__ double red(double x) const
+            {
+                return __fma_rn(-rnd(__dmul_rn(x, pinv)), p, x);
+            }
+            __device__ __forceinline__ double mul(double a, double w) const
+            {
+                const double h = __dmul_rn(a, w);
+                const double l = __fma_rn(a, w, -h);
+                const double r = __dadd_rn(__fma_rn(-rnd(__dmul_rn(h, pinv)), p, h), l);
+                return WIDE ? red(r) : r;
+            }
+            // canonical / lazy uint64 below 2^52 -> double, exactly (bit trick, no I2F)
+            __device__ __forceinline__ elem in_outer(u64 v) const
+            {
+                return __dadd_rn(__longlong_as_double((long long)(v | 0x4330000000000000ull)), -4503599627370496.0);
+            }
+            __device__ __forceinline__ elem in_mid(u64 v) const { return __longlong_as_double((long long)v); }
+            __device__ __forceinline__ u64 out_mid(elem x) const { return (u64)__double_as_longlong(x); }
+            __device__ __forceinline__ u64 canon(elem x) const
+            {
+                double r = red(x);
+                r = r < 0.0 ? __dadd_rn(r, p) : r;
+                r = r >= p ? __dadd_rn(r, -p) : r;
+                return (u64)__double_as_longlong(__dadd_rn(r, 4503599627370496.0)) & 0x000FFFFFFFFFFFFFull;
+            }
+            __device__ __forceinline__ u64 out_fwd(elem x) const { return canon(x); }
+            __device__ __forceinline__ u64 out_inv(elem x) const { return canon(x); }
+            // forward: only the WIDE class needs the per-phase reduction; inverse: only NARROW does
+            // (WIDE reduces every sum inside gs()).
+            __device__ __forceinline__ void phase_begin_fwd(elem (&x)[16]) const
+            {
+                if (WIDE)
+                {
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                    {
+                        x[k] = red(x[k]);
+                    }
+                }
+            }
+            __device__ __forceinline__ void phase_begin_inv(elem (&x)[16]) const
+            {
+                if (!WIDE)
+                {
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                    {
+                        x[k] = red(x[k]);
+                    }
+                }
+            }
+            __device__ __forceinline__ void ct(elem &x, elem &y, const tw_t &w) const
+            {
+                const double v = mul(y, w);
+                const double u = x;
+                x = __dadd_rn(u, v);
+                y = __dadd_rn(u, -v);
+            }
+            __device__ __forceinline__ void gs(elem &x, elem &y, const tw_t &w) const
+            {
+                const double u = x, v = y;
+                const double s = __dadd_rn(u, v);
+                x = WIDE ? red(s) : s;
+                y = mul(__dadd_rn(u, -v), w);
+            }
+            __device__ __forceinline__ void gs_last(elem &x, elem &y) const
+            {
+                const double u = x, v = y;
+                x = mul(__dadd_rn(u, v), inv_n);
+                y = mul(__dadd_rn(u, -v), inv_n_w);
+            }
+        };
+
+        // ---- register stages over 16 elements; tw index of the j-th block of 2*GAP is base + j
+        template <int GAP, class F>
+        __device__ __forceinline__ void ct_stage(const F &f, typename F::elem (&x)[16], size_t tw_base)
+        {
+            typename F::tw_t tw[8 / GAP];
+#pragma unroll
+            for (int j = 0; j < 8 / GAP; j++)
+            {
+                tw[j] = f.tw(tw_base + j);
+            }
 #pragma unroll
             for (int k = 0; k < 16; k++)
             {
-                x[k] = base[(size_t)(t + T1 * k) * 256];
+                if (!(k & GAP))
+                {
+                    f.ct(x[k], x[k + GAP], tw[k / (2 * GAP)]);
+                }
             }
+        }
+
+        template <int GAP, class F>
+        __device__ __forceinline__ void gs_stage(const F &f, typename F::elem (&x)[16], size_t tw_base)
+        {
+            typename F::tw_t tw[8 / GAP];
+#pragma unroll
+            for (int j = 0; j < 8 / GAP; j++)
+            {
+                tw[j] = f.tw(tw_base + j);
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+            {
+                if (!(k & GAP))
+                {
+                    f.gs(x[k], x[k + GAP], tw[k / (2 * GAP)]);
+                }
+            }
+        }
+
+        template <class F>
+        __device__ __forceinline__ void gs_stage_last(const F &f, typename F::elem (&x)[16])
+        {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+            {
+                f.gs_last(x[k], x[k + 8]);
+            }
+        }
+
+        // =====================================================================================
+        // Pass bodies (policy-generic).  `sm` is the CTA's shared buffer viewed as 8-byte words.
+        // =====================================================================================
+        template <int LOGR, class F>
+        __device__ __forceinline__ void fwd_pass_a_body(const F &f, u64 *base, u64 *sm, int t, int tb)
+        {
+            constexpr int R = 1 << LOGR, T1 = R / 16;
+            typename F::elem x[16];
+            typename F::elem *smf = reinterpret_cast<typename F::elem *>(sm);
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+            {
+                x[k] = f.in_outer(base[(size_t)(t + T1 * k) * 256]);
+            }
+            f.phase_begin_fwd(x);
             // stages 0..3 pair the top four bits of a (k): root index 2^s + block
-            load_tw<1>(tw, tw_tab + 1);
-            ct_stage<8>(x, tw, q, two_q);
-            load_tw<2>(tw, tw_tab + 2);
-            ct_stage<4>(x, tw, q, two_q);
-            load_tw<4>(tw, tw_tab + 4);
-            ct_stage<2>(x, tw, q, two_q);
-            load_tw<8>(tw, tw_tab + 8);
-            ct_stage<1>(x, tw, q, two_q);
+            ct_stage<8>(f, x, 1);
+            ct_stage<4>(f, x, 2);
+            ct_stage<2>(f, x, 4);
+            ct_stage<1>(f, x, 8);
             if constexpr (LOGR > 4)
             {
 #pragma unroll
                 for (int k = 0; k < 16; k++)
                 {
-                    sm[(t + T1 * k) * TB + tb] = x[k];
+                    smf[(t + T1 * k) * TB + tb] = x[k];
                 }
                 __syncthreads();
 #pragma unroll
                 for (int k = 0; k < 16; k++)
                 {
-                    x[k] = sm[(16 * t + k) * TB + tb];
+                    x[k] = smf[(16 * t + k) * TB + tb];
                 }
+                f.phase_begin_fwd(x);
                 // remaining stages: a = 16 t + k, row gap G in {R/32 .. 1}; root index R/(2G) + a/(2G)
                 if constexpr (R / 32 >= 8)
                 {
-                    load_tw<1>(tw, tw_tab + R / 16 + t);
-                    ct_stage<8>(x, tw, q, two_q);
+                    ct_stage<8>(f, x, R / 16 + t);
                 }
                 if constexpr (R / 32 >= 4)
                 {
-                    load_tw<2>(tw, tw_tab + R / 8 + 2 * t);
-                    ct_stage<4>(x, tw, q, two_q);
+                    ct_stage<4>(f, x, R / 8 + 2 * t);
                 }
                 if constexpr (R / 32 >= 2)
                 {
-                    load_tw<4>(tw, tw_tab + R / 4 + 4 * t);
-                    ct_stage<2>(x, tw, q, two_q);
+                    ct_stage<2>(f, x, R / 4 + 4 * t);
                 }
-                load_tw<8>(tw, tw_tab + R / 2 + 8 * t);
-                ct_stage<1>(x, tw, q, two_q);
+                ct_stage<1>(f, x, R / 2 + 8 * t);
 #pragma unroll
                 for (int k = 0; k < 16; k++)
                 {
-                    base[(size_t)(16 * t + k) * 256] = x[k];
+                    base[(size_t)(16 * t + k) * 256] = f.out_mid(x[k]);
                 }
             }
             else
@@ -93,43 +274,27 @@ namespace moai
 #pragma unroll
                 for (int k = 0; k < 16; k++)
                 {
-                    base[(size_t)(t + T1 * k) * 256] = x[k];
+                    base[(size_t)(t + T1 * k) * 256] = f.out_mid(x[k]);
                 }
             }
         }
 
-        // ------------------------------------------------------------------ forward, pass B
-        __global__ void __launch_bounds__(ROWS * 16) ntt_fwd_pass_b(NttArgs a)
+        template <class F>
+        __device__ __forceinline__ void fwd_pass_b_body(const F &f, u64 *base, u64 *srow64, int t, size_t ra)
         {
-            __shared__ u64 sm[ROWS * ROW_PAD];
-            const int t = threadIdx.x & 15, r = threadIdx.x >> 4;
-            const int R = 1 << (a.log_n - 8);
-            const int ctas_per_poly = R / ROWS;
-            const long long poly = blockIdx.x / ctas_per_poly;
-            const int row = (blockIdx.x % ctas_per_poly) * ROWS + r;
-            const int limb = a.limb_ids[(poly / a.div) % a.period];
-            const LimbConst lc = a.limb[limb];
-            const Twiddle *__restrict__ tw_tab = a.tw + ((size_t)limb << a.log_n);
-            u64 *base = a.data + ((size_t)poly << a.log_n) + (size_t)row * 256;
-            const u64 q = lc.q, two_q = lc.two_q;
-            const size_t ra = (size_t)R + row; // root index of stage t' is 2^t' (R + a) + b / (2 gap)
-
-            u64 x[16];
-            Twiddle tw[8];
+            typename F::elem x[16];
+            typename F::elem *srow = reinterpret_cast<typename F::elem *>(srow64);
 #pragma unroll
             for (int k = 0; k < 16; k++)
             {
-                x[k] = base[t + 16 * k];
+                x[k] = f.in_mid(base[t + 16 * k]);
             }
-            load_tw<1>(tw, tw_tab + ra);
-            ct_stage<8>(x, tw, q, two_q);
-            load_tw<2>(tw, tw_tab + 2 * ra);
-            ct_stage<4>(x, tw, q, two_q);
-            load_tw<4>(tw, tw_tab + 4 * ra);
-            ct_stage<2>(x, tw, q, two_q);
-            load_tw<8>(tw, tw_tab + 8 * ra);
-            ct_stage<1>(x, tw, q, two_q);
-            u64 *srow = sm + r * ROW_PAD;
+            f.phase_begin_fwd(x);
+            // root index of stage t' is 2^t' (R + a) + b / (2 gap)
+            ct_stage<8>(f, x, ra);
+            ct_stage<4>(f, x, 2 * ra);
+            ct_stage<2>(f, x, 4 * ra);
+            ct_stage<1>(f, x, 8 * ra);
 #pragma unroll
             for (int k = 0; k < 16; k++)
             {
@@ -141,62 +306,40 @@ namespace moai
             {
                 x[k] = srow[17 * t + k];
             }
-            load_tw<1>(tw, tw_tab + 16 * ra + t);
-            ct_stage<8>(x, tw, q, two_q);
-            load_tw<2>(tw, tw_tab + 32 * ra + 2 * t);
-            ct_stage<4>(x, tw, q, two_q);
-            load_tw<4>(tw, tw_tab + 64 * ra + 4 * t);
-            ct_stage<2>(x, tw, q, two_q);
-            load_tw<8>(tw, tw_tab + 128 * ra + 8 * t);
-            ct_stage<1>(x, tw, q, two_q);
-            // canonical residues out: [0, 4q) -> [0, q)   (S/util/ntt.cpp:425-434)
+            f.phase_begin_fwd(x);
+            ct_stage<8>(f, x, 16 * ra + t);
+            ct_stage<4>(f, x, 32 * ra + 2 * t);
+            ct_stage<2>(f, x, 64 * ra + 4 * t);
+            ct_stage<1>(f, x, 128 * ra + 8 * t);
             ulonglong2 *out = reinterpret_cast<ulonglong2 *>(base + 16 * t);
 #pragma unroll
             for (int k = 0; k < 16; k += 2)
             {
                 ulonglong2 v;
-                v.x = csub(csub(x[k], two_q), q);
-                v.y = csub(csub(x[k + 1], two_q), q);
+                v.x = f.out_fwd(x[k]);
+                v.y = f.out_fwd(x[k + 1]);
                 out[k >> 1] = v;
             }
         }
 
-        // ------------------------------------------------------------------ inverse, pass B'
-        __global__ void __launch_bounds__(ROWS * 16) ntt_inv_pass_b(NttArgs a)
+        template <class F>
+        __device__ __forceinline__ void inv_pass_b_body(const F &f, u64 *base, u64 *srow64, int t, size_t row, size_t n)
         {
-            __shared__ u64 sm[ROWS * ROW_PAD];
-            const int t = threadIdx.x & 15, r = threadIdx.x >> 4;
-            const int R = 1 << (a.log_n - 8);
-            const size_t n = (size_t)1 << a.log_n;
-            const int ctas_per_poly = R / ROWS;
-            const long long poly = blockIdx.x / ctas_per_poly;
-            const int row = (blockIdx.x % ctas_per_poly) * ROWS + r;
-            const int limb = a.limb_ids[(poly / a.div) % a.period];
-            const LimbConst lc = a.limb[limb];
-            const Twiddle *__restrict__ tw_tab = a.tw + ((size_t)limb << a.log_n);
-            u64 *base = a.data + ((size_t)poly << a.log_n) + (size_t)row * 256;
-            const u64 q = lc.q, two_q = lc.two_q;
-
-            u64 x[16];
-            Twiddle tw[8];
+            typename F::elem x[16];
+            typename F::elem *srow = reinterpret_cast<typename F::elem *>(srow64);
             const ulonglong2 *in = reinterpret_cast<const ulonglong2 *>(base + 16 * t);
 #pragma unroll
             for (int k = 0; k < 16; k += 2)
             {
-                ulonglong2 v = in[k >> 1];
-                x[k] = v.x;
-                x[k + 1] = v.y;
+                const ulonglong2 v = in[k >> 1];
+                x[k] = f.in_outer(v.x);
+                x[k + 1] = f.in_outer(v.y);
             }
             // stage with gap g: root index n - n/g + 1 + row*(128/g) + b/(2g); here b = 16 t + k
-            load_tw<8>(tw, tw_tab + (n - n + 1) + (size_t)row * 128 + 8 * t);
-            gs_stage<1>(x, tw, q, two_q);
-            load_tw<4>(tw, tw_tab + (n - n / 2 + 1) + (size_t)row * 64 + 4 * t);
-            gs_stage<2>(x, tw, q, two_q);
-            load_tw<2>(tw, tw_tab + (n - n / 4 + 1) + (size_t)row * 32 + 2 * t);
-            gs_stage<4>(x, tw, q, two_q);
-            load_tw<1>(tw, tw_tab + (n - n / 8 + 1) + (size_t)row * 16 + t);
-            gs_stage<8>(x, tw, q, two_q);
-            u64 *srow = sm + r * ROW_PAD;
+            gs_stage<1>(f, x, (n - n + 1) + row * 128 + 8 * t);
+            gs_stage<2>(f, x, (n - n / 2 + 1) + row * 64 + 4 * t);
+            gs_stage<4>(f, x, (n - n / 4 + 1) + row * 32 + 2 * t);
+            gs_stage<8>(f, x, (n - n / 8 + 1) + row * 16 + t);
 #pragma unroll
             for (int k = 0; k < 16; k++)
             {
@@ -208,96 +351,152 @@ namespace moai
             {
                 x[k] = srow[t + 17 * k];
             }
+            f.phase_begin_inv(x);
             // b = t + 16 k ; gaps 16, 32, 64, 128
-            load_tw<8>(tw, tw_tab + (n - n / 16 + 1) + (size_t)row * 8);
-            gs_stage<1>(x, tw, q, two_q);
-            load_tw<4>(tw, tw_tab + (n - n / 32 + 1) + (size_t)row * 4);
-            gs_stage<2>(x, tw, q, two_q);
-            load_tw<2>(tw, tw_tab + (n - n / 64 + 1) + (size_t)row * 2);
-            gs_stage<4>(x, tw, q, two_q);
-            load_tw<1>(tw, tw_tab + (n - n / 128 + 1) + (size_t)row);
-            gs_stage<8>(x, tw, q, two_q);
+            gs_stage<1>(f, x, (n - n / 16 + 1) + row * 8);
+            gs_stage<2>(f, x, (n - n / 32 + 1) + row * 4);
+            gs_stage<4>(f, x, (n - n / 64 + 1) + row * 2);
+            gs_stage<8>(f, x, (n - n / 128 + 1) + row);
+            f.phase_begin_inv(x);
 #pragma unroll
             for (int k = 0; k < 16; k++)
             {
-                base[t + 16 * k] = x[k];
+                base[t + 16 * k] = f.out_mid(x[k]);
             }
         }
 
-        // ------------------------------------------------------------------ inverse, pass A'
+        template <int LOGR, class F>
+        __device__ __forceinline__ void inv_pass_a_body(const F &f, u64 *base, u64 *sm, int t, int tb, size_t n)
+        {
+            constexpr int R = 1 << LOGR, T1 = R / 16;
+            typename F::elem x[16];
+            typename F::elem *smf = reinterpret_cast<typename F::elem *>(sm);
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+            {
+                x[k] = f.in_mid(base[(size_t)(16 * t + k) * 256]);
+            }
+            // row gap G: root index n - R/G + 1 + a/(2G), a = 16 t + k
+            gs_stage<1>(f, x, (n - R + 1) + 8 * t);
+            gs_stage<2>(f, x, (n - R / 2 + 1) + 4 * t);
+            gs_stage<4>(f, x, (n - R / 4 + 1) + 2 * t);
+            if constexpr (LOGR == 4)
+            {
+                gs_stage_last(f, x);
+            }
+            else
+            {
+                gs_stage<8>(f, x, (n - R / 8 + 1) + t);
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                {
+                    smf[(16 * t + k) * TB + tb] = x[k];
+                }
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                {
+                    x[k] = smf[(t + T1 * k) * TB + tb];
+                }
+                f.phase_begin_inv(x);
+                // a = t + T1 k ; row gaps G = T1 * kgap for kgap >= 256 / R
+                if constexpr (256 / R <= 1)
+                {
+                    gs_stage<1>(f, x, n - R / T1 + 1);
+                }
+                if constexpr (256 / R <= 2)
+                {
+                    gs_stage<2>(f, x, n - R / (2 * T1) + 1);
+                }
+                if constexpr (256 / R <= 4)
+                {
+                    gs_stage<4>(f, x, n - R / (4 * T1) + 1);
+                }
+                gs_stage_last(f, x);
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+            {
+                const int row = (LOGR == 4) ? (16 * t + k) : (t + T1 * k);
+                base[(size_t)row * 256] = f.out_inv(x[k]);
+            }
+        }
+
+        // =====================================================================================
+        // Kernels: resolve (poly, tile) -> limb, pick the arithmetic path of that limb.
+        // =====================================================================================
+#define MOAI_DISPATCH_FIELD(lc, CALL)                                                                                  \
+    if ((lc).fp_class == 1)                                                                                            \
+    {                                                                                                                  \
+        const FpField<false> f(a, limb, lc);                                                                           \
+        CALL;                                                                                                          \
+    }                                                                                                                  \
+    else if ((lc).fp_class == 2)                                                                                       \
+    {                                                                                                                  \
+        const FpField<true> f(a, limb, lc);                                                                            \
+        CALL;                                                                                                          \
+    }                                                                                                                  \
+    else                                                                                                               \
+    {                                                                                                                  \
+        const IntField f(a, limb, lc);                                                                                 \
+        CALL;                                                                                                          \
+    }
+
+        template <int LOGR>
+        __global__ void __launch_bounds__((1 << LOGR) / 16 * TB) ntt_fwd_pass_a(NttArgs a)
+        {
+            __shared__ u64 sm[(1 << LOGR) * TB];
+            const int tb = threadIdx.x & (TB - 1), t = threadIdx.x >> 4;
+            const long long poly = blockIdx.x / (256 / TB);
+            const int tile = blockIdx.x % (256 / TB);
+            const int limb = a.limb_ids[(poly / a.div) % a.period];
+            const LimbConst lc = a.limb[limb];
+            u64 *base = a.data + ((size_t)poly << a.log_n) + tile * TB + tb;
+            MOAI_DISPATCH_FIELD(lc, (fwd_pass_a_body<LOGR>(f, base, sm, t, tb)))
+        }
+
+        __global__ void __launch_bounds__(ROWS * 16) ntt_fwd_pass_b(NttArgs a)
+        {
+            __shared__ u64 sm[ROWS * ROW_PAD];
+            const int t = threadIdx.x & 15, r = threadIdx.x >> 4;
+            const int R = 1 << (a.log_n - 8);
+            const int ctas_per_poly = R / ROWS;
+            const long long poly = blockIdx.x / ctas_per_poly;
+            const int row = (blockIdx.x % ctas_per_poly) * ROWS + r;
+            const int limb = a.limb_ids[(poly / a.div) % a.period];
+            const LimbConst lc = a.limb[limb];
+            u64 *base = a.data + ((size_t)poly << a.log_n) + (size_t)row * 256;
+            const size_t ra = (size_t)R + row;
+            MOAI_DISPATCH_FIELD(lc, (fwd_pass_b_body(f, base, sm + r * ROW_PAD, t, ra)))
+        }
+
+        __global__ void __launch_bounds__(ROWS * 16) ntt_inv_pass_b(NttArgs a)
+        {
+            __shared__ u64 sm[ROWS * ROW_PAD];
+            const int t = threadIdx.x & 15, r = threadIdx.x >> 4;
+            const int R = 1 << (a.log_n - 8);
+            const size_t n = (size_t)1 << a.log_n;
+            const int ctas_per_poly = R / ROWS;
+            const long long poly = blockIdx.x / ctas_per_poly;
+            const int row = (blockIdx.x % ctas_per_poly) * ROWS + r;
+            const int limb = a.limb_ids[(poly / a.div) % a.period];
+            const LimbConst lc = a.limb[limb];
+            u64 *base = a.data + ((size_t)poly << a.log_n) + (size_t)row * 256;
+            MOAI_DISPATCH_FIELD(lc, (inv_pass_b_body(f, base, sm + r * ROW_PAD, t, (size_t)row, n)))
+        }
+
         template <int LOGR>
         __global__ void __launch_bounds__((1 << LOGR) / 16 * TB) ntt_inv_pass_a(NttArgs a)
         {
-            constexpr int R = 1 << LOGR, T1 = R / 16;
-            __shared__ u64 sm[R * TB];
+            __shared__ u64 sm[(1 << LOGR) * TB];
             const int tb = threadIdx.x & (TB - 1), t = threadIdx.x >> 4;
             const size_t n = (size_t)1 << a.log_n;
             const long long poly = blockIdx.x / (256 / TB);
             const int tile = blockIdx.x % (256 / TB);
             const int limb = a.limb_ids[(poly / a.div) % a.period];
             const LimbConst lc = a.limb[limb];
-            const Twiddle *__restrict__ tw_tab = a.tw + ((size_t)limb << a.log_n);
             u64 *base = a.data + ((size_t)poly << a.log_n) + tile * TB + tb;
-            const u64 q = lc.q, two_q = lc.two_q;
-
-            u64 x[16];
-            Twiddle tw[8];
-#pragma unroll
-            for (int k = 0; k < 16; k++)
-            {
-                x[k] = base[(size_t)(16 * t + k) * 256];
-            }
-            // row gap G: root index n - R/G + 1 + a/(2G), a = 16 t + k
-            load_tw<8>(tw, tw_tab + (n - R + 1) + 8 * t);
-            gs_stage<1>(x, tw, q, two_q);
-            load_tw<4>(tw, tw_tab + (n - R / 2 + 1) + 4 * t);
-            gs_stage<2>(x, tw, q, two_q);
-            load_tw<2>(tw, tw_tab + (n - R / 4 + 1) + 2 * t);
-            gs_stage<4>(x, tw, q, two_q);
-            if constexpr (LOGR == 4)
-            {
-                gs_stage_last(x, lc);
-            }
-            else
-            {
-                load_tw<1>(tw, tw_tab + (n - R / 8 + 1) + t);
-                gs_stage<8>(x, tw, q, two_q);
-#pragma unroll
-                for (int k = 0; k < 16; k++)
-                {
-                    sm[(16 * t + k) * TB + tb] = x[k];
-                }
-                __syncthreads();
-#pragma unroll
-                for (int k = 0; k < 16; k++)
-                {
-                    x[k] = sm[(t + T1 * k) * TB + tb];
-                }
-                // a = t + T1 k ; row gaps G = T1 * kgap for kgap >= 256 / R
-                if constexpr (256 / R <= 1)
-                {
-                    load_tw<8>(tw, tw_tab + (n - R / T1 + 1));
-                    gs_stage<1>(x, tw, q, two_q);
-                }
-                if constexpr (256 / R <= 2)
-                {
-                    load_tw<4>(tw, tw_tab + (n - R / (2 * T1) + 1));
-                    gs_stage<2>(x, tw, q, two_q);
-                }
-                if constexpr (256 / R <= 4)
-                {
-                    load_tw<2>(tw, tw_tab + (n - R / (4 * T1) + 1));
-                    gs_stage<4>(x, tw, q, two_q);
-                }
-                gs_stage_last(x, lc);
-            }
-            // canonical residues out: [0, 2q) -> [0, q)   (S/util/ntt.cpp:466-472)
-#pragma unroll
-            for (int k = 0; k < 16; k++)
-            {
-                const int row = (LOGR == 4) ? (16 * t + k) : (t + T1 * k);
-                base[(size_t)row * 256] = csub(x[k], q);
-            }
+            MOAI_DISPATCH_FIELD(lc, (inv_pass_a_body<LOGR>(f, base, sm, t, tb, n)))
         }
 
         template <int LOGR>
@@ -325,7 +524,7 @@ namespace moai
         {
             return;
         }
-        NttArgs a{ data, c->d_fwd, c->d_limb, d_limb_ids, period, div, c->log_n, count };
+        NttArgs a{ data, c->d_fwd, c->d_fwd_fp, c->d_limb, d_limb_ids, period, div, c->log_n, count };
         switch (c->log_n)
         {
         case 12: launch_fwd<4>(a, c->stream); break;
@@ -345,7 +544,7 @@ namespace moai
         {
             return;
         }
-        NttArgs a{ data, c->d_inv, c->d_limb, d_limb_ids, period, div, c->log_n, count };
+        NttArgs a{ data, c->d_inv, c->d_inv_fp, c->d_limb, d_limb_ids, period, div, c->log_n, count };
         switch (c->log_n)
         {
         case 12: launch_inv<4>(a, c->stream); break;

@@ -4,6 +4,7 @@
 // (forward: DWTHandler::transform_to_rev, S/util/dwthandler.h:94-191, natural -> bit-reversed;
 //  inverse: transform_from_rev, S/util/dwthandler.h:202-356, bit-reversed -> natural with N^-1
 //  folded into the last stage), with the tables of NTTTables::initialize (S/util/ntt.cpp:241-300).
+// All public results are canonical residues, so the internal arithmetic is free.
 //
 // B200 mapping (N = 2^logN, viewed as R x 256 with R = N/256; i = a*256 + b):
 //   pass A : the logN-8 stages that pair rows (gap >= 256).  One CTA owns all R rows of 16
@@ -13,10 +14,17 @@
 //   pass B : the 8 stages inside a 256-element row.  One CTA owns 16 rows; 4 + 4 register
 //            stages with one padded (conflict-free) shared-memory transpose.
 // A limb (512 KiB at N = 65536) exceeds one SM's shared memory, hence two passes: 2 MiB of
-// traffic per limb-transform against the 1 MiB algorithmic floor; the pass-A -> pass-B
-// intermediate of a batch stays L2-resident when the batch fits in the 126 MB L2.
-// Butterflies use lazy Harvey arithmetic in [0, 4q) with Shoup twiddles (one 16-byte load per
-// twiddle); the ALU cost (64-bit mul-hi emulated by IMAD.WIDE) is what bounds this kernel.
+// traffic per limb-transform against the 1 MiB algorithmic floor.
+//
+// Arithmetic.  B200 has no 64-bit integer multiplier and IMAD.WIDE (32x32->64) issues at a
+// quarter of the FP64 FMA rate (tools/microbench.cu, profiles/), so the integer Shoup butterfly is
+// multiplier-bound at ~0.9 us per limb-transform.  Two exact paths are therefore compiled and
+// selected per limb (CTA-uniform):
+//   * FP64 path for primes below 2^51 (all 35 data primes of the repo's chain): residues are
+//     integer-valued doubles in a symmetric lazy range; x*w mod p = (h + l) - rint(h/p) p with
+//     h = fl(x w), l = fma(x, w, -h) — every step is exact because all intermediate integers stay
+//     below 2^53 (bounds in csrc/ntt.cu).  No precomputed Shoup quotient: 8-byte twiddles.
+//   * integer Harvey/Shoup path (lazy [0, 4q)) for wider primes (the 58-bit special prime).
 #pragma once
 #include "context.hpp"
 
@@ -25,7 +33,8 @@ namespace moai
     struct NttArgs
     {
         u64 *data;             // [count][n]
-        const Twiddle *tw;     // forward or inverse table, [kl][n]
+        const Twiddle *tw;     // integer path: forward or inverse Shoup table, [kl][n]
+        const double *tw_fp;   // FP64 path: the same roots as symmetric doubles, [kl][n]
         const LimbConst *limb; // [kl]
         const int *limb_ids;   // [period]; poly p uses prime limb_ids[(p / div) % period]
         int period;
@@ -33,54 +42,6 @@ namespace moai
         int log_n;
         long long count;
     };
-
-    // ---- register butterfly stages over 16 residues ------------------------------------------
-    // Cooley-Tukey stage pairing k and k+GAP; tw[j] is the twiddle of the j-th block of 2*GAP.
-    template <int GAP>
-    __device__ __forceinline__ void ct_stage(u64 (&x)[16], const Twiddle (&tw)[8], u64 q, u64 two_q)
-    {
-#pragma unroll
-        for (int k = 0; k < 16; k++)
-        {
-            if (!(k & GAP))
-            {
-                const Twiddle w = tw[k / (2 * GAP)];
-                u64 u = csub(x[k], two_q);
-                u64 v = mul_shoup_lazy(x[k + GAP], w.w, w.wq, q);
-                x[k] = u + v;
-                x[k + GAP] = u + two_q - v;
-            }
-        }
-    }
-
-    // Gentleman-Sande stage pairing k and k+GAP.
-    template <int GAP>
-    __device__ __forceinline__ void gs_stage(u64 (&x)[16], const Twiddle (&tw)[8], u64 q, u64 two_q)
-    {
-#pragma unroll
-        for (int k = 0; k < 16; k++)
-        {
-            if (!(k & GAP))
-            {
-                const Twiddle w = tw[k / (2 * GAP)];
-                u64 u = x[k], v = x[k + GAP];
-                x[k] = csub(u + v, two_q);
-                x[k + GAP] = mul_shoup_lazy(u + two_q - v, w.w, w.wq, q);
-            }
-        }
-    }
-
-    // Last inverse stage (GAP = 8 of the final phase): output scaled by N^-1.
-    __device__ __forceinline__ void gs_stage_last(u64 (&x)[16], const LimbConst &lc)
-    {
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-        {
-            u64 u = x[k], v = x[k + 8];
-            x[k] = mul_shoup_lazy(csub(u + v, lc.two_q), lc.inv_n, lc.inv_n_quo, lc.q);
-            x[k + 8] = mul_shoup_lazy(u + lc.two_q - v, lc.inv_n_w, lc.inv_n_w_quo, lc.q);
-        }
-    }
 
     // Transforms `count` consecutive polynomials in place; polynomial p lives at data + p*n and
     // uses the prime with index d_limb_ids[(p / div) % period].
