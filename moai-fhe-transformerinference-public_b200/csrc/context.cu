@@ -203,10 +203,11 @@ namespace moai
         std::vector<double> fwd_fp((size_t)kl * n), inv_fp((size_t)kl * n);
         c->h_limb.resize(kl);
         // NTT arithmetic selection (see csrc/ntt.cuh).  MOAI_NTT_FP=0 forces the integer path;
-        // MOAI_NTT_WIDE_FP_EVERY=k sends every k-th 48..51-bit prime through the FP64 path too, the
-        // others stay on the integer pipe so that both pipes of an SM are busy in mixed batches.
+        // MOAI_NTT_WIDE_FP_EVERY=k sends every k-th 48..51-bit prime through the FP64 path (default 1 =
+        // all of them; 0 = none).  Measured on B200 (profiles/ntt_arith_r1.md): all-FP64 is fastest; leaving
+        // part of the wide primes on the integer pipe does not overlap the two pipes enough to pay.
         const bool use_fp = !(getenv("MOAI_NTT_FP") && atoi(getenv("MOAI_NTT_FP")) == 0);
-        const int wide_every = getenv("MOAI_NTT_WIDE_FP_EVERY") ? atoi(getenv("MOAI_NTT_WIDE_FP_EVERY")) : 0;
+        const int wide_every = getenv("MOAI_NTT_WIDE_FP_EVERY") ? atoi(getenv("MOAI_NTT_WIDE_FP_EVERY")) : 1;
         int wide_seen = 0;
         for (int l = 0; l < kl; l++)
         {

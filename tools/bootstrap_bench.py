@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""BASELINE.json config 3 — bootstrapping microbench at the repo's parameters (N = 65536, 35 + 1
+primes, full slots).  Times Bootstrapper::bootstrap_3 on a batch of ciphertexts with CUDA events and
+prints per-ciphertext milliseconds plus the projected per-layer / per-input cost
+(4 x 768 + 12 bootstrappings per layer, M/test/test_full_scheme.hpp:654,758,991,1081; softmax.hpp:536).
+Key material is uniformly random residues: the timing of a key switch does not depend on key values
+(correctness with valid keys is covered by tests/test_gpu_bootstrap.py).
+usage: python tools/bootstrap_bench.py [--batch 16] [--keys required|pow2]"""
+import argparse
+import importlib
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def main():
+    import torch
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--iters", type=int, default=2)
+    ap.add_argument("--keys", default="required", choices=["required", "pow2"])
+    args = ap.parse_args()
+    pkg = importlib.import_module("moai-fhe-transformerinference-public_b200")
+    primes = bench.moai_primes()
+    be = pkg.Backend(16, primes)
+    n, kl = 1 << 16, len(primes)
+    boot = pkg.Bootstrapper(be, total_limbs=35)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+
+    def rand_key():
+        k = torch.empty((kl - 1, 2, kl, n), dtype=torch.int64, device="cuda")
+        for l in range(kl):
+            k[:, :, l, :] = torch.randint(0, primes[l], (kl - 1, 2, n), generator=g, device="cuda", dtype=torch.int64)
+        return k
+
+    if args.keys == "required":
+        steps = boot.required_steps()
+    else:
+        steps = [1 << k for k in range(15)] + [(n // 2) - (1 << k) for k in range(15)]
+    gal = {}
+    for st in steps + [0]:
+        gal[be.galois_elt_from_step(st)] = rand_key()
+    keys = be.make_keys(relin=rand_key(), galois=gal)
+    x = torch.randint(0, primes[0], (args.batch, 2, 1, n), generator=g, device="cuda", dtype=torch.int64)
+    boot.bootstrap_3(keys, x, 2.0 ** 46)         # warm-up: encodes the linear-transform plaintexts once
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.iters):
+        boot.bootstrap_3(keys, x, 2.0 ** 46)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.iters
+    per_ct = ms / args.batch
+    per_layer_s = per_ct * 3084 / 1000.0
+    print(json.dumps({"op": "bootstrap_3", "batch": args.batch, "keys": args.keys, "galois_keys": len(gal),
+                      "ms_per_batch": round(ms, 2), "ms_per_ciphertext": round(per_ct, 2),
+                      "projected_bootstrap_s_per_layer": round(per_layer_s, 1),
+                      "projected_bootstrap_s_per_input_12_layers": round(per_layer_s * 12 / 256, 2),
+                      "reference_bootstrap_s_per_input_12_layers": 384.8,
+                      "gpu_mem_GiB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}))
+    be.close()
+
+
+if __name__ == "__main__":
+    main()
