@@ -21,12 +21,20 @@ namespace moai
             typedef Twiddle tw_t;
             u64 q, two_q;
             u64 inv_n, inv_n_quo, inv_n_w, inv_n_w_quo;
+            u64 bar_m;
+            u32 bar_shift;
             const Twiddle *__restrict__ tab;
 
             __device__ IntField(const NttArgs &a, int limb, const LimbConst &lc)
                 : q(lc.q), two_q(lc.two_q), inv_n(lc.inv_n), inv_n_quo(lc.inv_n_quo), inv_n_w(lc.inv_n_w),
-                  inv_n_w_quo(lc.inv_n_w_quo), tab(a.tw + ((size_t)limb << a.log_n))
+                  inv_n_w_quo(lc.inv_n_w_quo), bar_m(lc.bar_m), bar_shift(lc.bar_shift),
+                  tab(a.tw + ((size_t)limb << a.log_n))
             {}
+            __device__ __forceinline__ elem pro_reduce(elem v) const
+            {
+                const u64 t = __umul64hi(v >> bar_shift, bar_m);
+                return csub(csub(v - t * q, two_q), q);
+            }
             __device__ __forceinline__ tw_t tw(size_t idx) const
             {
                 const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(tab + idx));
@@ -88,6 +96,7 @@ namespace moai
                   tab(a.tw_fp + ((size_t)limb << a.log_n))
             {}
             __device__ __forceinline__ tw_t tw(size_t idx) const { return __ldg(tab + idx); }
+            __device__ __forceinline__ elem pro_reduce(elem x) const { return red(x); }
             static __device__ __forceinline__ double rnd(double x)
             {
                 const double M = 6755399441055744.0;
@@ -218,8 +227,16 @@ namespace moai
         // =====================================================================================
         // Pass bodies (policy-generic).  `sm` is the CTA's shared buffer viewed as 8-byte words.
         // =====================================================================================
+        struct ProArgs
+        {
+            const u64 *src; // source polynomial + tile offset (== base when there is no prologue)
+            int mode;
+            u64 q_last, half, fix;
+            LimbConst lc;   // target limb (mode 2 integer reduction)
+        };
+
         template <int LOGR, class F>
-        __device__ __forceinline__ void fwd_pass_a_body(const F &f, u64 *base, u64 *sm, int t, int tb)
+        __device__ __forceinline__ void fwd_pass_a_body(const F &f, u64 *base, u64 *sm, int t, int tb, const ProArgs &pa)
         {
             constexpr int R = 1 << LOGR, T1 = R / 16;
             typename F::elem x[16];
@@ -227,7 +244,16 @@ namespace moai
 #pragma unroll
             for (int k = 0; k < 16; k++)
             {
-                x[k] = f.in_outer(base[(size_t)(t + T1 * k) * 256]);
+                u64 v = pa.src[(size_t)(t + T1 * k) * 256];
+                if (pa.mode == 2)
+                {
+                    v = reduce64(addmod(v, pa.half, pa.q_last), pa.lc) + pa.fix; // < 2 q_i
+                }
+                x[k] = f.in_outer(v);
+                if (pa.mode == 1)
+                {
+                    x[k] = f.pro_reduce(x[k]);
+                }
             }
             f.phase_begin_fwd(x);
             // stages 0..3 pair the top four bits of a (k): root index 2^s + block
@@ -452,7 +478,24 @@ namespace moai
             const int limb = a.limb_ids[(poly / a.div) % a.period];
             const LimbConst lc = a.limb[limb];
             u64 *base = a.data + ((size_t)poly << a.log_n) + tile * TB + tb;
-            MOAI_DISPATCH_FIELD(lc, (fwd_pass_a_body<LOGR>(f, base, sm, t, tb)))
+            ProArgs pa;
+            pa.src = base;
+            pa.mode = a.src_mode;
+            if (a.src_mode == 1)
+            {
+                const long long sp = (poly / ((long long)a.period * a.div)) * a.div + poly % a.div;
+                pa.src = a.src + ((size_t)sp << a.log_n) + tile * TB + tb;
+            }
+            else if (a.src_mode == 2)
+            {
+                const long long sp = poly / a.period;
+                pa.src = a.src + ((size_t)sp << a.log_n) + tile * TB + tb;
+                pa.q_last = a.limb[a.last_id].q;
+                pa.half = pa.q_last >> 1;
+                pa.fix = lc.q - a.half_mod[(size_t)a.last_id * a.kl + limb];
+                pa.lc = lc;
+            }
+            MOAI_DISPATCH_FIELD(lc, (fwd_pass_a_body<LOGR>(f, base, sm, t, tb, pa)))
         }
 
         __global__ void __launch_bounds__(ROWS * 16) ntt_fwd_pass_b(NttArgs a)
@@ -518,13 +561,22 @@ namespace moai
         }
     } // namespace
 
-    void ntt_forward(Context *c, u64 *data, long long count, const int *d_limb_ids, int period, int div)
+    void ntt_forward(Context *c, u64 *data, long long count, const int *d_limb_ids, int period, int div,
+                     const NttPrologue *pro)
     {
         if (count <= 0)
         {
             return;
         }
         NttArgs a{ data, c->d_fwd, c->d_fwd_fp, c->d_limb, d_limb_ids, period, div, c->log_n, count };
+        if (pro)
+        {
+            a.src = pro->src;
+            a.src_mode = pro->mode;
+            a.last_id = pro->last_id;
+            a.kl = c->kl;
+            a.half_mod = c->d_half_mod;
+        }
         switch (c->log_n)
         {
         case 12: launch_fwd<4>(a, c->stream); break;

@@ -41,10 +41,30 @@ namespace moai
         int div;
         int log_n;
         long long count;
+        // Optional fused prologue of the forward transform (pass A reads `src` instead of `data`):
+        //   src_mode 1 (key-switch digit extension, S/evaluator.cpp:2831-2856): polynomial p reads the
+        //              coefficient-form digit src[(p / (period*div)) * div + p % div] and reduces it
+        //              modulo its own prime;
+        //   src_mode 2 (divide-and-round expansion, S/util/rns.cpp:851-880 / S/evaluator.cpp:2966-2990):
+        //              polynomial p reads t = src[p / period] (coefficients modulo prime `last_id`) and
+        //              forms ((t + half) mod q_last) mod q_i + (q_i - half mod q_i).
+        const u64 *src = nullptr;
+        int src_mode = 0;
+        int last_id = 0;
+        int kl = 0;
+        const u64 *half_mod = nullptr; // [kl][kl]
+    };
+
+    struct NttPrologue
+    {
+        const u64 *src = nullptr;
+        int mode = 0;
+        int last_id = 0;
     };
 
     // Transforms `count` consecutive polynomials in place; polynomial p lives at data + p*n and
     // uses the prime with index d_limb_ids[(p / div) % period].
-    void ntt_forward(Context *c, u64 *data, long long count, const int *d_limb_ids, int period, int div = 1);
+    void ntt_forward(Context *c, u64 *data, long long count, const int *d_limb_ids, int period, int div = 1,
+                     const NttPrologue *pro = nullptr);
     void ntt_inverse(Context *c, u64 *data, long long count, const int *d_limb_ids, int period, int div = 1);
 } // namespace moai

@@ -265,11 +265,12 @@ namespace moai
                                               cudaMemcpyDeviceToDevice, c->stream));
             ntt_inverse(c, t.as<u64>(), P, c->d_ids + last_id, 1);
             const long long total2 = P * targets * (long long)(n / 2);
-            k_divround_expand<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
-                t.as<ulonglong2>(), u.as<ulonglong2>(), total2, c->log_n - 1, targets, last_id, c->kl, c->d_limb,
-                c->d_half_mod);
-        c->launches += 1;
-            ntt_forward(c, u.as<u64>(), P * targets, c->d_ids, targets);
+            // expansion (+half, reduce into every target prime, +fix) fused into the NTT's first pass
+            NttPrologue pro;
+            pro.src = t.as<u64>();
+            pro.mode = 2;
+            pro.last_id = last_id;
+            ntt_forward(c, u.as<u64>(), P * targets, c->d_ids, targets, 1, &pro);
             k_divround_finish<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
                 reinterpret_cast<const ulonglong2 *>(in), u.as<ulonglong2>(),
                 reinterpret_cast<const ulonglong2 *>(addend), reinterpret_cast<ulonglong2 *>(out), total2, c->log_n - 1,
@@ -446,10 +447,11 @@ namespace moai
                                  const int *__restrict__ ids_ks, const LimbConst *__restrict__ lcs,
                                  const Twiddle *__restrict__ two64)
         {
-            // grid: x = n/2 / blockDim, y = I, z = batch chunk
-            const long long within = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            // grid: x = batch item (fastest, so that CTAs sharing a key tile run together and the evk
+            // is streamed from HBM once per chunk), y = I, z = coefficient block
+            const long long within = (long long)blockIdx.z * blockDim.x + threadIdx.x;
             const int I = blockIdx.y;
-            const long long b = blockIdx.z;
+            const long long b = blockIdx.x;
             const int key_limb = ids_ks[I];
             const LimbConst lc = lcs[key_limb];
             const Twiddle t64 = two64[key_limb];
@@ -659,6 +661,11 @@ namespace moai
         const size_t n = c->n;
         const int rns = limbs + 1;
         const int *ids_ks = c->d_ids_ks + (size_t)limbs * (c->kl + 1);
+        bool fuse_expand = true; // the FP64 path ingests digits below 2^52 only
+        for (int l = 0; l < limbs; l++)
+        {
+            fuse_expand = fuse_expand && (c->q[l] >> 52) == 0;
+        }
         // bound the extended-digit workspace (batch chunking); ~2 GiB
         const size_t ext_per_ct = (size_t)rns * limbs * n * sizeof(u64);
         long long chunk = (long long)(((size_t)2 << 30) / ext_per_ct);
@@ -674,14 +681,26 @@ namespace moai
             MOAI_CUDA_CHECK(cudaMemcpyAsync(d.p, tg, (size_t)nb * limbs * n * sizeof(u64), cudaMemcpyDeviceToDevice,
                                             c->stream));
             ntt_inverse(c, d.as<u64>(), nb * limbs, c->d_ids, limbs);
-            const long long total2 = nb * rns * limbs * (long long)(n / 2);
-            k_ks_expand<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(d.as<ulonglong2>(), ext.as<ulonglong2>(), total2,
-                                                                        c->log_n - 1, limbs, ids_ks, c->d_limb);
-        c->launches += 1;
             // NTT_I(d_I mod q_I) reproduces the target limb itself, so the I == J digits need no
             // special case (S/evaluator.cpp:2831-2836 takes the NTT-form input there: same residues)
-            ntt_forward(c, ext.as<u64>(), nb * rns * limbs, ids_ks, rns, limbs);
-            dim3 grid((unsigned)((n / 2) / EW_THREADS), (unsigned)rns, (unsigned)nb);
+            if (fuse_expand)
+            {
+                // digit extension (d_J mod m_I) fused into the NTT's first pass: ext is written once
+                NttPrologue pro;
+                pro.src = d.as<u64>();
+                pro.mode = 1;
+                ntt_forward(c, ext.as<u64>(), nb * rns * limbs, ids_ks, rns, limbs, &pro);
+            }
+            else
+            {
+                const long long total2 = nb * rns * limbs * (long long)(n / 2);
+                k_ks_expand<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(d.as<ulonglong2>(), ext.as<ulonglong2>(),
+                                                                            total2, c->log_n - 1, limbs, ids_ks,
+                                                                            c->d_limb);
+                c->launches += 1;
+                ntt_forward(c, ext.as<u64>(), nb * rns * limbs, ids_ks, rns, limbs);
+            }
+            dim3 grid((unsigned)nb, (unsigned)rns, (unsigned)((n / 2) / EW_THREADS));
             k_ks_mac<<<grid, EW_THREADS, 0, c->stream>>>(ext.as<ulonglong2>(), reinterpret_cast<const ulonglong2 *>(ksk),
                                                          acc.as<ulonglong2>(), nb, c->log_n - 1, limbs, c->kl, ids_ks,
                                                          c->d_limb, c->d_two64);
