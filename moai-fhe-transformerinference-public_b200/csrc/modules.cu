@@ -583,8 +583,21 @@ namespace moai
                                     bias_vec, scale);
         }
         {
+            // 3072 independent GELUs (test_full_scheme.hpp:884-888); chunked: gelu_v2 keeps 24 powers alive
             PhaseTimer t(c, "gelu");
-            inter = gelu_v2(ev, inter, keys);
+            const long long chunk = 256;
+            Ct g;
+            for (long long b0 = 0; b0 < inter.batch; b0 += chunk)
+            {
+                const long long nb = std::min(chunk, inter.batch - b0);
+                Ct part = gelu_v2(ev, ev.view(inter, b0, nb), keys);
+                if (g.empty())
+                {
+                    g = ev.alloc(inter.batch, 2, part.limbs, part.scale);
+                }
+                ev.copy_into(part, g, b0);
+            }
+            inter = g;
         }
         Ct fin;
         {

@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""BASELINE.json config 4 — one full BERT-base encoder layer (12 heads, hidden 768, FFN 3072;
+4 x 768 + 12 bootstrappings) on one packed batch of 256 inputs x 128 tokens at the repo's CKKS
+parameters (N = 65536, 35 + 1 primes), all 128 token slots valid, on ONE B200.
+Inputs, weights and evaluation keys are synthetic (uniform residues / Gaussian weights): kernel
+timing does not depend on the values; correctness of the same pipeline is covered at N = 4096 by
+tests/test_gpu_layer.py.  Prints the per-stage device time (the rows of P:Table 3) and the
+amortized seconds per input extrapolated to 12 identical layers."""
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+REFERENCE_TABLE3 = {  # P:Table 3, seconds per input summed over 12 layers
+    "attention": 37.4 + 40.3 + 53.3 + 1.4, "selfoutput_matmul": 1.7, "bootstrap_1": 95.4, "layernorm_1": 0.6,
+    "bootstrap_2": 95.8, "intermediate_matmul": 44.1, "gelu": 3.3, "final_matmul": 7.1, "bootstrap_3": 98.8,
+    "layernorm_2": 0.6, "bootstrap_4": 94.8}
+
+
+def main():
+    import torch
+    pkg = importlib.import_module("moai-fhe-transformerinference-public_b200")
+    primes = bench.moai_primes()
+    be = pkg.Backend(16, primes)
+    n, kl = 1 << 16, len(primes)
+    boot = pkg.Bootstrapper(be, total_limbs=35)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(11)
+
+    def rand_key():
+        k = torch.empty((kl - 1, 2, kl, n), dtype=torch.int64, device="cuda")
+        for l in range(kl):
+            k[:, :, l, :] = torch.randint(0, primes[l], (kl - 1, 2, n), generator=g, device="cuda", dtype=torch.int64)
+        return k
+
+    steps = set(boot.required_steps())
+    for k in range(15):                       # the driver's default power-of-two Galois keys
+        steps |= {1 << k, (n // 2) - (1 << k)}
+    gal = {be.galois_elt_from_step(st): rand_key() for st in sorted(steps) + [0]}
+    keys = be.make_keys(relin=rand_key(), galois=gal)
+    hidden, heads, hd, inter = 768, 12, 64, 3072
+    rng = np.random.default_rng(20250991)
+    w = {"hidden": hidden, "heads": heads, "head_dim": hd, "inter": inter,
+         "WQ": rng.normal(size=(heads, hidden, hd)) * 0.04, "WK": rng.normal(size=(heads, hidden, hd)) * 0.04,
+         "WV": rng.normal(size=(heads, hidden, hd)) * 0.04, "bQ": rng.normal(size=(heads, hd)) * 0.04,
+         "bK": rng.normal(size=(heads, hd)) * 0.04, "bV": rng.normal(size=(heads, hd)) * 0.04,
+         "selfoutput": rng.normal(size=(hidden, hidden)) * 0.04, "selfoutput_bias": rng.normal(size=hidden) * 0.04,
+         "ln1_gamma": np.ones(hidden), "ln1_beta": np.zeros(hidden),
+         "inter_weight": rng.normal(size=(hidden, inter)) * 0.04, "inter_bias": rng.normal(size=inter) * 0.04,
+         "final_weight": rng.normal(size=(inter, hidden)) * 0.04, "final_bias": rng.normal(size=hidden) * 0.04,
+         "ln2_gamma": np.ones(hidden), "ln2_beta": np.zeros(hidden)}
+    x = torch.empty((hidden, 2, 21, n), dtype=torch.int64, device="cuda")
+    for l in range(21):
+        x[:, :, l, :] = torch.randint(0, primes[l], (hidden, 2, n), generator=g, device="cuda", dtype=torch.int64)
+    mask = np.ones(n // 2, dtype=np.int32)     # all 128 tokens of all 256 inputs valid
+    boot_chunk = int(os.environ.get("MOAI_BOOT_CHUNK", "32"))
+    be.profile(True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out, out_scale = boot.encoder_layer(keys, x, 2.0 ** 46, w, mask, 128, 256, layer_id=0, boot_chunk=boot_chunk)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = e0.elapsed_time(e1)
+    stages = be.profile_dump()
+    be.profile(False)
+    rows = {}
+    for k, (v, cnt) in stages.items():
+        if k == "ctpt_gemm":
+            continue
+        rows[k] = {"ms": round(v, 1), "s_per_input_12_layers": round(v / 1000.0 * 12 / 256, 3),
+                   "reference_s_per_input_12_layers": REFERENCE_TABLE3.get(k)}
+    total = ms / 1000.0
+    print(json.dumps({"workload": "C4: one BERT-base encoder layer, 256 inputs x 128 tokens, N=65536, 1 x B200",
+                      "layer_seconds": round(total, 2), "host_wall_seconds": round(wall, 2),
+                      "amortized_s_per_input_12_layers": round(total * 12 / 256, 3),
+                      "reference_s_per_input_12_layers": 574.6, "galois_keys": len(gal),
+                      "gpu_mem_GiB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
+                      "launches": be.launch_count(), "stages": rows}))
+    assert out.shape == (hidden, 2, 21, n) and out_scale == 2.0 ** 46
+    be.close()
+
+
+if __name__ == "__main__":
+    main()
