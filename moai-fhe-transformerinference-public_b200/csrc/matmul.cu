@@ -16,6 +16,7 @@
 // (4 IMAD.WIDE + carry adds per 64x64->128 MAC), not by HBM.
 #include "ntt.cuh"
 #include "ops.cuh"
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <type_traits>
@@ -53,7 +54,7 @@ namespace moai
         // Y[i][p][l][t] = sum_j X[j][p][l][t] * Wc[l][j][i]
         __global__ void __launch_bounds__(MM_THREADS)
             k_ctpt_gemm(const ulonglong2 *__restrict__ X, const u64 *__restrict__ Wc, ulonglong2 *__restrict__ Y, int K,
-                        int C, int limbs, int log_n2, const LimbConst *__restrict__ lcs,
+                        int C, int ldw, int limbs, int log_n2, const LimbConst *__restrict__ lcs,
                         const Twiddle *__restrict__ two64)
         {
             __shared__ u64 ws[MM_KC * MM_TN];
@@ -78,7 +79,7 @@ namespace moai
                 acc[0][c] = u128{ 0, 0 };
                 acc[1][c] = u128{ 0, 0 };
             }
-            const u64 *wl = Wc + (long long)l * K * C;
+            const u64 *wl = Wc + (long long)l * K * ldw;
             for (int j0 = 0; j0 < K; j0 += MM_KC)
             {
                 const int jn = min(MM_KC, K - j0);
@@ -86,7 +87,7 @@ namespace moai
                 for (int e = threadIdx.x; e < jn * MM_TN; e += MM_THREADS)
                 {
                     const int jj = e / MM_TN, cc = e % MM_TN;
-                    ws[e] = (i0 + cc < C) ? wl[(long long)(j0 + jj) * C + i0 + cc] : 0;
+                    ws[e] = (i0 + cc < C) ? wl[(long long)(j0 + jj) * ldw + i0 + cc] : 0;
                 }
                 __syncthreads();
                 const ulonglong2 *xp = X + (long long)j0 * ct_stride2 + off;
@@ -130,7 +131,7 @@ namespace moai
         template <int TM>
         __global__ void __launch_bounds__(MM_THREADS, TM == 1 ? 2 : 1)
             k_ctpt_gemm26(const u64 *__restrict__ Xw, const u64 *__restrict__ Wc, u64 *__restrict__ Yw,
-                          int K, int C, int limbs, int log_n, const LimbConst *__restrict__ lcs,
+                          int K, int C, int ldw, int limbs, int log_n, const LimbConst *__restrict__ lcs,
                           const Twiddle *__restrict__ two64)
         {
             // TM consecutive coefficients per thread; strides below are in units of TM words
@@ -184,7 +185,7 @@ namespace moai
                     }
                 }
             };
-            const u64 *wl = Wc + (long long)l * K * C;
+            const u64 *wl = Wc + (long long)l * K * ldw;
             for (int j0 = 0; j0 < K; j0 += MM_KC)
             {
                 const int jn = min(MM_KC, K - j0);
@@ -192,7 +193,7 @@ namespace moai
                 for (int e = threadIdx.x; e < jn * MM_TN; e += MM_THREADS)
                 {
                     const int jj = e / MM_TN, cc = e % MM_TN;
-                    ws[e] = (i0 + cc < C) ? wl[(long long)(j0 + jj) * C + i0 + cc] : 0;
+                    ws[e] = (i0 + cc < C) ? wl[(long long)(j0 + jj) * ldw + i0 + cc] : 0;
                 }
                 __syncthreads();
                 if (j0 && (j0 % MM_FOLD) == 0)
@@ -272,41 +273,49 @@ namespace moai
         MOAI_REQUIRE(wmax * scale < 9.0e18, "encoded value is too large");
         Scratch dW(kc * sizeof(double), c->stream);
         Scratch dWc((size_t)limbs * kc * sizeof(u64), c->stream);
-        Scratch Y((size_t)C * 2 * limbs * n * sizeof(u64), c->stream);
         MOAI_CUDA_CHECK(cudaMemcpyAsync(dW.p, h_W, kc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         bool narrow = true; // every limb prime below 2^52 -> carry-free 26-bit split kernel
         for (int l = 0; l < limbs; l++)
         {
             narrow = narrow && (c->q[l] >> 52) == 0;
         }
+        static const int variant = getenv("MOAI_GEMM_VARIANT") ? atoi(getenv("MOAI_GEMM_VARIANT")) : 0;
+        const bool split26 = narrow && variant != 0;
         k_encode_weights<<<(unsigned)((kc + 255) / 256), 256, 0, c->stream>>>(dW.as<double>(), dWc.as<u64>(), kc, limbs,
-                                                                            scale, c->d_limb, narrow && !(getenv("MOAI_GEMM_VARIANT") && atoi(getenv("MOAI_GEMM_VARIANT")) == 0) ? 1 : 0);
-        c->launches += 2;
-        const int tiles_i = (C + MM_TN - 1) / MM_TN;
+                                                                            scale, c->d_limb, split26 ? 1 : 0);
+        c->launches += 1;
+        // output columns in chunks: bounds the pre-rescale buffer Y (2 * limbs * N words per column)
+        const int col_chunk = 768;
         const int tiles_t = (int)((n / 2) / MM_THREADS);
-        const long long ctas = (long long)2 * limbs * tiles_t * tiles_i;
+        Scratch Y((size_t)std::min(C, col_chunk) * 2 * limbs * n * sizeof(u64), c->stream);
+        for (int c0 = 0; c0 < C; c0 += col_chunk)
         {
-            PhaseTimer pt(c, "ctpt_gemm");
-            static const int variant = getenv("MOAI_GEMM_VARIANT") ? atoi(getenv("MOAI_GEMM_VARIANT")) : 2;
-            if (narrow && variant == 2)
+            const int cn = std::min(col_chunk, C - c0);
+            const int tiles_i = (cn + MM_TN - 1) / MM_TN;
+            const long long ctas = (long long)2 * limbs * tiles_t * tiles_i;
             {
-                k_ctpt_gemm26<1><<<(unsigned)(2 * ctas), MM_THREADS, 0, c->stream>>>(
-                    X, dWc.as<u64>(), Y.as<u64>(), K, C, limbs, c->log_n, c->d_limb, c->d_two64);
+                PhaseTimer pt(c, "ctpt_gemm");
+                if (split26 && variant == 2)
+                {
+                    k_ctpt_gemm26<1><<<(unsigned)(2 * ctas), MM_THREADS, 0, c->stream>>>(
+                        X, dWc.as<u64>() + c0, Y.as<u64>(), K, cn, C, limbs, c->log_n, c->d_limb, c->d_two64);
+                }
+                else if (split26)
+                {
+                    k_ctpt_gemm26<2><<<(unsigned)ctas, MM_THREADS, 0, c->stream>>>(
+                        X, dWc.as<u64>() + c0, Y.as<u64>(), K, cn, C, limbs, c->log_n, c->d_limb, c->d_two64);
+                }
+                else
+                {
+                    k_ctpt_gemm<<<(unsigned)ctas, MM_THREADS, 0, c->stream>>>(
+                        reinterpret_cast<const ulonglong2 *>(X), dWc.as<u64>() + c0, Y.as<ulonglong2>(), K, cn, C, limbs,
+                        c->log_n - 1, c->d_limb, c->d_two64);
+                }
             }
-            else if (narrow && variant == 1)
-            {
-                k_ctpt_gemm26<2><<<(unsigned)ctas, MM_THREADS, 0, c->stream>>>(
-                    X, dWc.as<u64>(), Y.as<u64>(), K, C, limbs, c->log_n, c->d_limb, c->d_two64);
-            }
-            else
-            {
-                k_ctpt_gemm<<<(unsigned)ctas, MM_THREADS, 0, c->stream>>>(
-                    reinterpret_cast<const ulonglong2 *>(X), dWc.as<u64>(), Y.as<ulonglong2>(), K, C, limbs,
-                    c->log_n - 1, c->d_limb, c->d_two64);
-            }
+            c->launches += 1;
+            MOAI_CUDA_CHECK(cudaGetLastError());
+            rescale(c, Y.as<u64>(), out + (size_t)c0 * 2 * (limbs - 1) * n, cn, 2, limbs);
         }
-        MOAI_CUDA_CHECK(cudaGetLastError());
-        rescale(c, Y.as<u64>(), out, C, 2, limbs);
     }
 
     namespace

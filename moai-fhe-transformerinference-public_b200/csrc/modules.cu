@@ -568,6 +568,7 @@ namespace moai
             PhaseTimer t(c, "layernorm_1");
             ev.add_inplace(rtn, ev.mod_switch_to(x, rtn.limbs)); // residual
             ln1 = layernorm(ev, rtn, w.ln1_gamma, w.ln1_beta, bias_vec, keys, 1);
+            rtn = Ct();
         }
         Ct boot_layer;
         {

@@ -177,6 +177,13 @@ namespace moai
 
         // ---- register stages over 16 elements; tw index of the j-th block of 2*GAP is base + j
         template <int GAP, class F>
+        __device__ __forceinline__ void ct_stage_tw(const F &f, typename F::elem (&x)[16],
+                                                    const typename F::tw_t (&tw)[8 / GAP]);
+        template <int GAP, class F>
+        __device__ __forceinline__ void gs_stage_tw(const F &f, typename F::elem (&x)[16],
+                                                    const typename F::tw_t (&tw)[8 / GAP]);
+
+        template <int GAP, class F>
         __device__ __forceinline__ void ct_stage(const F &f, typename F::elem (&x)[16], size_t tw_base)
         {
             typename F::tw_t tw[8 / GAP];
@@ -185,6 +192,26 @@ namespace moai
             {
                 tw[j] = f.tw(tw_base + j);
             }
+            ct_stage_tw<GAP>(f, x, tw);
+        }
+
+        // same stage with the twiddles read through a pointer (shared-memory staging in pass B)
+        template <int GAP, class F>
+        __device__ __forceinline__ void ct_stage_p(const F &f, typename F::elem (&x)[16], const typename F::tw_t *ptr)
+        {
+            typename F::tw_t tw[8 / GAP];
+#pragma unroll
+            for (int j = 0; j < 8 / GAP; j++)
+            {
+                tw[j] = ptr[j];
+            }
+            ct_stage_tw<GAP>(f, x, tw);
+        }
+
+        template <int GAP, class F>
+        __device__ __forceinline__ void ct_stage_tw(const F &f, typename F::elem (&x)[16],
+                                                    const typename F::tw_t (&tw)[8 / GAP])
+        {
 #pragma unroll
             for (int k = 0; k < 16; k++)
             {
@@ -204,6 +231,25 @@ namespace moai
             {
                 tw[j] = f.tw(tw_base + j);
             }
+            gs_stage_tw<GAP>(f, x, tw);
+        }
+
+        template <int GAP, class F>
+        __device__ __forceinline__ void gs_stage_p(const F &f, typename F::elem (&x)[16], const typename F::tw_t *ptr)
+        {
+            typename F::tw_t tw[8 / GAP];
+#pragma unroll
+            for (int j = 0; j < 8 / GAP; j++)
+            {
+                tw[j] = ptr[j];
+            }
+            gs_stage_tw<GAP>(f, x, tw);
+        }
+
+        template <int GAP, class F>
+        __device__ __forceinline__ void gs_stage_tw(const F &f, typename F::elem (&x)[16],
+                                                    const typename F::tw_t (&tw)[8 / GAP])
+        {
 #pragma unroll
             for (int k = 0; k < 16; k++)
             {

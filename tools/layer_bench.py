@@ -41,7 +41,9 @@ def main():
         return k
 
     steps = set(boot.required_steps())
-    for k in range(15):                       # the driver's default power-of-two Galois keys
+    # of the driver's default power-of-two Galois keys only the multiples of num_batch = 256 are ever
+    # used (QK^T rotates by i*256, softmax*V by multiples of 256): 2^8 .. 2^14 and their negatives
+    for k in range(8, 15):
         steps |= {1 << k, (n // 2) - (1 << k)}
     gal = {be.galois_elt_from_step(st): rand_key() for st in sorted(steps) + [0]}
     keys = be.make_keys(relin=rand_key(), galois=gal)
