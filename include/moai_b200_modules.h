@@ -38,6 +38,27 @@ int32_t moai_keys_destroy(moai_keys *keys);
 int32_t moai_keys_set_relin(moai_keys *keys, const uint64_t *ksk);
 int32_t moai_keys_add_galois(moai_keys *keys, uint32_t galois_elt, const uint64_t *ksk);
 
+/* ---- fast mode (NOT SEAL's residues: same plaintext, different but
+ * equally small key-switching noise; judged on decrypted tolerance).
+ * moai_key_prepare: device-side re-layout of one Galois key of SEAL's KeyGenerator
+ * (S/keygenerator.cpp:303-336, [key_limbs-1][2][key_limbs][N]) into a level-truncated key
+ * [max_limbs][2][max_limbs+1][N] (first max_limbs digits / data limbs + the special prime); with
+ * pre_permute != 0 every limb is additionally mapped through the NTT-domain automorphism of
+ * galois_elt^-1 (S/util/galois.cpp:192-218), K' = sigma^-1(K), so that
+ *     rotate(ct) = sigma((c0, 0) + ModDown(sum_J digit_J(c1) (.) K'_J))
+ * needs the digit decomposition of the UNROTATED c1 only: every rotation of one ciphertext shares
+ * one decomposition ("hoisting"), which SEAL's rotate (automorphism first, S/evaluator.cpp:2635-2657)
+ * cannot do.  moai_keys_add_galois_fast registers such a key (key_limbs = max_limbs + 1; several
+ * truncations of one element may coexist, the smallest that covers the level is used);
+ * moai_rotate_vector / the modules use it when no SEAL-layout key of that element is registered.
+ * moai_rotate_many: out[s][batch][2][limbs][N] = rotate(in, steps[s]) for n_steps steps, hoisted
+ * when every step has a pre-permuted key.                                                        */
+int32_t moai_key_prepare(moai_context *ctx, const uint64_t *ksk_in, uint32_t galois_elt, int32_t max_limbs,
+                         int32_t pre_permute, uint64_t *ksk_out);
+int32_t moai_keys_add_galois_fast(moai_keys *keys, uint32_t galois_elt, const uint64_t *ksk_pre, int32_t key_limbs);
+int32_t moai_rotate_many(moai_context *ctx, moai_keys *keys, const uint64_t *in, int64_t batch, int32_t limbs,
+                         const int32_t *steps, int32_t n_steps, uint64_t *out);
+
 /* Evaluator::rotate_vector incl. SEAL's NAF fallback for missing keys (S/evaluator.cpp:2667-2722) */
 int32_t moai_rotate_vector(moai_context *ctx, moai_keys *keys, const uint64_t *in, uint64_t *out, int64_t batch,
                            int32_t limbs, int32_t steps);
@@ -81,6 +102,9 @@ typedef struct moai_bootstrapper moai_bootstrapper;
 int32_t moai_bootstrapper_create(moai_context *ctx, int32_t total_limbs, double final_scale, int32_t boundary_K,
                                  int32_t deg, int32_t double_angles, int32_t log_width, moai_bootstrapper **out);
 int32_t moai_bootstrapper_destroy(moai_bootstrapper *b);
+/* fast mode: plan the linear stages for hoisted baby steps (16 baby x 4 giant instead of 8 x 8);
+ * call before moai_bootstrapper_required_steps and register the keys with moai_keys_add_galois_fast */
+int32_t moai_bootstrapper_set_hoisting(moai_bootstrapper *b, int32_t on);
 int32_t moai_bootstrapper_required_steps(moai_bootstrapper *b, int32_t *steps, int32_t capacity, int32_t *count);
 int32_t moai_bootstrap(moai_context *ctx, moai_bootstrapper *b, moai_keys *keys, const uint64_t *in, int64_t batch,
                        double scale, uint64_t *out, int32_t *out_limbs, double *out_scale);

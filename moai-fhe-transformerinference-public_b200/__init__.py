@@ -350,9 +350,11 @@ class Backend:
         return out[0] if single else out
 
     # ---- evaluation keys + MOAI modules (B4-B9)
-    def make_keys(self, relin=None, galois=None):
-        """relin: device key tensor; galois: dict galois_elt -> device key tensor.  The returned
-        handle keeps the tensors alive."""
+    def make_keys(self, relin=None, galois=None, galois_fast=None):
+        """relin: device key tensor; galois: dict galois_elt -> device key tensor (SEAL layout,
+        bit-exact rotations); galois_fast: dict galois_elt -> tensor or list of tensors produced by
+        key_prepare(pre_permute=True), shaped [L, 2, L + 1, n] (hoisted fast-mode rotations).  The
+        returned handle keeps the tensors alive."""
         h = C.c_void_p()
         self._chk(self.lib.moai_keys_create(self.h, C.byref(h)))
         keep = []
@@ -362,12 +364,44 @@ class Backend:
         for elt, t in (galois or {}).items():
             self._chk(self.lib.moai_keys_add_galois(h, C.c_uint32(elt), _ptr(t)))
             keep.append(t)
+        for elt, ts in (galois_fast or {}).items():
+            for t in (ts if isinstance(ts, (list, tuple)) else [ts]):
+                self._chk(self.lib.moai_keys_add_galois_fast(h, C.c_uint32(elt), _ptr(t), C.c_int32(t.shape[2])))
+                keep.append(t)
         return _KeysHandle(self.lib, h, keep)
 
-    def _module(self, fn, x, scale, *extra, out_count=None):
+    def key_prepare(self, ksk, elt, max_limbs=None, pre_permute=True):
+        """SEAL-layout Galois key [kl-1, 2, kl, n] -> level-truncated (and pre-permuted) key
+        [L, 2, L + 1, n] for the hoisted fast-mode rotations (include/moai_b200_modules.h)."""
+        L = self.kl - 1 if max_limbs is None else max_limbs
+        out = self.empty(L, 2, L + 1, self.n)
+        self._chk(self.lib.moai_key_prepare(self.h, _ptr(ksk), C.c_uint32(elt), C.c_int32(L),
+                                            C.c_int32(int(pre_permute)), _ptr(out)))
+        return out
+
+    def rotate_vector_keys(self, keys, a, steps):
+        """Evaluator::rotate_vector through a key handle (SEAL-layout key, else pre-permuted key,
+        else SEAL's NAF fallback)."""
+        bt, p, l, n = a.shape
+        out = self.torch.empty_like(a)
+        self._chk(self.lib.moai_rotate_vector(self.h, keys.h, _ptr(a), _ptr(out), C.c_int64(bt), C.c_int32(l),
+                                              C.c_int32(steps)))
+        return out
+
+    def rotate_many(self, keys, a, steps):
+        """[len(steps), batch, 2, limbs, n]: every rotation of the batch, one shared digit
+        decomposition when all steps have pre-permuted keys."""
+        bt, p, l, n = a.shape
+        st = (C.c_int32 * len(steps))(*steps)
+        out = self.empty(len(steps), bt, 2, l, n)
+        self._chk(self.lib.moai_rotate_many(self.h, keys.h, _ptr(a), C.c_int64(bt), C.c_int32(l), st,
+                                            C.c_int32(len(steps)), _ptr(out)))
+        return out
+
+    def _module(self, fn, x, scale, *extra, out_count=None, out=None):
         bt, p, l, n = x.shape
         cnt = bt if out_count is None else out_count
-        buf = self.empty(cnt, 2, l, n)
+        buf = self.empty(cnt, 2, l, n) if out is None else out
         ol, osc = C.c_int32(), C.c_double()
         self._chk(fn(*extra, _ptr(buf), C.byref(ol), C.byref(osc)))
         flat = buf.reshape(-1)[: cnt * 2 * ol.value * n]
@@ -411,6 +445,23 @@ class Backend:
                             C.c_int32(col_W), C.c_int32(row_W), C.c_int32(num_batch), out_count=col_W)
 
 
+def attention_rotation_steps(num_batch, tokens=128):
+    """Rotation steps (left, in slots) one attention head takes in fast mode, so that no rotation
+    falls back to SEAL's NAF chain: {level tag: steps}.  "qk": ct_ct_matrix_mul_colpacking at the
+    Q/K level (giant 16 a, hoisted baby b; csrc/modules.cu); "sv": ct_ct_matrix_mul_diagpacking at
+    the softmax-output level (Ct_ct_matrix_mul.hpp:70-151: g = ceil(sqrt(tokens)) baby steps of V,
+    group rotations of the diagonals, giant rotations of the partial sums)."""
+    import math
+    qk = {b * num_batch for b in range(1, 16)} | {a * num_batch for a in range(16, tokens, 16)}
+    g = int(math.sqrt(tokens))
+    g += g * g < tokens
+    b = -(-tokens // g)
+    sv = {k * num_batch for k in range(1, g)}
+    sv |= {(tokens - i * g) * num_batch for i in range(1, b) if i * g < tokens}
+    sv |= {j * g * num_batch for j in range(1, b)}
+    return {"qk": sorted(qk), "sv": sorted(sv)}
+
+
 class LayerWeightsC(C.Structure):
     _fields_ = [("hidden", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32), ("inter", C.c_int32)] + \
         [(k, C.POINTER(C.c_double)) for k in ("WQ", "WK", "WV", "bQ", "bK", "bV", "selfoutput", "selfoutput_bias",
@@ -429,6 +480,10 @@ class Bootstrapper:
                                                 C.c_int32(log_width), C.byref(h)))
         self.h = h
         self.total_limbs = total_limbs
+
+    def set_hoisting(self, on=True):
+        """Plan the linear stages for hoisted baby steps; call before required_steps()."""
+        self.be._chk(self.be.lib.moai_bootstrapper_set_hoisting(self.h, C.c_int32(int(on))))
 
     def required_steps(self):
         buf = (C.c_int32 * 1024)()
@@ -468,8 +523,10 @@ class Bootstrapper:
                           bv.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int32(input_num), C.c_int32(num_batch),
                           C.c_int32(iters), C.c_int32(layer_id), out_count=col_W)
 
-    def encoder_layer(self, keys, x, scale, weights, bias_vec, input_num, num_batch, layer_id=0, boot_chunk=32):
-        """weights: dict with the fields of moai_layer_weights (numpy float64 arrays)."""
+    def encoder_layer(self, keys, x, scale, weights, bias_vec, input_num, num_batch, layer_id=0, boot_chunk=32,
+                      inplace=False):
+        """weights: dict with the fields of moai_layer_weights (numpy float64 arrays).  inplace=True
+        writes the layer output over x (same shape; saves one 15.75 GiB buffer at the repo's size)."""
         be = self.be
         bt, p, l, n = x.shape
         dp = C.POINTER(C.c_double)
@@ -480,7 +537,8 @@ class Bootstrapper:
         bv = np.ascontiguousarray(bias_vec, dtype=np.int32)
         return be._module(be.lib.moai_encoder_layer, x, scale, be.h, keys.h, self.h, _ptr(x), C.c_int32(l),
                           C.c_double(scale), C.byref(w), bv.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int32(input_num),
-                          C.c_int32(num_batch), C.c_int32(layer_id), C.c_int64(boot_chunk))
+                          C.c_int32(num_batch), C.c_int32(layer_id), C.c_int64(boot_chunk),
+                          out=x if inplace else None)
 
     def __del__(self):
         try:

@@ -273,24 +273,73 @@ namespace moai
             MOAI_REQUIRE(kv.first % stride == 0, "diagonal offsets are not multiples of a common stride");
         }
         const int cnt = (int)st.diags.size();
+        auto split = [&](int g, std::set<int> &bs, std::set<int> &gs) {
+            bs.clear();
+            gs.clear();
+            for (auto &kv : st.diags)
+            {
+                const int e = kv.first / stride;
+                const int i = (int)std::floor((double)e / g);
+                bs.insert(e - i * g);
+                gs.insert(i);
+            }
+        };
         int g = 1;
         while (g * g < cnt)
         {
             g++;
         }
+        std::set<int> bs, gs;
+        if (prm.hoisting)
+        {
+            // baby steps share one digit decomposition (hoisted: inner product + mod-down only), giant
+            // steps pay a full key switch: weigh them ~1 : 3.5 (measured at 35 limbs) and stay inside
+            // the fused inner-sum kernel's limits
+            double best = 1e300;
+            int best_g = g;
+            for (int cand = 1; cand <= BSGS_MAX_BABY; cand++)
+            {
+                split(cand, bs, gs);
+                if ((int)bs.size() > BSGS_MAX_BABY || (int)gs.size() > BSGS_MAX_GIANT)
+                {
+                    continue;
+                }
+                int nb = 0, ng = 0;
+                for (int j : bs)
+                {
+                    nb += j != 0;
+                }
+                for (int i : gs)
+                {
+                    ng += i != 0;
+                }
+                const double cost = nb * 1.0 + ng * 3.5;
+                if (cost < best)
+                {
+                    best = cost;
+                    best_g = cand;
+                }
+            }
+            g = best_g;
+        }
+        split(g, bs, gs);
         st.stride = stride;
         st.giant = g;
-        std::set<int> bs, gs;
-        for (auto &kv : st.diags)
-        {
-            const int e = kv.first / stride;
-            const int i = (int)std::floor((double)e / g);
-            const int j = e - i * g;
-            bs.insert(j);
-            gs.insert(i);
-        }
         st.baby.assign(bs.begin(), bs.end());
         st.giants.assign(gs.begin(), gs.end());
+    }
+
+    void Bootstrapper::set_hoisting(bool on)
+    {
+        prm.hoisting = on ? 1 : 0;
+        for (int s = 0; s < 3; s++)
+        {
+            plan_bsgs(cts_[s]);
+            plan_bsgs(stc_[s]);
+            cts_[s].pts.clear(); // pre-rotation of the diagonals depends on the plan
+            stc_[s].pts.clear();
+        }
+        stc_encoded_for_scale_ = 0;
     }
 
     std::vector<int> Bootstrapper::required_steps() const
@@ -388,49 +437,63 @@ namespace moai
         MOAI_REQUIRE(ct.limbs == st.limbs, "linear stage applied at the wrong level");
         const long long n = slots();
         auto norm = [&](long long step) { return (int)(((step % n) + n) % n); }; // left rotation in [0, slots)
-        std::map<int, Ct> rots;
+        // baby steps: rotations of the same ciphertexts (hoisted when the keys are pre-permuted)
+        std::vector<int> bsteps;
         for (int j : st.baby)
         {
-            const int step = norm((long long)j * st.stride);
-            rots[j] = step == 0 ? ct : ev.rotate_vector(ct, step, keys);
+            bsteps.push_back(norm((long long)j * st.stride));
         }
-        Ct acc;
+        std::vector<Ct> rots = ev.rotate_many(ct, bsteps, keys);
+        // every giant step's inner sum  sum_j P[i][j] (.) rot_j  in one fused pass
+        const int nb = (int)st.baby.size();
+        std::vector<int> gi;
+        std::vector<const u64 *> pts;
         for (int i : st.giants)
         {
-            Ct inner;
+            bool any = false;
             for (int j : st.baby)
             {
-                auto it = st.pts.find({ i, j });
-                if (it == st.pts.end())
-                {
-                    continue;
-                }
-                Ct term = ev.multiply_plain(rots[j], it->second);
-                if (inner.empty())
-                {
-                    inner = term;
-                }
-                else
-                {
-                    ev.add_inplace(inner, term);
-                }
+                any = any || st.pts.count({ i, j });
             }
-            if (inner.empty())
+            if (!any)
             {
                 continue;
             }
-            const int gstep = norm((long long)i * st.giant * st.stride);
-            if (gstep != 0)
+            gi.push_back(i);
+            for (int j : st.baby)
             {
-                inner = ev.rotate_vector(inner, gstep, keys);
+                auto it = st.pts.find({ i, j });
+                pts.push_back(it == st.pts.end() ? nullptr : it->second.d);
             }
+        }
+        MOAI_REQUIRE(!gi.empty(), "empty linear stage");
+        std::vector<Ct> inner(gi.size());
+        std::vector<const u64 *> rp;
+        std::vector<u64 *> op;
+        for (auto &r : rots)
+        {
+            rp.push_back(r.d);
+        }
+        for (auto &x : inner)
+        {
+            x = ev.alloc(ct.batch, 2, ct.limbs, ct.scale * st.pt_scale);
+            op.push_back(x.d);
+        }
+        bsgs_inner(c_, rp.data(), nb, pts.data(), (int)gi.size(), op.data(), ct.batch, ct.limbs);
+        rots.clear();
+        Ct acc;
+        for (size_t k = 0; k < gi.size(); k++)
+        {
+            const int gstep = norm((long long)gi[k] * st.giant * st.stride);
+            Ct term = gstep != 0 ? ev.rotate_vector(inner[k], gstep, keys) : inner[k];
+            inner[k] = Ct();
             if (acc.empty())
             {
-                acc = inner;
+                acc = term;
             }
             else
             {
-                ev.add_inplace(acc, inner);
+                ev.add_inplace(acc, term);
             }
         }
         return ev.rescale_to_next(acc);
@@ -568,12 +631,17 @@ namespace moai
             }
         }
         // 1. ModRaise; the plaintext is now t = m + q0 I, declared at scale q0
-        Ct ct = ev.mod_raise(in, prm.total_limbs);
+        Ct ct;
+        {
+            PhaseTimer t(c_, "boot_modraise");
+            ct = ev.mod_raise(in, prm.total_limbs);
+        }
         const double initial_scale = in.scale;
         ct.scale = q0;
         // 2. CoeffToSlot: slots <- (c_lo + i c_hi) / (2 K q0)   (bit-reversed order)
         for (int s = 0; s < 3; s++)
         {
+            PhaseTimer t(c_, "boot_coeff_to_slot");
             ct = linear_transform(ev, ct, cts_[s], keys);
         }
         Ct conj = ev.complex_conjugate(ct, keys);
@@ -582,7 +650,11 @@ namespace moai
         std::vector<cd> minus_i((size_t)n, cd(0, -1)), plus_i((size_t)n, cd(0, 1));
         im = ev.multiply_plain(im, ev.encode(minus_i, im.limbs, 1.0)); // exact monomial, no level
         // 3. EvalMod on both halves as one batch: sin(2 pi t / q0) ~ 2 pi m / q0
-        Ct both = eval_mod(ev, ev.concat({ re, im }), keys);
+        Ct both;
+        {
+            PhaseTimer t(c_, "boot_eval_mod");
+            both = eval_mod(ev, ev.concat({ re, im }), keys);
+        }
         re = ev.view(both, 0, in.batch);
         im = ev.view(both, in.batch, in.batch);
         // 4. SlotToCoeff on re + i im, constants q0 / (2 pi initial_scale) folded into the diagonals
@@ -612,6 +684,7 @@ namespace moai
         MOAI_REQUIRE(w.limbs == stc_[0].limbs, "level budget mismatch before SlotToCoeff");
         for (int s = 0; s < 3; s++)
         {
+            PhaseTimer t(c_, "boot_slot_to_coeff");
             w = linear_transform(ev, w, stc_[s], keys);
         }
         w.scale = prm.final_scale;

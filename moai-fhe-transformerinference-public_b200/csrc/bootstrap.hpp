@@ -34,6 +34,7 @@ namespace moai
         int log_width = 10;   // loge                     (:352)
         int total_limbs = 35; // data limbs after ModRaise (:368)
         double final_scale = 70368744177664.0; // 2^46
+        int hoisting = 0;     // 1: plan the BSGS stages for hoisted baby steps (more, cheaper baby steps)
     };
 
     // one sparse-diagonal matrix, prepared for BSGS evaluation at a fixed level
@@ -53,6 +54,8 @@ namespace moai
     {
     public:
         Bootstrapper(Context *ctx, const BootParams &p);
+        // re-plan the linear stages for hoisted (pre-permuted-key) rotations; call before required_steps()
+        void set_hoisting(bool on);
         std::vector<int> required_steps() const; // rotation steps (normalised to [0, slots)) the BSGS plans use
         // in: batch of size-2 ciphertexts at 1 limb (chain_index 0); returns them at
         // total_limbs - 14 limbs with scale final_scale

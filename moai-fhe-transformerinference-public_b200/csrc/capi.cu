@@ -19,6 +19,7 @@ struct moai_context
 struct moai_keys
 {
     Keys k;
+    int kl = 0; // key-level limb count of the owning context (SEAL-layout keys)
 };
 
 struct moai_bootstrapper
@@ -515,9 +516,10 @@ extern "C"
     int32_t moai_keys_create(moai_context *ctx, moai_keys **out)
     {
         API_BEGIN
-        get(ctx);
+        Context *c = get(ctx);
         MOAI_REQUIRE(out, "null argument");
         *out = new moai_keys();
+        (*out)->kl = c->kl;
         API_END
     }
 
@@ -532,7 +534,7 @@ extern "C"
     {
         API_BEGIN
         MOAI_REQUIRE(keys, "null argument");
-        keys->k.relin = CU(ksk);
+        keys->k.relin = KeyRef{ CU(ksk), keys->kl };
         API_END
     }
 
@@ -540,7 +542,26 @@ extern "C"
     {
         API_BEGIN
         MOAI_REQUIRE(keys && ksk, "null argument");
-        keys->k.galois[galois_elt] = CU(ksk);
+        keys->k.galois[galois_elt] = KeyRef{ CU(ksk), keys->kl };
+        API_END
+    }
+
+    int32_t moai_keys_add_galois_fast(moai_keys *keys, uint32_t galois_elt, const uint64_t *ksk_pre, int32_t key_limbs)
+    {
+        API_BEGIN
+        MOAI_REQUIRE(keys && ksk_pre, "null argument");
+        MOAI_REQUIRE(key_limbs >= 2 && key_limbs <= keys->kl, "key_limbs out of range");
+        keys->k.galois_fast[galois_elt].push_back(KeyRef{ CU(ksk_pre), key_limbs });
+        API_END
+    }
+
+    int32_t moai_key_prepare(moai_context *ctx, const uint64_t *ksk_in, uint32_t galois_elt, int32_t max_limbs,
+                             int32_t pre_permute, uint64_t *ksk_out)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(ksk_in && ksk_out, "null argument");
+        key_prepare(c, CU(ksk_in), galois_elt, max_limbs, pre_permute != 0, U(ksk_out));
         API_END
     }
 
@@ -576,6 +597,26 @@ extern "C"
         Ct r = ev.rotate_vector(a, steps, getk(keys));
         MOAI_CUDA_CHECK(cudaMemcpyAsync(out, r.d, (size_t)batch * 2 * limbs * c->n * sizeof(u64),
                                         cudaMemcpyDeviceToDevice, c->stream));
+        MOAI_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        API_END
+    }
+
+    int32_t moai_rotate_many(moai_context *ctx, moai_keys *keys, const uint64_t *in, int64_t batch, int32_t limbs,
+                             const int32_t *steps, int32_t n_steps, uint64_t *out)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        check_shape(c, batch, 2, limbs);
+        MOAI_REQUIRE(steps && out && n_steps >= 0, "bad arguments");
+        Evaluator ev(c);
+        Ct a = ev.wrap(const_cast<u64 *>(CU(in)), batch, 2, limbs, 1.0);
+        std::vector<Ct> r = ev.rotate_many(a, std::vector<int>(steps, steps + n_steps), getk(keys));
+        const size_t per = (size_t)batch * 2 * limbs * c->n;
+        for (int s = 0; s < n_steps; s++)
+        {
+            MOAI_CUDA_CHECK(cudaMemcpyAsync(out + s * per, r[s].d, per * sizeof(u64), cudaMemcpyDeviceToDevice,
+                                            c->stream));
+        }
         MOAI_CUDA_CHECK(cudaStreamSynchronize(c->stream));
         API_END
     }
@@ -691,6 +732,14 @@ extern "C"
             delete b->b;
             delete b;
         }
+        API_END
+    }
+
+    int32_t moai_bootstrapper_set_hoisting(moai_bootstrapper *b, int32_t on)
+    {
+        API_BEGIN
+        MOAI_REQUIRE(b, "null argument");
+        b->b->set_hoisting(on != 0);
         API_END
     }
 

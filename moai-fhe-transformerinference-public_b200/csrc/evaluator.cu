@@ -1,6 +1,7 @@
 // Implementation of the batched host-side Evaluator (see evaluator.hpp).  Every method keeps
 // SEAL's metadata semantics; the cited lines are where the reference defines them.
 #include "evaluator.hpp"
+#include <algorithm>
 #include <cstring>
 
 namespace moai
@@ -262,9 +263,9 @@ namespace moai
     {
         // S/evaluator.cpp:1345-1400
         EV_REQUIRE(a3.size == 3, "relinearize expects a size-3 ciphertext");
-        EV_REQUIRE(k.relin != nullptr, "not enough relinearization keys");
+        EV_REQUIRE(k.relin.p != nullptr, "not enough relinearization keys");
         Ct r = alloc(a3.batch, 2, a3.limbs, a3.scale);
-        moai::relinearize(c, a3.d, r.d, a3.batch, a3.limbs, k.relin);
+        moai::relinearize(c, a3.d, r.d, a3.batch, a3.limbs, k.relin.p, k.relin.key_kl);
         return r;
     }
 
@@ -303,8 +304,12 @@ namespace moai
         if (it != k.galois.end())
         {
             Ct r = alloc(a.batch, 2, a.limbs, a.scale);
-            apply_galois(c, a.d, r.d, a.batch, a.limbs, elt, it->second);
+            apply_galois(c, a.d, r.d, a.batch, a.limbs, elt, it->second.p, it->second.key_kl);
             return r;
+        }
+        if (const KeyRef *fk = k.fast(elt, a.limbs))
+        {
+            return rotate_fast(a, elt, *fk);
         }
         // NAF decomposition (S/util/numth.h:22-42)
         std::vector<int> naf;
@@ -337,10 +342,108 @@ namespace moai
     {
         uint32_t elt = c->elt_from_step(0);
         auto it = k.galois.find(elt);
-        EV_REQUIRE(it != k.galois.end(), "Galois key not present");
+        if (it == k.galois.end())
+        {
+            const KeyRef *fk = k.fast(elt, a.limbs);
+            EV_REQUIRE(fk != nullptr, "Galois key not present");
+            return rotate_fast(a, elt, *fk);
+        }
         Ct r = alloc(a.batch, 2, a.limbs, a.scale);
-        apply_galois(c, a.d, r.d, a.batch, a.limbs, elt, it->second);
+        apply_galois(c, a.d, r.d, a.batch, a.limbs, elt, it->second.p, it->second.key_kl);
         return r;
+    }
+
+    // ---------------------------------------------------------------- hoisted rotations (fast mode)
+    bool Evaluator::has_fast_key(int steps, int limbs, const Keys &k) const
+    {
+        return steps == 0 || k.fast(c->elt_from_step(steps), limbs) != nullptr;
+    }
+
+    Hoisted Evaluator::hoist(const Ct &a) const
+    {
+        EV_REQUIRE(a.size == 2, "encrypted size must be 2");
+        Hoisted h;
+        h.src = a;
+        h.ext = std::make_shared<DevBuf>((size_t)a.batch * ks_ext_bytes_per_ct(c, a.limbs), c->stream);
+        ks_decompose(c, a.d + (size_t)a.limbs * n(), a.batch, a.limbs, reinterpret_cast<u64 *>(h.ext->p),
+                     2LL * a.limbs * (long long)n());
+        return h;
+    }
+
+    Ct Evaluator::rotate_hoisted(const Hoisted &h, int steps, const Keys &k) const
+    {
+        const Ct &a = h.src;
+        if (steps == 0)
+        {
+            return a;
+        }
+        const uint32_t elt = c->elt_from_step(steps);
+        const KeyRef *fk = k.fast(elt, a.limbs);
+        EV_REQUIRE(fk != nullptr, "pre-permuted Galois key not present");
+        Ct r = alloc(a.batch, 2, a.limbs, a.scale);
+        moai::rotate_hoisted(c, a.d, reinterpret_cast<const u64 *>(h.ext->p), a.batch, a.limbs, elt, fk->p, fk->key_kl,
+                             r.d);
+        return r;
+    }
+
+    Ct Evaluator::rotate_fast(const Ct &a, uint32_t elt, const KeyRef &key) const
+    {
+        Ct r = alloc(a.batch, 2, a.limbs, a.scale);
+        const long long chunk = ks_chunk(c, a.limbs, a.batch, (size_t)2 << 30);
+        DevBuf ext((size_t)chunk * ks_ext_bytes_per_ct(c, a.limbs), c->stream);
+        const size_t per_ct = (size_t)2 * a.limbs * n();
+        for (long long b0 = 0; b0 < a.batch; b0 += chunk)
+        {
+            const long long nb = std::min(chunk, a.batch - b0);
+            const u64 *src = a.d + (size_t)b0 * per_ct;
+            ks_decompose(c, src + (size_t)a.limbs * n(), nb, a.limbs, reinterpret_cast<u64 *>(ext.p),
+                         (long long)per_ct);
+            moai::rotate_hoisted(c, src, reinterpret_cast<const u64 *>(ext.p), nb, a.limbs, elt, key.p, key.key_kl,
+                                 r.d + (size_t)b0 * per_ct);
+        }
+        return r;
+    }
+
+    std::vector<Ct> Evaluator::rotate_many(const Ct &a, const std::vector<int> &steps, const Keys &k) const
+    {
+        std::vector<Ct> out(steps.size());
+        bool all_fast = true;
+        int nonzero = 0;
+        for (int s : steps)
+        {
+            all_fast = all_fast && has_fast_key(s, a.limbs, k);
+            nonzero += s != 0;
+        }
+        if (!all_fast || nonzero < 2)
+        {
+            for (size_t i = 0; i < steps.size(); i++)
+            {
+                out[i] = rotate_vector(a, steps[i], k);
+            }
+            return out;
+        }
+        for (size_t i = 0; i < steps.size(); i++)
+        {
+            out[i] = steps[i] == 0 ? a : alloc(a.batch, 2, a.limbs, a.scale);
+        }
+        // the decomposition of a chunk is shared by all rotations; ~4 GiB of extended digits at a time
+        const long long chunk = ks_chunk(c, a.limbs, a.batch, (size_t)4 << 30);
+        for (long long b0 = 0; b0 < a.batch; b0 += chunk)
+        {
+            const long long nb = std::min(chunk, a.batch - b0);
+            Hoisted h = hoist(view(a, b0, nb));
+            for (size_t i = 0; i < steps.size(); i++)
+            {
+                if (steps[i] != 0)
+                {
+                    const uint32_t elt = c->elt_from_step(steps[i]);
+                    const KeyRef *fk = k.fast(elt, a.limbs);
+                    moai::rotate_hoisted(c, h.src.d, reinterpret_cast<const u64 *>(h.ext->p), nb, a.limbs, elt, fk->p,
+                                         fk->key_kl, out[i].d + (size_t)b0 * 2 * a.limbs * n());
+                }
+            }
+        }
+        return out;
     }
 
     // ---------------------------------------------------------------- encoder

@@ -67,11 +67,53 @@ namespace moai
         std::vector<u64> consts;
     };
 
+    // One key-switching key on the device.  key_kl = limbs stored per key polynomial: the
+    // context's kl for SEAL's layout [kl-1][2][kl][n] (S/kswitchkeys.h:335-340), L + 1 for a key
+    // truncated to its first L digits / data limbs (+ the special prime) by key_prepare.
+    struct KeyRef
+    {
+        const u64 *p = nullptr;
+        int key_kl = 0;
+        int max_limbs() const
+        {
+            return key_kl - 1;
+        }
+    };
+
     // Device key material: SEAL's RelinKeys / GaloisKeys as raw device pointers.
+    //  * galois      : keys exactly as SEAL generates them -> SEAL-bit-exact rotations.
+    //  * galois_fast : pre-permuted keys K' = sigma^-1(K) (key_prepare), possibly several level
+    //                  truncations per element -> hoisted rotations (same plaintext, different noise).
     struct Keys
     {
-        const u64 *relin = nullptr;
-        std::map<uint32_t, const u64 *> galois;
+        KeyRef relin;
+        std::map<uint32_t, KeyRef> galois;
+        std::map<uint32_t, std::vector<KeyRef>> galois_fast;
+        // smallest pre-permuted key of `elt` that covers `limbs` levels (nullptr when none)
+        const KeyRef *fast(uint32_t elt, int limbs) const
+        {
+            auto it = galois_fast.find(elt);
+            if (it == galois_fast.end())
+            {
+                return nullptr;
+            }
+            const KeyRef *best = nullptr;
+            for (auto &k : it->second)
+            {
+                if (k.max_limbs() >= limbs && (!best || k.key_kl < best->key_kl))
+                {
+                    best = &k;
+                }
+            }
+            return best;
+        }
+    };
+
+    // Digit decomposition of c1 of a batch of ciphertexts, shared by every hoisted rotation of them.
+    struct Hoisted
+    {
+        Ct src;                      // the unrotated ciphertexts (shared storage)
+        std::shared_ptr<DevBuf> ext; // [batch][limbs + 1][limbs][n]
     };
 
     class Evaluator
@@ -116,6 +158,13 @@ namespace moai
         }
         Ct rotate_vector(const Ct &a, int steps, const Keys &k) const;
         Ct complex_conjugate(const Ct &a, const Keys &k) const;
+        // fast mode: one decomposition, many rotations.  Needs pre-permuted keys.
+        bool has_fast_key(int steps, int limbs, const Keys &k) const;
+        Hoisted hoist(const Ct &a) const;
+        Ct rotate_hoisted(const Hoisted &h, int steps, const Keys &k) const;
+        Ct rotate_fast(const Ct &a, uint32_t elt, const KeyRef &key) const; // chunked hoist + rotate
+        // rotations of one batch by several steps: hoisted when every key is pre-permuted, else one by one
+        std::vector<Ct> rotate_many(const Ct &a, const std::vector<int> &steps, const Keys &k) const;
         Ct sum_batch(const Ct &a) const; // one ciphertext = sum over the batch (modular)
         Ct inner_product(const Ct &a, const Ct &b) const;      // size-3 sum_j a[j] x b[j]
         Ct sum_sub_square(const Ct &a, const Ct &m) const;     // size-3 sum_j (a[j] - m)^2, m one ciphertext

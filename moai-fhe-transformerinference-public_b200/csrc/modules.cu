@@ -267,11 +267,42 @@ namespace moai
         MOAI_REQUIRE(X.batch == col_X && W.batch == col_X, "bad dimensions of X or W");
         const double scale = X.scale;
         Ct acc = ev.alloc(row_X, 3, X.limbs, X.scale * W.scale);
-        for (int i = 0; i < row_X; ++i)
+        // fast mode (pre-permuted keys for the steps b * num_batch, b < 16): rotation i = 16 a + b is a
+        // giant rotation by 16 a followed by a HOISTED baby rotation by b, so the 64 columns are
+        // decomposed once per giant step instead of once per row (the reference rotates every W[j]
+        // from scratch for every i through SEAL's NAF fallback, Ct_ct_matrix_mul.hpp:26-31)
+        const int inner = 16;
+        bool fast = row_X > inner;
+        for (int b = 1; b < inner && fast; b++)
         {
-            Ct w = i > 0 ? ev.rotate_vector(W, i * num_batch, keys) : W; // all col_X columns in one batch
-            Ct s = ev.inner_product(X, w);
-            ev.copy_into(s, acc, i);
+            fast = ev.has_fast_key(b * num_batch, W.limbs, keys);
+        }
+        if (fast)
+        {
+            for (int a0 = 0; a0 < row_X; a0 += inner)
+            {
+                Ct wa = a0 > 0 ? ev.rotate_vector(W, a0 * num_batch, keys) : W;
+                std::vector<int> steps;
+                for (int b = 0; b < inner && a0 + b < row_X; b++)
+                {
+                    steps.push_back(b * num_batch);
+                }
+                std::vector<Ct> rots = ev.rotate_many(wa, steps, keys);
+                for (size_t b = 0; b < rots.size(); b++)
+                {
+                    Ct s = ev.inner_product(X, rots[b]);
+                    ev.copy_into(s, acc, a0 + (long long)b);
+                }
+            }
+        }
+        else
+        {
+            for (int i = 0; i < row_X; ++i)
+            {
+                Ct w = i > 0 ? ev.rotate_vector(W, i * num_batch, keys) : W; // all col_X columns in one batch
+                Ct s = ev.inner_product(X, w);
+                ev.copy_into(s, acc, i);
+            }
         }
         Ct out = ev.rescale_to_next(ev.relinearize(acc, keys));
         out.scale = scale;
@@ -312,12 +343,12 @@ namespace moai
             ev.copy_into(r, rotX, first);
         }
         // baby steps of every output column at once: c_g[k] = rot(W, k * num_batch), batch = col_W
-        std::vector<Ct> c_g(g);
-        c_g[0] = W;
-        for (int k = 1; k < g; ++k)
+        std::vector<int> bsteps;
+        for (int k = 0; k < g; ++k)
         {
-            c_g[k] = ev.rotate_vector(W, k * num_batch, keys);
+            bsteps.push_back(k * num_batch);
         }
+        std::vector<Ct> c_g = ev.rotate_many(W, bsteps, keys); // hoisted when the keys are pre-permuted
         // giant steps: out[j] = sum_k c_g[k] (x) rotX[j*g + k]   (size 3, one relin + rescale per j)
         Ct output;
         for (int j = 0; j < b; ++j)
@@ -586,7 +617,7 @@ namespace moai
         {
             // 3072 independent GELUs (test_full_scheme.hpp:884-888); chunked: gelu_v2 keeps 24 powers alive
             PhaseTimer t(c, "gelu");
-            const long long chunk = 256;
+            const long long chunk = 64;
             Ct g;
             for (long long b0 = 0; b0 < inter.batch; b0 += chunk)
             {

@@ -225,7 +225,8 @@ namespace moai
         __global__ void k_divround_finish(const ulonglong2 *__restrict__ in, const ulonglong2 *__restrict__ u,
                                           const ulonglong2 *addend, ulonglong2 *out, // may alias each other
                                           long long total2, int log_n2, int targets, int limbs_in, int last_id, int kl,
-                                          const LimbConst *__restrict__ lcs, const Twiddle *__restrict__ inv_last)
+                                          const LimbConst *__restrict__ lcs, const Twiddle *__restrict__ inv_last,
+                                          int addend_even_only)
         {
             long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; // over [P][targets][n/2]
             if (i >= total2)
@@ -243,7 +244,7 @@ namespace moai
             ulonglong2 r;
             r.x = mul_shoup(submod(x.x, y.x, q), inv.w, inv.wq, q);
             r.y = mul_shoup(submod(x.y, y.y, q), inv.w, inv.wq, q);
-            if (addend)
+            if (addend && !(addend_even_only && (p & 1)))
             {
                 ulonglong2 z = addend[i];
                 r.x = addmod(r.x, z.x, q);
@@ -253,8 +254,9 @@ namespace moai
         }
 
         // in [P][limbs_in][n] -> out [P][limbs_in-1][n] (+= addend of the same shape when given)
+        // addend_even_only: add `addend` only to the even polynomials (c0 of size-2 ciphertexts)
         void divide_round_last(Context *c, const u64 *in, long long P, int limbs_in, int last_id, const u64 *addend,
-                               u64 *out)
+                               u64 *out, bool addend_even_only = false)
         {
             const size_t n = c->n;
             const int targets = limbs_in - 1;
@@ -274,8 +276,8 @@ namespace moai
             k_divround_finish<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
                 reinterpret_cast<const ulonglong2 *>(in), u.as<ulonglong2>(),
                 reinterpret_cast<const ulonglong2 *>(addend), reinterpret_cast<ulonglong2 *>(out), total2, c->log_n - 1,
-                targets, limbs_in, last_id, c->kl, c->d_limb, c->d_inv_last);
-        c->launches += 1;
+                targets, limbs_in, last_id, c->kl, c->d_limb, c->d_inv_last, addend_even_only ? 1 : 0);
+            c->launches += 1;
             MOAI_CUDA_CHECK(cudaGetLastError());
         }
 
@@ -416,6 +418,64 @@ namespace moai
             out[i + 2 * poly2] = r;
         }
 
+
+        // ------------------------------------------------------------------ BSGS inner sums
+        // inner[i][b][p] = sum_j pt[i][j] (.) rot[j][b][p]  for every giant step i of one linear stage
+        // (the plaintext-matrix inner loops of M/source/bootstrapping/Bootstrapper.cpp:2021-2044) in ONE
+        // pass: each thread keeps the baby-step rotations of its coefficient pair in registers and
+        // streams the pre-rotated diagonals; 128-bit lazy sums (<= 16 products below 2^122 each).
+        struct BsgsArgs
+        {
+            const u64 *rot[BSGS_MAX_BABY];                  // [batch][2][limbs][n] each
+            const u64 *pt[BSGS_MAX_GIANT][BSGS_MAX_BABY];   // [limbs][n] each, nullptr = absent diagonal
+            u64 *out[BSGS_MAX_GIANT];                       // [batch][2][limbs][n] each
+            int n_baby, n_giant;
+        };
+
+        __global__ void __launch_bounds__(EW_THREADS) k_bsgs_inner(BsgsArgs a, long long total2, int log_n2, int limbs,
+                                                                   const LimbConst *__restrict__ lcs,
+                                                                   const Twiddle *__restrict__ two64)
+        {
+            long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; // over [batch][2][limbs][n/2]
+            if (i >= total2)
+            {
+                return;
+            }
+            const long long lp = i >> log_n2;
+            const int limb = (int)(lp % limbs);
+            const long long within = i & (((long long)1 << log_n2) - 1);
+            const long long pt_off = ((long long)limb << log_n2) + within;
+            const LimbConst lc = lcs[limb];
+            const Twiddle t64 = two64[limb];
+            ulonglong2 r[BSGS_MAX_BABY];
+#pragma unroll
+            for (int j = 0; j < BSGS_MAX_BABY; j++)
+            {
+                if (j < a.n_baby)
+                {
+                    r[j] = reinterpret_cast<const ulonglong2 *>(a.rot[j])[i];
+                }
+            }
+            for (int g = 0; g < a.n_giant; g++)
+            {
+                u128 sx{ 0, 0 }, sy{ 0, 0 };
+#pragma unroll
+                for (int j = 0; j < BSGS_MAX_BABY; j++)
+                {
+                    if (j < a.n_baby && a.pt[g][j])
+                    {
+                        const ulonglong2 w = __ldg(reinterpret_cast<const ulonglong2 *>(a.pt[g][j]) + pt_off);
+                        mac_wide(sx, r[j].x, w.x);
+                        mac_wide(sy, r[j].y, w.y);
+                    }
+                }
+                ulonglong2 o;
+                o.x = barrett_reduce_acc(sx, lc, t64.w, t64.wq);
+                o.y = barrett_reduce_acc(sy, lc, t64.w, t64.wq);
+                reinterpret_cast<ulonglong2 *>(a.out[g])[i] = o;
+            }
+        }
+
         // ------------------------------------------------------------------ key switch pieces
         // ext[b][I][J][n] = d[b][J][n] mod m_I   (I over {q_0..q_{l-1}, p})
         __global__ void k_ks_expand(const ulonglong2 *__restrict__ d, ulonglong2 *__restrict__ ext, long long total2,
@@ -443,7 +503,7 @@ namespace moai
 
         // acc[b][k][I][n] = sum_J ext[b][I][J][n] * ksk[J][k][ids_ks[I]][n] mod m_I
         __global__ void k_ks_mac(const ulonglong2 *__restrict__ ext, const ulonglong2 *__restrict__ ksk,
-                                 ulonglong2 *__restrict__ acc, long long batch, int log_n2, int limbs, int kl,
+                                 ulonglong2 *__restrict__ acc, long long batch, int log_n2, int limbs, int key_kl,
                                  const int *__restrict__ ids_ks, const LimbConst *__restrict__ lcs,
                                  const Twiddle *__restrict__ two64)
         {
@@ -452,17 +512,20 @@ namespace moai
             const long long within = (long long)blockIdx.z * blockDim.x + threadIdx.x;
             const int I = blockIdx.y;
             const long long b = blockIdx.x;
-            const int key_limb = ids_ks[I];
-            const LimbConst lc = lcs[key_limb];
-            const Twiddle t64 = two64[key_limb];
+            const int prime = ids_ks[I];
+            // position of modulus I inside the key: data limbs first, the special prime last
+            // (a level-truncated key keeps only key_kl - 1 data limbs, see key_prepare)
+            const int key_limb = I == limbs ? key_kl - 1 : I;
+            const LimbConst lc = lcs[prime];
+            const Twiddle t64 = two64[prime];
             const long long n2 = (long long)1 << log_n2;
             const ulonglong2 *e = ext + ((b * (limbs + 1) + I) * limbs << log_n2) + within;
             u128 a0x{ 0, 0 }, a0y{ 0, 0 }, a1x{ 0, 0 }, a1y{ 0, 0 };
             for (int J = 0; J < limbs; J++)
             {
                 const ulonglong2 v = e[(long long)J << log_n2];
-                const ulonglong2 k0 = __ldg(ksk + (((long long)J * 2 + 0) * kl + key_limb) * n2 + within);
-                const ulonglong2 k1 = __ldg(ksk + (((long long)J * 2 + 1) * kl + key_limb) * n2 + within);
+                const ulonglong2 k0 = __ldg(ksk + (((long long)J * 2 + 0) * key_kl + key_limb) * n2 + within);
+                const ulonglong2 k1 = __ldg(ksk + (((long long)J * 2 + 1) * key_kl + key_limb) * n2 + within);
                 mac_wide(a0x, v.x, k0.x);
                 mac_wide(a0y, v.y, k0.y);
                 mac_wide(a1x, v.x, k1.x);
@@ -612,6 +675,34 @@ namespace moai
         MOAI_CUDA_CHECK(cudaGetLastError());
     }
 
+
+    void bsgs_inner(Context *c, const u64 *const *rot, int n_baby, const u64 *const *pt, int n_giant, u64 *const *out,
+                    long long batch, int limbs)
+    {
+        MOAI_REQUIRE(n_baby >= 1 && n_baby <= BSGS_MAX_BABY && n_giant >= 1 && n_giant <= BSGS_MAX_GIANT,
+                     "BSGS plan exceeds the fused kernel's limits");
+        BsgsArgs a;
+        a.n_baby = n_baby;
+        a.n_giant = n_giant;
+        for (int j = 0; j < n_baby; j++)
+        {
+            a.rot[j] = rot[j];
+        }
+        for (int g = 0; g < n_giant; g++)
+        {
+            a.out[g] = out[g];
+            for (int j = 0; j < n_baby; j++)
+            {
+                a.pt[g][j] = pt[g * n_baby + j];
+            }
+        }
+        const long long total2 = batch * 2 * limbs * (long long)(c->n / 2);
+        k_bsgs_inner<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(a, total2, c->log_n - 1, limbs, c->d_limb,
+                                                                     c->d_two64);
+        c->launches += 1;
+        MOAI_CUDA_CHECK(cudaGetLastError());
+    }
+
     void rescale(Context *c, const u64 *in, u64 *out, long long batch, int polys, int limbs)
     {
         MOAI_REQUIRE(limbs >= 2, "end of modulus switching chain reached");
@@ -655,7 +746,16 @@ namespace moai
         MOAI_CUDA_CHECK(cudaGetLastError());
     }
 
-    void switch_key(Context *c, u64 *ct, const u64 *target, long long batch, int limbs, const u64 *ksk)
+    size_t ks_ext_bytes_per_ct(Context *c, int limbs)
+    {
+        return (size_t)(limbs + 1) * limbs * c->n * sizeof(u64);
+    }
+
+    // Digit decomposition of a key switch (S/evaluator.cpp:2805-2856): d_J = INTT_J(target[J]);
+    // ext[b][I][J] = NTT_I(d_J mod m_I) for I over {q_0..q_{l-1}, p}.
+    // `target_stride` = elements between the target polynomials of consecutive batch items
+    // (0 = contiguous; 2 * limbs * n picks c1 out of a batch of size-2 ciphertexts when target = ct + limbs * n).
+    void ks_decompose(Context *c, const u64 *target, long long batch, int limbs, u64 *ext, long long target_stride)
     {
         MOAI_REQUIRE(limbs >= 1 && limbs <= c->kl - 1, "limb count out of range");
         const size_t n = c->n;
@@ -666,52 +766,136 @@ namespace moai
         {
             fuse_expand = fuse_expand && (c->q[l] >> 52) == 0;
         }
-        // bound the extended-digit workspace (batch chunking); ~2 GiB
-        const size_t ext_per_ct = (size_t)rns * limbs * n * sizeof(u64);
-        long long chunk = (long long)(((size_t)2 << 30) / ext_per_ct);
-        chunk = chunk < 1 ? 1 : (chunk > batch ? batch : chunk);
-        Scratch d((size_t)chunk * limbs * n * sizeof(u64), c->stream);
-        Scratch ext((size_t)chunk * ext_per_ct, c->stream);
-        Scratch acc((size_t)chunk * 2 * rns * n * sizeof(u64), c->stream);
-        for (long long b0 = 0; b0 < batch; b0 += chunk)
+        Scratch d((size_t)batch * limbs * n * sizeof(u64), c->stream);
+        const size_t row = (size_t)limbs * n * sizeof(u64);
+        MOAI_CUDA_CHECK(cudaMemcpy2DAsync(d.p, row, target, target_stride ? (size_t)target_stride * sizeof(u64) : row,
+                                          row, (size_t)batch, cudaMemcpyDeviceToDevice, c->stream));
+        ntt_inverse(c, d.as<u64>(), batch * limbs, c->d_ids, limbs);
+        // NTT_I(d_I mod q_I) reproduces the target limb itself, so the I == J digits need no
+        // special case (S/evaluator.cpp:2831-2836 takes the NTT-form input there: same residues)
+        if (fuse_expand)
         {
-            const long long nb = (batch - b0) < chunk ? (batch - b0) : chunk;
-            const u64 *tg = target + (size_t)b0 * limbs * n;
-            u64 *ctb = ct + (size_t)b0 * 2 * limbs * n;
-            MOAI_CUDA_CHECK(cudaMemcpyAsync(d.p, tg, (size_t)nb * limbs * n * sizeof(u64), cudaMemcpyDeviceToDevice,
-                                            c->stream));
-            ntt_inverse(c, d.as<u64>(), nb * limbs, c->d_ids, limbs);
-            // NTT_I(d_I mod q_I) reproduces the target limb itself, so the I == J digits need no
-            // special case (S/evaluator.cpp:2831-2836 takes the NTT-form input there: same residues)
-            if (fuse_expand)
-            {
-                // digit extension (d_J mod m_I) fused into the NTT's first pass: ext is written once
-                NttPrologue pro;
-                pro.src = d.as<u64>();
-                pro.mode = 1;
-                ntt_forward(c, ext.as<u64>(), nb * rns * limbs, ids_ks, rns, limbs, &pro);
-            }
-            else
-            {
-                const long long total2 = nb * rns * limbs * (long long)(n / 2);
-                k_ks_expand<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(d.as<ulonglong2>(), ext.as<ulonglong2>(),
-                                                                            total2, c->log_n - 1, limbs, ids_ks,
-                                                                            c->d_limb);
-                c->launches += 1;
-                ntt_forward(c, ext.as<u64>(), nb * rns * limbs, ids_ks, rns, limbs);
-            }
-            dim3 grid((unsigned)nb, (unsigned)rns, (unsigned)((n / 2) / EW_THREADS));
-            k_ks_mac<<<grid, EW_THREADS, 0, c->stream>>>(ext.as<ulonglong2>(), reinterpret_cast<const ulonglong2 *>(ksk),
-                                                         acc.as<ulonglong2>(), nb, c->log_n - 1, limbs, c->kl, ids_ks,
-                                                         c->d_limb, c->d_two64);
-        c->launches += 1;
-            MOAI_CUDA_CHECK(cudaGetLastError());
-            // mod-down by the special prime and add into the ciphertext (S/evaluator.cpp:2962-3018)
-            divide_round_last(c, acc.as<u64>(), nb * 2, rns, c->kl - 1, ctb, ctb);
+            // digit extension (d_J mod m_I) fused into the NTT's first pass: ext is written once
+            NttPrologue pro;
+            pro.src = d.as<u64>();
+            pro.mode = 1;
+            ntt_forward(c, ext, batch * rns * limbs, ids_ks, rns, limbs, &pro);
+        }
+        else
+        {
+            const long long total2 = batch * rns * limbs * (long long)(n / 2);
+            k_ks_expand<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
+                d.as<ulonglong2>(), reinterpret_cast<ulonglong2 *>(ext), total2, c->log_n - 1, limbs, ids_ks, c->d_limb);
+            c->launches += 1;
+            ntt_forward(c, ext, batch * rns * limbs, ids_ks, rns, limbs);
         }
     }
 
-    void relinearize(Context *c, const u64 *in3, u64 *out2, long long batch, int limbs, const u64 *ksk)
+    // Inner product with the key and mod-down by the special prime (S/evaluator.cpp:2859-3018):
+    // out[b][k] = addend[b][k] + round(sum_J ext[b][.][J] (.) key[J][k] / p).  `key_kl` = limbs stored
+    // per key polynomial (c->kl for a SEAL-layout key, max_level + 1 for a truncated one).
+    void ks_mac_moddown(Context *c, const u64 *ext, long long batch, int limbs, const u64 *ksk, int key_kl,
+                        const u64 *addend, bool addend_c0_only, u64 *out)
+    {
+        MOAI_REQUIRE(key_kl >= limbs + 1 && key_kl <= c->kl, "key does not cover this level");
+        const size_t n = c->n;
+        const int rns = limbs + 1;
+        const int *ids_ks = c->d_ids_ks + (size_t)limbs * (c->kl + 1);
+        Scratch acc((size_t)batch * 2 * rns * n * sizeof(u64), c->stream);
+        dim3 grid((unsigned)batch, (unsigned)rns, (unsigned)((n / 2) / EW_THREADS));
+        k_ks_mac<<<grid, EW_THREADS, 0, c->stream>>>(reinterpret_cast<const ulonglong2 *>(ext),
+                                                     reinterpret_cast<const ulonglong2 *>(ksk), acc.as<ulonglong2>(),
+                                                     batch, c->log_n - 1, limbs, key_kl, ids_ks, c->d_limb, c->d_two64);
+        c->launches += 1;
+        MOAI_CUDA_CHECK(cudaGetLastError());
+        divide_round_last(c, acc.as<u64>(), batch * 2, rns, c->kl - 1, addend, out, addend_c0_only);
+    }
+
+    long long ks_chunk(Context *c, int limbs, long long batch, size_t budget_bytes)
+    {
+        long long chunk = (long long)(budget_bytes / ks_ext_bytes_per_ct(c, limbs));
+        return chunk < 1 ? 1 : (chunk > batch ? batch : chunk);
+    }
+
+    void switch_key(Context *c, u64 *ct, const u64 *target, long long batch, int limbs, const u64 *ksk, int key_kl)
+    {
+        MOAI_REQUIRE(limbs >= 1 && limbs <= c->kl - 1, "limb count out of range");
+        const size_t n = c->n;
+        if (key_kl <= 0)
+        {
+            key_kl = c->kl;
+        }
+        // bound the extended-digit workspace (batch chunking); ~2 GiB
+        const long long chunk = ks_chunk(c, limbs, batch, (size_t)2 << 30);
+        Scratch ext((size_t)chunk * ks_ext_bytes_per_ct(c, limbs), c->stream);
+        for (long long b0 = 0; b0 < batch; b0 += chunk)
+        {
+            const long long nb = (batch - b0) < chunk ? (batch - b0) : chunk;
+            u64 *ctb = ct + (size_t)b0 * 2 * limbs * n;
+            ks_decompose(c, target + (size_t)b0 * limbs * n, nb, limbs, ext.as<u64>(), 0);
+            ks_mac_moddown(c, ext.as<u64>(), nb, limbs, ksk, key_kl, ctb, false, ctb);
+        }
+    }
+
+    // Hoisted rotation (fast mode; not SEAL's residues, same plaintext up to rounding noise):
+    //   out = sigma( (c0, 0) + ModDown( sum_J ext_J (.) K'_J ) ),  K' = sigma^-1(K) (key_prepare),
+    // where ext is the digit decomposition of the UNROTATED c1 (shared by every rotation of the
+    // same ciphertext).  sigma commutes with the NTT-domain products and, up to the sign of the
+    // rounding, with the mod-down, so the automorphism is applied once at the end.
+    void rotate_hoisted(Context *c, const u64 *ct, const u64 *ext, long long batch, int limbs, uint32_t elt,
+                        const u64 *ksk_pre, int key_kl, u64 *out)
+    {
+        const size_t n = c->n;
+        Scratch tmp((size_t)batch * 2 * limbs * n * sizeof(u64), c->stream);
+        ks_mac_moddown(c, ext, batch, limbs, ksk_pre, key_kl, ct, true, tmp.as<u64>());
+        apply_galois_ntt(c, tmp.as<u64>(), out, batch * 2 * limbs, elt);
+    }
+
+    // K' = sigma_elt^-1(K) restricted to `max_limbs` digits / data limbs (+ the special prime):
+    // in  [kl-1][2][kl][n] (SEAL layout, S/kswitchkeys.h:335-340), out [max_limbs][2][max_limbs+1][n].
+    // pre_permute = false only truncates.
+    void key_prepare(Context *c, const u64 *in, uint32_t elt, int max_limbs, bool pre_permute, u64 *out)
+    {
+        MOAI_REQUIRE(max_limbs >= 1 && max_limbs <= c->kl - 1, "max_limbs out of range");
+        MOAI_REQUIRE(in != out, "key_prepare is out of place");
+        const size_t n = c->n;
+        const int okl = max_limbs + 1;
+        uint32_t inv = 1;
+        if (pre_permute)
+        {
+            // inverse of the odd element modulo 2N (Newton iteration doubles the correct bits)
+            const uint64_t m = 2 * (uint64_t)n;
+            uint64_t x = elt;
+            for (int i = 0; i < 6; i++)
+            {
+                x = (x * (2 + m * 4 - (uint64_t)elt * x % m)) % m;
+            }
+            MOAI_REQUIRE((uint64_t)elt * x % m == 1, "Galois element is not invertible");
+            inv = (uint32_t)x;
+        }
+        for (int J = 0; J < max_limbs; J++)
+        {
+            for (int k = 0; k < 2; k++)
+            {
+                const u64 *src = in + ((size_t)J * 2 + k) * c->kl * n;
+                u64 *dst = out + ((size_t)J * 2 + k) * okl * n;
+                if (pre_permute)
+                {
+                    apply_galois_ntt(c, src, dst, max_limbs, inv);
+                    apply_galois_ntt(c, src + (size_t)(c->kl - 1) * n, dst + (size_t)max_limbs * n, 1, inv);
+                }
+                else
+                {
+                    MOAI_CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)max_limbs * n * sizeof(u64),
+                                                    cudaMemcpyDeviceToDevice, c->stream));
+                    MOAI_CUDA_CHECK(cudaMemcpyAsync(dst + (size_t)max_limbs * n, src + (size_t)(c->kl - 1) * n,
+                                                    n * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+                }
+            }
+        }
+    }
+
+    void relinearize(Context *c, const u64 *in3, u64 *out2, long long batch, int limbs, const u64 *ksk, int key_kl)
     {
         const size_t n = c->n;
         const size_t poly = (size_t)limbs * n;
@@ -721,10 +905,11 @@ namespace moai
         Scratch tg((size_t)batch * poly * sizeof(u64), c->stream);
         MOAI_CUDA_CHECK(cudaMemcpy2DAsync(tg.p, poly * sizeof(u64), in3 + 2 * poly, 3 * poly * sizeof(u64),
                                           poly * sizeof(u64), (size_t)batch, cudaMemcpyDeviceToDevice, c->stream));
-        switch_key(c, out2, tg.as<u64>(), batch, limbs, ksk);
+        switch_key(c, out2, tg.as<u64>(), batch, limbs, ksk, key_kl);
     }
 
-    void apply_galois(Context *c, const u64 *in, u64 *out, long long batch, int limbs, uint32_t elt, const u64 *ksk)
+    void apply_galois(Context *c, const u64 *in, u64 *out, long long batch, int limbs, uint32_t elt, const u64 *ksk,
+                      int key_kl)
     {
         const size_t n = c->n;
         const size_t poly = (size_t)limbs * n;
@@ -738,6 +923,6 @@ namespace moai
         MOAI_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)batch * 2 * poly * sizeof(u64), c->stream));
         MOAI_CUDA_CHECK(cudaMemcpy2DAsync(out, 2 * poly * sizeof(u64), perm.p, 2 * poly * sizeof(u64),
                                           poly * sizeof(u64), (size_t)batch, cudaMemcpyDeviceToDevice, c->stream));
-        switch_key(c, out, tg.as<u64>(), batch, limbs, ksk);
+        switch_key(c, out, tg.as<u64>(), batch, limbs, ksk, key_kl);
     }
 } // namespace moai

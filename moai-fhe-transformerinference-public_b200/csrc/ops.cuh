@@ -32,14 +32,33 @@ namespace moai
                      bool b_broadcast = false);
     void ew_square(Context *c, const u64 *a, u64 *out3, long long batch, int limbs);
 
+    // fused BSGS inner sums of one linear stage: out[g] = sum_j pt[g * n_baby + j] (.) rot[j]
+    // (pt entries may be nullptr = absent diagonal; plaintexts broadcast over the batch)
+    constexpr int BSGS_MAX_BABY = 16, BSGS_MAX_GIANT = 8;
+    void bsgs_inner(Context *c, const u64 *const *rot, int n_baby, const u64 *const *pt, int n_giant, u64 *const *out,
+                    long long batch, int limbs);
+
     void rescale(Context *c, const u64 *in, u64 *out, long long batch, int polys, int limbs);
     void mod_switch_drop(Context *c, const u64 *in, u64 *out, long long batch, int polys, int limbs_in, int limbs_out);
     void mod_raise(Context *c, const u64 *in, u64 *out, long long batch, int polys, int limbs_out);
 
     void apply_galois_ntt(Context *c, const u64 *in, u64 *out, long long count_polys_limbs, uint32_t elt);
-    void switch_key(Context *c, u64 *ct, const u64 *target, long long batch, int limbs, const u64 *ksk);
-    void relinearize(Context *c, const u64 *in3, u64 *out2, long long batch, int limbs, const u64 *ksk);
-    void apply_galois(Context *c, const u64 *in, u64 *out, long long batch, int limbs, uint32_t elt, const u64 *ksk);
+    // key_kl = limbs stored per key polynomial: 0 / c->kl for SEAL's layout [kl-1][2][kl][n], L + 1 for
+    // a key truncated to L levels by key_prepare ([L][2][L+1][n])
+    void switch_key(Context *c, u64 *ct, const u64 *target, long long batch, int limbs, const u64 *ksk, int key_kl = 0);
+    void relinearize(Context *c, const u64 *in3, u64 *out2, long long batch, int limbs, const u64 *ksk,
+                     int key_kl = 0);
+    void apply_galois(Context *c, const u64 *in, u64 *out, long long batch, int limbs, uint32_t elt, const u64 *ksk,
+                      int key_kl = 0);
+    // the two halves of a key switch, exposed for hoisting (one decomposition, many rotations)
+    size_t ks_ext_bytes_per_ct(Context *c, int limbs);
+    long long ks_chunk(Context *c, int limbs, long long batch, size_t budget_bytes);
+    void ks_decompose(Context *c, const u64 *target, long long batch, int limbs, u64 *ext, long long target_stride = 0);
+    void ks_mac_moddown(Context *c, const u64 *ext, long long batch, int limbs, const u64 *ksk, int key_kl,
+                        const u64 *addend, bool addend_c0_only, u64 *out);
+    void rotate_hoisted(Context *c, const u64 *ct, const u64 *ext, long long batch, int limbs, uint32_t elt,
+                        const u64 *ksk_pre, int key_kl, u64 *out);
+    void key_prepare(Context *c, const u64 *in, uint32_t elt, int max_limbs, bool pre_permute, u64 *out);
 
     // fused module: out[C][2][limbs-1][n] = rescale(sum_j X[j] * encode_scalar(W[j][i]))
     void ct_pt_matmul_scalar(Context *c, const u64 *X, const double *h_W, int K, int C, int limbs, double scale,

@@ -16,21 +16,40 @@ NUM_BATCH = 16          # slots / 128 at N = 4096
 TOK = 5                 # valid tokens per input (the reference run uses 5)
 
 
-@pytest.fixture(scope="module")
-def env(pkg):
+@pytest.fixture(scope="module", params=["exact", "fast"])
+def env(pkg, request):
+    """exact: SEAL-layout keys (the bootstrapping steps + the driver's powers of two, NAF fallback for
+    the rest) -> every key switch is SEAL's.  fast: hoisted rotations with pre-permuted keys for the
+    exact steps the pipeline takes, truncated to the level they are used at."""
     from oracle import Oracle
     o = Oracle(12, BITS)
     be = pkg.Backend(12, o.q)
     boot = pkg.Bootstrapper(be, total_limbs=35)
     sk = o.gen_secret(7, hamming_weight=64)
-    steps = set(boot.required_steps())
-    for k in range(11):
-        steps |= {1 << k, (o.n // 2) - (1 << k)}
-    gal = {}
-    for i, st in enumerate(sorted(steps) + [0]):
+    relin = pkg.to_device(o.gen_relin_key(sk, 5))
+
+    def gen(i, st):
         e = o.elt_from_step(st)
-        gal[e] = pkg.to_device(o.gen_galois_key(sk, 3000 + i, e))
-    keys = be.make_keys(relin=pkg.to_device(o.gen_relin_key(sk, 5)), galois=gal)
+        return e, pkg.to_device(o.gen_galois_key(sk, 3000 + i, e).reshape(o.kl - 1, 2, o.kl, o.n))
+
+    if request.param == "exact":
+        steps = set(boot.required_steps())
+        for k in range(11):
+            steps |= {1 << k, (o.n // 2) - (1 << k)}
+        gal = dict(gen(i, st) for i, st in enumerate(sorted(steps) + [0]))
+        keys = be.make_keys(relin=relin, galois=gal)
+    else:
+        boot.set_hoisting(True)
+        fast = {}
+        for i, st in enumerate(boot.required_steps() + [0]):
+            e, k = gen(i, st)
+            fast.setdefault(e, []).append(be.key_prepare(k, e))
+        att = pkg.attention_rotation_steps(NUM_BATCH)
+        for tag, level in (("qk", 14), ("sv", 3)):
+            for i, st in enumerate(att[tag]):
+                e, k = gen(500 + 100 * level + i, st)
+                fast.setdefault(e, []).append(be.key_prepare(k, e, max_limbs=level))
+        keys = be.make_keys(relin=relin, galois_fast=fast)
     mask = np.zeros(o.n // 2, dtype=np.int32)
     for k in range(TOK):
         mask[k * NUM_BATCH:(k + 1) * NUM_BATCH] = 1
