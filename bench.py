@@ -109,12 +109,13 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, reasons, smax = [], set(), None
+        sm, reasons, smax, power = [], set(), None, []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 smax = float(r[1])
+                power.append(float(r[2]))
                 for nm, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
@@ -123,7 +124,8 @@ class ClockSampler:
         sm.sort()
         # under load = upper half of the samples (the sampler also sees idle gaps between steps)
         med = sm[(len(sm) * 3) // 4] if sm else None
-        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
+                "sm_mhz_min": sm[0] if sm else None, "power_w_max": max(power) if power else None}
 
 
 def synth_inputs(torch, primes, device, seed):

@@ -155,7 +155,7 @@ extern "C"
         API_BEGIN
         Context *c = get(ctx);
         MOAI_REQUIRE(out, "null argument");
-        MOAI_CUDA_CHECK(cudaMallocAsync(out, bytes ? bytes : 8, c->stream));
+        *out = device_alloc(bytes, c->stream);
         API_END
     }
 
@@ -897,7 +897,8 @@ extern "C"
         lw.ln2_beta.assign(w->ln2_beta, w->ln2_beta + H);
         std::vector<int> bv(bias_vec, bias_vec + c->n / 2);
         Ct r = encoder_layer(ev, ev.wrap(const_cast<u64 *>(CU(x)), w->hidden, 2, limbs, scale), lw, bv, input_num,
-                             getk(keys), *b->b, num_batch, layer_id, boot_chunk > 0 ? boot_chunk : 32);
+                             getk(keys), *b->b, num_batch, layer_id, boot_chunk > 0 ? boot_chunk : 32,
+                             /*reuse_input=*/out == x);
         emit(c, r, out, w->hidden, out_limbs, out_scale);
         API_END
     }
@@ -912,6 +913,9 @@ extern "C"
         {
             s += kv.first + ":" + std::to_string(kv.second.first) + ":" + std::to_string(kv.second.second) + ";";
         }
+        const AllocStats as = alloc_stats();
+        s += "alloc_host:" + std::to_string(as.host_ms) + ":" + std::to_string(as.calls) + ";";
+        s += "alloc_trim_retries:0:" + std::to_string(as.retries) + ";";
         MOAI_REQUIRE((int)s.size() < capacity, "buffer too small");
         std::memcpy(buf, s.c_str(), s.size() + 1);
         API_END

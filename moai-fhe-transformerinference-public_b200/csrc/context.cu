@@ -4,6 +4,8 @@
 // NTTTables::initialize (S/util/ntt.cpp:241-300), RNSTool::initialize (S/util/rns.cpp:578-787),
 // GaloisTool (S/util/galois.cpp:18-95) and CKKSEncoder::CKKSEncoder (S/ckks.cpp:20-75).
 #include "context.hpp"
+#include <chrono>
+#include <cstdio>
 #include <cmath>
 #include <complex>
 #include <cstring>
@@ -100,11 +102,68 @@ namespace moai
         return g_last_error;
     }
 
+    // Stream-ordered allocation from the device's default pool.  The pool keeps freed blocks cached
+    // (unlimited release threshold), which fragments under GiB-sized, ever-changing requests: on failure
+    // drain the stream, hand the cached blocks back to the driver and retry once; a second failure is
+    // reported with the request size and the pool's state.
+    static thread_local const char *g_phase = "";
+    void set_phase(const char *name)
+    {
+        g_phase = name ? name : "";
+    }
+
+    static AllocStats g_alloc_stats;
+    AllocStats alloc_stats()
+    {
+        return g_alloc_stats;
+    }
+
+    void *device_alloc(size_t bytes, cudaStream_t stream)
+    {
+        void *p = nullptr;
+        bytes = bytes ? bytes : 8;
+        const auto t0 = std::chrono::steady_clock::now();
+        cudaError_t e = cudaMallocAsync(&p, bytes, stream);
+        g_alloc_stats.calls += 1;
+        g_alloc_stats.host_ms +=
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (e == cudaSuccess)
+        {
+            return p;
+        }
+        g_alloc_stats.retries += 1;
+        cudaGetLastError();
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaMemPool_t pool;
+        cudaDeviceGetDefaultMemPool(&pool, dev);
+        cudaStreamSynchronize(stream);
+        cudaMemPoolTrimTo(pool, 0);
+        e = cudaMallocAsync(&p, bytes, stream);
+        if (e == cudaSuccess)
+        {
+            return p;
+        }
+        cudaGetLastError();
+        size_t free_b = 0, total_b = 0;
+        uint64_t reserved = 0, used = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+        char buf[320];
+        snprintf(buf, sizeof buf,
+                 "device allocation of %.2f GiB failed in phase '%s': %s (device free %.1f of %.1f GiB; pool reserved "
+                 "%.1f GiB, in use %.1f GiB)",
+                 bytes / 1073741824.0, g_phase, cudaGetErrorString(e), free_b / 1073741824.0, total_b / 1073741824.0,
+                 reserved / 1073741824.0, used / 1073741824.0);
+        throw StatusError{ e == cudaErrorMemoryAllocation ? OUT_OF_MEMORY : CUDA_ERROR, buf };
+    }
+
     Scratch::Scratch(size_t bytes, cudaStream_t stream) : s(stream)
     {
         if (bytes)
         {
-            MOAI_CUDA_CHECK(cudaMallocAsync(&p, bytes, stream));
+            p = device_alloc(bytes, stream);
         }
     }
 

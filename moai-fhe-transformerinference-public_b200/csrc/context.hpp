@@ -33,6 +33,15 @@ namespace moai
 
     void set_last_error(const std::string &msg);
     const std::string &last_error();
+    // stream-ordered allocation with one trim-and-retry on failure (context.cu)
+    void *device_alloc(size_t bytes, cudaStream_t stream);
+    void set_phase(const char *name); // last pipeline phase entered (for allocation-failure reports)
+    struct AllocStats
+    {
+        unsigned long long calls = 0, retries = 0; // retries = allocations that needed a pool trim
+        double host_ms = 0;                        // host time spent inside cudaMallocAsync
+    };
+    AllocStats alloc_stats();
 
 #define MOAI_CUDA_CHECK(expr)                                                                                          \
     do                                                                                                                 \
@@ -115,6 +124,7 @@ namespace moai
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         PhaseTimer(Context *ctx, const char *nm) : c(ctx), name(nm)
         {
+            set_phase(nm);
             if (c->profiling)
             {
                 cudaEventCreate(&e0);
@@ -138,6 +148,7 @@ namespace moai
             }
         }
     };
+
 
     // stream-ordered scratch allocation
     struct Scratch

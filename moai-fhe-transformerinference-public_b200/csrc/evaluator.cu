@@ -191,6 +191,22 @@ namespace moai
         return r;
     }
 
+    void Evaluator::add_plain_inplace(Ct &a, const Pt &p) const
+    {
+        EV_REQUIRE(a.limbs == p.limbs, "encrypted and plain parameter mismatch");
+        EV_REQUIRE(are_close(a.scale, p.scale), "scale mismatch");
+        if (p.is_scalar)
+        {
+            ew_add_scalar(c, a.d, p.consts.data(), a.d, a.batch, a.size, a.limbs);
+        }
+        else
+        {
+            EV_REQUIRE(p.count == 1 || p.count == a.batch, "plaintext batch mismatch");
+            ew_addsub_plain(c, EW_ADD, a.d, p.d, a.d, a.batch, a.size, a.limbs,
+                            p.count == 1 ? 0 : (long long)a.limbs * (long long)n());
+        }
+    }
+
     Ct Evaluator::sub_plain(const Ct &a, const Pt &p) const
     {
         EV_REQUIRE(a.limbs == p.limbs, "encrypted and plain parameter mismatch");

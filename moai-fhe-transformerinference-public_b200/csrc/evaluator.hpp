@@ -24,7 +24,7 @@ namespace moai
         cudaStream_t s;
         DevBuf(size_t bytes, cudaStream_t stream) : s(stream)
         {
-            MOAI_CUDA_CHECK(cudaMallocAsync(&p, bytes ? bytes : 8, stream));
+            p = device_alloc(bytes, stream);
         }
         ~DevBuf()
         {
@@ -144,6 +144,7 @@ namespace moai
         void sub_inplace(Ct &a, const Ct &b) const;
         Ct negate(const Ct &a) const;
         Ct add_plain(const Ct &a, const Pt &p) const;
+        void add_plain_inplace(Ct &a, const Pt &p) const;
         Ct sub_plain(const Ct &a, const Pt &p) const;
         Ct multiply_plain(const Ct &a, const Pt &p) const;
         Ct multiply(const Ct &a, const Ct &b) const;     // size 2 x size 2 -> size 3

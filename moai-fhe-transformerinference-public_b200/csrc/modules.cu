@@ -190,8 +190,18 @@ namespace moai
         const long long num_ct = x.batch;
         const double nd = 768.0; // the reference hard-codes 768 in every constant
         Ct ave_x = ev.sum_batch(x);
-        Ct nx = ev.rescale_to_next(ev.multiply_plain(x, ev.encode(masked(bias_vec, nd), x.limbs, x.scale)));
-        nx.scale = scale;
+        // nx = rescale(x * encode(768 * mask)), 128 ciphertexts at a time (bounds the rescale workspace)
+        Ct nx = ev.alloc(num_ct, 2, x.limbs - 1, scale);
+        {
+            Pt nd_mask = ev.encode(masked(bias_vec, nd), x.limbs, x.scale);
+            for (long long b0 = 0; b0 < num_ct; b0 += 128)
+            {
+                const long long nb = std::min<long long>(128, num_ct - b0);
+                Ct part = ev.rescale_to_next(ev.multiply_plain(ev.view(x, b0, nb), nd_mask));
+                part.scale = scale;
+                ev.copy_into(part, nx, b0);
+            }
+        }
         ave_x = ev.mod_switch_to(ave_x, nx.limbs);
         ave_x.scale = scale;
         // var = sum_i (nx_i - u)^2 accumulated at size 3, ONE relinearization (layernorm.hpp:245-266)
@@ -398,26 +408,32 @@ namespace moai
 
     namespace
     {
-        // x[i] += encode(b[i] * mask) with both scales forced to `scale` (single_att_block.hpp:32-45)
+        // x[i] += encode(b[i] * mask) with both scales forced to `scale` (single_att_block.hpp:32-45);
+        // in place on x's storage, the plaintexts encoded and consumed 256 at a time
         Ct add_masked_bias(const Evaluator &ev, Ct x, const std::vector<double> &b, const std::vector<int> &bias_vec,
                            double scale)
         {
             const size_t slots = bias_vec.size();
-            std::vector<std::complex<double>> vals((size_t)x.batch * slots, 0.0);
-            for (long long i = 0; i < x.batch; i++)
+            const long long chunk = 256;
+            const double enc_scale = x.scale;
+            x.scale = scale;
+            std::vector<std::complex<double>> vals((size_t)std::min<long long>(chunk, x.batch) * slots);
+            for (long long b0 = 0; b0 < x.batch; b0 += chunk)
             {
-                for (size_t j = 0; j < slots; j++)
+                const long long nb = std::min(chunk, x.batch - b0);
+                for (long long i = 0; i < nb; i++)
                 {
-                    if (bias_vec[j] == 1)
+                    for (size_t j = 0; j < slots; j++)
                     {
-                        vals[(size_t)i * slots + j] = b[i];
+                        vals[(size_t)i * slots + j] = bias_vec[j] == 1 ? b[b0 + i] : 0.0;
                     }
                 }
+                Pt p = ev.encode_batch(vals.data(), nb, (int)slots, x.limbs, enc_scale);
+                p.scale = scale;
+                Ct part = ev.view(x, b0, nb);
+                ev.add_plain_inplace(part, p);
             }
-            Pt p = ev.encode_batch(vals.data(), x.batch, (int)slots, x.limbs, x.scale);
-            x.scale = scale;
-            p.scale = scale;
-            return ev.add_plain(x, p);
+            return x;
         }
     } // namespace
 
@@ -512,12 +528,23 @@ namespace moai
     {
         const double scale = X.scale;
         const int col_W = (int)bQ.size();
-        Ct Q = add_masked_bias(ev, ct_pt_matrix_mul_wo_pre(ev, X, WQ, col_W), bQ, bias_vec, scale);
-        Ct K = add_masked_bias(ev, ct_pt_matrix_mul_wo_pre(ev, X, WK, col_W), bK, bias_vec, scale);
-        Ct Xv = X.limbs > 4 ? ev.mod_switch_to(X, 4) : X; // chain_index <= 3
-        Ct V = add_masked_bias(ev, ct_pt_matrix_mul_wo_pre(ev, Xv, WV, col_W), bV, bias_vec, scale);
-        Ct QK = ct_ct_matrix_mul_colpacking(ev, Q, K, keys, col_W, 128, col_W, 128, num_batch);
-        Ct sm = softmax_boot(ev, QK, bias_vec, input_num, keys, iter, boot, layer_id);
+        Ct Q, K, V, QK, sm;
+        {
+            PhaseTimer t(ev.c, "att_qkv_matmul");
+            Q = add_masked_bias(ev, ct_pt_matrix_mul_wo_pre(ev, X, WQ, col_W), bQ, bias_vec, scale);
+            K = add_masked_bias(ev, ct_pt_matrix_mul_wo_pre(ev, X, WK, col_W), bK, bias_vec, scale);
+            Ct Xv = X.limbs > 4 ? ev.mod_switch_to(X, 4) : X; // chain_index <= 3
+            V = add_masked_bias(ev, ct_pt_matrix_mul_wo_pre(ev, Xv, WV, col_W), bV, bias_vec, scale);
+        }
+        {
+            PhaseTimer t(ev.c, "att_qk_colpacking");
+            QK = ct_ct_matrix_mul_colpacking(ev, Q, K, keys, col_W, 128, col_W, 128, num_batch);
+        }
+        {
+            PhaseTimer t(ev.c, "att_softmax_boot");
+            sm = softmax_boot(ev, QK, bias_vec, input_num, keys, iter, boot, layer_id);
+        }
+        PhaseTimer t(ev.c, "att_sv_diagpacking");
         return ct_ct_matrix_mul_diagpacking(ev, sm, V, keys, 128, 128, col_W, 128, num_batch);
     }
 
@@ -546,10 +573,13 @@ namespace moai
         }
 
         // 768 independent bootstrappings (test_full_scheme.hpp:654-660), chunked to bound the workspace
-        Ct bootstrap_all(const Evaluator &ev, const Ct &x, const Keys &keys, Bootstrapper &boot, long long chunk)
+        // `into`: optional caller-provided storage for the result (same shape)
+        Ct bootstrap_all(const Evaluator &ev, const Ct &x, const Keys &keys, Bootstrapper &boot, long long chunk,
+                         const Ct *into = nullptr)
         {
             Ct in = ev.mod_switch_to(x, 1);
-            Ct out = ev.alloc(x.batch, 2, boot.prm.total_limbs - 14, boot.prm.final_scale);
+            Ct out = into ? *into : ev.alloc(x.batch, 2, boot.prm.total_limbs - 14, boot.prm.final_scale);
+            out.scale = boot.prm.final_scale;
             for (long long b0 = 0; b0 < x.batch; b0 += chunk)
             {
                 const long long nb = std::min(chunk, x.batch - b0);
@@ -562,7 +592,7 @@ namespace moai
 
     Ct encoder_layer(const Evaluator &ev, const Ct &x, const LayerWeights &w, const std::vector<int> &bias_vec,
                      int input_num, const Keys &keys, Bootstrapper &boot, int num_batch, int layer_id,
-                     long long boot_chunk)
+                     long long boot_chunk, bool reuse_input)
     {
         const double scale = x.scale;
         const int hidden = w.hidden;
@@ -604,7 +634,8 @@ namespace moai
         Ct boot_layer;
         {
             PhaseTimer t(c, "bootstrap_2");
-            boot_layer = bootstrap_all(ev, ln1, keys, boot, boot_chunk);
+            // x is dead after the first residual: with reuse_input its storage receives this result
+            boot_layer = bootstrap_all(ev, ln1, keys, boot, boot_chunk, reuse_input ? &x : nullptr);
             ln1 = Ct();
         }
         Ct inter;

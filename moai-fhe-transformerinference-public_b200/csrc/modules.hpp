@@ -39,8 +39,9 @@ namespace moai
 
     // One encoder layer of all_layer_test (M/test/test_full_scheme.hpp:484-1087): x = 768 column
     // ciphertexts at chain_index 20; returns the layer output at chain_index 20 (after the 4th
-    // bootstrapping), ready to be the next layer's input.
+    // bootstrapping), ready to be the next layer's input.  reuse_input: x's storage may be overwritten
+    // once the first residual has consumed it (saves one 15.75 GiB buffer at the repo's size).
     Ct encoder_layer(const Evaluator &ev, const Ct &x, const LayerWeights &w, const std::vector<int> &bias_vec,
                      int input_num, const Keys &keys, Bootstrapper &boot, int num_batch, int layer_id,
-                     long long boot_chunk);
+                     long long boot_chunk, bool reuse_input = false);
 } // namespace moai

@@ -59,8 +59,9 @@ namespace moai
         }
 
         // ct[b][p][l][i] (op) pt[b*stride][l][i] on poly 0, copy on the others
-        __global__ void k_addsub_plain(int op, const ulonglong2 *__restrict__ ct, const ulonglong2 *__restrict__ pt,
-                                       ulonglong2 *__restrict__ out, long long total2, int log_n2, int polys, int limbs,
+        __global__ void k_addsub_plain(int op, const ulonglong2 *ct, const ulonglong2 *__restrict__ pt,
+                                       ulonglong2 *out /* may alias ct */, long long total2, int log_n2, int polys,
+                                       int limbs,
                                        long long pt_stride2, const LimbConst *__restrict__ lcs)
         {
             long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

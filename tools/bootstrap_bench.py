@@ -54,11 +54,14 @@ def main():
     boot.bootstrap_3(keys, x, 2.0 ** 46)         # warm-up: encodes the linear-transform plaintexts once
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = bench.ClockSampler(0)
+    sampler.start()
     e0.record()
     for _ in range(args.iters):
         boot.bootstrap_3(keys, x, 2.0 ** 46)
     e1.record()
     torch.cuda.synchronize()
+    clocks = sampler.stop()
     be.profile(True)                             # per-phase breakdown from one more (event-bracketed) call
     boot.bootstrap_3(keys, x, 2.0 ** 46)
     phases = {k: round(v[0] / args.batch, 2) for k, v in be.profile_dump().items() if k.startswith("boot_")}
@@ -67,7 +70,7 @@ def main():
     per_ct = ms / args.batch
     per_layer_s = per_ct * 3084 / 1000.0
     print(json.dumps({"op": "bootstrap_3", "batch": args.batch, "keys": args.keys, "mode": "fast (hoisted)" if args.fast else "exact (SEAL key switch)",
-                      "galois_keys": len(gal),
+                      "galois_keys": len(gal), "clocks": clocks,
                       "ms_per_batch": round(ms, 2), "ms_per_ciphertext": round(per_ct, 2), "phase_ms_per_ciphertext": phases,
                       "projected_bootstrap_s_per_layer": round(per_layer_s, 1),
                       "projected_bootstrap_s_per_input_12_layers": round(per_layer_s * 12 / 256, 2),

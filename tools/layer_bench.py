@@ -6,6 +6,7 @@ Inputs, weights and evaluation keys are synthetic (uniform residues / Gaussian w
 timing does not depend on the values; correctness of the same pipeline is covered at N = 4096 by
 tests/test_gpu_layer.py.  Prints the per-stage device time (the rows of P:Table 3) and the
 amortized seconds per input extrapolated to 12 identical layers."""
+import argparse
 import importlib
 import json
 import os
@@ -19,13 +20,18 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 REFERENCE_TABLE3 = {  # P:Table 3, seconds per input summed over 12 layers
-    "attention": 37.4 + 40.3 + 53.3 + 1.4, "selfoutput_matmul": 1.7, "bootstrap_1": 95.4, "layernorm_1": 0.6,
+    "attention": 37.4 + 40.3 + 53.3 + 1.4, "att_qkv_matmul": 37.4, "att_qk_colpacking": 40.3, "att_softmax_boot": 53.3,
+    "att_sv_diagpacking": 1.4, "selfoutput_matmul": 1.7, "bootstrap_1": 95.4, "layernorm_1": 0.6,
     "bootstrap_2": 95.8, "intermediate_matmul": 44.1, "gelu": 3.3, "final_matmul": 7.1, "bootstrap_3": 98.8,
     "layernorm_2": 0.6, "bootstrap_4": 94.8}
 
 
 def main():
     import torch
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", default="fast", choices=["fast", "exact"],
+                    help="fast: hoisted rotations, pre-permuted level-truncated keys; exact: SEAL-identical key switches")
+    args = ap.parse_args()
     pkg = importlib.import_module("moai-fhe-transformerinference-public_b200")
     primes = bench.moai_primes()
     be = pkg.Backend(16, primes)
@@ -34,19 +40,35 @@ def main():
     g = torch.Generator(device="cuda")
     g.manual_seed(11)
 
-    def rand_key():
-        k = torch.empty((kl - 1, 2, kl, n), dtype=torch.int64, device="cuda")
-        for l in range(kl):
-            k[:, :, l, :] = torch.randint(0, primes[l], (kl - 1, 2, n), generator=g, device="cuda", dtype=torch.int64)
+    def rand_key(levels=kl - 1):
+        """uniform residues in a key's layout: SEAL's [kl-1, 2, kl, n], or truncated [L, 2, L + 1, n]"""
+        ids = list(range(levels)) + [kl - 1]
+        k = torch.empty((levels, 2, levels + 1, n), dtype=torch.int64, device="cuda")
+        for pos, l in enumerate(ids):
+            k[:, :, pos, :] = torch.randint(0, primes[l], (levels, 2, n), generator=g, device="cuda", dtype=torch.int64)
         return k
 
-    steps = set(boot.required_steps())
-    # of the driver's default power-of-two Galois keys only the multiples of num_batch = 256 are ever
-    # used (QK^T rotates by i*256, softmax*V by multiples of 256): 2^8 .. 2^14 and their negatives
-    for k in range(8, 15):
-        steps |= {1 << k, (n // 2) - (1 << k)}
-    gal = {be.galois_elt_from_step(st): rand_key() for st in sorted(steps) + [0]}
-    keys = be.make_keys(relin=rand_key(), galois=gal)
+    if args.mode == "exact":
+        steps = set(boot.required_steps())
+        # of the driver's default power-of-two Galois keys only the multiples of num_batch = 256 are ever
+        # used (QK^T rotates by i*256, softmax*V by multiples of 256): 2^8 .. 2^14 and their negatives
+        for k in range(8, 15):
+            steps |= {1 << k, (n // 2) - (1 << k)}
+        gal = {be.galois_elt_from_step(st): rand_key() for st in sorted(steps) + [0]}
+        keys = be.make_keys(relin=rand_key(), galois=gal)
+        n_keys = len(gal)
+    else:
+        boot.set_hoisting(True)
+        gal = {}
+        for st in boot.required_steps() + [0]:
+            gal.setdefault(be.galois_elt_from_step(st), []).append(rand_key())
+        att = pkg.attention_rotation_steps(256)
+        for tag, level in (("qk", 14), ("sv", 3)):     # keys truncated to the level they are used at
+            for st in att[tag]:
+                gal.setdefault(be.galois_elt_from_step(st), []).append(rand_key(level))
+        keys = be.make_keys(relin=rand_key(), galois_fast=gal)
+        n_keys = sum(len(v) for v in gal.values())
+    key_gib = torch.cuda.memory_allocated() / 2 ** 30
     hidden, heads, hd, inter = 768, 12, 64, 3072
     rng = np.random.default_rng(20250991)
     w = {"hidden": hidden, "heads": heads, "head_dim": hd, "inter": inter,
@@ -64,17 +86,26 @@ def main():
     mask = np.ones(n // 2, dtype=np.int32)     # all 128 tokens of all 256 inputs valid
     boot_chunk = int(os.environ.get("MOAI_BOOT_CHUNK", "32"))
     be.profile(True)
+    sampler = bench.ClockSampler(0)
+    sampler.start()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    out, out_scale = boot.encoder_layer(keys, x, 2.0 ** 46, w, mask, 128, 256, layer_id=0, boot_chunk=boot_chunk)
+    try:
+        out, out_scale = boot.encoder_layer(keys, x, 2.0 ** 46, w, mask, 128, 256, layer_id=0, boot_chunk=boot_chunk,
+                                            inplace=True)
+    except Exception as exc:      # report how far the layer got
+        print(json.dumps({"error": str(exc), "stages_done_ms": {k: round(v[0], 1) for k, v in be.profile_dump().items()},
+                          "evaluation_keys_GiB": round(key_gib, 1)}))
+        raise
     e1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     ms = e0.elapsed_time(e1)
     stages = be.profile_dump()
     be.profile(False)
+    clocks = sampler.stop()
     rows = {}
     for k, (v, cnt) in stages.items():
         if k == "ctpt_gemm":
@@ -83,9 +114,10 @@ def main():
                    "reference_s_per_input_12_layers": REFERENCE_TABLE3.get(k)}
     total = ms / 1000.0
     print(json.dumps({"workload": "C4: one BERT-base encoder layer, 256 inputs x 128 tokens, N=65536, 1 x B200",
+                      "mode": args.mode, "evaluation_keys_GiB": round(key_gib, 1),
                       "layer_seconds": round(total, 2), "host_wall_seconds": round(wall, 2),
                       "amortized_s_per_input_12_layers": round(total * 12 / 256, 3),
-                      "reference_s_per_input_12_layers": 574.6, "galois_keys": len(gal),
+                      "reference_s_per_input_12_layers": 574.6, "galois_keys": n_keys, "clocks": clocks,
                       "gpu_mem_GiB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
                       "launches": be.launch_count(), "stages": rows}))
     assert out.shape == (hidden, 2, 21, n) and out_scale == 2.0 ** 46
