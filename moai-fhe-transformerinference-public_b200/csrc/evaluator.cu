@@ -405,7 +405,7 @@ namespace moai
     Ct Evaluator::rotate_fast(const Ct &a, uint32_t elt, const KeyRef &key) const
     {
         Ct r = alloc(a.batch, 2, a.limbs, a.scale);
-        const long long chunk = ks_chunk(c, a.limbs, a.batch, (size_t)2 << 30);
+        const long long chunk = ks_chunk(c, a.limbs, a.batch, ks_ext_budget());
         DevBuf ext((size_t)chunk * ks_ext_bytes_per_ct(c, a.limbs), c->stream);
         const size_t per_ct = (size_t)2 * a.limbs * n();
         for (long long b0 = 0; b0 < a.batch; b0 += chunk)
@@ -443,7 +443,7 @@ namespace moai
             out[i] = steps[i] == 0 ? a : alloc(a.batch, 2, a.limbs, a.scale);
         }
         // the decomposition of a chunk is shared by all rotations; ~4 GiB of extended digits at a time
-        const long long chunk = ks_chunk(c, a.limbs, a.batch, (size_t)4 << 30);
+        const long long chunk = ks_chunk(c, a.limbs, a.batch, ks_ext_budget());
         for (long long b0 = 0; b0 < a.batch; b0 += chunk)
         {
             const long long nb = std::min(chunk, a.batch - b0);

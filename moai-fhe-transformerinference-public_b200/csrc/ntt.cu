@@ -69,8 +69,8 @@ namespace moai
         };
 
         // ---- exact FP64 path for primes p < 2^51.
-        // Residues are integer-valued doubles.  With M = 1.5 * 2^52, rnd(x) = (x + M) - M is
-        // round-to-nearest-integer for |x| < 2^51.
+        // Residues are integer-valued doubles.  With M = 1.5 * 2^52, rnd(y) = (y + M) - M is
+        // round-to-nearest-integer for |y| < 2^51; quot(x) = fma(x, 1/p, M) - M = rnd(x/p).
         //   red(x)      = x - rnd(x/p) p                 : |x| < 2^53  ->  |red| <= p/2 + 1
         //   mul(a, w)   : h = fl(a w), l = fma(a, w, -h) (so a w = h + l exactly),
         //                 r = fma(-rnd(h/p), p, h) + l   : needs |a| < 2^52, |w| <= p/2;
@@ -88,29 +88,32 @@ namespace moai
         {
             typedef double elem;
             typedef double tw_t;
-            double p, pinv, inv_n, inv_n_w;
+            double p, pinv, inv_n, inv_n_w, pshift;
+            u64 pi;
             const double *__restrict__ tab;
 
             __device__ FpField(const NttArgs &a, int limb, const LimbConst &lc)
                 : p(lc.pd), pinv(lc.pinv), inv_n(lc.inv_n_d), inv_n_w(lc.inv_n_w_d),
-                  tab(a.tw_fp + ((size_t)limb << a.log_n))
+                  pshift(lc.pd + 4503599627370496.0), pi(lc.q), tab(a.tw_fp + ((size_t)limb << a.log_n))
             {}
             __device__ __forceinline__ tw_t tw(size_t idx) const { return __ldg(tab + idx); }
             __device__ __forceinline__ elem pro_reduce(elem x) const { return red(x); }
-            static __device__ __forceinline__ double rnd(double x)
+            // nearest integer to x * pinv: the product is folded into the magic-constant addition (one
+            // FMA, one rounding fewer than mul + add), valid for |x * pinv| < 2^51
+            __device__ __forceinline__ double quot(double x) const
             {
                 const double M = 6755399441055744.0;
-                return __dadd_rn(__dadd_rn(x, M), -M);
+                return __dadd_rn(__fma_rn(x, pinv, M), -M);
             }
             __device__ __forceinline__ double red(double x) const
             {
-                return __fma_rn(-rnd(__dmul_rn(x, pinv)), p, x);
+                return __fma_rn(-quot(x), p, x);
             }
             __device__ __forceinline__ double mul(double a, double w) const
             {
                 const double h = __dmul_rn(a, w);
                 const double l = __fma_rn(a, w, -h);
-                const double r = __dadd_rn(__fma_rn(-rnd(__dmul_rn(h, pinv)), p, h), l);
+                const double r = __dadd_rn(__fma_rn(-quot(h), p, h), l);
                 return WIDE ? red(r) : r;
             }
             // canonical / lazy uint64 below 2^52 -> double, exactly (bit trick, no I2F)
@@ -120,12 +123,14 @@ namespace moai
             }
             __device__ __forceinline__ elem in_mid(u64 v) const { return __longlong_as_double((long long)v); }
             __device__ __forceinline__ u64 out_mid(elem x) const { return (u64)__double_as_longlong(x); }
+            // |red(x)| <= p/2 + 1: shift into the positive range in FP64 (one exact add), then finish
+            // with integer compares on the otherwise idle ALU pipe.  2^52 + p + r is an integer in
+            // [2^52, 2^53), so its mantissa field is p + r exactly.
             __device__ __forceinline__ u64 canon(elem x) const
             {
-                double r = red(x);
-                r = r < 0.0 ? __dadd_rn(r, p) : r;
-                r = r >= p ? __dadd_rn(r, -p) : r;
-                return (u64)__double_as_longlong(__dadd_rn(r, 4503599627370496.0)) & 0x000FFFFFFFFFFFFFull;
+                const double r = __dadd_rn(red(x), pshift);
+                const u64 v = (u64)__double_as_longlong(r) & 0x000FFFFFFFFFFFFFull; // p + red(x) in (p/2 - 2, 3p/2 + 2)
+                return v >= pi ? v - pi : v;
             }
             __device__ __forceinline__ u64 out_fwd(elem x) const { return canon(x); }
             __device__ __forceinline__ u64 out_inv(elem x) const { return canon(x); }

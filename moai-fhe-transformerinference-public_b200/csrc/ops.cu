@@ -12,6 +12,7 @@
 // lookup per thread (limb index is uniform per 2-element vector because n is even).
 #include "ntt.cuh"
 #include "ops.cuh"
+#include <cstdlib>
 
 namespace moai
 {
@@ -812,6 +813,17 @@ namespace moai
         divide_round_last(c, acc.as<u64>(), batch * 2, rns, c->kl - 1, addend, out, addend_c0_only);
     }
 
+    // workspace budget for the extended digits of one key-switch chunk (MOAI_KS_EXT_GIB, default 4)
+    size_t ks_ext_budget()
+    {
+        static const size_t budget = [] {
+            const char *e = getenv("MOAI_KS_EXT_GIB");
+            const double gib = e ? atof(e) : 4.0;
+            return (size_t)((gib > 0.25 ? gib : 0.25) * 1073741824.0);
+        }();
+        return budget;
+    }
+
     long long ks_chunk(Context *c, int limbs, long long batch, size_t budget_bytes)
     {
         long long chunk = (long long)(budget_bytes / ks_ext_bytes_per_ct(c, limbs));
@@ -826,8 +838,8 @@ namespace moai
         {
             key_kl = c->kl;
         }
-        // bound the extended-digit workspace (batch chunking); ~2 GiB
-        const long long chunk = ks_chunk(c, limbs, batch, (size_t)2 << 30);
+        // bound the extended-digit workspace (batch chunking); the evk is streamed once per chunk
+        const long long chunk = ks_chunk(c, limbs, batch, ks_ext_budget());
         Scratch ext((size_t)chunk * ks_ext_bytes_per_ct(c, limbs), c->stream);
         for (long long b0 = 0; b0 < batch; b0 += chunk)
         {

@@ -52,6 +52,7 @@ namespace moai
                       int key_kl = 0);
     // the two halves of a key switch, exposed for hoisting (one decomposition, many rotations)
     size_t ks_ext_bytes_per_ct(Context *c, int limbs);
+    size_t ks_ext_budget();
     long long ks_chunk(Context *c, int limbs, long long batch, size_t budget_bytes);
     void ks_decompose(Context *c, const u64 *target, long long batch, int limbs, u64 *ext, long long target_stride = 0);
     void ks_mac_moddown(Context *c, const u64 *ext, long long batch, int limbs, const u64 *ksk, int key_kl,
