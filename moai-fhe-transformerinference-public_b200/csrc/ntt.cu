@@ -559,7 +559,8 @@ namespace moai
             const int row = (blockIdx.x % ctas_per_poly) * ROWS + r;
             const int limb = a.limb_ids[(poly / a.div) % a.period];
             const LimbConst lc = a.limb[limb];
-            u64 *base = a.data + ((size_t)poly << a.log_n) + (size_t)row * 256;
+            const long long phys = a.grp_size ? (poly / a.grp_size) * a.grp_stride + poly % a.grp_size : poly;
+            u64 *base = a.data + ((size_t)phys << a.log_n) + (size_t)row * 256;
             const size_t ra = (size_t)R + row;
             MOAI_DISPATCH_FIELD(lc, (fwd_pass_b_body(f, base, sm + r * ROW_PAD, t, ra)))
         }
@@ -593,13 +594,264 @@ namespace moai
             MOAI_DISPATCH_FIELD(lc, (inv_pass_a_body<LOGR>(f, base, sm, t, tb, n)))
         }
 
-        template <int LOGR>
-        void launch_fwd(const NttArgs &a, cudaStream_t s)
+
+        // =====================================================================================
+        // Fused key-switch kernel: pass B of the digit-extension NTT + inner product with the evk.
+        //
+        // One CTA owns FR rows (FR x 256 output coefficients) of ONE target modulus I of ONE
+        // ciphertext and loops over the digits J: it finishes NTT_I(d_J) for its rows in registers
+        // (the 8 in-row stages, twiddles loaded once for all J) and multiplies the result straight
+        // into the two accumulators  acc_k += NTT_I(d_J) (.) key[J][k][I]  (S/evaluator.cpp:2859-2883),
+        // so the extended digits never reach HBM in NTT form and the separate MAC pass disappears.
+        // Arithmetic: the exact FP64 products of the NTT (FpField::mul); the accumulators are integer-
+        // valued doubles reduced often enough to stay below 2^53; the final canonical residues are
+        // the same numbers the 128-bit integer inner product yields.  Data tiles and key tiles of
+        // the next digit are prefetched with cp.async into per-thread shared-memory slots.
+        // =====================================================================================
+        constexpr int FR = 8;          // rows per CTA
+        constexpr int FT = FR * 16;    // threads per CTA
+        // shared memory: row tiles (landing zone of the next digit + transpose), per-thread twiddle
+        // slots of the last four stages, row-uniform twiddles of the first four, key staging
+        constexpr int KS_SM_ROWS = FR * ROW_PAD * 8, KS_SM_TW2 = FT * 8 * 16, KS_SM_TW1 = FR * 16 * 8,
+                      KS_SM_KEYS = FT * 16 * 16;
+        constexpr int KS_FUSED_SMEM = KS_SM_ROWS + KS_SM_TW2 + KS_SM_TW1 + KS_SM_KEYS; // 67584 B: 3 CTAs / SM
+
+        __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
         {
-            const long long ctas_a = a.count * (256 / TB);
-            ntt_fwd_pass_a<LOGR><<<(unsigned)ctas_a, (1 << LOGR) / 16 * TB, 0, s>>>(a);
-            const long long ctas_b = a.count * ((1 << LOGR) / ROWS);
-            ntt_fwd_pass_b<<<(unsigned)ctas_b, ROWS * 16, 0, s>>>(a);
+            const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+        }
+        __device__ __forceinline__ void cp_async_commit()
+        {
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        __device__ __forceinline__ void cp_async_wait_1()
+        {
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        }
+
+        struct KsFusedArgs
+        {
+            const u64 *mid;         // [batch][rns][limbs][n]: pass-A output of the extended digits
+            const u64 *ksk;         // [limbs..][2][key_kl][n]
+            u64 *acc;               // [batch][2][rns][n] canonical
+            const double *tw_fp;    // [kl][n]
+            const LimbConst *limb;  // [kl]
+            const int *ids_ks;      // [rns]: prime index of target modulus I
+            int limbs, rns, key_kl, log_n;
+        };
+
+        template <bool WIDE>
+        __device__ __forceinline__ void ks_fused_body(const FpField<WIDE> &f, const KsFusedArgs &a, int I, long long b,
+                                                      int rb, unsigned char *smem)
+        {
+            const int tid = threadIdx.x, t = tid & 15, r = tid >> 4;
+            const int R = 1 << (a.log_n - 8);
+            const int row = rb * FR + r;
+            const size_t ra = (size_t)R + row;
+            double *srow = reinterpret_cast<double *>(smem) + r * ROW_PAD;
+            double2 *tws = reinterpret_cast<double2 *>(smem + KS_SM_ROWS) + tid; // unit u at tws[u * FT]
+            double2 *tw1 = reinterpret_cast<double2 *>(smem + KS_SM_ROWS + KS_SM_TW2) + r * 8;
+            ulonglong2 *kst = reinterpret_cast<ulonglong2 *>(smem + KS_SM_ROWS + KS_SM_TW2 + KS_SM_TW1) + tid;
+
+            const int key_limb = I == a.limbs ? a.key_kl - 1 : I;
+            const u64 *mid0 = a.mid + (((size_t)b * a.rns + I) * a.limbs << a.log_n) + (size_t)row * 256;
+            const u64 *key0 = a.ksk + ((size_t)key_limb << a.log_n) + (size_t)row * 256 + 16 * t;
+            const size_t key_poly = (size_t)a.key_kl << a.log_n; // stride between key[J][0] and key[J][1]
+
+            // the row's 256 residues of digit J, natural order, 16 bytes per copy (coalesced)
+            auto issue_data = [&](int J) {
+                const u64 *src = mid0 + ((size_t)J << a.log_n);
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                {
+                    cp_async16(srow + 2 * (t + 16 * j), src + 2 * (t + 16 * j));
+                }
+            };
+            auto issue_keys = [&](int J) {
+                const u64 *src = key0 + (size_t)J * 2 * key_poly;
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                {
+                    cp_async16(kst + u * FT, src + 2 * u);
+                    cp_async16(kst + (8 + u) * FT, src + key_poly + 2 * u);
+                }
+            };
+            issue_data(0);
+            cp_async_commit();
+            issue_keys(0);
+            cp_async_commit();
+
+            // twiddles, loaded once for all digits: the 15 row-uniform ones of the first four stages
+            // (tw1: [0] = 2^0 block, [1..2], [3..6], [7..14]) and this thread's 15 of the last four
+            if (t < 15)
+            {
+                const int lvl = t == 0 ? 0 : (t < 3 ? 1 : (t < 7 ? 2 : 3));
+                const size_t idx = (ra << lvl) + (t - ((1 << lvl) - 1));
+                reinterpret_cast<double *>(tw1)[t] = f.tw(idx);
+            }
+            {
+                const double *g1 = f.tab + 128 * ra + 8 * t, *g2 = f.tab + 64 * ra + 4 * t, *g4 = f.tab + 32 * ra + 2 * t;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                {
+                    tws[u * FT] = make_double2(__ldg(g1 + 2 * u), __ldg(g1 + 2 * u + 1));
+                }
+                tws[4 * FT] = make_double2(__ldg(g2), __ldg(g2 + 1));
+                tws[5 * FT] = make_double2(__ldg(g2 + 2), __ldg(g2 + 3));
+                tws[6 * FT] = make_double2(__ldg(g4), __ldg(g4 + 1));
+                tws[7 * FT] = make_double2(__ldg(f.tab + 16 * ra + t), 0.0);
+            }
+
+            double acc0[16], acc1[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+            {
+                acc0[k] = 0.0;
+                acc1[k] = 0.0;
+            }
+            // canonical key residue (< 2^52) -> double.  The key is NOT centred: for a multiplier input
+            // |x| <= 6.2 p (narrow) / p/2 + 1 (wide) the product stays below 2^99 / 2^101, its low part
+            // below p/8, so FpField::mul's result bound grows only from 0.52 p to 0.65 p (narrow).
+            auto key_d = [&](u64 v) { return f.in_outer(v); };
+            const int red_every = WIDE ? 4 : 8; // |acc| <= 0.5 p + 8 * 0.65 p  /  0.5 p + 4 * (0.5 p + 1)
+
+            for (int J = 0; J < a.limbs; J++)
+            {
+                double x[16];
+                cp_async_wait_1(); // data(J) has landed (keys(J) may still be in flight)
+                __syncwarp();      // a row is half a warp: its 16 threads' copies are now visible to each other
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                {
+                    x[k] = srow[t + 16 * k];
+                }
+                f.phase_begin_fwd(x);
+                {
+                    const double2 w0 = tw1[0], w1 = tw1[1], w2 = tw1[2], w3 = tw1[3], w4 = tw1[4], w5 = tw1[5],
+                                  w6 = tw1[6], w7 = tw1[7];
+                    const double t8[1] = { w0.x };
+                    const double t4[2] = { w0.y, w1.x };
+                    const double t2[4] = { w1.y, w2.x, w2.y, w3.x };
+                    const double t1[8] = { w3.y, w4.x, w4.y, w5.x, w5.y, w6.x, w6.y, w7.x };
+                    ct_stage_tw<8>(f, x, t8);
+                    ct_stage_tw<4>(f, x, t4);
+                    ct_stage_tw<2>(f, x, t2);
+                    ct_stage_tw<1>(f, x, t1);
+                }
+                __syncwarp(); // every thread of the row has read its inputs: the tile can be overwritten
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                {
+                    srow[t + 17 * k] = x[k];
+                }
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                {
+                    x[k] = srow[17 * t + k];
+                }
+                __syncwarp();
+                if (J + 1 < a.limbs)
+                {
+                    issue_data(J + 1); // lands in the row tile while the last stages and the MAC run
+                }
+                cp_async_commit();
+                f.phase_begin_fwd(x);
+                {
+                    const double2 a0 = tws[0 * FT], a1 = tws[1 * FT], a2 = tws[2 * FT], a3 = tws[3 * FT];
+                    const double2 b0 = tws[4 * FT], b1 = tws[5 * FT], c0 = tws[6 * FT], d0 = tws[7 * FT];
+                    const double t8[1] = { d0.x };
+                    const double t4[2] = { c0.x, c0.y };
+                    const double t2[4] = { b0.x, b0.y, b1.x, b1.y };
+                    const double t1[8] = { a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y };
+                    ct_stage_tw<8>(f, x, t8);
+                    ct_stage_tw<4>(f, x, t4);
+                    ct_stage_tw<2>(f, x, t2);
+                    ct_stage_tw<1>(f, x, t1);
+                }
+                if (WIDE)
+                {
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                    {
+                        x[k] = f.red(x[k]); // multiplier input below 2^52
+                    }
+                }
+                cp_async_wait_1(); // keys(J) have landed
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                {
+                    const ulonglong2 k0 = kst[u * FT], k1 = kst[(8 + u) * FT];
+                    acc0[2 * u] = __dadd_rn(acc0[2 * u], f.mul(x[2 * u], key_d(k0.x)));
+                    acc0[2 * u + 1] = __dadd_rn(acc0[2 * u + 1], f.mul(x[2 * u + 1], key_d(k0.y)));
+                    acc1[2 * u] = __dadd_rn(acc1[2 * u], f.mul(x[2 * u], key_d(k1.x)));
+                    acc1[2 * u + 1] = __dadd_rn(acc1[2 * u + 1], f.mul(x[2 * u + 1], key_d(k1.y)));
+                }
+                if (J + 1 < a.limbs)
+                {
+                    issue_keys(J + 1);
+                }
+                cp_async_commit();
+                if ((J + 1) % red_every == 0)
+                {
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                    {
+                        acc0[k] = f.red(acc0[k]);
+                        acc1[k] = f.red(acc1[k]);
+                    }
+                }
+            }
+            u64 *o0 = a.acc + ((((size_t)b * 2 + 0) * a.rns + I) << a.log_n) + (size_t)row * 256 + 16 * t;
+            u64 *o1 = a.acc + ((((size_t)b * 2 + 1) * a.rns + I) << a.log_n) + (size_t)row * 256 + 16 * t;
+#pragma unroll
+            for (int k = 0; k < 16; k += 2)
+            {
+                ulonglong2 v;
+                v.x = f.canon(acc0[k]);
+                v.y = f.canon(acc0[k + 1]);
+                reinterpret_cast<ulonglong2 *>(o0)[k >> 1] = v;
+                v.x = f.canon(acc1[k]);
+                v.y = f.canon(acc1[k + 1]);
+                reinterpret_cast<ulonglong2 *>(o1)[k >> 1] = v;
+            }
+        }
+
+        __global__ void __launch_bounds__(FT, 3) ks_passb_mac_kernel(KsFusedArgs a, NttArgs na)
+        {
+            extern __shared__ __align__(16) unsigned char ks_smem[];
+            const long long b = blockIdx.x;
+            const int rb = blockIdx.y;
+            const int I = blockIdx.z;
+            const int limb = a.ids_ks[I];
+            const LimbConst lc = a.limb[limb];
+            if (lc.fp_class == 1)
+            {
+                const FpField<false> f(na, limb, lc);
+                ks_fused_body<false>(f, a, I, b, rb, ks_smem);
+            }
+            else if (lc.fp_class == 2)
+            {
+                const FpField<true> f(na, limb, lc);
+                ks_fused_body<true>(f, a, I, b, rb, ks_smem);
+            }
+            // integer-path moduli (the 58-bit special prime) are handled by the un-fused kernels
+        }
+
+        template <int LOGR>
+        void launch_fwd(const NttArgs &a, cudaStream_t s, bool do_a = true, bool do_b = true)
+        {
+            if (do_a)
+            {
+                const long long ctas_a = a.count * (256 / TB);
+                ntt_fwd_pass_a<LOGR><<<(unsigned)ctas_a, (1 << LOGR) / 16 * TB, 0, s>>>(a);
+            }
+            if (do_b)
+            {
+                const long long ctas_b = a.count * ((1 << LOGR) / ROWS);
+                ntt_fwd_pass_b<<<(unsigned)ctas_b, ROWS * 16, 0, s>>>(a);
+            }
         }
 
         template <int LOGR>
@@ -613,12 +865,13 @@ namespace moai
     } // namespace
 
     void ntt_forward(Context *c, u64 *data, long long count, const int *d_limb_ids, int period, int div,
-                     const NttPrologue *pro)
+                     const NttPrologue *pro, int passes)
     {
         if (count <= 0)
         {
             return;
         }
+        const bool do_a = (passes & 1) != 0, do_b = (passes & 2) != 0;
         NttArgs a{ data, c->d_fwd, c->d_fwd_fp, c->d_limb, d_limb_ids, period, div, c->log_n, count };
         if (pro)
         {
@@ -630,14 +883,56 @@ namespace moai
         }
         switch (c->log_n)
         {
-        case 12: launch_fwd<4>(a, c->stream); break;
-        case 13: launch_fwd<5>(a, c->stream); break;
-        case 14: launch_fwd<6>(a, c->stream); break;
-        case 15: launch_fwd<7>(a, c->stream); break;
-        case 16: launch_fwd<8>(a, c->stream); break;
+        case 12: launch_fwd<4>(a, c->stream, do_a, do_b); break;
+        case 13: launch_fwd<5>(a, c->stream, do_a, do_b); break;
+        case 14: launch_fwd<6>(a, c->stream, do_a, do_b); break;
+        case 15: launch_fwd<7>(a, c->stream, do_a, do_b); break;
+        case 16: launch_fwd<8>(a, c->stream, do_a, do_b); break;
         default: throw StatusError{ INVALID_ARGUMENT, "unsupported log_n" };
         }
-        c->launches += 2;
+        c->launches += (do_a ? 1 : 0) + (do_b ? 1 : 0);
+        MOAI_CUDA_CHECK(cudaGetLastError());
+    }
+
+    void ntt_forward_pass_b_strided(Context *c, u64 *data, long long groups, long long grp_size, long long grp_stride,
+                                    const int *d_limb_id)
+    {
+        if (groups <= 0 || grp_size <= 0)
+        {
+            return;
+        }
+        NttArgs a{ data, c->d_fwd, c->d_fwd_fp, c->d_limb, d_limb_id, 1, 1, c->log_n, groups * grp_size };
+        a.grp_size = grp_size;
+        a.grp_stride = grp_stride;
+        const long long ctas_b = a.count * ((1 << (c->log_n - 8)) / ROWS);
+        ntt_fwd_pass_b<<<(unsigned)ctas_b, ROWS * 16, 0, c->stream>>>(a);
+        c->launches += 1;
+        MOAI_CUDA_CHECK(cudaGetLastError());
+    }
+
+    void ks_passb_mac(Context *c, const u64 *mid, long long batch, int limbs, const u64 *ksk, int key_kl, u64 *acc)
+    {
+        MOAI_REQUIRE(c->log_n >= 12, "unsupported log_n");
+        static const cudaError_t attr = cudaFuncSetAttribute(
+            ks_passb_mac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KS_FUSED_SMEM);
+        (void)attr;
+        const int rns = limbs + 1;
+        KsFusedArgs a;
+        a.mid = mid;
+        a.ksk = ksk;
+        a.acc = acc;
+        a.tw_fp = c->d_fwd_fp;
+        a.limb = c->d_limb;
+        a.ids_ks = c->d_ids_ks + (size_t)limbs * (c->kl + 1);
+        a.limbs = limbs;
+        a.rns = rns;
+        a.key_kl = key_kl;
+        a.log_n = c->log_n;
+        NttArgs na{ nullptr, c->d_fwd, c->d_fwd_fp, c->d_limb, nullptr, 1, 1, c->log_n, 0 };
+        const int R = 1 << (c->log_n - 8);
+        dim3 grid((unsigned)batch, (unsigned)(R / FR), (unsigned)rns);
+        ks_passb_mac_kernel<<<grid, FT, KS_FUSED_SMEM, c->stream>>>(a, na);
+        c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
     }
 

@@ -48,6 +48,9 @@ namespace moai
         //   src_mode 2 (divide-and-round expansion, S/util/rns.cpp:851-880 / S/evaluator.cpp:2966-2990):
         //              polynomial p reads t = src[p / period] (coefficients modulo prime `last_id`) and
         //              forms ((t + half) mod q_last) mod q_i + (q_i - half mod q_i).
+        // pass B only: logical polynomial p lives at data + ((p / grp_size) * grp_stride + p % grp_size) * n
+        // (grp_size = 0: contiguous)
+        long long grp_size = 0, grp_stride = 0;
         const u64 *src = nullptr;
         int src_mode = 0;
         int last_id = 0;
@@ -64,7 +67,17 @@ namespace moai
 
     // Transforms `count` consecutive polynomials in place; polynomial p lives at data + p*n and
     // uses the prime with index d_limb_ids[(p / div) % period].
+    // passes: bit 0 = pass A (row-pairing stages, + prologue), bit 1 = pass B (in-row stages)
     void ntt_forward(Context *c, u64 *data, long long count, const int *d_limb_ids, int period, int div = 1,
-                     const NttPrologue *pro = nullptr);
+                     const NttPrologue *pro = nullptr, int passes = 3);
+    // pass B of `groups` runs of `grp_size` consecutive polynomials, run g starting at
+    // data + g * grp_stride * n, all modulo the single prime *d_limb_id
+    void ntt_forward_pass_b_strided(Context *c, u64 *data, long long groups, long long grp_size, long long grp_stride,
+                                    const int *d_limb_id);
+    // Fused key-switch kernel (csrc/ntt.cu): pass B of the digit-extension NTT + inner product with
+    // the evk for every FP64-path modulus.  mid = pass-A output [batch][limbs+1][limbs][n];
+    // acc[batch][2][limbs+1][n] receives canonical residues for those moduli (integer-path moduli
+    // are left untouched for the un-fused kernels).
+    void ks_passb_mac(Context *c, const u64 *mid, long long batch, int limbs, const u64 *ksk, int key_kl, u64 *acc);
     void ntt_inverse(Context *c, u64 *data, long long count, const int *d_limb_ids, int period, int div = 1);
 } // namespace moai

@@ -507,12 +507,12 @@ namespace moai
         __global__ void k_ks_mac(const ulonglong2 *__restrict__ ext, const ulonglong2 *__restrict__ ksk,
                                  ulonglong2 *__restrict__ acc, long long batch, int log_n2, int limbs, int key_kl,
                                  const int *__restrict__ ids_ks, const LimbConst *__restrict__ lcs,
-                                 const Twiddle *__restrict__ two64)
+                                 const Twiddle *__restrict__ two64, int I0)
         {
             // grid: x = batch item (fastest, so that CTAs sharing a key tile run together and the evk
             // is streamed from HBM once per chunk), y = I, z = coefficient block
             const long long within = (long long)blockIdx.z * blockDim.x + threadIdx.x;
-            const int I = blockIdx.y;
+            const int I = blockIdx.y + I0; // I0: first target modulus of this launch
             const long long b = blockIdx.x;
             const int prime = ids_ks[I];
             // position of modulus I inside the key: data limbs first, the special prime last
@@ -807,10 +807,72 @@ namespace moai
         dim3 grid((unsigned)batch, (unsigned)rns, (unsigned)((n / 2) / EW_THREADS));
         k_ks_mac<<<grid, EW_THREADS, 0, c->stream>>>(reinterpret_cast<const ulonglong2 *>(ext),
                                                      reinterpret_cast<const ulonglong2 *>(ksk), acc.as<ulonglong2>(),
-                                                     batch, c->log_n - 1, limbs, key_kl, ids_ks, c->d_limb, c->d_two64);
+                                                     batch, c->log_n - 1, limbs, key_kl, ids_ks, c->d_limb, c->d_two64, 0);
         c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
         divide_round_last(c, acc.as<u64>(), batch * 2, rns, c->kl - 1, addend, out, addend_c0_only);
+    }
+
+    // One complete key switch of a chunk with the fused kernel: INTT, pass A of the extended digits
+    // (digit extension fused into its loads), then pass B + inner product in one kernel for the
+    // FP64-path moduli; integer-path moduli (the 58-bit special prime) finish with the plain pass B
+    // and the integer inner-product kernel.  Same residues as ks_decompose + ks_mac_moddown.
+    static void ks_fused(Context *c, const u64 *target, long long batch, int limbs, u64 *ext, const u64 *ksk,
+                         int key_kl, const u64 *addend, u64 *out)
+    {
+        const size_t n = c->n;
+        const int rns = limbs + 1;
+        const int *ids_ks = c->d_ids_ks + (size_t)limbs * (c->kl + 1);
+        Scratch d((size_t)batch * limbs * n * sizeof(u64), c->stream);
+        MOAI_CUDA_CHECK(cudaMemcpyAsync(d.p, target, (size_t)batch * limbs * n * sizeof(u64), cudaMemcpyDeviceToDevice,
+                                        c->stream));
+        ntt_inverse(c, d.as<u64>(), batch * limbs, c->d_ids, limbs);
+        NttPrologue pro;
+        pro.src = d.as<u64>();
+        pro.mode = 1;
+        ntt_forward(c, ext, batch * rns * limbs, ids_ks, rns, limbs, &pro, /*passes=*/1);
+        Scratch acc((size_t)batch * 2 * rns * n * sizeof(u64), c->stream);
+        ks_passb_mac(c, ext, batch, limbs, ksk, key_kl, acc.as<u64>());
+        for (int I = 0; I < rns; I++)
+        {
+            const int prime = I == limbs ? c->kl - 1 : I;
+            if (c->h_limb[prime].fp_class != 0)
+            {
+                continue;
+            }
+            ntt_forward_pass_b_strided(c, ext + (size_t)I * limbs * n, batch, limbs, (long long)rns * limbs,
+                                       c->d_ids + prime);
+            dim3 grid((unsigned)batch, 1u, (unsigned)((n / 2) / EW_THREADS));
+            k_ks_mac<<<grid, EW_THREADS, 0, c->stream>>>(reinterpret_cast<const ulonglong2 *>(ext),
+                                                         reinterpret_cast<const ulonglong2 *>(ksk),
+                                                         acc.as<ulonglong2>(), batch, c->log_n - 1, limbs, key_kl,
+                                                         ids_ks, c->d_limb, c->d_two64, I);
+            c->launches += 1;
+            MOAI_CUDA_CHECK(cudaGetLastError());
+        }
+        divide_round_last(c, acc.as<u64>(), batch * 2, rns, c->kl - 1, addend, out, false);
+    }
+
+    static bool ks_can_fuse(Context *c, int limbs)
+    {
+        static const bool enabled = [] {
+            const char *e = getenv("MOAI_KS_FUSED");
+            return !e || atoi(e) != 0;
+        }();
+        if (!enabled)
+        {
+            return false;
+        }
+        bool any_fp = false;
+        for (int l = 0; l < limbs; l++)
+        {
+            if ((c->q[l] >> 52) != 0)
+            {
+                return false; // digits must enter the FP64 prologue below 2^52
+            }
+            any_fp = any_fp || c->h_limb[l].fp_class != 0;
+        }
+        return any_fp;
     }
 
     // workspace budget for the extended digits of one key-switch chunk (MOAI_KS_EXT_GIB, default 4)
@@ -840,13 +902,21 @@ namespace moai
         }
         // bound the extended-digit workspace (batch chunking); the evk is streamed once per chunk
         const long long chunk = ks_chunk(c, limbs, batch, ks_ext_budget());
+        const bool fused = ks_can_fuse(c, limbs);
         Scratch ext((size_t)chunk * ks_ext_bytes_per_ct(c, limbs), c->stream);
         for (long long b0 = 0; b0 < batch; b0 += chunk)
         {
             const long long nb = (batch - b0) < chunk ? (batch - b0) : chunk;
             u64 *ctb = ct + (size_t)b0 * 2 * limbs * n;
-            ks_decompose(c, target + (size_t)b0 * limbs * n, nb, limbs, ext.as<u64>(), 0);
-            ks_mac_moddown(c, ext.as<u64>(), nb, limbs, ksk, key_kl, ctb, false, ctb);
+            if (fused)
+            {
+                ks_fused(c, target + (size_t)b0 * limbs * n, nb, limbs, ext.as<u64>(), ksk, key_kl, ctb, ctb);
+            }
+            else
+            {
+                ks_decompose(c, target + (size_t)b0 * limbs * n, nb, limbs, ext.as<u64>(), 0);
+                ks_mac_moddown(c, ext.as<u64>(), nb, limbs, ksk, key_kl, ctb, false, ctb);
+            }
         }
     }
 
