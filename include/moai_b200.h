@@ -56,9 +56,14 @@ int32_t moai_profile_enable(moai_context *ctx, int32_t on);
 int32_t moai_profile_get(moai_context *ctx, const char *name, double *ms, int64_t *count);
 int32_t moai_launch_count(moai_context *ctx, uint64_t *count);
 
-/* ---- device memory (plumbing for hosts without their own allocator) ------------------------ */
+/* ---- device memory (plumbing for hosts without their own allocator) ------------------------
+ * The library keeps its temporaries in a stream-ordered best-fit block cache (the role SEAL's
+ * MemoryPoolMT plays on the host, S/util/mempool.h:228): freed blocks are reused by later work on
+ * the same stream and returned to the driver only when an allocation fails or on
+ * moai_release_cached_memory. */
 int32_t moai_malloc(moai_context *ctx, uint64_t bytes, void **out);
 int32_t moai_free(moai_context *ctx, void *ptr);
+int32_t moai_release_cached_memory(moai_context *ctx);
 int32_t moai_memcpy_h2d(moai_context *ctx, void *dst, const void *src, uint64_t bytes);
 int32_t moai_memcpy_d2h(moai_context *ctx, void *dst, const void *src, uint64_t bytes);
 int32_t moai_memcpy_d2d(moai_context *ctx, void *dst, const void *src, uint64_t bytes);

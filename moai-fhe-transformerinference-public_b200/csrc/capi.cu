@@ -98,6 +98,7 @@ extern "C"
             {
                 cudaSetDevice(ctx->c->device);
                 cudaDeviceSynchronize();
+                device_release_cached();
                 delete ctx->c;
             }
             delete ctx;
@@ -163,10 +164,15 @@ extern "C"
     {
         API_BEGIN
         Context *c = get(ctx);
-        if (ptr)
-        {
-            MOAI_CUDA_CHECK(cudaFreeAsync(ptr, c->stream));
-        }
+        device_free(ptr, c->stream);
+        API_END
+    }
+
+    int32_t moai_release_cached_memory(moai_context *ctx)
+    {
+        API_BEGIN
+        get(ctx);
+        device_release_cached();
         API_END
     }
 
@@ -915,7 +921,8 @@ extern "C"
         }
         const AllocStats as = alloc_stats();
         s += "alloc_host:" + std::to_string(as.host_ms) + ":" + std::to_string(as.calls) + ";";
-        s += "alloc_trim_retries:0:" + std::to_string(as.retries) + ";";
+        s += "alloc_cache_flushes:0:" + std::to_string(as.retries) + ";";
+        s += "alloc_owned_GiB:" + std::to_string(as.owned_bytes / 1073741824.0) + ":1;";
         MOAI_REQUIRE((int)s.size() < capacity, "buffer too small");
         std::memcpy(buf, s.c_str(), s.size() + 1);
         API_END

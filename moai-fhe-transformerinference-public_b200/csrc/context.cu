@@ -5,6 +5,7 @@
 // GaloisTool (S/util/galois.cpp:18-95) and CKKSEncoder::CKKSEncoder (S/ckks.cpp:20-75).
 #include "context.hpp"
 #include <chrono>
+#include <set>
 #include <cstdio>
 #include <cmath>
 #include <complex>
@@ -102,61 +103,298 @@ namespace moai
         return g_last_error;
     }
 
-    // Stream-ordered allocation from the device's default pool.  The pool keeps freed blocks cached
-    // (unlimited release threshold), which fragments under GiB-sized, ever-changing requests: on failure
-    // drain the stream, hand the cached blocks back to the driver and retry once; a second failure is
-    // reported with the request size and the pool's state.
+    // ---------------------------------------------------------------------------------------------
+    // Device memory: a best-fit, splitting / coalescing block cache over cudaMalloc'ed segments, one
+    // arena pair per stream.
+    //
+    // Every temporary of the pipeline (ciphertext batches, extended digits, ...) is allocated and freed
+    // in stream order on the context's stream, so a freed block may be handed out again immediately:
+    // the work that last touched it precedes the new owner's work on the same stream.  That makes
+    // allocation a host-side map lookup.  (cudaMallocAsync, used before, spent 64 s of host time per
+    // encoder layer growing / defragmenting its pool under GiB-sized, ever-changing requests and
+    // stalled the launch queue: profiles/layer_r1_fast_b.json "alloc_host".)  When cudaMalloc fails,
+    // all cached blocks are returned to the driver and the request is retried once.
+    // ---------------------------------------------------------------------------------------------
     static thread_local const char *g_phase = "";
     void set_phase(const char *name)
     {
         g_phase = name ? name : "";
     }
 
-    static AllocStats g_alloc_stats;
+    namespace
+    {
+        // One arena = a set of cudaMalloc'ed segments carved into blocks: best-fit with splitting on
+        // allocation, coalescing with the neighbours on release (the scheme of caching tensor
+        // allocators).  Unlike one free list per size, a freed 17 GiB batch can serve the next
+        // level's slightly smaller requests, so the memory held stays close to the working set.
+        struct Block
+        {
+            char *ptr;
+            size_t size;
+            bool is_free;
+            Block *prev, *next; // neighbours inside the same segment
+        };
+
+        struct Arena
+        {
+            size_t granule, min_segment;
+            std::set<std::pair<size_t, Block *>> free_set; // (size, block), best fit = lower_bound
+            std::map<void *, Block *> used;
+            size_t owned = 0, in_use = 0;
+
+            Arena(size_t g, size_t seg) : granule(g), min_segment(seg)
+            {}
+
+            void *take(Block *b, size_t want)
+            {
+                if (b->size - want >= granule)
+                {
+                    Block *rest = new Block{ b->ptr + want, b->size - want, true, b, b->next };
+                    if (b->next)
+                    {
+                        b->next->prev = rest;
+                    }
+                    b->next = rest;
+                    b->size = want;
+                    free_set.insert({ rest->size, rest });
+                }
+                b->is_free = false;
+                used[b->ptr] = b;
+                in_use += b->size;
+                return b->ptr;
+            }
+
+            // nullptr when a new segment is needed
+            void *alloc_cached(size_t want)
+            {
+                auto it = free_set.lower_bound({ want, nullptr });
+                if (it == free_set.end())
+                {
+                    return nullptr;
+                }
+                Block *b = it->second;
+                free_set.erase(it);
+                return take(b, want);
+            }
+
+            cudaError_t grow(size_t want, void **out)
+            {
+                const size_t seg = want > min_segment ? want : min_segment;
+                void *p = nullptr;
+                cudaError_t e = cudaMalloc(&p, seg);
+                if (e != cudaSuccess && seg > want)
+                {
+                    cudaGetLastError();
+                    e = cudaMalloc(&p, want); // memory is tight: ask for exactly what is needed
+                    if (e == cudaSuccess)
+                    {
+                        owned += want;
+                        *out = take(new Block{ (char *)p, want, true, nullptr, nullptr }, want);
+                        return e;
+                    }
+                }
+                if (e != cudaSuccess)
+                {
+                    return e;
+                }
+                owned += seg;
+                *out = take(new Block{ (char *)p, seg, true, nullptr, nullptr }, want);
+                return e;
+            }
+
+            bool release(void *p)
+            {
+                auto it = used.find(p);
+                if (it == used.end())
+                {
+                    return false;
+                }
+                Block *b = it->second;
+                used.erase(it);
+                in_use -= b->size;
+                b->is_free = true;
+                if (b->next && b->next->is_free)
+                {
+                    Block *n = b->next;
+                    free_set.erase({ n->size, n });
+                    b->size += n->size;
+                    b->next = n->next;
+                    if (n->next)
+                    {
+                        n->next->prev = b;
+                    }
+                    delete n;
+                }
+                if (b->prev && b->prev->is_free)
+                {
+                    Block *pv = b->prev;
+                    free_set.erase({ pv->size, pv });
+                    pv->size += b->size;
+                    pv->next = b->next;
+                    if (b->next)
+                    {
+                        b->next->prev = pv;
+                    }
+                    delete b;
+                    b = pv;
+                }
+                free_set.insert({ b->size, b });
+                return true;
+            }
+
+            // return every completely free segment to the driver
+            void trim()
+            {
+                for (auto it = free_set.begin(); it != free_set.end();)
+                {
+                    Block *b = it->second;
+                    if (!b->prev && !b->next)
+                    {
+                        cudaFree(b->ptr);
+                        owned -= b->size;
+                        it = free_set.erase(it);
+                        delete b;
+                    }
+                    else
+                    {
+                        ++it;
+                    }
+                }
+            }
+        };
+
+        struct DeviceCache
+        {
+            std::mutex mu;
+            struct PerStream
+            {
+                Arena small{ 512, (size_t)8 << 20 };            // requests below 1 MiB
+                Arena large{ (size_t)1 << 20, (size_t)1 << 30 }; // everything else, 1 GiB segments at least
+            };
+            std::map<cudaStream_t, PerStream> arenas;
+            AllocStats stats;
+
+            void trim_all_locked()
+            {
+                for (auto &kv : arenas)
+                {
+                    kv.second.small.trim();
+                    kv.second.large.trim();
+                }
+            }
+
+            size_t owned_locked() const
+            {
+                size_t t = 0;
+                for (auto &kv : arenas)
+                {
+                    t += kv.second.small.owned + kv.second.large.owned;
+                }
+                return t;
+            }
+
+            size_t in_use_locked() const
+            {
+                size_t t = 0;
+                for (auto &kv : arenas)
+                {
+                    t += kv.second.small.in_use + kv.second.large.in_use;
+                }
+                return t;
+            }
+
+            void *alloc(size_t bytes, cudaStream_t stream)
+            {
+                bytes = bytes ? bytes : 8;
+                std::lock_guard<std::mutex> lock(mu);
+                stats.calls += 1;
+                PerStream &ps = arenas[stream];
+                Arena &a = bytes < ((size_t)1 << 20) ? ps.small : ps.large;
+                const size_t want = (bytes + a.granule - 1) / a.granule * a.granule;
+                if (void *p = a.alloc_cached(want))
+                {
+                    return p;
+                }
+                const auto t0 = std::chrono::steady_clock::now();
+                void *p = nullptr;
+                cudaError_t e = a.grow(want, &p);
+                if (e != cudaSuccess)
+                {
+                    cudaGetLastError();
+                    stats.retries += 1;
+                    cudaDeviceSynchronize();
+                    trim_all_locked();
+                    e = a.grow(want, &p);
+                }
+                stats.host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                if (e != cudaSuccess)
+                {
+                    cudaGetLastError();
+                    size_t free_b = 0, total_b = 0;
+                    cudaMemGetInfo(&free_b, &total_b);
+                    char buf[320];
+                    snprintf(buf, sizeof buf,
+                             "device allocation of %.2f GiB failed in phase '%s': %s (device free %.1f of %.1f GiB; "
+                             "this library holds %.1f GiB, %.1f GiB in use)",
+                             want / 1073741824.0, g_phase, cudaGetErrorString(e), free_b / 1073741824.0,
+                             total_b / 1073741824.0, owned_locked() / 1073741824.0, in_use_locked() / 1073741824.0);
+                    throw StatusError{ e == cudaErrorMemoryAllocation ? OUT_OF_MEMORY : CUDA_ERROR, buf };
+                }
+                return p;
+            }
+
+            void release(void *p, cudaStream_t stream)
+            {
+                std::lock_guard<std::mutex> lock(mu);
+                auto it = arenas.find(stream);
+                if (it != arenas.end() && (it->second.large.release(p) || it->second.small.release(p)))
+                {
+                    return;
+                }
+                for (auto &kv : arenas) // freed on another stream than it was allocated on
+                {
+                    if (kv.second.large.release(p) || kv.second.small.release(p))
+                    {
+                        return;
+                    }
+                }
+            }
+        };
+
+        DeviceCache &cache()
+        {
+            static DeviceCache *c = new DeviceCache(); // leaked on purpose: outlives every static destructor
+            return *c;
+        }
+    } // namespace
+
     AllocStats alloc_stats()
     {
-        return g_alloc_stats;
+        std::lock_guard<std::mutex> lock(cache().mu);
+        AllocStats s = cache().stats;
+        s.owned_bytes = cache().owned_locked();
+        s.cached_bytes = s.owned_bytes - cache().in_use_locked();
+        return s;
     }
 
     void *device_alloc(size_t bytes, cudaStream_t stream)
     {
-        void *p = nullptr;
-        bytes = bytes ? bytes : 8;
-        const auto t0 = std::chrono::steady_clock::now();
-        cudaError_t e = cudaMallocAsync(&p, bytes, stream);
-        g_alloc_stats.calls += 1;
-        g_alloc_stats.host_ms +=
-            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        if (e == cudaSuccess)
+        return cache().alloc(bytes, stream);
+    }
+
+    void device_free(void *p, cudaStream_t stream)
+    {
+        if (p)
         {
-            return p;
+            cache().release(p, stream);
         }
-        g_alloc_stats.retries += 1;
-        cudaGetLastError();
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaMemPool_t pool;
-        cudaDeviceGetDefaultMemPool(&pool, dev);
-        cudaStreamSynchronize(stream);
-        cudaMemPoolTrimTo(pool, 0);
-        e = cudaMallocAsync(&p, bytes, stream);
-        if (e == cudaSuccess)
-        {
-            return p;
-        }
-        cudaGetLastError();
-        size_t free_b = 0, total_b = 0;
-        uint64_t reserved = 0, used = 0;
-        cudaMemGetInfo(&free_b, &total_b);
-        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
-        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
-        char buf[320];
-        snprintf(buf, sizeof buf,
-                 "device allocation of %.2f GiB failed in phase '%s': %s (device free %.1f of %.1f GiB; pool reserved "
-                 "%.1f GiB, in use %.1f GiB)",
-                 bytes / 1073741824.0, g_phase, cudaGetErrorString(e), free_b / 1073741824.0, total_b / 1073741824.0,
-                 reserved / 1073741824.0, used / 1073741824.0);
-        throw StatusError{ e == cudaErrorMemoryAllocation ? OUT_OF_MEMORY : CUDA_ERROR, buf };
+    }
+
+    void device_release_cached()
+    {
+        cudaDeviceSynchronize();
+        std::lock_guard<std::mutex> lock(cache().mu);
+        cache().trim_all_locked();
     }
 
     Scratch::Scratch(size_t bytes, cudaStream_t stream) : s(stream)
@@ -169,10 +407,7 @@ namespace moai
 
     Scratch::~Scratch()
     {
-        if (p)
-        {
-            cudaFreeAsync(p, s);
-        }
+        device_free(p, s);
     }
 
     Context::~Context()

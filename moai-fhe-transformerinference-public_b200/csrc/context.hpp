@@ -33,13 +33,17 @@ namespace moai
 
     void set_last_error(const std::string &msg);
     const std::string &last_error();
-    // stream-ordered allocation with one trim-and-retry on failure (context.cu)
+    // stream-ordered allocation from a best-fit block cache (context.cu); freed blocks are reusable at
+    // once by later work on the same stream.  device_release_cached() returns the cache to the driver.
     void *device_alloc(size_t bytes, cudaStream_t stream);
+    void device_free(void *p, cudaStream_t stream);
+    void device_release_cached();
     void set_phase(const char *name); // last pipeline phase entered (for allocation-failure reports)
     struct AllocStats
     {
-        unsigned long long calls = 0, retries = 0; // retries = allocations that needed a pool trim
-        double host_ms = 0;                        // host time spent inside cudaMallocAsync
+        unsigned long long calls = 0, retries = 0; // retries = allocations that had to flush the cache
+        double host_ms = 0;                        // host time spent inside cudaMalloc (cache misses)
+        size_t cached_bytes = 0, owned_bytes = 0;
     };
     AllocStats alloc_stats();
 

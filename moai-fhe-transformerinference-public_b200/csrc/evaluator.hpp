@@ -28,10 +28,7 @@ namespace moai
         }
         ~DevBuf()
         {
-            if (p)
-            {
-                cudaFreeAsync(p, s);
-            }
+            device_free(p, s);
         }
         DevBuf(const DevBuf &) = delete;
         DevBuf &operator=(const DevBuf &) = delete;

@@ -46,6 +46,7 @@ namespace moai
             __device__ __forceinline__ u64 out_fwd(elem x) const { return csub(csub(x, two_q), q); } // [0,4q)->[0,q)
             __device__ __forceinline__ u64 out_inv(elem x) const { return csub(x, q); }              // [0,2q)->[0,q)
             __device__ __forceinline__ void phase_begin_fwd(elem (&)[16]) const {}
+            __device__ __forceinline__ void phase_mid_fwd(elem (&)[16]) const {}
             __device__ __forceinline__ void phase_begin_inv(elem (&)[16]) const {}
             __device__ __forceinline__ void ct(elem &x, elem &y, const tw_t &w) const
             {
@@ -77,9 +78,10 @@ namespace moai
         //                 |r| <= 1.125 p for p < 2^51 and <= 0.52 p for p < 2^48 (error terms: rounding of
         //                 h/p, of 1/p, and |l| <= ulp(h)/2); r is an exact integer because h - t p is an
         //                 integer below 2^53.
-        // WIDE  (2^48 <= p, 2p + 64 < 2^52): mul() is followed by red() so |v| <= p/2 + 1; the 16
-        //        registers are reduced at the start of each 4-stage phase, so the multiplier input
-        //        grows 0.5p -> 1.0p -> 1.5p -> 2.0p (< 2^52) and sums stay below 2.5p < 2^53.
+        // WIDE  (2^48 <= p, 2p + 64 < 2^52).  Forward: products are left unreduced (|v| <= 1.125 p) and
+        //        the 16 registers are reduced after every second stage: 0.5p -> 1.625p -> 2.75p (< 2^53),
+        //        multiplier inputs <= 1.625p < 2^52.  Inverse: mul() is followed by red() (|v| <= p/2 + 1)
+        //        and every sum is reduced.
         // NARROW (p < 2^48): 32p of headroom below 2^53; no intermediate reductions in the forward
         //        transform (|x| <= 2p + 8 * 0.52p per pass); in the inverse, sums double for at most 4
         //        stages between the phase reductions.
@@ -109,11 +111,16 @@ namespace moai
             {
                 return __fma_rn(-quot(x), p, x);
             }
-            __device__ __forceinline__ double mul(double a, double w) const
+            // a w mod p without the final reduction: |result| <= 1.125 p (WIDE) / 0.65 p (NARROW)
+            __device__ __forceinline__ double mul_lazy(double a, double w) const
             {
                 const double h = __dmul_rn(a, w);
                 const double l = __fma_rn(a, w, -h);
-                const double r = __dadd_rn(__fma_rn(-quot(h), p, h), l);
+                return __dadd_rn(__fma_rn(-quot(h), p, h), l);
+            }
+            __device__ __forceinline__ double mul(double a, double w) const
+            {
+                const double r = mul_lazy(a, w);
                 return WIDE ? red(r) : r;
             }
             // canonical / lazy uint64 below 2^52 -> double, exactly (bit trick, no I2F)
@@ -158,9 +165,17 @@ namespace moai
                     }
                 }
             }
+            // forward only: the WIDE class no longer reduces every product; values grow by <= 1.125 p per
+            // stage from <= p/2 + 1 and all 16 registers are reduced after every second stage
+            // (phase_begin_fwd / phase_mid_fwd), so multiplier inputs stay <= 1.625 p < 2^52 and sums
+            // <= 2.75 p < 2^53: 2 x 16 reductions per four stages instead of 16 + 32.
+            __device__ __forceinline__ void phase_mid_fwd(elem (&x)[16]) const
+            {
+                phase_begin_fwd(x);
+            }
             __device__ __forceinline__ void ct(elem &x, elem &y, const tw_t &w) const
             {
-                const double v = mul(y, w);
+                const double v = mul_lazy(y, w);
                 const double u = x;
                 x = __dadd_rn(u, v);
                 y = __dadd_rn(u, -v);
@@ -310,6 +325,7 @@ namespace moai
             // stages 0..3 pair the top four bits of a (k): root index 2^s + block
             ct_stage<8>(f, x, 1);
             ct_stage<4>(f, x, 2);
+            f.phase_mid_fwd(x);
             ct_stage<2>(f, x, 4);
             ct_stage<1>(f, x, 8);
             if constexpr (LOGR > 4)
@@ -335,9 +351,17 @@ namespace moai
                 {
                     ct_stage<4>(f, x, R / 8 + 2 * t);
                 }
+                if constexpr (R / 32 >= 8)
+                {
+                    f.phase_mid_fwd(x); // two stages done
+                }
                 if constexpr (R / 32 >= 2)
                 {
                     ct_stage<2>(f, x, R / 4 + 4 * t);
+                }
+                if constexpr (R / 32 == 4)
+                {
+                    f.phase_mid_fwd(x); // stages <4>, <2> done
                 }
                 ct_stage<1>(f, x, R / 2 + 8 * t);
 #pragma unroll
@@ -370,6 +394,7 @@ namespace moai
             // root index of stage t' is 2^t' (R + a) + b / (2 gap)
             ct_stage<8>(f, x, ra);
             ct_stage<4>(f, x, 2 * ra);
+            f.phase_mid_fwd(x);
             ct_stage<2>(f, x, 4 * ra);
             ct_stage<1>(f, x, 8 * ra);
 #pragma unroll
@@ -386,6 +411,7 @@ namespace moai
             f.phase_begin_fwd(x);
             ct_stage<8>(f, x, 16 * ra + t);
             ct_stage<4>(f, x, 32 * ra + 2 * t);
+            f.phase_mid_fwd(x);
             ct_stage<2>(f, x, 64 * ra + 4 * t);
             ct_stage<1>(f, x, 128 * ra + 8 * t);
             ulonglong2 *out = reinterpret_cast<ulonglong2 *>(base + 16 * t);
@@ -714,7 +740,7 @@ namespace moai
             // |x| <= 6.2 p (narrow) / p/2 + 1 (wide) the product stays below 2^99 / 2^101, its low part
             // below p/8, so FpField::mul's result bound grows only from 0.52 p to 0.65 p (narrow).
             auto key_d = [&](u64 v) { return f.in_outer(v); };
-            const int red_every = WIDE ? 4 : 8; // |acc| <= 0.5 p + 8 * 0.65 p  /  0.5 p + 4 * (0.5 p + 1)
+            const int red_every = WIDE ? 2 : 8; // |acc| <= 0.5 p + 8 * 0.65 p  /  0.5 p + 2 * 1.125 p
 
             for (int J = 0; J < a.limbs; J++)
             {
@@ -736,6 +762,7 @@ namespace moai
                     const double t1[8] = { w3.y, w4.x, w4.y, w5.x, w5.y, w6.x, w6.y, w7.x };
                     ct_stage_tw<8>(f, x, t8);
                     ct_stage_tw<4>(f, x, t4);
+                    f.phase_mid_fwd(x);
                     ct_stage_tw<2>(f, x, t2);
                     ct_stage_tw<1>(f, x, t1);
                 }
@@ -767,6 +794,7 @@ namespace moai
                     const double t1[8] = { a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y };
                     ct_stage_tw<8>(f, x, t8);
                     ct_stage_tw<4>(f, x, t4);
+                    f.phase_mid_fwd(x);
                     ct_stage_tw<2>(f, x, t2);
                     ct_stage_tw<1>(f, x, t1);
                 }
@@ -783,10 +811,10 @@ namespace moai
                 for (int u = 0; u < 8; u++)
                 {
                     const ulonglong2 k0 = kst[u * FT], k1 = kst[(8 + u) * FT];
-                    acc0[2 * u] = __dadd_rn(acc0[2 * u], f.mul(x[2 * u], key_d(k0.x)));
-                    acc0[2 * u + 1] = __dadd_rn(acc0[2 * u + 1], f.mul(x[2 * u + 1], key_d(k0.y)));
-                    acc1[2 * u] = __dadd_rn(acc1[2 * u], f.mul(x[2 * u], key_d(k1.x)));
-                    acc1[2 * u + 1] = __dadd_rn(acc1[2 * u + 1], f.mul(x[2 * u + 1], key_d(k1.y)));
+                    acc0[2 * u] = __dadd_rn(acc0[2 * u], f.mul_lazy(x[2 * u], key_d(k0.x)));
+                    acc0[2 * u + 1] = __dadd_rn(acc0[2 * u + 1], f.mul_lazy(x[2 * u + 1], key_d(k0.y)));
+                    acc1[2 * u] = __dadd_rn(acc1[2 * u], f.mul_lazy(x[2 * u], key_d(k1.x)));
+                    acc1[2 * u + 1] = __dadd_rn(acc1[2 * u + 1], f.mul_lazy(x[2 * u + 1], key_d(k1.y)));
                 }
                 if (J + 1 < a.limbs)
                 {

@@ -64,7 +64,9 @@ def main():
     clocks = sampler.stop()
     be.profile(True)                             # per-phase breakdown from one more (event-bracketed) call
     boot.bootstrap_3(keys, x, 2.0 ** 46)
-    phases = {k: round(v[0] / args.batch, 2) for k, v in be.profile_dump().items() if k.startswith("boot_")}
+    dump = be.profile_dump()
+    phases = {k: round(v[0] / args.batch, 2) for k, v in dump.items() if k.startswith("boot_")}
+    phases["allocator"] = {k: (round(v[0], 1), v[1]) for k, v in dump.items() if k.startswith("alloc_")}
     be.profile(False)
     ms = e0.elapsed_time(e1) / args.iters
     per_ct = ms / args.batch
