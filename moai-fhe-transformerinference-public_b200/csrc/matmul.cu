@@ -254,6 +254,227 @@ namespace moai
                 }
             }
         }
+
+        // ======================================================================================
+        // Tensor-core version (north_star (3): "int8 limb-split").  Residues and weights are split into
+        // byte planes, x = sum_a 2^(8a) x_a, w = sum_b 2^(8b) w_b, and the modular GEMM becomes NP^2
+        // unsigned 8-bit GEMMs whose s32 results are summed per diagonal s = a + b:
+        //      D_s[m][i] = sum_j sum_{a+b=s} x_a[j][m] * w_b[j][i]      (< NP * K * 255^2 < 2^31 for K <= 4096)
+        //      Y[m][i]   = (sum_s 2^(8s) D_s[m][i]) mod q               (exact: same canonical residue)
+        // One warp owns a 16 (coefficients) x 16 (output columns) tile: 2 n-tiles x (2 NP - 1) diagonals
+        // x 4 = 104 accumulator registers for NP = 7, and issues NP^2 mma.sync.m16n8k32.u8.u8 per n-tile
+        // and 32-deep k-step.  The A fragments are built on the fly from the ciphertexts (16 coalesced
+        // 64-bit loads + two 4x4 byte transposes per fragment register set, PRMT on the ALU pipe, hidden
+        // under the tensor pipe); the weights arrive pre-packed in fragment order (k_pack_weights).
+        // Measured basis (tools/microbench_mma.cu on B200): mma.sync u8 571 T MAC/s -> 11.7 T modular
+        // MAC/s at NP = 7, against 1.18 T for the IMAD kernel above.
+        // ======================================================================================
+        constexpr int IM_WARPS_M = 4, IM_WARPS_N = 2;               // CTA = 8 warps: 64 coefficients x 32 columns
+        constexpr int IM_TILE_M = 16 * IM_WARPS_M, IM_TILE_N = 16 * IM_WARPS_N;
+
+        // Wp[l][ks][nt][b][lane] (uint2): B fragments of byte plane b of Wc[l][32 ks .. +31][8 nt .. +7]
+        __global__ void k_pack_weights(const double *__restrict__ W, uint2 *__restrict__ Wp, int K, int C, int Kp, int Cp,
+                                       int limbs, int np, double scale, const LimbConst *__restrict__ lcs)
+        {
+            const long long total = (long long)limbs * (Kp / 32) * (Cp / 8) * 32;
+            const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= total)
+            {
+                return;
+            }
+            const int lane = (int)(i % 32);
+            const long long r1 = i / 32;
+            const int nt = (int)(r1 % (Cp / 8));
+            const long long r2 = r1 / (Cp / 8);
+            const int ks = (int)(r2 % (Kp / 32));
+            const int l = (int)(r2 / (Kp / 32));
+            const LimbConst lc = lcs[l];
+            const int g = lane >> 2, t = lane & 3;
+            const int col = nt * 8 + g;
+            u64 w[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++)
+            {
+                const int j = ks * 32 + (e >> 2) * 16 + 4 * t + (e & 3);
+                u64 r = 0;
+                if (j < K && col < C)
+                {
+                    // residue of round(W * scale) mod q_l, sign-magnitude like SEAL (S/ckks.cpp:110-153)
+                    const double v = round(W[(long long)j * C + col] * scale);
+                    const u64 mag = (u64)fabs(v);
+                    r = reduce64(mag, lc);
+                    r = signbit(v) ? negmod(r, lc.q) : r;
+                }
+                w[e] = r;
+            }
+            for (int b = 0; b < np; b++)
+            {
+                uint2 o;
+                o.x = (u32)((w[0] >> (8 * b)) & 0xFF) | ((u32)((w[1] >> (8 * b)) & 0xFF) << 8) |
+                      ((u32)((w[2] >> (8 * b)) & 0xFF) << 16) | ((u32)((w[3] >> (8 * b)) & 0xFF) << 24);
+                o.y = (u32)((w[4] >> (8 * b)) & 0xFF) | ((u32)((w[5] >> (8 * b)) & 0xFF) << 8) |
+                      ((u32)((w[6] >> (8 * b)) & 0xFF) << 16) | ((u32)((w[7] >> (8 * b)) & 0xFF) << 24);
+                Wp[((((long long)l * (Kp / 32) + ks) * (Cp / 8) + nt) * np + b) * 32 + lane] = o;
+            }
+        }
+
+        __device__ __forceinline__ u32 prmt(u32 a, u32 b, u32 sel)
+        {
+            u32 r;
+            asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+            return r;
+        }
+
+        // r[e] = four bytes of element e  ->  p[i] = byte i of elements 0..3 (element 0 in the low byte)
+        __device__ __forceinline__ void transpose4x4(const u32 (&r)[4], u32 (&p)[4])
+        {
+            const u32 t0 = prmt(r[0], r[1], 0x5140), t1 = prmt(r[0], r[1], 0x7362);
+            const u32 t2 = prmt(r[2], r[3], 0x5140), t3 = prmt(r[2], r[3], 0x7362);
+            p[0] = prmt(t0, t2, 0x5410);
+            p[1] = prmt(t0, t2, 0x7632);
+            p[2] = prmt(t1, t3, 0x5410);
+            p[3] = prmt(t1, t3, 0x7632);
+        }
+
+        __device__ __forceinline__ void imma_u8(int (&d)[4], const u32 (&a)[4], const uint2 &b)
+        {
+            asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+                         "{%0,%1,%2,%3};"
+                         : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+        }
+
+        // NP = byte planes per residue (6 for primes below 2^48, 7 below 2^56).
+        // X: [K][2][limbs][n], Y: [C][2][limbs][n] (pre-rescale), one launch per class of limbs (limb_mask).
+        template <int NP>
+        __global__ void __launch_bounds__(256, 1)
+            k_ctpt_gemm_imma(const u64 *__restrict__ X, const uint2 *__restrict__ Wp, u64 *__restrict__ Y, int K, int C,
+                             int Kp, int Cp, int wnp, int tiles_n, int limbs, int log_n,
+                             const LimbConst *__restrict__ lcs, const Twiddle *__restrict__ two64,
+                             unsigned long long limb_mask)
+        {
+            // Cp, wnp: padded column count and planes per entry of the packed weight layout;
+            // C, tiles_n: columns / 32-column tiles of this launch (a column chunk of the layout)
+            constexpr int ND = 2 * NP - 1;
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            const int g = lane >> 2, t = lane & 3;
+            const int wm = warp % IM_WARPS_M, wn = warp / IM_WARPS_M;
+            // blockIdx.x = ((pl * tiles_m) + tile_m) * tiles_n + tile_n   (tile_n fastest: X tile stays in L2)
+            const int tiles_m = (1 << log_n) / IM_TILE_M;
+            const int tile_n = blockIdx.x % tiles_n;
+            const int rest = blockIdx.x / tiles_n;
+            const int tile_m = rest % tiles_m;
+            const int pl = rest / tiles_m; // p * limbs + l
+            const int l = pl % limbs;
+            if (!((limb_mask >> l) & 1))
+            {
+                return;
+            }
+            const size_t n = (size_t)1 << log_n;
+            const size_t ct_stride = (size_t)2 * limbs * n;
+            const size_t m0 = (size_t)tile_m * IM_TILE_M + 16 * wm + g; // this thread's first row (second = +8)
+            const u64 *xp = X + (size_t)pl * n + m0;
+            const int nt0 = (tile_n * IM_TILE_N + 16 * wn) / 8; // first of this warp's two n-tiles
+            const uint2 *wp = Wp + (((size_t)l * (Kp / 32)) * (Cp / 8) + nt0) * wnp * 32 + lane;
+            const size_t wp_ks = (size_t)(Cp / 8) * wnp * 32;
+
+            int acc[2][ND][4];
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+            {
+#pragma unroll
+                for (int s = 0; s < ND; s++)
+                {
+                    acc[q][s][0] = acc[q][s][1] = acc[q][s][2] = acc[q][s][3] = 0;
+                }
+            }
+            for (int ks = 0; ks < Kp / 32; ks++)
+            {
+                // A fragments: planes[a][kk * 2 + rr] for k-half kk and row g + 8 rr
+                u32 A[NP][4];
+#pragma unroll
+                for (int kk = 0; kk < 2; kk++)
+                {
+#pragma unroll
+                    for (int rr = 0; rr < 2; rr++)
+                    {
+                        u32 lo[4], hi[4], pl4[4], ph4[4];
+#pragma unroll
+                        for (int e = 0; e < 4; e++)
+                        {
+                            const int j = ks * 32 + kk * 16 + 4 * t + e;
+                            const u64 v = j < K ? __ldg(xp + (size_t)j * ct_stride + 8 * rr) : 0;
+                            lo[e] = (u32)v;
+                            hi[e] = (u32)(v >> 32);
+                        }
+                        transpose4x4(lo, pl4);
+                        transpose4x4(hi, ph4);
+#pragma unroll
+                        for (int a = 0; a < NP; a++)
+                        {
+                            A[a][kk * 2 + rr] = a < 4 ? pl4[a] : ph4[a - 4];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 2; q++)
+                {
+                    uint2 B[NP];
+#pragma unroll
+                    for (int b = 0; b < NP; b++)
+                    {
+                        B[b] = __ldg(wp + (size_t)ks * wp_ks + ((size_t)q * wnp + b) * 32);
+                    }
+#pragma unroll
+                    for (int a = 0; a < NP; a++)
+                    {
+#pragma unroll
+                        for (int b = 0; b < NP; b++)
+                        {
+                            imma_u8(acc[q][a + b], A[a], B[b]);
+                        }
+                    }
+                }
+            }
+            // epilogue: Y = (sum_s 2^(8s) D_s) mod q; c0,c1: row g, columns 2t, 2t+1; c2,c3: row g + 8
+            const LimbConst lc = lcs[l];
+            const Twiddle t64 = two64[l];
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+            {
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                {
+                    u64 lo = 0, hi = 0;
+#pragma unroll
+                    for (int s = 0; s < ND; s++)
+                    {
+                        const u64 v = (u64)(u32)acc[q][s][r];
+                        const int sh = 8 * s;
+                        if (sh == 0)
+                        {
+                            lo = v;
+                        }
+                        else if (sh < 64)
+                        {
+                            const u64 add = v << sh;
+                            lo += add;
+                            hi += (lo < add) + (v >> (64 - sh));
+                        }
+                        else
+                        {
+                            hi += v << (sh - 64);
+                        }
+                    }
+                    const int col = (nt0 + q) * 8 + 2 * t + (r & 1);
+                    if (col < C)
+                    {
+                        Y[(size_t)col * ct_stride + (size_t)pl * n + m0 + 8 * (r >> 1)] =
+                            barrett_reduce_acc(u128{ lo, hi }, lc, t64.w, t64.wq);
+                    }
+                }
+            }
+        }
     } // namespace
 
     // X: [K][2][limbs][n] device; W: host row-major K x C doubles; out: [C][2][limbs-1][n] device
@@ -279,8 +500,60 @@ namespace moai
         {
             narrow = narrow && (c->q[l] >> 52) == 0;
         }
-        static const int variant = getenv("MOAI_GEMM_VARIANT") ? atoi(getenv("MOAI_GEMM_VARIANT")) : 0;
-        const bool split26 = narrow && variant != 0;
+        // 3 (default): int8 byte-plane GEMM on the tensor cores; 0: IMAD 128-bit; 1, 2: IMAD 26-bit split
+        static const int variant = getenv("MOAI_GEMM_VARIANT") ? atoi(getenv("MOAI_GEMM_VARIANT")) : 3;
+        bool bytes7 = n >= (size_t)IM_TILE_M; // every limb prime below 2^56 -> at most 7 byte planes
+        for (int l = 0; l < limbs; l++)
+        {
+            bytes7 = bytes7 && (c->q[l] >> 56) == 0;
+        }
+        if (variant == 3 && bytes7)
+        {
+            const int Kp = (K + 31) / 32 * 32, Cp = (C + IM_TILE_N - 1) / IM_TILE_N * IM_TILE_N;
+            const int np = 7;
+            Scratch dWp((size_t)limbs * (Kp / 32) * (Cp / 8) * np * 32 * sizeof(uint2), c->stream);
+            const long long pack_threads = (long long)limbs * (Kp / 32) * (Cp / 8) * 32;
+            k_pack_weights<<<(unsigned)((pack_threads + 255) / 256), 256, 0, c->stream>>>(
+                dW.as<double>(), dWp.as<uint2>(), K, C, Kp, Cp, limbs, np, scale, c->d_limb);
+            c->launches += 1;
+            unsigned long long mask6 = 0, mask7 = 0; // limbs whose prime fits 6 / needs 7 byte planes
+            for (int l = 0; l < limbs; l++)
+            {
+                ((c->q[l] >> 48) == 0 ? mask6 : mask7) |= 1ull << l;
+            }
+            const int col_chunk = 768;
+            Scratch Y((size_t)std::min(C, col_chunk) * 2 * limbs * n * sizeof(u64), c->stream);
+            MOAI_REQUIRE(C <= col_chunk || C % IM_TILE_N == 0, "column count must be a multiple of 32 beyond 768");
+            for (int c0 = 0; c0 < C; c0 += col_chunk)
+            {
+                const int cn = std::min(col_chunk, C - c0);
+                const int cnp = (cn + IM_TILE_N - 1) / IM_TILE_N * IM_TILE_N;
+                const long long ctas = (long long)2 * limbs * (n / IM_TILE_M) * (cnp / IM_TILE_N);
+                {
+                    PhaseTimer pt(c, "ctpt_gemm");
+                    // the packed weights of column chunk c0 start c0 / 8 n-tiles into every k-step row
+                    const uint2 *wp0 = dWp.as<uint2>() + (size_t)(c0 / 8) * np * 32;
+                    if (mask7)
+                    {
+                        k_ctpt_gemm_imma<7><<<(unsigned)ctas, 256, 0, c->stream>>>(
+                            X, wp0, Y.as<u64>(), K, cn, Kp, Cp, np, cnp / IM_TILE_N, limbs, c->log_n, c->d_limb,
+                            c->d_two64, mask7);
+                        c->launches += 1;
+                    }
+                    if (mask6)
+                    {
+                        k_ctpt_gemm_imma<6><<<(unsigned)ctas, 256, 0, c->stream>>>(
+                            X, wp0, Y.as<u64>(), K, cn, Kp, Cp, np, cnp / IM_TILE_N, limbs, c->log_n, c->d_limb,
+                            c->d_two64, mask6);
+                        c->launches += 1;
+                    }
+                }
+                MOAI_CUDA_CHECK(cudaGetLastError());
+                rescale(c, Y.as<u64>(), out + (size_t)c0 * 2 * (limbs - 1) * n, cn, 2, limbs);
+            }
+            return;
+        }
+        const bool split26 = narrow && variant != 0 && variant != 3;
         k_encode_weights<<<(unsigned)((kc + 255) / 256), 256, 0, c->stream>>>(dW.as<double>(), dWc.as<u64>(), kc, limbs,
                                                                             scale, c->d_limb, split26 ? 1 : 0);
         c->launches += 1;

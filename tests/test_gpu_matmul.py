@@ -14,7 +14,7 @@ def rand_cts(o, rng, count, limbs):
     return out
 
 
-@pytest.mark.parametrize("K,C,limbs", [(5, 11, 3), (1, 1, 2), (300, 8, 4)])
+@pytest.mark.parametrize("K,C,limbs", [(5, 11, 3), (1, 1, 2), (300, 8, 4), (70, 45, 3)])
 def test_matmul_small_vs_oracle(pkg, backend_small, oracle_small, K, C, limbs):
     o, be = oracle_small, backend_small
     rng = np.random.default_rng(K * 100 + C)
