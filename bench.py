@@ -286,13 +286,21 @@ def run_gpu(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         limb_bytes = n * 8
         algo_bytes = (2 * K_IN + 2 * C_OUT) * LIMBS * limb_bytes          # (K + C) * l MiB
         gemm_avg_ms = gemm_ms / max(1, gemm_cnt)
-        achieved = algo_bytes / (gemm_avg_ms * 1e-3) / 1e9 if gemm_avg_ms > 0 else 0.0
         macs = 2 * n * K_IN * C_OUT * LIMBS
+        # the GEMM runs on the tensor pipe as NP^2 unsigned 8-bit GEMMs per limb (NP = 7 byte planes for the
+        # 51-bit prime q0, 6 for the 46-bit q1; csrc/matmul.cu): int8 operations = 2 * NP^2 per modular MAC
+        planes = [7 if primes[l] >> 48 else 6 for l in range(LIMBS)]
+        int8_ops = sum(2 * np_ * np_ for np_ in planes) * (macs // LIMBS)
+        achieved = int8_ops / (gemm_avg_ms * 1e-3) / 1e12 if gemm_avg_ms > 0 else 0.0
+        # dense int8 peak = 2 x dense bf16; MEASURED_PEAKS.json carries the measured bf16 burst figure
+        if "bf16_tflops" in peaks:
+            peak, peak_src = 2.0 * float(peaks["bf16_tflops"]), "2 x measured dense bf16 (MEASURED_PEAKS.json bf16_tflops)"
+        else:
+            peak, peak_src = 4500.0, "nominal dense int8 (B200_PROFILING.md fallback 2 x 2250 bf16)"
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ctpt_gemm_traffic.json")
         if os.path.exists(tpath):
@@ -301,6 +309,7 @@ def run_gpu(args):
             except Exception:
                 traffic = None
         cb = cpu_baseline_sample() if world == 1 and not args.no_cpu_baseline else None
+        hbm_achieved = algo_bytes / (gemm_avg_ms * 1e-3) / 1e9 if gemm_avg_ms > 0 else 0.0
         line = {"metric": METRIC, "value": value, "unit": "s/input", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak",
                 "vs_baseline": value / PUBLISHED_S_PER_INPUT, "dtype": "u64", "data": "synthetic",
@@ -311,14 +320,18 @@ def run_gpu(args):
                 "e2e": {"value": e2e_value, "unit": "s/input", "h2d_bytes_per_step": int(hX.numel() * 8),
                         "d2h_bytes_per_step": int(hOut.numel() * 8)},
                 "gpu_launches": int(launches),
-                "roofline": {"kernel": "k_ctpt_gemm", "bound": "hbm", "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                "roofline": {"kernel": "k_ctpt_gemm_imma (two launches per step: 7- and 6-byte-plane limbs)",
+                             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                             "frac": achieved / peak if peak else None, "traffic": traffic,
                              "peak_source": peak_src, "kernel_ms": gemm_avg_ms,
                              "kernel_share_of_step": gemm_avg_ms / ms_per_step if ms_per_step else None,
                              "algorithmic_bytes": algo_bytes, "modular_macs": macs,
                              "gmacs_per_s": macs / (gemm_avg_ms * 1e-3) / 1e9 if gemm_avg_ms > 0 else None,
-                             "note": "integer-pipe bound (64x64->128 MAC on IMAD), far from the HBM roof by design; "
-                                     "see DESIGN.md §5"},
+                             "hbm_achieved_gbs": hbm_achieved, "hbm_peak_gbs": hbm_peak,
+                             "hbm_frac": hbm_achieved / hbm_peak if hbm_peak else None,
+                             "note": "int8 operations on the legacy mma.sync path (IMMA.16832.U8), whose own ceiling "
+                                     "measured with tools/microbench_mma.cu is 1143 TOP/s = 1/4 of the tcgen05 int8 "
+                                     "peak; `achieved` counts 2 * NP^2 int8 ops per modular MAC; see DESIGN.md section 5"},
                 }
         if cb is not None:
             line["cpu_baseline"] = cb

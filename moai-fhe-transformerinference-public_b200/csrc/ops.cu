@@ -434,18 +434,20 @@ namespace moai
             int n_baby, n_giant;
         };
 
-        __global__ void __launch_bounds__(EW_THREADS) k_bsgs_inner(BsgsArgs a, long long total2, int log_n2, int limbs,
+        __global__ void __launch_bounds__(EW_THREADS) k_bsgs_inner(BsgsArgs a, long long polys, int log_n2, int limbs,
                                                                    const LimbConst *__restrict__ lcs,
                                                                    const Twiddle *__restrict__ two64)
         {
-            long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; // over [batch][2][limbs][n/2]
-            if (i >= total2)
-            {
-                return;
-            }
-            const long long lp = i >> log_n2;
-            const int limb = (int)(lp % limbs);
-            const long long within = i & (((long long)1 << log_n2) - 1);
+            // grid: the (ciphertext, polynomial) index is FASTEST, then the coefficient block, then the limb:
+            // CTAs that share a tile of the diagonals run together, so the plaintexts (63 x limbs x 512 KiB
+            // per stage, far more than the ciphertext data) are streamed from HBM once per batch, not
+            // once per ciphertext.
+            const long long bp = blockIdx.x % polys; // b * 2 + p
+            const long long rest = blockIdx.x / polys;
+            const int cblks = (1 << log_n2) / EW_THREADS;
+            const long long within = (rest % cblks) * EW_THREADS + threadIdx.x;
+            const int limb = (int)(rest / cblks);
+            const long long i = ((bp * limbs + limb) << log_n2) + within; // over [batch][2][limbs][n/2]
             const long long pt_off = ((long long)limb << log_n2) + within;
             const LimbConst lc = lcs[limb];
             const Twiddle t64 = two64[limb];
@@ -698,9 +700,10 @@ namespace moai
                 a.pt[g][j] = pt[g * n_baby + j];
             }
         }
-        const long long total2 = batch * 2 * limbs * (long long)(c->n / 2);
-        k_bsgs_inner<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(a, total2, c->log_n - 1, limbs, c->d_limb,
-                                                                     c->d_two64);
+        const long long ctas = batch * 2 * limbs * (long long)((c->n / 2) / EW_THREADS);
+        MOAI_REQUIRE((c->n / 2) % EW_THREADS == 0 && ctas < (1ll << 31), "unsupported shape for the fused inner sums");
+        k_bsgs_inner<<<(unsigned)ctas, EW_THREADS, 0, c->stream>>>(a, batch * 2, c->log_n - 1, limbs, c->d_limb,
+                                                                   c->d_two64);
         c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
     }
