@@ -128,7 +128,11 @@ int32_t moai_single_att_block(moai_context *ctx, moai_keys *keys, moai_bootstrap
  * (12 heads) -> self-output matmul -> bootstrap -> residual + LayerNorm -> bootstrap ->
  * intermediate matmul -> GELU -> final matmul -> bootstrap -> residual + LayerNorm2 -> bootstrap.
  * x: [hidden][2][limbs][N] at chain_index 20; out: the next layer's input at chain_index 20.
- * All weight pointers are HOST row-major [in][out] doubles as the driver reads them (:94-337).    */
+ * All weight pointers are HOST row-major [in][out] doubles as the driver reads them (:94-337).
+ * `out` may equal `x` (same shape): the layer then runs in place — x's storage receives the second
+ * bootstrapping's output once the first residual has consumed the input, and finally the layer
+ * output — which saves two 15.75 GiB buffers at the repo's size (the next layer's input is this
+ * layer's output anyway, :1081-1087).                                                             */
 typedef struct moai_layer_weights
 {
     int32_t hidden, heads, head_dim, inter;
