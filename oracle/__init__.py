@@ -457,6 +457,25 @@ class SealRef:
                                          C.byref(ol), C.byref(osc)))
         return out[: num_ct * 2 * ol.value * self.n].copy(), ol.value, osc.value
 
+    def save_ciphertext(self, ct, size, limbs, scale):
+        """Ciphertext::save(compr_mode_type::none) of the real library -> bytes."""
+        ct = np.ascontiguousarray(ct, dtype=np.uint64)
+        cap = C.c_int64(ct.nbytes + 4096)
+        buf = np.zeros(cap.value, dtype=np.uint8)
+        self._chk(self.lib.ref_save_ciphertext(self.h, _p(ct), C.c_int(size), C.c_int(limbs), C.c_double(scale),
+                                               buf.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(cap)))
+        return buf[: cap.value].tobytes()
+
+    def load_ciphertext(self, blob):
+        """Ciphertext::load (with SEAL's validity checks) -> (residues, size, limbs, scale)."""
+        b = np.frombuffer(blob, dtype=np.uint8)
+        out = np.zeros(len(blob) // 8 + 8, dtype=np.uint64)
+        size, limbs, scale = C.c_int(0), C.c_int(0), C.c_double(0)
+        self._chk(self.lib.ref_load_ciphertext(self.h, b.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int64(len(blob)),
+                                               _p(out), C.c_int64(out.size), C.byref(size), C.byref(limbs),
+                                               C.byref(scale)))
+        return out[: size.value * limbs.value * self.n].copy(), size.value, limbs.value, scale.value
+
     def ct_ct_matmul(self, which, X, nX, W, nW, limbs, scale_X, scale_W, col_X, row_X, col_W, row_W, num_batch):
         out = np.zeros(max(row_X, col_W) * 2 * limbs * self.n, dtype=np.uint64)
         oc, ol, osc = C.c_int(0), C.c_int(0), C.c_double(0)

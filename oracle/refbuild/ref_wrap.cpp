@@ -728,6 +728,44 @@ extern "C"
         return k;
     }
 
+    // ---- wire format: Ciphertext::save / load with compr_mode_type::none (S/ciphertext.cpp:153-330) ----
+    // *n_bytes in: capacity of buf, out: bytes written
+    int ref_save_ciphertext(void *h, const uint64_t *ct_raw, int size, int limbs, double scale, uint8_t *buf,
+                            int64_t *n_bytes)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        Ciphertext ct;
+        load_ct(*r, ct_raw, size, limbs, scale, ct);
+        const auto need = ct.save_size(compr_mode_type::none);
+        if (need > *n_bytes)
+        {
+            throw invalid_argument("buffer too small");
+        }
+        *n_bytes = ct.save(reinterpret_cast<seal_byte *>(buf), size_t(need), compr_mode_type::none);
+        REF_CATCH(r)
+    }
+
+    // loads with full validity checks (Ciphertext::load); fills the raw residues and the metadata
+    int ref_load_ciphertext(void *h, const uint8_t *buf, int64_t n_bytes, uint64_t *ct_raw, int64_t cap_words, int *size,
+                            int *limbs, double *scale)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        Ciphertext ct;
+        ct.load(*r->ctx, reinterpret_cast<const seal_byte *>(buf), size_t(n_bytes));
+        const int64_t words = int64_t(ct.size() * ct.coeff_modulus_size() * r->n);
+        if (words > cap_words)
+        {
+            throw invalid_argument("buffer too small");
+        }
+        store_ct(*r, ct, ct_raw);
+        *size = int(ct.size());
+        *limbs = int(ct.coeff_modulus_size());
+        *scale = ct.scale();
+        REF_CATCH(r)
+    }
+
     int ref_omp_threads()
     {
         return omp_get_max_threads();

@@ -42,3 +42,21 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "ckks_oracle" not in text and "libsealref" not in text, f
+
+
+def test_attention_rotation_steps_cover_the_pipeline():
+    """Host-side helper: the steps one head takes in fast mode (csrc/modules.cu) at the repo's packing
+    (num_batch = 256, 128 tokens, 32768 slots)."""
+    import importlib
+    pkg = importlib.import_module("moai-fhe-transformerinference-public_b200")
+    st = pkg.attention_rotation_steps(256)
+    slots = 128 * 256
+    # QK^T: hoisted baby steps b * 256 (b < 16), +-16 a * 256 for the outer part (a < 8)
+    assert set(b * 256 for b in range(1, 16)) <= set(st["qk"])
+    for a in range(1, 8):
+        assert 16 * a * 256 in st["qk"] and (slots - 16 * a * 256) in st["qk"]
+    # softmax * V (Ct_ct_matrix_mul.hpp:70-151): g = 12 baby steps of V, 10 group rotations, 10 giant steps
+    assert set(k * 256 for k in range(1, 12)) <= set(st["sv"])
+    assert set((128 - 12 * i) * 256 for i in range(1, 11)) <= set(st["sv"])
+    assert set(12 * j * 256 for j in range(1, 11)) <= set(st["sv"])
+    assert all(0 < s < slots for s in st["qk"] + st["sv"])
