@@ -22,6 +22,14 @@ extern "C" {
 int32_t moai_ct_pt_matrix_mul_wo_pre(moai_context *ctx, const uint64_t *enc_X, const double *W, int32_t col_X,
                                      int32_t col_W, int32_t row_W, int32_t limbs, double scale, uint64_t *out);
 
+/* B1/B2 with HOST buffers — the shape of the reference's own call, whose vector<Ciphertext> lives in host
+ * memory (Ct_pt_matrix_mul.hpp:4-6): host_enc_X [row_W][2][limbs][N] (pinned memory for full PCIe speed) ->
+ * host_out [col_W][2][limbs-1][N], col_W <= 768.  Upload, GEMM and download are pipelined per
+ * (polynomial, limb) slice; returns when host_out is complete.                                     */
+int32_t moai_ct_pt_matrix_mul_wo_pre_host(moai_context *ctx, const uint64_t *host_enc_X, const double *W,
+                                          int32_t col_X, int32_t col_W, int32_t row_W, int32_t limbs, double scale,
+                                          uint64_t *host_out);
+
 /* B3: ct_pt_matrix_mul_wo_pre_w_mask (M/source/matrix_mul/Ct_pt_matrix_mul.hpp:103-170):
  * the plaintext of weight w is encode(w * mask) with mask = bias_vec (HOST, N/2 ints, 1 = valid
  * token slot).  An all-ones mask takes the scalar path above (bit-identical); any other mask is

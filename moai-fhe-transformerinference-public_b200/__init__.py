@@ -320,6 +320,23 @@ class Backend:
 
     ct_pt_matrix_mul_wo_pre_large = ct_pt_matrix_mul_wo_pre
 
+    def ct_pt_matrix_mul_wo_pre_host(self, host_X, W, scale, out=None):
+        """The same module on HOST tensors (pinned CPU int64 [K, 2, limbs, n] -> [C, 2, limbs-1, n]):
+        upload, tensor-core GEMM and download pipelined inside the library
+        (moai_ct_pt_matrix_mul_wo_pre_host)."""
+        K, p, l, n = host_X.shape
+        assert host_X.device.type == "cpu" and host_X.is_contiguous()
+        W = np.ascontiguousarray(W, dtype=np.float64)
+        if W.shape[0] != K:
+            raise MoaiError(1, "bad dimensions of X or W")
+        Cc = W.shape[1]
+        if out is None:
+            out = self.torch.empty((Cc, 2, l - 1, n), dtype=self.torch.int64, pin_memory=True)
+        self._chk(self.lib.moai_ct_pt_matrix_mul_wo_pre_host(
+            self.h, C.c_void_p(host_X.data_ptr()), W.ctypes.data_as(C.POINTER(C.c_double)), C.c_int32(K),
+            C.c_int32(Cc), C.c_int32(K), C.c_int32(l), C.c_double(scale), C.c_void_p(out.data_ptr())))
+        return out
+
     def ct_pt_matrix_mul_wo_pre_w_mask(self, enc_X, W, bias_vec, scale, out=None):
         """ct_pt_matrix_mul_wo_pre_w_mask (M/source/matrix_mul/Ct_pt_matrix_mul.hpp:103-170)."""
         K, p, l, n = enc_X.shape

@@ -482,6 +482,18 @@ extern "C"
         API_END
     }
 
+    int32_t moai_ct_pt_matrix_mul_wo_pre_host(moai_context *ctx, const uint64_t *host_enc_X, const double *W,
+                                              int32_t col_X, int32_t col_W, int32_t row_W, int32_t limbs, double scale,
+                                              uint64_t *host_out)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(col_X == row_W, "bad dimensions of X or W");
+        MOAI_REQUIRE(host_enc_X && W && host_out, "null argument");
+        ct_pt_matmul_scalar_host(c, CU(host_enc_X), W, row_W, col_W, limbs, scale, U(host_out));
+        API_END
+    }
+
     int32_t moai_ct_pt_matrix_mul_wo_pre_w_mask(moai_context *ctx, const uint64_t *enc_X, const double *W,
                                                 const int32_t *bias_vec, int32_t col_X, int32_t col_W, int32_t row_W,
                                                 int32_t limbs, double scale, uint64_t *out)

@@ -344,19 +344,44 @@ namespace moai
                          : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
         }
 
+        __device__ __forceinline__ void mm_cp_async16(void *smem, const void *gmem, bool valid)
+        {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+            const int bytes = valid ? 16 : 0; // src-size 0: the 16 bytes are zero-filled
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(bytes) : "memory");
+        }
+
+        constexpr int IM_STAGES = 3;
+        constexpr int IM_A_BYTES = 32 * IM_TILE_M * 8; // one k-step of raw residues: [32 j][64 m] u64, swizzled
+        __host__ __device__ constexpr int im_b_bytes(int np)
+        {
+            return (IM_TILE_N / 8) * np * 32 * 8; // B fragments of the CTA's n-tiles, all planes
+        }
+        __host__ __device__ constexpr int im_smem_bytes(int np)
+        {
+            return IM_STAGES * (IM_A_BYTES + im_b_bytes(np));
+        }
+
         // NP = byte planes per residue (6 for primes below 2^48, 7 below 2^56).
         // X: [K][2][limbs][n], Y: [C][2][limbs][n] (pre-rescale), one launch per class of limbs (limb_mask).
+        // Operands of the next two k-steps travel global -> shared memory with cp.async (3-stage ring):
+        // the raw residues of the CTA's 64 coefficients x 32 ciphertexts (rows of 512 B, 32-byte chunks
+        // XOR-swizzled with (j >> 2) & 3 so that the fragment gathers are bank-conflict free) and the
+        // pre-packed weight fragments of its 4 n-tiles.
         template <int NP>
         __global__ void __launch_bounds__(256, 1)
             k_ctpt_gemm_imma(const u64 *__restrict__ X, const uint2 *__restrict__ Wp, u64 *__restrict__ Y, int K, int C,
                              int Kp, int Cp, int wnp, int tiles_n, int limbs, int log_n,
                              const LimbConst *__restrict__ lcs, const Twiddle *__restrict__ two64,
-                             unsigned long long limb_mask)
+                             unsigned long long limb_mask, int pl_first)
         {
             // Cp, wnp: padded column count and planes per entry of the packed weight layout;
-            // C, tiles_n: columns / 32-column tiles of this launch (a column chunk of the layout)
+            // C, tiles_n: columns / 32-column tiles of this launch (a column chunk of the layout);
+            // pl_first: first (polynomial, limb) slice of this launch (the grid spans consecutive ones)
             constexpr int ND = 2 * NP - 1;
-            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            constexpr int B_BYTES = im_b_bytes(NP);
+            extern __shared__ __align__(16) unsigned char im_smem[];
+            const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
             const int g = lane >> 2, t = lane & 3;
             const int wm = warp % IM_WARPS_M, wn = warp / IM_WARPS_M;
             // blockIdx.x = ((pl * tiles_m) + tile_m) * tiles_n + tile_n   (tile_n fastest: X tile stays in L2)
@@ -364,7 +389,7 @@ namespace moai
             const int tile_n = blockIdx.x % tiles_n;
             const int rest = blockIdx.x / tiles_n;
             const int tile_m = rest % tiles_m;
-            const int pl = rest / tiles_m; // p * limbs + l
+            const int pl = pl_first + rest / tiles_m; // p * limbs + l
             const int l = pl % limbs;
             if (!((limb_mask >> l) & 1))
             {
@@ -372,11 +397,37 @@ namespace moai
             }
             const size_t n = (size_t)1 << log_n;
             const size_t ct_stride = (size_t)2 * limbs * n;
-            const size_t m0 = (size_t)tile_m * IM_TILE_M + 16 * wm + g; // this thread's first row (second = +8)
-            const u64 *xp = X + (size_t)pl * n + m0;
-            const int nt0 = (tile_n * IM_TILE_N + 16 * wn) / 8; // first of this warp's two n-tiles
-            const uint2 *wp = Wp + (((size_t)l * (Kp / 32)) * (Cp / 8) + nt0) * wnp * 32 + lane;
+            const size_t m_cta = (size_t)tile_m * IM_TILE_M;
+            const size_t m0 = m_cta + 16 * wm + g; // this thread's first row (second = +8)
+            const int nt_cta = tile_n * (IM_TILE_N / 8);
+            const int nt0 = nt_cta + 2 * wn; // first of this warp's two n-tiles
+            const u64 *xg = X + (size_t)pl * n + m_cta;
+            const uint2 *wg = Wp + (((size_t)l * (Kp / 32)) * (Cp / 8) + nt_cta) * wnp * 32;
             const size_t wp_ks = (size_t)(Cp / 8) * wnp * 32;
+            const int nks = Kp / 32;
+
+            // stage loader: A rows j = tid / 8 (32 rows), four 16-byte chunks each; B: contiguous B_BYTES
+            auto issue_stage = [&](int ks) {
+                unsigned char *sa = im_smem + (ks % IM_STAGES) * (IM_A_BYTES + B_BYTES);
+                unsigned char *sb = sa + IM_A_BYTES;
+                const int jr = tid >> 3, c4 = tid & 7;
+                const int j = ks * 32 + jr;
+                const u64 *src = xg + (size_t)(j < K ? j : 0) * ct_stride;
+                const int swz = ((jr >> 2) & 3) << 1; // XOR on the 32-byte chunk index = bits 1-2 of the 16-byte one
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                {
+                    const int ch = c4 * 4 + u;
+                    mm_cp_async16(sa + jr * 512 + ((ch ^ swz) << 4), src + 2 * ch, j < K);
+                }
+                const unsigned char *bsrc = reinterpret_cast<const unsigned char *>(wg + (size_t)ks * wp_ks);
+                for (int off = tid * 16; off < B_BYTES; off += 256 * 16)
+                {
+                    // layout planes per entry may exceed NP (7 stored, 6 used): copy plane by plane
+                    const int e = off / (NP * 256), rem = off % (NP * 256); // n-tile, byte inside its NP planes
+                    mm_cp_async16(sb + off, bsrc + (size_t)e * wnp * 256 + rem, true);
+                }
+            };
 
             int acc[2][ND][4];
 #pragma unroll
@@ -388,8 +439,24 @@ namespace moai
                     acc[q][s][0] = acc[q][s][1] = acc[q][s][2] = acc[q][s][3] = 0;
                 }
             }
-            for (int ks = 0; ks < Kp / 32; ks++)
+            issue_stage(0);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (nks > 1)
             {
+                issue_stage(1);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            for (int ks = 0; ks < nks; ks++)
+            {
+                asm volatile("cp.async.wait_group 1;" ::: "memory"); // stage ks has landed
+                __syncthreads();                                      // ... for every thread; stage ks - 1 is free
+                if (ks + 2 < nks)
+                {
+                    issue_stage(ks + 2);
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                const unsigned char *sa = im_smem + (ks % IM_STAGES) * (IM_A_BYTES + B_BYTES);
+                const uint2 *sb = reinterpret_cast<const uint2 *>(sa + IM_A_BYTES);
                 // A fragments: planes[a][kk * 2 + rr] for k-half kk and row g + 8 rr
                 u32 A[NP][4];
 #pragma unroll
@@ -399,11 +466,13 @@ namespace moai
                     for (int rr = 0; rr < 2; rr++)
                     {
                         u32 lo[4], hi[4], pl4[4], ph4[4];
+                        const int mloc = 16 * wm + g + 8 * rr;
 #pragma unroll
                         for (int e = 0; e < 4; e++)
                         {
-                            const int j = ks * 32 + kk * 16 + 4 * t + e;
-                            const u64 v = j < K ? __ldg(xp + (size_t)j * ct_stride + 8 * rr) : 0;
+                            const int jr = kk * 16 + 4 * t + e; // (jr >> 2) & 3 == t
+                            const u64 v = *reinterpret_cast<const u64 *>(sa + jr * 512 + (((mloc >> 2) ^ t) << 5) +
+                                                                         ((mloc & 3) << 3));
                             lo[e] = (u32)v;
                             hi[e] = (u32)(v >> 32);
                         }
@@ -423,7 +492,7 @@ namespace moai
 #pragma unroll
                     for (int b = 0; b < NP; b++)
                     {
-                        B[b] = __ldg(wp + (size_t)ks * wp_ks + ((size_t)q * wnp + b) * 32);
+                        B[b] = sb[((2 * wn + q) * NP + b) * 32 + lane];
                     }
 #pragma unroll
                     for (int a = 0; a < NP; a++)
@@ -477,6 +546,43 @@ namespace moai
         }
     } // namespace
 
+    namespace
+    {
+        // byte-plane GEMM of the slices [pl_first, pl_first + pl_count) (pl = polynomial * limbs + limb):
+        // one launch per plane-count class (7 planes for primes >= 2^48, 6 below) present among them
+        void launch_imma(Context *c, const u64 *X, const uint2 *wp0, u64 *Y, int K, int cn, int Kp, int Cp, int np,
+                         int limbs, int pl_first, int pl_count, cudaStream_t stream)
+        {
+            static const cudaError_t attr7 = cudaFuncSetAttribute(
+                k_ctpt_gemm_imma<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, im_smem_bytes(7));
+            static const cudaError_t attr6 = cudaFuncSetAttribute(
+                k_ctpt_gemm_imma<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, im_smem_bytes(6));
+            (void)attr7;
+            (void)attr6;
+            unsigned long long mask6 = 0, mask7 = 0;
+            for (int pl = pl_first; pl < pl_first + pl_count; pl++)
+            {
+                const int l = pl % limbs;
+                ((c->q[l] >> 48) == 0 ? mask6 : mask7) |= 1ull << l;
+            }
+            const int cnp = (cn + IM_TILE_N - 1) / IM_TILE_N * IM_TILE_N;
+            const long long ctas = (long long)pl_count * (c->n / IM_TILE_M) * (cnp / IM_TILE_N);
+            if (mask7)
+            {
+                k_ctpt_gemm_imma<7><<<(unsigned)ctas, 256, im_smem_bytes(7), stream>>>(
+                    X, wp0, Y, K, cn, Kp, Cp, np, cnp / IM_TILE_N, limbs, c->log_n, c->d_limb, c->d_two64, mask7, pl_first);
+                c->launches += 1;
+            }
+            if (mask6)
+            {
+                k_ctpt_gemm_imma<6><<<(unsigned)ctas, 256, im_smem_bytes(6), stream>>>(
+                    X, wp0, Y, K, cn, Kp, Cp, np, cnp / IM_TILE_N, limbs, c->log_n, c->d_limb, c->d_two64, mask6, pl_first);
+                c->launches += 1;
+            }
+            MOAI_CUDA_CHECK(cudaGetLastError());
+        }
+    } // namespace
+
     // X: [K][2][limbs][n] device; W: host row-major K x C doubles; out: [C][2][limbs-1][n] device
     void ct_pt_matmul_scalar(Context *c, const u64 *X, const double *h_W, int K, int C, int limbs, double scale,
                              u64 *out)
@@ -507,6 +613,26 @@ namespace moai
         {
             bytes7 = bytes7 && (c->q[l] >> 56) == 0;
         }
+        if (variant == 4 && bytes7 && n >= 128)
+        {
+            // tcgen05.mma.kind::i8 with TMEM accumulators (csrc/matmul_tc5.cu)
+            const int np = 7;
+            Scratch dBp(tc5_packed_weight_bytes(K, C, limbs, np), c->stream);
+            tc5_pack_weights(c, dW.as<double>(), dBp.as<unsigned char>(), K, C, limbs, np, scale);
+            const int col_chunk = 768;
+            Scratch Y((size_t)std::min(C, col_chunk) * 2 * limbs * n * sizeof(u64), c->stream);
+            MOAI_REQUIRE(C <= col_chunk || C % 32 == 0, "column count must be a multiple of 32 beyond 768");
+            for (int c0 = 0; c0 < C; c0 += col_chunk)
+            {
+                const int cn = std::min(col_chunk, C - c0);
+                {
+                    PhaseTimer pt(c, "ctpt_gemm");
+                    tc5_gemm(c, X, dBp.as<unsigned char>(), Y.as<u64>(), K, C, c0, cn, np, limbs, 0, 2 * limbs, c->stream);
+                }
+                rescale(c, Y.as<u64>(), out + (size_t)c0 * 2 * (limbs - 1) * n, cn, 2, limbs);
+            }
+            return;
+        }
         if (variant == 3 && bytes7)
         {
             const int Kp = (K + 31) / 32 * 32, Cp = (C + IM_TILE_N - 1) / IM_TILE_N * IM_TILE_N;
@@ -516,37 +642,17 @@ namespace moai
             k_pack_weights<<<(unsigned)((pack_threads + 255) / 256), 256, 0, c->stream>>>(
                 dW.as<double>(), dWp.as<uint2>(), K, C, Kp, Cp, limbs, np, scale, c->d_limb);
             c->launches += 1;
-            unsigned long long mask6 = 0, mask7 = 0; // limbs whose prime fits 6 / needs 7 byte planes
-            for (int l = 0; l < limbs; l++)
-            {
-                ((c->q[l] >> 48) == 0 ? mask6 : mask7) |= 1ull << l;
-            }
             const int col_chunk = 768;
             Scratch Y((size_t)std::min(C, col_chunk) * 2 * limbs * n * sizeof(u64), c->stream);
             MOAI_REQUIRE(C <= col_chunk || C % IM_TILE_N == 0, "column count must be a multiple of 32 beyond 768");
             for (int c0 = 0; c0 < C; c0 += col_chunk)
             {
                 const int cn = std::min(col_chunk, C - c0);
-                const int cnp = (cn + IM_TILE_N - 1) / IM_TILE_N * IM_TILE_N;
-                const long long ctas = (long long)2 * limbs * (n / IM_TILE_M) * (cnp / IM_TILE_N);
                 {
                     PhaseTimer pt(c, "ctpt_gemm");
                     // the packed weights of column chunk c0 start c0 / 8 n-tiles into every k-step row
-                    const uint2 *wp0 = dWp.as<uint2>() + (size_t)(c0 / 8) * np * 32;
-                    if (mask7)
-                    {
-                        k_ctpt_gemm_imma<7><<<(unsigned)ctas, 256, 0, c->stream>>>(
-                            X, wp0, Y.as<u64>(), K, cn, Kp, Cp, np, cnp / IM_TILE_N, limbs, c->log_n, c->d_limb,
-                            c->d_two64, mask7);
-                        c->launches += 1;
-                    }
-                    if (mask6)
-                    {
-                        k_ctpt_gemm_imma<6><<<(unsigned)ctas, 256, 0, c->stream>>>(
-                            X, wp0, Y.as<u64>(), K, cn, Kp, Cp, np, cnp / IM_TILE_N, limbs, c->log_n, c->d_limb,
-                            c->d_two64, mask6);
-                        c->launches += 1;
-                    }
+                    launch_imma(c, X, dWp.as<uint2>() + (size_t)(c0 / 8) * np * 32, Y.as<u64>(), K, cn, Kp, Cp, np, limbs,
+                                0, 2 * limbs, c->stream);
                 }
                 MOAI_CUDA_CHECK(cudaGetLastError());
                 rescale(c, Y.as<u64>(), out + (size_t)c0 * 2 * (limbs - 1) * n, cn, 2, limbs);
@@ -589,6 +695,103 @@ namespace moai
             MOAI_CUDA_CHECK(cudaGetLastError());
             rescale(c, Y.as<u64>(), out + (size_t)c0 * 2 * (limbs - 1) * n, cn, 2, limbs);
         }
+    }
+
+
+    // Same module with HOST buffers (what the reference's callers hold: vector<Ciphertext> in host memory):
+    // h_X [K][2][limbs][n] -> h_out [C][2][limbs-1][n].  The upload is cut into the 2 * limbs (polynomial, limb)
+    // slices of the batch — highest limb first, because the rescale needs it for every output limb — and the
+    // byte-plane GEMM of a slice starts as soon as the slice has landed, so the tensor cores run under the
+    // PCIe transfer; the rescaled columns are downloaded in chunks while the next chunk is rescaled.
+    void ct_pt_matmul_scalar_host(Context *c, const u64 *h_X, const double *h_W, int K, int C, int limbs, double scale,
+                                  u64 *h_out)
+    {
+        MOAI_REQUIRE(K >= 1 && C >= 1 && C <= 768, "bad dimensions of X or W");
+        MOAI_REQUIRE(limbs >= 2 && limbs <= c->kl - 1, "end of modulus switching chain reached");
+        MOAI_REQUIRE(K <= 4096, "K too large for the lazy accumulators");
+        const size_t n = c->n;
+        MOAI_REQUIRE(n >= (size_t)IM_TILE_M, "ring degree too small for the tensor-core kernel");
+        for (int l = 0; l < limbs; l++)
+        {
+            MOAI_REQUIRE((c->q[l] >> 56) == 0, "primes of 56 bits or more are not supported by the byte-plane kernel");
+        }
+        const long long kc = (long long)K * C;
+        double wmax = 0;
+        for (long long i = 0; i < kc; i++)
+        {
+            wmax = std::fmax(wmax, std::fabs(h_W[i]));
+        }
+        MOAI_REQUIRE(wmax * scale < 9.0e18, "encoded value is too large");
+        cudaStream_t s_in, s_out;
+        MOAI_CUDA_CHECK(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        MOAI_CUDA_CHECK(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        std::vector<cudaEvent_t> landed(2 * limbs);
+        for (auto &e : landed)
+        {
+            MOAI_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        const int Kp = (K + 31) / 32 * 32, Cp = (C + IM_TILE_N - 1) / IM_TILE_N * IM_TILE_N, np = 7;
+        const size_t ct_words = (size_t)2 * limbs * n;
+        {
+            Scratch dW(kc * sizeof(double), c->stream);
+            Scratch dWp((size_t)limbs * (Kp / 32) * (Cp / 8) * np * 32 * sizeof(uint2), c->stream);
+            Scratch dX((size_t)K * ct_words * sizeof(u64), c->stream);
+            Scratch Y((size_t)C * ct_words * sizeof(u64), c->stream);
+            Scratch dOut((size_t)C * 2 * (limbs - 1) * n * sizeof(u64), c->stream);
+            MOAI_CUDA_CHECK(cudaMemcpyAsync(dW.p, h_W, kc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            const long long pack_threads = (long long)limbs * (Kp / 32) * (Cp / 8) * 32;
+            k_pack_weights<<<(unsigned)((pack_threads + 255) / 256), 256, 0, c->stream>>>(
+                dW.as<double>(), dWp.as<uint2>(), K, C, Kp, Cp, limbs, np, scale, c->d_limb);
+            c->launches += 1;
+            // the buffers come from the stream-ordered arena of c->stream: order the side streams after it
+            cudaEvent_t ready;
+            MOAI_CUDA_CHECK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+            MOAI_CUDA_CHECK(cudaEventRecord(ready, c->stream));
+            MOAI_CUDA_CHECK(cudaStreamWaitEvent(s_in, ready, 0));
+            MOAI_CUDA_CHECK(cudaStreamWaitEvent(s_out, ready, 0));
+            int order = 0;
+            for (int l = limbs - 1; l >= 0; l--)
+            {
+                for (int p = 0; p < 2; p++, order++)
+                {
+                    const size_t off = ((size_t)p * limbs + l) * n;
+                    MOAI_CUDA_CHECK(cudaMemcpy2DAsync(dX.as<u64>() + off, ct_words * sizeof(u64), h_X + off,
+                                                      ct_words * sizeof(u64), n * sizeof(u64), (size_t)K,
+                                                      cudaMemcpyHostToDevice, s_in));
+                    MOAI_CUDA_CHECK(cudaEventRecord(landed[order], s_in));
+                    MOAI_CUDA_CHECK(cudaStreamWaitEvent(c->stream, landed[order], 0));
+                    PhaseTimer pt(c, "ctpt_gemm");
+                    launch_imma(c, dX.as<u64>(), dWp.as<uint2>(), Y.as<u64>(), K, C, Kp, Cp, np, limbs, p * limbs + l, 1,
+                                c->stream);
+                }
+            }
+            const int out_chunk = 96;
+            const size_t out_ct = (size_t)2 * (limbs - 1) * n;
+            std::vector<cudaEvent_t> done((C + out_chunk - 1) / out_chunk);
+            for (int c0 = 0, k = 0; c0 < C; c0 += out_chunk, k++)
+            {
+                const int cn = std::min(out_chunk, C - c0);
+                rescale(c, Y.as<u64>() + (size_t)c0 * ct_words, dOut.as<u64>() + (size_t)c0 * out_ct, cn, 2, limbs);
+                MOAI_CUDA_CHECK(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+                MOAI_CUDA_CHECK(cudaEventRecord(done[k], c->stream));
+                MOAI_CUDA_CHECK(cudaStreamWaitEvent(s_out, done[k], 0));
+                MOAI_CUDA_CHECK(cudaMemcpyAsync(h_out + (size_t)c0 * out_ct, dOut.as<u64>() + (size_t)c0 * out_ct,
+                                                (size_t)cn * out_ct * sizeof(u64), cudaMemcpyDeviceToHost, s_out));
+            }
+            MOAI_CUDA_CHECK(cudaStreamSynchronize(s_out));
+            MOAI_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            for (auto &e : done)
+            {
+                cudaEventDestroy(e);
+            }
+            cudaEventDestroy(ready);
+        } // device buffers return to the arena after every stream has drained
+        for (auto &e : landed)
+        {
+            cudaEventDestroy(e);
+        }
+        cudaStreamDestroy(s_in);
+        cudaStreamDestroy(s_out);
     }
 
     namespace

@@ -277,33 +277,57 @@ namespace moai
         MOAI_REQUIRE(X.batch == col_X && W.batch == col_X, "bad dimensions of X or W");
         const double scale = X.scale;
         Ct acc = ev.alloc(row_X, 3, X.limbs, X.scale * W.scale);
-        // fast mode (pre-permuted keys for the steps b * num_batch, b < 16): rotation i = 16 a + b is a
-        // giant rotation by 16 a followed by a HOISTED baby rotation by b, so the 64 columns are
-        // decomposed once per giant step instead of once per row (the reference rotates every W[j]
-        // from scratch for every i through SEAL's NAF fallback, Ct_ct_matrix_mul.hpp:26-31)
+        // fast mode (pre-permuted keys): with i = 16 a + b,
+        //     sum_j X[j] (x) rot_i(W[j]) = rot_{16a}( sum_j rot_{-16a}(X[j]) (x) rot_b(W[j]) ),
+        // so the 64 columns of W are rotated 15 times and those of X 7 times — all hoisted, one digit
+        // decomposition per ciphertext — and the 16 a part is applied to the 128 relinearised, rescaled
+        // outputs (one ciphertext each, one limb lower).  The reference rotates every W[j] from scratch
+        // for every i through SEAL's NAF fallback: 127 x 64 calls, 240 k key switches per layer
+        // (Ct_ct_matrix_mul.hpp:26-31); here: 22 x 64 hoisted rotations + 112 single ones.
         const int inner = 16;
-        bool fast = row_X > inner;
+        const int slots = (int)(ev.n() / 2);
+        bool fast = row_X > inner && row_X % inner == 0;
         for (int b = 1; b < inner && fast; b++)
         {
             fast = ev.has_fast_key(b * num_batch, W.limbs, keys);
         }
+        for (int a0 = inner; a0 < row_X && fast; a0 += inner)
+        {
+            fast = ev.has_fast_key(slots - a0 * num_batch, X.limbs, keys) &&
+                   ev.has_fast_key(a0 * num_batch, X.limbs - 1, keys);
+        }
         if (fast)
         {
+            std::vector<int> steps_b, steps_a;
+            for (int b = 0; b < inner; b++)
+            {
+                steps_b.push_back(b * num_batch);
+            }
             for (int a0 = 0; a0 < row_X; a0 += inner)
             {
-                Ct wa = a0 > 0 ? ev.rotate_vector(W, a0 * num_batch, keys) : W;
-                std::vector<int> steps;
-                for (int b = 0; b < inner && a0 + b < row_X; b++)
+                steps_a.push_back(a0 == 0 ? 0 : slots - a0 * num_batch); // rotation by -16 a
+            }
+            std::vector<Ct> rotW = ev.rotate_many(W, steps_b, keys);
+            std::vector<Ct> rotX = ev.rotate_many(X, steps_a, keys);
+            for (size_t a = 0; a < rotX.size(); a++)
+            {
+                for (int b = 0; b < inner; b++)
                 {
-                    steps.push_back(b * num_batch);
-                }
-                std::vector<Ct> rots = ev.rotate_many(wa, steps, keys);
-                for (size_t b = 0; b < rots.size(); b++)
-                {
-                    Ct s = ev.inner_product(X, rots[b]);
-                    ev.copy_into(s, acc, a0 + (long long)b);
+                    Ct s = ev.inner_product(rotX[a], rotW[b]);
+                    ev.copy_into(s, acc, (long long)a * inner + b);
                 }
             }
+            rotW.clear();
+            rotX.clear();
+            Ct out = ev.rescale_to_next(ev.relinearize(acc, keys));
+            out.scale = scale;
+            for (int a0 = inner; a0 < row_X; a0 += inner)
+            {
+                Ct grp = ev.view(out, a0, inner);
+                Ct r = ev.rotate_vector(grp, a0 * num_batch, keys);
+                ev.copy_into(r, out, a0);
+            }
+            return out;
         }
         else
         {

@@ -1,4 +1,5 @@
 #include "ntt.cuh"
+#include <cstdlib>
 
 namespace moai
 {
@@ -867,6 +868,165 @@ namespace moai
             // integer-path moduli (the 58-bit special prime) are handled by the un-fused kernels
         }
 
+        // =====================================================================================
+        // Grouped pass B: the same 8 in-row stages as ntt_fwd_pass_b, but one CTA transforms its 8 rows of
+        // UP TO GS POLYNOMIALS THAT SHARE A PRIME one after the other (in a ciphertext batch [P][limbs]
+        // those are the polynomials `limbs` apart; in the extended digits of a key switch the `limbs`
+        // consecutive ones).  The 15 + 15 twiddles per thread are loaded once per CTA instead of once
+        // per polynomial and the next polynomial's rows arrive by cp.async while the current one
+        // computes, which removes the twiddle-latency stalls that held ntt_fwd_pass_b at 53 % FP64
+        // utilisation (profiles/ncu_full_ntt_r1.csv).  Integer-path primes run the classic body.
+        // =====================================================================================
+        constexpr int GS = 16; // polynomials per CTA
+        constexpr int GROUPED_SMEM = KS_SM_ROWS + KS_SM_TW2 + KS_SM_TW1;
+
+        template <bool WIDE>
+        __device__ __forceinline__ void fwd_pass_b_grouped_fp(const FpField<WIDE> &f, const NttArgs &a, long long slot,
+                                                              long long q0, long long q1, int rb, unsigned char *smem)
+        {
+            const int tid = threadIdx.x, t = tid & 15, r = tid >> 4;
+            const int R = 1 << (a.log_n - 8);
+            const int row = rb * FR + r;
+            const size_t ra = (size_t)R + row;
+            double *srow = reinterpret_cast<double *>(smem) + r * ROW_PAD;
+            double2 *tws = reinterpret_cast<double2 *>(smem + KS_SM_ROWS) + tid;
+            double2 *tw1 = reinterpret_cast<double2 *>(smem + KS_SM_ROWS + KS_SM_TW2) + r * 8;
+            // q-th polynomial of this prime: p = ((q / div) * period + slot) * div + q % div
+            auto poly_ptr = [&](long long q) {
+                const long long p = ((q / a.div) * a.period + slot) * a.div + q % a.div;
+                return a.data + ((size_t)p << a.log_n) + (size_t)row * 256;
+            };
+            auto issue_data = [&](long long q) {
+                const u64 *src = poly_ptr(q);
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                {
+                    cp_async16(srow + 2 * (t + 16 * j), src + 2 * (t + 16 * j));
+                }
+            };
+            issue_data(q0);
+            cp_async_commit();
+            if (t < 15)
+            {
+                const int lvl = t == 0 ? 0 : (t < 3 ? 1 : (t < 7 ? 2 : 3));
+                const size_t idx = (ra << lvl) + (t - ((1 << lvl) - 1));
+                reinterpret_cast<double *>(tw1)[t] = f.tw(idx);
+            }
+            {
+                const double *g1 = f.tab + 128 * ra + 8 * t, *g2 = f.tab + 64 * ra + 4 * t, *g4 = f.tab + 32 * ra + 2 * t;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                {
+                    tws[u * FT] = make_double2(__ldg(g1 + 2 * u), __ldg(g1 + 2 * u + 1));
+                }
+                tws[4 * FT] = make_double2(__ldg(g2), __ldg(g2 + 1));
+                tws[5 * FT] = make_double2(__ldg(g2 + 2), __ldg(g2 + 3));
+                tws[6 * FT] = make_double2(__ldg(g4), __ldg(g4 + 1));
+                tws[7 * FT] = make_double2(__ldg(f.tab + 16 * ra + t), 0.0);
+            }
+            for (long long q = q0; q < q1; q++)
+            {
+                double x[16];
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp(); // a row is half a warp
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                {
+                    x[k] = srow[t + 16 * k];
+                }
+                f.phase_begin_fwd(x);
+                {
+                    const double2 w0 = tw1[0], w1 = tw1[1], w2 = tw1[2], w3 = tw1[3], w4 = tw1[4], w5 = tw1[5],
+                                  w6 = tw1[6], w7 = tw1[7];
+                    const double t8[1] = { w0.x };
+                    const double t4[2] = { w0.y, w1.x };
+                    const double t2[4] = { w1.y, w2.x, w2.y, w3.x };
+                    const double t1[8] = { w3.y, w4.x, w4.y, w5.x, w5.y, w6.x, w6.y, w7.x };
+                    ct_stage_tw<8>(f, x, t8);
+                    ct_stage_tw<4>(f, x, t4);
+                    f.phase_mid_fwd(x);
+                    ct_stage_tw<2>(f, x, t2);
+                    ct_stage_tw<1>(f, x, t1);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                {
+                    srow[t + 17 * k] = x[k];
+                }
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                {
+                    x[k] = srow[17 * t + k];
+                }
+                __syncwarp();
+                if (q + 1 < q1)
+                {
+                    issue_data(q + 1);
+                }
+                cp_async_commit();
+                f.phase_begin_fwd(x);
+                {
+                    const double2 a0 = tws[0 * FT], a1 = tws[1 * FT], a2 = tws[2 * FT], a3 = tws[3 * FT];
+                    const double2 b0 = tws[4 * FT], b1 = tws[5 * FT], c0 = tws[6 * FT], d0 = tws[7 * FT];
+                    const double t8[1] = { d0.x };
+                    const double t4[2] = { c0.x, c0.y };
+                    const double t2[4] = { b0.x, b0.y, b1.x, b1.y };
+                    const double t1[8] = { a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y };
+                    ct_stage_tw<8>(f, x, t8);
+                    ct_stage_tw<4>(f, x, t4);
+                    f.phase_mid_fwd(x);
+                    ct_stage_tw<2>(f, x, t2);
+                    ct_stage_tw<1>(f, x, t1);
+                }
+                ulonglong2 *out = reinterpret_cast<ulonglong2 *>(poly_ptr(q) + 16 * t);
+#pragma unroll
+                for (int k = 0; k < 16; k += 2)
+                {
+                    ulonglong2 v;
+                    v.x = f.out_fwd(x[k]);
+                    v.y = f.out_fwd(x[k + 1]);
+                    out[k >> 1] = v;
+                }
+            }
+        }
+
+        __global__ void __launch_bounds__(FT) ntt_fwd_pass_b_grouped(NttArgs a, long long seq_len)
+        {
+            extern __shared__ __align__(16) unsigned char grp_smem[];
+            const long long q0 = (long long)blockIdx.x * GS;
+            const long long q1 = q0 + GS < seq_len ? q0 + GS : seq_len;
+            const int rb = blockIdx.y;
+            const long long slot = blockIdx.z;
+            const int limb = a.limb_ids[slot];
+            const LimbConst lc = a.limb[limb];
+            if (lc.fp_class == 1)
+            {
+                const FpField<false> f(a, limb, lc);
+                fwd_pass_b_grouped_fp<false>(f, a, slot, q0, q1, rb, grp_smem);
+            }
+            else if (lc.fp_class == 2)
+            {
+                const FpField<true> f(a, limb, lc);
+                fwd_pass_b_grouped_fp<true>(f, a, slot, q0, q1, rb, grp_smem);
+            }
+            else
+            {
+                const IntField f(a, limb, lc);
+                const int t = threadIdx.x & 15, r = threadIdx.x >> 4;
+                const int R = 1 << (a.log_n - 8);
+                const int row = rb * FR + r;
+                for (long long q = q0; q < q1; q++)
+                {
+                    const long long p = ((q / a.div) * a.period + slot) * a.div + q % a.div;
+                    u64 *base = a.data + ((size_t)p << a.log_n) + (size_t)row * 256;
+                    __syncthreads(); // the transpose rows are reused by the next polynomial
+                    fwd_pass_b_body(f, base, reinterpret_cast<u64 *>(grp_smem) + r * ROW_PAD, t, (size_t)R + row);
+                }
+            }
+        }
+
         template <int LOGR>
         void launch_fwd(const NttArgs &a, cudaStream_t s, bool do_a = true, bool do_b = true)
         {
@@ -877,8 +1037,23 @@ namespace moai
             }
             if (do_b)
             {
-                const long long ctas_b = a.count * ((1 << LOGR) / ROWS);
-                ntt_fwd_pass_b<<<(unsigned)ctas_b, ROWS * 16, 0, s>>>(a);
+                // polynomials sharing a prime: count / period of them per limb slot
+                const long long seq_len = a.count / a.period;
+                static const bool grouped_on = [] {
+                    const char *e = getenv("MOAI_NTT_GROUPED");
+                    return !e || atoi(e) != 0;
+                }();
+                if (grouped_on && !a.grp_size && a.count % ((long long)a.period * a.div) == 0 && seq_len >= 4 &&
+                    a.period <= 65535)
+                {
+                    dim3 grid((unsigned)((seq_len + GS - 1) / GS), (unsigned)((1 << LOGR) / FR), (unsigned)a.period);
+                    ntt_fwd_pass_b_grouped<<<grid, FT, GROUPED_SMEM, s>>>(a, seq_len);
+                }
+                else
+                {
+                    const long long ctas_b = a.count * ((1 << LOGR) / ROWS);
+                    ntt_fwd_pass_b<<<(unsigned)ctas_b, ROWS * 16, 0, s>>>(a);
+                }
             }
         }
 

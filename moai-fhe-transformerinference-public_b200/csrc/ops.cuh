@@ -65,6 +65,16 @@ namespace moai
     void ct_pt_matmul_scalar(Context *c, const u64 *X, const double *h_W, int K, int C, int limbs, double scale,
                              u64 *out);
 
+    // tcgen05 (5th-generation tensor core) version of the byte-plane GEMM (csrc/matmul_tc5.cu)
+    size_t tc5_packed_weight_bytes(int K, int C, int limbs, int np);
+    void tc5_pack_weights(Context *c, const double *dW, unsigned char *Bp, int K, int C, int limbs, int np, double scale);
+    void tc5_gemm(Context *c, const u64 *X, const unsigned char *Bp, u64 *Y, int K, int C_total, int c0, int cn, int np,
+                  int limbs, int pl_first, int pl_count, cudaStream_t stream);
+
+    // the same module with HOST buffers: upload, tensor-core GEMM and download pipelined per (polynomial, limb) slice
+    void ct_pt_matmul_scalar_host(Context *c, const u64 *h_X, const double *h_W, int K, int C, int limbs, double scale,
+                                  u64 *h_out);
+
     // CKKSEncoder::encode(vector) on the device; values: DEVICE [count][n_vals] complex (re, im)
     void encode_vector(Context *c, const double *d_values, long long count, int n_vals, double scale, int limbs,
                        u64 *out);

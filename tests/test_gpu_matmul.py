@@ -95,3 +95,18 @@ def test_matmul_bad_dimensions(pkg, backend_small, oracle_small):
     X = pkg.to_device(rand_cts(o, np.random.default_rng(0), 3, 2))
     with pytest.raises(pkg.MoaiError):
         be.ct_pt_matrix_mul_wo_pre(X, np.zeros((4, 2)), 2.0 ** 30)   # "bad dimensions of X or W"
+
+
+def test_matmul_host_entry_matches_device_entry(pkg, backend_moai, oracle_moai):
+    """moai_ct_pt_matrix_mul_wo_pre_host (pipelined upload / GEMM / download) returns the same residues
+    as the device-pointer call."""
+    import torch
+    o, be = oracle_moai, backend_moai
+    rng = np.random.default_rng(77)
+    K, C, limbs, scale = 40, 33, 3, 2.0 ** 46
+    X = rand_cts(o, rng, K, limbs)
+    W = rng.normal(size=(K, C)) * 0.04
+    dev = pkg.to_host(be.ct_pt_matrix_mul_wo_pre(pkg.to_device(X), W, scale))
+    hX = torch.from_numpy(X.view(np.int64)).pin_memory()
+    host = be.ct_pt_matrix_mul_wo_pre_host(hX, W, scale).numpy().view(np.uint64)
+    assert (host == dev).all()
