@@ -317,7 +317,7 @@ def run_gpu(args):
                 "e2e": {"value": e2e_value, "unit": "s/input", "h2d_bytes_per_step": int(hX.numel() * 8),
                         "d2h_bytes_per_step": int(hOut.numel() * 8)},
                 "gpu_launches": int(launches),
-                "roofline": {"kernel": "k_ctpt_gemm_imma (two launches per step: 7- and 6-byte-plane limbs)",
+                "roofline": {"kernel": "k_ctpt_gemm_tc5 (tcgen05.mma kind::i8; two launches per step: 7- and 6-byte-plane limbs)",
                              "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": achieved / peak if peak else None, "traffic": traffic,
                              "peak_source": peak_src, "kernel_ms": gemm_avg_ms,
@@ -326,9 +326,10 @@ def run_gpu(args):
                              "gmacs_per_s": macs / (gemm_avg_ms * 1e-3) / 1e9 if gemm_avg_ms > 0 else None,
                              "hbm_achieved_gbs": hbm_achieved, "hbm_peak_gbs": hbm_peak,
                              "hbm_frac": hbm_achieved / hbm_peak if hbm_peak else None,
-                             "note": "int8 operations on the legacy mma.sync path (IMMA.16832.U8), whose own ceiling "
-                                     "measured with tools/microbench_mma.cu is 1143 TOP/s = 1/4 of the tcgen05 int8 "
-                                     "peak; `achieved` counts 2 * NP^2 int8 ops per modular MAC; see DESIGN.md section 5"},
+                             "note": "int8 byte-plane GEMM on the 5th-generation tensor cores (UTCIMMA, accumulators and A "
+                                     "planes in TMEM); `achieved` counts 2 * NP^2 int8 ops per modular MAC; "
+                                     "MOAI_GEMM_VARIANT=3 selects the legacy mma.sync version, 0 the CUDA-core one; "
+                                     "see DESIGN.md section 5.4"},
                 }
         if cb is not None:
             line["cpu_baseline"] = cb

@@ -606,8 +606,10 @@ namespace moai
         {
             narrow = narrow && (c->q[l] >> 52) == 0;
         }
-        // 3 (default): int8 byte-plane GEMM on the tensor cores; 0: IMAD 128-bit; 1, 2: IMAD 26-bit split
-        static const int variant = getenv("MOAI_GEMM_VARIANT") ? atoi(getenv("MOAI_GEMM_VARIANT")) : 3;
+        // 4 (default): int8 byte-plane GEMM, tcgen05.mma with TMEM accumulators (csrc/matmul_tc5.cu);
+        // 3: the same GEMM on the legacy mma.sync path; 0: IMAD 128-bit; 1, 2: IMAD 26-bit split
+        static const int variant_env = getenv("MOAI_GEMM_VARIANT") ? atoi(getenv("MOAI_GEMM_VARIANT")) : 4;
+        const int variant = (variant_env == 4 && n < 128) ? 3 : variant_env;
         bool bytes7 = n >= (size_t)IM_TILE_M; // every limb prime below 2^56 -> at most 7 byte planes
         for (int l = 0; l < limbs; l++)
         {
@@ -732,17 +734,28 @@ namespace moai
         }
         const int Kp = (K + 31) / 32 * 32, Cp = (C + IM_TILE_N - 1) / IM_TILE_N * IM_TILE_N, np = 7;
         const size_t ct_words = (size_t)2 * limbs * n;
+        static const bool use_tc5 = !(getenv("MOAI_GEMM_VARIANT") && atoi(getenv("MOAI_GEMM_VARIANT")) != 4);
+        const bool tc5 = use_tc5 && n >= 128;
         {
             Scratch dW(kc * sizeof(double), c->stream);
-            Scratch dWp((size_t)limbs * (Kp / 32) * (Cp / 8) * np * 32 * sizeof(uint2), c->stream);
+            Scratch dWp(tc5 ? tc5_packed_weight_bytes(K, C, limbs, np)
+                            : (size_t)limbs * (Kp / 32) * (Cp / 8) * np * 32 * sizeof(uint2),
+                        c->stream);
             Scratch dX((size_t)K * ct_words * sizeof(u64), c->stream);
             Scratch Y((size_t)C * ct_words * sizeof(u64), c->stream);
             Scratch dOut((size_t)C * 2 * (limbs - 1) * n * sizeof(u64), c->stream);
             MOAI_CUDA_CHECK(cudaMemcpyAsync(dW.p, h_W, kc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-            const long long pack_threads = (long long)limbs * (Kp / 32) * (Cp / 8) * 32;
-            k_pack_weights<<<(unsigned)((pack_threads + 255) / 256), 256, 0, c->stream>>>(
-                dW.as<double>(), dWp.as<uint2>(), K, C, Kp, Cp, limbs, np, scale, c->d_limb);
-            c->launches += 1;
+            if (tc5)
+            {
+                tc5_pack_weights(c, dW.as<double>(), dWp.as<unsigned char>(), K, C, limbs, np, scale);
+            }
+            else
+            {
+                const long long pack_threads = (long long)limbs * (Kp / 32) * (Cp / 8) * 32;
+                k_pack_weights<<<(unsigned)((pack_threads + 255) / 256), 256, 0, c->stream>>>(
+                    dW.as<double>(), dWp.as<uint2>(), K, C, Kp, Cp, limbs, np, scale, c->d_limb);
+                c->launches += 1;
+            }
             // the buffers come from the stream-ordered arena of c->stream: order the side streams after it
             cudaEvent_t ready;
             MOAI_CUDA_CHECK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
@@ -761,8 +774,16 @@ namespace moai
                     MOAI_CUDA_CHECK(cudaEventRecord(landed[order], s_in));
                     MOAI_CUDA_CHECK(cudaStreamWaitEvent(c->stream, landed[order], 0));
                     PhaseTimer pt(c, "ctpt_gemm");
-                    launch_imma(c, dX.as<u64>(), dWp.as<uint2>(), Y.as<u64>(), K, C, Kp, Cp, np, limbs, p * limbs + l, 1,
-                                c->stream);
+                    if (tc5)
+                    {
+                        tc5_gemm(c, dX.as<u64>(), dWp.as<unsigned char>(), Y.as<u64>(), K, C, 0, C, np, limbs,
+                                 p * limbs + l, 1, c->stream);
+                    }
+                    else
+                    {
+                        launch_imma(c, dX.as<u64>(), dWp.as<uint2>(), Y.as<u64>(), K, C, Kp, Cp, np, limbs, p * limbs + l,
+                                    1, c->stream);
+                    }
                 }
             }
             const int out_chunk = 96;
