@@ -90,7 +90,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -238,11 +238,13 @@ def run_gpu(args):
         # the reference-facing call with HOST buffers: upload, GEMM, rescale and download inside the library
         be.ct_pt_matrix_mul_wo_pre_host(hX, W, SCALE, out=hOut)
 
+    # clocks / throttle reasons are sampled from the warm-up to the end of the end-to-end loop (the timed
+    # regions are tens of milliseconds: a sampler confined to them would see no sample at all)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step_resident()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     l0 = be.launch_count()
     be.profile(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -256,7 +258,6 @@ def run_gpu(args):
     launches = be.launch_count() - l0
     gemm_ms, gemm_cnt = be.profile_get("ctpt_gemm")
     be.profile(False)
-    clocks = sampler.stop()
 
     # end-to-end through the public call with host buffers
     for _ in range(max(1, min(args.warmup, 2))):
@@ -268,6 +269,7 @@ def run_gpu(args):
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
+    clocks = sampler.stop()
 
     t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=device)
     if dist is not None:
