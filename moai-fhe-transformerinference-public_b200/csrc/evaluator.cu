@@ -448,15 +448,44 @@ namespace moai
         {
             const long long nb = std::min(chunk, a.batch - b0);
             Hoisted h = hoist(view(a, b0, nb));
+            const u64 *extp = reinterpret_cast<const u64 *>(h.ext->p);
+            std::vector<size_t> todo;
             for (size_t i = 0; i < steps.size(); i++)
             {
                 if (steps[i] != 0)
                 {
-                    const uint32_t elt = c->elt_from_step(steps[i]);
-                    const KeyRef *fk = k.fast(elt, a.limbs);
-                    moai::rotate_hoisted(c, h.src.d, reinterpret_cast<const u64 *>(h.ext->p), nb, a.limbs, elt, fk->p,
-                                         fk->key_kl, out[i].d + (size_t)b0 * 2 * a.limbs * n());
+                    todo.push_back(i);
                 }
+            }
+            size_t g0 = 0;
+            if (ks_multi_enabled(c, a.limbs))
+            {
+                // KSM_R rotations share one pass over the extended digits
+                for (; g0 + KSM_R <= todo.size(); g0 += KSM_R)
+                {
+                    uint32_t elts[KSM_R];
+                    const u64 *kp[KSM_R];
+                    int kkl[KSM_R];
+                    u64 *outs[KSM_R];
+                    for (int r = 0; r < KSM_R; r++)
+                    {
+                        const size_t i = todo[g0 + r];
+                        elts[r] = c->elt_from_step(steps[i]);
+                        const KeyRef *fk = k.fast(elts[r], a.limbs);
+                        kp[r] = fk->p;
+                        kkl[r] = fk->key_kl;
+                        outs[r] = out[i].d + (size_t)b0 * 2 * a.limbs * n();
+                    }
+                    rotate_hoisted_multi(c, h.src.d, extp, nb, a.limbs, elts, kp, kkl, outs);
+                }
+            }
+            for (; g0 < todo.size(); g0++)
+            {
+                const size_t i = todo[g0];
+                const uint32_t elt = c->elt_from_step(steps[i]);
+                const KeyRef *fk = k.fast(elt, a.limbs);
+                moai::rotate_hoisted(c, h.src.d, extp, nb, a.limbs, elt, fk->p, fk->key_kl,
+                                     out[i].d + (size_t)b0 * 2 * a.limbs * n());
             }
         }
         return out;

@@ -937,6 +937,58 @@ namespace moai
         apply_galois_ntt(c, tmp.as<u64>(), out, batch * 2 * limbs, elt);
     }
 
+    // KSM_R hoisted rotations of the same ciphertexts in one pass over the extended digits (FP64 inner
+    // products, csrc/ntt.cu); each result then gets its own mod-down and permutation.
+    void rotate_hoisted_multi(Context *c, const u64 *ct, const u64 *ext, long long batch, int limbs,
+                              const uint32_t *elts, const u64 *const *ksk_pre, const int *key_kl, u64 *const *outs)
+    {
+        const size_t n = c->n;
+        const int rns = limbs + 1;
+        const int *ids_ks = c->d_ids_ks + (size_t)limbs * (c->kl + 1);
+        const size_t acc_words = (size_t)batch * 2 * rns * n;
+        Scratch acc(acc_words * KSM_R * sizeof(u64), c->stream);
+        u64 *accp[KSM_R];
+        for (int r = 0; r < KSM_R; r++)
+        {
+            accp[r] = acc.as<u64>() + acc_words * r;
+            MOAI_REQUIRE(key_kl[r] >= limbs + 1 && key_kl[r] <= c->kl, "key does not cover this level");
+        }
+        ks_mac_multi(c, ext, batch, limbs, ksk_pre, key_kl, accp);
+        for (int I = 0; I < rns; I++)
+        {
+            const int prime = I == limbs ? c->kl - 1 : I;
+            if (c->h_limb[prime].fp_class != 0)
+            {
+                continue;
+            }
+            for (int r = 0; r < KSM_R; r++) // integer-path modulus (the special prime)
+            {
+                dim3 grid((unsigned)batch, 1u, (unsigned)((n / 2) / EW_THREADS));
+                k_ks_mac<<<grid, EW_THREADS, 0, c->stream>>>(reinterpret_cast<const ulonglong2 *>(ext),
+                                                             reinterpret_cast<const ulonglong2 *>(ksk_pre[r]),
+                                                             reinterpret_cast<ulonglong2 *>(accp[r]), batch, c->log_n - 1,
+                                                             limbs, key_kl[r], ids_ks, c->d_limb, c->d_two64, I);
+                c->launches += 1;
+            }
+            MOAI_CUDA_CHECK(cudaGetLastError());
+        }
+        Scratch tmp((size_t)batch * 2 * limbs * n * sizeof(u64), c->stream);
+        for (int r = 0; r < KSM_R; r++)
+        {
+            divide_round_last(c, accp[r], batch * 2, rns, c->kl - 1, ct, tmp.as<u64>(), true);
+            apply_galois_ntt(c, tmp.as<u64>(), outs[r], batch * 2 * limbs, elts[r]);
+        }
+    }
+
+    bool ks_multi_enabled(Context *c, int limbs)
+    {
+        static const bool multi = [] {
+            const char *e = getenv("MOAI_KSM_MULTI");
+            return !e || atoi(e) != 0;
+        }();
+        return multi && ks_can_fuse(c, limbs);
+    }
+
     // K' = sigma_elt^-1(K) restricted to `max_limbs` digits / data limbs (+ the special prime):
     // in  [kl-1][2][kl][n] (SEAL layout, S/kswitchkeys.h:335-340), out [max_limbs][2][max_limbs+1][n].
     // pre_permute = false only truncates.
