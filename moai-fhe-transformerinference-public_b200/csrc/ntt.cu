@@ -1045,9 +1045,18 @@ namespace moai
             int limbs, rns, log_n;
         };
 
+        // Streams of one digit J for a CTA: the extended digit and key[J][0], key[J][1] of each of the R keys,
+        // 256 x 16 bytes each.  They travel through a KSM_STAGES-deep cp.async ring of thread-private
+        // 16-byte slots (a thread consumes exactly what it copied: no CTA barrier), so the loads of the next
+        // digits are in flight while the current one is multiplied: the kernel was latency-bound on its
+        // loads (ncu: long_scoreboard 13 warps per issue, FP64 pipe 49 %) with direct global loads.
+        constexpr int KSM_STAGES = 3;
+        constexpr int KSM_STREAMS = 1 + 2 * KSM_R;
+        constexpr int KSM_SMEM = KSM_STAGES * KSM_STREAMS * 256 * 16;
+
         template <bool WIDE, int R>
         __device__ __forceinline__ void ks_mac_multi_body(const FpField<WIDE> &f, const KsMacMultiArgs &a, int I, long long b,
-                                                          long long within)
+                                                          long long within, unsigned char *smem)
         {
             const int log_n2 = a.log_n - 1;
             const long long n2 = (long long)1 << log_n2;
@@ -1062,69 +1071,67 @@ namespace moai
                 kpoly[r] = (long long)a.key_kl[r] * n2;  // key[J][0] -> key[J][1]
                 kstep[r] = 2 * kpoly[r];                 // key[J] -> key[J + 1]
             }
+            ulonglong2 *slot = reinterpret_cast<ulonglong2 *>(smem) + threadIdx.x; // stream q of stage s: slot[(s * STREAMS + q) * 256]
+            auto issue = [&](int J) {
+                ulonglong2 *dst = slot + (size_t)(J % KSM_STAGES) * KSM_STREAMS * 256;
+                cp_async16(dst, e + ((long long)J << log_n2));
+#pragma unroll
+                for (int r = 0; r < R; r++)
+                {
+                    const ulonglong2 *p = kp[r] + (long long)J * kstep[r];
+                    cp_async16(dst + (1 + 2 * r) * 256, p);
+                    cp_async16(dst + (2 + 2 * r) * 256, p + kpoly[r]);
+                }
+            };
+#pragma unroll
+            for (int J = 0; J < KSM_STAGES - 1; J++)
+            {
+                if (J < a.limbs)
+                {
+                    issue(J);
+                }
+                cp_async_commit();
+            }
             double acc[R][4];
 #pragma unroll
             for (int r = 0; r < R; r++)
             {
                 acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0;
             }
-            auto mac = [&](const ulonglong2 &v, const ulonglong2 (&k0)[R], const ulonglong2 (&k1)[R]) {
+            const int red_every = WIDE ? 2 : 8; // |term| <= 1.125 p (51-bit class) / 0.65 p (46-bit class)
+            for (int J = 0; J < a.limbs; J++)
+            {
+                asm volatile("cp.async.wait_group %0;" ::"n"(KSM_STAGES - 2) : "memory"); // digit J has landed
+                const ulonglong2 *src = slot + (size_t)(J % KSM_STAGES) * KSM_STREAMS * 256;
+                const ulonglong2 v = src[0];
                 const double ex = f.in_outer(v.x), ey = f.in_outer(v.y);
 #pragma unroll
                 for (int r = 0; r < R; r++)
                 {
-                    acc[r][0] = __dadd_rn(acc[r][0], f.mul_lazy(ex, f.in_outer(k0[r].x)));
-                    acc[r][1] = __dadd_rn(acc[r][1], f.mul_lazy(ey, f.in_outer(k0[r].y)));
-                    acc[r][2] = __dadd_rn(acc[r][2], f.mul_lazy(ex, f.in_outer(k1[r].x)));
-                    acc[r][3] = __dadd_rn(acc[r][3], f.mul_lazy(ey, f.in_outer(k1[r].y)));
+                    const ulonglong2 k0 = src[(1 + 2 * r) * 256], k1 = src[(2 + 2 * r) * 256];
+                    acc[r][0] = __dadd_rn(acc[r][0], f.mul_lazy(ex, f.in_outer(k0.x)));
+                    acc[r][1] = __dadd_rn(acc[r][1], f.mul_lazy(ey, f.in_outer(k0.y)));
+                    acc[r][2] = __dadd_rn(acc[r][2], f.mul_lazy(ex, f.in_outer(k1.x)));
+                    acc[r][3] = __dadd_rn(acc[r][3], f.mul_lazy(ey, f.in_outer(k1.y)));
                 }
-            };
-            auto reduce_all = [&]() {
-#pragma unroll
-                for (int r = 0; r < R; r++)
+                // digit J + STAGES - 1 lands in the slots digit J - 1 was read from (same thread, program order)
+                if (J + KSM_STAGES - 1 < a.limbs)
+                {
+                    issue(J + KSM_STAGES - 1);
+                }
+                cp_async_commit();
+                if ((J + 1) % red_every == 0)
                 {
 #pragma unroll
-                    for (int q = 0; q < 4; q++)
+                    for (int r = 0; r < R; r++)
                     {
-                        acc[r][q] = f.red(acc[r][q]);
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                        {
+                            acc[r][q] = f.red(acc[r][q]);
+                        }
                     }
                 }
-            };
-            int J = 0;
-            for (; J + 1 < a.limbs; J += 2)
-            {
-                ulonglong2 va, vb, ka0[R], ka1[R], kb0[R], kb1[R];
-                va = e[(long long)J << log_n2];
-                vb = e[(long long)(J + 1) << log_n2];
-#pragma unroll
-                for (int r = 0; r < R; r++)
-                {
-                    const ulonglong2 *p = kp[r] + (long long)J * kstep[r];
-                    ka0[r] = __ldg(p);
-                    ka1[r] = __ldg(p + kpoly[r]);
-                    kb0[r] = __ldg(p + kstep[r]);
-                    kb1[r] = __ldg(p + kstep[r] + kpoly[r]);
-                }
-                mac(va, ka0, ka1);
-                mac(vb, kb0, kb1);
-                // |term| <= 1.125 p (51-bit class): reduce after every pair; 46-bit class: every 8 digits
-                if (WIDE || (J & 6) == 6)
-                {
-                    reduce_all();
-                }
-            }
-            if (J < a.limbs)
-            {
-                ulonglong2 va, ka0[R], ka1[R];
-                va = e[(long long)J << log_n2];
-#pragma unroll
-                for (int r = 0; r < R; r++)
-                {
-                    const ulonglong2 *p = kp[r] + (long long)J * kstep[r];
-                    ka0[r] = __ldg(p);
-                    ka1[r] = __ldg(p + kpoly[r]);
-                }
-                mac(va, ka0, ka1);
             }
 #pragma unroll
             for (int r = 0; r < R; r++)
@@ -1142,6 +1149,7 @@ namespace moai
 
         __global__ void __launch_bounds__(256) ks_mac_multi_kernel(KsMacMultiArgs a, NttArgs na)
         {
+            extern __shared__ __align__(16) unsigned char ksm_smem[];
             // grid: x = ciphertext (fastest: CTAs sharing a key tile run together), y = I, z = coefficient block
             const long long b = blockIdx.x;
             const int I = blockIdx.y;
@@ -1151,12 +1159,12 @@ namespace moai
             if (lc.fp_class == 1)
             {
                 const FpField<false> f(na, limb, lc);
-                ks_mac_multi_body<false, KSM_R>(f, a, I, b, within);
+                ks_mac_multi_body<false, KSM_R>(f, a, I, b, within, ksm_smem);
             }
             else if (lc.fp_class == 2)
             {
                 const FpField<true> f(na, limb, lc);
-                ks_mac_multi_body<true, KSM_R>(f, a, I, b, within);
+                ks_mac_multi_body<true, KSM_R>(f, a, I, b, within, ksm_smem);
             }
         }
 
@@ -1248,7 +1256,10 @@ namespace moai
         a.log_n = c->log_n;
         NttArgs na{ nullptr, c->d_fwd, c->d_fwd_fp, c->d_limb, nullptr, 1, 1, c->log_n, 0 };
         dim3 grid((unsigned)batch, (unsigned)(limbs + 1), (unsigned)((c->n / 2) / 256));
-        ks_mac_multi_kernel<<<grid, 256, 0, c->stream>>>(a, na);
+        static const cudaError_t attr =
+            cudaFuncSetAttribute(ks_mac_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KSM_SMEM);
+        (void)attr;
+        ks_mac_multi_kernel<<<grid, 256, KSM_SMEM, c->stream>>>(a, na);
         c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
     }
