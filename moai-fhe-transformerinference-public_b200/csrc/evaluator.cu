@@ -460,14 +460,15 @@ namespace moai
             size_t g0 = 0;
             if (ks_multi_enabled(c, a.limbs))
             {
-                // KSM_R rotations share one pass over the extended digits
-                for (; g0 + KSM_R <= todo.size(); g0 += KSM_R)
+                // up to KSM_R rotations share one pass over the extended digits
+                for (; g0 < todo.size(); g0 += KSM_R)
                 {
+                    const int cnt = (int)std::min<size_t>(KSM_R, todo.size() - g0);
                     uint32_t elts[KSM_R];
                     const u64 *kp[KSM_R];
                     int kkl[KSM_R];
                     u64 *outs[KSM_R];
-                    for (int r = 0; r < KSM_R; r++)
+                    for (int r = 0; r < cnt; r++)
                     {
                         const size_t i = todo[g0 + r];
                         elts[r] = c->elt_from_step(steps[i]);
@@ -476,7 +477,7 @@ namespace moai
                         kkl[r] = fk->key_kl;
                         outs[r] = out[i].d + (size_t)b0 * 2 * a.limbs * n();
                     }
-                    rotate_hoisted_multi(c, h.src.d, extp, nb, a.limbs, elts, kp, kkl, outs);
+                    rotate_hoisted_multi(c, h.src.d, extp, nb, a.limbs, cnt, elts, kp, kkl, outs);
                 }
             }
             for (; g0 < todo.size(); g0++)

@@ -1051,8 +1051,10 @@ namespace moai
         // digits are in flight while the current one is multiplied: the kernel was latency-bound on its
         // loads (ncu: long_scoreboard 13 warps per issue, FP64 pipe 49 %) with direct global loads.
         constexpr int KSM_STAGES = 3;
-        constexpr int KSM_STREAMS = 1 + 2 * KSM_R;
-        constexpr int KSM_SMEM = KSM_STAGES * KSM_STREAMS * 256 * 16;
+        __host__ __device__ constexpr int ksm_smem_bytes(int r)
+        {
+            return KSM_STAGES * (1 + 2 * r) * 256 * 16;
+        }
 
         template <bool WIDE, int R>
         __device__ __forceinline__ void ks_mac_multi_body(const FpField<WIDE> &f, const KsMacMultiArgs &a, int I, long long b,
@@ -1071,6 +1073,7 @@ namespace moai
                 kpoly[r] = (long long)a.key_kl[r] * n2;  // key[J][0] -> key[J][1]
                 kstep[r] = 2 * kpoly[r];                 // key[J] -> key[J + 1]
             }
+            constexpr int KSM_STREAMS = 1 + 2 * R;
             ulonglong2 *slot = reinterpret_cast<ulonglong2 *>(smem) + threadIdx.x; // stream q of stage s: slot[(s * STREAMS + q) * 256]
             auto issue = [&](int J) {
                 ulonglong2 *dst = slot + (size_t)(J % KSM_STAGES) * KSM_STREAMS * 256;
@@ -1147,6 +1150,7 @@ namespace moai
             }
         }
 
+        template <int R>
         __global__ void __launch_bounds__(256) ks_mac_multi_kernel(KsMacMultiArgs a, NttArgs na)
         {
             extern __shared__ __align__(16) unsigned char ksm_smem[];
@@ -1159,12 +1163,12 @@ namespace moai
             if (lc.fp_class == 1)
             {
                 const FpField<false> f(na, limb, lc);
-                ks_mac_multi_body<false, KSM_R>(f, a, I, b, within, ksm_smem);
+                ks_mac_multi_body<false, R>(f, a, I, b, within, ksm_smem);
             }
             else if (lc.fp_class == 2)
             {
                 const FpField<true> f(na, limb, lc);
-                ks_mac_multi_body<true, KSM_R>(f, a, I, b, within, ksm_smem);
+                ks_mac_multi_body<true, R>(f, a, I, b, within, ksm_smem);
             }
         }
 
@@ -1238,16 +1242,29 @@ namespace moai
         MOAI_CUDA_CHECK(cudaGetLastError());
     }
 
-    void ks_mac_multi(Context *c, const u64 *ext, long long batch, int limbs, const u64 *const *ksk, const int *key_kl,
-                      u64 *const *acc)
+    namespace
     {
+        template <int R>
+        void launch_ks_mac_multi(const KsMacMultiArgs &a, const NttArgs &na, dim3 grid, cudaStream_t s)
+        {
+            static const cudaError_t attr =
+                cudaFuncSetAttribute(ks_mac_multi_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, ksm_smem_bytes(R));
+            (void)attr;
+            ks_mac_multi_kernel<R><<<grid, 256, ksm_smem_bytes(R), s>>>(a, na);
+        }
+    } // namespace
+
+    void ks_mac_multi(Context *c, const u64 *ext, long long batch, int limbs, int n_keys, const u64 *const *ksk,
+                      const int *key_kl, u64 *const *acc)
+    {
+        MOAI_REQUIRE(n_keys >= 1 && n_keys <= KSM_R, "too many keys for one multi-key inner product");
         KsMacMultiArgs a;
         a.ext = ext;
         for (int r = 0; r < KSM_R; r++)
         {
-            a.ksk[r] = ksk[r];
-            a.acc[r] = acc[r];
-            a.key_kl[r] = key_kl[r];
+            a.ksk[r] = r < n_keys ? ksk[r] : nullptr;
+            a.acc[r] = r < n_keys ? acc[r] : nullptr;
+            a.key_kl[r] = r < n_keys ? key_kl[r] : 0;
         }
         a.limb = c->d_limb;
         a.ids_ks = c->d_ids_ks + (size_t)limbs * (c->kl + 1);
@@ -1256,10 +1273,13 @@ namespace moai
         a.log_n = c->log_n;
         NttArgs na{ nullptr, c->d_fwd, c->d_fwd_fp, c->d_limb, nullptr, 1, 1, c->log_n, 0 };
         dim3 grid((unsigned)batch, (unsigned)(limbs + 1), (unsigned)((c->n / 2) / 256));
-        static const cudaError_t attr =
-            cudaFuncSetAttribute(ks_mac_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KSM_SMEM);
-        (void)attr;
-        ks_mac_multi_kernel<<<grid, 256, KSM_SMEM, c->stream>>>(a, na);
+        switch (n_keys)
+        {
+        case 1: launch_ks_mac_multi<1>(a, na, grid, c->stream); break;
+        case 2: launch_ks_mac_multi<2>(a, na, grid, c->stream); break;
+        case 3: launch_ks_mac_multi<3>(a, na, grid, c->stream); break;
+        default: launch_ks_mac_multi<4>(a, na, grid, c->stream); break;
+        }
         c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
     }

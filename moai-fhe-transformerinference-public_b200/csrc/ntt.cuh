@@ -74,12 +74,12 @@ namespace moai
     // data + g * grp_stride * n, all modulo the single prime *d_limb_id
     void ntt_forward_pass_b_strided(Context *c, u64 *data, long long groups, long long grp_size, long long grp_stride,
                                     const int *d_limb_id);
-    // Hoisted rotations: inner products of one set of extended digits (NTT form) with exactly KSM_R keys
+    // Hoisted rotations: inner products of one set of extended digits (NTT form) with up to KSM_R keys
     // in one pass on the FP64 pipe; acc[r][batch][2][limbs+1][n] receives canonical residues for every
     // FP64-path modulus (integer-path moduli are left untouched).
-    constexpr int KSM_R = 2;
-    void ks_mac_multi(Context *c, const u64 *ext, long long batch, int limbs, const u64 *const *ksk, const int *key_kl,
-                      u64 *const *acc);
+    constexpr int KSM_R = 4;
+    void ks_mac_multi(Context *c, const u64 *ext, long long batch, int limbs, int n_keys, const u64 *const *ksk,
+                      const int *key_kl, u64 *const *acc);
     // Fused key-switch kernel (csrc/ntt.cu): pass B of the digit-extension NTT + inner product with
     // the evk for every FP64-path modulus.  mid = pass-A output [batch][limbs+1][limbs][n];
     // acc[batch][2][limbs+1][n] receives canonical residues for those moduli (integer-path moduli

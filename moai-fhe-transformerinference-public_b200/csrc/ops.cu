@@ -937,23 +937,24 @@ namespace moai
         apply_galois_ntt(c, tmp.as<u64>(), out, batch * 2 * limbs, elt);
     }
 
-    // KSM_R hoisted rotations of the same ciphertexts in one pass over the extended digits (FP64 inner
+    // Up to KSM_R hoisted rotations of the same ciphertexts in one pass over the extended digits (FP64 inner
     // products, csrc/ntt.cu); each result then gets its own mod-down and permutation.
-    void rotate_hoisted_multi(Context *c, const u64 *ct, const u64 *ext, long long batch, int limbs,
+    void rotate_hoisted_multi(Context *c, const u64 *ct, const u64 *ext, long long batch, int limbs, int n_rot,
                               const uint32_t *elts, const u64 *const *ksk_pre, const int *key_kl, u64 *const *outs)
     {
+        MOAI_REQUIRE(n_rot >= 1 && n_rot <= KSM_R, "too many rotations for one multi-key pass");
         const size_t n = c->n;
         const int rns = limbs + 1;
         const int *ids_ks = c->d_ids_ks + (size_t)limbs * (c->kl + 1);
         const size_t acc_words = (size_t)batch * 2 * rns * n;
-        Scratch acc(acc_words * KSM_R * sizeof(u64), c->stream);
+        Scratch acc(acc_words * n_rot * sizeof(u64), c->stream);
         u64 *accp[KSM_R];
-        for (int r = 0; r < KSM_R; r++)
+        for (int r = 0; r < n_rot; r++)
         {
             accp[r] = acc.as<u64>() + acc_words * r;
             MOAI_REQUIRE(key_kl[r] >= limbs + 1 && key_kl[r] <= c->kl, "key does not cover this level");
         }
-        ks_mac_multi(c, ext, batch, limbs, ksk_pre, key_kl, accp);
+        ks_mac_multi(c, ext, batch, limbs, n_rot, ksk_pre, key_kl, accp);
         for (int I = 0; I < rns; I++)
         {
             const int prime = I == limbs ? c->kl - 1 : I;
@@ -961,7 +962,7 @@ namespace moai
             {
                 continue;
             }
-            for (int r = 0; r < KSM_R; r++) // integer-path modulus (the special prime)
+            for (int r = 0; r < n_rot; r++) // integer-path modulus (the special prime)
             {
                 dim3 grid((unsigned)batch, 1u, (unsigned)((n / 2) / EW_THREADS));
                 k_ks_mac<<<grid, EW_THREADS, 0, c->stream>>>(reinterpret_cast<const ulonglong2 *>(ext),
@@ -973,7 +974,7 @@ namespace moai
             MOAI_CUDA_CHECK(cudaGetLastError());
         }
         Scratch tmp((size_t)batch * 2 * limbs * n * sizeof(u64), c->stream);
-        for (int r = 0; r < KSM_R; r++)
+        for (int r = 0; r < n_rot; r++)
         {
             divide_round_last(c, accp[r], batch * 2, rns, c->kl - 1, ct, tmp.as<u64>(), true);
             apply_galois_ntt(c, tmp.as<u64>(), outs[r], batch * 2 * limbs, elts[r]);

@@ -59,9 +59,9 @@ namespace moai
                         const u64 *addend, bool addend_c0_only, u64 *out);
     void rotate_hoisted(Context *c, const u64 *ct, const u64 *ext, long long batch, int limbs, uint32_t elt,
                         const u64 *ksk_pre, int key_kl, u64 *out);
-    // exactly KSM_R (csrc/ntt.cuh) hoisted rotations in one pass over the extended digits
+    // up to KSM_R (csrc/ntt.cuh) hoisted rotations in one pass over the extended digits
     bool ks_multi_enabled(Context *c, int limbs);
-    void rotate_hoisted_multi(Context *c, const u64 *ct, const u64 *ext, long long batch, int limbs,
+    void rotate_hoisted_multi(Context *c, const u64 *ct, const u64 *ext, long long batch, int limbs, int n_rot,
                               const uint32_t *elts, const u64 *const *ksk_pre, const int *key_kl, u64 *const *outs);
     void key_prepare(Context *c, const u64 *in, uint32_t elt, int max_limbs, bool pre_permute, u64 *out);
 
