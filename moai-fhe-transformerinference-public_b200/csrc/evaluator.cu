@@ -405,18 +405,7 @@ namespace moai
     Ct Evaluator::rotate_fast(const Ct &a, uint32_t elt, const KeyRef &key) const
     {
         Ct r = alloc(a.batch, 2, a.limbs, a.scale);
-        const long long chunk = ks_chunk(c, a.limbs, a.batch, ks_ext_budget());
-        DevBuf ext((size_t)chunk * ks_ext_bytes_per_ct(c, a.limbs), c->stream);
-        const size_t per_ct = (size_t)2 * a.limbs * n();
-        for (long long b0 = 0; b0 < a.batch; b0 += chunk)
-        {
-            const long long nb = std::min(chunk, a.batch - b0);
-            const u64 *src = a.d + (size_t)b0 * per_ct;
-            ks_decompose(c, src + (size_t)a.limbs * n(), nb, a.limbs, reinterpret_cast<u64 *>(ext.p),
-                         (long long)per_ct);
-            moai::rotate_hoisted(c, src, reinterpret_cast<const u64 *>(ext.p), nb, a.limbs, elt, key.p, key.key_kl,
-                                 r.d + (size_t)b0 * per_ct);
-        }
+        rotate_prepermuted(c, a.d, a.batch, a.limbs, elt, key.p, key.key_kl, r.d);
         return r;
     }
 

@@ -196,33 +196,9 @@ namespace moai
         // ------------------------------------------------------------------ divide-and-round by the last limb
         // in:  [P][limbs_in][n] with the divisor limb last (prime index `last_id`), targets 0..limbs_in-2
         // step 1 (host): t[P][n] = INTT_last(in[.][limbs_in-1])
-        // step 2: u[P][limbs_in-1][n] = ((t + half) mod q_last) mod q_i + (q_i - half mod q_i)     (< 2 q_i)
-        __global__ void k_divround_expand(const ulonglong2 *__restrict__ t, ulonglong2 *__restrict__ u, long long total2,
-                                          int log_n2, int targets, int last_id, int kl,
-                                          const LimbConst *__restrict__ lcs, const u64 *__restrict__ half_mod)
-        {
-            long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; // over [P][targets][n/2]
-            if (i >= total2)
-            {
-                return;
-            }
-            const long long lp = i >> log_n2;
-            const int limb = (int)(lp % targets);
-            const long long p = lp / targets;
-            const long long within = i & (((long long)1 << log_n2) - 1);
-            const LimbConst lq = lcs[last_id];
-            const LimbConst lc = lcs[limb];
-            const u64 half = lq.q >> 1;
-            const u64 fix = lc.q - half_mod[(size_t)last_id * kl + limb];
-            ulonglong2 v = t[(p << log_n2) + within];
-            v.x = addmod(v.x, half, lq.q);
-            v.y = addmod(v.y, half, lq.q);
-            ulonglong2 r;
-            r.x = reduce64(v.x, lc) + fix;
-            r.y = reduce64(v.y, lc) + fix;
-            u[i] = r;
-        }
-
+        // step 2 (fused into the forward NTT's first pass, NttPrologue mode 2):
+        //         u[P][limbs_in-1][n] = ((t + half) mod q_last) mod q_i + (q_i - half mod q_i)     (< 2 q_i)
+        // step 3: u = NTT_i(u)
         // step 4: out[P][targets][n] = (in[P][limbs_in][n](limb i) - u) * q_last^-1 mod q_i  (+ addend)
         __global__ void k_divround_finish(const ulonglong2 *__restrict__ in, const ulonglong2 *__restrict__ u,
                                           const ulonglong2 *addend, ulonglong2 *out, // may alias each other
@@ -821,14 +797,16 @@ namespace moai
     // FP64-path moduli; integer-path moduli (the 58-bit special prime) finish with the plain pass B
     // and the integer inner-product kernel.  Same residues as ks_decompose + ks_mac_moddown.
     static void ks_fused(Context *c, const u64 *target, long long batch, int limbs, u64 *ext, const u64 *ksk,
-                         int key_kl, const u64 *addend, u64 *out)
+                         int key_kl, const u64 *addend, u64 *out, long long target_stride = 0,
+                         bool addend_c0_only = false)
     {
         const size_t n = c->n;
         const int rns = limbs + 1;
         const int *ids_ks = c->d_ids_ks + (size_t)limbs * (c->kl + 1);
         Scratch d((size_t)batch * limbs * n * sizeof(u64), c->stream);
-        MOAI_CUDA_CHECK(cudaMemcpyAsync(d.p, target, (size_t)batch * limbs * n * sizeof(u64), cudaMemcpyDeviceToDevice,
-                                        c->stream));
+        const size_t row = (size_t)limbs * n * sizeof(u64);
+        MOAI_CUDA_CHECK(cudaMemcpy2DAsync(d.p, row, target, target_stride ? (size_t)target_stride * sizeof(u64) : row, row,
+                                          (size_t)batch, cudaMemcpyDeviceToDevice, c->stream));
         ntt_inverse(c, d.as<u64>(), batch * limbs, c->d_ids, limbs);
         NttPrologue pro;
         pro.src = d.as<u64>();
@@ -853,7 +831,38 @@ namespace moai
             c->launches += 1;
             MOAI_CUDA_CHECK(cudaGetLastError());
         }
-        divide_round_last(c, acc.as<u64>(), batch * 2, rns, c->kl - 1, addend, out, false);
+        divide_round_last(c, acc.as<u64>(), batch * 2, rns, c->kl - 1, addend, out, addend_c0_only);
+    }
+
+    static bool ks_can_fuse(Context *c, int limbs);
+
+    // One rotation with a pre-permuted key and its own digit decomposition (giant steps, conjugation):
+    // out = sigma((c0, 0) + keyswitch(c1; K')), through the fused key-switch kernel when the primes allow.
+    void rotate_prepermuted(Context *c, const u64 *ct, long long batch, int limbs, uint32_t elt, const u64 *ksk_pre,
+                            int key_kl, u64 *out)
+    {
+        const size_t n = c->n;
+        const size_t per_ct = (size_t)2 * limbs * n;
+        const long long chunk = ks_chunk(c, limbs, batch, ks_ext_budget());
+        const bool fused = ks_can_fuse(c, limbs);
+        Scratch ext((size_t)chunk * ks_ext_bytes_per_ct(c, limbs), c->stream);
+        Scratch tmp((size_t)chunk * per_ct * sizeof(u64), c->stream);
+        for (long long b0 = 0; b0 < batch; b0 += chunk)
+        {
+            const long long nb = (batch - b0) < chunk ? (batch - b0) : chunk;
+            const u64 *src = ct + (size_t)b0 * per_ct;
+            if (fused)
+            {
+                ks_fused(c, src + (size_t)limbs * n, nb, limbs, ext.as<u64>(), ksk_pre, key_kl, src, tmp.as<u64>(),
+                         (long long)per_ct, true);
+                apply_galois_ntt(c, tmp.as<u64>(), out + (size_t)b0 * per_ct, nb * 2 * limbs, elt);
+            }
+            else
+            {
+                ks_decompose(c, src + (size_t)limbs * n, nb, limbs, ext.as<u64>(), (long long)per_ct);
+                rotate_hoisted(c, src, ext.as<u64>(), nb, limbs, elt, ksk_pre, key_kl, out + (size_t)b0 * per_ct);
+            }
+        }
     }
 
     static bool ks_can_fuse(Context *c, int limbs)

@@ -59,6 +59,9 @@ namespace moai
                         const u64 *addend, bool addend_c0_only, u64 *out);
     void rotate_hoisted(Context *c, const u64 *ct, const u64 *ext, long long batch, int limbs, uint32_t elt,
                         const u64 *ksk_pre, int key_kl, u64 *out);
+    // one rotation with a pre-permuted key and its own decomposition (fused key-switch kernel)
+    void rotate_prepermuted(Context *c, const u64 *ct, long long batch, int limbs, uint32_t elt, const u64 *ksk_pre,
+                            int key_kl, u64 *out);
     // up to KSM_R (csrc/ntt.cuh) hoisted rotations in one pass over the extended digits
     bool ks_multi_enabled(Context *c, int limbs);
     void rotate_hoisted_multi(Context *c, const u64 *ct, const u64 *ext, long long batch, int limbs, int n_rot,

@@ -40,7 +40,7 @@ def decrypt_batch(o, sk, pkg, ct):
 def test_fast_rotation_matches_exact_rotation(pkg, env, limbs):
     o, be, sk = env
     rng = np.random.default_rng(limbs)
-    steps = [1, 5, 64, o.n // 2 - 3]
+    steps = [1, 5, 64, o.n // 2 - 3, 7, 100]   # 6 rotations: one pass with four keys, one with two
     zs, cts = encrypt_batch(o, sk, rng, 3, limbs)
     d = pkg.to_device(cts)
     exact, fast, fast_trunc = {}, {}, {}
