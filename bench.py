@@ -314,7 +314,10 @@ def run_gpu(args):
                 "vs_baseline": value / PUBLISHED_S_PER_INPUT, "dtype": "u64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "inputs_per_step": INPUTS_PER_BATCH * world,
                            "l2": "inputs (1.5 GiB per rank) larger than the 126 MB L2; no flush needed",
-                           "parallelism": "replicas x%d (one packed batch per GPU, no collective)" % world},
+                           "parallelism": "replicas x%d (one packed batch per GPU, no collective)" % world,
+                           "other_workloads": "BASELINE.json's 12-layer metric itself: `bench.py --workload layers "
+                                              "--steps 1 --warmup 0` (217 s per layer); measured runs in profiles/ "
+                                              "(layer_r1_fast_e.json, model12_r1_fast.json)"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "s/input", "h2d_bytes_per_step": int(hX.numel() * 8),
                         "d2h_bytes_per_step": int(hOut.numel() * 8)},
@@ -341,6 +344,150 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------------
+# Optional workload: BASELINE.json configs[3]/[4] — the encoder layer(s) themselves (`--workload layers`).
+# One step = `--layers` L encoder layers back to back on one packed batch (217 s per layer on one B200, so
+# this is NOT the default: `--steps 1 --warmup 0 --layers 1` takes about five minutes including key set-up).
+# value = measured seconds per layer x 12 / 256 = BASELINE.json's metric (exact for L = 12, extrapolated
+# from identical layers otherwise — profiles/model12_r1_fast.json shows 12 layers within +-0.1 % of each other).
+# ---------------------------------------------------------------------------------------------------------
+LAYER_METRIC = "amortized sec/input, 12-layer BERT-base (256x128 tok)"
+PUBLISHED_12_LAYERS = 574.6   # P:Table 3 total
+# key switches per encoder layer in the reference's algorithm, by limb count:
+# 3084 bootstrappings x (42 @ ~34, 36 @ ~28, 42 @ ~23), QK^T 240384 @ 14, softmax ~12.7k @ ~8,
+# GELU ~70.7k @ ~5, softmax*V ~31.9k @ 3
+REFERENCE_KS_CENSUS = [(34, 3084 * 42), (28, 3084 * 36), (23, 3084 * 42), (14, 240384), (8, 12700), (5, 70700), (3, 31900)]
+
+
+def cpu_baseline_layers():
+    """Composed CPU figure for the layer workload: the reference's real SEAL (oracle/_ref) is
+    timed on single rotations at the limb counts of the census above (one thread each, ~15 s in total) and the
+    counts are applied with perfect scaling over all host threads.  Key switches are > 90 % of the reference's
+    time (P:Table 3); everything else is left out, so the figure is a LOWER bound of the CPU time."""
+    import oracle
+    if not oracle.have_ref():
+        return None
+    ref = oracle.SealRef(LOG_N, MOAI_BITS, hamming_weight=192, seed=11)
+    ref.make_galois_keys([1])
+    threads = ref.omp_threads()
+    rng = np.random.default_rng(5)
+    n = 1 << LOG_N
+    secs, sample = 0.0, []
+    for limbs, count in REFERENCE_KS_CENSUS:
+        ct = np.empty((2, limbs, n), dtype=np.uint64)
+        for l in range(limbs):
+            ct[:, l, :] = rng.integers(0, int(ref.q[l]), (2, n), dtype=np.uint64)
+        t0 = time.perf_counter()
+        ref.eval(oracle.OP_ROTATE, ct.reshape(-1), 2, limbs, SCALE, iarg=1)
+        dt = time.perf_counter() - t0
+        sample.append("%d limbs %.2f s" % (limbs, dt))
+        secs += dt * count
+    per_layer = secs / threads
+    return {"value": per_layer * 12 / INPUTS_PER_BATCH, "unit": "s/input", "cores": threads, "kind": "reference",
+            "sample": "one rotate_vector of the reference's SEAL per level (" + ", ".join(sample) + ", one thread), "
+                      "times the reference algorithm's key-switch census per layer, divided by %d threads; "
+                      "key switches only (lower bound)" % threads}
+
+
+def run_layers(args):
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import layer_bench
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    st = layer_bench.setup(layer_bench.Args(args.layers, "fast"), device=local_rank)
+    be, boot, keys, w, x, mask = st["be"], st["boot"], st["keys"], st["w"], st["x"], st["mask"]
+    hx = torch.empty(x.shape, dtype=torch.int64, pin_memory=True)
+    hx.copy_(x)
+    hout = torch.empty(x.shape, dtype=torch.int64, pin_memory=True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def layers_once():
+        for layer_id in range(args.layers):
+            boot.encoder_layer(keys, x, SCALE, w, mask, 128, 256, layer_id=layer_id % 12, inplace=True)
+
+    for _ in range(args.warmup):
+        layers_once()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = be.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4 * args.steps)]
+    barrier()
+    for s_ in range(args.steps):
+        a, b, c_, d = ev[4 * s_:4 * s_ + 4]
+        a.record()
+        x.copy_(hx, non_blocking=True)        # the packed batch of ciphertexts arrives from the host
+        b.record()
+        layers_once()
+        c_.record()
+        hout.copy_(x, non_blocking=True)      # encrypted result back to the host
+        d.record()
+    barrier()
+    ms_dev = sum(ev[4 * i + 1].elapsed_time(ev[4 * i + 2]) for i in range(args.steps))
+    ms_e2e = sum(ev[4 * i].elapsed_time(ev[4 * i + 3]) for i in range(args.steps))
+    launches = be.launch_count() - l0
+    clocks = sampler.stop()
+    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=torch.device("cuda", local_rank))
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    per_layer_s = ms_dev / args.steps / args.layers / 1000.0
+    per_layer_e2e = ms_e2e / args.steps / args.layers / 1000.0
+    value = per_layer_s * 12 / (INPUTS_PER_BATCH * world)
+    if rank == 0:
+        cb = cpu_baseline_layers() if world == 1 and not args.no_cpu_baseline else None
+        line = {"metric": LAYER_METRIC, "value": value, "unit": "s/input", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": False, "scaling": "weak",
+                "vs_baseline": value / PUBLISHED_12_LAYERS, "dtype": "u64/f64", "data": "synthetic",
+                "config": {"workload": "C4/C5: %d encoder layer(s) per step on one packed batch (768 cts, N=65536, "
+                                       "35+1 primes), fast mode; 12-layer figure = seconds per layer x 12" % args.layers,
+                           "layers_per_step": args.layers, "inputs_per_step": INPUTS_PER_BATCH * world,
+                           "l2": "working set (GiBs per stage) far larger than the 126 MB L2",
+                           "parallelism": "replicas x%d (one packed batch per GPU, no collective)" % world},
+                "clocks": clocks,
+                "e2e": {"value": per_layer_e2e * 12 / (INPUTS_PER_BATCH * world), "unit": "s/input",
+                        "h2d_bytes_per_step": int(hx.numel() * 8), "d2h_bytes_per_step": int(hout.numel() * 8)},
+                "gpu_launches": int(launches),
+                "roofline": {"kernel": "key switching (ntt_fwd_pass_a, ks_passb_mac_kernel, ks_mac_multi_kernel: ~75 % of "
+                                       "the step)", "bound": "hbm", "achieved": None, "peak": None, "unit": "GB/s",
+                             "frac": None, "traffic": None,
+                             "note": "per-kernel rooflines of this workload are in profiles/ (ncu_full_*.csv, "
+                                     "launch_summary_r1_bootstrap_fast.txt) and DESIGN.md section 5; this line times the step"}}
+        if cb is not None:
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    be.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_reference_layers(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cb = cpu_baseline_layers()
+    if cb is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (the reference's SEAL) is not built"}))
+        return
+    v = cb["value"]
+    print(json.dumps({"impl": "reference", "metric": LAYER_METRIC, "value": v, "unit": "s/input", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": v * INPUTS_PER_BATCH / 12 * 1000.0,
+                      "higher_is_better": False, "scaling": "weak", "vs_baseline": v / PUBLISHED_12_LAYERS,
+                      "dtype": "u64/f64", "data": "synthetic", "config": {"workload": "C4/C5 composed from the key-switch census"},
+                      "cpu_baseline": cb,
+                      "e2e": {"value": v, "unit": "s/input", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -348,8 +495,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="moai_b200", choices=["moai_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c1", choices=["c1", "layers"],
+                    help="c1 (default): self-output ct-pt matmul, finishes in seconds; layers: whole encoder layers "
+                         "(217 s each — use --steps 1 --warmup 0)")
+    ap.add_argument("--layers", type=int, default=1, help="encoder layers per step of --workload layers")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "layers":
+        (run_reference_layers if args.impl == "reference" else run_layers)(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)

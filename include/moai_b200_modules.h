@@ -64,6 +64,10 @@ int32_t moai_keys_add_galois(moai_keys *keys, uint32_t galois_elt, const uint64_
 int32_t moai_key_prepare(moai_context *ctx, const uint64_t *ksk_in, uint32_t galois_elt, int32_t max_limbs,
                          int32_t pre_permute, uint64_t *ksk_out);
 int32_t moai_keys_add_galois_fast(moai_keys *keys, uint32_t galois_elt, const uint64_t *ksk_pre, int32_t key_limbs);
+/* SEAL-exact rotations with a level-truncated key (moai_key_prepare with pre_permute = 0): the residues are
+ * SEAL's bit for bit — a key switch at l limbs never reads digits or limbs beyond l — at (L/35)^2 of the
+ * memory; a rotation above L limbs with such a key is rejected.                                    */
+int32_t moai_keys_add_galois_truncated(moai_keys *keys, uint32_t galois_elt, const uint64_t *ksk, int32_t key_limbs);
 int32_t moai_rotate_many(moai_context *ctx, moai_keys *keys, const uint64_t *in, int64_t batch, int32_t limbs,
                          const int32_t *steps, int32_t n_steps, uint64_t *out);
 

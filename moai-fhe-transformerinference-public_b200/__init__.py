@@ -379,7 +379,10 @@ class Backend:
             self._chk(self.lib.moai_keys_set_relin(h, _ptr(relin)))
             keep.append(relin)
         for elt, t in (galois or {}).items():
-            self._chk(self.lib.moai_keys_add_galois(h, C.c_uint32(elt), _ptr(t)))
+            if t.shape[2] == self.kl:
+                self._chk(self.lib.moai_keys_add_galois(h, C.c_uint32(elt), _ptr(t)))
+            else:   # level-truncated SEAL-exact key [L, 2, L + 1, n] (key_prepare(pre_permute=False))
+                self._chk(self.lib.moai_keys_add_galois_truncated(h, C.c_uint32(elt), _ptr(t), C.c_int32(t.shape[2])))
             keep.append(t)
         for elt, ts in (galois_fast or {}).items():
             for t in (ts if isinstance(ts, (list, tuple)) else [ts]):

@@ -564,6 +564,15 @@ extern "C"
         API_END
     }
 
+    int32_t moai_keys_add_galois_truncated(moai_keys *keys, uint32_t galois_elt, const uint64_t *ksk, int32_t key_limbs)
+    {
+        API_BEGIN
+        MOAI_REQUIRE(keys && ksk, "null argument");
+        MOAI_REQUIRE(key_limbs >= 2 && key_limbs <= keys->kl, "key_limbs out of range");
+        keys->k.galois[galois_elt] = KeyRef{ CU(ksk), key_limbs };
+        API_END
+    }
+
     int32_t moai_keys_add_galois_fast(moai_keys *keys, uint32_t galois_elt, const uint64_t *ksk_pre, int32_t key_limbs)
     {
         API_BEGIN

@@ -319,6 +319,7 @@ namespace moai
         auto it = k.galois.find(elt);
         if (it != k.galois.end())
         {
+            EV_REQUIRE(it->second.max_limbs() >= a.limbs, "Galois key was truncated below this level");
             Ct r = alloc(a.batch, 2, a.limbs, a.scale);
             apply_galois(c, a.d, r.d, a.batch, a.limbs, elt, it->second.p, it->second.key_kl);
             return r;

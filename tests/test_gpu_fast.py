@@ -133,3 +133,19 @@ def test_colpacking_fast_matches_exact(pkg, env):
     want = np.stack([sum(zx[j] * np.roll(zw[j], -i * nb) for j in range(cols)) for i in range(rows)])
     assert np.abs(de - want).max() < 1e-5
     assert np.abs(df - want).max() < 1e-5, np.abs(df - want).max()
+
+
+def test_truncated_exact_key_is_bit_identical(pkg, env):
+    """A level-truncated SEAL-layout key (key_prepare(pre_permute=False)) gives SEAL's residues bit for bit."""
+    o, be, sk = env
+    rng = np.random.default_rng(21)
+    limbs = 5
+    _, cts = encrypt_batch(o, sk, rng, 2, limbs)
+    e = o.elt_from_step(3)
+    k = pkg.to_device(o.gen_galois_key(sk, 900, e).reshape(o.kl - 1, 2, o.kl, o.n))
+    full = be.rotate_vector_keys(be.make_keys(galois={e: k}), pkg.to_device(cts), 3)
+    trunc = be.rotate_vector_keys(be.make_keys(galois={e: be.key_prepare(k, e, max_limbs=limbs, pre_permute=False)}),
+                                  pkg.to_device(cts), 3)
+    assert (full == trunc).all()
+    exp = o.apply_galois(cts[0].reshape(-1), limbs, e, pkg.to_host(k).reshape(-1))
+    assert (pkg.to_host(full[0]).reshape(-1) == exp).all()

@@ -26,17 +26,18 @@ REFERENCE_TABLE3 = {  # P:Table 3, seconds per input summed over 12 layers (BASE
     "layernorm_2": 0.6, "bootstrap_4": 94.8}
 
 
-def main():
+class Args:
+    def __init__(self, layers=1, mode="fast"):
+        self.layers, self.mode = layers, mode
+
+
+def setup(args, device=0):
+    """Backend, bootstrapper, synthetic keys / weights / input for one packed batch on `device`."""
     import torch
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--layers", type=int, default=1,
-                    help="encoder layers run back to back on the same packed batch (BASELINE config 5 = 12)")
-    ap.add_argument("--mode", default="fast", choices=["fast", "exact"],
-                    help="fast: hoisted rotations, pre-permuted level-truncated keys; exact: SEAL-identical key switches")
-    args = ap.parse_args()
     pkg = importlib.import_module("moai-fhe-transformerinference-public_b200")
     primes = bench.moai_primes()
-    be = pkg.Backend(16, primes)
+    torch.cuda.set_device(device)
+    be = pkg.Backend(16, primes, device=device)
     n, kl = 1 << 16, len(primes)
     boot = pkg.Bootstrapper(be, total_limbs=35)
     g = torch.Generator(device="cuda")
@@ -54,9 +55,14 @@ def main():
         steps = set(boot.required_steps())
         # of the driver's default power-of-two Galois keys only the multiples of num_batch = 256 are ever
         # used (QK^T rotates by i*256, softmax*V by multiples of 256): 2^8 .. 2^14 and their negatives
+        att = set()
         for k in range(8, 15):
-            steps |= {1 << k, (n // 2) - (1 << k)}
+            att |= {1 << k, (n // 2) - (1 << k)}
         gal = {be.galois_elt_from_step(st): rand_key() for st in sorted(steps) + [0]}
+        for st in sorted(att):          # used at <= 14 limbs only: SEAL-exact keys truncated to 14 levels
+            e = be.galois_elt_from_step(st)
+            if e not in gal:
+                gal[e] = rand_key(14)
         keys = be.make_keys(relin=rand_key(), galois=gal)
         n_keys = len(gal)
     else:
@@ -86,6 +92,21 @@ def main():
     for l in range(21):
         x[:, :, l, :] = torch.randint(0, primes[l], (hidden, 2, n), generator=g, device="cuda", dtype=torch.int64)
     mask = np.ones(n // 2, dtype=np.int32)     # all 128 tokens of all 256 inputs valid
+    return {"be": be, "boot": boot, "keys": keys, "w": w, "x": x, "mask": mask, "key_gib": key_gib, "n_keys": n_keys,
+            "hidden": hidden, "n": n}
+
+
+def main():
+    import torch
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--layers", type=int, default=1,
+                    help="encoder layers run back to back on the same packed batch (BASELINE config 5 = 12)")
+    ap.add_argument("--mode", default="fast", choices=["fast", "exact"],
+                    help="fast: hoisted rotations, pre-permuted level-truncated keys; exact: SEAL-identical key switches")
+    args = ap.parse_args()
+    st = setup(args)
+    be, boot, keys, w, x, mask = st["be"], st["boot"], st["keys"], st["w"], st["x"], st["mask"]
+    key_gib, n_keys, hidden, n = st["key_gib"], st["n_keys"], st["hidden"], st["n"]
     boot_chunk = int(os.environ.get("MOAI_BOOT_CHUNK", "32"))
     be.profile(True)
     sampler = bench.ClockSampler(0)
