@@ -1,0 +1,613 @@
+// facade_driver.cpp — TEST INFRASTRUCTURE.  The reference's module headers, UNMODIFIED, compiled against
+// the B200 facade (include/facade/seal/seal.h -> include/moai_b200_seal.hpp) instead of stock SEAL, behind
+// the same flat C interface oracle/refbuild/ref_wrap.cpp gives the real library — so one Python test feeds
+// identical keys / ciphertexts to both and compares the residues bit for bit.
+//
+// Built twice by tests/facade_harness/build.py (needs /root/reference for the module headers; outputs in
+// oracle/_ref/, git-ignored, travel to the GPU box):
+//   libfacade_driver.so       linked against libmoai_b200.so                (the `-m gpu` tests)
+//   libfacade_driver_mock.so  linked against the CPU test double mock_cabi.c (host-logic tests, no GPU)
+#include "seal/seal.h"
+
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <iostream>
+#include <memory>
+#include <omp.h>
+#include <sstream>
+#include <string>
+#include <sys/time.h>
+#include <vector>
+
+// the reference's own module code (include path: /root/reference/include)
+#include "source/matrix_mul/Ct_pt_matrix_mul.hpp"
+#include "source/matrix_mul/Ct_ct_matrix_mul.hpp"
+#include "source/non_linear_func/softmax.hpp" // pulls the facade's Bootstrapper.h / ckks_evaluator.h
+#include "source/non_linear_func/layernorm.hpp"
+#include "source/non_linear_func/gelu_others.hpp"
+#include "source/att_block/single_att_block.hpp"
+
+using namespace seal;
+using namespace std;
+
+namespace
+{
+    struct Drv
+    {
+        unique_ptr<SEALContext> ctx;
+        unique_ptr<CKKSEncoder> encoder;
+        unique_ptr<Evaluator> evaluator;
+        RelinKeys rlk;
+        GaloisKeys glk;
+        SecretKey sk;
+        unique_ptr<Bootstrapper> boot;
+        size_t n = 0;
+        string err;
+    };
+
+    void load_ct(const Drv &d, const uint64_t *raw, size_t size, size_t limbs, double scale, Ciphertext &ct)
+    {
+        ct.upload(*d.ctx, raw, size, limbs, scale);
+    }
+
+    struct CoutMute
+    {
+        std::streambuf *old;
+        std::ostringstream sink;
+        CoutMute() : old(std::cout.rdbuf(sink.rdbuf()))
+        {}
+        ~CoutMute()
+        {
+            std::cout.rdbuf(old);
+        }
+    };
+
+    int store_all(const Drv &d, const vector<Ciphertext> &res, uint64_t *out, int *out_limbs, double *out_scale)
+    {
+        for (size_t i = 0; i < res.size(); i++)
+        {
+            *out_limbs = int(res[i].coeff_modulus_size());
+            *out_scale = res[i].scale();
+            res[i].download(out + i * res[i].size() * res[i].coeff_modulus_size() * d.n);
+        }
+        return int(res.size());
+    }
+} // namespace
+
+#define FD_TRY try {
+#define FD_CATCH(d)                                                                                                    \
+    }                                                                                                                  \
+    catch (const invalid_argument &e)                                                                                  \
+    {                                                                                                                  \
+        (d)->err = string("invalid_argument: ") + e.what();                                                            \
+        return -1;                                                                                                     \
+    }                                                                                                                  \
+    catch (const logic_error &e)                                                                                       \
+    {                                                                                                                  \
+        (d)->err = string("logic_error: ") + e.what();                                                                 \
+        return -2;                                                                                                     \
+    }                                                                                                                  \
+    catch (const exception &e)                                                                                         \
+    {                                                                                                                  \
+        (d)->err = string("exception: ") + e.what();                                                                   \
+        return -3;                                                                                                     \
+    }                                                                                                                  \
+    return 0;
+
+extern "C"
+{
+    // bits != nullptr: CoeffModulus::Create(N, bits) as M/test/test_full_scheme.hpp:381-389 does;
+    // otherwise the given primes.  Never returns nullptr; fd_ok() tells whether the context exists.
+    void *fd_create(int log_n, const int *bits, const uint64_t *primes, int count, int device)
+    {
+        auto d = new Drv();
+        try
+        {
+            EncryptionParameters parms(scheme_type::ckks);
+            size_t n = size_t(1) << log_n;
+            parms.set_poly_modulus_degree(n);
+            if (bits)
+            {
+                parms.set_coeff_modulus(CoeffModulus::Create(n, vector<int>(bits, bits + count)));
+            }
+            else
+            {
+                vector<Modulus> m;
+                for (int i = 0; i < count; i++)
+                {
+                    m.emplace_back(primes[i]);
+                }
+                parms.set_coeff_modulus(m);
+            }
+            d->ctx = make_unique<SEALContext>(parms, true, sec_level_type::none, device);
+            d->encoder = make_unique<CKKSEncoder>(*d->ctx);
+            d->evaluator = make_unique<Evaluator>(*d->ctx, *d->encoder);
+            d->n = n;
+        }
+        catch (const exception &e)
+        {
+            d->err = e.what();
+            d->ctx.reset();
+        }
+        return d;
+    }
+    void fd_destroy(void *h)
+    {
+        delete static_cast<Drv *>(h);
+    }
+    const char *fd_error(void *h)
+    {
+        return static_cast<Drv *>(h)->err.c_str();
+    }
+    int fd_ok(void *h)
+    {
+        return static_cast<Drv *>(h)->ctx ? 1 : 0;
+    }
+    int fd_n_key_limbs(void *h)
+    {
+        return int(static_cast<Drv *>(h)->ctx->key_context_data()->parms().coeff_modulus().size());
+    }
+    void fd_primes(void *h, uint64_t *out)
+    {
+        auto &cm = static_cast<Drv *>(h)->ctx->key_context_data()->parms().coeff_modulus();
+        for (size_t i = 0; i < cm.size(); i++)
+        {
+            out[i] = cm[i].value();
+        }
+    }
+    // chain_index of the level with `limbs` limbs, through get_context_data (what the modules print)
+    int fd_chain_index(void *h, int limbs)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        return int(d->ctx->get_context_data(d->ctx->parms_id_for_limbs(limbs))->chain_index());
+        FD_CATCH(d)
+    }
+
+    int fd_set_relin(void *h, const uint64_t *key)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        d->rlk.upload(*d->ctx, key);
+        FD_CATCH(d)
+    }
+    int fd_add_galois(void *h, uint32_t elt, const uint64_t *key)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        d->glk.upload(*d->ctx, elt, key);
+        FD_CATCH(d)
+    }
+    int fd_add_galois_fast(void *h, uint32_t elt, const uint64_t *key, int max_limbs)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        d->glk.upload_fast(*d->ctx, elt, key, max_limbs);
+        FD_CATCH(d)
+    }
+    int fd_set_secret(void *h, const uint64_t *sk)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        d->sk.upload(*d->ctx, sk);
+        FD_CATCH(d)
+    }
+
+    // ---- Evaluator ops on raw ciphertexts: same op codes and argument meaning as ref_eval ----
+    enum
+    {
+        OP_ADD = 0,
+        OP_SUB = 1,
+        OP_MULTIPLY = 2,
+        OP_SQUARE = 3,
+        OP_RELINEARIZE = 4,
+        OP_RESCALE = 5,
+        OP_MOD_SWITCH = 6,
+        OP_ROTATE = 7,
+        OP_CONJUGATE = 8,
+        OP_MULTIPLY_PLAIN = 9,
+        OP_ADD_PLAIN = 10,
+        OP_SUB_PLAIN = 11,
+        OP_NEGATE = 12,
+        OP_MULTIPLY_CONST = 13,
+        OP_ADD_CONST = 14,
+        OP_DOUBLE = 15,
+        OP_ADD_REDUCED_ERROR = 16,
+        OP_SUB_REDUCED_ERROR = 17,
+        OP_MULTIPLY_REDUCED_ERROR = 18,
+        OP_MULTIPLY_VECTOR_REDUCED_ERROR = 19,
+    };
+
+    int fd_eval(void *h, int op, const uint64_t *a, int size_a, int limbs_a, double scale_a, const uint64_t *b,
+                int size_b, int limbs_b, double scale_b, int iarg, double darg, const double *varg, uint64_t *out,
+                int *out_size, int *out_limbs, double *out_scale)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        Ciphertext ca, cb, res;
+        Plaintext pb;
+        load_ct(*d, a, size_a, limbs_a, scale_a, ca);
+        auto &ev = *d->evaluator;
+        auto need_ct = [&]() { load_ct(*d, b, size_b, limbs_b, scale_b, cb); };
+        auto need_pt = [&]() { pb.upload(*d->ctx, b, limbs_b, scale_b); };
+        switch (op)
+        {
+        case OP_ADD:
+            need_ct();
+            ev.add(ca, cb, res);
+            break;
+        case OP_SUB:
+            need_ct();
+            ev.sub(ca, cb, res);
+            break;
+        case OP_MULTIPLY:
+            need_ct();
+            ev.multiply(ca, cb, res);
+            break;
+        case OP_SQUARE:
+            ev.square(ca, res);
+            break;
+        case OP_RELINEARIZE:
+            ev.relinearize(ca, d->rlk, res);
+            break;
+        case OP_RESCALE:
+            ev.rescale_to_next(ca, res);
+            break;
+        case OP_MOD_SWITCH:
+            ev.mod_switch_to_next(ca, res);
+            break;
+        case OP_ROTATE:
+            ev.rotate_vector(ca, iarg, d->glk, res);
+            break;
+        case OP_CONJUGATE:
+            ev.complex_conjugate(ca, d->glk, res);
+            break;
+        case OP_MULTIPLY_PLAIN:
+            need_pt();
+            ev.multiply_plain(ca, pb, res);
+            break;
+        case OP_ADD_PLAIN:
+            need_pt();
+            ev.add_plain(ca, pb, res);
+            break;
+        case OP_SUB_PLAIN:
+            need_pt();
+            ev.sub_plain(ca, pb, res);
+            break;
+        case OP_NEGATE:
+            ev.negate(ca, res);
+            break;
+        case OP_MULTIPLY_CONST:
+            ev.multiply_const(ca, darg, res);
+            break;
+        case OP_ADD_CONST:
+            ev.add_const(ca, darg, res);
+            break;
+        case OP_DOUBLE:
+            res = ca;
+            ev.double_inplace(res);
+            break;
+        case OP_ADD_REDUCED_ERROR:
+            need_ct();
+            ev.add_reduced_error(ca, cb, res);
+            break;
+        case OP_SUB_REDUCED_ERROR:
+            need_ct();
+            ev.sub_reduced_error(ca, cb, res);
+            break;
+        case OP_MULTIPLY_REDUCED_ERROR:
+            need_ct();
+            ev.multiply_reduced_error(ca, cb, d->rlk, res);
+            break;
+        case OP_MULTIPLY_VECTOR_REDUCED_ERROR:
+        {
+            vector<complex<double>> v(d->n / 2);
+            for (size_t i = 0; i < v.size(); i++)
+            {
+                v[i] = complex<double>(varg[2 * i], varg[2 * i + 1]);
+            }
+            res = ca;
+            ev.multiply_vector_inplace_reduced_error(res, v);
+            break;
+        }
+        default:
+            throw invalid_argument("unknown op");
+        }
+        res.download(out);
+        *out_size = int(res.size());
+        *out_limbs = int(res.coeff_modulus_size());
+        *out_scale = res.scale();
+        FD_CATCH(d)
+    }
+
+    // encode(vector<complex>) / encode(vector<double>) / encode(double) -> raw residues [limbs][N]
+    int fd_encode_complex(void *h, const double *values, int n_vals, int limbs, double scale, uint64_t *out)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        vector<complex<double>> v(n_vals);
+        for (int i = 0; i < n_vals; i++)
+        {
+            v[i] = complex<double>(values[2 * i], values[2 * i + 1]);
+        }
+        Plaintext pt;
+        d->encoder->encode(v, d->ctx->parms_id_for_limbs(limbs), scale, pt);
+        pt.download(out);
+        FD_CATCH(d)
+    }
+    int fd_encode_real(void *h, const double *values, int n_vals, int limbs, double scale, uint64_t *out)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        vector<double> v(values, values + n_vals);
+        Plaintext pt;
+        d->encoder->encode(v, d->ctx->parms_id_for_limbs(limbs), scale, pt);
+        pt.download(out);
+        FD_CATCH(d)
+    }
+    // decode of a raw plaintext -> n/2 complex values (interleaved)
+    int fd_decode(void *h, const uint64_t *raw, int limbs, double scale, double *out)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        Plaintext pt;
+        pt.upload(*d->ctx, raw, limbs, scale);
+        vector<complex<double>> v;
+        d->encoder->decode(pt, v);
+        for (size_t i = 0; i < v.size(); i++)
+        {
+            out[2 * i] = v[i].real();
+            out[2 * i + 1] = v[i].imag();
+        }
+        FD_CATCH(d)
+    }
+    // Decryptor::decrypt -> raw plaintext residues [limbs][N]
+    int fd_decrypt(void *h, const uint64_t *ct_raw, int size, int limbs, double scale, uint64_t *out)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        Ciphertext ct;
+        load_ct(*d, ct_raw, size, limbs, scale, ct);
+        Decryptor dec(*d->ctx, d->sk);
+        Plaintext pt;
+        dec.decrypt(ct, pt);
+        pt.download(out);
+        FD_CATCH(d)
+    }
+
+    // ---- the reference's modules, same signatures as ref_ct_pt_matmul / ref_gelu_v2 / ref_layernorm /
+    //      ref_ct_ct_matmul in oracle/refbuild/ref_wrap.cpp ----
+    int fd_ct_pt_matmul(void *h, int variant, const uint64_t *X, const double *W, const int *mask, int K, int C, int limbs,
+                        double scale, uint64_t *out, double *seconds)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        size_t ctsz = size_t(2) * limbs * d->n;
+        vector<Ciphertext> enc_X(K);
+        for (int j = 0; j < K; j++)
+        {
+            load_ct(*d, X + size_t(j) * ctsz, 2, limbs, scale, enc_X[j]);
+        }
+        vector<vector<double>> Wm(K, vector<double>(C));
+        for (int j = 0; j < K; j++)
+        {
+            for (int i = 0; i < C; i++)
+            {
+                Wm[j][i] = W[size_t(j) * C + i];
+            }
+        }
+        vector<int> bias_vec;
+        if (mask)
+        {
+            bias_vec.assign(mask, mask + d->n / 2);
+        }
+        vector<Ciphertext> res;
+        auto t0 = chrono::steady_clock::now();
+        if (variant == 0)
+        {
+            res = ct_pt_matrix_mul_wo_pre(enc_X, Wm, K, C, K, *d->ctx);
+        }
+        else if (variant == 1)
+        {
+            res = ct_pt_matrix_mul_wo_pre_large(enc_X, Wm, K, C, K, *d->ctx);
+        }
+        else
+        {
+            res = ct_pt_matrix_mul_wo_pre_w_mask(enc_X, Wm, bias_vec, K, C, K, *d->ctx);
+        }
+        d->ctx->synchronize();
+        if (seconds)
+        {
+            *seconds = chrono::duration<double>(chrono::steady_clock::now() - t0).count();
+        }
+        size_t outsz = size_t(2) * (limbs - 1) * d->n;
+        for (int i = 0; i < C; i++)
+        {
+            if (res[i].size() != 2 || res[i].coeff_modulus_size() != size_t(limbs - 1))
+            {
+                throw logic_error("unexpected output shape");
+            }
+            res[i].download(out + size_t(i) * outsz);
+        }
+        FD_CATCH(d)
+    }
+
+    int fd_gelu_v2(void *h, const uint64_t *x, int count, int limbs, double scale, uint64_t *out, int *out_limbs,
+                   double *out_scale)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        CoutMute mute;
+        size_t ctsz = size_t(2) * limbs * d->n;
+        for (int i = 0; i < count; i++)
+        {
+            Ciphertext ct;
+            load_ct(*d, x + size_t(i) * ctsz, 2, limbs, scale, ct);
+            Ciphertext res = gelu_v2(ct, *d->ctx, d->rlk, d->sk);
+            *out_limbs = int(res.coeff_modulus_size());
+            *out_scale = res.scale();
+            res.download(out + size_t(i) * 2 * res.coeff_modulus_size() * d->n);
+        }
+        FD_CATCH(d)
+    }
+
+    // `printed` (optional, capacity cap): what the module wrote to std::cout (its debug decryptions)
+    int fd_layernorm(void *h, int variant, const uint64_t *x, int num_ct, int limbs, double scale, const double *gamma,
+                     const double *beta, const int *bias_vec, uint64_t *out, int *out_limbs, double *out_scale,
+                     char *printed, int cap)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        CoutMute mute;
+        size_t ctsz = size_t(2) * limbs * d->n;
+        vector<Ciphertext> xs(num_ct);
+        for (int i = 0; i < num_ct; i++)
+        {
+            load_ct(*d, x + size_t(i) * ctsz, 2, limbs, scale, xs[i]);
+        }
+        vector<double> g(gamma, gamma + num_ct), b(beta, beta + num_ct);
+        vector<int> bv(bias_vec, bias_vec + d->n / 2);
+        vector<Ciphertext> res = variant == 1 ? layernorm(xs, g, b, bv, *d->ctx, d->rlk, d->sk)
+                                              : layernorm2(xs, g, b, bv, *d->ctx, d->rlk, d->sk);
+        store_all(*d, res, out, out_limbs, out_scale);
+        if (printed && cap > 0)
+        {
+            string s = mute.sink.str();
+            strncpy(printed, s.c_str(), size_t(cap) - 1);
+            printed[cap - 1] = 0;
+        }
+        FD_CATCH(d)
+    }
+
+    int fd_ct_ct_matmul(void *h, int which, const uint64_t *X, int nX, const uint64_t *W, int nW, int limbs, double scale_X,
+                        double scale_W, int col_X, int row_X, int col_W, int row_W, int num_batch, uint64_t *out,
+                        int *out_count, int *out_limbs, double *out_scale)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        CoutMute mute;
+        size_t ctsz = size_t(2) * limbs * d->n;
+        vector<Ciphertext> xs(nX), ws(nW);
+        for (int i = 0; i < nX; i++)
+        {
+            load_ct(*d, X + size_t(i) * ctsz, 2, limbs, scale_X, xs[i]);
+        }
+        for (int i = 0; i < nW; i++)
+        {
+            load_ct(*d, W + size_t(i) * ctsz, 2, limbs, scale_W, ws[i]);
+        }
+        vector<Ciphertext> res =
+            which == 0 ? ct_ct_matrix_mul_colpacking(xs, ws, d->glk, d->rlk, *d->ctx, col_X, row_X, col_W, row_W, num_batch)
+                       : ct_ct_matrix_mul_diagpacking(xs, ws, d->glk, d->rlk, *d->ctx, col_X, row_X, col_W, row_W,
+                                                      num_batch);
+        *out_count = store_all(*d, res, out, out_limbs, out_scale);
+        FD_CATCH(d)
+    }
+
+    // exp / inverse of softmax.hpp (:9-82): no bootstrapping, bit-exact against the same headers on real SEAL
+    // only where NTL exists; here they are compared with the op-for-op C-ABI modules (moai_exp / moai_inverse)
+    int fd_exp(void *h, const uint64_t *x, int limbs, double scale, uint64_t *out, int *out_limbs, double *out_scale)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        CoutMute mute;
+        Ciphertext ct;
+        load_ct(*d, x, 2, limbs, scale, ct);
+        Ciphertext res = exp(ct, *d->ctx, d->rlk);
+        *out_limbs = int(res.coeff_modulus_size());
+        *out_scale = res.scale();
+        res.download(out);
+        FD_CATCH(d)
+    }
+    int fd_inverse(void *h, const uint64_t *x, int limbs, double scale, int iter, uint64_t *out, int *out_limbs,
+                   double *out_scale)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        CoutMute mute;
+        Ciphertext ct;
+        load_ct(*d, x, 2, limbs, scale, ct);
+        Ciphertext res = inverse(ct, *d->ctx, d->rlk, iter);
+        *out_limbs = int(res.coeff_modulus_size());
+        *out_scale = res.scale();
+        res.download(out);
+        FD_CATCH(d)
+    }
+
+    // ---- bootstrapping through the facade's Bootstrapper (GPU only) ----
+    // constructor arguments as M/test/test_full_scheme.hpp:413-431; returns the rotation steps it needs
+    int fd_boot_create(void *h, int loge, int logn, int total_level, double final_scale, int boundary_K, int deg,
+                       int scale_factor, int hoisting, int *steps, int cap, int *n_steps)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        d->boot = make_unique<Bootstrapper>(loge, logn, logn, total_level, final_scale, boundary_K, deg, scale_factor, 1,
+                                            *d->ctx, d->rlk, d->glk);
+        d->boot->set_hoisting(hoisting != 0);
+        d->boot->prepare_mod_polynomial();
+        vector<int> v;
+        d->boot->addLeftRotKeys_Linear_to_vector_3(v);
+        d->boot->slot_vec.push_back(logn);
+        d->boot->generate_LT_coefficient_3();
+        *n_steps = int(v.size());
+        for (int i = 0; i < int(v.size()) && i < cap; i++)
+        {
+            steps[i] = v[i];
+        }
+        FD_CATCH(d)
+    }
+    int fd_bootstrap_3(void *h, const uint64_t *x, double scale, uint64_t *out, int *out_limbs, double *out_scale)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        if (!d->boot)
+        {
+            throw logic_error("fd_boot_create first");
+        }
+        Ciphertext ct, rtn;
+        load_ct(*d, x, 2, 1, scale, ct);
+        d->boot->bootstrap_3(rtn, ct);
+        *out_limbs = int(rtn.coeff_modulus_size());
+        *out_scale = rtn.scale();
+        rtn.download(out);
+        FD_CATCH(d)
+    }
+    // argument checks of bootstrap_3 on a ciphertext at `limbs` limbs (expected to throw for limbs != 1)
+    int fd_bootstrap_limbs(void *h, const uint64_t *x, int limbs, double scale)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        if (!d->boot)
+        {
+            throw logic_error("fd_boot_create first");
+        }
+        Ciphertext ct, rtn;
+        load_ct(*d, x, 2, limbs, scale, ct);
+        d->boot->bootstrap_3(rtn, ct);
+        FD_CATCH(d)
+    }
+    // softmax_boot of the reference (softmax.hpp:308-581) on `num` ciphertexts
+    int fd_softmax_boot(void *h, const uint64_t *x, int num, int limbs, double scale, const int *bias_vec, int input_num,
+                        int iter, int layer_id, uint64_t *out, int *out_limbs, double *out_scale)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        if (!d->boot)
+        {
+            throw logic_error("fd_boot_create first");
+        }
+        CoutMute mute;
+        size_t ctsz = size_t(2) * limbs * d->n;
+        vector<Ciphertext> xs(num);
+        for (int i = 0; i < num; i++)
+        {
+            load_ct(*d, x + size_t(i) * ctsz, 2, limbs, scale, xs[i]);
+        }
+        vector<int> bv(bias_vec, bias_vec + d->n / 2);
+        vector<Ciphertext> res = softmax_boot(xs, bv, input_num, *d->ctx, d->rlk, iter, d->sk, *d->boot, layer_id);
+        store_all(*d, res, out, out_limbs, out_scale);
+        FD_CATCH(d)
+    }
+}

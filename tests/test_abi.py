@@ -35,13 +35,15 @@ def test_no_cpu_fallback():
 
 def test_product_never_imports_oracle():
     """The product package and its CUDA sources must not reference oracle/ (③)."""
-    pkg_dir = os.path.join(ROOT, "moai-fhe-transformerinference-public_b200")
-    for dirpath, _, files in os.walk(pkg_dir):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
-                text = open(os.path.join(dirpath, f)).read()
-                assert "import oracle" not in text and "from oracle" not in text, f
-                assert "ckks_oracle" not in text and "libsealref" not in text, f
+    # the package, the C-ABI headers and the header-only C++ facade (include/moai_b200_seal.hpp, include/facade/)
+    for top in (os.path.join(ROOT, "moai-fhe-transformerinference-public_b200"), os.path.join(ROOT, "include")):
+        for dirpath, _, files in os.walk(top):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
+                    text = open(os.path.join(dirpath, f)).read()
+                    assert "import oracle" not in text and "from oracle" not in text, f
+                    assert "ckks_oracle" not in text and "libsealref" not in text, f
+                    assert "moai_b200_mock" not in text and "mock_cabi" not in text and "orc_" not in text, f
 
 
 def test_attention_rotation_steps_cover_the_pipeline():
