@@ -163,6 +163,12 @@ public:
         create();
         return h_;
     }
+    // the single key set (relinearisation + every registered Galois key) the fused modules run with
+    moai_keys *bound_keys()
+    {
+        bind_keys();
+        return keys_;
+    }
 
 private:
     void create()

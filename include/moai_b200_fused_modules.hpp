@@ -1,0 +1,419 @@
+// moai_b200_fused_modules.hpp — the MOAI module functions with the
+// reference's own names and signatures, each implemented as ONE call into libmoai_b200.so's fused device
+// pipelines (include/moai_b200_modules.h) on the whole vector<Ciphertext>.
+//
+// Two ways to run the reference's driver (M/test/test_full_scheme.hpp) on the B200 backend:
+//   -Iinclude/facade                          the reference's own module headers, unchanged, one C-ABI call
+//                                             per Evaluator method (bit-exact, one ciphertext per launch);
+//   -Iinclude/facade_fused -Iinclude/facade   `#include "source/matrix_mul/Ct_pt_matrix_mul.hpp"` & co. resolve
+//                                             to one-line headers that include THIS file: same functions, same
+//                                             residues, but every module is a batched device pipeline (the
+//                                             reference's `#pragma omp parallel for` over ciphertexts becomes
+//                                             the batch dimension of the kernels).
+// Functions of those headers that all_layer_test never reaches (ct_pt_matrix_mul with pre-encoded weights,
+// softmax without bootstrapping, gelu / sgn_eval) are not provided here; use the reference's headers over the
+// plain facade for them.
+//
+// Results: bit-identical to the reference's headers on real SEAL for the ct-pt / ct-ct matmuls, layernorm,
+// layernorm2, gelu_v2, exp and inverse (exact mode; tests/test_gpu_modules.py, tests/test_gpu_zz_facade.py);
+// softmax_boot and single_att_block contain a bootstrapping and match by decrypted tolerance.
+#ifndef MOAI_B200_FUSED_MODULES_HPP
+#define MOAI_B200_FUSED_MODULES_HPP
+
+#include "moai_b200_seal.hpp"
+#include "facade/Bootstrapper.h"
+
+#include <iostream>
+#include <vector>
+
+namespace moai_b200
+{
+namespace fused
+{
+    using namespace sealapi;
+
+    // vector<Ciphertext> (separate device blocks) -> one contiguous [count][2][limbs][N] block
+    inline detail::DeviceBlock pack(const SEALContext &ctx, const std::vector<Ciphertext> &v, std::size_t &limbs)
+    {
+        if (v.empty())
+        {
+            throw std::invalid_argument("empty ciphertext vector");
+        }
+        limbs = v[0].coeff_modulus_size();
+        auto &c = ctx.impl();
+        const std::size_t per = 2 * limbs * c->n;
+        detail::DeviceBlock blk;
+        blk.ensure(c, per * v.size());
+        detail::Lock lk(c->mu);
+        for (std::size_t i = 0; i < v.size(); i++)
+        {
+            if (v[i].size() != 2 || v[i].coeff_modulus_size() != limbs || v[i].context() != c)
+            {
+                throw std::invalid_argument("encrypted is not valid for encryption parameters");
+            }
+            detail::chk(moai_memcpy_d2d(c->h, blk.ptr() + i * per, v[i].data(), per * sizeof(std::uint64_t)));
+        }
+        return blk;
+    }
+
+    // contiguous [count][2][limbs][N] -> vector<Ciphertext> at that level with the given scale
+    inline std::vector<Ciphertext> unpack(const SEALContext &ctx, const std::uint64_t *src, std::size_t count,
+                                          std::size_t limbs, double scale)
+    {
+        auto &c = ctx.impl();
+        const std::size_t per = 2 * limbs * c->n;
+        const parms_id_type &id = ctx.parms_id_for_limbs(limbs);
+        std::vector<Ciphertext> out(count);
+        detail::Lock lk(c->mu);
+        for (std::size_t i = 0; i < count; i++)
+        {
+            out[i].resize(ctx, id, 2);
+            out[i].scale() = scale;
+            out[i].is_ntt_form() = true;
+            detail::chk(moai_memcpy_d2d(c->h, out[i].data(), src + i * per, per * sizeof(std::uint64_t)));
+        }
+        return out;
+    }
+
+    inline std::vector<double> flatten(const std::vector<std::vector<double>> &W, int rows, int cols)
+    {
+        if (int(W.size()) < rows)
+        {
+            throw std::invalid_argument("weight matrix has too few rows");
+        }
+        std::vector<double> flat(std::size_t(rows) * cols);
+        for (int j = 0; j < rows; j++)
+        {
+            if (int(W[j].size()) < cols)
+            {
+                throw std::invalid_argument("weight matrix has too few columns");
+            }
+            std::copy(W[j].begin(), W[j].begin() + cols, flat.begin() + std::size_t(j) * cols);
+        }
+        return flat;
+    }
+
+    // the module entry points take ONE key set: relinearisation key + Galois keys
+    class KeyBundle
+    {
+    public:
+        KeyBundle(const SEALContext &ctx, const RelinKeys *rk, const GaloisKeys *gk) : c_(ctx.impl())
+        {
+            detail::Lock lk(c_->mu);
+            detail::chk(moai_keys_create(c_->h, &h_));
+            if (rk && rk->has_key(2))
+            {
+                detail::chk(moai_keys_set_relin(h_, rk->device_key()));
+            }
+            auto gs = gk ? gk->key_set() : nullptr;
+            if (gs)
+            {
+                for (auto &kv : gs->galois)
+                {
+                    detail::chk(moai_keys_add_galois(h_, kv.first, kv.second));
+                }
+                for (auto &f : gs->fast)
+                {
+                    detail::chk(moai_keys_add_galois_fast(h_, f.elt, f.p, f.key_limbs));
+                }
+            }
+        }
+        KeyBundle(const KeyBundle &) = delete;
+        KeyBundle &operator=(const KeyBundle &) = delete;
+        ~KeyBundle()
+        {
+            if (h_)
+            {
+                detail::Lock lk(c_->mu);
+                moai_keys_destroy(h_);
+            }
+        }
+        moai_keys *get() const
+        {
+            return h_;
+        }
+
+    private:
+        detail::ContextPtr c_;
+        moai_keys *h_ = nullptr;
+    };
+
+    inline std::vector<Ciphertext> ct_pt(const std::vector<Ciphertext> &enc_X, const std::vector<std::vector<double>> &W,
+                                         const std::vector<int> *bias_vec, int col_X, int col_W, int row_W,
+                                         const SEALContext &ctx)
+    {
+        std::vector<Ciphertext> output(col_W);
+        if (col_X != row_W)
+        {
+            std::cout << "ERROR: bad dimensions of X or W. " << std::endl; // Ct_pt_matrix_mul.hpp:11-14
+            return output;
+        }
+        if (int(enc_X.size()) < row_W)
+        {
+            throw std::invalid_argument("enc_X has fewer ciphertexts than row_W");
+        }
+        const double scale = enc_X[0].scale();
+        std::size_t limbs = 0;
+        std::vector<Ciphertext> used(enc_X.begin(), enc_X.begin() + row_W);
+        detail::DeviceBlock x = pack(ctx, used, limbs);
+        if (limbs < 2)
+        {
+            throw std::invalid_argument("end of modulus switching chain reached");
+        }
+        auto &c = ctx.impl();
+        const std::vector<double> flat = flatten(W, row_W, col_W);
+        detail::DeviceBlock out;
+        out.ensure(c, std::size_t(col_W) * 2 * (limbs - 1) * c->n);
+        {
+            detail::Lock lk(c->mu);
+            if (bias_vec)
+            {
+                if (bias_vec->size() < c->n / 2)
+                {
+                    throw std::invalid_argument("bias_vec has fewer entries than slots");
+                }
+                std::vector<std::int32_t> mask(bias_vec->begin(), bias_vec->begin() + c->n / 2);
+                detail::chk(moai_ct_pt_matrix_mul_wo_pre_w_mask(c->h, x.ptr(), flat.data(), mask.data(), col_X, col_W, row_W,
+                                                                std::int32_t(limbs), scale, out.ptr()));
+            }
+            else
+            {
+                detail::chk(moai_ct_pt_matrix_mul_wo_pre(c->h, x.ptr(), flat.data(), col_X, col_W, row_W, std::int32_t(limbs),
+                                                         scale, out.ptr()));
+            }
+        }
+        return unpack(ctx, out.ptr(), std::size_t(col_W), limbs - 1, scale); // output[i].scale() = scale (:41)
+    }
+
+    template <typename F>
+    inline std::vector<Ciphertext> module_call(const SEALContext &ctx, std::size_t out_count, std::size_t limbs, F &&f)
+    {
+        auto &c = ctx.impl();
+        detail::DeviceBlock out;
+        out.ensure(c, out_count * 2 * limbs * c->n);
+        std::int32_t out_limbs = 0;
+        double out_scale = 0.0;
+        {
+            detail::Lock lk(c->mu);
+            detail::chk(f(c->h, out.ptr(), &out_limbs, &out_scale));
+        }
+        return unpack(ctx, out.ptr(), out_count, std::size_t(out_limbs), out_scale);
+    }
+} // namespace fused
+} // namespace moai_b200
+
+// ---- M/source/matrix_mul/Ct_pt_matrix_mul.hpp:4-170 ----
+inline std::vector<seal::Ciphertext> ct_pt_matrix_mul_wo_pre(const std::vector<seal::Ciphertext> &enc_X,
+                                                             const std::vector<std::vector<double>> &W, int col_X, int col_W,
+                                                             int row_W, const seal::SEALContext &seal_context)
+{
+    return moai_b200::fused::ct_pt(enc_X, W, nullptr, col_X, col_W, row_W, seal_context);
+}
+// differs from the function above only in its OpenMP tiling (:51-101)
+inline std::vector<seal::Ciphertext> ct_pt_matrix_mul_wo_pre_large(const std::vector<seal::Ciphertext> &enc_X,
+                                                                   const std::vector<std::vector<double>> &W, int col_X,
+                                                                   int col_W, int row_W, const seal::SEALContext &seal_context)
+{
+    return moai_b200::fused::ct_pt(enc_X, W, nullptr, col_X, col_W, row_W, seal_context);
+}
+inline std::vector<seal::Ciphertext> ct_pt_matrix_mul_wo_pre_w_mask(const std::vector<seal::Ciphertext> &enc_X,
+                                                                    const std::vector<std::vector<double>> &W,
+                                                                    const std::vector<int> &bias_vec, int col_X, int col_W,
+                                                                    int row_W, const seal::SEALContext &seal_context)
+{
+    return moai_b200::fused::ct_pt(enc_X, W, &bias_vec, col_X, col_W, row_W, seal_context);
+}
+
+// ---- M/source/matrix_mul/Ct_ct_matrix_mul.hpp:5-156 ----
+inline std::vector<seal::Ciphertext> ct_ct_matrix_mul_colpacking(const std::vector<seal::Ciphertext> &enc_X,
+                                                                 const std::vector<seal::Ciphertext> &enc_W,
+                                                                 const seal::GaloisKeys &RotK, const seal::RelinKeys &relin_keys,
+                                                                 const seal::SEALContext &seal_context, int col_X, int row_X,
+                                                                 int col_W, int row_W, int num_batch)
+{
+    namespace f = moai_b200::fused;
+    std::size_t lx = 0, lw = 0;
+    auto x = f::pack(seal_context, enc_X, lx);
+    auto w = f::pack(seal_context, enc_W, lw);
+    if (lx != lw)
+    {
+        throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
+    }
+    f::KeyBundle keys(seal_context, &relin_keys, &RotK);
+    const double sx = enc_X[0].scale(), sw = enc_W[0].scale();
+    return f::module_call(seal_context, std::size_t(row_X), lx, [&](moai_context *h, std::uint64_t *out, std::int32_t *ol, double *os) {
+        return moai_ct_ct_matrix_mul_colpacking(h, keys.get(), x.ptr(), w.ptr(), std::int32_t(lx), sx, sw, col_X, row_X, col_W,
+                                                row_W, num_batch, out, ol, os);
+    });
+}
+inline std::vector<seal::Ciphertext> ct_ct_matrix_mul_diagpacking(const std::vector<seal::Ciphertext> &enc_X,
+                                                                  const std::vector<seal::Ciphertext> &enc_W,
+                                                                  const seal::GaloisKeys &RotK, const seal::RelinKeys &relin_keys,
+                                                                  const seal::SEALContext &seal_context, int col_X, int row_X,
+                                                                  int col_W, int row_W, int num_batch)
+{
+    namespace f = moai_b200::fused;
+    std::size_t lx = 0, lw = 0;
+    auto x = f::pack(seal_context, enc_X, lx);
+    auto w = f::pack(seal_context, enc_W, lw);
+    if (lx != lw)
+    {
+        throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
+    }
+    f::KeyBundle keys(seal_context, &relin_keys, &RotK);
+    const double sx = enc_X[0].scale(), sw = enc_W[0].scale();
+    return f::module_call(seal_context, std::size_t(col_W), lx, [&](moai_context *h, std::uint64_t *out, std::int32_t *ol, double *os) {
+        return moai_ct_ct_matrix_mul_diagpacking(h, keys.get(), x.ptr(), w.ptr(), std::int32_t(lx), sx, sw, col_X, row_X, col_W,
+                                                 row_W, num_batch, out, ol, os);
+    });
+}
+
+// ---- M/source/non_linear_func/layernorm.hpp:157-547 (the SecretKey only feeds the reference's debug prints) ----
+namespace moai_b200
+{
+namespace fused
+{
+    inline std::vector<Ciphertext> layernorm_variant(int variant, const std::vector<Ciphertext> &x, const std::vector<double> &gamma,
+                                                     const std::vector<double> &beta, const std::vector<int> &bias_vec,
+                                                     const SEALContext &ctx, const RelinKeys &relin_keys)
+    {
+        const int num_ct = int(x.size());
+        if (num_ct != 768)
+        {
+            std::cout << "ERROR: INPUT SIZE IS NOT CORRECT. " << std::endl; // layernorm.hpp:169-171
+        }
+        if (int(gamma.size()) < num_ct || int(beta.size()) < num_ct || bias_vec.size() < ctx.impl()->n / 2)
+        {
+            throw std::invalid_argument("gamma / beta / bias_vec are too short");
+        }
+        std::size_t limbs = 0;
+        auto xs = pack(ctx, x, limbs);
+        KeyBundle keys(ctx, &relin_keys, nullptr);
+        std::vector<std::int32_t> mask(bias_vec.begin(), bias_vec.begin() + ctx.impl()->n / 2);
+        const double scale = x[0].scale();
+        return module_call(ctx, std::size_t(num_ct), limbs, [&](moai_context *h, std::uint64_t *out, std::int32_t *ol, double *os) {
+            return moai_layernorm(h, keys.get(), xs.ptr(), num_ct, std::int32_t(limbs), scale, gamma.data(), beta.data(),
+                                  mask.data(), variant, out, ol, os);
+        });
+    }
+} // namespace fused
+} // namespace moai_b200
+inline std::vector<seal::Ciphertext> layernorm(const std::vector<seal::Ciphertext> &x, const std::vector<double> &gamma,
+                                               const std::vector<double> &beta, const std::vector<int> &bias_vec,
+                                               const seal::SEALContext &seal_context, const seal::RelinKeys &relin_keys,
+                                               const seal::SecretKey &)
+{
+    return moai_b200::fused::layernorm_variant(1, x, gamma, beta, bias_vec, seal_context, relin_keys);
+}
+inline std::vector<seal::Ciphertext> layernorm2(const std::vector<seal::Ciphertext> &x, const std::vector<double> &gamma,
+                                                const std::vector<double> &beta, const std::vector<int> &bias_vec,
+                                                const seal::SEALContext &seal_context, const seal::RelinKeys &relin_keys,
+                                                const seal::SecretKey &)
+{
+    return moai_b200::fused::layernorm_variant(2, x, gamma, beta, bias_vec, seal_context, relin_keys);
+}
+
+// ---- M/source/non_linear_func/gelu_others.hpp:4-154 ----
+// batched form: what the driver's `#pragma omp parallel for` over 3072 ciphertexts amounts to (test_full_scheme.hpp:878-888)
+inline std::vector<seal::Ciphertext> gelu_v2(const std::vector<seal::Ciphertext> &x, const seal::SEALContext &seal_context,
+                                             const seal::RelinKeys &relin_keys)
+{
+    namespace f = moai_b200::fused;
+    std::size_t limbs = 0;
+    auto xs = f::pack(seal_context, x, limbs);
+    f::KeyBundle keys(seal_context, &relin_keys, nullptr);
+    const double scale = x[0].scale();
+    const std::int64_t batch = std::int64_t(x.size());
+    return f::module_call(seal_context, x.size(), limbs, [&](moai_context *h, std::uint64_t *out, std::int32_t *ol, double *os) {
+        return moai_gelu_v2(h, keys.get(), xs.ptr(), batch, std::int32_t(limbs), scale, out, ol, os);
+    });
+}
+inline seal::Ciphertext gelu_v2(const seal::Ciphertext &x, const seal::SEALContext &seal_context, const seal::RelinKeys &relin_keys,
+                                const seal::SecretKey &)
+{
+    return std::move(gelu_v2(std::vector<seal::Ciphertext>(1, x), seal_context, relin_keys)[0]);
+}
+
+// ---- M/source/non_linear_func/softmax.hpp:9-82, 308-581 ----
+inline seal::Ciphertext exp(const seal::Ciphertext &x, const seal::SEALContext &seal_context, const seal::RelinKeys &relin_keys)
+{
+    namespace f = moai_b200::fused;
+    std::size_t limbs = 0;
+    auto xs = f::pack(seal_context, std::vector<seal::Ciphertext>(1, x), limbs);
+    f::KeyBundle keys(seal_context, &relin_keys, nullptr);
+    const double scale = x.scale();
+    return std::move(f::module_call(seal_context, 1, limbs, [&](moai_context *h, std::uint64_t *out, std::int32_t *ol, double *os) {
+        return moai_exp(h, keys.get(), xs.ptr(), 1, std::int32_t(limbs), scale, out, ol, os);
+    })[0]);
+}
+inline seal::Ciphertext inverse(const seal::Ciphertext &x, const seal::SEALContext &seal_context, const seal::RelinKeys &relin_keys,
+                                int iter)
+{
+    namespace f = moai_b200::fused;
+    std::size_t limbs = 0;
+    auto xs = f::pack(seal_context, std::vector<seal::Ciphertext>(1, x), limbs);
+    f::KeyBundle keys(seal_context, &relin_keys, nullptr);
+    const double scale = x.scale();
+    return std::move(f::module_call(seal_context, 1, limbs, [&](moai_context *h, std::uint64_t *out, std::int32_t *ol, double *os) {
+        return moai_inverse(h, keys.get(), xs.ptr(), 1, std::int32_t(limbs), scale, iter, out, ol, os);
+    })[0]);
+}
+inline std::vector<seal::Ciphertext> softmax_boot(const std::vector<seal::Ciphertext> &enc_X, const std::vector<int> &bias_vec,
+                                                  int input_num, const seal::SEALContext &seal_context,
+                                                  const seal::RelinKeys &relin_keys, int iter, const seal::SecretKey &,
+                                                  Bootstrapper &bootstrapper_att, int layer_id)
+{
+    namespace f = moai_b200::fused;
+    std::size_t limbs = 0;
+    auto xs = f::pack(seal_context, enc_X, limbs);
+    if (bias_vec.size() < seal_context.impl()->n / 2)
+    {
+        throw std::invalid_argument("bias_vec has fewer entries than slots");
+    }
+    std::vector<std::int32_t> mask(bias_vec.begin(), bias_vec.begin() + seal_context.impl()->n / 2);
+    const double scale = enc_X[0].scale();
+    const int num = int(enc_X.size());
+    moai_bootstrapper *b = bootstrapper_att.handle();
+    moai_keys *keys = bootstrapper_att.bound_keys();
+    return f::module_call(seal_context, enc_X.size(), std::max<std::size_t>(limbs, std::size_t(bootstrapper_att.L + 1 - 14)),
+                          [&](moai_context *h, std::uint64_t *out, std::int32_t *ol, double *os) {
+                              return moai_softmax_boot(h, keys, b, xs.ptr(), num, std::int32_t(limbs), scale, mask.data(), input_num,
+                                                       iter, layer_id, out, ol, os);
+                          });
+}
+
+// ---- M/source/att_block/single_att_block.hpp:10-207 ----
+inline std::vector<seal::Ciphertext> single_att_block(const std::vector<seal::Ciphertext> &enc_X, const std::vector<std::vector<double>> &WQ,
+                                                      const std::vector<std::vector<double>> &WK, const std::vector<std::vector<double>> &WV,
+                                                      const std::vector<double> &bQ, const std::vector<double> &bK,
+                                                      const std::vector<double> &bV, const std::vector<int> &bias_vec, int input_num,
+                                                      const seal::SEALContext &seal_context, const seal::RelinKeys &relin_keys,
+                                                      const seal::GaloisKeys &RotK, Bootstrapper &bootstrapper_att, int num_batch,
+                                                      const seal::SecretKey &, int iter, int layer_id)
+{
+    namespace f = moai_b200::fused;
+    (void)relin_keys;
+    (void)RotK; // the Bootstrapper was constructed over these very key objects (test_full_scheme.hpp:413-431)
+    const int col_W = int(WQ.at(0).size());
+    const int num_col = int(enc_X.size());
+    std::size_t limbs = 0;
+    auto xs = f::pack(seal_context, enc_X, limbs);
+    const std::vector<double> wq = f::flatten(WQ, num_col, col_W), wk = f::flatten(WK, num_col, col_W),
+                              wv = f::flatten(WV, num_col, col_W);
+    if (int(bQ.size()) < col_W || int(bK.size()) < col_W || int(bV.size()) < col_W ||
+        bias_vec.size() < seal_context.impl()->n / 2)
+    {
+        throw std::invalid_argument("bias vectors are too short");
+    }
+    std::vector<std::int32_t> mask(bias_vec.begin(), bias_vec.begin() + seal_context.impl()->n / 2);
+    const double scale = enc_X[0].scale();
+    moai_bootstrapper *b = bootstrapper_att.handle();
+    moai_keys *keys = bootstrapper_att.bound_keys();
+    return f::module_call(seal_context, std::size_t(col_W), limbs, [&](moai_context *h, std::uint64_t *out, std::int32_t *ol, double *os) {
+        return moai_single_att_block(h, keys, b, xs.ptr(), num_col, std::int32_t(limbs), scale, wq.data(), wk.data(), wv.data(),
+                                     bQ.data(), bK.data(), bV.data(), col_W, mask.data(), input_num, num_batch, iter, layer_id, out,
+                                     ol, os);
+    });
+}
+
+#endif // MOAI_B200_FUSED_MODULES_HPP

@@ -21,9 +21,15 @@ def _p(a, t=u64p):
     return a.ctypes.data_as(t)
 
 
-def available(mock):
+def _path(mock, fused):
+    if fused:
+        return _build.DRIVER_FUSED_MOCK_SO if mock else _build.DRIVER_FUSED_SO
+    return _build.DRIVER_MOCK_SO if mock else _build.DRIVER_SO
+
+
+def available(mock, fused=False):
     _build.build()
-    return os.path.exists(_build.DRIVER_MOCK_SO if mock else _build.DRIVER_SO)
+    return os.path.exists(_path(mock, fused))
 
 
 class FacadeError(RuntimeError):
@@ -31,8 +37,8 @@ class FacadeError(RuntimeError):
 
 
 class FacadeDriver:
-    def __init__(self, log_n, bits=None, primes=None, mock=True, device=0):
-        path = _build.DRIVER_MOCK_SO if mock else _build.DRIVER_SO
+    def __init__(self, log_n, bits=None, primes=None, mock=True, device=0, fused=False):
+        path = _path(mock, fused)
         self.lib = C.CDLL(path)
         L = self.lib
         L.fd_create.restype = C.c_void_p

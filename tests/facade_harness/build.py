@@ -7,6 +7,9 @@ gpurun-ignored: they travel to the GPU box like libsealref.so):
   oracle/_ref/libmoai_b200_mock.so      mock_cabi.c, the CPU test double of the C ABI (over the C oracle)
   oracle/_ref/libfacade_driver_mock.so  driver + facade bound to the test double   (`-m "not gpu"` tests)
   oracle/_ref/libfacade_driver.so       driver + facade bound to libmoai_b200.so   (`-m gpu` tests)
+  oracle/_ref/libfacade_driver_fused.so the same driver with include/facade_fused first on the include path: the
+                                        module functions resolve to the fused device pipelines (`-m gpu` tests)
+  oracle/_ref/libfacade_driver_fused_mock.so  the fused variant on the test double (ct-pt matmuls only on the CPU)
 """
 import os
 import subprocess
@@ -19,6 +22,8 @@ PKG = os.path.join(ROOT, "moai-fhe-transformerinference-public_b200")
 MOCK_SO = os.path.join(OUT, "libmoai_b200_mock.so")
 DRIVER_MOCK_SO = os.path.join(OUT, "libfacade_driver_mock.so")
 DRIVER_SO = os.path.join(OUT, "libfacade_driver.so")
+DRIVER_FUSED_SO = os.path.join(OUT, "libfacade_driver_fused.so")
+DRIVER_FUSED_MOCK_SO = os.path.join(OUT, "libfacade_driver_fused_mock.so")
 
 
 def _stale(out, deps):
@@ -47,6 +52,15 @@ def build(force=False):
     if os.path.exists(lib) and (force or _stale(DRIVER_SO, [drv_src, lib] + hdrs)):
         subprocess.check_call(common + ["-o", DRIVER_SO, "-L" + PKG, "-lmoai_b200",
                                         "-Wl,-rpath,$ORIGIN/../../" + os.path.basename(PKG)])
+    fused_inc = os.path.join(inc, "facade_fused")
+    fused_hdrs = [os.path.join(inc, "moai_b200_fused_modules.hpp")]
+    if os.path.exists(lib) and (force or _stale(DRIVER_FUSED_SO, [drv_src, lib] + hdrs + fused_hdrs)):
+        subprocess.check_call([common[0]] + common[1:7] + ["-I" + fused_inc] + common[7:] +
+                              ["-o", DRIVER_FUSED_SO, "-L" + PKG, "-lmoai_b200",
+                               "-Wl,-rpath,$ORIGIN/../../" + os.path.basename(PKG)])
+    if force or _stale(DRIVER_FUSED_MOCK_SO, [drv_src, MOCK_SO] + hdrs + fused_hdrs):
+        subprocess.check_call([common[0]] + common[1:7] + ["-I" + fused_inc] + common[7:] +
+                              ["-o", DRIVER_FUSED_MOCK_SO, "-L" + OUT, "-lmoai_b200_mock", "-Wl,-rpath,$ORIGIN"])
     return os.path.exists(DRIVER_SO)
 
 

@@ -1,4 +1,4 @@
-"""Parity cases shared by tests/test_facade.py (facade over the CPU test double) and tests/test_gpu_facade.py
+"""Parity cases shared by tests/test_facade.py (facade over the CPU test double) and tests/test_gpu_zz_facade.py
 (facade over libmoai_b200.so): the reference's UNMODIFIED module headers run twice — against the reference's
 real SEAL (oracle.SealRef) and against the facade (facade_harness.FacadeDriver) — on identical SEAL-generated
 keys and encryptions; every residue of every output must match."""

@@ -364,6 +364,57 @@ int32_t moai_rotate_vector(moai_context *c, moai_keys *k, const uint64_t *in, ui
     return MOAI_OK;
 }
 
+/* ---- fused modules: the ct-pt matmuls exist in the oracle (enough to exercise the pack / unpack glue of
+ * include/moai_b200_fused_modules.hpp on the CPU); the others are GPU-only ---- */
+extern void orc_ct_pt_matmul_scalar(const orc_ctx *c, const u64 *X, const double *W, int K, int C, int limbs, double scale,
+                                    int c_begin, int c_end, u64 *out);
+extern void orc_ct_pt_matmul_masked(const orc_ctx *c, const u64 *X, const double *W, const int *mask, int K, int C, int limbs,
+                                    double scale, int c_begin, int c_end, u64 *out);
+int32_t moai_ct_pt_matrix_mul_wo_pre(moai_context *c, const uint64_t *X, const double *W, int32_t col_X, int32_t col_W,
+                                     int32_t row_W, int32_t limbs, double scale, uint64_t *out)
+{
+    REQ(c && col_X == row_W && limbs >= 2 && limbs <= c->kl, "bad dimensions of X or W");
+    orc_ct_pt_matmul_scalar(c->o, X, W, row_W, col_W, limbs, scale, 0, col_W, out);
+    return MOAI_OK;
+}
+int32_t moai_ct_pt_matrix_mul_wo_pre_w_mask(moai_context *c, const uint64_t *X, const double *W, const int32_t *mask,
+                                            int32_t col_X, int32_t col_W, int32_t row_W, int32_t limbs, double scale,
+                                            uint64_t *out)
+{
+    REQ(c && col_X == row_W && limbs >= 2 && limbs <= c->kl && mask, "bad dimensions of X or W");
+    orc_ct_pt_matmul_masked(c->o, X, W, mask, row_W, col_W, limbs, scale, 0, col_W, out);
+    return MOAI_OK;
+}
+int32_t moai_ct_pt_matrix_mul_wo_pre_host(moai_context *c, const uint64_t *X, const double *W, int32_t a, int32_t b, int32_t d,
+                                          int32_t l, double s, uint64_t *out)
+{
+    (void)c; (void)X; (void)W; (void)a; (void)b; (void)d; (void)l; (void)s; (void)out;
+    UNSUPPORTED("moai_ct_pt_matrix_mul_wo_pre_host");
+}
+#define GPU_ONLY_MODULE(name, ...)                                                                                     \
+    int32_t name(__VA_ARGS__) { UNSUPPORTED(#name); }
+GPU_ONLY_MODULE(moai_gelu_v2, moai_context *c, moai_keys *k, const uint64_t *x, int64_t b, int32_t l, double s, uint64_t *o,
+                int32_t *ol, double *os)
+GPU_ONLY_MODULE(moai_layernorm, moai_context *c, moai_keys *k, const uint64_t *x, int32_t n, int32_t l, double s,
+                const double *g, const double *be, const int32_t *bv, int32_t v, uint64_t *o, int32_t *ol, double *os)
+GPU_ONLY_MODULE(moai_exp, moai_context *c, moai_keys *k, const uint64_t *x, int64_t b, int32_t l, double s, uint64_t *o,
+                int32_t *ol, double *os)
+GPU_ONLY_MODULE(moai_inverse, moai_context *c, moai_keys *k, const uint64_t *x, int64_t b, int32_t l, double s, int32_t it,
+                uint64_t *o, int32_t *ol, double *os)
+GPU_ONLY_MODULE(moai_ct_ct_matrix_mul_colpacking, moai_context *c, moai_keys *k, const uint64_t *x, const uint64_t *w,
+                int32_t l, double sx, double sw, int32_t a, int32_t b, int32_t d, int32_t e, int32_t nb, uint64_t *o,
+                int32_t *ol, double *os)
+GPU_ONLY_MODULE(moai_ct_ct_matrix_mul_diagpacking, moai_context *c, moai_keys *k, const uint64_t *x, const uint64_t *w,
+                int32_t l, double sx, double sw, int32_t a, int32_t b, int32_t d, int32_t e, int32_t nb, uint64_t *o,
+                int32_t *ol, double *os)
+GPU_ONLY_MODULE(moai_softmax_boot, moai_context *c, moai_keys *k, moai_bootstrapper *bt, const uint64_t *x, int32_t n,
+                int32_t l, double s, const int32_t *bv, int32_t in, int32_t it, int32_t li, uint64_t *o, int32_t *ol,
+                double *os)
+GPU_ONLY_MODULE(moai_single_att_block, moai_context *c, moai_keys *k, moai_bootstrapper *bt, const uint64_t *x, int32_t nc,
+                int32_t l, double s, const double *wq, const double *wk, const double *wv, const double *bq,
+                const double *bk, const double *bv, int32_t cw, const int32_t *mask, int32_t in, int32_t nb, int32_t it,
+                int32_t li, uint64_t *o, int32_t *ol, double *os)
+
 /* ---- not needed by the CPU host-logic tests ---- */
 int32_t moai_key_prepare(moai_context *c, const uint64_t *a, uint32_t e, int32_t m, int32_t p, uint64_t *o)
 {

@@ -5,7 +5,7 @@ and run on the CPU test double of the C ABI (tests/facade_harness/mock_cabi.c, a
 headers run on the reference's real SEAL (oracle/_ref/libsealref.so).  Identical SEAL-generated keys and
 encryptions go to both; all residues and all metadata must match bit for bit.  What this pins is the facade:
 metadata bookkeeping, SEAL's checks and exception classes, operation sequencing, value semantics, the
-encoder/decoder glue.  The CUDA library itself is pinned by the `-m gpu` tests (tests/test_gpu_facade.py runs
+encoder/decoder glue.  The CUDA library itself is pinned by the `-m gpu` tests (tests/test_gpu_zz_facade.py runs
 this same list on libmoai_b200.so)."""
 import os
 import subprocess
@@ -17,11 +17,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference"
 
 
-def _driver(ref, mock=True):
+def _driver(ref, mock=True, fused=False):
     import facade_harness as facade
-    if not facade.available(mock=mock):
+    if not facade.available(mock=mock, fused=fused):
         pytest.skip("facade driver not built (needs /root/reference at build time)")
-    d = facade.FacadeDriver(ref.log_n, bits=ref.bits, mock=mock)
+    d = facade.FacadeDriver(ref.log_n, bits=ref.bits, mock=mock, fused=fused)
     d.take_keys_from(ref)
     return d
 
@@ -122,3 +122,12 @@ def test_reference_ct_ct_matmul_header(deep, which):
 def test_reference_softmax_header_exp_inverse(deep):
     from facade_harness import cases
     cases.case_exp_inverse(*deep, np.random.default_rng(50))
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_fused_ct_pt_matmul_shadow_header(sealref_small, variant):
+    """include/facade_fused first on the include path: `source/matrix_mul/Ct_pt_matrix_mul.hpp` resolves to the
+    fused pipeline wrapper (include/moai_b200_fused_modules.hpp); same call, same residues.  Exercises the
+    pack / one-call / unpack glue all fused wrappers share."""
+    from facade_harness import cases
+    cases.case_ct_pt(sealref_small, _driver(sealref_small, fused=True), np.random.default_rng(60 + variant), variant)

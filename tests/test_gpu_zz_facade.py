@@ -11,11 +11,11 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _driver(ref):
+def _driver(ref, fused=False):
     import facade_harness as facade
-    if not facade.available(mock=False):
-        pytest.skip("oracle/_ref/libfacade_driver.so not built (needs /root/reference at build time)")
-    d = facade.FacadeDriver(ref.log_n, bits=ref.bits, mock=False)
+    if not facade.available(mock=False, fused=fused):
+        pytest.skip("oracle/_ref/libfacade_driver*.so not built (needs /root/reference at build time)")
+    d = facade.FacadeDriver(ref.log_n, bits=ref.bits, mock=False, fused=fused)
     assert d.lib.fd_ok(d.h)
     d.take_keys_from(ref)
     return d
@@ -117,3 +117,51 @@ def test_bootstrapper_facade_preserves_message():
     two = np.zeros(2 * 2 * o.n, dtype=np.uint64)
     with pytest.raises(facade.FacadeError, match="lowest level"):
         d._chk(d.lib.fd_bootstrap_limbs(d.h, two.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_int(2), C.c_double(scale)))
+
+
+# ---- include/facade_fused first on the include path: the same module functions as fused device pipelines ----
+@pytest.fixture(scope="module")
+def small_fused(sealref_small):
+    return sealref_small, _driver(sealref_small, fused=True)
+
+
+@pytest.fixture(scope="module")
+def deep_fused(sealref_deep):
+    return sealref_deep, _driver(sealref_deep, fused=True)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_fused_ct_pt_matmul(small_fused, variant):
+    from facade_harness import cases
+    cases.case_ct_pt(*small_fused, np.random.default_rng(60 + variant), variant)
+
+
+def test_fused_gelu(deep_fused):
+    from facade_harness import cases
+    cases.case_gelu(*deep_fused, np.random.default_rng(70))
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_fused_layernorm(deep_fused, variant):
+    from facade_harness import cases
+    r, d = deep_fused
+    rng = np.random.default_rng(80 + variant)
+    num_ct, limbs = 768, 21
+    mask = np.zeros(r.n // 2, dtype=np.int32)
+    mask[::16][:5] = 1
+    x16, _ = cases.encrypt_batch(r, rng, 16, limbs, sigma=0.3, mask=mask)
+    x = np.ascontiguousarray(np.tile(x16, (num_ct // 16, 1, 1, 1)))
+    gamma, beta = rng.normal(size=num_ct), rng.normal(size=num_ct) * 0.1
+    cases.same(d.layernorm(variant, x.reshape(-1), num_ct, limbs, cases.SCALE, gamma, beta, mask),
+               r.layernorm(variant, x.reshape(-1), num_ct, limbs, cases.SCALE, gamma, beta, mask))
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_fused_ct_ct_matmul(deep_fused, which):
+    from facade_harness import cases
+    cases.case_ct_ct(*deep_fused, np.random.default_rng(90 + which), which)
+
+
+def test_fused_exp_inverse(deep_fused):
+    from facade_harness import cases
+    cases.case_exp_inverse(*deep_fused, np.random.default_rng(95))
