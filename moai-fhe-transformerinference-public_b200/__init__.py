@@ -379,7 +379,7 @@ class Backend:
             self._chk(self.lib.moai_keys_set_relin(h, _ptr(relin)))
             keep.append(relin)
         for elt, t in (galois or {}).items():
-            if t.shape[2] == self.kl:
+            if t.dim() != 4 or t.shape[2] == self.kl:   # flat or [kl - 1, 2, kl, n]: a full SEAL-layout key
                 self._chk(self.lib.moai_keys_add_galois(h, C.c_uint32(elt), _ptr(t)))
             else:   # level-truncated SEAL-exact key [L, 2, L + 1, n] (key_prepare(pre_permute=False))
                 self._chk(self.lib.moai_keys_add_galois_truncated(h, C.c_uint32(elt), _ptr(t), C.c_int32(t.shape[2])))

@@ -501,8 +501,13 @@ namespace moai
 
     // ------------------------------------------------------------------------------------ EvalMod
     // Chebyshev series sum coef[k] T_k evaluated to exactly (target_limbs, target_scale).
-    Ct Bootstrapper::eval_cheb(const Evaluator &ev, const std::vector<double> &coef, int target_limbs,
-                               double target_scale, const std::map<int, Ct> &T, const Keys &keys) const
+    // Recursive division p = q * T_g + r (g the largest giant <= deg p).  The remainder r is evaluated to the same
+    // (level, scale) as p, so its own product q_r * T_{g/2} lands on the same level and the same scale as q * T_g:
+    // the whole remainder chain q * T_g + q_r * T_{g/2} + ... is accumulated as size-3 ciphertexts and
+    // relinearized + rescaled once (7 -> 4 key switches for the degree-59 cosine).
+    void Bootstrapper::eval_cheb_parts(const Evaluator &ev, const std::vector<double> &coef, int target_limbs,
+                                       double target_scale, const std::map<int, Ct> &T, const Keys &keys, Ct &acc3,
+                                       Ct &rest) const
     {
         int d = (int)coef.size() - 1;
         while (d > 0 && coef[d] == 0.0)
@@ -539,7 +544,8 @@ namespace moai
             MOAI_REQUIRE(!acc.empty(), "degenerate polynomial leaf");
             Ct r = ev.rescale_to_next(acc);
             r.scale = target_scale;
-            return ev.add_plain(r, ev.encode(coef[0], r.limbs, target_scale));
+            rest = ev.add_plain(r, ev.encode(coef[0], r.limbs, target_scale));
+            return;
         }
         // split at the largest giant g = 8 * 2^m <= d :  p = q * T_g + r
         int g = kbaby;
@@ -566,19 +572,45 @@ namespace moai
         {
             q_const = q_const && q[i] == 0.0;
         }
-        Ct prod;
+        Ct prod2; // a constant quotient needs no ciphertext product
         if (q_const)
         {
-            prod = ev.rescale_to_next(ev.multiply_plain(tg, ev.encode(q[0], lv, target_scale * ql / tg.scale)));
+            prod2 = ev.rescale_to_next(ev.multiply_plain(tg, ev.encode(q[0], lv, target_scale * ql / tg.scale)));
+            prod2.scale = target_scale;
         }
         else
         {
             Ct qc = eval_cheb(ev, q, lv, target_scale * ql / tg.scale, T, keys);
-            prod = ev.rescale_to_next(ev.relinearize(ev.multiply(qc, tg), keys));
+            Ct prod3 = ev.multiply(qc, tg);
+            prod3.scale = target_scale * ql; // qc was evaluated to exactly target_scale * ql / tg.scale
+            if (acc3.empty())
+            {
+                acc3 = prod3;
+            }
+            else
+            {
+                ev.add_inplace(acc3, prod3);
+            }
         }
+        eval_cheb_parts(ev, r, target_limbs, target_scale, T, keys, acc3, rest);
+        if (q_const)
+        {
+            rest = ev.add(rest, prod2);
+        }
+    }
+
+    Ct Bootstrapper::eval_cheb(const Evaluator &ev, const std::vector<double> &coef, int target_limbs,
+                               double target_scale, const std::map<int, Ct> &T, const Keys &keys) const
+    {
+        Ct acc3, rest;
+        eval_cheb_parts(ev, coef, target_limbs, target_scale, T, keys, acc3, rest);
+        if (acc3.empty())
+        {
+            return rest;
+        }
+        Ct prod = ev.rescale_to_next(ev.relinearize(acc3, keys));
         prod.scale = target_scale;
-        Ct rc = eval_cheb(ev, r, target_limbs, target_scale, T, keys);
-        return ev.add(prod, rc);
+        return ev.add(prod, rest);
     }
 
     Ct Bootstrapper::eval_mod(const Evaluator &ev, const Ct &y, const Keys &keys) const

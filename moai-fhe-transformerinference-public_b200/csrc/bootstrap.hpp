@@ -91,5 +91,9 @@ namespace moai
         Ct eval_mod(const Evaluator &ev, const Ct &y, const Keys &keys) const;
         Ct eval_cheb(const Evaluator &ev, const std::vector<double> &coef, int target_limbs, double target_scale,
                      const std::map<int, Ct> &T, const Keys &keys) const;
+        // p = rescale(relinearize(acc3)) + rest: the products q * T_g of one remainder chain share a level and a
+        // scale, so they are summed as size-3 ciphertexts and relinearized ONCE (lazy relinearization)
+        void eval_cheb_parts(const Evaluator &ev, const std::vector<double> &coef, int target_limbs, double target_scale,
+                             const std::map<int, Ct> &T, const Keys &keys, Ct &acc3, Ct &rest) const;
     };
 } // namespace moai
