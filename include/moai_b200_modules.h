@@ -120,6 +120,16 @@ int32_t moai_bootstrapper_set_hoisting(moai_bootstrapper *b, int32_t on);
 int32_t moai_bootstrapper_required_steps(moai_bootstrapper *b, int32_t *steps, int32_t capacity, int32_t *count);
 int32_t moai_bootstrap(moai_context *ctx, moai_bootstrapper *b, moai_keys *keys, const uint64_t *in, int64_t batch,
                        double scale, uint64_t *out, int32_t *out_limbs, double *out_scale);
+/* Bootstrapping of REAL-slot messages (all of MOAI's activations), two per bootstrapping: z = a + i b is one
+ * full-slot message, so ceil(batch/2) bootstrappings refresh `batch` ciphertexts; the halves are separated by
+ * one conjugation at the output level (needs the conjugation key, which bootstrap_3 needs anyway).  Same
+ * arguments as moai_bootstrap plus chunk_pairs (pairs bootstrapped together; <= 0: 32).  The imaginary parts
+ * of the inputs must be zero (they are mixed into the partner otherwise).  moai_encoder_layer uses this for its
+ * 4 x 768 bootstrappings (M/test/test_full_scheme.hpp:654-660, 758-764, 991-995, 1081-1085) unless the
+ * environment sets MOAI_BOOT_PAIR=0.                                                                        */
+int32_t moai_bootstrap_real(moai_context *ctx, moai_bootstrapper *b, moai_keys *keys, const uint64_t *in,
+                            int64_t batch, double scale, int64_t chunk_pairs, uint64_t *out, int32_t *out_limbs,
+                            double *out_scale);
 /* host-only inspection of the plan (no GPU): one linear stage's diagonals and the cosine coefficients */
 int32_t moai_bootstrap_plan_debug(int32_t log_n, const uint64_t *primes, int32_t n_key_limbs, int32_t total_limbs,
                                   int32_t dir, int32_t stage, int32_t *n_diags, int32_t *offsets, double *diag_values,

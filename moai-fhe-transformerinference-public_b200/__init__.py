@@ -522,6 +522,18 @@ class Bootstrapper:
         assert ol.value == self.total_limbs - 14
         return out, osc.value
 
+    def bootstrap_real(self, keys, x, scale, chunk_pairs=32):
+        """Real-slot messages, two per bootstrapping (moai_bootstrap_real): x [batch, 2, 1, n] ->
+        ([batch, 2, total_limbs - 14, n], final_scale) with ceil(batch / 2) bootstrappings."""
+        be = self.be
+        bt, p, l, n = x.shape
+        out = be.empty(bt, 2, self.total_limbs - 14, n)
+        ol, osc = C.c_int32(), C.c_double()
+        be._chk(be.lib.moai_bootstrap_real(be.h, self.h, keys.h, _ptr(x), C.c_int64(bt), C.c_double(scale),
+                                           C.c_int64(chunk_pairs), _ptr(out), C.byref(ol), C.byref(osc)))
+        assert ol.value == self.total_limbs - 14
+        return out, osc.value
+
     def softmax_boot(self, keys, x, scale, bias_vec, input_num, iters=16, layer_id=0):
         be = self.be
         bt, p, l, n = x.shape

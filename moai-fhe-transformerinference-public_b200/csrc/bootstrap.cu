@@ -722,4 +722,41 @@ namespace moai
         w.scale = prm.final_scale;
         return w;
     }
+    Ct Bootstrapper::bootstrap_real_pairs(const Evaluator &ev, const Ct &in, const Keys &keys, long long chunk_pairs,
+                                          const Ct *into)
+    {
+        MOAI_REQUIRE(in.size == 2 && in.limbs == 1, "bootstrap expects size-2 ciphertexts at the last level");
+        MOAI_REQUIRE(chunk_pairs >= 1, "chunk must be positive");
+        const long long B = in.batch, P = (B + 1) / 2;
+        const int out_limbs = prm.total_limbs - 14;
+        Ct out = into ? *into : ev.alloc(B, 2, out_limbs, prm.final_scale);
+        MOAI_REQUIRE(out.batch == B && out.size == 2 && out.limbs == out_limbs, "output storage shape mismatch");
+        out.scale = prm.final_scale;
+        const size_t n = (size_t)slots();
+        std::vector<cd> minus_i(n, cd(0, -1)), plus_i(n, cd(0, 1));
+        const Pt pi_in = ev.encode(plus_i, 1, 1.0);           // X^(N/2): exact, no level
+        const Pt mi_out = ev.encode(minus_i, out_limbs, 1.0);
+        for (long long p0 = 0; p0 < P; p0 += chunk_pairs)
+        {
+            const long long np = std::min(chunk_pairs, P - p0);
+            const long long nb = std::max(0LL, std::min(np, B - P - p0)); // partners j + P < B
+            Ct z = ev.clone(ev.view(in, p0, np));
+            if (nb > 0)
+            {
+                Ct ib = ev.multiply_plain(ev.view(in, P + p0, nb), pi_in);
+                Ct head = ev.view(z, 0, nb);
+                ev.add_inplace(head, ib);
+            }
+            z.scale = 2.0 * in.scale; // the result then carries (a + i b) / 2 at final_scale
+            Ct r = bootstrap(ev, z, keys);
+            Ct cj = ev.complex_conjugate(r, keys);
+            ev.copy_into(ev.add(r, cj), out, p0);
+            if (nb > 0)
+            {
+                Ct d = ev.sub(ev.view(r, 0, nb), ev.view(cj, 0, nb));
+                ev.copy_into(ev.multiply_plain(d, mi_out), out, P + p0);
+            }
+        }
+        return out;
+    }
 } // namespace moai

@@ -61,6 +61,19 @@ namespace moai
         // total_limbs - 14 limbs with scale final_scale
         Ct bootstrap(const Evaluator &ev, const Ct &in, const Keys &keys);
 
+        // Bootstrapping of REAL-slot messages, two per bootstrapping.  A full-slot bootstrapping refreshes N
+        // independent real coefficients; a real-slot message only uses N/2 of them (its polynomial is fixed by
+        // the conjugation), so z = a + i b carries two messages through ONE bootstrapping:
+        //   z <- a + X^(N/2) b  (exact monomial product at one limb),  declared at twice the input scale
+        //   r  = bootstrap(z) ~ (a + i b) / 2,   c = conj(r)   (one key switch at total_limbs - 14 limbs)
+        //   a' = r + c,  b' = -i (r - c)
+        // MOAI's activations are real, so the 4 x 768 bootstrappings of an encoder layer
+        // (M/test/test_full_scheme.hpp:654-660, 758-764, 991-995, 1081-1085) become 4 x 384.
+        // in: [B][2][1][N]; pairs (j, j + ceil(B/2)); an unpaired ciphertext travels alone.  `into`: optional
+        // storage for the [B][2][total_limbs - 14][N] result; chunk_pairs bounds the workspace.
+        Ct bootstrap_real_pairs(const Evaluator &ev, const Ct &in, const Keys &keys, long long chunk_pairs,
+                                const Ct *into = nullptr);
+
         // host-side artefacts, exposed for the CPU test-suite
         const std::vector<double> &cheb_coeffs() const
         {

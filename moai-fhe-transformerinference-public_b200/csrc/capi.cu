@@ -802,6 +802,25 @@ extern "C"
         API_END
     }
 
+    int32_t moai_bootstrap_real(moai_context *ctx, moai_bootstrapper *b, moai_keys *keys, const uint64_t *in,
+                                int64_t batch, double scale, int64_t chunk_pairs, uint64_t *out, int32_t *out_limbs,
+                                double *out_scale)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(b && in && out && out_limbs && out_scale, "null argument");
+        check_shape(c, batch, 2, 1);
+        Evaluator ev(c);
+        const int ol = b->b->prm.total_limbs - 14;
+        Ct into = ev.wrap(reinterpret_cast<u64 *>(out), batch, 2, ol, b->b->prm.final_scale);
+        Ct r = b->b->bootstrap_real_pairs(ev, ev.wrap(const_cast<u64 *>(CU(in)), batch, 2, 1, scale), getk(keys),
+                                          chunk_pairs > 0 ? chunk_pairs : 32, &into);
+        *out_limbs = r.limbs;
+        *out_scale = r.scale;
+        MOAI_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        API_END
+    }
+
     // Host-only view of the bootstrapping plan (no GPU needed): the sparse-diagonal matrix of one
     // linear stage (dir 0 = CoeffToSlot, 1 = SlotToCoeff; stage 0..2) and the cosine coefficients.
     // Call with diag_values == NULL to query *n_diags.

@@ -6,6 +6,7 @@
 // the batch dimension of single kernel launches, and reductions over ciphertexts are fused
 // (Evaluator::sum_batch / inner_product / sum_sub_square).
 #include "modules.hpp"
+#include <cstdlib>
 #include <algorithm>
 
 namespace moai
@@ -602,6 +603,16 @@ namespace moai
                          const Ct *into = nullptr)
         {
             Ct in = ev.mod_switch_to(x, 1);
+            // activations are real: two ciphertexts per bootstrapping (bootstrap.hpp); MOAI_BOOT_PAIR=0 restores the
+            // reference's one-bootstrapping-per-ciphertext schedule
+            static const bool pair = []() {
+                const char *e = std::getenv("MOAI_BOOT_PAIR");
+                return !(e && e[0] == '0');
+            }();
+            if (pair && x.batch >= 2)
+            {
+                return boot.bootstrap_real_pairs(ev, in, keys, chunk, into);
+            }
             Ct out = into ? *into : ev.alloc(x.batch, 2, boot.prm.total_limbs - 14, boot.prm.final_scale);
             out.scale = boot.prm.final_scale;
             for (long long b0 = 0; b0 < x.batch; b0 += chunk)

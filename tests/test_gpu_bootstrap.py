@@ -61,3 +61,22 @@ def test_bootstrap_with_power_of_two_keys_only(pkg, boot_small):
     out, out_scale = boot.bootstrap_3(keys, pkg.to_device(ct.reshape(1, 2, 1, o.n)), scale)
     dec = o.decode(o.decrypt(sk, pkg.to_host(out).reshape(-1), 2, 3), 3, out_scale)
     assert np.abs(dec - z).max() < 2e-3
+
+
+@pytest.mark.parametrize("batch,chunk", [(5, 2), (4, 32), (1, 32)])
+def test_bootstrap_real_pairs(pkg, boot_small, batch, chunk):
+    """Two real-slot messages per bootstrapping (z = a + i b, separated by one conjugation afterwards): every
+    ciphertext comes back with its own message, max-abs slot error < 2e-3 (the tolerance of the plain
+    bootstrapping), imaginary parts included; odd batches leave one ciphertext unpaired; several chunks."""
+    o, be, boot, sk, keys = boot_small
+    rng = np.random.default_rng(7 + batch)
+    scale = 2.0 ** 46
+    vs = rng.normal(size=(batch, o.n // 2)) * 0.1
+    vs[0, :8] = [0.5, -0.5, 0.25, 0.0, 0.3, -0.3, 0.1, -0.1]
+    cts = np.stack([o.encrypt_sym(sk, 70 + i, o.encode(vs[i].astype(np.complex128), scale, 1), 1) for i in range(batch)])
+    out, out_scale = boot.bootstrap_real(keys, pkg.to_device(cts.reshape(batch, 2, 1, o.n)), scale, chunk_pairs=chunk)
+    assert out.shape == (batch, 2, 3, o.n) and out_scale == scale
+    res = pkg.to_host(out)
+    for i in range(batch):
+        dec = o.decode(o.decrypt(sk, res[i].reshape(-1), 2, 3), 3, out_scale)
+        assert np.abs(dec - vs[i]).max() < 2e-3, (i, np.abs(dec - vs[i]).max())
