@@ -316,8 +316,8 @@ def run_gpu(args):
                            "l2": "inputs (1.5 GiB per rank) larger than the 126 MB L2; no flush needed",
                            "parallelism": "replicas x%d (one packed batch per GPU, no collective)" % world,
                            "other_workloads": "BASELINE.json's 12-layer metric itself: `bench.py --workload layers "
-                                              "--steps 1 --warmup 0` (217 s per layer); measured runs in profiles/ "
-                                              "(layer_r1_fast_e.json, model12_r1_fast.json)"},
+                                              "--steps 1 --warmup 0` (108 s per layer); measured runs in profiles/ "
+                                              "(layer_r1_fast_f.json, model12_r1_fast.json)"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "s/input", "h2d_bytes_per_step": int(hX.numel() * 8),
                         "d2h_bytes_per_step": int(hOut.numel() * 8)},
@@ -346,8 +346,8 @@ def run_gpu(args):
 
 # ---------------------------------------------------------------------------------------------------------
 # Optional workload: BASELINE.json configs[3]/[4] — the encoder layer(s) themselves (`--workload layers`).
-# One step = `--layers` L encoder layers back to back on one packed batch (217 s per layer on one B200, so
-# this is NOT the default: `--steps 1 --warmup 0 --layers 1` takes about five minutes including key set-up).
+# One step = `--layers` L encoder layers back to back on one packed batch (108 s per layer on one B200, so
+# this is NOT the default: `--steps 1 --warmup 0 --layers 1` takes about three minutes including key set-up).
 # value = measured seconds per layer x 12 / 256 = BASELINE.json's metric (exact for L = 12, extrapolated
 # from identical layers otherwise — profiles/model12_r1_fast.json shows 12 layers within +-0.1 % of each other).
 # ---------------------------------------------------------------------------------------------------------
@@ -497,7 +497,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="c1", choices=["c1", "layers"],
                     help="c1 (default): self-output ct-pt matmul, finishes in seconds; layers: whole encoder layers "
-                         "(217 s each — use --steps 1 --warmup 0)")
+                         "(108 s each — use --steps 1 --warmup 0)")
     ap.add_argument("--layers", type=int, default=1, help="encoder layers per step of --workload layers")
     args = ap.parse_args()
     if args.workload == "layers":
