@@ -33,19 +33,25 @@ namespace fused
     using namespace sealapi;
 
     // vector<Ciphertext> (separate device blocks) -> one contiguous [count][2][limbs][N] block
-    inline detail::DeviceBlock pack(const SEALContext &ctx, const std::vector<Ciphertext> &v, std::size_t &limbs)
+    // (the first `count` ciphertexts; count = 0: all of them)
+    inline detail::DeviceBlock pack(const SEALContext &ctx, const std::vector<Ciphertext> &v, std::size_t &limbs,
+                                    std::size_t count = 0)
     {
-        if (v.empty())
+        if (count == 0)
         {
-            throw std::invalid_argument("empty ciphertext vector");
+            count = v.size();
+        }
+        if (v.empty() || count > v.size())
+        {
+            throw std::invalid_argument("too few ciphertexts");
         }
         limbs = v[0].coeff_modulus_size();
         auto &c = ctx.impl();
         const std::size_t per = 2 * limbs * c->n;
         detail::DeviceBlock blk;
-        blk.ensure(c, per * v.size());
+        blk.ensure(c, per * count);
         detail::Lock lk(c->mu);
-        for (std::size_t i = 0; i < v.size(); i++)
+        for (std::size_t i = 0; i < count; i++)
         {
             if (v[i].size() != 2 || v[i].coeff_modulus_size() != limbs || v[i].context() != c)
             {
@@ -154,8 +160,7 @@ namespace fused
         }
         const double scale = enc_X[0].scale();
         std::size_t limbs = 0;
-        std::vector<Ciphertext> used(enc_X.begin(), enc_X.begin() + row_W);
-        detail::DeviceBlock x = pack(ctx, used, limbs);
+        detail::DeviceBlock x = pack(ctx, enc_X, limbs, std::size_t(row_W));
         if (limbs < 2)
         {
             throw std::invalid_argument("end of modulus switching chain reached");

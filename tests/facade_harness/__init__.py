@@ -96,6 +96,12 @@ class FacadeDriver:
     def chain_index(self, limbs):
         return int(self.lib.fd_chain_index(self.h, C.c_int(limbs)))
 
+    def alias_checks(self, a, b, limbs, scale):
+        """Value-semantics / aliasing self-checks inside the driver; returns the number of failed checks."""
+        failed = C.c_int(-1)
+        self._chk(self.lib.fd_alias_checks(self.h, _p(a), _p(b), C.c_int(limbs), C.c_double(scale), C.byref(failed)))
+        return failed.value
+
     # ---- same calls as oracle.SealRef ----
     def eval(self, op, a, size_a, limbs_a, scale_a, b=None, size_b=0, limbs_b=0, scale_b=1.0, iarg=0, darg=0.0,
              varg=None):

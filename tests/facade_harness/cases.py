@@ -208,3 +208,9 @@ def case_exp_inverse(r, d, rng, limbs=12):
     a = x[0].reshape(-1)
     same(d.exp(a, limbs, SCALE), replay_exp(r, a, limbs))
     same(d.inverse(a, limbs, SCALE, 3), replay_inverse(r, a, limbs, 3))
+
+
+def case_value_semantics(r, d, rng, limbs=3):
+    """destination == operand, deep copies, scalar vs vector encodings of a constant, plaintext mod switch."""
+    x, _ = encrypt_batch(r, rng, 2, limbs)
+    assert d.alias_checks(x[0].reshape(-1), x[1].reshape(-1), limbs, SCALE) == 0

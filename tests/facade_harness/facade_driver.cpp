@@ -322,6 +322,112 @@ extern "C"
         FD_CATCH(d)
     }
 
+    // Value semantics and aliasing (S/ciphertext.h:701-715, S/evaluator.cpp:155-240): destination == operand
+    // must give the same residues as distinct objects; a copy must not follow later changes of its source.
+    // Returns the number of failed checks.
+    int fd_alias_checks(void *h, const uint64_t *a_raw, const uint64_t *b_raw, int limbs, double scale, int *failed)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        auto &ev = *d->evaluator;
+        const size_t words2 = size_t(2) * limbs * d->n, words3 = size_t(3) * limbs * d->n;
+        auto host = [&](const Ciphertext &c) {
+            vector<uint64_t> v(c.size() * c.coeff_modulus_size() * d->n);
+            c.download(v.data());
+            return v;
+        };
+        int bad = 0;
+        Ciphertext a, b;
+        load_ct(*d, a_raw, 2, limbs, scale, a);
+        load_ct(*d, b_raw, 2, limbs, scale, b);
+        Ciphertext ref, x;
+        // add(a, b, a) and add(a, b, b)
+        ev.add(a, b, ref);
+        x = a;
+        ev.add(x, b, x);
+        bad += host(x) != host(ref);
+        x = b;
+        ev.add(a, x, x);
+        bad += host(x) != host(ref);
+        // sub(a, b, b) = a - b
+        ev.sub(a, b, ref);
+        x = b;
+        ev.sub(a, x, x);
+        bad += host(x) != host(ref);
+        // multiply(a, b, b), square(a, a)
+        ev.multiply(a, b, ref);
+        x = b;
+        ev.multiply(a, x, x);
+        bad += host(x) != host(ref) || x.size() != 3 || x.scale() != ref.scale();
+        ev.square(a, ref);
+        x = a;
+        ev.square(x, x);
+        bad += host(x) != host(ref);
+        // multiply_plain(a, p, a) with a vector plaintext and with a scalar plaintext
+        Plaintext pv, ps;
+        vector<double> vals(d->n / 2, 0.25);
+        vals[1] = -1.5;
+        d->encoder->encode(vals, a.parms_id(), scale, pv);
+        d->encoder->encode(0.75, a.parms_id(), scale, ps);
+        for (Plaintext *p : { &pv, &ps })
+        {
+            ev.multiply_plain(a, *p, ref);
+            x = a;
+            ev.multiply_plain(x, *p, x);
+            bad += host(x) != host(ref) || x.scale() != ref.scale();
+            x = a;
+            ev.multiply_plain_inplace(x, *p);
+            bad += host(x) != host(ref);
+        }
+        // a scalar encoding and the vector encoding of the same constant are the same plaintext
+        vector<double> cst(d->n / 2, 0.75);
+        Plaintext pc;
+        d->encoder->encode(cst, a.parms_id(), scale, pc);
+        Ciphertext y;
+        ev.multiply_plain(a, pc, y);
+        ev.multiply_plain(a, ps, ref);
+        bad += host(y) != host(ref);
+        ev.add_plain(a, pc, y);
+        ev.add_plain(a, ps, ref);
+        bad += host(y) != host(ref);
+        ev.sub_plain(a, pc, y);
+        ev.sub_plain(a, ps, ref);
+        bad += host(y) != host(ref);
+        // deep copies: the copy keeps its value when the source changes; vector(n, ct) copies n times
+        Ciphertext keep = a;
+        vector<uint64_t> before = host(keep);
+        ev.add_inplace(a, b);
+        bad += host(keep) != before;
+        vector<Ciphertext> many(3, b);
+        ev.negate_inplace(many[1]);
+        bad += host(many[0]) != host(b) || host(many[2]) != host(b) || host(many[1]) == host(b);
+        // a moved-from / default ciphertext is rejected like an invalid one
+        Ciphertext empty;
+        try
+        {
+            ev.add_inplace(empty, b);
+            bad++;
+        }
+        catch (const invalid_argument &)
+        {}
+        // Plaintext mod_switch_to_inplace drops limbs: equal to encoding at the lower level
+        if (limbs >= 2)
+        {
+            Plaintext lo;
+            d->encoder->encode(vals, d->ctx->parms_id_for_limbs(limbs - 1), scale, lo);
+            Plaintext hi = pv;
+            ev.mod_switch_to_inplace(hi, lo.parms_id());
+            vector<uint64_t> h1((limbs - 1) * d->n), h2((limbs - 1) * d->n);
+            hi.download(h1.data());
+            lo.download(h2.data());
+            bad += h1 != h2 || hi.parms_id() != lo.parms_id();
+        }
+        (void)words2;
+        (void)words3;
+        *failed = bad;
+        FD_CATCH(d)
+    }
+
     // encode(vector<complex>) / encode(vector<double>) / encode(double) -> raw residues [limbs][N]
     int fd_encode_complex(void *h, const double *values, int n_vals, int limbs, double scale, uint64_t *out)
     {

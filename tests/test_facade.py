@@ -87,6 +87,11 @@ def test_evaluator_ops_bit_exact(small):
     cases.case_evaluator_ops(*small, np.random.default_rng(1))
 
 
+def test_value_semantics_and_aliasing(small):
+    from facade_harness import cases
+    cases.case_value_semantics(*small, np.random.default_rng(4))
+
+
 def test_seal_exception_rules(small):
     from facade_harness import cases
     cases.case_errors(*small, np.random.default_rng(2))
