@@ -18,13 +18,20 @@
 //   * There is no CPU arithmetic path: without a CUDA device SEALContext's constructor throws.
 //     The one host computation is CKKSEncoder::decode (CRT composition + FFT of a downloaded
 //     plaintext) — in the reference that call only feeds debug prints (layernorm.hpp:279-310).
-//   * Client-side classes (KeyGenerator, Encryptor) are NOT provided: key generation and encryption
-//     stay in stock SEAL on the client.  Raw residues cross the boundary with
-//     Ciphertext::upload / download, RelinKeys::upload, GaloisKeys::upload, SecretKey::upload; the
-//     layouts are SEAL's own (S/ciphertext.h:339-370, S/kswitchkeys.h:335-340).
+//   * KeyGenerator is NOT provided: key generation stays in stock SEAL on the client.
+//     Keys and ciphertexts cross the boundary either as raw residues (Ciphertext::upload / download,
+//     RelinKeys::upload, GaloisKeys::upload, PublicKey::upload, SecretKey::upload; SEAL's own layouts,
+//     S/ciphertext.h:339-370, S/kswitchkeys.h:335-340) or in SEAL's wire format: Ciphertext::save / load,
+//     PublicKey::load, RelinKeys::load, GaloisKeys::load read what the stock library's save() writes
+//     (compr_mode_type::none), INCLUDING the seeded form a client normally ships — the uniform half of every
+//     key component is a 64-byte seed, expanded here with SEAL's PRNG and rejection sampling
+//     (moai_b200_seal_prng.hpp) — which halves the key upload.
+//   * Encryptor (public-key encryption, S/encryptor.cpp:88-318, S/util/rlwe.cpp:224-309) IS provided, for
+//     M/source/matrix_mul/Batch_encode_encrypt.hpp: u and the errors are sampled on the host from SEAL's PRNG
+//     stream, the arithmetic runs on the device; with the same seed the ciphertext is SEAL's bit for bit.
 //   * Ciphertext::data() / Plaintext::data() return DEVICE pointers.
-//   * parms_id values identify a level of THIS context (they are not SEAL's BLAKE2 hashes; the wire
-//     format with the real hashes is sealio.py's job).
+//   * parms_id values are SEAL's own (BLAKE2b-256 of the level's parameters, S/encryptionparams.cpp:124-158),
+//     so serialized objects carry ids a stock SEAL context recognises and vice versa.
 //
 // Threading: the reference calls one shared Evaluator from all OpenMP threads
 // (M/test/test_full_scheme.hpp:654-660).  All entry points here are re-entrant; calls into one context
@@ -35,6 +42,7 @@
 
 #include "moai_b200.h"
 #include "moai_b200_modules.h"
+#include "moai_b200_seal_prng.hpp"
 
 #include <algorithm>
 #include <array>
@@ -43,10 +51,13 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <istream>
 #include <limits>
 #include <map>
 #include <memory>
 #include <mutex>
+#include <ostream>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -282,9 +293,19 @@ namespace sealapi
         {
             return parms_id_;
         }
+        // S/encryptionparams.h:268-285: the source of randomness of client-side operations (Encryptor)
+        void set_random_generator(std::shared_ptr<UniformRandomGeneratorFactory> f) noexcept
+        {
+            random_generator_ = std::move(f);
+        }
+        std::shared_ptr<UniformRandomGeneratorFactory> random_generator() const noexcept
+        {
+            return random_generator_ ? random_generator_ : UniformRandomGeneratorFactory::DefaultFactory();
+        }
 
     private:
         friend class SEALContext;
+        std::shared_ptr<UniformRandomGeneratorFactory> random_generator_;
         scheme_type scheme_;
         std::size_t poly_modulus_degree_ = 0;
         std::vector<Modulus> coeff_modulus_;
@@ -424,20 +445,22 @@ namespace sealapi
             std::size_t words_ = 0;
         };
 
+        // SEAL's parms_id: BLAKE2b-256 over (scheme, N, the level's primes, plain_modulus = 0) as u64 words
+        // (S/encryptionparams.cpp:124-158, S/util/hash.h:30-37)
         inline parms_id_type level_id(const ContextImpl &c, std::size_t limbs, bool key_level)
         {
-            // FNV-1a over the primes of the level: distinct per level and per context
-            std::uint64_t hsh = 1469598103934665603ull;
+            (void)key_level;
+            std::vector<std::uint64_t> words;
+            words.push_back(static_cast<std::uint64_t>(scheme_type::ckks));
+            words.push_back(static_cast<std::uint64_t>(c.n));
             for (std::size_t i = 0; i < limbs; i++)
             {
-                for (int b = 0; b < 8; b++)
-                {
-                    hsh ^= (c.primes[i] >> (8 * b)) & 0xff;
-                    hsh *= 1099511628211ull;
-                }
+                words.push_back(c.primes[i]);
             }
-            return { { 0x4d4f41495f423230ull /* "MOAI_B20" */, (std::uint64_t(c.log_n) << 32) | limbs, hsh,
-                       key_level ? 1ull : 0ull } };
+            words.push_back(0);
+            parms_id_type id;
+            util::blake2b(id.data(), 32, words.data(), words.size() * sizeof(std::uint64_t));
+            return id;
         }
     } // namespace detail
 
@@ -639,6 +662,123 @@ namespace sealapi
                 throw std::invalid_argument(std::string(what) + " is not valid for encryption parameters");
             }
             return cd->parms().coeff_modulus().size();
+        }
+    } // namespace detail
+
+    namespace detail
+    {
+        // SEAL's stream framing (S/serialization.h:76-93): 16-byte header, little endian
+        constexpr std::uint16_t seal_magic = 0xA15E;
+        constexpr std::uint8_t seal_header_size = 0x10;
+
+        template <typename T>
+        inline void put(std::ostream &o, const T &v)
+        {
+            o.write(reinterpret_cast<const char *>(&v), sizeof(T));
+        }
+        template <typename T>
+        inline T get(std::istream &in)
+        {
+            T v;
+            in.read(reinterpret_cast<char *>(&v), sizeof(T));
+            if (!in)
+            {
+                throw std::runtime_error("I/O error");
+            }
+            return v;
+        }
+        inline void put_header(std::ostream &o, std::uint64_t total_size)
+        {
+            put<std::uint16_t>(o, seal_magic);
+            put<std::uint8_t>(o, seal_header_size);
+            put<std::uint8_t>(o, 4); // version 4.1
+            put<std::uint8_t>(o, 1);
+            put<std::uint8_t>(o, 0); // compr_mode_type::none
+            put<std::uint16_t>(o, 0);
+            put<std::uint64_t>(o, total_size);
+        }
+        // returns the total size (header included) the header announces
+        inline std::uint64_t get_header(std::istream &in)
+        {
+            const auto magic = get<std::uint16_t>(in);
+            const auto hsize = get<std::uint8_t>(in);
+            const auto vmaj = get<std::uint8_t>(in);
+            (void)get<std::uint8_t>(in);
+            const auto compr = get<std::uint8_t>(in);
+            (void)get<std::uint16_t>(in);
+            const auto total = get<std::uint64_t>(in);
+            if (magic != seal_magic || hsize != seal_header_size)
+            {
+                throw std::logic_error("loaded SEALHeader is invalid");
+            }
+            if (vmaj != 4 && vmaj != 3)
+            {
+                throw std::logic_error("incompatible version");
+            }
+            if (compr != 0)
+            {
+                throw std::logic_error("unsupported compression mode (save with compr_mode_type::none)");
+            }
+            return total;
+        }
+
+        // One serialized Ciphertext / PublicKey (S/ciphertext.cpp:190-330) -> host residues [size][limbs][N].
+        // A seeded object stores c0 and a PRNG seed; c1 is expanded at the object's own level
+        // (Ciphertext::expand_seed, S/ciphertext.cpp:118-136).
+        struct LoadedCiphertext
+        {
+            parms_id_type parms_id;
+            bool is_ntt_form = true, was_seeded = false;
+            std::size_t size = 0, limbs = 0;
+            double scale = 1.0;
+            std::vector<std::uint64_t> data;
+        };
+        inline LoadedCiphertext load_ciphertext_stream(const ContextImpl &c, std::istream &in)
+        {
+            LoadedCiphertext r;
+            (void)get_header(in);
+            in.read(reinterpret_cast<char *>(r.parms_id.data()), 32);
+            r.is_ntt_form = get<std::uint8_t>(in) != 0;
+            r.size = static_cast<std::size_t>(get<std::uint64_t>(in));
+            const auto n = get<std::uint64_t>(in);
+            r.limbs = static_cast<std::size_t>(get<std::uint64_t>(in));
+            r.scale = get<double>(in);
+            (void)get<std::uint64_t>(in); // correction_factor (BGV only)
+            if (n != c.n || r.limbs < 1 || r.limbs > c.key_limbs() || r.size < 2 || r.size > 6 ||
+                r.parms_id != level_id(c, r.limbs, false))
+            {
+                throw std::logic_error("ciphertext data is invalid");
+            }
+            (void)get_header(in); // the DynArray's own header
+            const auto count = get<std::uint64_t>(in);
+            const std::uint64_t total = std::uint64_t(r.size) * r.limbs * c.n;
+            if (count != total && !(r.size == 2 && count == total / 2))
+            {
+                throw std::logic_error("ciphertext data is invalid");
+            }
+            r.data.resize(total);
+            in.read(reinterpret_cast<char *>(r.data.data()), std::streamsize(count * sizeof(std::uint64_t)));
+            if (!in)
+            {
+                throw std::runtime_error("I/O error");
+            }
+            if (count != total)
+            {
+                // UniformRandomGeneratorInfo: header, prng_type, 64-byte seed (S/randomgen.cpp:99-121)
+                (void)get_header(in);
+                const auto type = static_cast<prng_type>(get<std::uint8_t>(in));
+                prng_seed_type seed;
+                in.read(reinterpret_cast<char *>(seed.data()), prng_seed_byte_count);
+                if (!in)
+                {
+                    throw std::runtime_error("I/O error");
+                }
+                std::vector<std::uint64_t> primes(c.primes.begin(), c.primes.begin() + r.limbs);
+                util::sample_poly_uniform(UniformRandomGeneratorInfo(type, seed).make_prng(), primes, c.n,
+                                          r.data.data() + total / 2);
+                r.was_seeded = true;
+            }
+            return r;
         }
     } // namespace detail
 
@@ -929,6 +1069,51 @@ namespace sealapi
             detail::chk(moai_memcpy_d2h(c->h, host, mem_.ptr(), words() * sizeof(std::uint64_t)));
         }
 
+        // ---- SEAL's wire format (Ciphertext::save / load with compr_mode_type::none, S/ciphertext.cpp:153-330):
+        //      byte-identical to the stock library, so encrypted inputs / outputs / checkpoints interoperate
+        std::streamoff save_size() const
+        {
+            return std::streamoff(16 + 32 + 1 + 24 + 8 + 8 + 16 + 8 + words() * sizeof(std::uint64_t));
+        }
+        std::streamoff save(std::ostream &stream) const
+        {
+            auto c = mem_.context();
+            if (!c || !words())
+            {
+                throw std::logic_error("ciphertext is empty");
+            }
+            std::vector<std::uint64_t> host(words());
+            download(host.data());
+            const std::uint64_t dyn = 16 + 8 + host.size() * sizeof(std::uint64_t);
+            detail::put_header(stream, std::uint64_t(save_size()));
+            stream.write(reinterpret_cast<const char *>(pid_.data()), 32);
+            detail::put<std::uint8_t>(stream, ntt_ ? 1 : 0);
+            detail::put<std::uint64_t>(stream, size_);
+            detail::put<std::uint64_t>(stream, c->n);
+            detail::put<std::uint64_t>(stream, limbs_);
+            detail::put<double>(stream, scale_);
+            detail::put<std::uint64_t>(stream, 1); // correction_factor
+            detail::put_header(stream, dyn);
+            detail::put<std::uint64_t>(stream, host.size());
+            stream.write(reinterpret_cast<const char *>(host.data()), std::streamsize(host.size() * sizeof(std::uint64_t)));
+            if (!stream)
+            {
+                throw std::runtime_error("I/O error");
+            }
+            return save_size();
+        }
+        // accepts the seeded form as well (Encryptor::encrypt_symmetric(...).save() of a stock client)
+        void load(const SEALContext &ctx, std::istream &stream)
+        {
+            detail::LoadedCiphertext r = detail::load_ciphertext_stream(*ctx.impl(), stream);
+            if (!ctx.get_context_data(r.parms_id))
+            {
+                throw std::logic_error("ciphertext data is invalid");
+            }
+            upload(ctx, r.data.data(), r.size, r.limbs, r.scale);
+            ntt_ = r.is_ntt_form;
+        }
+
         // internal: (re)shape without preserving contents
         void shape(const detail::ContextPtr &c, std::size_t size, std::size_t limbs)
         {
@@ -963,6 +1148,45 @@ namespace sealapi
     // keys (S/secretkey.h, S/relinkeys.h, S/galoiskeys.h, S/kswitchkeys.h): generated by stock SEAL on
     // the client, uploaded as raw residues
     // ------------------------------------------------------------------------------------------
+    // PublicKey (S/publickey.h): one size-2 "ciphertext" at the key level, [2][key limbs][N]
+    class PublicKey
+    {
+    public:
+        PublicKey() = default;
+        // PublicKey::data().data() of SEAL
+        void upload(const SEALContext &ctx, const std::uint64_t *host)
+        {
+            auto &c = ctx.impl();
+            mem_ = std::make_shared<detail::DeviceBlock>();
+            mem_->ensure(c, 2 * c->key_limbs() * c->n);
+            detail::Lock lk(c->mu);
+            detail::chk(moai_memcpy_h2d(c->h, mem_->ptr(), host, 2 * c->key_limbs() * c->n * sizeof(std::uint64_t)));
+            detail::chk(moai_synchronize(c->h));
+        }
+        // what PublicKey::save writes (a Ciphertext stream; seeded form accepted)
+        void load(const SEALContext &ctx, std::istream &stream)
+        {
+            detail::LoadedCiphertext r = detail::load_ciphertext_stream(*ctx.impl(), stream);
+            if (r.size != 2 || r.limbs != ctx.impl()->key_limbs())
+            {
+                throw std::logic_error("PublicKey data is invalid");
+            }
+            upload(ctx, r.data.data());
+        }
+        const std::uint64_t *data() const noexcept
+        {
+            return mem_ ? mem_->ptr() : nullptr;
+        }
+        const detail::ContextPtr &context() const
+        {
+            static const detail::ContextPtr none;
+            return mem_ ? mem_->context() : none;
+        }
+
+    private:
+        std::shared_ptr<detail::DeviceBlock> mem_;
+    };
+
     class SecretKey
     {
     public:
@@ -1047,6 +1271,50 @@ namespace sealapi
                 set_ = std::make_shared<detail::KeySet>(ctx.impl());
             }
         }
+        // KSwitchKeys::load_members (S/kswitchkeys.cpp:86-150): parms_id, then a vector (by key index) of vectors
+        // (one PublicKey per decomposition digit).  Calls `sink(index, host [digits][2][kl][N])` per present key.
+        // Seeded entries — what `keygen.create_relin_keys()` / `create_galois_keys(...)` return for shipping —
+        // are expanded on the fly; returns how many digits were seeded.
+        template <typename Sink>
+        static std::size_t load_entries(const SEALContext &ctx, std::istream &stream, Sink &&sink)
+        {
+            const detail::ContextImpl &c = *ctx.impl();
+            (void)detail::get_header(stream);
+            parms_id_type id;
+            stream.read(reinterpret_cast<char *>(id.data()), 32);
+            if (!stream || id != ctx.key_parms_id())
+            {
+                throw std::logic_error("KSwitchKeys data is invalid");
+            }
+            const auto dim1 = detail::get<std::uint64_t>(stream);
+            const std::size_t kl = c.key_limbs(), per = 2 * kl * c.n;
+            std::size_t seeded = 0;
+            for (std::uint64_t index = 0; index < dim1; index++)
+            {
+                const auto dim2 = detail::get<std::uint64_t>(stream);
+                if (dim2 == 0)
+                {
+                    continue;
+                }
+                if (dim2 != kl - 1)
+                {
+                    throw std::logic_error("KSwitchKeys data is invalid");
+                }
+                std::vector<std::uint64_t> key(std::size_t(dim2) * per);
+                for (std::uint64_t j = 0; j < dim2; j++)
+                {
+                    detail::LoadedCiphertext r = detail::load_ciphertext_stream(c, stream);
+                    if (r.size != 2 || r.limbs != kl || !r.is_ntt_form)
+                    {
+                        throw std::logic_error("KSwitchKeys data is invalid");
+                    }
+                    seeded += r.was_seeded;
+                    std::copy(r.data.begin(), r.data.end(), key.begin() + std::size_t(j) * per);
+                }
+                sink(static_cast<std::size_t>(index), key.data());
+            }
+            return seeded;
+        }
         std::shared_ptr<detail::KeySet> set_;
     };
 
@@ -1060,6 +1328,18 @@ namespace sealapi
             set_->relin = set_->store(host);
             detail::Lock lk(set_->c->mu);
             detail::chk(moai_keys_set_relin(set_->h, set_->relin));
+        }
+        // RelinKeys::load (S/relinkeys.h, S/kswitchkeys.cpp:86-150); index = key_power - 2.  Returns the number of
+        // seeded digits that were expanded.
+        std::size_t load(const SEALContext &ctx, std::istream &stream)
+        {
+            return load_entries(ctx, stream, [&](std::size_t index, const std::uint64_t *host) {
+                if (index != 0)
+                {
+                    throw std::logic_error("only the key for s^2 is supported (MOAI relinearises after every product)");
+                }
+                upload(ctx, host);
+            });
         }
         bool has_key(std::size_t key_power) const
         {
@@ -1105,6 +1385,22 @@ namespace sealapi
         const std::shared_ptr<detail::KeySet> &key_set() const
         {
             return set_;
+        }
+        // GaloisKeys::load; index = (galois_elt - 1) / 2 (S/galoiskeys.h:52-56).  With max_limbs > 0 every key is
+        // re-laid out level-truncated and pre-permuted for the fast mode (upload_fast) instead of SEAL's layout.
+        std::size_t load(const SEALContext &ctx, std::istream &stream, int fast_max_limbs = 0)
+        {
+            return load_entries(ctx, stream, [&](std::size_t index, const std::uint64_t *host) {
+                const std::uint32_t elt = static_cast<std::uint32_t>(2 * index + 1);
+                if (fast_max_limbs > 0)
+                {
+                    upload_fast(ctx, elt, host, fast_max_limbs);
+                }
+                else
+                {
+                    upload(ctx, elt, host);
+                }
+            });
         }
         bool has_key(std::uint32_t galois_elt) const
         {
@@ -2014,6 +2310,112 @@ namespace sealapi
         const SEALContext &ctx_;
         std::unique_ptr<CKKSEncoder> own_encoder_;
         const CKKSEncoder &encoder_;
+    };
+
+    // ------------------------------------------------------------------------------------------
+    // Encryptor, public-key mode (S/encryptor.cpp:88-318; S/util/rlwe.cpp:224-309):
+    //   (c0, c1) = round_down_one_level( pk * u + (e0, e1) ),  u <- R_3, e <- chi;  c0 += plain
+    // computed one level above the target (the key level for a fresh ciphertext) and divided by that level's
+    // last prime with rounding, exactly like SEAL.  u, e0, e1 come from parms.random_generator()->create() in
+    // SEAL's order; NTTs, products, sums and the rounding run on the device.
+    // ------------------------------------------------------------------------------------------
+    class Encryptor
+    {
+    public:
+        Encryptor(const SEALContext &ctx, const PublicKey &pk) : ctx_(ctx), pk_(pk)
+        {
+            if (!pk.data() || pk.context() != ctx.impl())
+            {
+                throw std::invalid_argument("public key is not valid for encryption parameters");
+            }
+        }
+
+        void encrypt_zero(const parms_id_type &id, Ciphertext &destination) const
+        {
+            auto cd = ctx_.get_context_data(id);
+            if (!cd || id == ctx_.key_parms_id())
+            {
+                throw std::invalid_argument("parms_id is not valid for encryption parameters");
+            }
+            auto &c = ctx_.impl();
+            const std::size_t limbs = cd->parms().coeff_modulus().size(), n = c->n;
+            // the level above: one more prime of the chain, or ALL primes (key level) above the first data level
+            const bool has_prev = ctx_.using_keyswitching();
+            const std::size_t le = has_prev ? (limbs == c->first_limbs() ? c->key_limbs() : limbs + 1) : limbs;
+            // the key level is (q_0 .. q_{L-1}, p); a lower "level above" is (q_0 .. q_limbs): a prefix either way
+            const std::vector<std::uint64_t> primes(c->primes.begin(), c->primes.begin() + le);
+            auto prng = cd->parms().random_generator()->create();
+            std::vector<std::uint64_t> u(le * n), e(2 * le * n);
+            util::sample_poly_ternary(prng, primes, n, u.data());
+            util::sample_poly_cbd(prng, primes, n, e.data());
+            util::sample_poly_cbd(prng, primes, n, e.data() + le * n);
+
+            detail::DeviceBlock du, de, pk, wide;
+            du.ensure(c, le * n);
+            de.ensure(c, 2 * le * n);
+            pk.ensure(c, 2 * le * n);
+            wide.ensure(c, 2 * le * n);
+            const std::int32_t l32 = static_cast<std::int32_t>(le);
+            detail::Lock lk(c->mu);
+            detail::chk(moai_memcpy_h2d(c->h, du.ptr(), u.data(), u.size() * sizeof(std::uint64_t)));
+            detail::chk(moai_memcpy_h2d(c->h, de.ptr(), e.data(), e.size() * sizeof(std::uint64_t)));
+            // the first `le` limbs of each public-key polynomial (all of them at the key level)
+            const std::size_t kl = c->key_limbs();
+            for (int j = 0; j < 2; j++)
+            {
+                detail::chk(moai_memcpy_d2d(c->h, pk.ptr() + j * le * n, pk_.data() + j * kl * n,
+                                            le * n * sizeof(std::uint64_t)));
+            }
+            detail::chk(moai_ntt_forward(c->h, du.ptr(), 1, 1, l32));
+            detail::chk(moai_multiply_plain(c->h, pk.ptr(), du.ptr(), wide.ptr(), 1, 2, l32, 0));
+            detail::chk(moai_ntt_forward(c->h, de.ptr(), 1, 2, l32));
+            detail::chk(moai_add(c->h, wide.ptr(), de.ptr(), wide.ptr(), 1, 2, l32));
+            destination.resize(ctx_, id, 2);
+            if (le == limbs)
+            {
+                detail::chk(moai_memcpy_d2d(c->h, destination.data(), wide.ptr(), 2 * le * n * sizeof(std::uint64_t)));
+            }
+            else
+            {
+                // divide_and_round_q_last_ntt_inplace (S/util/rns.cpp:830-901) == the rescaling kernel
+                detail::chk(moai_rescale_to_next(c->h, wide.ptr(), destination.data(), 1, 2, l32));
+            }
+            detail::chk(moai_synchronize(c->h)); // the host vectors go out of scope
+            destination.is_ntt_form() = true;
+            destination.scale() = 1.0;
+        }
+        void encrypt_zero(Ciphertext &destination) const
+        {
+            encrypt_zero(ctx_.first_parms_id(), destination);
+        }
+        void encrypt(const Plaintext &plain, Ciphertext &destination) const
+        {
+            if (!plain.is_ntt_form())
+            {
+                throw std::invalid_argument("plain must be in NTT form");
+            }
+            if (!ctx_.get_context_data(plain.parms_id()))
+            {
+                throw std::invalid_argument("plain is not valid for encryption parameters");
+            }
+            encrypt_zero(plain.parms_id(), destination);
+            auto &c = ctx_.impl();
+            const std::int32_t limbs = static_cast<std::int32_t>(destination.coeff_modulus_size());
+            detail::Lock lk(c->mu);
+            if (plain.is_scalar())
+            {
+                detail::chk(moai_add_scalar(c->h, destination.data(), plain.scalar_consts().data(), destination.data(), 1, 2, limbs));
+            }
+            else
+            {
+                detail::chk(moai_add_plain(c->h, destination.data(), plain.data(), destination.data(), 1, 2, limbs, 0));
+            }
+            destination.scale() = plain.scale();
+        }
+
+    private:
+        const SEALContext &ctx_;
+        const PublicKey &pk_;
     };
 
     // ------------------------------------------------------------------------------------------

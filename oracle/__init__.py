@@ -469,12 +469,59 @@ class SealRef:
     def load_ciphertext(self, blob):
         """Ciphertext::load (with SEAL's validity checks) -> (residues, size, limbs, scale)."""
         b = np.frombuffer(blob, dtype=np.uint8)
-        out = np.zeros(len(blob) // 8 + 8, dtype=np.uint64)
+        out = np.zeros(len(blob) // 4 + 8, dtype=np.uint64)      # a seeded stream expands to twice its size
         size, limbs, scale = C.c_int(0), C.c_int(0), C.c_double(0)
         self._chk(self.lib.ref_load_ciphertext(self.h, b.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int64(len(blob)),
                                                _p(out), C.c_int64(out.size), C.byref(size), C.byref(limbs),
                                                C.byref(scale)))
         return out[: size.value * limbs.value * self.n].copy(), size.value, limbs.value, scale.value
+
+    # ---- randomness and key wire format (client-side pieces of the facade) ----
+    def prng_bytes(self, seed8, n):
+        out = np.zeros(n, dtype=np.uint8)
+        s = np.ascontiguousarray(seed8, dtype=np.uint64)
+        self.lib.ref_prng_bytes(_p(s), C.c_int64(n), out.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return out
+
+    def sample_uniform(self, seed8):
+        out = np.zeros(self.kl * self.n, dtype=np.uint64)
+        s = np.ascontiguousarray(seed8, dtype=np.uint64)
+        self._chk(self.lib.ref_sample_uniform(self.h, _p(s), _p(out)))
+        return out
+
+    def public_key(self):
+        out = np.zeros(2 * self.kl * self.n, dtype=np.uint64)
+        self.lib.ref_public_key(self.h, _p(out))
+        return out
+
+    def save_keys(self, kind, seeded, steps=(), conjugate=False):
+        """kind 0 RelinKeys, 1 GaloisKeys, 2 PublicKey -> bytes of save(compr_mode_type::none); seeded: the
+        Serializable<> form of freshly generated keys."""
+        cap = C.c_int64(((self.kl - 1) * 2 * self.kl * self.n * 8 + 4096) * max(1, len(steps) + int(conjugate)) + 65536)
+        buf = np.zeros(cap.value, dtype=np.uint8)
+        arr = (C.c_int * max(1, len(steps)))(*steps)
+        self._chk(self.lib.ref_save_keys(self.h, C.c_int(kind), C.c_int(int(seeded)), arr, C.c_int(len(steps)),
+                                         C.c_int(int(conjugate)), buf.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(cap)))
+        return buf[: cap.value].tobytes()
+
+    def load_keys(self, kind, blob):
+        b = np.frombuffer(blob, dtype=np.uint8)
+        self._chk(self.lib.ref_load_keys(self.h, C.c_int(kind), b.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int64(len(blob))))
+
+    def save_ciphertext_seeded(self, pt, limbs, scale):
+        cap = C.c_int64(2 * limbs * self.n * 8 + 4096)
+        buf = np.zeros(cap.value, dtype=np.uint8)
+        self._chk(self.lib.ref_save_ciphertext_seeded(self.h, _p(pt), C.c_int(limbs), C.c_double(scale),
+                                                      buf.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(cap)))
+        return buf[: cap.value].tobytes()
+
+    def batch_input(self, X, scale):
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        num_X, num_row, num_col = X.shape
+        out = np.zeros(num_col * 2 * (self.kl - 1) * self.n, dtype=np.uint64)
+        self._chk(self.lib.ref_batch_input(self.h, _p(X, f64p), C.c_int(num_X), C.c_int(num_row), C.c_int(num_col),
+                                           C.c_double(scale), _p(out)))
+        return out
 
     def ct_ct_matmul(self, which, X, nX, W, nW, limbs, scale_X, scale_W, col_X, row_X, col_W, row_W, num_batch):
         out = np.zeros(max(row_X, col_W) * 2 * limbs * self.n, dtype=np.uint64)

@@ -9,6 +9,7 @@
 // (S/ciphertext.h:339-370).  Nothing here re-implements arithmetic: each entry point loads the
 // raw residues into seal:: value types and calls the reference's public API.
 #include "seal/seal.h"
+#include "seal/util/rlwe.h"
 #include <cstdint>
 #include <cstring>
 #include <complex>
@@ -21,6 +22,7 @@
 #include <iostream>
 
 // The reference's own module code, unmodified (M/source/matrix_mul/Ct_pt_matrix_mul.hpp).
+#include "source/matrix_mul/Batch_encode_encrypt.hpp"
 #include "source/matrix_mul/Ct_pt_matrix_mul.hpp"
 #include "source/matrix_mul/Ct_ct_matrix_mul.hpp"
 #include "source/non_linear_func/layernorm.hpp"
@@ -769,5 +771,164 @@ extern "C"
     int ref_omp_threads()
     {
         return omp_get_max_threads();
+    }
+
+    // ---- randomness and key wire format (for the facade's client-side pieces) --------------------------------
+    // the first n bytes of SEAL's Blake2xb PRNG stream for a seed (S/randomgen.cpp:176-211)
+    int ref_prng_bytes(const uint64_t *seed8, int64_t n, uint8_t *out)
+    {
+        prng_seed_type seed;
+        copy_n(seed8, seed.size(), seed.begin());
+        Blake2xbPRNG prng(seed);
+        // in odd-sized pieces, to exercise the buffering
+        int64_t done = 0, piece = 7;
+        while (done < n)
+        {
+            int64_t take = min<int64_t>(piece, n - done);
+            prng.generate(size_t(take), reinterpret_cast<seal_byte *>(out + done));
+            done += take;
+            piece = piece * 3 + 1;
+        }
+        return 0;
+    }
+
+    // util::sample_poly_uniform at the key level (S/util/rlwe.cpp:137-166): out [key limbs][N]
+    int ref_sample_uniform(void *h, const uint64_t *seed8, uint64_t *out)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        prng_seed_type seed;
+        copy_n(seed8, seed.size(), seed.begin());
+        util::sample_poly_uniform(make_shared<Blake2xbPRNG>(seed), r->ctx->key_context_data()->parms(), out);
+        REF_CATCH(r)
+    }
+
+    // what a client ships: kind 0 = RelinKeys, 1 = GaloisKeys for `steps` (+ conjugation), 2 = PublicKey;
+    // seeded != 0: the Serializable<> form (the uniform halves replaced by PRNG seeds), compr_mode none.
+    // The seeded keys are freshly generated (a Serializable cannot be kept); load them back with ref_load_keys.
+    int ref_save_keys(void *h, int kind, int seeded, const int *steps, int n_steps, int with_conjugate, uint8_t *buf,
+                      int64_t *n_bytes)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        stringstream ss;
+        vector<uint32_t> elts;
+        auto gt = r->ctx->key_context_data()->galois_tool();
+        for (int i = 0; i < n_steps; i++)
+        {
+            elts.push_back(gt->get_elt_from_step(steps[i]));
+        }
+        if (with_conjugate)
+        {
+            elts.push_back(gt->get_elt_from_step(0));
+        }
+        if (kind == 0)
+        {
+            if (seeded)
+            {
+                r->keygen->create_relin_keys().save(ss, compr_mode_type::none);
+            }
+            else
+            {
+                r->rlk.save(ss, compr_mode_type::none);
+            }
+        }
+        else if (kind == 1)
+        {
+            if (seeded)
+            {
+                r->keygen->create_galois_keys(elts).save(ss, compr_mode_type::none);
+            }
+            else
+            {
+                r->glk.save(ss, compr_mode_type::none);
+            }
+        }
+        else
+        {
+            if (seeded)
+            {
+                r->keygen->create_public_key().save(ss, compr_mode_type::none);
+            }
+            else
+            {
+                r->pk.save(ss, compr_mode_type::none);
+            }
+        }
+        string b = ss.str();
+        if (int64_t(b.size()) > *n_bytes)
+        {
+            throw invalid_argument("buffer too small");
+        }
+        memcpy(buf, b.data(), b.size());
+        *n_bytes = int64_t(b.size());
+        REF_CATCH(r)
+    }
+
+    // SEAL's own loader (expands seeds); replaces the handle's relin / Galois / public key
+    int ref_load_keys(void *h, int kind, const uint8_t *buf, int64_t n_bytes)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        if (kind == 0)
+        {
+            r->rlk.load(*r->ctx, reinterpret_cast<const seal_byte *>(buf), size_t(n_bytes));
+            r->have_rlk = true;
+        }
+        else if (kind == 1)
+        {
+            r->glk.load(*r->ctx, reinterpret_cast<const seal_byte *>(buf), size_t(n_bytes));
+        }
+        else
+        {
+            r->pk.load(*r->ctx, reinterpret_cast<const seal_byte *>(buf), size_t(n_bytes));
+            r->encryptor = make_unique<Encryptor>(*r->ctx, r->pk);
+        }
+        REF_CATCH(r)
+    }
+
+    // a seeded symmetric-key ciphertext stream (Encryptor::encrypt_symmetric(...).save), as a client ships inputs
+    int ref_save_ciphertext_seeded(void *h, const uint64_t *pt_raw, int limbs, double scale, uint8_t *buf, int64_t *n_bytes)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        Plaintext pt;
+        load_pt(*r, pt_raw, limbs, scale, pt);
+        Encryptor enc(*r->ctx, r->sk);
+        stringstream ss;
+        enc.encrypt_symmetric(pt).save(ss, compr_mode_type::none);
+        string b = ss.str();
+        if (int64_t(b.size()) > *n_bytes)
+        {
+            throw invalid_argument("buffer too small");
+        }
+        memcpy(buf, b.data(), b.size());
+        *n_bytes = int64_t(b.size());
+        REF_CATCH(r)
+    }
+
+    // the reference's batch_input (M/source/matrix_mul/Batch_encode_encrypt.hpp:8-38): X [num_X][num_row][num_col]
+    // -> num_col fresh ciphertexts [2][first limbs][n]
+    int ref_batch_input(void *h, const double *X, int num_X, int num_row, int num_col, double scale, uint64_t *out)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        vector<vector<vector<double>>> Xv(num_X, vector<vector<double>>(num_row, vector<double>(num_col)));
+        for (int j = 0; j < num_X; j++)
+        {
+            for (int k = 0; k < num_row; k++)
+            {
+                for (int i = 0; i < num_col; i++)
+                {
+                    Xv[j][k][i] = X[(size_t(j) * num_row + k) * num_col + i];
+                }
+            }
+        }
+        vector<Ciphertext> res = batch_input(Xv, num_X, num_row, num_col, scale, *r->ctx, r->pk);
+        for (size_t i = 0; i < res.size(); i++)
+        {
+            store_ct(*r, res[i], out + i * 2 * r->n_data_limbs * r->n);
+        }
+        REF_CATCH(r)
     }
 }

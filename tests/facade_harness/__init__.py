@@ -37,7 +37,7 @@ class FacadeError(RuntimeError):
 
 
 class FacadeDriver:
-    def __init__(self, log_n, bits=None, primes=None, mock=True, device=0, fused=False):
+    def __init__(self, log_n, bits=None, primes=None, mock=True, device=0, fused=False, prng_seed=None):
         path = _path(mock, fused)
         self.lib = C.CDLL(path)
         L = self.lib
@@ -52,6 +52,8 @@ class FacadeDriver:
             self.h = C.c_void_p(L.fd_create(C.c_int(log_n), None, _p(pr), C.c_int(len(pr)), C.c_int(device)))
         if not L.fd_ok(self.h):
             raise FacadeError("fd_create: " + L.fd_error(self.h).decode())
+        if prng_seed is not None:
+            self.set_prng_seed(prng_seed)       # same seeding rule as oracle.SealRef(seed=...)
         self.kl = L.fd_n_key_limbs(self.h)
         q = np.zeros(self.kl, dtype=np.uint64)
         L.fd_primes(self.h, _p(q))
@@ -95,6 +97,67 @@ class FacadeDriver:
 
     def chain_index(self, limbs):
         return int(self.lib.fd_chain_index(self.h, C.c_int(limbs)))
+
+    # ---- client-side pieces ----
+    def prng_bytes(self, seed8, n):
+        out = np.zeros(n, dtype=np.uint8)
+        s = np.ascontiguousarray(seed8, dtype=np.uint64)
+        self.lib.fd_prng_bytes(_p(s), C.c_int64(n), out.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return out
+
+    def sample_uniform(self, seed8):
+        out = np.zeros(self.kl * self.n, dtype=np.uint64)
+        s = np.ascontiguousarray(seed8, dtype=np.uint64)
+        self._chk(self.lib.fd_sample_uniform(self.h, _p(s), _p(out)))
+        return out
+
+    def set_prng_seed(self, seed):
+        self._chk(self.lib.fd_set_prng_seed(self.h, C.c_uint64(seed)))
+
+    def set_public_key(self, pk):
+        self._chk(self.lib.fd_set_public_key(self.h, _p(np.ascontiguousarray(pk, dtype=np.uint64))))
+
+    def load_keys(self, kind, blob):
+        b = np.frombuffer(blob, dtype=np.uint8)
+        seeded = C.c_int(0)
+        self._chk(self.lib.fd_load_keys(self.h, C.c_int(kind), b.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int64(len(blob)),
+                                        C.byref(seeded)))
+        return seeded.value
+
+    def export_key(self, kind, elt=0):
+        words = (1 if kind == 2 else self.kl - 1) * 2 * self.kl * self.n
+        out = np.zeros(words, dtype=np.uint64)
+        self._chk(self.lib.fd_export_key(self.h, C.c_int(kind), C.c_uint32(elt), _p(out)))
+        return out
+
+    def encrypt(self, pt, limbs, scale):
+        out = np.zeros(2 * limbs * self.n, dtype=np.uint64)
+        self._chk(self.lib.fd_encrypt(self.h, _p(pt), C.c_int(limbs), C.c_double(scale), _p(out)))
+        return out
+
+    def save_ciphertext(self, ct, size, limbs, scale):
+        ct = np.ascontiguousarray(ct, dtype=np.uint64)
+        cap = C.c_int64(ct.nbytes + 4096)
+        buf = np.zeros(cap.value, dtype=np.uint8)
+        self._chk(self.lib.fd_save_ciphertext(self.h, _p(ct), C.c_int(size), C.c_int(limbs), C.c_double(scale),
+                                              buf.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(cap)))
+        return buf[: cap.value].tobytes()
+
+    def load_ciphertext(self, blob, max_words):
+        b = np.frombuffer(blob, dtype=np.uint8)
+        out = np.zeros(max_words, dtype=np.uint64)
+        size, limbs, scale = C.c_int(0), C.c_int(0), C.c_double(0)
+        self._chk(self.lib.fd_load_ciphertext(self.h, b.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int64(len(blob)),
+                                              _p(out), C.c_int64(out.size), C.byref(size), C.byref(limbs), C.byref(scale)))
+        return out[: size.value * limbs.value * self.n].copy(), size.value, limbs.value, scale.value
+
+    def batch_input(self, X, scale):
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        num_X, num_row, num_col = X.shape
+        out = np.zeros(num_col * 2 * (self.kl - 1) * self.n, dtype=np.uint64)
+        self._chk(self.lib.fd_batch_input(self.h, _p(X, f64p), C.c_int(num_X), C.c_int(num_row), C.c_int(num_col),
+                                          C.c_double(scale), _p(out)))
+        return out
 
     def alias_checks(self, a, b, limbs, scale):
         """Value-semantics / aliasing self-checks inside the driver; returns the number of failed checks."""

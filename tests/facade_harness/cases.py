@@ -214,3 +214,93 @@ def case_value_semantics(r, d, rng, limbs=3):
     """destination == operand, deep copies, scalar vs vector encodings of a constant, plaintext mod switch."""
     x, _ = encrypt_batch(r, rng, 2, limbs)
     assert d.alias_checks(x[0].reshape(-1), x[1].reshape(-1), limbs, SCALE) == 0
+
+
+# ---- client-side pieces (SURVEY section 8(f) ranks 1, 3, 4): PRNG, seeded keys, wire format, Encryptor ----
+def case_prng(make_ref, make_drv):
+    """SEAL's Blake2xb PRNG stream and its uniform sampler with rejection, byte for byte."""
+    r, d = make_ref(5), make_drv(5)
+    rng = np.random.default_rng(100)
+    for _ in range(3):
+        seed = rng.integers(0, 2 ** 63, 8, dtype=np.uint64)
+        assert (d.prng_bytes(seed, 10007) == r.prng_bytes(seed, 10007)).all()      # crosses two 4096-byte refills
+        assert (d.sample_uniform(seed) == r.sample_uniform(seed)).all()
+
+
+def case_key_wire_format(make_ref, make_drv):
+    """RelinKeys / GaloisKeys / PublicKey streams of the stock library, plain and SEEDED (the form a client ships:
+    half the bytes), loaded by the facade == loaded by SEAL itself."""
+    seed = 9
+    r, d = make_ref(seed), make_drv(seed)
+    r.make_relin_key()
+    r.make_galois_keys([1, -2], conjugate=True)
+    digits = r.kl - 1
+    for seeded in (False, True):
+        blob = r.save_keys(0, seeded)
+        r.load_keys(0, blob)                       # SEAL's own loader (expands the seeds)
+        assert d.load_keys(0, blob) == (digits if seeded else 0)
+        assert (d.export_key(0) == r.export_relin_key()).all()
+        blob = r.save_keys(1, seeded, steps=[1, -2], conjugate=True)
+        r.load_keys(1, blob)
+        elts = r.galois_elts()
+        assert len(elts) == 3
+        assert d.load_keys(1, blob) == (3 * digits if seeded else 0)
+        for e in elts:
+            assert (d.export_key(1, e) == r.export_galois_key(e)).all()
+        blob = r.save_keys(2, seeded)
+        r.load_keys(2, blob)
+        d.load_keys(2, blob)
+        assert (d.export_key(2) == r.public_key()).all()
+    # a seeded stream is about half the size of the plain one
+    assert len(r.save_keys(0, True)) < 0.51 * len(r.save_keys(0, False)) + 4096
+
+
+def case_encrypt(make_ref, make_drv):
+    """Encryptor::encrypt with the same PRNG seed: SEAL's ciphertext bit for bit (u, e0, e1 from the same stream,
+    arithmetic one level up, division by the last prime with rounding)."""
+    seed = 13
+    r, d = make_ref(seed), make_drv(seed)
+    d.set_public_key(r.public_key())
+    rng = np.random.default_rng(101)
+    top = r.kl - 1
+    for limbs in (top, top - 1, 1):
+        v = rng.normal(size=r.n // 2)
+        pt = r.encode_real(v, SCALE, limbs)
+        got, exp = d.encrypt(pt, limbs, SCALE), r.encrypt(pt, limbs, SCALE)
+        assert (got == exp).all()
+    # and it decrypts
+    assert np.abs(r.decode(r.decrypt(got, 2, 1, SCALE), 1, SCALE).real - v).max() < 1e-4
+
+
+def case_ciphertext_wire_format(make_ref, make_drv):
+    seed = 17
+    r, d = make_ref(seed), make_drv(seed)
+    rng = np.random.default_rng(102)
+    top = r.kl - 1
+    pt = r.encode_real(rng.normal(size=r.n // 2), SCALE, top)
+    ct = r.encrypt(pt, top, SCALE)
+    blob = r.save_ciphertext(ct, 2, top, SCALE)
+    assert d.save_ciphertext(ct, 2, top, SCALE) == blob                      # byte-identical to Ciphertext::save
+    got = d.load_ciphertext(blob, 3 * r.kl * r.n)
+    assert (got[0] == ct).all() and got[1:] == (2, top, SCALE)
+    sq = r.eval(OP_SQUARE, ct, 2, top, SCALE)                                # size 3, squared scale, lower level
+    sq = r.eval(OP_MOD_SWITCH, sq[0], 3, top, sq[3])
+    blob = r.save_ciphertext(sq[0], 3, sq[2], sq[3])
+    assert d.save_ciphertext(sq[0], 3, sq[2], sq[3]) == blob
+    # the seeded form of a symmetric-key encryption (what a client ships as input): c1 expanded from the seed
+    blob = r.save_ciphertext_seeded(pt, top, SCALE)
+    exp = r.load_ciphertext(blob)
+    got = d.load_ciphertext(blob, 3 * r.kl * r.n)
+    assert (got[0] == exp[0]).all() and got[1:] == tuple(exp[1:])
+    assert len(blob) < 0.51 * len(r.save_ciphertext(ct, 2, top, SCALE)) + 256
+
+
+def case_batch_input(make_ref, make_drv):
+    """The reference's batch_input (M/source/matrix_mul/Batch_encode_encrypt.hpp:8-38), unchanged, through the
+    facade's CKKSEncoder + Encryptor == the same header on real SEAL."""
+    seed = 19
+    r, d = make_ref(seed), make_drv(seed)
+    d.set_public_key(r.public_key())
+    rng = np.random.default_rng(103)
+    X = rng.normal(size=(4, 8, 3))
+    assert (d.batch_input(X, SCALE) == r.batch_input(X, SCALE)).all()

@@ -22,6 +22,7 @@
 #include <vector>
 
 // the reference's own module code (include path: /root/reference/include)
+#include "source/matrix_mul/Batch_encode_encrypt.hpp"
 #include "source/matrix_mul/Ct_pt_matrix_mul.hpp"
 #include "source/matrix_mul/Ct_ct_matrix_mul.hpp"
 #include "source/non_linear_func/softmax.hpp" // pulls the facade's Bootstrapper.h / ckks_evaluator.h
@@ -42,6 +43,9 @@ namespace
         RelinKeys rlk;
         GaloisKeys glk;
         SecretKey sk;
+        PublicKey pk;
+        EncryptionParameters parms;
+        int device = 0;
         unique_ptr<Bootstrapper> boot;
         size_t n = 0;
         string err;
@@ -121,6 +125,8 @@ extern "C"
                 }
                 parms.set_coeff_modulus(m);
             }
+            d->parms = parms;
+            d->device = device;
             d->ctx = make_unique<SEALContext>(parms, true, sec_level_type::none, device);
             d->encoder = make_unique<CKKSEncoder>(*d->ctx);
             d->evaluator = make_unique<Evaluator>(*d->ctx, *d->encoder);
@@ -319,6 +325,178 @@ extern "C"
         *out_size = int(res.size());
         *out_limbs = int(res.coeff_modulus_size());
         *out_scale = res.scale();
+        FD_CATCH(d)
+    }
+
+    // ---- client-side pieces: PRNG, seeded keys, wire format, Encryptor --------------------------------------
+    int fd_prng_bytes(const uint64_t *seed8, int64_t n, uint8_t *out)
+    {
+        prng_seed_type seed;
+        copy_n(seed8, seed.size(), seed.begin());
+        Blake2xbPRNG prng(seed);
+        int64_t done = 0, piece = 5; // other piece sizes than the reference wrapper: the stream must not care
+        while (done < n)
+        {
+            int64_t take = min<int64_t>(piece, n - done);
+            prng.generate(size_t(take), out + done);
+            done += take;
+            piece = piece * 2 + 3;
+        }
+        return 0;
+    }
+    int fd_sample_uniform(void *h, const uint64_t *seed8, uint64_t *out)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        prng_seed_type seed;
+        copy_n(seed8, seed.size(), seed.begin());
+        auto &cm = d->ctx->key_context_data()->parms().coeff_modulus();
+        vector<uint64_t> primes;
+        for (auto &m : cm)
+        {
+            primes.push_back(m.value());
+        }
+        seal::util::sample_poly_uniform(make_shared<Blake2xbPRNG>(seed), primes, d->n, out);
+        FD_CATCH(d)
+    }
+    // same seeding rule as ref_create: every PRNG the context hands out starts from this seed
+    int fd_set_prng_seed(void *h, uint64_t seed)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        prng_seed_type s;
+        for (size_t i = 0; i < s.size(); i++)
+        {
+            s[i] = seed + 0x9E3779B97F4A7C15ULL * (i + 1);
+        }
+        d->parms.set_random_generator(make_shared<Blake2xbPRNGFactory>(s));
+        // keys already uploaded stay valid only for the old context: this is called right after fd_create
+        d->ctx = make_unique<SEALContext>(d->parms, true, sec_level_type::none, d->device);
+        d->encoder = make_unique<CKKSEncoder>(*d->ctx);
+        d->evaluator = make_unique<Evaluator>(*d->ctx, *d->encoder);
+        FD_CATCH(d)
+    }
+    int fd_set_public_key(void *h, const uint64_t *pk)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        d->pk.upload(*d->ctx, pk);
+        FD_CATCH(d)
+    }
+    // kind 0 = RelinKeys, 1 = GaloisKeys, 2 = PublicKey, in SEAL's wire format (seeded or not)
+    int fd_load_keys(void *h, int kind, const uint8_t *buf, int64_t n_bytes, int *seeded_digits)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        stringstream ss(string(reinterpret_cast<const char *>(buf), size_t(n_bytes)));
+        size_t seeded = 0;
+        if (kind == 0)
+        {
+            seeded = d->rlk.load(*d->ctx, ss);
+        }
+        else if (kind == 1)
+        {
+            seeded = d->glk.load(*d->ctx, ss);
+        }
+        else
+        {
+            d->pk.load(*d->ctx, ss);
+        }
+        if (seeded_digits)
+        {
+            *seeded_digits = int(seeded);
+        }
+        FD_CATCH(d)
+    }
+    // the device copy of a key back as raw residues: kind 0 relin [digits][2][kl][N], 1 Galois key of `elt`,
+    // 2 public key [2][kl][N]
+    int fd_export_key(void *h, int kind, uint32_t elt, uint64_t *out)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        const size_t kl = size_t(fd_n_key_limbs(h));
+        const uint64_t *src = kind == 0 ? d->rlk.device_key() : kind == 1 ? d->glk.device_key(elt) : d->pk.data();
+        if (!src)
+        {
+            throw invalid_argument("key not present");
+        }
+        const size_t words = (kind == 2 ? 1 : kl - 1) * 2 * kl * d->n;
+        seal::detail::chk(moai_memcpy_d2h(d->ctx->handle(), out, src, words * sizeof(uint64_t)));
+        FD_CATCH(d)
+    }
+    // Encryptor::encrypt of a raw plaintext -> [2][limbs][N]
+    int fd_encrypt(void *h, const uint64_t *pt_raw, int limbs, double scale, uint64_t *out)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        Plaintext pt;
+        pt.upload(*d->ctx, pt_raw, limbs, scale);
+        Encryptor enc(*d->ctx, d->pk);
+        Ciphertext ct;
+        enc.encrypt(pt, ct);
+        if (ct.size() != 2 || int(ct.coeff_modulus_size()) != limbs || ct.scale() != scale)
+        {
+            throw logic_error("unexpected ciphertext shape");
+        }
+        ct.download(out);
+        FD_CATCH(d)
+    }
+    int fd_save_ciphertext(void *h, const uint64_t *ct_raw, int size, int limbs, double scale, uint8_t *buf, int64_t *n_bytes)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        Ciphertext ct;
+        load_ct(*d, ct_raw, size, limbs, scale, ct);
+        stringstream ss;
+        const auto written = ct.save(ss);
+        string b = ss.str();
+        if (int64_t(b.size()) != int64_t(written) || int64_t(b.size()) > *n_bytes)
+        {
+            throw logic_error("save size mismatch");
+        }
+        memcpy(buf, b.data(), b.size());
+        *n_bytes = int64_t(b.size());
+        FD_CATCH(d)
+    }
+    int fd_load_ciphertext(void *h, const uint8_t *buf, int64_t n_bytes, uint64_t *ct_raw, int64_t cap_words, int *size,
+                           int *limbs, double *scale)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        stringstream ss(string(reinterpret_cast<const char *>(buf), size_t(n_bytes)));
+        Ciphertext ct;
+        ct.load(*d->ctx, ss);
+        if (int64_t(ct.size() * ct.coeff_modulus_size() * d->n) > cap_words)
+        {
+            throw invalid_argument("buffer too small");
+        }
+        ct.download(ct_raw);
+        *size = int(ct.size());
+        *limbs = int(ct.coeff_modulus_size());
+        *scale = ct.scale();
+        FD_CATCH(d)
+    }
+    // the reference's batch_input (Batch_encode_encrypt.hpp:8-38), unchanged, through the facade
+    int fd_batch_input(void *h, const double *X, int num_X, int num_row, int num_col, double scale, uint64_t *out)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        vector<vector<vector<double>>> Xv(num_X, vector<vector<double>>(num_row, vector<double>(num_col)));
+        for (int j = 0; j < num_X; j++)
+        {
+            for (int k = 0; k < num_row; k++)
+            {
+                for (int i = 0; i < num_col; i++)
+                {
+                    Xv[j][k][i] = X[(size_t(j) * num_row + k) * num_col + i];
+                }
+            }
+        }
+        vector<Ciphertext> res = batch_input(Xv, num_X, num_row, num_col, scale, *d->ctx, d->pk);
+        for (size_t i = 0; i < res.size(); i++)
+        {
+            res[i].download(out + i * 2 * res[i].coeff_modulus_size() * d->n);
+        }
         FD_CATCH(d)
     }
 

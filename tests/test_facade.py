@@ -38,8 +38,8 @@ def deep(sealref_deep):
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="needs the reference's headers")
 def test_reference_headers_compile_unchanged_against_the_facade(tmp_path):
-    """Every module header of the reference except the client-side Batch_encode_encrypt.hpp (Encryptor)
-    compiles as it is with include/facade first on the include path — including softmax.hpp and
+    """EVERY module header of the reference compiles as it is with include/facade first on the include path —
+    including the client-side Batch_encode_encrypt.hpp (Encryptor, PublicKey) and softmax.hpp /
     single_att_block.hpp, which do NOT compile against stock SEAL here (they need NTL through Bootstrapper.h)."""
     src = tmp_path / "tu.cpp"
     src.write_text("""
@@ -50,6 +50,7 @@ def test_reference_headers_compile_unchanged_against_the_facade(tmp_path):
 #include <chrono>
 #include <omp.h>
 #include <sys/time.h>
+#include "source/matrix_mul/Batch_encode_encrypt.hpp"
 #include "source/matrix_mul/Ct_pt_matrix_mul.hpp"
 #include "source/matrix_mul/Ct_ct_matrix_mul.hpp"
 #include "source/non_linear_func/softmax.hpp"
@@ -136,3 +137,21 @@ def test_fused_ct_pt_matmul_shadow_header(sealref_small, variant):
     pack / one-call / unpack glue all fused wrappers share."""
     from facade_harness import cases
     cases.case_ct_pt(sealref_small, _driver(sealref_small, fused=True), np.random.default_rng(60 + variant), variant)
+
+
+# ---- client-side pieces: PRNG, seeded keys, wire format, Encryptor, batch_input ----
+def _makers(mock):
+    import facade_harness as facade
+    from oracle import SealRef, have_ref
+    from conftest import SMALL_BITS, SMALL_LOGN
+    if not have_ref() or not facade.available(mock=mock):
+        pytest.skip("oracle/_ref or the facade driver is not built")
+    return (lambda seed: SealRef(SMALL_LOGN, SMALL_BITS, hamming_weight=0, seed=seed),
+            lambda seed: facade.FacadeDriver(SMALL_LOGN, bits=SMALL_BITS, mock=mock, prng_seed=seed))
+
+
+@pytest.mark.parametrize("case", ["case_prng", "case_key_wire_format", "case_encrypt", "case_ciphertext_wire_format",
+                                  "case_batch_input"])
+def test_client_side(case):
+    from facade_harness import cases
+    getattr(cases, case)(*_makers(mock=True))

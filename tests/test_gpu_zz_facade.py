@@ -170,3 +170,21 @@ def test_fused_ct_ct_matmul(deep_fused, which):
 def test_fused_exp_inverse(deep_fused):
     from facade_harness import cases
     cases.case_exp_inverse(*deep_fused, np.random.default_rng(95))
+
+
+# ---- client-side pieces: PRNG, seeded keys, wire format, Encryptor, batch_input ----
+def _makers(mock):
+    import facade_harness as facade
+    from oracle import SealRef, have_ref
+    from conftest import SMALL_BITS, SMALL_LOGN
+    if not have_ref() or not facade.available(mock=mock):
+        pytest.skip("oracle/_ref or the facade driver is not built")
+    return (lambda seed: SealRef(SMALL_LOGN, SMALL_BITS, hamming_weight=0, seed=seed),
+            lambda seed: facade.FacadeDriver(SMALL_LOGN, bits=SMALL_BITS, mock=mock, prng_seed=seed))
+
+
+@pytest.mark.parametrize("case", ["case_prng", "case_key_wire_format", "case_encrypt", "case_ciphertext_wire_format",
+                                  "case_batch_input"])
+def test_client_side(case):
+    from facade_harness import cases
+    getattr(cases, case)(*_makers(mock=False))
