@@ -322,8 +322,9 @@ extern "C"
     {
         API_BEGIN
         Context *c = get(ctx);
+        // limbs == key limbs is the key level: dividing by the special prime with rounding is how a fresh
+        // public-key encryption comes down to the first data level (S/encryptor.cpp:122-150)
         check_shape(c, batch, size, limbs);
-        MOAI_REQUIRE(limbs <= c->kl - 1, "encrypted is not valid for encryption parameters");
         rescale(c, CU(in), U(out), batch, size, limbs);
         API_END
     }

@@ -187,4 +187,13 @@ def _makers(mock):
                                   "case_batch_input"])
 def test_client_side(case):
     from facade_harness import cases
+    if case == "case_batch_input" and not _ENCRYPT_OK:
+        # the reference's batch_input encrypts inside `#pragma omp parallel for`: an exception there terminates
+        # the process (the reference never catches), so it only runs once Encryptor::encrypt is known to work
+        pytest.skip("Encryptor::encrypt did not pass")
     getattr(cases, case)(*_makers(mock=False))
+    if case == "case_encrypt":
+        globals()["_ENCRYPT_OK"] = True
+
+
+_ENCRYPT_OK = False
