@@ -18,7 +18,9 @@
 //   * There is no CPU arithmetic path: without a CUDA device SEALContext's constructor throws.
 //     The one host computation is CKKSEncoder::decode (CRT composition + FFT of a downloaded
 //     plaintext) — in the reference that call only feeds debug prints (layernorm.hpp:279-310).
-//   * KeyGenerator is NOT provided: key generation stays in stock SEAL on the client.
+//   * A deployment generates its keys on the client with stock SEAL; KeyGenerator exists
+//     here so that the reference's driver and test programs, which create keys in the function that evaluates,
+//     compile unchanged (with the same PRNG seed it yields SEAL's keys bit for bit).
 //     Keys and ciphertexts cross the boundary either as raw residues (Ciphertext::upload / download,
 //     RelinKeys::upload, GaloisKeys::upload, PublicKey::upload, SecretKey::upload; SEAL's own layouts,
 //     S/ciphertext.h:339-370, S/kswitchkeys.h:335-340) or in SEAL's wire format: Ciphertext::save / load,
@@ -288,6 +290,11 @@ namespace sealapi
         const std::vector<Modulus> &coeff_modulus() const noexcept
         {
             return coeff_modulus_;
+        }
+        // CKKS has no plaintext modulus (S/encryptionparams.h:240-262); present for code that prints parameters
+        Modulus plain_modulus() const noexcept
+        {
+            return Modulus(0);
         }
         const parms_id_type &parms_id() const noexcept
         {
@@ -2310,6 +2317,215 @@ namespace sealapi
         const SEALContext &ctx_;
         std::unique_ptr<CKKSEncoder> own_encoder_;
         const CKKSEncoder &encoder_;
+    };
+
+    // ------------------------------------------------------------------------------------------
+    // KeyGenerator (S/keygenerator.cpp:56-336, S/util/rlwe.cpp:311-430) — so that the reference's driver and test
+    // programs (M/test/**), which create their keys in the same function that evaluates, compile unchanged.
+    // A deployment generates keys on the client with stock SEAL; with the same PRNG seed this class produces SEAL's
+    // keys bit for bit (dense ternary secrets; for the fork's sparse secrets see sample_poly_sparse_ternary).
+    // Randomness on the host in SEAL's order, arithmetic on the device:
+    //   pk / every key-switching digit:  seed <- prng (64 bytes);  a <- uniform(Blake2xb(seed));  e <- chi(prng);
+    //                                    (c0, c1) = (-(a s + e), a);   digit i:  c0[limb i] += (P mod q_i) * key'[limb i]
+    // ------------------------------------------------------------------------------------------
+    class KeyGenerator
+    {
+    public:
+        explicit KeyGenerator(const SEALContext &ctx) : ctx_(ctx)
+        {
+            auto &c = ctx_.impl();
+            const std::size_t kl = c->key_limbs(), n = c->n;
+            auto &parms = ctx_.key_context_data()->parms();
+            std::vector<std::uint64_t> s(kl * n);
+            auto prng = parms.random_generator()->create();
+            if (!parms.secret_key_hamming_weight())
+            {
+                util::sample_poly_ternary(prng, c->primes, n, s.data());
+            }
+            else
+            {
+                util::sample_poly_sparse_ternary(prng, c->primes, n, parms.secret_key_hamming_weight(), s.data());
+            }
+            detail::DeviceBlock d;
+            d.ensure(c, kl * n);
+            sk_host_.resize(kl * n);
+            {
+                detail::Lock lk(c->mu);
+                detail::chk(moai_memcpy_h2d(c->h, d.ptr(), s.data(), s.size() * sizeof(std::uint64_t)));
+                detail::chk(moai_ntt_forward(c->h, d.ptr(), 1, 1, static_cast<std::int32_t>(kl)));
+                detail::chk(moai_memcpy_d2h(c->h, sk_host_.data(), d.ptr(), s.size() * sizeof(std::uint64_t)));
+            }
+            sk_.upload(ctx_, sk_host_.data());
+        }
+
+        const SecretKey &secret_key() const
+        {
+            return sk_;
+        }
+        void create_public_key(PublicKey &destination) const
+        {
+            auto &c = ctx_.impl();
+            detail::DeviceBlock pk;
+            pk.ensure(c, 2 * c->key_limbs() * c->n);
+            encrypt_zero_symmetric(pk.ptr());
+            std::vector<std::uint64_t> host(2 * c->key_limbs() * c->n);
+            {
+                detail::Lock lk(c->mu);
+                detail::chk(moai_memcpy_d2h(c->h, host.data(), pk.ptr(), host.size() * sizeof(std::uint64_t)));
+            }
+            destination.upload(ctx_, host.data());
+        }
+        void create_relin_keys(RelinKeys &destination) const
+        {
+            auto &c = ctx_.impl();
+            const std::int32_t kl = static_cast<std::int32_t>(c->key_limbs());
+            detail::DeviceBlock s2;
+            s2.ensure(c, c->key_limbs() * c->n);
+            {
+                detail::Lock lk(c->mu); // s^2 (compute_secret_key_array, S/keygenerator.cpp:232-290)
+                detail::chk(moai_multiply_plain(c->h, sk_.data(), sk_.data(), s2.ptr(), 1, 1, kl, 0));
+            }
+            std::vector<std::uint64_t> key = one_kswitch_key(s2.ptr());
+            destination.upload(ctx_, key.data());
+        }
+        void create_galois_keys(const std::vector<std::uint32_t> &galois_elts, GaloisKeys &destination) const
+        {
+            auto &c = ctx_.impl();
+            const std::size_t kl = c->key_limbs(), n = c->n;
+            GaloisKeys fresh;
+            for (std::uint32_t elt : galois_elts)
+            {
+                if (!(elt & 1) || elt >= 2 * n)
+                {
+                    throw std::invalid_argument("Galois element is not valid");
+                }
+                if (fresh.has_key(elt))
+                {
+                    continue;
+                }
+                // apply_galois_ntt on the secret (S/util/galois.cpp:18-55, 192-218): result[i] = s[table[i]]
+                std::vector<std::uint64_t> rot(kl * n);
+                for (std::size_t i = 0; i < n; i++)
+                {
+                    const std::uint64_t reversed = 2 * reverse_bits(i, c->log_n) + 1;
+                    const std::uint64_t index_raw = ((std::uint64_t(elt) * reversed) >> 1) & (n - 1);
+                    const std::size_t src = reverse_bits(static_cast<std::size_t>(index_raw), c->log_n);
+                    for (std::size_t l = 0; l < kl; l++)
+                    {
+                        rot[l * n + i] = sk_host_[l * n + src];
+                    }
+                }
+                detail::DeviceBlock d;
+                d.ensure(c, kl * n);
+                {
+                    detail::Lock lk(c->mu);
+                    detail::chk(moai_memcpy_h2d(c->h, d.ptr(), rot.data(), rot.size() * sizeof(std::uint64_t)));
+                    detail::chk(moai_synchronize(c->h));
+                }
+                std::vector<std::uint64_t> key = one_kswitch_key(d.ptr());
+                fresh.upload(ctx_, elt, key.data());
+            }
+            destination = std::move(fresh);
+        }
+        void create_galois_keys(const std::vector<int> &steps, GaloisKeys &destination) const
+        {
+            std::vector<std::uint32_t> elts;
+            auto &c = ctx_.impl();
+            detail::Lock lk(c->mu);
+            for (int st : steps)
+            {
+                std::uint32_t e = 0;
+                detail::chk(moai_galois_elt_from_step(c->h, st, &e));
+                elts.push_back(e);
+            }
+            create_galois_keys(elts, destination);
+        }
+        // all power-of-two rotations and the conjugation (GaloisTool::get_elts_all, S/util/galois.cpp:106-131)
+        void create_galois_keys(GaloisKeys &destination) const
+        {
+            const std::uint64_t m = 2 * std::uint64_t(ctx_.impl()->n);
+            std::vector<std::uint32_t> elts{ static_cast<std::uint32_t>(m - 1) };
+            std::uint64_t pos = 5, neg = 1;
+            while ((neg * 5) % m != 1)
+            {
+                neg += 2; // 5^-1 mod 2N (found once; m is a power of two, the inverse is odd)
+            }
+            for (int i = 0; i < ctx_.impl()->log_n - 1; i++)
+            {
+                elts.push_back(static_cast<std::uint32_t>(pos));
+                pos = (pos * pos) & (m - 1);
+                elts.push_back(static_cast<std::uint32_t>(neg));
+                neg = (neg * neg) & (m - 1);
+            }
+            create_galois_keys(elts, destination);
+        }
+
+    private:
+        static std::size_t reverse_bits(std::size_t v, int bits)
+        {
+            std::size_t r = 0;
+            for (int i = 0; i < bits; i++)
+            {
+                r = (r << 1) | ((v >> i) & 1);
+            }
+            return r;
+        }
+        // encrypt_zero_symmetric at the key level, NTT form, into dst [2][kl][N] (device)
+        void encrypt_zero_symmetric(std::uint64_t *dst) const
+        {
+            auto &c = ctx_.impl();
+            const std::size_t kl = c->key_limbs(), n = c->n;
+            const std::int32_t l32 = static_cast<std::int32_t>(kl);
+            auto bootstrap_prng = ctx_.key_context_data()->parms().random_generator()->create();
+            prng_seed_type public_seed;
+            bootstrap_prng->generate(prng_seed_byte_count, reinterpret_cast<seal_byte *>(public_seed.data()));
+            std::vector<std::uint64_t> a(kl * n), e(kl * n);
+            util::sample_poly_uniform(UniformRandomGeneratorFactory::DefaultFactory()->create(public_seed), c->primes, n, a.data());
+            util::sample_poly_cbd(bootstrap_prng, c->primes, n, e.data());
+            detail::DeviceBlock de;
+            de.ensure(c, kl * n);
+            std::uint64_t *c0 = dst, *c1 = dst + kl * n;
+            detail::Lock lk(c->mu);
+            detail::chk(moai_memcpy_h2d(c->h, c1, a.data(), a.size() * sizeof(std::uint64_t)));
+            detail::chk(moai_memcpy_h2d(c->h, de.ptr(), e.data(), e.size() * sizeof(std::uint64_t)));
+            detail::chk(moai_ntt_forward(c->h, de.ptr(), 1, 1, l32));
+            detail::chk(moai_multiply_plain(c->h, c1, sk_.data(), c0, 1, 1, l32, 0)); // a s
+            detail::chk(moai_add(c->h, de.ptr(), c0, c0, 1, 1, l32));                  // + e
+            detail::chk(moai_negate(c->h, c0, c0, 1, 1, l32));                         // -(a s + e)
+            detail::chk(moai_synchronize(c->h));
+        }
+        // generate_one_kswitch_key (S/keygenerator.cpp:292-336): host copy [digits][2][kl][N]
+        std::vector<std::uint64_t> one_kswitch_key(const std::uint64_t *new_key_dev) const
+        {
+            auto &c = ctx_.impl();
+            if (!ctx_.using_keyswitching())
+            {
+                throw std::logic_error("keyswitching is not supported by the context");
+            }
+            const std::size_t kl = c->key_limbs(), n = c->n, digits = kl - 1, per = 2 * kl * n;
+            const std::int32_t l32 = static_cast<std::int32_t>(kl);
+            detail::DeviceBlock all, tmp;
+            all.ensure(c, digits * per);
+            tmp.ensure(c, kl * n);
+            for (std::size_t i = 0; i < digits; i++)
+            {
+                std::uint64_t *dst = all.ptr() + i * per;
+                encrypt_zero_symmetric(dst);
+                std::vector<std::uint64_t> consts(kl, 0);
+                consts[i] = c->primes[kl - 1] % c->primes[i]; // P mod q_i
+                detail::Lock lk(c->mu);
+                detail::chk(moai_multiply_scalar(c->h, new_key_dev, consts.data(), tmp.ptr(), 1, 1, l32));
+                detail::chk(moai_add(c->h, dst, tmp.ptr(), dst, 1, 1, l32));
+            }
+            std::vector<std::uint64_t> host(digits * per);
+            detail::Lock lk(c->mu);
+            detail::chk(moai_memcpy_d2h(c->h, host.data(), all.ptr(), host.size() * sizeof(std::uint64_t)));
+            return host;
+        }
+
+        const SEALContext &ctx_;
+        SecretKey sk_;
+        std::vector<std::uint64_t> sk_host_;
     };
 
     // ------------------------------------------------------------------------------------------

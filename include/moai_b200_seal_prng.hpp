@@ -470,6 +470,35 @@ namespace sealapi
             }
         }
 
+        // the fork's sparse ternary secret of a given Hamming weight (S/util/rlwe.cpp:40-72).  The reference draws
+        // positions from [0, n] INCLUSIVE and indexes destination[n] when n comes up (one element past the first
+        // limb: undefined behaviour, probability weight/(n+1) per key); that draw is skipped here, every other
+        // draw is consumed exactly as the reference does.
+        inline void sample_poly_sparse_ternary(const std::shared_ptr<UniformRandomGenerator> &prng,
+                                               const std::vector<std::uint64_t> &primes, std::size_t n,
+                                               std::size_t hamming_weight, std::uint64_t *destination)
+        {
+            RandomToStandardAdapter engine(prng);
+            std::uniform_int_distribution<std::uint64_t> dist(0, 1), dist_non_zero_position(0, n);
+            std::fill(destination, destination + primes.size() * n, std::uint64_t(0));
+            std::size_t current_weight = 0;
+            while (current_weight < hamming_weight)
+            {
+                const std::size_t index = static_cast<std::size_t>(dist_non_zero_position(engine));
+                if (index >= n || destination[index] != 0)
+                {
+                    continue;
+                }
+                const std::uint64_t nonzero_rand = 2 * dist(engine);
+                const std::uint64_t flag = static_cast<std::uint64_t>(-static_cast<std::int64_t>(nonzero_rand == 0));
+                for (std::size_t j = 0; j < primes.size(); j++)
+                {
+                    destination[j * n + index] = nonzero_rand + (flag & primes[j]) - 1;
+                }
+                current_weight++;
+            }
+        }
+
         // e <- centred binomial with sigma 3.2 (S/util/rlwe.cpp:104-135), SEAL's default noise
         inline void sample_poly_cbd(const std::shared_ptr<UniformRandomGenerator> &prng,
                                     const std::vector<std::uint64_t> &primes, std::size_t n, std::uint64_t *destination)

@@ -37,7 +37,8 @@ class FacadeError(RuntimeError):
 
 
 class FacadeDriver:
-    def __init__(self, log_n, bits=None, primes=None, mock=True, device=0, fused=False, prng_seed=None):
+    def __init__(self, log_n, bits=None, primes=None, mock=True, device=0, fused=False, prng_seed=None,
+                 hamming_weight=0):
         path = _path(mock, fused)
         self.lib = C.CDLL(path)
         L = self.lib
@@ -53,7 +54,7 @@ class FacadeDriver:
         if not L.fd_ok(self.h):
             raise FacadeError("fd_create: " + L.fd_error(self.h).decode())
         if prng_seed is not None:
-            self.set_prng_seed(prng_seed)       # same seeding rule as oracle.SealRef(seed=...)
+            self.set_prng_seed(prng_seed, hamming_weight)       # same seeding rule as oracle.SealRef(seed=...)
         self.kl = L.fd_n_key_limbs(self.h)
         q = np.zeros(self.kl, dtype=np.uint64)
         L.fd_primes(self.h, _p(q))
@@ -111,8 +112,8 @@ class FacadeDriver:
         self._chk(self.lib.fd_sample_uniform(self.h, _p(s), _p(out)))
         return out
 
-    def set_prng_seed(self, seed):
-        self._chk(self.lib.fd_set_prng_seed(self.h, C.c_uint64(seed)))
+    def set_prng_seed(self, seed, hamming_weight=0):
+        self._chk(self.lib.fd_set_prng_seed(self.h, C.c_uint64(seed), C.c_int(hamming_weight)))
 
     def set_public_key(self, pk):
         self._chk(self.lib.fd_set_public_key(self.h, _p(np.ascontiguousarray(pk, dtype=np.uint64))))
@@ -129,6 +130,21 @@ class FacadeDriver:
         out = np.zeros(words, dtype=np.uint64)
         self._chk(self.lib.fd_export_key(self.h, C.c_int(kind), C.c_uint32(elt), _p(out)))
         return out
+
+    def keygen(self, steps=None, conjugate=False):
+        if steps is None:
+            self._chk(self.lib.fd_keygen(self.h, None, C.c_int(0), C.c_int(0)))
+        else:
+            arr = (C.c_int * max(1, len(steps)))(*steps)
+            self._chk(self.lib.fd_keygen(self.h, arr, C.c_int(len(steps)), C.c_int(int(conjugate))))
+
+    def export_secret(self):
+        out = np.zeros(self.kl * self.n, dtype=np.uint64)
+        self._chk(self.lib.fd_export_secret(self.h, _p(out)))
+        return out
+
+    def has_galois(self, elt):
+        return bool(self.lib.fd_has_galois(self.h, C.c_uint32(elt)))
 
     def encrypt(self, pt, limbs, scale):
         out = np.zeros(2 * limbs * self.n, dtype=np.uint64)
@@ -285,3 +301,11 @@ class FacadeDriver:
                                            C.c_int(input_num), C.c_int(iters), C.c_int(layer_id), _p(out), C.byref(ol),
                                            C.byref(osc)))
         return out[: num * 2 * ol.value * self.n].copy(), ol.value, osc.value
+
+
+def reference_seal_ckks_test(mock=True, fused=False):
+    """Runs the reference's own SEAL_ckks_test() through the facade; returns (ok, printed text)."""
+    lib = C.CDLL(_path(mock, fused))
+    buf = C.create_string_buffer(1 << 16)
+    rc = lib.fd_reference_seal_ckks_test(buf, C.c_int(1 << 16))
+    return rc == 0, buf.value.decode(errors="replace")

@@ -304,3 +304,45 @@ def case_batch_input(make_ref, make_drv):
     rng = np.random.default_rng(103)
     X = rng.normal(size=(4, 8, 3))
     assert (d.batch_input(X, SCALE) == r.batch_input(X, SCALE)).all()
+
+
+def case_keygen(make_ref, make_drv):
+    """KeyGenerator with the same PRNG seed: SEAL's secret key, public key, relinearisation key and Galois keys bit
+    for bit; the keys work (a rotation with the generated key equals SEAL's)."""
+    seed = 23
+    r, d = make_ref(seed), make_drv(seed)
+    r.make_relin_key()
+    r.make_galois_keys([1, -2, 16], conjugate=True)
+    d.keygen(steps=[1, -2, 16], conjugate=True)
+    assert (d.export_secret() == r.secret_key()).all()
+    assert (d.export_key(2) == r.public_key()).all()
+    assert (d.export_key(0) == r.export_relin_key()).all()
+    elts = r.galois_elts()
+    assert len(elts) == 4
+    for e in elts:
+        assert (d.export_key(1, e) == r.export_galois_key(e)).all()
+    rng = np.random.default_rng(104)
+    x, _ = encrypt_batch(r, rng, 1, 2)
+    a = x[0].reshape(-1)
+    same(d.eval(OP_ROTATE, a, 2, 2, SCALE, iarg=16), r.eval(OP_ROTATE, a, 2, 2, SCALE, iarg=16))
+    sq = r.eval(OP_SQUARE, a, 2, 2, SCALE)
+    same(d.eval(OP_RELINEARIZE, sq[0], 3, 2, sq[3]), r.eval(OP_RELINEARIZE, sq[0], 3, 2, sq[3]))
+    # the default key set of create_galois_keys(GaloisKeys&): conjugation and +-2^k (S/util/galois.cpp:106-131)
+    d2 = make_drv(seed)
+    d2.keygen()
+    n2 = 2 * r.n
+    want = {n2 - 1}
+    pos, neg = 5, pow(5, -1, n2)
+    for _ in range(r.log_n - 1):
+        want |= {pos, neg}
+        pos, neg = pos * pos % n2, neg * neg % n2
+    assert all(d2.has_galois(e) for e in want) and not d2.has_galois(3 if 3 not in want else 7)
+
+
+def case_keygen_sparse(make_ref_sparse, make_drv_sparse):
+    """The fork's sparse ternary secret (Hamming weight h, M/test/test_full_scheme.hpp:366): same key as SEAL."""
+    seed = 29
+    r, d = make_ref_sparse(seed), make_drv_sparse(seed)
+    d.keygen(steps=[1])
+    sk = d.export_secret()
+    assert (sk == r.secret_key()).all()

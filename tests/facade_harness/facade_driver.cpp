@@ -21,14 +21,10 @@
 #include <sys/time.h>
 #include <vector>
 
-// the reference's own module code (include path: /root/reference/include)
-#include "source/matrix_mul/Batch_encode_encrypt.hpp"
-#include "source/matrix_mul/Ct_pt_matrix_mul.hpp"
-#include "source/matrix_mul/Ct_ct_matrix_mul.hpp"
-#include "source/non_linear_func/softmax.hpp" // pulls the facade's Bootstrapper.h / ckks_evaluator.h
-#include "source/non_linear_func/layernorm.hpp"
-#include "source/non_linear_func/gelu_others.hpp"
-#include "source/att_block/single_att_block.hpp"
+// The reference's own code, all of it: M/include.hpp pulls "seal/seal.h" (the facade), every module header under
+// M/source/ and every test / driver header under M/test/ (all_layer_test, SEAL_ckks_test, ...) — unmodified.
+// (include path: include/facade [+ include/facade_fused] before /root/reference/include)
+#include "include.hpp"
 
 using namespace seal;
 using namespace std;
@@ -360,10 +356,11 @@ extern "C"
         FD_CATCH(d)
     }
     // same seeding rule as ref_create: every PRNG the context hands out starts from this seed
-    int fd_set_prng_seed(void *h, uint64_t seed)
+    int fd_set_prng_seed(void *h, uint64_t seed, int hamming_weight)
     {
         auto d = static_cast<Drv *>(h);
         FD_TRY
+        d->parms.set_secret_key_hamming_weight(size_t(hamming_weight));
         prng_seed_type s;
         for (size_t i = 0; i < s.size(); i++)
         {
@@ -424,6 +421,53 @@ extern "C"
         seal::detail::chk(moai_memcpy_d2h(d->ctx->handle(), out, src, words * sizeof(uint64_t)));
         FD_CATCH(d)
     }
+    // KeyGenerator of the facade: secret key, public key, relinearisation key, Galois keys for `steps`
+    // (+ conjugation), or — steps == nullptr — the default set of create_galois_keys(GaloisKeys&)
+    int fd_keygen(void *h, const int *steps, int n_steps, int with_conjugate)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        KeyGenerator keygen(*d->ctx);
+        d->sk = keygen.secret_key();
+        keygen.create_public_key(d->pk);
+        keygen.create_relin_keys(d->rlk);
+        if (steps)
+        {
+            vector<uint32_t> elts;
+            for (int i = 0; i < n_steps; i++)
+            {
+                uint32_t e = 0;
+                seal::detail::chk(moai_galois_elt_from_step(d->ctx->handle(), steps[i], &e));
+                elts.push_back(e);
+            }
+            if (with_conjugate)
+            {
+                elts.push_back(uint32_t(2 * d->n - 1));
+            }
+            keygen.create_galois_keys(elts, d->glk);
+        }
+        else
+        {
+            keygen.create_galois_keys(d->glk);
+        }
+        FD_CATCH(d)
+    }
+    int fd_export_secret(void *h, uint64_t *out)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        if (!d->sk.data())
+        {
+            throw invalid_argument("secret key not present");
+        }
+        seal::detail::chk(moai_memcpy_d2h(d->ctx->handle(), out, d->sk.data(), size_t(fd_n_key_limbs(h)) * d->n * sizeof(uint64_t)));
+        FD_CATCH(d)
+    }
+    int fd_has_galois(void *h, uint32_t elt)
+    {
+        return static_cast<Drv *>(h)->glk.has_key(elt) ? 1 : 0;
+    }
+
     // Encryptor::encrypt of a raw plaintext -> [2][limbs][N]
     int fd_encrypt(void *h, const uint64_t *pt_raw, int limbs, double scale, uint64_t *out)
     {
@@ -498,6 +542,28 @@ extern "C"
             res[i].download(out + i * 2 * res[i].coeff_modulus_size() * d->n);
         }
         FD_CATCH(d)
+    }
+
+    // The reference's own test program SEAL_ckks_test (M/test/test_SEAL_ckks.hpp:106-250: key generation, encode,
+    // encrypt, PI*x^3 + 0.4x + 1 with relinearisation and rescaling, decrypt, decode at N = 8192), UNMODIFIED, on this
+    // backend; returns what it printed.
+    int fd_reference_seal_ckks_test(char *printed, int cap)
+    {
+        try
+        {
+            CoutMute capture;
+            SEAL_ckks_test();
+            string s = capture.sink.str();
+            strncpy(printed, s.c_str(), size_t(cap) - 1);
+            printed[cap - 1] = 0;
+        }
+        catch (const exception &e)
+        {
+            strncpy(printed, e.what(), size_t(cap) - 1);
+            printed[cap - 1] = 0;
+            return -1;
+        }
+        return 0;
     }
 
     // Value semantics and aliasing (S/ciphertext.h:701-715, S/evaluator.cpp:155-240): destination == operand

@@ -38,31 +38,21 @@ def deep(sealref_deep):
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="needs the reference's headers")
 def test_reference_headers_compile_unchanged_against_the_facade(tmp_path):
-    """EVERY module header of the reference compiles as it is with include/facade first on the include path —
-    including the client-side Batch_encode_encrypt.hpp (Encryptor, PublicKey) and softmax.hpp /
-    single_att_block.hpp, which do NOT compile against stock SEAL here (they need NTL through Bootstrapper.h)."""
+    """The reference's WHOLE source — M/include.hpp: every module header and every test / driver program, including
+    all_layer_test (M/test/test_full_scheme.hpp) — compiles as it is with include/facade first on the include path;
+    also with include/facade_fused in front (module functions bound to the fused pipelines).  softmax.hpp,
+    single_att_block.hpp and the drivers do NOT compile against stock SEAL in this image (NTL through Bootstrapper.h)."""
     src = tmp_path / "tu.cpp"
+    # M/include.hpp is the reference's umbrella header: seal/seal.h, every module header under M/source/ and every
+    # test / driver header under M/test/ (all_layer_test, the matmul tests, SEAL_ckks_test)
     src.write_text("""
-#include "seal/seal.h"
-#include <iostream>
-#include <vector>
-#include <cmath>
-#include <chrono>
-#include <omp.h>
-#include <sys/time.h>
-#include "source/matrix_mul/Batch_encode_encrypt.hpp"
-#include "source/matrix_mul/Ct_pt_matrix_mul.hpp"
-#include "source/matrix_mul/Ct_ct_matrix_mul.hpp"
-#include "source/non_linear_func/softmax.hpp"
-#include "source/non_linear_func/layernorm.hpp"
-#include "source/non_linear_func/gelu.hpp"
-#include "source/non_linear_func/gelu_others.hpp"
-#include "source/att_block/single_att_block.hpp"
-int main() { return 0; }
+#include "include.hpp"
+int main() { all_layer_test(); return 0; }
 """)
     inc = os.path.join(ROOT, "include")
-    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-fsyntax-only", "-fopenmp", "-w", "-I" + os.path.join(inc, "facade"),
-                           "-I" + inc, "-I" + os.path.join(REF, "include"), str(src)])
+    for extra in ([], ["-I" + os.path.join(inc, "facade_fused")]):
+        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-fsyntax-only", "-fopenmp", "-w"] + extra +
+                              ["-I" + os.path.join(inc, "facade"), "-I" + inc, "-I" + os.path.join(REF, "include"), str(src)])
 
 
 def test_facade_fails_loudly_without_a_device():
@@ -151,7 +141,43 @@ def _makers(mock):
 
 
 @pytest.mark.parametrize("case", ["case_prng", "case_key_wire_format", "case_encrypt", "case_ciphertext_wire_format",
-                                  "case_batch_input"])
+                                  "case_batch_input", "case_keygen"])
 def test_client_side(case):
     from facade_harness import cases
     getattr(cases, case)(*_makers(mock=True))
+
+
+def test_keygen_sparse_secret():
+    import facade_harness as facade
+    from facade_harness import cases
+    from oracle import SealRef, have_ref
+    from conftest import SMALL_BITS, SMALL_LOGN
+    if not have_ref() or not facade.available(mock=True):
+        pytest.skip("oracle/_ref or the facade driver is not built")
+    cases.case_keygen_sparse(lambda seed: SealRef(SMALL_LOGN, SMALL_BITS, hamming_weight=64, seed=seed),
+                             lambda seed: facade.FacadeDriver(SMALL_LOGN, bits=SMALL_BITS, mock=True, prng_seed=seed,
+                                                              hamming_weight=64))
+
+
+def test_reference_program_seal_ckks_test_runs_unmodified():
+    """The reference's own test program SEAL_ckks_test() (M/test/test_SEAL_ckks.hpp:106-250) — KeyGenerator,
+    CKKSEncoder, Encryptor, Evaluator (square, relinearize, rescale, multiply_plain, mod_switch, add), Decryptor,
+    decode at N = 8192 with a {60, 40, 40, 60}-bit chain — compiled as it is against the facade (the driver includes
+    the reference's whole M/include.hpp) and run: the vector it prints as computed equals the one it prints as
+    expected, and the exact scales it prints are the ones stock SEAL prints for this example."""
+    import re
+    import facade_harness as facade
+    if not facade.available(mock=True):
+        pytest.skip("facade driver not built (needs /root/reference at build time)")
+    ok, text = facade.reference_seal_ckks_test(mock=True)
+    assert ok, text
+    vecs = re.findall(r"\[ ([-0-9., ]+)\.\.\., ([-0-9., ]+) \]", text)
+    assert len(vecs) == 3, text                                   # input, expected, computed
+    nums = [[float(v) for v in (a + b).replace(" ", "").strip(",").split(",")] for a, b in vecs]
+    expected, computed = np.array(nums[1]), np.array(nums[2])
+    assert expected.shape == computed.shape == (6,)
+    assert np.abs(expected - computed).max() < 1e-5, (expected, computed)
+    assert abs(expected[-1] - 4.5415926) < 1e-6
+    assert "Exact scale in PI*x^3: 1099512659965.7514648438" in text     # SEAL's own printed values
+    assert "Exact scale in  0.4*x: 1099511775231.0197753906" in text
+    assert "Modulus chain index for x3_encrypted: 0" in text and "coeff_modulus size: 200 (60 + 40 + 40 + 60) bits" in text
