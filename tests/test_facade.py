@@ -181,3 +181,24 @@ def test_reference_program_seal_ckks_test_runs_unmodified():
     assert "Exact scale in PI*x^3: 1099512659965.7514648438" in text     # SEAL's own printed values
     assert "Exact scale in  0.4*x: 1099511775231.0197753906" in text
     assert "Modulus chain index for x3_encrypted: 0" in text and "coeff_modulus size: 200 (60 + 40 + 40 + 60) bits" in text
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="needs the reference's sources")
+def test_reference_main_program_builds_unmodified_and_fails_loudly_without_gpu(tmp_path):
+    """The reference's main program (test.cpp -> batch_input_test, ct_pt_matrix_mul_test, ct_ct_matrix_mul_test,
+    all_layer_test) compiled and LINKED as it is against the facade (fused module headers first) and libmoai_b200.so.
+    In this container there is no GPU: the executable must stop at its first SEALContext with the library's
+    "no CPU fallback" error instead of computing anything on the host."""
+    import torch
+    inc = os.path.join(ROOT, "include")
+    pkg = os.path.join(ROOT, "moai-fhe-transformerinference-public_b200")
+    exe = str(tmp_path / "moai_reference_main")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O0", "-fopenmp", "-w", "-I" + os.path.join(inc, "facade_fused"),
+                           "-I" + os.path.join(inc, "facade"), "-I" + inc, "-I" + os.path.join(REF, "include"),
+                           os.path.join(REF, "test.cpp"), "-L" + pkg, "-lmoai_b200", "-Wl,-rpath," + pkg, "-o", exe])
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the program would run the full 12-layer workload")
+    res = subprocess.run([exe], cwd=str(tmp_path), capture_output=True, text=True, timeout=60)
+    assert res.returncode != 0
+    assert "BATCH ENCODE ENCRYPT" in res.stdout
+    assert "no CPU fallback" in res.stderr
