@@ -1668,7 +1668,7 @@ namespace sealapi
             }
         }
 
-        const SEALContext &ctx_;
+        const SEALContext ctx_; // a copy, like SEAL's own classes keep (shared state inside)
     };
 
     // ------------------------------------------------------------------------------------------
@@ -2314,7 +2314,7 @@ namespace sealapi
             }
         }
 
-        const SEALContext &ctx_;
+        const SEALContext ctx_; // a copy, like SEAL's own classes keep (shared state inside)
         std::unique_ptr<CKKSEncoder> own_encoder_;
         const CKKSEncoder &encoder_;
     };
@@ -2523,7 +2523,7 @@ namespace sealapi
             return host;
         }
 
-        const SEALContext &ctx_;
+        const SEALContext ctx_; // a copy, like SEAL's own classes keep (shared state inside)
         SecretKey sk_;
         std::vector<std::uint64_t> sk_host_;
     };
@@ -2630,8 +2630,8 @@ namespace sealapi
         }
 
     private:
-        const SEALContext &ctx_;
-        const PublicKey &pk_;
+        const SEALContext ctx_; // a copy, like SEAL's own classes keep (shared state inside)
+        const PublicKey pk_;
     };
 
     // ------------------------------------------------------------------------------------------
@@ -2679,8 +2679,8 @@ namespace sealapi
         }
 
     private:
-        const SEALContext &ctx_;
-        const SecretKey &sk_;
+        const SEALContext ctx_; // a copy, like SEAL's own classes keep (shared state inside)
+        const SecretKey sk_;
     };
 } // namespace sealapi
 } // namespace moai_b200
