@@ -211,8 +211,6 @@ def test_keygen_sparse_secret():
                                                               hamming_weight=64))
 
 
-@pytest.mark.xfail(strict=False, reason="uses a 60-bit prime chain; the widest primes verified on the B200 so far are "
-                                         "58 bits (the repo's special prime) — first GPU run of this program pending")
 def test_reference_program_seal_ckks_test_runs_unmodified():
     """The reference's own test program SEAL_ckks_test() (M/test/test_SEAL_ckks.hpp:106-250) — KeyGenerator,
     CKKSEncoder, Encryptor, Evaluator (square, relinearize, rescale, multiply_plain, mod_switch, add), Decryptor,
