@@ -147,6 +147,11 @@ extern "C"
     {
         return static_cast<Drv *>(h)->ctx ? 1 : 0;
     }
+    // moai_version() of whatever library this driver is bound to: >= 100 for libmoai_b200.so, -1 for the test double
+    int fd_backend_version()
+    {
+        return int(moai_version());
+    }
     int fd_n_key_limbs(void *h)
     {
         return int(static_cast<Drv *>(h)->ctx->key_context_data()->parms().coeff_modulus().size());

@@ -34,9 +34,8 @@ def deep(sealref_deep):
 def test_driver_is_bound_to_the_cuda_library(small):
     """The driver must resolve the C ABI in libmoai_b200.so, not in the CPU test double."""
     r, d = small
-    maps = open("/proc/self/maps").read()
-    assert "libmoai_b200.so" in maps and "libfacade_driver.so" in maps
-    assert "libmoai_b200_mock.so" not in maps and "libfacade_driver_mock.so" not in maps
+    assert d.lib.fd_backend_version() >= 100          # the test double answers -1
+    assert "libmoai_b200.so" in open("/proc/self/maps").read()
 
 
 def test_context_and_chain(small):
