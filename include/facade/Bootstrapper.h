@@ -18,6 +18,10 @@
 // never uses on this path; they are accepted as any type and ignored.
 #pragma once
 #include "seal/seal.h"
+#include <chrono>
+#include <condition_variable>
+#include <exception>
+#include <mutex>
 #include <vector>
 
 class Bootstrapper
@@ -120,6 +124,28 @@ public:
         create();
     }
 
+    // Opt-in request combining.  The reference's driver bootstraps 768 ciphertexts with one bootstrap_3 call each inside
+    // `#pragma omp parallel for` (M/test/test_full_scheme.hpp:654-660): with combining on, calls that arrive
+    // concurrently from different threads are collected by the first caller (the "leader") and go to the device as ONE
+    // batched call — and, for real-slot messages (all of MOAI's activations), two ciphertexts per bootstrapping
+    // (moai_bootstrap_real) — while the other callers wait for their result.  Each caller still gets exactly its own
+    // ciphertext back; nothing changes for a single-threaded caller except `linger_us` of latency.
+    //   real_slots: the messages are real (required for the two-per-bootstrapping packing); false = batching only
+    //   max_batch : most requests per device call;  linger_us: how long the leader waits for more requests
+    void set_combining(bool on, bool real_slots = true, int max_batch = 64, int linger_us = 300)
+    {
+        std::lock_guard<std::mutex> lk(qmu_);
+        combining_ = on;
+        combine_real_ = real_slots;
+        combine_max_ = max_batch < 1 ? 1 : max_batch;
+        combine_linger_us_ = linger_us < 0 ? 0 : linger_us;
+    }
+    // device calls made on behalf of combined requests so far (for tests / tuning)
+    std::size_t combined_device_calls() const
+    {
+        return combined_calls_;
+    }
+
     // Bootstrapper.cpp:3496-3502 (+ modraise_inplace :2938-2945 for the argument checks)
     void bootstrap_3(seal::Ciphertext &rtncipher, seal::Ciphertext &cipher)
     {
@@ -130,6 +156,11 @@ public:
         if (cipher.coeff_modulus_size() != 1)
         {
             throw std::invalid_argument("Ciphertexts in the lowest level are supported only!");
+        }
+        if (combining_)
+        {
+            bootstrap_combined(rtncipher, cipher);
+            return;
         }
         create();
         bind_keys();
@@ -171,6 +202,133 @@ public:
     }
 
 private:
+    struct Request
+    {
+        const seal::Ciphertext *in;
+        seal::Ciphertext *out;
+        bool done = false;
+        std::exception_ptr error;
+    };
+
+    void bootstrap_combined(seal::Ciphertext &rtncipher, const seal::Ciphertext &cipher)
+    {
+        Request rq{ &cipher, &rtncipher };
+        std::unique_lock<std::mutex> lk(qmu_);
+        pending_.push_back(&rq);
+        if (leader_active_)
+        {
+            qcv_.wait(lk, [&] { return rq.done; }); // a leader is collecting: it will serve this request
+        }
+        else
+        {
+            // first caller: become the leader.  pending_ held nothing else (a leader only leaves with it empty), so
+            // this request is served by the first batch below.
+            leader_active_ = true;
+            while (!pending_.empty())
+            {
+                const std::size_t want = static_cast<std::size_t>(combine_max_);
+                qcv_.wait_for(lk, std::chrono::microseconds(combine_linger_us_), [&] { return pending_.size() >= want; });
+                const std::size_t take = std::min(pending_.size(), want);
+                std::vector<Request *> batch(pending_.begin(), pending_.begin() + take);
+                pending_.erase(pending_.begin(), pending_.begin() + take);
+                lk.unlock();
+                serve(batch);
+                lk.lock();
+                for (Request *r : batch)
+                {
+                    r->done = true;
+                }
+                qcv_.notify_all();
+            }
+            leader_active_ = false;
+        }
+        lk.unlock();
+        if (rq.error)
+        {
+            std::rethrow_exception(rq.error);
+        }
+    }
+
+    // one device call for a batch of requests that share their scale (others are served one scale at a time)
+    void serve(std::vector<Request *> &batch)
+    {
+        try
+        {
+            create();
+            bind_keys();
+            auto &c = context.impl();
+            const std::size_t n = c->n, out_limbs = static_cast<std::size_t>(L + 1 - 14);
+            std::vector<bool> taken(batch.size(), false);
+            for (std::size_t first = 0; first < batch.size(); first++)
+            {
+                if (taken[first])
+                {
+                    continue;
+                }
+                std::vector<std::size_t> group;
+                for (std::size_t i = first; i < batch.size(); i++)
+                {
+                    if (!taken[i] && batch[i]->in->scale() == batch[first]->in->scale())
+                    {
+                        group.push_back(i);
+                        taken[i] = true;
+                    }
+                }
+                const std::size_t B = group.size();
+                seal::detail::DeviceBlock in, out;
+                in.ensure(c, B * 2 * n);
+                out.ensure(c, B * 2 * out_limbs * n);
+                std::int32_t got_limbs = 0;
+                double got_scale = 0.0;
+                {
+                    seal::detail::Lock lk(c->mu);
+                    for (std::size_t k = 0; k < B; k++)
+                    {
+                        seal::detail::chk(moai_memcpy_d2d(c->h, in.ptr() + k * 2 * n, batch[group[k]]->in->data(),
+                                                          2 * n * sizeof(std::uint64_t)));
+                    }
+                    const double scale = batch[first]->in->scale();
+                    if (combine_real_)
+                    {
+                        seal::detail::chk(moai_bootstrap_real(c->h, h_, keys_, in.ptr(), static_cast<std::int64_t>(B), scale, 32,
+                                                              out.ptr(), &got_limbs, &got_scale));
+                    }
+                    else
+                    {
+                        seal::detail::chk(moai_bootstrap(c->h, h_, keys_, in.ptr(), static_cast<std::int64_t>(B), scale, out.ptr(),
+                                                         &got_limbs, &got_scale));
+                    }
+                    combined_calls_++;
+                }
+                if (static_cast<std::size_t>(got_limbs) != out_limbs)
+                {
+                    throw std::logic_error("unexpected level after bootstrapping");
+                }
+                const seal::parms_id_type &id = context.parms_id_for_limbs(out_limbs);
+                for (std::size_t k = 0; k < B; k++)
+                {
+                    seal::Ciphertext r(context, id, 2);
+                    r.scale() = got_scale;
+                    r.is_ntt_form() = true;
+                    {
+                        seal::detail::Lock lk(c->mu);
+                        seal::detail::chk(moai_memcpy_d2d(c->h, r.data(), out.ptr() + k * 2 * out_limbs * n,
+                                                          2 * out_limbs * n * sizeof(std::uint64_t)));
+                    }
+                    *batch[group[k]]->out = std::move(r);
+                }
+            }
+            initial_scale = batch.back()->in->scale();
+        }
+        catch (...)
+        {
+            for (Request *r : batch)
+            {
+                r->error = std::current_exception();
+            }
+        }
+    }
+
     void create()
     {
         if (h_)
@@ -228,4 +386,11 @@ private:
     moai_keys *keys_ = nullptr;
     std::size_t bound_ = 0;
     bool hoisting_ = false;
+    // request combining
+    std::mutex qmu_;
+    std::condition_variable qcv_;
+    std::vector<Request *> pending_;
+    bool leader_active_ = false, combining_ = false, combine_real_ = true;
+    int combine_max_ = 64, combine_linger_us_ = 300;
+    std::size_t combined_calls_ = 0;
 };

@@ -293,6 +293,13 @@ class FacadeDriver:
         self._chk(self.lib.fd_bootstrap_3(self.h, _p(x), C.c_double(scale), _p(out), C.byref(ol), C.byref(osc)))
         return out[: 2 * ol.value * self.n].copy(), ol.value, osc.value
 
+    def boot_combined(self, x, n_cts, scale, max_limbs, real_slots=True, max_batch=64, linger_us=300):
+        out = np.zeros(n_cts * 2 * max_limbs * self.n, dtype=np.uint64)
+        ol, calls = C.c_int(0), C.c_int(0)
+        self._chk(self.lib.fd_boot_combined(self.h, _p(x), C.c_int(n_cts), C.c_double(scale), C.c_int(int(real_slots)),
+                                            C.c_int(max_batch), C.c_int(linger_us), _p(out), C.byref(ol), C.byref(calls)))
+        return out[: n_cts * 2 * ol.value * self.n].reshape(n_cts, 2, ol.value, self.n).copy(), calls.value
+
     def softmax_boot(self, x, num, limbs, scale, bias_vec, input_num, iters, layer_id, max_limbs):
         out = np.zeros(num * 2 * max_limbs * self.n, dtype=np.uint64)
         ol, osc = C.c_int(0), C.c_double(0)

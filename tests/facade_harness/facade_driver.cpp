@@ -943,6 +943,52 @@ extern "C"
         d->boot->bootstrap_3(rtn, ct);
         FD_CATCH(d)
     }
+    // Request combining of the facade Bootstrapper: n ciphertexts, one bootstrap_3 call each from an OpenMP loop like
+    // the reference's driver (test_full_scheme.hpp:654-660).  x: [n][2][1][N] -> out: [n][2][L-13][N]; *device_calls =
+    // device calls the combiner made.
+    int fd_boot_combined(void *h, const uint64_t *x, int n_cts, double scale, int real_slots, int max_batch, int linger_us,
+                         uint64_t *out, int *out_limbs, int *device_calls)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        if (!d->boot)
+        {
+            throw logic_error("fd_boot_create first");
+        }
+        d->boot->set_combining(true, real_slots != 0, max_batch, linger_us);
+        const size_t before = d->boot->combined_device_calls();
+        vector<Ciphertext> in(n_cts), rtn(n_cts);
+        for (int i = 0; i < n_cts; i++)
+        {
+            load_ct(*d, x + size_t(i) * 2 * d->n, 2, 1, scale, in[i]);
+        }
+        vector<string> errors(n_cts);
+#pragma omp parallel for
+        for (int i = 0; i < n_cts; i++)
+        {
+            try
+            {
+                d->boot->bootstrap_3(rtn[i], in[i]);
+            }
+            catch (const exception &e)
+            {
+                errors[i] = e.what();
+            }
+        }
+        d->boot->set_combining(false);
+        for (int i = 0; i < n_cts; i++)
+        {
+            if (!errors[i].empty())
+            {
+                throw logic_error("request " + to_string(i) + ": " + errors[i]);
+            }
+            *out_limbs = int(rtn[i].coeff_modulus_size());
+            rtn[i].download(out + size_t(i) * 2 * rtn[i].coeff_modulus_size() * d->n);
+        }
+        *device_calls = int(d->boot->combined_device_calls() - before);
+        FD_CATCH(d)
+    }
+
     // softmax_boot of the reference (softmax.hpp:308-581) on `num` ciphertexts
     int fd_softmax_boot(void *h, const uint64_t *x, int num, int limbs, double scale, const int *bias_vec, int input_num,
                         int iter, int layer_id, uint64_t *out, int *out_limbs, double *out_scale)

@@ -11,7 +11,7 @@
  * Built only by tests/facade_harness/build.py into oracle/_ref/ (git-ignored); nothing in the product package
  * or in libmoai_b200.so references it, and the product never falls back to it
  * (tests/test_abi.py::test_product_never_imports_oracle).  Entry points the facade does not need on the
- * CPU (bootstrapping, fast-mode keys) return MOAI_LOGIC_ERROR.
+ * CPU (GPU-only modules, fast-mode keys) return MOAI_LOGIC_ERROR; the bootstrapper is a plumbing fake (below).
  */
 #include "moai_b200.h"
 #include "moai_b200_modules.h"
@@ -426,22 +426,63 @@ int32_t moai_keys_add_galois_fast(moai_keys *k, uint32_t e, const uint64_t *p, i
     (void)k; (void)e; (void)p; (void)l;
     UNSUPPORTED("moai_keys_add_galois_fast");
 }
-int32_t moai_bootstrapper_create(moai_context *c, int32_t a, double b, int32_t d, int32_t e, int32_t f, int32_t g,
-                                 moai_bootstrapper **o)
+/* ---- bootstrapper: a PLUMBING FAKE, not a bootstrapping.  It lets the CPU tests exercise the host logic around
+ * moai_bootstrap / moai_bootstrap_real (the facade Bootstrapper's request combining: which ciphertext goes into which
+ * batch and comes back to which caller).  The "result" of ciphertext b is a fixed function of ITS OWN input only:
+ *   out[b][p][l][i] = in[b][p][0][i] mod q_l,  at total_limbs - 14 limbs with scale final_scale.                    */
+struct moai_bootstrapper
 {
-    (void)c; (void)a; (void)b; (void)d; (void)e; (void)f; (void)g; (void)o;
-    UNSUPPORTED("moai_bootstrapper_create");
+    int total_limbs;
+    double final_scale;
+};
+static int g_boot_calls = 0;
+int moai_mock_bootstrap_calls(void) { return g_boot_calls; }
+int32_t moai_bootstrapper_create(moai_context *c, int32_t total_limbs, double final_scale, int32_t K, int32_t deg, int32_t da,
+                                 int32_t lw, moai_bootstrapper **out)
+{
+    (void)K; (void)deg; (void)da; (void)lw;
+    REQ(c && out && total_limbs >= 15 && total_limbs <= c->kl - 1, "bad level budget");
+    moai_bootstrapper *b = (moai_bootstrapper *)calloc(1, sizeof *b);
+    b->total_limbs = total_limbs;
+    b->final_scale = final_scale;
+    *out = b;
+    return MOAI_OK;
 }
-int32_t moai_bootstrapper_destroy(moai_bootstrapper *b) { (void)b; return MOAI_OK; }
-int32_t moai_bootstrapper_set_hoisting(moai_bootstrapper *b, int32_t on) { (void)b; (void)on; UNSUPPORTED("moai_bootstrapper_set_hoisting"); }
+int32_t moai_bootstrapper_destroy(moai_bootstrapper *b) { free(b); return MOAI_OK; }
+int32_t moai_bootstrapper_set_hoisting(moai_bootstrapper *b, int32_t on) { (void)b; (void)on; return MOAI_OK; }
 int32_t moai_bootstrapper_required_steps(moai_bootstrapper *b, int32_t *s, int32_t cap, int32_t *n)
 {
-    (void)b; (void)s; (void)cap; (void)n;
-    UNSUPPORTED("moai_bootstrapper_required_steps");
+    (void)b;
+    REQ(cap >= 2, "capacity");
+    s[0] = 1;
+    s[1] = 2;
+    *n = 2;
+    return MOAI_OK;
+}
+static int32_t fake_bootstrap(moai_context *c, moai_bootstrapper *b, const uint64_t *in, int64_t batch, uint64_t *out,
+                              int32_t *ol, double *os)
+{
+    REQ(c && b && in && out && batch >= 0, "null argument");
+    const int L = b->total_limbs - 14;
+    for (int64_t i = 0; i < batch; i++)
+        for (int p = 0; p < 2; p++)
+            for (int l = 0; l < L; l++)
+                for (size_t k = 0; k < c->n; k++)
+                    out[(((size_t)i * 2 + p) * L + l) * c->n + k] = in[((size_t)i * 2 + p) * c->n + k] % c->q[l];
+    *ol = L;
+    *os = b->final_scale;
+    __atomic_add_fetch(&g_boot_calls, 1, __ATOMIC_SEQ_CST);
+    return MOAI_OK;
 }
 int32_t moai_bootstrap(moai_context *c, moai_bootstrapper *b, moai_keys *k, const uint64_t *in, int64_t batch, double scale,
                        uint64_t *out, int32_t *ol, double *os)
 {
-    (void)c; (void)b; (void)k; (void)in; (void)batch; (void)scale; (void)out; (void)ol; (void)os;
-    UNSUPPORTED("moai_bootstrap");
+    (void)k; (void)scale;
+    return fake_bootstrap(c, b, in, batch, out, ol, os);
+}
+int32_t moai_bootstrap_real(moai_context *c, moai_bootstrapper *b, moai_keys *k, const uint64_t *in, int64_t batch,
+                            double scale, int64_t chunk_pairs, uint64_t *out, int32_t *ol, double *os)
+{
+    (void)k; (void)scale; (void)chunk_pairs;
+    return fake_bootstrap(c, b, in, batch, out, ol, os);
 }

@@ -203,3 +203,34 @@ def test_reference_main_program_builds_unmodified_and_fails_loudly_without_gpu(t
     assert res.returncode != 0
     assert "BATCH ENCODE ENCRYPT" in res.stdout
     assert "no CPU fallback" in res.stderr
+
+
+@pytest.mark.parametrize("real_slots", [True, False])
+def test_bootstrapper_request_combining_routes_every_ciphertext(real_slots):
+    """Opt-in combining of concurrent bootstrap_3 calls (include/facade/Bootstrapper.h): 40 ciphertexts bootstrapped from
+    an OpenMP loop like the reference's driver.  On the CPU test double the "bootstrapping" is a plumbing fake whose
+    result depends on the ciphertext's own input only — so this checks the host logic: every caller gets ITS result,
+    requests are actually combined (fewer device calls than ciphertexts), nothing deadlocks with many threads, small
+    batches and a zero linger."""
+    import facade_harness as facade
+    from oracle import Oracle
+    if not facade.available(mock=True):
+        pytest.skip("facade driver not built")
+    bits = [40] + [30] * 16 + [40]                      # 17 data limbs: the bootstrapper's level budget needs >= 15
+    o = Oracle(10, bits)
+    rng = np.random.default_rng(7)
+    n_cts, L = 40, 17 - 14
+    x = rng.integers(0, int(o.q[0]), (n_cts, 2, 1, o.n), dtype=np.uint64)
+    want = np.stack([x[:, :, 0, :] % np.uint64(o.q[l]) for l in range(L)], axis=2)
+    for max_batch, linger in ((64, 2000), (4, 0), (1, 0)):
+        d = facade.FacadeDriver(10, primes=o.q, mock=True)
+        d.boot_create(loge=10, logn=9, total_level=16, final_scale=2.0 ** 30)
+        d.set_relin(np.zeros((o.kl - 1) * 2 * o.kl * o.n, dtype=np.uint64))
+        got, calls = d.boot_combined(x.reshape(-1), n_cts, 2.0 ** 30, max_limbs=L, real_slots=real_slots,
+                                     max_batch=max_batch, linger_us=linger)
+        assert got.shape == want.shape and (got == want).all()
+        assert 1 <= calls <= n_cts
+        if max_batch == 1:
+            assert calls == n_cts
+        if max_batch == 64 and (os.cpu_count() or 1) > 1:
+            assert calls < n_cts                          # concurrent callers were actually combined
