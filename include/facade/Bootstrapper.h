@@ -26,6 +26,14 @@
 
 class Bootstrapper
 {
+    struct Request
+    {
+        const seal::Ciphertext *in = nullptr;
+        seal::Ciphertext *out = nullptr;
+        bool done = false;
+        std::exception_ptr error;
+    };
+
 public:
     long loge, logn, n, logNh, Nh, L;
     double initial_scale = 0.0, final_scale;
@@ -182,6 +190,41 @@ public:
         out.is_ntt_form() = true;
         rtncipher = std::move(out);
     }
+    // explicit batch form (not in the reference): all ciphertexts in one device call, two real-slot ciphertexts per
+    // bootstrapping when real_slots is true — what the driver's 768-iteration loop amounts to
+    void bootstrap_3(std::vector<seal::Ciphertext> &rtnciphers, const std::vector<seal::Ciphertext> &ciphers,
+                     bool real_slots = true)
+    {
+        std::vector<Request> rq(ciphers.size());
+        std::vector<Request *> batch;
+        rtnciphers.resize(ciphers.size());
+        for (std::size_t i = 0; i < ciphers.size(); i++)
+        {
+            if (ciphers[i].size() != 2)
+            {
+                throw std::invalid_argument("Ciphertexts of size 2 are supported only!");
+            }
+            if (ciphers[i].coeff_modulus_size() != 1)
+            {
+                throw std::invalid_argument("Ciphertexts in the lowest level are supported only!");
+            }
+            rq[i].in = &ciphers[i];
+            rq[i].out = &rtnciphers[i];
+            batch.push_back(&rq[i]);
+        }
+        if (batch.empty())
+        {
+            return;
+        }
+        const bool saved = combine_real_;
+        combine_real_ = real_slots;
+        serve(batch);
+        combine_real_ = saved;
+        if (rq[0].error)
+        {
+            std::rethrow_exception(rq[0].error);
+        }
+    }
     void bootstrap_inplace_3(seal::Ciphertext &cipher)
     {
         seal::Ciphertext r;
@@ -202,17 +245,11 @@ public:
     }
 
 private:
-    struct Request
-    {
-        const seal::Ciphertext *in;
-        seal::Ciphertext *out;
-        bool done = false;
-        std::exception_ptr error;
-    };
-
     void bootstrap_combined(seal::Ciphertext &rtncipher, const seal::Ciphertext &cipher)
     {
-        Request rq{ &cipher, &rtncipher };
+        Request rq;
+        rq.in = &cipher;
+        rq.out = &rtncipher;
         std::unique_lock<std::mutex> lk(qmu_);
         pending_.push_back(&rq);
         if (leader_active_)

@@ -964,7 +964,7 @@ extern "C"
         }
         vector<string> errors(n_cts);
 #pragma omp parallel for
-        for (int i = 0; i < n_cts; i++)
+        for (int i = 0; i < (max_batch < 0 ? 0 : n_cts); i++)
         {
             try
             {
@@ -976,6 +976,12 @@ extern "C"
             }
         }
         d->boot->set_combining(false);
+        if (max_batch < 0)
+        {
+            // the explicit batch overload instead of the combiner
+            rtn.clear();
+            d->boot->bootstrap_3(rtn, in, real_slots != 0);
+        }
         for (int i = 0; i < n_cts; i++)
         {
             if (!errors[i].empty())

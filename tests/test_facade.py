@@ -222,7 +222,7 @@ def test_bootstrapper_request_combining_routes_every_ciphertext(real_slots):
     n_cts, L = 40, 17 - 14
     x = rng.integers(0, int(o.q[0]), (n_cts, 2, 1, o.n), dtype=np.uint64)
     want = np.stack([x[:, :, 0, :] % np.uint64(o.q[l]) for l in range(L)], axis=2)
-    for max_batch, linger in ((64, 2000), (4, 0), (1, 0)):
+    for max_batch, linger in ((64, 2000), (4, 0), (1, 0), (-1, 0)):      # -1: the explicit vector overload of bootstrap_3
         d = facade.FacadeDriver(10, primes=o.q, mock=True)
         d.boot_create(loge=10, logn=9, total_level=16, final_scale=2.0 ** 30)
         d.set_relin(np.zeros((o.kl - 1) * 2 * o.kl * o.n, dtype=np.uint64))
@@ -230,6 +230,8 @@ def test_bootstrapper_request_combining_routes_every_ciphertext(real_slots):
                                      max_batch=max_batch, linger_us=linger)
         assert got.shape == want.shape and (got == want).all()
         assert 1 <= calls <= n_cts
+        if max_batch == -1:
+            assert calls == 1
         if max_batch == 1:
             assert calls == n_cts
         if max_batch == 64 and (os.cpu_count() or 1) > 1:

@@ -117,6 +117,15 @@ def test_bootstrapper_facade_preserves_message():
     dec = o.decode(o.decrypt(sk, out, 2, 3), 3, out_scale)
     assert np.abs(dec - z).max() < 2e-3, np.abs(dec - z).max()
     # the reference's argument checks (Bootstrapper.cpp:2939-2945)
+    # the explicit batch overload bootstrap_3(vector, vector): three real-slot ciphertexts, one device call, two of
+    # them sharing a bootstrapping (moai_bootstrap_real); every ciphertext comes back with its own message
+    vs = rng.normal(size=(3, o.n // 2)) * 0.1
+    cts = np.stack([o.encrypt_sym(sk, 80 + i, o.encode(vs[i].astype(np.complex128), scale, 1), 1) for i in range(3)])
+    outs, calls = d.boot_combined(cts.reshape(-1), 3, scale, max_limbs=3, real_slots=True, max_batch=-1)
+    assert calls == 1 and outs.shape == (3, 2, 3, o.n)
+    for i in range(3):
+        dec = o.decode(o.decrypt(sk, outs[i].reshape(-1), 2, 3), 3, scale)
+        assert np.abs(dec - vs[i]).max() < 2e-3, (i, np.abs(dec - vs[i]).max())
     import ctypes as C
     two = np.zeros(2 * 2 * o.n, dtype=np.uint64)
     with pytest.raises(facade.FacadeError, match="lowest level"):
