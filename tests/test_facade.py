@@ -236,3 +236,44 @@ def test_bootstrapper_request_combining_routes_every_ciphertext(real_slots):
             assert calls == n_cts
         if max_batch == 64 and (os.cpu_count() or 1) > 1:
             assert calls < n_cts                          # concurrent callers were actually combined
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="needs the reference's headers")
+def test_example_server_program_end_to_end(sealref_small, tmp_path):
+    """examples/server_ct_pt_matmul.cpp — the deployment split: a stock-SEAL client writes parameters, encrypted inputs
+    (Ciphertext::save streams) and weights to files; the server program (facade + the reference's module header name,
+    here linked against the CPU test double) writes encrypted outputs; the client reads them back with SEAL's own
+    loader.  The outputs equal the reference's ct_pt_matrix_mul_wo_pre on real SEAL bit for bit."""
+    import facade_harness as facade
+    from facade_harness import cases
+    from conftest import SMALL_BITS, SMALL_LOGN
+    if not facade.available(mock=True):
+        pytest.skip("facade test double not built")
+    r = sealref_small
+    inc = os.path.join(ROOT, "include")
+    ref_out = os.path.join(ROOT, "oracle", "_ref")
+    exe = str(tmp_path / "server")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-fopenmp", "-w", "-I" + os.path.join(inc, "facade_fused"),
+                           "-I" + os.path.join(inc, "facade"), "-I" + inc, "-I" + os.path.join(REF, "include"),
+                           os.path.join(ROOT, "examples", "server_ct_pt_matmul.cpp"), "-L" + ref_out, "-lmoai_b200_mock",
+                           "-Wl,-rpath," + ref_out, "-o", exe])
+    rng = np.random.default_rng(77)
+    K, Cc, limbs = 4, 3, 2
+    X, _ = cases.encrypt_batch(r, rng, K, limbs)
+    W = rng.normal(size=(K, Cc)) * 0.3
+    (tmp_path / "params.txt").write_text("%d %s\n" % (SMALL_LOGN, " ".join(str(b) for b in SMALL_BITS)))
+    (tmp_path / "weights.txt").write_text("%d %d\n%s\n" % (K, Cc, " ".join(repr(float(w)) for w in W.reshape(-1))))
+    with open(tmp_path / "inputs.seal", "wb") as f:
+        for j in range(K):
+            f.write(r.save_ciphertext(X[j].reshape(-1), 2, limbs, cases.SCALE))
+    res = subprocess.run([exe, "params.txt", "inputs.seal", "weights.txt", "outputs.seal"], cwd=str(tmp_path),
+                         capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr
+    assert "3 ciphertexts at chain_index 0" in res.stdout
+    exp, _ = r.ct_pt_matmul(0, X.reshape(-1), W, None, K, Cc, limbs, cases.SCALE)
+    blob = (tmp_path / "outputs.seal").read_bytes()
+    per = len(blob) // Cc
+    for i in range(Cc):
+        ct, size, l, scale = r.load_ciphertext(blob[i * per:(i + 1) * per])     # SEAL's own loader, validity checks on
+        assert (size, l, scale) == (2, limbs - 1, cases.SCALE)
+        assert (ct == exp.reshape(Cc, -1)[i]).all()
