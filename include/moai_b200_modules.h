@@ -135,6 +135,13 @@ int32_t moai_bootstrap_plan_debug(int32_t log_n, const uint64_t *primes, int32_t
                                   int32_t dir, int32_t stage, int32_t *n_diags, int32_t *offsets, double *diag_values,
                                   double *cheb, int32_t *n_cheb);
 
+/* host-only: the EvalMod cosine fit for (boundary_K, deg, double_angles, log_width); *poly_levels = the levels the
+ * polynomial spends, ceil(log2(deg + 1)).  moai_bootstrapper_create accepts any pair with
+ * poly_levels + double_angles == 8 (the level budget of bootstrap_3): the reference's (59, 2); (31, 3) would save two
+ * relinearizations per EvalMod but its fit error is 3e-4 after the double angles (2.7e-9 for (59, 2)): not advisable. */
+int32_t moai_bootstrap_cosine_fit_debug(int32_t boundary_K, int32_t deg, int32_t double_angles, int32_t log_width,
+                                        double *cheb, int32_t *n_cheb, int32_t *poly_levels);
+
 /* ---- B7/B6: softmax_boot (M/source/non_linear_func/softmax.hpp:308-581) and single_att_block
  * (M/source/att_block/single_att_block.hpp:10-207); weights row-major num_col x col_W doubles.     */
 int32_t moai_softmax_boot(moai_context *ctx, moai_keys *keys, moai_bootstrapper *b, const uint64_t *enc_X,

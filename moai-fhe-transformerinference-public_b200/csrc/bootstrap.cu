@@ -194,6 +194,8 @@ namespace moai
     {
         MOAI_REQUIRE(p.total_limbs >= 15 && p.total_limbs <= ctx->kl - 1, "bootstrapping needs at least 15 data limbs");
         MOAI_REQUIRE(p.deg >= 15 && p.deg <= 63, "cosine degree must be in [15, 63]");
+        MOAI_REQUIRE(p.double_angles >= 0 && p.poly_levels() + p.double_angles == 8,
+                     "EvalMod must spend 8 levels: ceil(log2(deg + 1)) + double_angles == 8, e.g. (59, 2) or (31, 3)");
         build_matrices();
         fit_cosine();
     }
@@ -249,7 +251,7 @@ namespace moai
                     const int off = kv.first > n / 2 ? kv.first - n : kv.first;
                     stc_[s].diags[off] = kv.second;
                 }
-                stc_[s].limbs = prm.total_limbs - 3 - (6 + prm.double_angles) - s;
+                stc_[s].limbs = prm.total_limbs - 3 - (prm.poly_levels() + prm.double_angles) - s;
                 plan_bsgs(stc_[s]);
             }
         }
@@ -638,9 +640,15 @@ namespace moai
         T[6] = t_even(3);
         T[7] = t_sum(4, 3);
         T[8] = t_even(4);
-        T[16] = t_even(8);
-        T[32] = t_even(16);
-        Ct cosv = eval_cheb(ev, cheb_, y.limbs - 6, y.scale, T, keys);
+        if (prm.deg >= 16)
+        {
+            T[16] = t_even(8);
+        }
+        if (prm.deg >= 32)
+        {
+            T[32] = t_even(16);
+        }
+        Ct cosv = eval_cheb(ev, cheb_, y.limbs - prm.poly_levels(), y.scale, T, keys);
         for (int i = 0; i < prm.double_angles; i++)
         {
             cosv = dbl_minus_one(ev.square(cosv)); // cos(2a) = 2 cos(a)^2 - 1

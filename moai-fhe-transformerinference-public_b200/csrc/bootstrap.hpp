@@ -35,6 +35,18 @@ namespace moai
         int total_limbs = 35; // data limbs after ModRaise (:368)
         double final_scale = 70368744177664.0; // 2^46
         int hoisting = 0;     // 1: plan the BSGS stages for hoisted baby steps (more, cheaper baby steps)
+        // levels the recursive Chebyshev division of the cosine spends: ceil(log2(deg + 1)) (59 -> 6, 31 -> 5).
+        // The whole EvalMod spends poly_levels() + double_angles, which must be 8 (output at total_limbs - 14):
+        // the reference's (59, 2); (31, 3) also fits the budget but not the precision (fit error 3e-4).
+        int poly_levels() const
+        {
+            int l = 0;
+            while ((1 << l) < deg + 1)
+            {
+                l++;
+            }
+            return l;
+        }
     };
 
     // one sparse-diagonal matrix, prepared for BSGS evaluation at a fixed level

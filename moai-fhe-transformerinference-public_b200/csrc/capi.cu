@@ -867,6 +867,35 @@ extern "C"
         API_END
     }
 
+    // Host-only: the Chebyshev coefficients of the EvalMod cosine cos(2 pi (x - 1/4) / 2^double_angles) fitted on
+    // the intervals [i - 2^-log_width, i + 2^-log_width], |i| < boundary_K, in y = x / boundary_K (no GPU needed).
+    int32_t moai_bootstrap_cosine_fit_debug(int32_t boundary_K, int32_t deg, int32_t double_angles, int32_t log_width,
+                                            double *cheb, int32_t *n_cheb, int32_t *poly_levels)
+    {
+        API_BEGIN
+        MOAI_REQUIRE(cheb && n_cheb && poly_levels, "null argument");
+        static const uint64_t dummy_primes[17] = { 0 };
+        Context host;
+        host.log_n = 4;
+        host.n = 16;
+        host.kl = 17;
+        host.q.assign(dummy_primes, dummy_primes + 17);
+        BootParams p;
+        p.boundary_K = boundary_K;
+        p.deg = deg;
+        p.double_angles = double_angles;
+        p.log_width = log_width;
+        p.total_limbs = 16;
+        Bootstrapper b(&host, p);
+        *poly_levels = p.poly_levels();
+        *n_cheb = (int32_t)b.cheb_coeffs().size();
+        for (size_t i = 0; i < b.cheb_coeffs().size(); i++)
+        {
+            cheb[i] = b.cheb_coeffs()[i];
+        }
+        API_END
+    }
+
     // ---- attention / encoder layer ----------------------------------------------------------------
     int32_t moai_softmax_boot(moai_context *ctx, moai_keys *keys, moai_bootstrapper *b, const uint64_t *enc_X,
                               int32_t num, int32_t limbs, double scale, const int32_t *bias_vec, int32_t input_num,

@@ -86,3 +86,40 @@ def test_cosine_polynomial_accuracy():
     exact = np.cos(2 * np.pi * (xs - 0.25) / 2 ** r)
     assert np.abs(approx - exact).max() < 1e-8        # fit error 2.6e-10 measured
     assert np.abs(cheb).max() < 2.0                   # O(1) coefficients: benign for CKKS scales
+
+
+def cosine_fit(K, deg, r, log_width=10):
+    lib = load_pkg().load_library()
+    cheb = (C.c_double * 128)()
+    n, pl = C.c_int32(), C.c_int32()
+    rc = lib.moai_bootstrap_cosine_fit_debug(C.c_int32(K), C.c_int32(deg), C.c_int32(r), C.c_int32(log_width), cheb,
+                                             C.byref(n), C.byref(pl))
+    if rc:
+        raise ValueError(lib.moai_last_error().decode())
+    return np.array(cheb[: n.value]), pl.value
+
+
+def evalmod_error(K, deg, r, log_width=10):
+    """max error of the fitted cosine on the approximation domain, and of sin(2 pi x) after the r double angles"""
+    c, pl = cosine_fit(K, deg, r, log_width)
+    w = 2.0 ** -log_width
+    xs = np.concatenate([i + np.linspace(-w, w, 41) for i in range(-(K - 1), K)])
+    v = np.polynomial.chebyshev.chebval(xs / K, c)
+    e_poly = np.abs(v - np.cos(2 * np.pi * (xs - 0.25) / 2 ** r)).max()
+    for _ in range(r):
+        v = 2 * v * v - 1
+    return pl, e_poly, np.abs(v - np.sin(2 * np.pi * xs)).max()
+
+
+def test_evalmod_level_budget_and_fit_error():
+    """The polynomial's level count follows from its degree (59 -> 6, 31 -> 5) and EvalMod must spend 8 levels in all.
+    The reference's (deg 59, 2 double angles) is accurate to 1e-8 after the double angles; (31, 3), which would save
+    two relinearizations, fits the budget but leaves ~3e-4 (25 periods do not fit a degree-31 polynomial) — the
+    reason it is not used."""
+    pl, e_poly, e_sin = evalmod_error(25, 59, 2)
+    assert pl == 6 and e_poly < 1e-9 and e_sin < 1e-8
+    pl, e_poly, e_sin = evalmod_error(25, 31, 3)
+    assert pl == 5 and 1e-5 < e_sin < 1e-3
+    for deg, r in ((31, 2), (59, 3), (47, 1)):
+        with pytest.raises(ValueError, match="8 levels"):
+            cosine_fit(25, deg, r)
