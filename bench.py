@@ -1,17 +1,28 @@
 #!/usr/bin/env python
-"""bench.py — amortized seconds per input of MOAI's encrypted BERT-base hot path on B200.
+"""bench.py — amortized seconds per input of MOAI's encrypted 12-layer BERT-base on B200 (BASELINE.json `metric`).
 
-Workload (round 1): BASELINE.json configs[0] — the self-output 768x768 ciphertext-plaintext matmul
-(ct_pt_matrix_mul_wo_pre_w_mask, M/source/matrix_mul/Ct_pt_matrix_mul.hpp:103-170) on one packed
-batch of 256 inputs x 128 tokens (768 column ciphertexts at chain_index 1 -> 0, N = 65536, repo CKKS
-parameters), all 128 token slots valid, for which the masked plaintexts are exactly the scalar
-encodings — P:Table 3 "SelfOutput Pt-ct MatMul", 1.7 s/input on 56 CPU cores.
+Default workload (`--workload layer`, BASELINE.json configs[3]/[4], M/test/test_full_scheme.hpp:484-1087): the encoder
+layer itself on one packed batch of 256 inputs x 128 tokens (768 column ciphertexts at chain_index 20, N = 65536,
+35 + 1 primes, fast mode), timed in its four bootstrap-delimited quarters:
 
-One step = one pass of that matmul over one packed batch.  With N ranks every rank processes its
-own packed batch (replicas, weak scaling, no data-path collective; SURVEY §8(e) partitioning B).
+  step i runs quarter i mod 4 of the layer through moai_encoder_layer_stage —
+    0: attention (12 heads) + self-output matmul + 768 bootstrappings      1: residual + LayerNorm + 768 bootstrappings
+    2: intermediate matmul + GELU + final matmul + 768 bootstrappings      3: residual + LayerNorm2 + 768 bootstrappings
+  — with the activations flowing from step to step exactly as in the layer (4 consecutive steps = 1 layer, 48 = the
+  12-layer model).  A whole layer per step (about 100 s) would not fit the driver's 25-step run; a quarter (about 25 s)
+  does, and every kernel of the metric runs in its true proportion.  value = (sum over the four quarters of their mean
+  device time) x 12 layers / 256 inputs (/ world size: every rank runs its own packed batch, replicas, no collective).
+
+  e2e: every step copies its input ciphertext batch(es) from pinned host memory and reads its result batch back,
+  inside the timed region (more traffic than a real serving loop, which keeps activations resident between quarters).
+  roofline: the forward NTT passes (ntt_fwd_pass_a + ntt_fwd_pass_b[_grouped]), the dominant kernel pair, timed live
+  with CUDA events around every launch on the launching stream; algorithmic 1 MiB per limb-transform.
+
+Other workloads: `--workload c1` (configs[0], the self-output 768x768 ct-pt matmul; tensor-core roofline),
+`--workload boot` (configs[2], 768 ciphertexts through moai_bootstrap_real).
 
   python bench.py --gpus N --steps K --warmup W            # this repo (CUDA)
-  python bench.py --impl reference --steps K --warmup W    # the reference's SEAL CPU code (oracle/_ref)
+  python bench.py --impl reference --steps K --warmup W    # the reference's SEAL CPU code (oracle/_ref) on all host threads
 """
 import argparse
 import importlib
@@ -33,7 +44,7 @@ MOAI_BITS = [51] + [46] * 20 + [51] * 14 + [58]
 K_IN, C_OUT, LIMBS = 768, 768, 2
 INPUTS_PER_BATCH = 256
 SCALE = 2.0 ** 46
-PUBLISHED_S_PER_INPUT = 1.7  # P:Table 3, SelfOutput Pt-ct MatMul 768x768
+PUBLISHED_S_PER_INPUT = 1.7 / 12  # P:Table 3 "SelfOutput Pt-ct MatMul" is 1.7 s summed over 12 layers: one matmul = 0.142 s/input
 METRIC = "amortized sec/input, self-output 768x768 ct-pt matmul (256 inputs x 128 tok, chain 1->0)"
 WORKLOAD = "C1: ct_pt_matrix_mul_wo_pre_w_mask 768x768, 768 cts @2 limbs, N=65536, all 128 tokens valid"
 LAYER_METRIC = "amortized sec/input, 12-layer BERT-base (256x128 tok)"
@@ -158,7 +169,7 @@ def cpu_baseline_sample(primes_bits_ok=True, cores=None, max_cols=None):
     mask = np.ones(n // 2, dtype=np.int32)
     if oracle.have_ref():
         ref = oracle.SealRef(LOG_N, MOAI_BITS, hamming_weight=192, seed=11)
-        threads = ref.omp_threads()
+        threads = ref.set_threads()          # every host core, whatever OMP_NUM_THREADS says (torchrun exports 1)
         cols = max(1, min(threads, 768 if max_cols is None else max_cols))
         X = np.empty((K_IN, 2, LIMBS, n), dtype=np.uint64)
         for l in range(LIMBS):
@@ -308,7 +319,7 @@ def run_gpu(args):
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        cb = cpu_baseline_sample() if world == 1 and not args.no_cpu_baseline else None
+        cb = cpu_baseline_sample() if not args.no_cpu_baseline else None
         hbm_achieved = algo_bytes / (gemm_avg_ms * 1e-3) / 1e9 if gemm_avg_ms > 0 else 0.0
         line = {"metric": METRIC, "value": value, "unit": "s/input", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak",
@@ -316,9 +327,7 @@ def run_gpu(args):
                 "config": {"workload": WORKLOAD, "inputs_per_step": INPUTS_PER_BATCH * world,
                            "l2": "inputs (1.5 GiB per rank) larger than the 126 MB L2; no flush needed",
                            "parallelism": "replicas x%d (one packed batch per GPU, no collective)" % world,
-                           "other_workloads": "BASELINE.json's 12-layer metric itself: `bench.py --workload layers "
-                                              "--steps 1 --warmup 0` (108 s per layer); measured runs in profiles/ "
-                                              "(layer_r1_fast_f.json, model12_r1_fast.json)"},
+                           "note": "configs[0]; the default workload (`--workload layer`) is BASELINE.json's 12-layer metric"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "s/input", "h2d_bytes_per_step": int(hX.numel() * 8),
                         "d2h_bytes_per_step": int(hOut.numel() * 8)},
@@ -339,17 +348,6 @@ def run_gpu(args):
                 }
         if cb is not None:
             line["cpu_baseline"] = cb
-        # BASELINE.json's own metric (12 encoder layers) takes 108 s per layer, too long for this default run: the
-        # latest COMMITTED measurement of it is attached for reference (not measured by this invocation; re-measure
-        # with `--workload layers --steps 1 --warmup 0`)
-        try:
-            lp = json.load(open(os.path.join(ROOT, "profiles", "layer_r1_fast_f.json")))
-            line["headline_committed"] = {"metric": LAYER_METRIC, "value": lp["amortized_s_per_input_12_layers"],
-                                          "unit": "s/input", "seconds_per_layer": lp["layer_seconds"], "n_gpus": 1,
-                                          "source": "profiles/layer_r1_fast_f.json (tools/layer_bench.py --mode fast)",
-                                          "vs_published_574.6": lp["amortized_s_per_input_12_layers"] / 574.6}
-        except Exception:
-            pass
         print(json.dumps(line))
     be.close()
     if dist is not None:
@@ -357,50 +355,63 @@ def run_gpu(args):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# Optional workload: BASELINE.json configs[3]/[4] — the encoder layer(s) themselves (`--workload layers`).
-# One step = `--layers` L encoder layers back to back on one packed batch (108 s per layer on one B200, so
-# this is NOT the default: `--steps 1 --warmup 0 --layers 1` takes about three minutes including key set-up).
-# value = measured seconds per layer x 12 / 256 = BASELINE.json's metric (exact for L = 12, extrapolated
-# from identical layers otherwise — profiles/model12_r1_fast.json shows 12 layers within +-0.1 % of each other).
+# Default workload: BASELINE.json configs[3]/[4] — the encoder layer, timed in its four bootstrap-delimited quarters
+# (see the module docstring).
 # ---------------------------------------------------------------------------------------------------------
-PUBLISHED_12_LAYERS = 574.6   # P:Table 3 total
-# key switches per encoder layer in the reference's algorithm, by limb count:
+PUBLISHED_12_LAYERS = 574.6   # P:Table 3 total, s per input for 12 layers on a 56-core Xeon 8480+
+LAYER_WORKLOAD = ("C4/C5: BERT-base encoder layer on one packed batch (768 cts @ chain 20, N=65536, 35+1 primes, "
+                  "256 inputs x 128 tokens, all tokens valid), fast mode; step = one bootstrap-delimited quarter of the "
+                  "layer (4 steps = 1 layer); 12-layer figure = seconds per layer x 12")
+STAGE_NAMES = ["attention+selfoutput+bootstrap_1", "layernorm_1+bootstrap_2", "intermediate+gelu+final+bootstrap_3",
+               "layernorm_2+bootstrap_4"]
+# key switches per encoder layer in the REFERENCE's algorithm, by limb count:
 # 3084 bootstrappings x (42 @ ~34, 36 @ ~28, 42 @ ~23), QK^T 240384 @ 14, softmax ~12.7k @ ~8,
 # GELU ~70.7k @ ~5, softmax*V ~31.9k @ 3
 REFERENCE_KS_CENSUS = [(34, 3084 * 42), (28, 3084 * 36), (23, 3084 * 42), (14, 240384), (8, 12700), (5, 70700), (3, 31900)]
+_REF_STATE = {}
 
 
-def cpu_baseline_layers():
-    """Composed CPU figure for the layer workload: the reference's real SEAL (oracle/_ref) is
-    timed on single rotations at the limb counts of the census above (one thread each, ~15 s in total) and the
-    counts are applied with perfect scaling over all host threads.  Key switches are > 90 % of the reference's
-    time (P:Table 3); everything else is left out, so the figure is a LOWER bound of the CPU time."""
+def cpu_baseline_layers(budget_s=20.0):
+    """CPU figure for the layer workload on a bounded sample: the reference's real SEAL (oracle/_ref)
+    runs `threads` independent rotate_vector calls CONCURRENTLY (one per host thread — the reference's own
+    parallelism is an OpenMP loop over independent ciphertexts, test_full_scheme.hpp:654-660) at each limb count of
+    the census above; the measured aggregate key-switch throughput per level is applied to the reference
+    algorithm's key-switch counts per layer.  Key switches are > 90 % of the reference's time (P:Table 3); everything
+    else (7 M encode + multiply_plain, rescales, ...) is left out, so the figure is a LOWER bound of the CPU time."""
+    import concurrent.futures as cf
     import oracle
     if not oracle.have_ref():
         return None
-    ref = oracle.SealRef(LOG_N, MOAI_BITS, hamming_weight=192, seed=11)
-    ref.make_galois_keys([1])
-    threads = ref.omp_threads()
+    if "ref" not in _REF_STATE:
+        ref = oracle.SealRef(LOG_N, MOAI_BITS, hamming_weight=192, seed=11)
+        ref.make_galois_keys([1])
+        _REF_STATE["ref"] = ref
+    ref = _REF_STATE["ref"]
+    threads = os.cpu_count() or 1
     rng = np.random.default_rng(5)
     n = 1 << LOG_N
-    secs, sample = 0.0, []
-    for limbs, count in REFERENCE_KS_CENSUS:
-        ct = np.empty((2, limbs, n), dtype=np.uint64)
-        for l in range(limbs):
-            ct[:, l, :] = rng.integers(0, int(ref.q[l]), (2, n), dtype=np.uint64)
-        t0 = time.perf_counter()
-        ref.eval(oracle.OP_ROTATE, ct.reshape(-1), 2, limbs, SCALE, iarg=1)
-        dt = time.perf_counter() - t0
-        sample.append("%d limbs %.2f s" % (limbs, dt))
-        secs += dt * count
-    per_layer = secs / threads
-    return {"value": per_layer * 12 / INPUTS_PER_BATCH, "unit": "s/input", "cores": threads, "kind": "reference",
-            "sample": "one rotate_vector of the reference's SEAL per level (" + ", ".join(sample) + ", one thread), "
-                      "times the reference algorithm's key-switch census per layer, divided by %d threads; "
-                      "key switches only (lower bound)" % threads}
+    secs, sample, cpu_work = 0.0, [], 0.0
+    with cf.ThreadPoolExecutor(max_workers=threads) as pool:
+        for limbs, count in REFERENCE_KS_CENSUS:
+            cts = []
+            for _ in range(threads):
+                ct = np.empty((2, limbs, n), dtype=np.uint64)
+                for l in range(limbs):
+                    ct[:, l, :] = rng.integers(0, int(ref.q[l]), (2, n), dtype=np.uint64)
+                cts.append(ct.reshape(-1))
+            t0 = time.perf_counter()
+            list(pool.map(lambda c: ref.eval(oracle.OP_ROTATE, c, 2, limbs, SCALE, iarg=1), cts))   # ctypes drops the GIL
+            dt = time.perf_counter() - t0
+            cpu_work += dt
+            sample.append("%d limbs: %d in %.2f s" % (limbs, threads, dt))
+            secs += dt / threads * count
+    return {"value": secs * 12 / INPUTS_PER_BATCH, "unit": "s/input", "cores": threads, "kind": "reference",
+            "sample": "%d concurrent rotate_vector calls of the reference's SEAL per level (" % threads + "; ".join(sample) +
+                      "), %.1f s of wall time in all; aggregate throughput x the reference algorithm's key-switch census "
+                      "per layer x 12 layers / 256 inputs; key switches only (lower bound); HEXL off" % cpu_work}
 
 
-def run_layers(args):
+def run_layer(args):
     import torch
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import layer_bench
@@ -412,69 +423,132 @@ def run_layers(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    st = layer_bench.setup(layer_bench.Args(args.layers, "fast"), device=local_rank)
+    device = torch.device("cuda", local_rank)
+    st = layer_bench.setup(layer_bench.Args(1, "fast"), device=local_rank, seed=11 + rank)
     be, boot, keys, w, x, mask = st["be"], st["boot"], st["keys"], st["w"], st["x"], st["mask"]
+    cw, keep = boot.layer_weights(w)
+    aux = torch.empty_like(x)
+    aux.copy_(x)
+    # host side of the e2e arm: both activation buffers in pinned memory
     hx = torch.empty(x.shape, dtype=torch.int64, pin_memory=True)
+    haux = torch.empty(x.shape, dtype=torch.int64, pin_memory=True)
     hx.copy_(x)
-    hout = torch.empty(x.shape, dtype=torch.int64, pin_memory=True)
+    haux.copy_(aux)
+    boot_chunk = int(os.environ.get("MOAI_BOOT_CHUNK", "32"))
+    nbytes = int(x.numel() * 8)
+    reads = {0: [(x, hx)], 1: [(x, hx), (aux, haux)], 2: [(x, hx)], 3: [(x, hx), (aux, haux)]}   # stage -> inputs
+    writes = {0: (aux, haux), 1: (x, hx), 2: (aux, haux), 3: (x, hx)}                           # stage -> result
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def layers_once():
-        for layer_id in range(args.layers):
-            boot.encoder_layer(keys, x, SCALE, w, mask, 128, 256, layer_id=layer_id % 12, inplace=True)
+    def step(i, ev=None):
+        stage = i % 4
+        if ev:
+            ev[0].record()
+        for dbuf, hbuf in reads[stage]:
+            dbuf.copy_(hbuf, non_blocking=True)            # this step's input ciphertexts arrive from the host
+        if ev:
+            ev[1].record()
+        boot.encoder_layer_stage(keys, stage, x, aux, SCALE, cw, mask, 128, 256, layer_id=(i // 4) % 12,
+                                 boot_chunk=boot_chunk)
+        if ev:
+            ev[2].record()
+        dbuf, hbuf = writes[stage]
+        hbuf.copy_(dbuf, non_blocking=True)                # the step's encrypted result goes back to the host
+        if ev:
+            ev[3].record()
 
-    for _ in range(args.warmup):
-        layers_once()
+    for i in range(args.warmup):
+        step(i)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = be.launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4 * args.steps)]
+    be.profile(True)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     barrier()
-    for s_ in range(args.steps):
-        a, b, c_, d = ev[4 * s_:4 * s_ + 4]
-        a.record()
-        x.copy_(hx, non_blocking=True)        # the packed batch of ciphertexts arrives from the host
-        b.record()
-        layers_once()
-        c_.record()
-        hout.copy_(x, non_blocking=True)      # encrypted result back to the host
-        d.record()
+    for k in range(args.steps):
+        step(args.warmup + k, evs[k])
     barrier()
-    ms_dev = sum(ev[4 * i + 1].elapsed_time(ev[4 * i + 2]) for i in range(args.steps))
-    ms_e2e = sum(ev[4 * i].elapsed_time(ev[4 * i + 3]) for i in range(args.steps))
+    prof = be.profile_dump()
+    be.profile(False)
     launches = be.launch_count() - l0
     clocks = sampler.stop()
-    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=torch.device("cuda", local_rank))
+    dev_ms = [evs[k][1].elapsed_time(evs[k][2]) for k in range(args.steps)]
+    e2e_ms = [evs[k][0].elapsed_time(evs[k][3]) for k in range(args.steps)]
+    stages = [(args.warmup + k) % 4 for k in range(args.steps)]
+
+    def per_layer(ms):
+        """sum over the four quarters of their mean time; quarters the run did not reach are filled with the mean step"""
+        by = {q: [m for m, s_ in zip(ms, stages) if s_ == q] for q in range(4)}
+        mean_all = sum(ms) / len(ms)
+        return sum((sum(v) / len(v)) if v else mean_all for v in by.values()), {q: (sum(v) / len(v) if v else None) for q, v in by.items()}
+
+    layer_ms, by_stage = per_layer(dev_ms)
+    layer_e2e_ms, _ = per_layer(e2e_ms)
+    h2d = sum(len(reads[s_]) for s_ in stages) * nbytes / args.steps
+    t = torch.tensor([layer_ms, layer_e2e_ms, sum(dev_ms)], dtype=torch.float64, device=device)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = float(t[0]), float(t[1])
-    per_layer_s = ms_dev / args.steps / args.layers / 1000.0
-    per_layer_e2e = ms_e2e / args.steps / args.layers / 1000.0
-    value = per_layer_s * 12 / (INPUTS_PER_BATCH * world)
+    layer_ms, layer_e2e_ms, total_ms = float(t[0]), float(t[1]), float(t[2])
+    value = layer_ms / 1000.0 * 12 / (INPUTS_PER_BATCH * world)
+    e2e_value = layer_e2e_ms / 1000.0 * 12 / (INPUTS_PER_BATCH * world)
     if rank == 0:
-        cb = cpu_baseline_layers() if world == 1 and not args.no_cpu_baseline else None
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        if "hbm_gbs" in peaks:
+            hbm_peak, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+        else:
+            hbm_peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
+        ta, ua = prof.get("k_ntt_fwd_pass_a", (0.0, 0))
+        tb, ub = prof.get("k_ntt_fwd_pass_b", (0.0, 0))
+        t1, u1 = prof.get("k_ntt_fwd_fused", (0.0, 0))
+        # one forward limb-transform = pass A + pass B (or the single fused kernel); pass A also feeds the fused
+        # key-switch kernel, so the pair is costed per limb-transform: (ms per unit of A) + (ms per unit of B)
+        units = ub + u1
+        pair_ms = (ta / ua * ub if ua else 0.0) + tb + t1
+        limb_bytes = (1 << LOG_N) * 8
+        achieved = units * 2 * limb_bytes / (pair_ms * 1e-3) / 1e9 if pair_ms > 0 else None
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ntt_fwd_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_limb_transform")
+            except Exception:
+                traffic = None
+        cb = cpu_baseline_layers() if not args.no_cpu_baseline else None
         line = {"metric": LAYER_METRIC, "value": value, "unit": "s/input", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": False, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": False, "scaling": "weak",
                 "vs_baseline": value / PUBLISHED_12_LAYERS, "dtype": "u64/f64", "data": "synthetic",
-                "config": {"workload": "C4/C5: %d encoder layer(s) per step on one packed batch (768 cts, N=65536, "
-                                       "35+1 primes), fast mode; 12-layer figure = seconds per layer x 12" % args.layers,
-                           "layers_per_step": args.layers, "inputs_per_step": INPUTS_PER_BATCH * world,
-                           "l2": "working set (GiBs per stage) far larger than the 126 MB L2",
-                           "parallelism": "replicas x%d (one packed batch per GPU, no collective)" % world},
+                "config": {"workload": LAYER_WORKLOAD, "steps_per_layer": 4, "inputs_per_step": INPUTS_PER_BATCH * world,
+                           "seconds_per_layer": layer_ms / 1000.0,
+                           "quarter_ms": {STAGE_NAMES[q]: v for q, v in by_stage.items()},
+                           "l2": "working set (GiBs per stage) far larger than the 126 MB L2; no flush needed",
+                           "parallelism": "replicas x%d (one packed batch per GPU, no data-path collective)" % world,
+                           "boot_chunk": boot_chunk, "evaluation_keys_GiB": round(st["key_gib"], 1)},
                 "clocks": clocks,
-                "e2e": {"value": per_layer_e2e * 12 / (INPUTS_PER_BATCH * world), "unit": "s/input",
-                        "h2d_bytes_per_step": int(hx.numel() * 8), "d2h_bytes_per_step": int(hout.numel() * 8)},
+                "e2e": {"value": e2e_value, "unit": "s/input", "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": nbytes},
                 "gpu_launches": int(launches),
-                "roofline": {"kernel": "key switching (ntt_fwd_pass_a, ks_passb_mac_kernel, ks_mac_multi_kernel: ~75 % of "
-                                       "the step)", "bound": "hbm", "achieved": None, "peak": None, "unit": "GB/s",
-                             "frac": None, "traffic": None,
-                             "note": "per-kernel rooflines of this workload are in profiles/ (ncu_full_*.csv, "
-                                     "launch_summary_r1_bootstrap_fast.txt) and DESIGN.md section 5; this line times the step"}}
+                "roofline": {"kernel": "forward NTT passes: ntt_fwd_pass_a + ntt_fwd_pass_b[_grouped] (one limb-transform = "
+                                       "both passes)",
+                             "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": achieved / hbm_peak if achieved else None, "traffic": traffic,
+                             "peak_source": peak_src, "limb_transforms": int(units),
+                             "algorithmic_bytes_per_limb_transform": 2 * limb_bytes,
+                             "us_per_limb_transform": pair_ms * 1e3 / units if units else None,
+                             "kernel_ms": {"pass_a": ta, "pass_b": tb, "fused": t1, "pass_a_units": int(ua)},
+                             "kernel_share_of_step": (ta + tb + t1) / sum(dev_ms) if dev_ms else None,
+                             "note": "timed live with CUDA events around every launch on the launching stream; `achieved` = "
+                                     "algorithmic bytes (1 MiB per limb-transform, SURVEY 8(d)) / time; `traffic` = DRAM bytes per "
+                                     "limb-transform from the ncu capture under profiles/"},
+                "phases_ms": {k: round(v[0], 1) for k, v in prof.items() if not k.startswith("alloc") and not k.startswith("k_")}}
         if cb is not None:
             line["cpu_baseline"] = cb
         print(json.dumps(line))
@@ -483,18 +557,25 @@ def run_layers(args):
         dist.destroy_process_group()
 
 
-def run_reference_layers(args):
+def run_reference_layer(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    cb = cpu_baseline_layers()
-    if cb is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (the reference's SEAL) is not built"}))
-        return
-    v = cb["value"]
+    vals, cb = [], None
+    for i in range(args.warmup + args.steps):
+        cb = cpu_baseline_layers()
+        if cb is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (the reference's SEAL) is not built"}))
+            return
+        if i >= args.warmup:
+            vals.append(cb["value"])
+    v = float(np.mean(vals)) if vals else cb["value"]
+    cb["value"] = v
     print(json.dumps({"impl": "reference", "metric": LAYER_METRIC, "value": v, "unit": "s/input", "n_gpus": args.gpus,
-                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": v * INPUTS_PER_BATCH / 12 * 1000.0,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": v * INPUTS_PER_BATCH / 48 * 1000.0,
                       "higher_is_better": False, "scaling": "weak", "vs_baseline": v / PUBLISHED_12_LAYERS,
-                      "dtype": "u64/f64", "data": "synthetic", "config": {"workload": "C4/C5 composed from the key-switch census"},
+                      "dtype": "u64/f64", "data": "synthetic",
+                      "config": {"workload": LAYER_WORKLOAD, "steps_per_layer": 4,
+                                 "note": "each step re-times the bounded sample described in cpu_baseline.sample"},
                       "cpu_baseline": cb,
                       "e2e": {"value": v, "unit": "s/input", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -502,21 +583,22 @@ def run_reference_layers(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="moai_b200", choices=["moai_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c1", choices=["c1", "layers"],
-                    help="c1 (default): self-output ct-pt matmul, finishes in seconds; layers: whole encoder layers "
-                         "(108 s each — use --steps 1 --warmup 0)")
-    ap.add_argument("--layers", type=int, default=1, help="encoder layers per step of --workload layers")
+    ap.add_argument("--workload", default="layer", choices=["layer", "c1"],
+                    help="layer (default): the encoder layer in bootstrap-delimited quarters = BASELINE.json's metric; "
+                         "c1: the self-output ct-pt matmul (configs[0])")
     args = ap.parse_args()
-    if args.workload == "layers":
-        (run_reference_layers if args.impl == "reference" else run_layers)(args)
-    elif args.impl == "reference":
-        run_reference(args)
+    if args.workload == "layer":
+        args.steps = 4 if args.steps is None else args.steps        # one whole layer timed, one as warm-up
+        args.warmup = 4 if args.warmup is None else args.warmup
+        (run_reference_layer if args.impl == "reference" else run_layer)(args)
     else:
-        run_gpu(args)
+        args.steps = 5 if args.steps is None else args.steps
+        args.warmup = 3 if args.warmup is None else args.warmup
+        (run_reference if args.impl == "reference" else run_gpu)(args)
 
 
 if __name__ == "__main__":

@@ -127,6 +127,14 @@ int32_t moai_bootstrap(moai_context *ctx, moai_bootstrapper *b, moai_keys *keys,
  * of the inputs must be zero (they are mixed into the partner otherwise).  moai_encoder_layer uses this for its
  * 4 x 768 bootstrappings (M/test/test_full_scheme.hpp:654-660, 758-764, 991-995, 1081-1085) unless the
  * environment sets MOAI_BOOT_PAIR=0.                                                                        */
+/* Diagnostics: the same pipeline stopped after one phase, for per-phase decrypted-error reports (bootstrap_full_3's
+ * phases, Bootstrapper.cpp:3231-3251).  stop_after 1: ModRaise -> batch ciphertexts at total_limbs, scale q0 (plaintext
+ * t = m + q0 I); 2: CoeffToSlot -> 2 x batch ciphertexts (real halves, then imaginary halves) whose slots hold
+ * t[bitrev(j)] / (K q0) and t[bitrev(j) + N/2] / (K q0); 3: EvalMod -> 2 x batch, slots ~ sin(2 pi t / q0).
+ * out must hold 2 x batch ciphertexts at total_limbs. */
+int32_t moai_bootstrap_phase_debug(moai_context *ctx, moai_bootstrapper *b, moai_keys *keys, const uint64_t *in,
+                                   int64_t batch, double scale, int32_t stop_after, uint64_t *out, int64_t *out_count,
+                                   int32_t *out_limbs, double *out_scale);
 int32_t moai_bootstrap_real(moai_context *ctx, moai_bootstrapper *b, moai_keys *keys, const uint64_t *in,
                             int64_t batch, double scale, int64_t chunk_pairs, uint64_t *out, int32_t *out_limbs,
                             double *out_scale);
@@ -177,6 +185,17 @@ int32_t moai_encoder_layer(moai_context *ctx, moai_keys *keys, moai_bootstrapper
                            double scale, const moai_layer_weights *w, const int32_t *bias_vec, int32_t input_num,
                            int32_t num_batch, int32_t layer_id, int64_t boot_chunk, uint64_t *out,
                            int32_t *out_limbs, double *out_scale);
+/* The same layer one bootstrap-delimited quarter at a time, on two caller-owned buffers of the layer's shape
+ * ([hidden][2][limbs][N]): x holds the layer input (and, after stage 3, the layer output = the next layer's input), aux
+ * the other live activation.  stage 0: attention + self-output matmul + bootstrapping (test_full_scheme.hpp:496-660)
+ * reads x, writes aux; 1: residual + LayerNorm + bootstrapping (:686-773) reads both, writes x; 2: intermediate matmul
+ * + GELU + final matmul + bootstrapping (:807-995) reads x, writes aux; 3: residual + LayerNorm2 + bootstrapping
+ * (:1016-1087) reads both, writes x.  moai_encoder_layer is exactly stages 0..3 in order.  A serving loop uses this to
+ * interleave several packed batches, to checkpoint between bootstrappings, and bench.py to time the layer in steps. */
+int32_t moai_encoder_layer_stage(moai_context *ctx, moai_keys *keys, moai_bootstrapper *b, int32_t stage, uint64_t *x,
+                                 uint64_t *aux, int32_t limbs, double scale, const moai_layer_weights *w,
+                                 const int32_t *bias_vec, int32_t input_num, int32_t num_batch, int32_t layer_id,
+                                 int64_t boot_chunk);
 /* "name:ms:count;" for every profiled phase (see moai_profile_enable) */
 int32_t moai_profile_dump(moai_context *ctx, char *buf, int32_t capacity);
 

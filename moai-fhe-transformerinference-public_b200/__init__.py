@@ -522,6 +522,19 @@ class Bootstrapper:
         assert ol.value == self.total_limbs - 14
         return out, osc.value
 
+    def bootstrap_phase_debug(self, keys, x, scale, stop_after):
+        """The pipeline stopped after ModRaise (1), CoeffToSlot (2) or EvalMod (3): (ciphertexts
+        [count, 2, limbs, n], scale); count = batch (1) or 2 * batch (2, 3: real halves then imaginary halves)."""
+        be = self.be
+        bt, p, l, n = x.shape
+        buf = be.empty(2 * bt, 2, self.total_limbs, n)
+        oc, ol, osc = C.c_int64(), C.c_int32(), C.c_double()
+        be._chk(be.lib.moai_bootstrap_phase_debug(be.h, self.h, keys.h, _ptr(x), C.c_int64(bt), C.c_double(scale),
+                                                  C.c_int32(stop_after), _ptr(buf), C.byref(oc), C.byref(ol),
+                                                  C.byref(osc)))
+        flat = buf.reshape(-1)[: oc.value * 2 * ol.value * n]
+        return flat.reshape(oc.value, 2, ol.value, n), osc.value
+
     def bootstrap_real(self, keys, x, scale, chunk_pairs=32):
         """Real-slot messages, two per bootstrapping (moai_bootstrap_real): x [batch, 2, 1, n] ->
         ([batch, 2, total_limbs - 14, n], final_scale) with ceil(batch / 2) bootstrappings."""
@@ -571,6 +584,27 @@ class Bootstrapper:
                           C.c_double(scale), C.byref(w), bv.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int32(input_num),
                           C.c_int32(num_batch), C.c_int32(layer_id), C.c_int64(boot_chunk),
                           out=x if inplace else None)
+
+    def layer_weights(self, weights):
+        """dict with the fields of moai_layer_weights -> (C struct, keep-alive list)."""
+        dp = C.POINTER(C.c_double)
+        keep = {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in weights.items()
+                if k not in ("hidden", "heads", "head_dim", "inter")}
+        w = LayerWeightsC(hidden=weights["hidden"], heads=weights["heads"], head_dim=weights["head_dim"],
+                          inter=weights["inter"], **{k: v.ctypes.data_as(dp) for k, v in keep.items()})
+        return w, keep
+
+    def encoder_layer_stage(self, keys, stage, x, aux, scale, cweights, bias_vec, input_num, num_batch, layer_id=0,
+                            boot_chunk=32):
+        """One bootstrap-delimited quarter of the encoder layer, in place on the two persistent buffers x and aux
+        (moai_encoder_layer_stage).  cweights: the struct returned by layer_weights()."""
+        be = self.be
+        bt, p, l, n = x.shape
+        bv = np.ascontiguousarray(bias_vec, dtype=np.int32)
+        be._chk(be.lib.moai_encoder_layer_stage(be.h, keys.h, self.h, C.c_int32(stage), _ptr(x), _ptr(aux), C.c_int32(l),
+                                                C.c_double(scale), C.byref(cweights),
+                                                bv.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int32(input_num),
+                                                C.c_int32(num_batch), C.c_int32(layer_id), C.c_int64(boot_chunk)))
 
     def __del__(self):
         try:

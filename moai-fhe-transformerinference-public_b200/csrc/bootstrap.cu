@@ -657,7 +657,7 @@ namespace moai
     }
 
     // ------------------------------------------------------------------------------------ bootstrap
-    Ct Bootstrapper::bootstrap(const Evaluator &ev, const Ct &in, const Keys &keys)
+    Ct Bootstrapper::bootstrap(const Evaluator &ev, const Ct &in, const Keys &keys, int stop_after)
     {
         MOAI_REQUIRE(in.size == 2 && in.limbs == 1, "bootstrap expects size-2 ciphertexts at the last level");
         const int n = slots();
@@ -678,6 +678,10 @@ namespace moai
         }
         const double initial_scale = in.scale;
         ct.scale = q0;
+        if (stop_after == 1)
+        {
+            return ct;
+        }
         // 2. CoeffToSlot: slots <- (c_lo + i c_hi) / (2 K q0)   (bit-reversed order)
         for (int s = 0; s < 3; s++)
         {
@@ -689,11 +693,19 @@ namespace moai
         Ct im = ev.sub(ct, conj);                 // 2 i c_hi / (2 K q0)
         std::vector<cd> minus_i((size_t)n, cd(0, -1)), plus_i((size_t)n, cd(0, 1));
         im = ev.multiply_plain(im, ev.encode(minus_i, im.limbs, 1.0)); // exact monomial, no level
+        if (stop_after == 2)
+        {
+            return ev.concat({ re, im });
+        }
         // 3. EvalMod on both halves as one batch: sin(2 pi t / q0) ~ 2 pi m / q0
         Ct both;
         {
             PhaseTimer t(c_, "boot_eval_mod");
             both = eval_mod(ev, ev.concat({ re, im }), keys);
+        }
+        if (stop_after == 3)
+        {
+            return both;
         }
         re = ev.view(both, 0, in.batch);
         im = ev.view(both, in.batch, in.batch);

@@ -71,7 +71,10 @@ namespace moai
         std::vector<int> required_steps() const; // rotation steps (normalised to [0, slots)) the BSGS plans use
         // in: batch of size-2 ciphertexts at 1 limb (chain_index 0); returns them at
         // total_limbs - 14 limbs with scale final_scale
-        Ct bootstrap(const Evaluator &ev, const Ct &in, const Keys &keys);
+        // stop_after (diagnostics, moai_bootstrap_phase_debug): 0 = the whole bootstrapping; 1 = return after ModRaise
+        // (scale q0); 2 = after CoeffToSlot (2 x batch ciphertexts: real halves then imaginary halves); 3 = after
+        // EvalMod (same order)
+        Ct bootstrap(const Evaluator &ev, const Ct &in, const Keys &keys, int stop_after = 0);
 
         // Bootstrapping of REAL-slot messages, two per bootstrapping.  A full-slot bootstrapping refreshes N
         // independent real coefficients; a real-slot message only uses N/2 of them (its polynomial is fixed by

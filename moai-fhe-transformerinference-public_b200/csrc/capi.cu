@@ -124,6 +124,7 @@ extern "C"
     {
         API_BEGIN
         Context *c = get(ctx);
+        c->kernel_timers_collect(true);
         c->profiling = on != 0;
         if (on)
         {
@@ -137,6 +138,7 @@ extern "C"
         API_BEGIN
         Context *c = get(ctx);
         MOAI_REQUIRE(name && ms && count, "null argument");
+        c->kernel_timers_collect(true);
         auto it = c->prof.find(name);
         *ms = it == c->prof.end() ? 0.0 : it->second.first;
         *count = it == c->prof.end() ? 0 : it->second.second;
@@ -803,6 +805,26 @@ extern "C"
         API_END
     }
 
+    int32_t moai_bootstrap_phase_debug(moai_context *ctx, moai_bootstrapper *b, moai_keys *keys, const uint64_t *in,
+                                       int64_t batch, double scale, int32_t stop_after, uint64_t *out, int64_t *out_count,
+                                       int32_t *out_limbs, double *out_scale)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(b && in && out && out_count && out_limbs && out_scale, "null argument");
+        MOAI_REQUIRE(stop_after >= 1 && stop_after <= 3, "stop_after must be 1 (ModRaise), 2 (CoeffToSlot) or 3 (EvalMod)");
+        check_shape(c, batch, 2, 1);
+        Evaluator ev(c);
+        Ct r = b->b->bootstrap(ev, ev.wrap(const_cast<u64 *>(CU(in)), batch, 2, 1, scale), getk(keys), stop_after);
+        MOAI_CUDA_CHECK(cudaMemcpyAsync(out, r.d, (size_t)r.batch * 2 * r.limbs * c->n * sizeof(u64),
+                                        cudaMemcpyDeviceToDevice, c->stream));
+        *out_count = r.batch;
+        *out_limbs = r.limbs;
+        *out_scale = r.scale;
+        MOAI_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        API_END
+    }
+
     int32_t moai_bootstrap_real(moai_context *ctx, moai_bootstrapper *b, moai_keys *keys, const uint64_t *in,
                                 int64_t batch, double scale, int64_t chunk_pairs, uint64_t *out, int32_t *out_limbs,
                                 double *out_scale)
@@ -934,17 +956,9 @@ extern "C"
         API_END
     }
 
-    int32_t moai_encoder_layer(moai_context *ctx, moai_keys *keys, moai_bootstrapper *b, const uint64_t *x,
-                               int32_t limbs, double scale, const moai_layer_weights *w, const int32_t *bias_vec,
-                               int32_t input_num, int32_t num_batch, int32_t layer_id, int64_t boot_chunk,
-                               uint64_t *out, int32_t *out_limbs, double *out_scale)
+    static LayerWeights to_layer_weights(const moai_layer_weights *w)
     {
-        API_BEGIN
-        Context *c = get(ctx);
-        MOAI_REQUIRE(b && w && bias_vec, "null argument");
-        check_shape(c, w->hidden, 2, limbs);
         MOAI_REQUIRE(w->hidden == w->heads * w->head_dim, "hidden must equal heads * head_dim");
-        Evaluator ev(c);
         LayerWeights lw;
         lw.hidden = w->hidden;
         lw.heads = w->heads;
@@ -971,11 +985,55 @@ extern "C"
         lw.final_bias.assign(w->final_bias, w->final_bias + H);
         lw.ln2_gamma.assign(w->ln2_gamma, w->ln2_gamma + H);
         lw.ln2_beta.assign(w->ln2_beta, w->ln2_beta + H);
+        return lw;
+    }
+
+    int32_t moai_encoder_layer(moai_context *ctx, moai_keys *keys, moai_bootstrapper *b, const uint64_t *x,
+                               int32_t limbs, double scale, const moai_layer_weights *w, const int32_t *bias_vec,
+                               int32_t input_num, int32_t num_batch, int32_t layer_id, int64_t boot_chunk,
+                               uint64_t *out, int32_t *out_limbs, double *out_scale)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(b && w && bias_vec, "null argument");
+        check_shape(c, w->hidden, 2, limbs);
+        Evaluator ev(c);
+        LayerWeights lw = to_layer_weights(w);
         std::vector<int> bv(bias_vec, bias_vec + c->n / 2);
         Ct r = encoder_layer(ev, ev.wrap(const_cast<u64 *>(CU(x)), w->hidden, 2, limbs, scale), lw, bv, input_num,
                              getk(keys), *b->b, num_batch, layer_id, boot_chunk > 0 ? boot_chunk : 32,
                              /*reuse_input=*/out == x);
-        emit(c, r, out, w->hidden, out_limbs, out_scale);
+        if (reinterpret_cast<const uint64_t *>(r.d) == out)
+        {
+            MOAI_REQUIRE(out_limbs && out_scale, "null argument");
+            *out_limbs = r.limbs;
+            *out_scale = r.scale;
+            MOAI_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        }
+        else
+        {
+            emit(c, r, out, w->hidden, out_limbs, out_scale);
+        }
+        API_END
+    }
+
+    int32_t moai_encoder_layer_stage(moai_context *ctx, moai_keys *keys, moai_bootstrapper *b, int32_t stage, uint64_t *x,
+                                     uint64_t *aux, int32_t limbs, double scale, const moai_layer_weights *w,
+                                     const int32_t *bias_vec, int32_t input_num, int32_t num_batch, int32_t layer_id,
+                                     int64_t boot_chunk)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(b && w && bias_vec && x && aux && x != aux, "null or aliased argument");
+        check_shape(c, w->hidden, 2, limbs);
+        Evaluator ev(c);
+        LayerWeights lw = to_layer_weights(w);
+        std::vector<int> bv(bias_vec, bias_vec + c->n / 2);
+        Ct cx = ev.wrap(reinterpret_cast<u64 *>(x), w->hidden, 2, limbs, scale);
+        Ct ca = ev.wrap(reinterpret_cast<u64 *>(aux), w->hidden, 2, limbs, scale);
+        encoder_layer_stage(ev, stage, cx, ca, lw, bv, input_num, getk(keys), *b->b, num_batch, layer_id,
+                            boot_chunk > 0 ? boot_chunk : 32);
+        MOAI_CUDA_CHECK(cudaStreamSynchronize(c->stream)); // temporaries of the stage are released on return
         API_END
     }
 
@@ -984,6 +1042,7 @@ extern "C"
         API_BEGIN
         Context *c = get(ctx);
         MOAI_REQUIRE(buf && capacity > 0, "bad arguments");
+        c->kernel_timers_collect(true);
         std::string s;
         for (auto &kv : c->prof)
         {

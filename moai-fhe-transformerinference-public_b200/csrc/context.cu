@@ -271,8 +271,35 @@ namespace moai
                 Arena small{ 512, (size_t)8 << 20 };            // requests below 1 MiB
                 Arena large{ (size_t)1 << 20, (size_t)1 << 30 }; // everything else, 1 GiB segments at least
             };
-            std::map<cudaStream_t, PerStream> arenas;
+            // keyed by (device, stream): stream 0 / torch's default stream is the same handle on every device, and a
+            // block cudaMalloc'ed on one device must never serve a context on another
+            typedef std::pair<int, cudaStream_t> ArenaKey;
+            std::map<ArenaKey, PerStream> arenas;
             AllocStats stats;
+
+            static int current_device()
+            {
+                int dev = 0;
+                cudaGetDevice(&dev);
+                return dev;
+            }
+
+            // every device this cache holds memory on (trim returns blocks that in-flight work may still use)
+            void sync_all_devices_locked()
+            {
+                const int cur = current_device();
+                std::set<int> devs{ cur };
+                for (auto &kv : arenas)
+                {
+                    devs.insert(kv.first.first);
+                }
+                for (int d : devs)
+                {
+                    cudaSetDevice(d);
+                    cudaDeviceSynchronize();
+                }
+                cudaSetDevice(cur);
+            }
 
             void trim_all_locked()
             {
@@ -308,7 +335,7 @@ namespace moai
                 bytes = bytes ? bytes : 8;
                 std::lock_guard<std::mutex> lock(mu);
                 stats.calls += 1;
-                PerStream &ps = arenas[stream];
+                PerStream &ps = arenas[ArenaKey(current_device(), stream)];
                 Arena &a = bytes < ((size_t)1 << 20) ? ps.small : ps.large;
                 const size_t want = (bytes + a.granule - 1) / a.granule * a.granule;
                 if (void *p = a.alloc_cached(want))
@@ -322,7 +349,7 @@ namespace moai
                 {
                     cudaGetLastError();
                     stats.retries += 1;
-                    cudaDeviceSynchronize();
+                    sync_all_devices_locked();
                     trim_all_locked();
                     e = a.grow(want, &p);
                 }
@@ -346,12 +373,12 @@ namespace moai
             void release(void *p, cudaStream_t stream)
             {
                 std::lock_guard<std::mutex> lock(mu);
-                auto it = arenas.find(stream);
+                auto it = arenas.find(ArenaKey(current_device(), stream));
                 if (it != arenas.end() && (it->second.large.release(p) || it->second.small.release(p)))
                 {
                     return;
                 }
-                for (auto &kv : arenas) // freed on another stream than it was allocated on
+                for (auto &kv : arenas) // freed on another stream (or with another current device) than it was allocated on
                 {
                     if (kv.second.large.release(p) || kv.second.small.release(p))
                     {
@@ -392,8 +419,8 @@ namespace moai
 
     void device_release_cached()
     {
-        cudaDeviceSynchronize();
         std::lock_guard<std::mutex> lock(cache().mu);
+        cache().sync_all_devices_locked();
         cache().trim_all_locked();
     }
 
@@ -410,8 +437,38 @@ namespace moai
         device_free(p, s);
     }
 
+    void Context::kernel_timers_collect(bool wait)
+    {
+        if (wait && !kpending.empty())
+        {
+            cudaEventSynchronize(kpending.back().e1);
+        }
+        while (!kpending.empty())
+        {
+            PendingKernel &k = kpending.front();
+            if (cudaEventQuery(k.e1) != cudaSuccess)
+            {
+                cudaGetLastError();
+                break;
+            }
+            float ms = 0;
+            cudaEventElapsedTime(&ms, k.e0, k.e1);
+            auto &slot = prof[k.name];
+            slot.first += ms;
+            slot.second += k.units;
+            kpool.push_back(k.e0);
+            kpool.push_back(k.e1);
+            kpending.pop_front();
+        }
+    }
+
     Context::~Context()
     {
+        kernel_timers_collect(true);
+        for (cudaEvent_t e : kpool)
+        {
+            cudaEventDestroy(e);
+        }
         cudaFree(d_limb);
         cudaFree(d_fwd);
         cudaFree(d_inv);

@@ -9,6 +9,7 @@
 #include "modarith.cuh"
 #include <cuda_runtime.h>
 #include <functional>
+#include <deque>
 #include <map>
 #include <mutex>
 #include <string>
@@ -108,6 +109,17 @@ namespace moai
         unsigned long long launches = 0;
         bool profiling = false;
         std::map<std::string, std::pair<double, long long>> prof; // name -> (ms, count)
+        // per-kernel timers (KernelTimer): event pairs recorded on the launching stream and resolved later, so that
+        // timing a kernel never stalls the launch queue; prof[name] accumulates (ms, units)
+        struct PendingKernel
+        {
+            const char *name;
+            cudaEvent_t e0, e1;
+            long long units;
+        };
+        std::deque<PendingKernel> kpending;
+        std::vector<cudaEvent_t> kpool;
+        void kernel_timers_collect(bool wait); // fold finished pairs into prof (wait: synchronise first)
 
         std::mutex galois_mu;
         std::map<uint32_t, uint32_t *> galois_tables; // elt -> device [n]
@@ -153,6 +165,51 @@ namespace moai
         }
     };
 
+
+    // RAII device timer around ONE kernel launch (only when Context::profiling): CUDA events on the launching stream,
+    // never synchronises; `units` = the kernel's work units (e.g. limb-transforms) for roofline accounting.
+    struct KernelTimer
+    {
+        Context *c;
+        Context::PendingKernel p{};
+        KernelTimer(Context *ctx, const char *nm, long long units) : c(ctx)
+        {
+            if (!c->profiling)
+            {
+                return;
+            }
+            auto take = [&]() {
+                cudaEvent_t e;
+                if (c->kpool.empty())
+                {
+                    cudaEventCreate(&e);
+                }
+                else
+                {
+                    e = c->kpool.back();
+                    c->kpool.pop_back();
+                }
+                return e;
+            };
+            p.name = nm;
+            p.units = units;
+            p.e0 = take();
+            p.e1 = take();
+            cudaEventRecord(p.e0, c->stream);
+        }
+        ~KernelTimer()
+        {
+            if (p.e0)
+            {
+                cudaEventRecord(p.e1, c->stream);
+                c->kpending.push_back(p);
+                if (c->kpending.size() > 65536)
+                {
+                    c->kernel_timers_collect(false);
+                }
+            }
+        }
+    };
 
     // stream-ordered scratch allocation
     struct Scratch

@@ -625,96 +625,123 @@ namespace moai
         }
     } // namespace
 
+    // One bootstrap-delimited quarter of the encoder layer, on two persistent buffers of the layer's shape
+    // ([hidden][2][total_limbs - 14][N]): `x` holds the layer input and `aux` the other live activation.
+    //   stage 0: attention + self-output matmul + bootstrap_1          reads x            writes aux
+    //   stage 1: residual (aux += x) + LayerNorm + bootstrap_2         reads x, aux       writes x   (x is dead after the residual)
+    //   stage 2: intermediate matmul + GELU + final matmul + bootstrap_3   reads x        writes aux
+    //   stage 3: residual (aux += x) + LayerNorm2 + bootstrap_4        reads x, aux       writes x   (= the next layer's input)
+    // (M/test/test_full_scheme.hpp:496-660, 686-773, 807-995, 1016-1087.)
+    void encoder_layer_stage(const Evaluator &ev, int stage, Ct &x, Ct &aux, const LayerWeights &w,
+                             const std::vector<int> &bias_vec, int input_num, const Keys &keys, Bootstrapper &boot,
+                             int num_batch, int layer_id, long long boot_chunk)
+    {
+        const double scale = x.scale;
+        const int hidden = w.hidden;
+        MOAI_REQUIRE(stage >= 0 && stage < 4, "stage must be 0..3");
+        MOAI_REQUIRE(x.batch == hidden && x.size == 2, "layer input must be one ciphertext per hidden column");
+        MOAI_REQUIRE(x.limbs == boot.prm.total_limbs - 14, "layer input must be at the post-bootstrapping level");
+        MOAI_REQUIRE(aux.batch == hidden && aux.size == 2 && aux.limbs == x.limbs, "aux must have the layer's shape");
+        Context *c = ev.c;
+        if (stage == 0)
+        {
+            // ---- attention (chain_index 14), heads processed one after the other like the reference
+            Ct att_out = ev.alloc(hidden, 2, 2, scale);
+            {
+                PhaseTimer t(c, "attention");
+                Ct x_att = ev.mod_switch_to(x, x.limbs - 6);
+                for (int h = 0; h < w.heads; h++)
+                {
+                    Ct o = single_att_block(ev, x_att, w.WQ[h], w.WK[h], w.WV[h], w.bQ[h], w.bK[h], w.bV[h], bias_vec,
+                                            input_num, keys, boot, num_batch, 16, layer_id);
+                    MOAI_REQUIRE(o.limbs == 2 && o.batch == w.head_dim, "attention head output shape");
+                    ev.copy_into(o, att_out, (long long)h * w.head_dim);
+                }
+            }
+            Ct so;
+            {
+                PhaseTimer t(c, "selfoutput_matmul");
+                so = add_masked_bias(ev, masked_matmul(ev, att_out, w.selfoutput, bias_vec, hidden), w.selfoutput_bias,
+                                     bias_vec, scale);
+                att_out = Ct();
+            }
+            PhaseTimer t(c, "bootstrap_1");
+            bootstrap_all(ev, so, keys, boot, boot_chunk, &aux);
+            aux.scale = boot.prm.final_scale;
+        }
+        else if (stage == 1)
+        {
+            Ct ln1;
+            {
+                PhaseTimer t(c, "layernorm_1");
+                ev.add_inplace(aux, x); // residual
+                ln1 = layernorm(ev, aux, w.ln1_gamma, w.ln1_beta, bias_vec, keys, 1);
+            }
+            PhaseTimer t(c, "bootstrap_2");
+            bootstrap_all(ev, ln1, keys, boot, boot_chunk, &x); // x is dead after the first residual
+            x.scale = boot.prm.final_scale;
+        }
+        else if (stage == 2)
+        {
+            Ct inter;
+            {
+                PhaseTimer t(c, "intermediate_matmul");
+                Ct lowered = ev.mod_switch_to(x, x.limbs - 11);
+                inter = add_masked_bias(ev, ct_pt_matrix_mul_wo_pre(ev, lowered, w.inter_weight, w.inter), w.inter_bias,
+                                        bias_vec, scale);
+            }
+            {
+                // 3072 independent GELUs (test_full_scheme.hpp:884-888); chunked: gelu_v2 keeps 24 powers alive
+                PhaseTimer t(c, "gelu");
+                const long long chunk = 64;
+                Ct g;
+                for (long long b0 = 0; b0 < inter.batch; b0 += chunk)
+                {
+                    const long long nb = std::min(chunk, inter.batch - b0);
+                    Ct part = gelu_v2(ev, ev.view(inter, b0, nb), keys);
+                    if (g.empty())
+                    {
+                        g = ev.alloc(inter.batch, 2, part.limbs, part.scale);
+                    }
+                    ev.copy_into(part, g, b0);
+                }
+                inter = g;
+            }
+            Ct fin;
+            {
+                PhaseTimer t(c, "final_matmul");
+                fin = add_masked_bias(ev, masked_matmul(ev, inter, w.final_weight, bias_vec, hidden), w.final_bias,
+                                      bias_vec, scale);
+                inter = Ct();
+            }
+            PhaseTimer t(c, "bootstrap_3");
+            bootstrap_all(ev, fin, keys, boot, boot_chunk, &aux);
+            aux.scale = boot.prm.final_scale;
+        }
+        else
+        {
+            Ct ln2;
+            {
+                PhaseTimer t(c, "layernorm_2");
+                ev.add_inplace(aux, x); // residual with the LN1 output
+                ln2 = layernorm(ev, aux, w.ln2_gamma, w.ln2_beta, bias_vec, keys, 2);
+            }
+            PhaseTimer t(c, "bootstrap_4");
+            bootstrap_all(ev, ln2, keys, boot, boot_chunk, &x);
+            x.scale = boot.prm.final_scale;
+        }
+    }
+
     Ct encoder_layer(const Evaluator &ev, const Ct &x, const LayerWeights &w, const std::vector<int> &bias_vec,
                      int input_num, const Keys &keys, Bootstrapper &boot, int num_batch, int layer_id,
                      long long boot_chunk, bool reuse_input)
     {
-        const double scale = x.scale;
-        const int hidden = w.hidden;
-        MOAI_REQUIRE(x.batch == hidden && x.size == 2, "layer input must be one ciphertext per hidden column");
-        MOAI_REQUIRE(x.limbs == boot.prm.total_limbs - 14, "layer input must be at the post-bootstrapping level");
-        Context *c = ev.c;
-        // ---- attention (chain_index 14), heads processed one after the other like the reference
-        Ct att_out = ev.alloc(hidden, 2, 2, scale);
+        Ct work = reuse_input ? x : ev.clone(x);
+        Ct aux = ev.alloc(x.batch, 2, x.limbs, x.scale);
+        for (int stage = 0; stage < 4; stage++)
         {
-            PhaseTimer t(c, "attention");
-            Ct x_att = ev.mod_switch_to(x, x.limbs - 6);
-            for (int h = 0; h < w.heads; h++)
-            {
-                Ct o = single_att_block(ev, x_att, w.WQ[h], w.WK[h], w.WV[h], w.bQ[h], w.bK[h], w.bV[h], bias_vec,
-                                        input_num, keys, boot, num_batch, 16, layer_id);
-                MOAI_REQUIRE(o.limbs == 2 && o.batch == w.head_dim, "attention head output shape");
-                ev.copy_into(o, att_out, (long long)h * w.head_dim);
-            }
+            encoder_layer_stage(ev, stage, work, aux, w, bias_vec, input_num, keys, boot, num_batch, layer_id, boot_chunk);
         }
-        Ct rtn;
-        {
-            PhaseTimer t(c, "selfoutput_matmul");
-            Ct so = add_masked_bias(ev, masked_matmul(ev, att_out, w.selfoutput, bias_vec, hidden), w.selfoutput_bias,
-                                    bias_vec, scale);
-            att_out = Ct();
-            rtn = so;
-        }
-        {
-            PhaseTimer t(c, "bootstrap_1");
-            rtn = bootstrap_all(ev, rtn, keys, boot, boot_chunk);
-        }
-        Ct ln1;
-        {
-            PhaseTimer t(c, "layernorm_1");
-            ev.add_inplace(rtn, ev.mod_switch_to(x, rtn.limbs)); // residual
-            ln1 = layernorm(ev, rtn, w.ln1_gamma, w.ln1_beta, bias_vec, keys, 1);
-            rtn = Ct();
-        }
-        Ct boot_layer;
-        {
-            PhaseTimer t(c, "bootstrap_2");
-            // x is dead after the first residual: with reuse_input its storage receives this result
-            boot_layer = bootstrap_all(ev, ln1, keys, boot, boot_chunk, reuse_input ? &x : nullptr);
-            ln1 = Ct();
-        }
-        Ct inter;
-        {
-            PhaseTimer t(c, "intermediate_matmul");
-            Ct lowered = ev.mod_switch_to(boot_layer, boot_layer.limbs - 11);
-            inter = add_masked_bias(ev, ct_pt_matrix_mul_wo_pre(ev, lowered, w.inter_weight, w.inter), w.inter_bias,
-                                    bias_vec, scale);
-        }
-        {
-            // 3072 independent GELUs (test_full_scheme.hpp:884-888); chunked: gelu_v2 keeps 24 powers alive
-            PhaseTimer t(c, "gelu");
-            const long long chunk = 64;
-            Ct g;
-            for (long long b0 = 0; b0 < inter.batch; b0 += chunk)
-            {
-                const long long nb = std::min(chunk, inter.batch - b0);
-                Ct part = gelu_v2(ev, ev.view(inter, b0, nb), keys);
-                if (g.empty())
-                {
-                    g = ev.alloc(inter.batch, 2, part.limbs, part.scale);
-                }
-                ev.copy_into(part, g, b0);
-            }
-            inter = g;
-        }
-        Ct fin;
-        {
-            PhaseTimer t(c, "final_matmul");
-            fin = add_masked_bias(ev, masked_matmul(ev, inter, w.final_weight, bias_vec, hidden), w.final_bias, bias_vec,
-                                  scale);
-            inter = Ct();
-        }
-        {
-            PhaseTimer t(c, "bootstrap_3");
-            fin = bootstrap_all(ev, fin, keys, boot, boot_chunk);
-        }
-        Ct ln2;
-        {
-            PhaseTimer t(c, "layernorm_2");
-            ev.add_inplace(fin, ev.mod_switch_to(boot_layer, fin.limbs)); // residual with the LN1 output
-            ln2 = layernorm(ev, fin, w.ln2_gamma, w.ln2_beta, bias_vec, keys, 2);
-        }
-        PhaseTimer t(c, "bootstrap_4");
-        return bootstrap_all(ev, ln2, keys, boot, boot_chunk);
+        return work;
     }
 } // namespace moai

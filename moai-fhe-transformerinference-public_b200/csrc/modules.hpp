@@ -44,4 +44,8 @@ namespace moai
     Ct encoder_layer(const Evaluator &ev, const Ct &x, const LayerWeights &w, const std::vector<int> &bias_vec,
                      int input_num, const Keys &keys, Bootstrapper &boot, int num_batch, int layer_id,
                      long long boot_chunk, bool reuse_input = false);
+    // One bootstrap-delimited quarter of the layer (stage 0..3) on two persistent buffers; see modules.cu.
+    void encoder_layer_stage(const Evaluator &ev, int stage, Ct &x, Ct &aux, const LayerWeights &w,
+                             const std::vector<int> &bias_vec, int input_num, const Keys &keys, Bootstrapper &boot,
+                             int num_batch, int layer_id, long long boot_chunk);
 } // namespace moai

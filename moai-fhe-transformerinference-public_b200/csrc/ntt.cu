@@ -1172,16 +1172,19 @@ namespace moai
             }
         }
 
+        // KernelTimer names: "k_ntt_fwd_pass_a" / "k_ntt_fwd_pass_b" with units = limb-transforms (bench.py's roofline)
         template <int LOGR>
-        void launch_fwd(const NttArgs &a, cudaStream_t s, bool do_a = true, bool do_b = true)
+        void launch_fwd(Context *c, const NttArgs &a, cudaStream_t s, bool do_a = true, bool do_b = true)
         {
             if (do_a)
             {
+                KernelTimer kt(c, "k_ntt_fwd_pass_a", a.count);
                 const long long ctas_a = a.count * (256 / TB);
                 ntt_fwd_pass_a<LOGR><<<(unsigned)ctas_a, (1 << LOGR) / 16 * TB, 0, s>>>(a);
             }
             if (do_b)
             {
+                KernelTimer kt(c, "k_ntt_fwd_pass_b", a.count);
                 // polynomials sharing a prime: count / period of them per limb slot
                 const long long seq_len = a.count / a.period;
                 static const bool grouped_on = [] {
@@ -1231,11 +1234,11 @@ namespace moai
         }
         switch (c->log_n)
         {
-        case 12: launch_fwd<4>(a, c->stream, do_a, do_b); break;
-        case 13: launch_fwd<5>(a, c->stream, do_a, do_b); break;
-        case 14: launch_fwd<6>(a, c->stream, do_a, do_b); break;
-        case 15: launch_fwd<7>(a, c->stream, do_a, do_b); break;
-        case 16: launch_fwd<8>(a, c->stream, do_a, do_b); break;
+        case 12: launch_fwd<4>(c, a, c->stream, do_a, do_b); break;
+        case 13: launch_fwd<5>(c, a, c->stream, do_a, do_b); break;
+        case 14: launch_fwd<6>(c, a, c->stream, do_a, do_b); break;
+        case 15: launch_fwd<7>(c, a, c->stream, do_a, do_b); break;
+        case 16: launch_fwd<8>(c, a, c->stream, do_a, do_b); break;
         default: throw StatusError{ INVALID_ARGUMENT, "unsupported log_n" };
         }
         c->launches += (do_a ? 1 : 0) + (do_b ? 1 : 0);

@@ -46,8 +46,10 @@ def build_ref(force=False):
     """Compile the reference's SEAL-4.1-bs into oracle/_ref (only where /root/reference exists)."""
     if not os.path.isdir(REFERENCE_ROOT):
         return _REF_SO if os.path.exists(_REF_SO) else None
-    wrap = os.path.join(_HERE, "refbuild", "ref_wrap.cpp")
-    if force or not os.path.exists(_REF_SO) or os.path.getmtime(_REF_SO) < os.path.getmtime(wrap):
+    rb = os.path.join(_HERE, "refbuild")
+    deps = [os.path.join(rb, "ref_wrap.cpp"), os.path.join(rb, "Makefile"), os.path.join(rb, "ntl_shim", "NTL", "RR.h"),
+            os.path.join(rb, "ntl_shim", "NTL", "mat_RR.h")]
+    if force or not os.path.exists(_REF_SO) or os.path.getmtime(_REF_SO) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(_HERE, "refbuild")])
     return _REF_SO
 
@@ -417,6 +419,12 @@ class SealRef:
                                     C.c_double(darg), vv, _p(out), C.byref(osz), C.byref(olm), C.byref(osc)))
         return out[: osz.value * olm.value * self.n].copy(), osz.value, olm.value, osc.value
 
+    def set_threads(self, n=None):
+        """Use n (default: every host core) OpenMP threads whatever OMP_NUM_THREADS says; returns the count."""
+        n = n or os.cpu_count() or 1
+        self.lib.ref_set_omp_threads(C.c_int(n))
+        return self.omp_threads()
+
     def omp_threads(self):
         return int(self.lib.ref_omp_threads())
 
@@ -531,3 +539,89 @@ class SealRef:
                                             C.c_int(row_X), C.c_int(col_W), C.c_int(row_W), C.c_int(num_batch),
                                             _p(out), C.byref(oc), C.byref(ol), C.byref(osc)))
         return out[: oc.value * 2 * ol.value * self.n].copy(), oc.value, ol.value, osc.value
+
+    # ---- the reference's Bootstrapper (M/source/bootstrapping/Bootstrapper.cpp), compiled unmodified ----
+    def boot_create(self, logn=None, total_level=None, loge=10, final_scale=2.0 ** 46, boundary_K=25, deg=59,
+                    scale_factor=2, inverse_deg=1):
+        """Bootstrapper(...) + prepare_mod_polynomial() as M/test/test_full_scheme.hpp:413-433 does (the reference's own
+        Remez runs here: ~15 s).  Needs make_relin_key() first.  Returns the rotation steps the driver generates keys
+        for (test_full_scheme.hpp:436-443)."""
+        logn = self.log_n - 1 if logn is None else logn
+        total_level = self.kl - 2 if total_level is None else total_level
+        self._chk(self.lib.ref_boot_create(self.h, C.c_int(loge), C.c_int(logn), C.c_int(self.log_n - 1),
+                                           C.c_int(total_level), C.c_double(final_scale), C.c_int(boundary_K),
+                                           C.c_int(deg), C.c_int(scale_factor), C.c_int(inverse_deg)))
+        buf = (C.c_int * 4096)()
+        k = self.lib.ref_boot_steps(self.h, buf, C.c_int(4096))
+        return [int(buf[i]) for i in range(k)]
+
+    def boot_prepare(self):
+        """generate_LT_coefficient_3() (test_full_scheme.hpp:445-448); Galois keys must have been made."""
+        self._chk(self.lib.ref_boot_prepare(self.h))
+
+    def boot_polynomial(self):
+        """(Chebyshev coefficients of the EvalMod cosine in x / K with the inverse-sine constant folded in,
+        scale_inverse_coeff) as the reference generated them."""
+        buf = np.zeros(256, dtype=np.float64)
+        sic = C.c_double(0)
+        deg = self.lib.ref_boot_polynomial(self.h, _p(buf, f64p), C.c_int(256), C.byref(sic))
+        if deg < 0:
+            raise RuntimeError("no bootstrapper")
+        return buf[: deg + 1].copy(), sic.value
+
+    def bootstrap_3(self, ct, scale):
+        """Bootstrapper::bootstrap_3 on one ciphertext [2][1][n] -> (residues [2][limbs][n], limbs, scale)."""
+        ct = np.ascontiguousarray(ct, dtype=np.uint64).reshape(-1)
+        out = np.zeros(2 * (self.kl - 1) * self.n, dtype=np.uint64)
+        ol, osc = C.c_int(0), C.c_double(0)
+        self._chk(self.lib.ref_boot_bootstrap_3(self.h, _p(ct), C.c_double(scale), _p(out), C.byref(ol), C.byref(osc)))
+        return out[: 2 * ol.value * self.n].copy(), ol.value, osc.value
+
+    def boot_phase(self, phase, cts, limbs, scale):
+        """One phase of bootstrap_full_3 (0 modraise, 1 coefftoslot_full_3 -> 2 cts, 2 modular_reduction,
+        3 slottocoeff_full_3 <- 2 cts) -> (residues, limbs, scale)."""
+        cts = np.ascontiguousarray(cts, dtype=np.uint64).reshape(-1)
+        out = np.zeros(2 * 2 * (self.kl - 1) * self.n, dtype=np.uint64)
+        ol, osc = C.c_int(0), C.c_double(0)
+        self._chk(self.lib.ref_boot_phase(self.h, C.c_int(phase), _p(cts), C.c_int(limbs), C.c_double(scale), _p(out),
+                                          C.byref(ol), C.byref(osc)))
+        cnt = 2 if phase == 1 else 1
+        return out[: cnt * 2 * ol.value * self.n].copy(), ol.value, osc.value
+
+    def softmax_boot(self, x, num, limbs, scale, bias_vec, input_num, iters, layer_id):
+        """softmax_boot (M/source/non_linear_func/softmax.hpp:308-581) -> (residues, limbs, scale)."""
+        x = np.ascontiguousarray(x, dtype=np.uint64).reshape(-1)
+        out = np.zeros(num * 2 * limbs * self.n, dtype=np.uint64)
+        ol, osc = C.c_int(0), C.c_double(0)
+        bv = np.ascontiguousarray(bias_vec, dtype=np.int32)
+        self._chk(self.lib.ref_softmax_boot(self.h, _p(x), C.c_int(num), C.c_int(limbs), C.c_double(scale), _p(bv, i32p),
+                                            C.c_int(input_num), C.c_int(iters), C.c_int(layer_id), _p(out),
+                                            C.byref(ol), C.byref(osc)))
+        return out[: num * 2 * ol.value * self.n].copy(), ol.value, osc.value
+
+    def single_att_block(self, X, num_col, limbs, scale, WQ, WK, WV, bQ, bK, bV, bias_vec, input_num, num_batch, iters,
+                         layer_id):
+        """single_att_block (M/source/att_block/single_att_block.hpp:10-207) -> (residues, count, limbs, scale)."""
+        X = np.ascontiguousarray(X, dtype=np.uint64).reshape(-1)
+        col_W = WQ.shape[1]
+        ws = [np.ascontiguousarray(w, dtype=np.float64) for w in (WQ, WK, WV)]
+        bs = [np.ascontiguousarray(b, dtype=np.float64) for b in (bQ, bK, bV)]
+        bv = np.ascontiguousarray(bias_vec, dtype=np.int32)
+        out = np.zeros(col_W * 2 * limbs * self.n, dtype=np.uint64)
+        oc, ol, osc = C.c_int(0), C.c_int(0), C.c_double(0)
+        self._chk(self.lib.ref_single_att_block(self.h, _p(X), C.c_int(num_col), C.c_int(limbs), C.c_double(scale),
+                                                _p(ws[0], f64p), _p(ws[1], f64p), _p(ws[2], f64p), C.c_int(col_W),
+                                                _p(bs[0], f64p), _p(bs[1], f64p), _p(bs[2], f64p), _p(bv, i32p),
+                                                C.c_int(input_num), C.c_int(num_batch), C.c_int(iters), C.c_int(layer_id),
+                                                _p(out), C.byref(oc), C.byref(ol), C.byref(osc)))
+        return out[: oc.value * 2 * ol.value * self.n].copy(), oc.value, ol.value, osc.value
+
+    def exp_inverse(self, which, x, count, limbs, scale, iters=16):
+        """The reference header's exp (which=0, softmax.hpp:9-47) / inverse (which=1, :49-82) -> (residues, limbs, scale)."""
+        x = np.ascontiguousarray(x, dtype=np.uint64).reshape(-1)
+        out = np.zeros(count * 2 * limbs * self.n, dtype=np.uint64)
+        ol, osc = C.c_int(0), C.c_double(0)
+        self._chk(self.lib.ref_exp_inverse(self.h, C.c_int(which), _p(x), C.c_int(count), C.c_int(limbs), C.c_double(scale),
+                                           C.c_int(iters), _p(out), C.byref(ol), C.byref(osc)))
+        return out[: count * 2 * ol.value * self.n].copy(), ol.value, osc.value
+

@@ -20,6 +20,7 @@
 #include <chrono>
 #include <omp.h>
 #include <iostream>
+#include <sys/time.h> // gettimeofday: the reference headers rely on M/include.hpp:17 for it
 
 // The reference's own module code, unmodified (M/source/matrix_mul/Ct_pt_matrix_mul.hpp).
 #include "source/matrix_mul/Batch_encode_encrypt.hpp"
@@ -27,6 +28,11 @@
 #include "source/matrix_mul/Ct_ct_matrix_mul.hpp"
 #include "source/non_linear_func/layernorm.hpp"
 #include "source/non_linear_func/gelu_others.hpp"
+// The reference's bootstrapper and the modules that contain a bootstrapping, unmodified.  Their NTL dependency
+// (Polynomial.h:3, Remez.h:3, func.h:3-4) is met by oracle/refbuild/ntl_shim (NTL::RR over libmpfr.so.6).
+#include "source/bootstrapping/Bootstrapper.h"
+#include "source/non_linear_func/softmax.hpp"
+#include "source/att_block/single_att_block.hpp"
 #include <sstream>
 
 using namespace seal;
@@ -47,6 +53,7 @@ namespace
         RelinKeys rlk;
         GaloisKeys glk;
         bool have_rlk = false;
+        unique_ptr<Bootstrapper> boot; // the reference's Bootstrapper (M/source/bootstrapping/Bootstrapper.h:14-221)
         size_t n = 0;
         size_t n_data_limbs = 0; // limbs at the first (fresh-ciphertext) level
         string err;
@@ -624,8 +631,13 @@ extern "C"
     {
         std::streambuf *old;
         std::ostringstream sink;
-        CoutMute() : old(std::cout.rdbuf(sink.rdbuf()))
-        {}
+        CoutMute() : old(std::cout.rdbuf())
+        {
+            if (!getenv("REF_VERBOSE")) // REF_VERBOSE=1 lets the reference's debug decryptions through
+            {
+                std::cout.rdbuf(sink.rdbuf());
+            }
+        }
         ~CoutMute()
         {
             std::cout.rdbuf(old);
@@ -771,6 +783,15 @@ extern "C"
     int ref_omp_threads()
     {
         return omp_get_max_threads();
+    }
+
+    // torch.distributed.run exports OMP_NUM_THREADS=1 to its children; the CPU baseline must still use every host core
+    void ref_set_omp_threads(int n)
+    {
+        if (n > 0)
+        {
+            omp_set_num_threads(n);
+        }
     }
 
     // ---- randomness and key wire format (for the facade's client-side pieces) --------------------------------
@@ -928,6 +949,257 @@ extern "C"
         for (size_t i = 0; i < res.size(); i++)
         {
             store_ct(*r, res[i], out + i * 2 * r->n_data_limbs * r->n);
+        }
+        REF_CATCH(r)
+    }
+
+    // ---- the reference's Bootstrapper (M/source/bootstrapping/Bootstrapper.cpp), compiled unmodified ---------------
+    // Construction as in M/test/test_full_scheme.hpp:413-433: Bootstrapper(loge, logn, logNh, L, final_scale, K, deg,
+    // scale_factor, inverse_deg, ...) then prepare_mod_polynomial() — the reference's own multi-interval Remez
+    // (common/Remez.cpp:557-586) at 1000+ bits.  Needs the relinearization key (ref_make_relin_key) first.
+    int ref_boot_create(void *h, int loge, int logn, int logNh, int L, double final_scale, int boundary_K, int deg,
+                        int scale_factor, int inverse_deg)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        if (!r->have_rlk)
+        {
+            throw logic_error("ref_boot_create: make the relinearization key first");
+        }
+        CoutMute mute;
+        r->boot = make_unique<Bootstrapper>(loge, logn, logNh, L, final_scale, boundary_K, deg, scale_factor, inverse_deg,
+                                            *r->ctx, *r->keygen, *r->encoder, *r->encryptor, *r->decryptor, *r->evaluator,
+                                            r->rlk, r->glk);
+        r->boot->prepare_mod_polynomial();
+        REF_CATCH(r)
+    }
+
+    // Rotation steps the driver asks keys for (test_full_scheme.hpp:436-443): 0, 2^i for i < logN - 1, then
+    // addLeftRotKeys_Linear_to_vector_3.  Returns the count.
+    int ref_boot_steps(void *h, int *out, int cap)
+    {
+        auto r = static_cast<Ref *>(h);
+        if (!r->boot)
+        {
+            return -1;
+        }
+        vector<int> steps;
+        steps.push_back(0);
+        int log_n = 0;
+        while ((size_t(1) << log_n) < r->n)
+        {
+            log_n++;
+        }
+        for (int i = 0; i < log_n - 1; i++)
+        {
+            steps.push_back(1 << i);
+        }
+        r->boot->addLeftRotKeys_Linear_to_vector_3(steps);
+        for (size_t i = 0; i < steps.size() && int(i) < cap; i++)
+        {
+            out[i] = steps[i];
+        }
+        return int(steps.size());
+    }
+
+    // slot_vec.push_back(logn); generate_LT_coefficient_3()   (test_full_scheme.hpp:445-448)
+    int ref_boot_prepare(void *h)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        if (!r->boot)
+        {
+            throw logic_error("no bootstrapper");
+        }
+        CoutMute mute;
+        r->boot->slot_vec.push_back(r->boot->logn);
+        r->boot->generate_LT_coefficient_3();
+        REF_CATCH(r)
+    }
+
+    // The EvalMod polynomial the reference generated: Chebyshev coefficients (variable x / K) of the cosine after the
+    // inverse-sine constant has been folded in (ModularReducer.cpp:34-48), and that constant.
+    int ref_boot_polynomial(void *h, double *cheb, int cap, double *scale_inverse_coeff)
+    {
+        auto r = static_cast<Ref *>(h);
+        if (!r->boot)
+        {
+            return -1;
+        }
+        auto &p = r->boot->mod_reducer->sin_cos_polynomial;
+        for (long i = 0; i <= p.deg && i < cap; i++)
+        {
+            cheb[i] = to_double(p.chebcoeff[i]);
+        }
+        *scale_inverse_coeff = r->boot->mod_reducer->scale_inverse_coeff;
+        return int(p.deg);
+    }
+
+    // Bootstrapper::bootstrap_3 (Bootstrapper.cpp:3496-3502) on one ciphertext at the lowest level.
+    int ref_boot_bootstrap_3(void *h, const uint64_t *in, double scale, uint64_t *out, int *out_limbs, double *out_scale)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        if (!r->boot)
+        {
+            throw logic_error("no bootstrapper");
+        }
+        CoutMute mute;
+        Ciphertext ct, res;
+        load_ct(*r, in, 2, 1, scale, ct);
+        r->boot->bootstrap_3(res, ct);
+        *out_limbs = int(res.coeff_modulus_size());
+        *out_scale = res.scale();
+        store_ct(*r, res, out);
+        REF_CATCH(r)
+    }
+
+    // The phases of bootstrap_full_3 (Bootstrapper.cpp:3231-3251) one by one, for per-phase comparisons:
+    // phase 0: modraise_inplace + scale = q0      in: 1 ct @1 limb           out: 1 ct @ all data limbs
+    // phase 1: coefftoslot_full_3                  in: 1 ct                   out: 2 cts (real, imaginary halves)
+    // phase 2: modular_reduction                   in: 1 ct                   out: 1 ct
+    // phase 3: slottocoeff_full_3 + final scale    in: 2 cts                  out: 1 ct
+    int ref_boot_phase(void *h, int phase, const uint64_t *in, int limbs, double scale, uint64_t *out, int *out_limbs,
+                       double *out_scale)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        if (!r->boot)
+        {
+            throw logic_error("no bootstrapper");
+        }
+        CoutMute mute;
+        size_t ctsz = size_t(2) * limbs * r->n;
+        Ciphertext a, b, o1, o2;
+        load_ct(*r, in, 2, limbs, scale, a);
+        if (phase == 0)
+        {
+            r->boot->modraise_inplace(a);
+            const auto &modulus = r->ctx->first_context_data()->parms().coeff_modulus();
+            a.scale() = double(modulus[0].value());
+            o1 = a;
+        }
+        else if (phase == 1)
+        {
+            r->boot->coefftoslot_full_3(o1, o2, a);
+        }
+        else if (phase == 2)
+        {
+            r->boot->mod_reducer->modular_reduction(o1, a);
+        }
+        else if (phase == 3)
+        {
+            load_ct(*r, in + ctsz, 2, limbs, scale, b);
+            r->boot->slottocoeff_full_3(o1, a, b);
+            o1.scale() = r->boot->final_scale;
+        }
+        else
+        {
+            throw invalid_argument("phase");
+        }
+        *out_limbs = int(o1.coeff_modulus_size());
+        *out_scale = o1.scale();
+        store_ct(*r, o1, out);
+        if (phase == 1)
+        {
+            store_ct(*r, o2, out + size_t(2) * o1.coeff_modulus_size() * r->n);
+        }
+        REF_CATCH(r)
+    }
+
+    // softmax_boot (M/source/non_linear_func/softmax.hpp:308-581) on `num` ciphertexts [num][2][limbs][n]
+    int ref_softmax_boot(void *h, const uint64_t *x, int num, int limbs, double scale, const int *bias_vec, int input_num,
+                         int iter, int layer_id, uint64_t *out, int *out_limbs, double *out_scale)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        if (!r->boot)
+        {
+            throw logic_error("no bootstrapper");
+        }
+        CoutMute mute;
+        size_t ctsz = size_t(2) * limbs * r->n;
+        vector<Ciphertext> xs(num);
+        for (int i = 0; i < num; i++)
+        {
+            load_ct(*r, x + size_t(i) * ctsz, 2, limbs, scale, xs[i]);
+        }
+        vector<int> bv(bias_vec, bias_vec + r->n / 2);
+        vector<Ciphertext> res = softmax_boot(xs, bv, input_num, *r->ctx, r->rlk, iter, r->sk, *r->boot, layer_id);
+        for (size_t i = 0; i < res.size(); i++)
+        {
+            *out_limbs = int(res[i].coeff_modulus_size());
+            *out_scale = res[i].scale();
+            memcpy(out + i * 2 * res[i].coeff_modulus_size() * r->n, res[i].data(),
+                   2 * res[i].coeff_modulus_size() * r->n * sizeof(uint64_t));
+        }
+        REF_CATCH(r)
+    }
+
+    // single_att_block (M/source/att_block/single_att_block.hpp:10-207): one attention head.
+    // X [num_col][2][limbs][n]; WQ/WK/WV row-major [num_col][col_W]; bQ/bK/bV [col_W].
+    int ref_single_att_block(void *h, const uint64_t *X, int num_col, int limbs, double scale, const double *WQ,
+                             const double *WK, const double *WV, int col_W, const double *bQ, const double *bK,
+                             const double *bV, const int *bias_vec, int input_num, int num_batch, int iter, int layer_id,
+                             uint64_t *out, int *out_count, int *out_limbs, double *out_scale)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        if (!r->boot)
+        {
+            throw logic_error("no bootstrapper");
+        }
+        CoutMute mute;
+        size_t ctsz = size_t(2) * limbs * r->n;
+        vector<Ciphertext> xs(num_col);
+        for (int i = 0; i < num_col; i++)
+        {
+            load_ct(*r, X + size_t(i) * ctsz, 2, limbs, scale, xs[i]);
+        }
+        auto mat = [&](const double *W) {
+            vector<vector<double>> m(num_col, vector<double>(col_W));
+            for (int i = 0; i < num_col; i++)
+            {
+                for (int j = 0; j < col_W; j++)
+                {
+                    m[i][j] = W[size_t(i) * col_W + j];
+                }
+            }
+            return m;
+        };
+        vector<double> vq(bQ, bQ + col_W), vk(bK, bK + col_W), vv(bV, bV + col_W);
+        vector<int> bv(bias_vec, bias_vec + r->n / 2);
+        vector<Ciphertext> res = single_att_block(xs, mat(WQ), mat(WK), mat(WV), vq, vk, vv, bv, input_num, *r->ctx, r->rlk,
+                                                  r->glk, *r->boot, num_batch, r->sk, iter, layer_id);
+        *out_count = int(res.size());
+        for (size_t i = 0; i < res.size(); i++)
+        {
+            *out_limbs = int(res[i].coeff_modulus_size());
+            *out_scale = res[i].scale();
+            memcpy(out + i * 2 * res[i].coeff_modulus_size() * r->n, res[i].data(),
+                   2 * res[i].coeff_modulus_size() * r->n * sizeof(uint64_t));
+        }
+        REF_CATCH(r)
+    }
+
+    // exp (which = 0, softmax.hpp:9-47) / inverse (which = 1, softmax.hpp:49-82) of the reference header on `count`
+    // ciphertexts [count][2][limbs][n]
+    int ref_exp_inverse(void *h, int which, const uint64_t *x, int count, int limbs, double scale, int iter, uint64_t *out,
+                        int *out_limbs, double *out_scale)
+    {
+        auto r = static_cast<Ref *>(h);
+        REF_TRY(r)
+        CoutMute mute;
+        size_t ctsz = size_t(2) * limbs * r->n;
+        for (int i = 0; i < count; i++)
+        {
+            Ciphertext ct;
+            load_ct(*r, x + size_t(i) * ctsz, 2, limbs, scale, ct);
+            Ciphertext res = which == 0 ? exp(ct, *r->ctx, r->rlk) : inverse(ct, *r->ctx, r->rlk, iter);
+            *out_limbs = int(res.coeff_modulus_size());
+            *out_scale = res.scale();
+            memcpy(out + size_t(i) * 2 * res.coeff_modulus_size() * r->n, res.data(),
+                   2 * res.coeff_modulus_size() * r->n * sizeof(uint64_t));
         }
         REF_CATCH(r)
     }

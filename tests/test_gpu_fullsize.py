@@ -1,0 +1,284 @@
+"""Full-size correctness gate: the repo's own parameters (N = 65536, 35 + 1 primes, Hamming-weight-192 secret, K = 25:
+M/test/test_full_scheme.hpp:345-368, 413-448) with VALID keys, decrypted results.
+
+* Bootstrapping in the mode every headline timing uses (fast: hoisted rotations,
+  pre-permuted keys; plain and two-real-ciphertexts-per-bootstrapping), with the decrypted error reported PER PHASE
+  (ModRaise / CoeffToSlot / EvalMod / SlotToCoeff).
+* Golden gate (north_star: "decrypted layer outputs must match the reference's"): the non-linear stages of encoder
+  layer 0 on the reference's own activations (tests/golden/layer0_activations.npz, made from
+  /root/reference/data/layer_0/**/allresults/*.csv by tests/golden/make_layer0_golden.py): softmax_boot vs aftsoftmax.csv,
+  layernorm vs real_self_output.csv, gelu_v2 vs real_intermediate_output.csv, layernorm2 vs real_final_output.csv, and
+  config C1 on data/selfoutput_linear.txt with the reference run's {5, 0, ...} token mask.  The reference's modules are
+  polynomial approximations; its OWN error against these CSVs (oracle/_ref at N = 4096, measured in this repo:
+  layernorm 4.4e-4, layernorm2 0.13 max-abs / 5.7 % rel, gelu_v2 0.029) bounds what can be asked of a faithful
+  implementation, and each tolerance below is stated next to that figure.
+
+Keys are generated on the device (tests/devkeygen.py): genuine RLWE keys in SEAL's layout with torch's randomness.
+~65 GiB of HBM; the whole module takes a few minutes on one B200."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+LOG_N = 16
+N = 1 << LOG_N
+SLOTS = N // 2
+NUM_BATCH = 256
+TOK = 5
+SCALE = 2.0 ** 46
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "layer0_activations.npz")
+
+
+@pytest.fixture(scope="module")
+def env(pkg):
+    import torch
+    from devkeygen import DeviceKeyGen
+    from oracle import Oracle, MOAI_BITS
+    o = Oracle(LOG_N, MOAI_BITS)
+    be = pkg.Backend(LOG_N, o.q)
+    kg = DeviceKeyGen(pkg, be, hamming_weight=192, seed=20250991)
+    boot = pkg.Bootstrapper(be, total_limbs=35)
+    boot.set_hoisting(True)
+    fast = {}
+    for st in boot.required_steps() + [0]:
+        e = be.galois_elt_from_step(st)
+        k = kg.galois_key(e)
+        fast.setdefault(e, []).append(be.key_prepare(k, e))
+        del k
+    keys = be.make_keys(relin=kg.relin_key(), galois_fast=fast)
+    torch.cuda.synchronize()
+    mask = np.zeros(SLOTS, dtype=np.int32)
+    for k in range(TOK):
+        mask[k * NUM_BATCH] = 1                           # bias_vec(input_len = {5, 0, ...}), Batch_encode_encrypt.hpp:39-49
+    yield {"o": o, "be": be, "kg": kg, "boot": boot, "keys": keys, "mask": mask, "g": np.load(GOLDEN)}
+    del keys, fast
+    be.close()
+
+
+def pack_rows(A):
+    """A [TOK, cols] activations of input 0 -> [cols, SLOTS]: slot 256 k holds token k (batch_input layout,
+    Batch_encode_encrypt.hpp:21-27); the other 255 inputs are empty, as in the reference run."""
+    v = np.zeros((A.shape[1], SLOTS))
+    for k in range(TOK):
+        v[:, k * NUM_BATCH] = A[k]
+    return v
+
+
+def encrypt_cols(e, V, limbs, chunk=256):
+    import torch
+    outs = []
+    for c0 in range(0, V.shape[0], chunk):
+        pt = e["be"].encode(V[c0:c0 + chunk], SCALE, limbs)
+        outs.append(e["kg"].encrypt(pt))
+    return torch.cat(outs)
+
+
+def slot_values(e, ct, scale, slots):
+    """Decrypt on the device and evaluate the plaintext polynomial at the requested slots only:
+    slot j <-> m(zeta^(5^j)), zeta = exp(i pi / N) (S/ckks.cpp:36-52)."""
+    import torch
+    be, kg = e["be"], e["kg"]
+    B = ct.shape[0]
+    m = kg.decrypt(ct[:, :, :1].contiguous()).view(B, N).contiguous()
+    be.ntt_inverse_limb_(m, 0)
+    q0 = int(be.primes[0])
+    c = torch.where(m > q0 // 2, m - q0, m).to(torch.float64)
+    idx = torch.arange(N, device=c.device, dtype=torch.int64)
+    pos = torch.tensor([pow(5, int(j), 2 * N) for j in slots], device=c.device, dtype=torch.int64)
+    ang = ((idx[:, None] * pos[None, :]) % (2 * N)).to(torch.float64) * (np.pi / N)
+    re = c @ torch.cos(ang)
+    im = c @ torch.sin(ang)
+    return ((re + 1j * im) / scale).cpu().numpy()
+
+
+VALID = [k * NUM_BATCH for k in range(TOK)]
+
+
+def test_slot_evaluation_matches_decode(pkg, env):
+    """Self-check of the shortcut above against the oracle's full decode."""
+    rng = np.random.default_rng(0)
+    z = rng.normal(size=(2, SLOTS)) * 0.3
+    ct = encrypt_cols(env, z, 2)
+    full = env["kg"].decrypt_decode(ct, SCALE, env["o"])
+    some = slot_values(env, ct, SCALE, [0, 1, 256, 1024, SLOTS - 1])
+    assert np.abs(full[:, [0, 1, 256, 1024, SLOTS - 1]] - some).max() < 1e-9
+    assert np.abs(full.real - z).max() < 1e-8             # fresh-encryption noise at scale 2^46
+
+
+def _bitrev_perm(n):
+    bits = n.bit_length() - 1
+    idx = np.arange(n)
+    out = np.zeros(n, dtype=np.int64)
+    for b in range(bits):
+        out |= ((idx >> b) & 1) << (bits - 1 - b)
+    return out
+
+
+def test_bootstrap_fullsize_per_phase(pkg, env):
+    """Plain full-slot bootstrapping of complex messages (C3's inputs: N(0, 0.3^2) per slot) at N = 65536 / HW-192,
+    error after every phase.  Tolerances: |I| < K = 25; CoeffToSlot 1e-6 on t / (K q0); EvalMod 1e-6 on
+    sin(2 pi t / q0); final message 1e-4 max-abs (the reference's bootstrap_3 measured 3e-6 ... 9e-6 at N = 8192)."""
+    import torch
+    o, be, kg, boot, keys = env["o"], env["be"], env["kg"], env["boot"], env["keys"]
+    rng = np.random.default_rng(3)
+    B = 2
+    z = (rng.normal(size=(B, SLOTS)) + 1j * rng.normal(size=(B, SLOTS))) * 0.3
+    ct = kg.encrypt(be.encode(z, SCALE, 1))
+    q0, q1 = int(be.primes[0]), int(be.primes[1])
+    K = 25
+
+    # phase 1: ModRaise.  t = m + q0 I over the integers; recover (m0, I) from the residues mod q0 and q1
+    r1, s1 = boot.bootstrap_phase_debug(keys, ct, SCALE, 1)
+    assert r1.shape == (B, 2, 35, N) and s1 == float(q0)
+    m2 = kg.decrypt(r1[:, :, :2].contiguous())
+    be.ntt_inverse_(m2.view(B, 1, 2, N))
+    m2 = m2.cpu().numpy()
+    m0 = np.where(m2[:, 0] > q0 // 2, m2[:, 0] - q0, m2[:, 0])
+    I = np.full(m0.shape, 1000, dtype=np.int64)
+    for cand in range(-40, 41):
+        hit = (m0 + cand * q0) % q1 == m2[:, 1]
+        I[hit] = cand
+    assert (I != 1000).all(), "ModRaise output is not m + q0 I with |I| <= 40"
+    print("ModRaise: max |I| = %d (K = %d), |m0| / q0 max = %.3g" % (np.abs(I).max(), K, np.abs(m0).max() / q0))
+    assert np.abs(I).max() < K
+    # the input's own plaintext (decrypt at one limb) must be m0 exactly: ModRaise changes no coefficient mod q0
+    m_in = kg.decrypt(ct).view(B, N).contiguous()
+    be.ntt_inverse_limb_(m_in, 0)
+    m_in = m_in.cpu().numpy()
+    assert (np.where(m_in > q0 // 2, m_in - q0, m_in) == m0).all()
+    t_over_q0 = I + m0 / q0                                # [B, N]
+
+    # phase 2: CoeffToSlot: slots of the real / imaginary halves = t[bitrev(j)] / (K q0), t[bitrev(j) + N/2] / (K q0)
+    P = _bitrev_perm(SLOTS)
+    r2, s2 = boot.bootstrap_phase_debug(keys, ct, SCALE, 2)
+    assert r2.shape[0] == 2 * B
+    d2 = kg.decrypt_decode(r2, s2, o)
+    e_cts = max(np.abs(d2[b] - t_over_q0[b][P] / K).max() for b in range(B))
+    e_cts = max(e_cts, max(np.abs(d2[B + b] - t_over_q0[b][P + SLOTS] / K).max() for b in range(B)))
+    print("CoeffToSlot: max |slot - t/(K q0)| = %.3g at %d limbs" % (e_cts, r2.shape[2]))
+    assert e_cts < 1e-6
+
+    # phase 3: EvalMod: slots ~ sin(2 pi t / q0)
+    r3, s3 = boot.bootstrap_phase_debug(keys, ct, SCALE, 3)
+    d3 = kg.decrypt_decode(r3, s3, o)
+    e_mod = max(np.abs(d3[b] - np.sin(2 * np.pi * (m0[b] / q0))[P]).max() for b in range(B))
+    e_mod = max(e_mod, max(np.abs(d3[B + b] - np.sin(2 * np.pi * (m0[b] / q0))[P + SLOTS]).max() for b in range(B)))
+    print("EvalMod: max |slot - sin(2 pi t / q0)| = %.3g at %d limbs" % (e_mod, r3.shape[2]))
+    assert e_mod < 1e-6
+
+    # phase 4: the whole bootstrapping
+    out, osc = boot.bootstrap_3(keys, ct, SCALE)
+    assert out.shape == (B, 2, 21, N) and osc == SCALE
+    d = kg.decrypt_decode(out, osc, o)
+    e_fin = np.abs(d - z).max()
+    print("bootstrap_3 (N = 65536, HW-192): max |out - msg| = %.3g" % e_fin)
+    assert e_fin < 1e-4
+
+
+def test_bootstrap_real_pairs_fullsize(pkg, env):
+    """moai_bootstrap_real — the call the encoder layer makes 4 x per layer — on real messages shaped like the layer's
+    activations: N(0, 0.3^2) full-slot rows and the LayerNorm-1 golden outputs of the 5-token sentence (|x| up to 63
+    in 5 of 32768 slots).  Odd batch: one ciphertext travels alone.  Tolerance 1e-4 max-abs on O(1) values."""
+    o, be, kg, boot, keys, g = env["o"], env["be"], env["kg"], env["boot"], env["keys"], env["g"]
+    rng = np.random.default_rng(4)
+    dense = rng.normal(size=(3, SLOTS)) * 0.3
+    sparse = pack_rows(g["ln1_out"][:, :4])
+    msgs = np.concatenate([dense, sparse])                 # 7 ciphertexts
+    ct = kg.encrypt(be.encode(msgs, SCALE, 1))
+    out, osc = boot.bootstrap_real(keys, ct, SCALE, chunk_pairs=2)
+    assert out.shape == (7, 2, 21, N) and osc == SCALE
+    d = kg.decrypt_decode(out, osc, o)
+    err = np.abs(d - msgs).max(axis=1)
+    print("bootstrap_real (N = 65536, HW-192): max |out - msg| per ciphertext =", ["%.2g" % v for v in err])
+    assert err.max() < 1e-4
+
+
+@pytest.mark.parametrize("name,variant,tol_abs,tol_rel", [("ln1", 1, 2e-3, 1e-3), ("ln2", 2, 0.25, 0.1)])
+def test_layernorm_golden(pkg, env, name, variant, tol_abs, tol_rel):
+    """layernorm / layernorm2 (layernorm.hpp:157-547) on layer 0's residual sums vs real_self_output.csv /
+    real_final_output.csv.  The reference's own code is 4.4e-4 (ln1) and 0.13 max-abs / 5.7 % rel (ln2: its inverse
+    square root is a low-degree iteration) away from these CSVs; tolerances: ln1 2e-3 abs / 1e-3 rel, ln2 0.25 abs /
+    0.1 rel (rel = |err| / max(1, |expected|))."""
+    be, keys, g = env["be"], env["keys"], env["g"]
+    x = encrypt_cols(env, pack_rows(g[name + "_in"]), 21)
+    out, osc = be.layernorm(keys, x, SCALE, g[name + "_gamma"], g[name + "_beta"], env["mask"], variant=variant)
+    del x
+    assert out.shape[0] == 768 and out.shape[2] == 1
+    got = slot_values(env, out, osc, VALID).real.T        # [TOK, 768]
+    exp = g[name + "_out"]
+    err = np.abs(got - exp)
+    rel = (err / np.maximum(1.0, np.abs(exp))).max()
+    print("%s golden: max-abs %.3g, rel %.3g" % (name, err.max(), rel))
+    assert err.max() < tol_abs and rel < tol_rel
+
+
+def test_gelu_golden(pkg, env):
+    """gelu_v2 (gelu_others.hpp:4-154) on all 3072 intermediate features of layer 0 vs real_intermediate_output.csv.
+    The reference's degree-24 polynomial is itself up to 0.03 away (inputs reach -15.4); tolerance 0.06 max-abs."""
+    be, keys, g = env["be"], env["keys"], env["g"]
+    V = pack_rows(g["gelu_in"])
+    errs = []
+    for c0 in range(0, 3072, 768):
+        x = encrypt_cols(env, V[c0:c0 + 768], 9)
+        out, osc = be.gelu_v2(keys, x, SCALE)
+        del x
+        assert out.shape[2] == 2
+        got = slot_values(env, out, osc, VALID).real.T
+        errs.append(np.abs(got - g["gelu_out"][:, c0:c0 + 768]).max())
+        del out
+    print("gelu_v2 golden: max-abs %.3g" % max(errs))
+    assert max(errs) < 0.06
+
+
+def test_softmax_golden(pkg, env):
+    """softmax_boot (softmax.hpp:308-581, one bootstrapping inside) on layer 0's scores, all 12 heads, vs
+    aftsoftmax.csv (true softmax).  The module computes exp as (1 + x / 128)^128 after subtracting the layer's
+    constant 7.5 (:324) and normalises with a 16-step Goldschmidt inverse; the float64 model of exactly that is
+    evaluated beside it.  Tolerances: 5e-3 max-abs against the model, 2e-2 against the CSV."""
+    be, kg, boot, keys, g = env["be"], env["kg"], env["boot"], env["keys"], env["g"]
+    worst_csv, worst_model = 0.0, 0.0
+    for h in range(12):
+        S = g["QKT"][:, 5 * h:5 * h + 5]
+        want = g["aftsoftmax"][:, 5 * h:5 * h + 5]
+        E = (1 + (S - 7.5) / 128.0) ** 128
+        model = E / (E.sum(axis=1, keepdims=True) + 1e-5)
+        V = np.zeros((128, SLOTS))
+        for i in range(128):
+            for k in range(TOK):
+                if (k + i) % 128 < TOK:
+                    V[i, k * NUM_BATCH] = S[k, (k + i) % 128]     # i-th generalized diagonal, Ct_ct_matrix_mul.hpp:24-41
+        x = encrypt_cols(env, V, 13)
+        out, osc = boot.softmax_boot(keys, x, SCALE, env["mask"], TOK, iters=16, layer_id=0)
+        del x
+        assert out.shape == (128, 2, 3, N)
+        got = slot_values(env, out, osc, VALID).real      # [128 diagonals, TOK]
+        P = np.zeros((TOK, TOK))
+        for i in range(128):
+            for k in range(TOK):
+                if (k + i) % 128 < TOK:
+                    P[k, (k + i) % 128] = got[i, k]
+        worst_csv = max(worst_csv, np.abs(P - want).max())
+        worst_model = max(worst_model, np.abs(P - model).max())
+    print("softmax_boot golden (12 heads): max-abs vs float64 model %.3g, vs aftsoftmax.csv %.3g" % (worst_model, worst_csv))
+    assert worst_model < 5e-3 and worst_csv < 2e-2
+
+
+def test_c1_selfoutput_linear_with_reference_mask(pkg, env):
+    """Config C1 as the reference runs it: data/selfoutput_linear.txt (5 tokens x 768) in input 0, mask {5, 0, ...},
+    ct_pt_matrix_mul_wo_pre_w_mask 768 x 768 at chain_index 1 -> 0 (test_full_scheme.hpp:601-617).  Decrypted result
+    vs float64 X W: max-abs <= 1e-4 relative to max |X W| (the reference achieved 1.2e-5)."""
+    be, g = env["be"], env["g"]
+    X = g["selfoutput_linear"]
+    rng = np.random.default_rng(20250991)
+    W = rng.normal(size=(768, 768)) * 0.04
+    x = encrypt_cols(env, pack_rows(X), 2)
+    out = be.ct_pt_matrix_mul_wo_pre_w_mask(x, W, env["mask"], SCALE)
+    assert out.shape == (768, 2, 1, N)
+    got = slot_values(env, out, SCALE, VALID + [1, 257]).real.T
+    exp = X @ W
+    err = np.abs(got[:TOK] - exp).max()
+    print("C1 masked matmul: max-abs %.3g (max |XW| %.3g), masked-out slots %.3g" % (err, np.abs(exp).max(), np.abs(got[TOK:]).max()))
+    assert err < 1e-4 * max(1.0, np.abs(exp).max())
+    assert np.abs(got[TOK:]).max() < 1e-6                 # other inputs' slots stay zero

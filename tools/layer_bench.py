@@ -31,7 +31,7 @@ class Args:
         self.layers, self.mode = layers, mode
 
 
-def setup(args, device=0):
+def setup(args, device=0, seed=11):
     """Backend, bootstrapper, synthetic keys / weights / input for one packed batch on `device`."""
     import torch
     pkg = importlib.import_module("moai-fhe-transformerinference-public_b200")
@@ -40,15 +40,15 @@ def setup(args, device=0):
     be = pkg.Backend(16, primes, device=device)
     n, kl = 1 << 16, len(primes)
     boot = pkg.Bootstrapper(be, total_limbs=35)
-    g = torch.Generator(device="cuda")
-    g.manual_seed(11)
+    g = torch.Generator(device=torch.device("cuda", device))
+    g.manual_seed(seed)
 
     def rand_key(levels=kl - 1):
         """uniform residues in a key's layout: SEAL's [kl-1, 2, kl, n], or truncated [L, 2, L + 1, n]"""
         ids = list(range(levels)) + [kl - 1]
-        k = torch.empty((levels, 2, levels + 1, n), dtype=torch.int64, device="cuda")
+        k = torch.empty((levels, 2, levels + 1, n), dtype=torch.int64, device=torch.device("cuda", device))
         for pos, l in enumerate(ids):
-            k[:, :, pos, :] = torch.randint(0, primes[l], (levels, 2, n), generator=g, device="cuda", dtype=torch.int64)
+            k[:, :, pos, :] = torch.randint(0, primes[l], (levels, 2, n), generator=g, device=torch.device("cuda", device), dtype=torch.int64)
         return k
 
     if args.mode == "exact":
@@ -88,9 +88,9 @@ def setup(args, device=0):
          "inter_weight": rng.normal(size=(hidden, inter)) * 0.04, "inter_bias": rng.normal(size=inter) * 0.04,
          "final_weight": rng.normal(size=(inter, hidden)) * 0.04, "final_bias": rng.normal(size=hidden) * 0.04,
          "ln2_gamma": np.ones(hidden), "ln2_beta": np.zeros(hidden)}
-    x = torch.empty((hidden, 2, 21, n), dtype=torch.int64, device="cuda")
+    x = torch.empty((hidden, 2, 21, n), dtype=torch.int64, device=torch.device("cuda", device))
     for l in range(21):
-        x[:, :, l, :] = torch.randint(0, primes[l], (hidden, 2, n), generator=g, device="cuda", dtype=torch.int64)
+        x[:, :, l, :] = torch.randint(0, primes[l], (hidden, 2, n), generator=g, device=torch.device("cuda", device), dtype=torch.int64)
     mask = np.ones(n // 2, dtype=np.int32)     # all 128 tokens of all 256 inputs valid
     return {"be": be, "boot": boot, "keys": keys, "w": w, "x": x, "mask": mask, "key_gib": key_gib, "n_keys": n_keys,
             "hidden": hidden, "n": n}
