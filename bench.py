@@ -424,8 +424,12 @@ def run_layer(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     device = torch.device("cuda", local_rank)
-    st = layer_bench.setup(layer_bench.Args(1, "fast"), device=local_rank, seed=11 + rank)
+    part_a = args.partition == "A" and world > 1
+    # replicas: every rank has its own packed batch (own seed); partitioning A: ONE packed batch, identical on every rank
+    st = layer_bench.setup(layer_bench.Args(1, "fast"), device=local_rank, seed=11 + (0 if part_a else rank))
     be, boot, keys, w, x, mask = st["be"], st["boot"], st["keys"], st["w"], st["x"], st["mask"]
+    if part_a:
+        be.comm_init(dist)
     cw, keep = boot.layer_weights(w)
     aux = torch.empty_like(x)
     aux.copy_(x)
@@ -494,8 +498,10 @@ def run_layer(args):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     layer_ms, layer_e2e_ms, total_ms = float(t[0]), float(t[1]), float(t[2])
-    value = layer_ms / 1000.0 * 12 / (INPUTS_PER_BATCH * world)
-    e2e_value = layer_e2e_ms / 1000.0 * 12 / (INPUTS_PER_BATCH * world)
+    batches = 1 if part_a else world
+    value = layer_ms / 1000.0 * 12 / (INPUTS_PER_BATCH * batches)
+    e2e_value = layer_e2e_ms / 1000.0 * 12 / (INPUTS_PER_BATCH * batches)
+    gathers, rx_bytes = be.comm_stats() if part_a else (0, 0)
     if rank == 0:
         peaks = {}
         try:
@@ -524,13 +530,18 @@ def run_layer(args):
                 traffic = None
         cb = cpu_baseline_layers() if not args.no_cpu_baseline else None
         line = {"metric": LAYER_METRIC, "value": value, "unit": "s/input", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": False, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": False,
+                "scaling": "strong" if part_a else "weak",
                 "vs_baseline": value / PUBLISHED_12_LAYERS, "dtype": "u64/f64", "data": "synthetic",
-                "config": {"workload": LAYER_WORKLOAD, "steps_per_layer": 4, "inputs_per_step": INPUTS_PER_BATCH * world,
+                "config": {"workload": LAYER_WORKLOAD, "steps_per_layer": 4, "inputs_per_step": INPUTS_PER_BATCH * batches,
                            "seconds_per_layer": layer_ms / 1000.0,
                            "quarter_ms": {STAGE_NAMES[q]: v for q, v in by_stage.items()},
                            "l2": "working set (GiBs per stage) far larger than the 126 MB L2; no flush needed",
-                           "parallelism": "replicas x%d (one packed batch per GPU, no data-path collective)" % world,
+                           "parallelism": ("partitioning A: ONE packed batch over %d GPUs — heads / intermediate columns / bootstrapping "
+                                           "pairs sharded, NCCL all-gather of uint64 limbs after each sharded loop (%d gathers, "
+                                           "%.1f GiB received per rank in the timed region); value = one-batch latency x 12 / 256"
+                                           % (world, gathers, rx_bytes / 2 ** 30)) if part_a else
+                                          "replicas x%d (one packed batch per GPU, no data-path collective)" % world,
                            "boot_chunk": boot_chunk, "evaluation_keys_GiB": round(st["key_gib"], 1)},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "s/input", "h2d_bytes_per_step": int(h2d),
@@ -548,7 +559,9 @@ def run_layer(args):
                              "note": "timed live with CUDA events around every launch on the launching stream; `achieved` = "
                                      "algorithmic bytes (1 MiB per limb-transform, SURVEY 8(d)) / time; `traffic` = DRAM bytes per "
                                      "limb-transform from the ncu capture under profiles/"},
-                "phases_ms": {k: round(v[0], 1) for k, v in prof.items() if not k.startswith("alloc") and not k.startswith("k_")}}
+                "phases_ms": {k: round(v[0], 1) for k, v in prof.items() if not k.startswith("alloc") and not k.startswith("k_")},
+                # live per-kernel device time over the timed steps (CUDA events around every launch): [ms, units]
+                "kernels_ms": {k: [round(v[0], 1), int(v[1])] for k, v in prof.items() if k.startswith("k_")}}
         if cb is not None:
             line["cpu_baseline"] = cb
         print(json.dumps(line))
@@ -587,6 +600,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="moai_b200", choices=["moai_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--partition", default="replicas", choices=["replicas", "A"],
+                    help="with N > 1 GPUs: replicas (default; one packed batch per GPU, throughput scaling, BASELINE's "
+                         "'shard the 256-input batches') or A (ONE packed batch over the N GPUs, latency scaling, NCCL all-gathers)")
     ap.add_argument("--workload", default="layer", choices=["layer", "c1"],
                     help="layer (default): the encoder layer in bootstrap-delimited quarters = BASELINE.json's metric; "
                          "c1: the self-output ct-pt matmul (configs[0])")

@@ -197,6 +197,20 @@ int32_t moai_encoder_layer_stage(moai_context *ctx, moai_keys *keys, moai_bootst
                                  const int32_t *bias_vec, int32_t input_num, int32_t num_batch, int32_t layer_id,
                                  int64_t boot_chunk);
 /* "name:ms:count;" for every profiled phase (see moai_profile_enable) */
+/* ---- one packed batch over several GPUs of one node ("partitioning A": the independent units of the layer are column
+ * ciphertexts — the 768 bootstrappings of a stage, test_full_scheme.hpp:654-660; the 12 heads, :530-533; the 3072
+ * intermediate columns with their GELUs, :807-888).  One process per GPU; each process creates its context on its device
+ * and joins the communicator: rank 0 obtains an id (moai_comm_unique_id) and ships the 128 bytes to the others by any
+ * means (bench.py: torch.distributed), then every rank calls moai_comm_init.  From then on moai_encoder_layer[_stage] on
+ * that context computes this rank's share of every sharded loop and exchanges the shares with an NCCL all-gather of raw
+ * uint64 limbs over NVLink (sums are modular: no reduction collective); LayerNorm and the two K = 768 / 3072 -> 768 matmuls
+ * are replicated (1 % of the layer).  Every rank ends each stage with the complete activations, bit-identical to a
+ * single-GPU run.  NCCL is resolved at run time (dlopen of libnccl.so.2): the library loads without it. */
+int32_t moai_comm_unique_id(uint8_t *out128);
+int32_t moai_comm_init(moai_context *ctx, const uint8_t *id128, int32_t rank, int32_t world);
+int32_t moai_comm_destroy(moai_context *ctx);
+int32_t moai_comm_stats(moai_context *ctx, uint64_t *gathers, uint64_t *received_bytes);
+
 int32_t moai_profile_dump(moai_context *ctx, char *buf, int32_t capacity);
 
 #ifdef __cplusplus

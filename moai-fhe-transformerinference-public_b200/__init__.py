@@ -107,6 +107,25 @@ class Backend:
         s = self.torch.cuda.current_stream(self.device).cuda_stream
         self._chk(self.lib.moai_set_stream(self.h, C.c_void_p(s)))
 
+    # ---- one packed batch over several GPUs (moai_comm_*): call after torch.distributed.init_process_group
+    def comm_init(self, dist):
+        """Join this context to an NCCL communicator spanning the ranks of torch.distributed process group `dist`
+        (rank 0 creates the id, torch.distributed ships the 128 bytes)."""
+        rank, world = dist.get_rank(), dist.get_world_size()
+        idb = (C.c_uint8 * 128)()
+        if rank == 0:
+            self._chk(self.lib.moai_comm_unique_id(idb))
+        t = self.torch.tensor(list(idb), dtype=self.torch.uint8, device=self.device)
+        dist.broadcast(t, src=0)
+        idb = (C.c_uint8 * 128)(*[int(v) for v in t.cpu().tolist()])
+        self._chk(self.lib.moai_comm_init(self.h, idb, C.c_int32(rank), C.c_int32(world)))
+        self.comm_rank, self.comm_world = rank, world
+
+    def comm_stats(self):
+        g, b = C.c_uint64(), C.c_uint64()
+        self._chk(self.lib.moai_comm_stats(self.h, C.byref(g), C.byref(b)))
+        return g.value, b.value
+
     def profile(self, on):
         self._chk(self.lib.moai_profile_enable(self.h, C.c_int32(int(on))))
 

@@ -743,7 +743,7 @@ namespace moai
         return w;
     }
     Ct Bootstrapper::bootstrap_real_pairs(const Evaluator &ev, const Ct &in, const Keys &keys, long long chunk_pairs,
-                                          const Ct *into)
+                                          const Ct *into, long long pair_first, long long pair_last)
     {
         MOAI_REQUIRE(in.size == 2 && in.limbs == 1, "bootstrap expects size-2 ciphertexts at the last level");
         MOAI_REQUIRE(chunk_pairs >= 1, "chunk must be positive");
@@ -756,9 +756,14 @@ namespace moai
         std::vector<cd> minus_i(n, cd(0, -1)), plus_i(n, cd(0, 1));
         const Pt pi_in = ev.encode(plus_i, 1, 1.0);           // X^(N/2): exact, no level
         const Pt mi_out = ev.encode(minus_i, out_limbs, 1.0);
-        for (long long p0 = 0; p0 < P; p0 += chunk_pairs)
+        if (pair_last < 0)
         {
-            const long long np = std::min(chunk_pairs, P - p0);
+            pair_last = P;
+        }
+        MOAI_REQUIRE(pair_first >= 0 && pair_first <= pair_last && pair_last <= P, "bad pair range");
+        for (long long p0 = pair_first; p0 < pair_last; p0 += chunk_pairs)
+        {
+            const long long np = std::min(chunk_pairs, pair_last - p0);
             const long long nb = std::max(0LL, std::min(np, B - P - p0)); // partners j + P < B
             Ct z = ev.clone(ev.view(in, p0, np));
             if (nb > 0)

@@ -86,8 +86,10 @@ namespace moai
         // (M/test/test_full_scheme.hpp:654-660, 758-764, 991-995, 1081-1085) become 4 x 384.
         // in: [B][2][1][N]; pairs (j, j + ceil(B/2)); an unpaired ciphertext travels alone.  `into`: optional
         // storage for the [B][2][total_limbs - 14][N] result; chunk_pairs bounds the workspace.
+        // [pair_first, pair_last): the pairs this call processes (default: all ceil(B/2)); the others' slots of the
+        // result are left untouched — a rank of a multi-GPU run computes its share and gathers the rest (comm.hpp)
         Ct bootstrap_real_pairs(const Evaluator &ev, const Ct &in, const Keys &keys, long long chunk_pairs,
-                                const Ct *into = nullptr);
+                                const Ct *into = nullptr, long long pair_first = 0, long long pair_last = -1);
 
         // host-side artefacts, exposed for the CPU test-suite
         const std::vector<double> &cheb_coeffs() const

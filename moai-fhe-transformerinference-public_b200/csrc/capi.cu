@@ -5,6 +5,7 @@
 #include "ntt.cuh"
 #include "bootstrap.hpp"
 #include "modules.hpp"
+#include "comm.hpp"
 #include "ops.cuh"
 #include <cmath>
 #include <cstring>
@@ -1034,6 +1035,41 @@ extern "C"
         encoder_layer_stage(ev, stage, cx, ca, lw, bv, input_num, getk(keys), *b->b, num_batch, layer_id,
                             boot_chunk > 0 ? boot_chunk : 32);
         MOAI_CUDA_CHECK(cudaStreamSynchronize(c->stream)); // temporaries of the stage are released on return
+        API_END
+    }
+
+    // ---- one packed batch over several GPUs (comm.hpp) ------------------------------------------------------------
+    int32_t moai_comm_unique_id(uint8_t *out128)
+    {
+        API_BEGIN
+        MOAI_REQUIRE(out128, "null argument");
+        comm_unique_id(out128);
+        API_END
+    }
+
+    int32_t moai_comm_init(moai_context *ctx, const uint8_t *id128, int32_t rank, int32_t world)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(id128 || world == 1, "null argument");
+        comm_init(c, id128, rank, world);
+        API_END
+    }
+
+    int32_t moai_comm_destroy(moai_context *ctx)
+    {
+        API_BEGIN
+        comm_destroy(get(ctx));
+        API_END
+    }
+
+    int32_t moai_comm_stats(moai_context *ctx, uint64_t *gathers, uint64_t *received_bytes)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(gathers && received_bytes, "null argument");
+        *gathers = c->comm ? c->comm->gathers : 0;
+        *received_bytes = c->comm ? c->comm->gathered_bytes : 0;
         API_END
     }
 

@@ -5,6 +5,7 @@
 // GaloisTool (S/util/galois.cpp:18-95) and CKKSEncoder::CKKSEncoder (S/ckks.cpp:20-75).
 #include "context.hpp"
 #include <chrono>
+#include "comm.hpp"
 #include <set>
 #include <cstdio>
 #include <cmath>
@@ -464,6 +465,7 @@ namespace moai
 
     Context::~Context()
     {
+        comm_destroy(this);
         kernel_timers_collect(true);
         for (cudaEvent_t e : kpool)
         {

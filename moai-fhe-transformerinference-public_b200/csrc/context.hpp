@@ -75,9 +75,12 @@ namespace moai
         u64 wq;
     };
 
+    struct Comm; // comm.hpp: NCCL communicator of a context that shares one packed batch with other GPUs
+
     struct Context
     {
         int device = 0;
+        Comm *comm = nullptr;
         int log_n = 0;
         size_t n = 0;
         int kl = 0; // key-level limb count (data primes + special prime)

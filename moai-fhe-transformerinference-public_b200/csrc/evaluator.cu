@@ -44,8 +44,8 @@ namespace moai
     Ct Evaluator::clone(const Ct &a) const
     {
         Ct r = alloc(a.batch, a.size, a.limbs, a.scale);
-        MOAI_CUDA_CHECK(cudaMemcpyAsync(r.d, a.d, (size_t)a.batch * a.size * a.limbs * n() * sizeof(u64),
-                                        cudaMemcpyDeviceToDevice, c->stream));
+        { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpyAsync(r.d, a.d, (size_t)a.batch * a.size * a.limbs * n() * sizeof(u64),
+                                        cudaMemcpyDeviceToDevice, c->stream)); }
         return r;
     }
 
@@ -53,9 +53,9 @@ namespace moai
     {
         EV_REQUIRE(src.size == dst.size && src.limbs == dst.limbs && dst_b0 + src.batch <= dst.batch,
                    "copy_into shape mismatch");
-        MOAI_CUDA_CHECK(cudaMemcpyAsync(dst.d + (size_t)dst_b0 * dst.size * dst.limbs * n(), src.d,
+        { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpyAsync(dst.d + (size_t)dst_b0 * dst.size * dst.limbs * n(), src.d,
                                         (size_t)src.batch * src.size * src.limbs * n() * sizeof(u64),
-                                        cudaMemcpyDeviceToDevice, c->stream));
+                                        cudaMemcpyDeviceToDevice, c->stream)); }
     }
 
     Ct Evaluator::concat(const std::vector<Ct> &parts) const

@@ -6,6 +6,7 @@
 // the batch dimension of single kernel launches, and reductions over ciphertexts are fused
 // (Evaluator::sum_batch / inner_product / sum_sub_square).
 #include "modules.hpp"
+#include "comm.hpp"
 #include <cstdlib>
 #include <algorithm>
 
@@ -609,17 +610,46 @@ namespace moai
                 const char *e = std::getenv("MOAI_BOOT_PAIR");
                 return !(e && e[0] == '0');
             }();
+            // one packed batch over several GPUs (comm.hpp): this rank bootstraps its share of the pairs / columns
+            // and the shares are exchanged with an all-gather of the refreshed limbs
+            const Comm *cm = ev.c->comm;
+            const int world = cm && x.batch >= 4LL * cm->world ? cm->world : 1, rank = world > 1 ? cm->rank : 0;
+            const size_t item_words = (size_t)2 * (boot.prm.total_limbs - 14) * ev.c->n;
             if (pair && x.batch >= 2)
             {
-                return boot.bootstrap_real_pairs(ev, in, keys, chunk, into);
+                const long long P = (x.batch + 1) / 2;
+                const auto mine = shard_range(P, world, rank);
+                Ct out = boot.bootstrap_real_pairs(ev, in, keys, chunk, into, mine.first, mine.second);
+                if (world > 1)
+                {
+                    std::vector<std::vector<std::pair<long long, long long>>> owned(world);
+                    for (int r = 0; r < world; r++)
+                    {
+                        const auto rg = shard_range(P, world, r);
+                        owned[r].push_back(rg);                                                   // first halves
+                        owned[r].push_back({ P + rg.first, std::min(x.batch, P + rg.second) });   // their partners
+                    }
+                    comm_all_gather_items(ev.c, out.d, item_words, owned);
+                }
+                return out;
             }
             Ct out = into ? *into : ev.alloc(x.batch, 2, boot.prm.total_limbs - 14, boot.prm.final_scale);
             out.scale = boot.prm.final_scale;
-            for (long long b0 = 0; b0 < x.batch; b0 += chunk)
+            const auto mine = shard_range(x.batch, world, rank);
+            for (long long b0 = mine.first; b0 < mine.second; b0 += chunk)
             {
-                const long long nb = std::min(chunk, x.batch - b0);
+                const long long nb = std::min(chunk, mine.second - b0);
                 Ct r = boot.bootstrap(ev, ev.view(in, b0, nb), keys);
                 ev.copy_into(r, out, b0);
+            }
+            if (world > 1)
+            {
+                std::vector<std::vector<std::pair<long long, long long>>> owned(world);
+                for (int r = 0; r < world; r++)
+                {
+                    owned[r].push_back(shard_range(x.batch, world, r));
+                }
+                comm_all_gather_items(ev.c, out.d, item_words, owned);
             }
             return out;
         }
@@ -650,12 +680,26 @@ namespace moai
             {
                 PhaseTimer t(c, "attention");
                 Ct x_att = ev.mod_switch_to(x, x.limbs - 6);
-                for (int h = 0; h < w.heads; h++)
+                // heads are independent (test_full_scheme.hpp:530-533): with several GPUs on the batch each rank runs its
+                // share of them and the 64-column outputs are all-gathered (at 2 limbs: 1.5 GiB in all)
+                const int world = c->comm ? c->comm->world : 1, rank = c->comm ? c->comm->rank : 0;
+                const auto mine = shard_range(w.heads, world, rank);
+                for (int h = (int)mine.first; h < (int)mine.second; h++)
                 {
                     Ct o = single_att_block(ev, x_att, w.WQ[h], w.WK[h], w.WV[h], w.bQ[h], w.bK[h], w.bV[h], bias_vec,
                                             input_num, keys, boot, num_batch, 16, layer_id);
                     MOAI_REQUIRE(o.limbs == 2 && o.batch == w.head_dim, "attention head output shape");
                     ev.copy_into(o, att_out, (long long)h * w.head_dim);
+                }
+                if (world > 1)
+                {
+                    std::vector<std::vector<std::pair<long long, long long>>> owned(world);
+                    for (int r = 0; r < world; r++)
+                    {
+                        const auto rg = shard_range(w.heads, world, r);
+                        owned[r].push_back({ rg.first * w.head_dim, rg.second * w.head_dim });
+                    }
+                    comm_all_gather_items(c, att_out.d, (size_t)2 * att_out.limbs * c->n, owned);
                 }
             }
             Ct so;
@@ -683,15 +727,35 @@ namespace moai
         }
         else if (stage == 2)
         {
+            // output columns of the intermediate matmul and their GELUs are independent (Ct_pt_matrix_mul.hpp:71,
+            // test_full_scheme.hpp:884-888): with several GPUs on the batch each rank computes its share of the 3072
+            // columns and the GELU outputs (2 limbs: 6 GiB in all) are all-gathered for the final matmul
+            const int world = c->comm ? c->comm->world : 1, rank = c->comm ? c->comm->rank : 0;
+            const auto mine = shard_range(w.inter, world, rank);
+            const int my_cols = (int)(mine.second - mine.first);
             Ct inter;
             {
                 PhaseTimer t(c, "intermediate_matmul");
                 Ct lowered = ev.mod_switch_to(x, x.limbs - 11);
-                inter = add_masked_bias(ev, ct_pt_matrix_mul_wo_pre(ev, lowered, w.inter_weight, w.inter), w.inter_bias,
-                                        bias_vec, scale);
+                if (world == 1)
+                {
+                    inter = add_masked_bias(ev, ct_pt_matrix_mul_wo_pre(ev, lowered, w.inter_weight, w.inter), w.inter_bias,
+                                            bias_vec, scale);
+                }
+                else
+                {
+                    std::vector<double> wsub((size_t)hidden * my_cols), bsub(w.inter_bias.begin() + mine.first,
+                                                                             w.inter_bias.begin() + mine.second);
+                    for (int j = 0; j < hidden; j++)
+                    {
+                        std::copy(w.inter_weight.begin() + (size_t)j * w.inter + mine.first,
+                                  w.inter_weight.begin() + (size_t)j * w.inter + mine.second, wsub.begin() + (size_t)j * my_cols);
+                    }
+                    inter = add_masked_bias(ev, ct_pt_matrix_mul_wo_pre(ev, lowered, wsub, my_cols), bsub, bias_vec, scale);
+                }
             }
             {
-                // 3072 independent GELUs (test_full_scheme.hpp:884-888); chunked: gelu_v2 keeps 24 powers alive
+                // chunked: gelu_v2 keeps 24 powers alive
                 PhaseTimer t(c, "gelu");
                 const long long chunk = 64;
                 Ct g;
@@ -701,9 +765,18 @@ namespace moai
                     Ct part = gelu_v2(ev, ev.view(inter, b0, nb), keys);
                     if (g.empty())
                     {
-                        g = ev.alloc(inter.batch, 2, part.limbs, part.scale);
+                        g = ev.alloc(w.inter, 2, part.limbs, part.scale);
                     }
-                    ev.copy_into(part, g, b0);
+                    ev.copy_into(part, g, mine.first + b0);
+                }
+                if (world > 1)
+                {
+                    std::vector<std::vector<std::pair<long long, long long>>> owned(world);
+                    for (int r = 0; r < world; r++)
+                    {
+                        owned[r].push_back(shard_range(w.inter, world, r));
+                    }
+                    comm_all_gather_items(c, g.d, (size_t)2 * g.limbs * c->n, owned);
                 }
                 inter = g;
             }

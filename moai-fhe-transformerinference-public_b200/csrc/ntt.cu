@@ -1276,6 +1276,7 @@ namespace moai
         a.log_n = c->log_n;
         NttArgs na{ nullptr, c->d_fwd, c->d_fwd_fp, c->d_limb, nullptr, 1, 1, c->log_n, 0 };
         dim3 grid((unsigned)batch, (unsigned)(limbs + 1), (unsigned)((c->n / 2) / 256));
+        KernelTimer kt(c, "k_ks_mac_multi", batch * (long long)n_keys);
         switch (n_keys)
         {
         case 1: launch_ks_mac_multi<1>(a, na, grid, c->stream); break;
@@ -1298,6 +1299,7 @@ namespace moai
         a.grp_size = grp_size;
         a.grp_stride = grp_stride;
         const long long ctas_b = a.count * ((1 << (c->log_n - 8)) / ROWS);
+        KernelTimer kt(c, "k_ntt_fwd_pass_b_strided", a.count);
         ntt_fwd_pass_b<<<(unsigned)ctas_b, ROWS * 16, 0, c->stream>>>(a);
         c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
@@ -1324,6 +1326,8 @@ namespace moai
         NttArgs na{ nullptr, c->d_fwd, c->d_fwd_fp, c->d_limb, nullptr, 1, 1, c->log_n, 0 };
         const int R = 1 << (c->log_n - 8);
         dim3 grid((unsigned)batch, (unsigned)(R / FR), (unsigned)rns);
+        // units: limb-transforms finished inside the kernel (one per (ciphertext, digit, target modulus))
+        KernelTimer kt(c, "k_ks_passb_mac", batch * (long long)limbs * rns);
         ks_passb_mac_kernel<<<grid, FT, KS_FUSED_SMEM, c->stream>>>(a, na);
         c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
@@ -1336,6 +1340,7 @@ namespace moai
             return;
         }
         NttArgs a{ data, c->d_inv, c->d_inv_fp, c->d_limb, d_limb_ids, period, div, c->log_n, count };
+        KernelTimer kt(c, "k_ntt_inv", count);
         switch (c->log_n)
         {
         case 12: launch_inv<4>(a, c->stream); break;

@@ -240,9 +240,9 @@ namespace moai
             const int targets = limbs_in - 1;
             Scratch t(P * n * sizeof(u64), c->stream);
             Scratch u((size_t)P * targets * n * sizeof(u64), c->stream);
-            MOAI_CUDA_CHECK(cudaMemcpy2DAsync(t.p, n * sizeof(u64), in + (size_t)targets * n,
+            { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(t.p, n * sizeof(u64), in + (size_t)targets * n,
                                               (size_t)limbs_in * n * sizeof(u64), n * sizeof(u64), (size_t)P,
-                                              cudaMemcpyDeviceToDevice, c->stream));
+                                              cudaMemcpyDeviceToDevice, c->stream)); }
             ntt_inverse(c, t.as<u64>(), P, c->d_ids + last_id, 1);
             const long long total2 = P * targets * (long long)(n / 2);
             // expansion (+half, reduce into every target prime, +fix) fused into the NTT's first pass
@@ -251,6 +251,7 @@ namespace moai
             pro.mode = 2;
             pro.last_id = last_id;
             ntt_forward(c, u.as<u64>(), P * targets, c->d_ids, targets, 1, &pro);
+            KernelTimer kt1(c, "k_divround_finish", 1);
             k_divround_finish<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
                 reinterpret_cast<const ulonglong2 *>(in), u.as<ulonglong2>(),
                 reinterpret_cast<const ulonglong2 *>(addend), reinterpret_cast<ulonglong2 *>(out), total2, c->log_n - 1,
@@ -530,6 +531,7 @@ namespace moai
         {
             return;
         }
+        KernelTimer kt2(c, "k_addsub", 1);
         k_addsub<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
             op, reinterpret_cast<const ulonglong2 *>(a), reinterpret_cast<const ulonglong2 *>(b),
             reinterpret_cast<ulonglong2 *>(out), total2, c->log_n - 1, limbs, c->d_limb,
@@ -561,6 +563,7 @@ namespace moai
         {
             return;
         }
+        KernelTimer kt3(c, "k_multiply_plain", 1);
         k_multiply_plain<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
             reinterpret_cast<const ulonglong2 *>(ct), reinterpret_cast<const ulonglong2 *>(pt),
             reinterpret_cast<ulonglong2 *>(out), total2, c->log_n - 1, polys, limbs, pt_stride / 2, c->d_limb);
@@ -586,6 +589,7 @@ namespace moai
         Scratch d(limbs * sizeof(Twiddle), c->stream);
         MOAI_CUDA_CHECK(cudaMemcpyAsync(d.p, h.data(), limbs * sizeof(Twiddle), cudaMemcpyHostToDevice, c->stream));
         // h is pageable: the copy is staged before returning, so it may go out of scope
+        KernelTimer kt4(c, "k_scalar", 1);
         k_scalar<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(mode, reinterpret_cast<const ulonglong2 *>(ct),
                                                                  d.as<Twiddle>(), reinterpret_cast<ulonglong2 *>(out),
                                                                  total2, c->log_n - 1, polys, limbs, c->d_limb);
@@ -612,6 +616,7 @@ namespace moai
         {
             return;
         }
+        KernelTimer kt5(c, "k_multiply", 1);
         k_multiply<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
             reinterpret_cast<const ulonglong2 *>(a), reinterpret_cast<const ulonglong2 *>(b),
             reinterpret_cast<ulonglong2 *>(out3), total2, c->log_n - 1, limbs, c->d_limb, accumulate ? 1 : 0, 0,
@@ -627,6 +632,7 @@ namespace moai
         {
             return;
         }
+        KernelTimer kt6(c, "k_multiply", 1);
         k_multiply<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
             reinterpret_cast<const ulonglong2 *>(a), reinterpret_cast<const ulonglong2 *>(a),
             reinterpret_cast<ulonglong2 *>(out3), total2, c->log_n - 1, limbs, c->d_limb, 0, 1, 0);
@@ -637,6 +643,7 @@ namespace moai
     void sum_batch(Context *c, const u64 *a, u64 *out, long long batch, int polys, int limbs)
     {
         const long long per_ct2 = (long long)polys * limbs * (long long)(c->n / 2);
+        KernelTimer kt7(c, "k_sum_batch", 1);
         k_sum_batch<<<grid_for(per_ct2), EW_THREADS, 0, c->stream>>>(reinterpret_cast<const ulonglong2 *>(a),
                                                                    reinterpret_cast<ulonglong2 *>(out), per_ct2, batch,
                                                                    c->log_n - 1, limbs, c->d_limb);
@@ -648,6 +655,7 @@ namespace moai
     {
         MOAI_REQUIRE(batch <= 1024, "inner product batch too large for the lazy accumulator");
         const long long total2 = (long long)limbs * (long long)(c->n / 2);
+        KernelTimer kt8(c, "k_inner_product", 1);
         k_inner_product<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
             reinterpret_cast<const ulonglong2 *>(a), reinterpret_cast<const ulonglong2 *>(b),
             reinterpret_cast<ulonglong2 *>(out3), batch, c->log_n - 1, limbs, mode, c->d_limb, c->d_two64);
@@ -678,6 +686,7 @@ namespace moai
         }
         const long long ctas = batch * 2 * limbs * (long long)((c->n / 2) / EW_THREADS);
         MOAI_REQUIRE((c->n / 2) % EW_THREADS == 0 && ctas < (1ll << 31), "unsupported shape for the fused inner sums");
+        KernelTimer kt9(c, "k_bsgs_inner", 1);
         k_bsgs_inner<<<(unsigned)ctas, EW_THREADS, 0, c->stream>>>(a, batch * 2, c->log_n - 1, limbs, c->d_limb,
                                                                    c->d_two64);
         c->launches += 1;
@@ -694,9 +703,9 @@ namespace moai
     {
         MOAI_REQUIRE(limbs_out >= 1 && limbs_out <= limbs_in, "end of modulus switching chain reached");
         const size_t n = c->n;
-        MOAI_CUDA_CHECK(cudaMemcpy2DAsync(out, (size_t)limbs_out * n * sizeof(u64), in,
+        { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(out, (size_t)limbs_out * n * sizeof(u64), in,
                                           (size_t)limbs_in * n * sizeof(u64), (size_t)limbs_out * n * sizeof(u64),
-                                          (size_t)(batch * polys), cudaMemcpyDeviceToDevice, c->stream));
+                                          (size_t)(batch * polys), cudaMemcpyDeviceToDevice, c->stream)); }
     }
 
     void mod_raise(Context *c, const u64 *in, u64 *out, long long batch, int polys, int limbs_out)
@@ -704,7 +713,7 @@ namespace moai
         const size_t n = c->n;
         const long long P = batch * polys;
         Scratch d(P * n * sizeof(u64), c->stream);
-        MOAI_CUDA_CHECK(cudaMemcpyAsync(d.p, in, P * n * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+        { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpyAsync(d.p, in, P * n * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream)); }
         ntt_inverse(c, d.as<u64>(), P, c->d_ids, 1);
         const long long total2 = P * limbs_out * (long long)(n / 2);
         k_modraise_expand<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
@@ -722,6 +731,7 @@ namespace moai
         {
             return;
         }
+        KernelTimer kt10(c, "k_galois", 1);
         k_galois<<<grid_for(total), EW_THREADS, 0, c->stream>>>(in, out, total, c->log_n, table);
         c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
@@ -749,8 +759,8 @@ namespace moai
         }
         Scratch d((size_t)batch * limbs * n * sizeof(u64), c->stream);
         const size_t row = (size_t)limbs * n * sizeof(u64);
-        MOAI_CUDA_CHECK(cudaMemcpy2DAsync(d.p, row, target, target_stride ? (size_t)target_stride * sizeof(u64) : row,
-                                          row, (size_t)batch, cudaMemcpyDeviceToDevice, c->stream));
+        { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(d.p, row, target, target_stride ? (size_t)target_stride * sizeof(u64) : row,
+                                          row, (size_t)batch, cudaMemcpyDeviceToDevice, c->stream)); }
         ntt_inverse(c, d.as<u64>(), batch * limbs, c->d_ids, limbs);
         // NTT_I(d_I mod q_I) reproduces the target limb itself, so the I == J digits need no
         // special case (S/evaluator.cpp:2831-2836 takes the NTT-form input there: same residues)
@@ -765,6 +775,7 @@ namespace moai
         else
         {
             const long long total2 = batch * rns * limbs * (long long)(n / 2);
+            KernelTimer kt11(c, "k_ks_expand", 1);
             k_ks_expand<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
                 d.as<ulonglong2>(), reinterpret_cast<ulonglong2 *>(ext), total2, c->log_n - 1, limbs, ids_ks, c->d_limb);
             c->launches += 1;
@@ -784,6 +795,7 @@ namespace moai
         const int *ids_ks = c->d_ids_ks + (size_t)limbs * (c->kl + 1);
         Scratch acc((size_t)batch * 2 * rns * n * sizeof(u64), c->stream);
         dim3 grid((unsigned)batch, (unsigned)rns, (unsigned)((n / 2) / EW_THREADS));
+        KernelTimer kt12(c, "k_ks_mac", 1);
         k_ks_mac<<<grid, EW_THREADS, 0, c->stream>>>(reinterpret_cast<const ulonglong2 *>(ext),
                                                      reinterpret_cast<const ulonglong2 *>(ksk), acc.as<ulonglong2>(),
                                                      batch, c->log_n - 1, limbs, key_kl, ids_ks, c->d_limb, c->d_two64, 0);
@@ -805,8 +817,8 @@ namespace moai
         const int *ids_ks = c->d_ids_ks + (size_t)limbs * (c->kl + 1);
         Scratch d((size_t)batch * limbs * n * sizeof(u64), c->stream);
         const size_t row = (size_t)limbs * n * sizeof(u64);
-        MOAI_CUDA_CHECK(cudaMemcpy2DAsync(d.p, row, target, target_stride ? (size_t)target_stride * sizeof(u64) : row, row,
-                                          (size_t)batch, cudaMemcpyDeviceToDevice, c->stream));
+        { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(d.p, row, target, target_stride ? (size_t)target_stride * sizeof(u64) : row, row,
+                                          (size_t)batch, cudaMemcpyDeviceToDevice, c->stream)); }
         ntt_inverse(c, d.as<u64>(), batch * limbs, c->d_ids, limbs);
         NttPrologue pro;
         pro.src = d.as<u64>();
@@ -824,6 +836,7 @@ namespace moai
             ntt_forward_pass_b_strided(c, ext + (size_t)I * limbs * n, batch, limbs, (long long)rns * limbs,
                                        c->d_ids + prime);
             dim3 grid((unsigned)batch, 1u, (unsigned)((n / 2) / EW_THREADS));
+            KernelTimer kt13(c, "k_ks_mac", 1);
             k_ks_mac<<<grid, EW_THREADS, 0, c->stream>>>(reinterpret_cast<const ulonglong2 *>(ext),
                                                          reinterpret_cast<const ulonglong2 *>(ksk),
                                                          acc.as<ulonglong2>(), batch, c->log_n - 1, limbs, key_kl,
@@ -974,6 +987,7 @@ namespace moai
             for (int r = 0; r < n_rot; r++) // integer-path modulus (the special prime)
             {
                 dim3 grid((unsigned)batch, 1u, (unsigned)((n / 2) / EW_THREADS));
+                KernelTimer kt14(c, "k_ks_mac", 1);
                 k_ks_mac<<<grid, EW_THREADS, 0, c->stream>>>(reinterpret_cast<const ulonglong2 *>(ext),
                                                              reinterpret_cast<const ulonglong2 *>(ksk_pre[r]),
                                                              reinterpret_cast<ulonglong2 *>(accp[r]), batch, c->log_n - 1,
@@ -1034,10 +1048,10 @@ namespace moai
                 }
                 else
                 {
-                    MOAI_CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)max_limbs * n * sizeof(u64),
-                                                    cudaMemcpyDeviceToDevice, c->stream));
-                    MOAI_CUDA_CHECK(cudaMemcpyAsync(dst + (size_t)max_limbs * n, src + (size_t)(c->kl - 1) * n,
-                                                    n * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+                    { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)max_limbs * n * sizeof(u64),
+                                                    cudaMemcpyDeviceToDevice, c->stream)); }
+                    { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpyAsync(dst + (size_t)max_limbs * n, src + (size_t)(c->kl - 1) * n,
+                                                    n * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream)); }
                 }
             }
         }
@@ -1048,11 +1062,11 @@ namespace moai
         const size_t n = c->n;
         const size_t poly = (size_t)limbs * n;
         // out2 <- (c0, c1) ; target <- c2
-        MOAI_CUDA_CHECK(cudaMemcpy2DAsync(out2, 2 * poly * sizeof(u64), in3, 3 * poly * sizeof(u64),
-                                          2 * poly * sizeof(u64), (size_t)batch, cudaMemcpyDeviceToDevice, c->stream));
+        { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(out2, 2 * poly * sizeof(u64), in3, 3 * poly * sizeof(u64),
+                                          2 * poly * sizeof(u64), (size_t)batch, cudaMemcpyDeviceToDevice, c->stream)); }
         Scratch tg((size_t)batch * poly * sizeof(u64), c->stream);
-        MOAI_CUDA_CHECK(cudaMemcpy2DAsync(tg.p, poly * sizeof(u64), in3 + 2 * poly, 3 * poly * sizeof(u64),
-                                          poly * sizeof(u64), (size_t)batch, cudaMemcpyDeviceToDevice, c->stream));
+        { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(tg.p, poly * sizeof(u64), in3 + 2 * poly, 3 * poly * sizeof(u64),
+                                          poly * sizeof(u64), (size_t)batch, cudaMemcpyDeviceToDevice, c->stream)); }
         switch_key(c, out2, tg.as<u64>(), batch, limbs, ksk, key_kl);
     }
 
@@ -1066,11 +1080,11 @@ namespace moai
         Scratch perm((size_t)batch * 2 * poly * sizeof(u64), c->stream);
         apply_galois_ntt(c, in, perm.as<u64>(), batch * 2 * limbs, elt);
         Scratch tg((size_t)batch * poly * sizeof(u64), c->stream);
-        MOAI_CUDA_CHECK(cudaMemcpy2DAsync(tg.p, poly * sizeof(u64), perm.as<u64>() + poly, 2 * poly * sizeof(u64),
-                                          poly * sizeof(u64), (size_t)batch, cudaMemcpyDeviceToDevice, c->stream));
-        MOAI_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)batch * 2 * poly * sizeof(u64), c->stream));
-        MOAI_CUDA_CHECK(cudaMemcpy2DAsync(out, 2 * poly * sizeof(u64), perm.p, 2 * poly * sizeof(u64),
-                                          poly * sizeof(u64), (size_t)batch, cudaMemcpyDeviceToDevice, c->stream));
+        { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(tg.p, poly * sizeof(u64), perm.as<u64>() + poly, 2 * poly * sizeof(u64),
+                                          poly * sizeof(u64), (size_t)batch, cudaMemcpyDeviceToDevice, c->stream)); }
+        { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)batch * 2 * poly * sizeof(u64), c->stream)); }
+        { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(out, 2 * poly * sizeof(u64), perm.p, 2 * poly * sizeof(u64),
+                                          poly * sizeof(u64), (size_t)batch, cudaMemcpyDeviceToDevice, c->stream)); }
         switch_key(c, out, tg.as<u64>(), batch, limbs, ksk, key_kl);
     }
 } // namespace moai

@@ -57,6 +57,17 @@ def env(pkg):
     be.close()
 
 
+@pytest.fixture(autouse=True)
+def _release_between_tests(env):
+    """torch's caching allocator and the library's arena both keep what they freed; with 65 GiB of keys resident the
+    GiB-sized batches of the next test need that memory back."""
+    import torch
+    yield
+    torch.cuda.synchronize()
+    env["be"].lib.moai_release_cached_memory(env["be"].h)
+    torch.cuda.empty_cache()
+
+
 def pack_rows(A):
     """A [TOK, cols] activations of input 0 -> [cols, SLOTS]: slot 256 k holds token k (batch_input layout,
     Batch_encode_encrypt.hpp:21-27); the other 255 inputs are empty, as in the reference run."""
@@ -220,13 +231,13 @@ def test_gelu_golden(pkg, env):
     be, keys, g = env["be"], env["keys"], env["g"]
     V = pack_rows(g["gelu_in"])
     errs = []
-    for c0 in range(0, 3072, 768):
-        x = encrypt_cols(env, V[c0:c0 + 768], 9)
+    for c0 in range(0, 3072, 256):
+        x = encrypt_cols(env, V[c0:c0 + 256], 9)
         out, osc = be.gelu_v2(keys, x, SCALE)
         del x
         assert out.shape[2] == 2
         got = slot_values(env, out, osc, VALID).real.T
-        errs.append(np.abs(got - g["gelu_out"][:, c0:c0 + 768]).max())
+        errs.append(np.abs(got - g["gelu_out"][:, c0:c0 + 256]).max())
         del out
     print("gelu_v2 golden: max-abs %.3g" % max(errs))
     assert max(errs) < 0.06
@@ -235,10 +246,15 @@ def test_gelu_golden(pkg, env):
 def test_softmax_golden(pkg, env):
     """softmax_boot (softmax.hpp:308-581, one bootstrapping inside) on layer 0's scores, all 12 heads, vs
     aftsoftmax.csv (true softmax).  The module computes exp as (1 + x / 128)^128 after subtracting the layer's
-    constant 7.5 (:324) and normalises with a 16-step Goldschmidt inverse; the float64 model of exactly that is
-    evaluated beside it.  Tolerances: 5e-3 max-abs against the model, 2e-2 against the CSV."""
+    constant 7.5 (:324), bootstraps the row sums and normalises with a 16-step Goldschmidt inverse; the float64 model of
+    exactly that is evaluated beside it.  With these scores the row sums of exp(S - 7.5) are as small as 1e-3, and the
+    bootstrapping error eps on a row sum (8e-6 max-abs at this size, test_bootstrap_fullsize_per_phase) comes back
+    multiplied by 1 / sum: |P - model| <= eps / sum per row.  The reference behaves the same way (oracle/_ref at
+    N = 8192, eps = 3e-6: 4.6e-4 ... 1.1e-3 from the model, 1.4e-2 ... 2.0e-2 from the CSV on heads 0, 1, 2, 5).
+    Tolerances: per row 1e-3 + 2e-5 / sum against the model; 4e-2 max-abs against the CSV (the (1 + x/128)^128
+    approximation of exp itself is 1.4e-2 ... 2e-2 away)."""
     be, kg, boot, keys, g = env["be"], env["kg"], env["boot"], env["keys"], env["g"]
-    worst_csv, worst_model = 0.0, 0.0
+    worst_csv, worst_model, worst_ratio = 0.0, 0.0, 0.0
     for h in range(12):
         S = g["QKT"][:, 5 * h:5 * h + 5]
         want = g["aftsoftmax"][:, 5 * h:5 * h + 5]
@@ -261,8 +277,11 @@ def test_softmax_golden(pkg, env):
                     P[k, (k + i) % 128] = got[i, k]
         worst_csv = max(worst_csv, np.abs(P - want).max())
         worst_model = max(worst_model, np.abs(P - model).max())
-    print("softmax_boot golden (12 heads): max-abs vs float64 model %.3g, vs aftsoftmax.csv %.3g" % (worst_model, worst_csv))
-    assert worst_model < 5e-3 and worst_csv < 2e-2
+        row_tol = 1e-3 + 2e-5 / E.sum(axis=1)
+        worst_ratio = max(worst_ratio, (np.abs(P - model).max(axis=1) / row_tol).max())
+    print("softmax_boot golden (12 heads): max-abs vs float64 model %.3g (worst row at %.2f of its bound "
+          "1e-3 + 2e-5 / sum), vs aftsoftmax.csv %.3g" % (worst_model, worst_ratio, worst_csv))
+    assert worst_ratio < 1.0 and worst_csv < 4e-2
 
 
 def test_c1_selfoutput_linear_with_reference_mask(pkg, env):
