@@ -523,25 +523,22 @@ namespace moai
             // rescale lands exactly on target_scale
             const int lv = target_limbs + 1;
             const double ql = ev.last_prime(lv);
-            Ct acc;
+            // one fused pass: every T_j is read at its own level (the mod-switch to lv is free) and multiplied by its
+            // constant encoded at target_scale * ql / T_j.scale, exactly what multiply_plain + add_inplace produced
+            std::vector<Ct> terms;
+            std::vector<double> cs;
             for (int j = 1; j <= d; j++)
             {
-                if (coef[j] == 0.0)
+                if (coef[j] != 0.0)
                 {
-                    continue;
+                    terms.push_back(T.at(j));
+                    cs.push_back(coef[j]);
                 }
-                Ct tj = ev.mod_switch_to(T.at(j), lv);
-                Pt cj = ev.encode(coef[j], lv, target_scale * ql / tj.scale);
-                Ct term = ev.multiply_plain(tj, cj);
-                term.scale = target_scale * ql;
-                if (acc.empty())
-                {
-                    acc = term;
-                }
-                else
-                {
-                    ev.add_inplace(acc, term);
-                }
+            }
+            Ct acc;
+            if (!terms.empty())
+            {
+                acc = ev.lincomb_scalar(terms, cs, lv, target_scale * ql);
             }
             MOAI_REQUIRE(!acc.empty(), "degenerate polynomial leaf");
             Ct r = ev.rescale_to_next(acc);

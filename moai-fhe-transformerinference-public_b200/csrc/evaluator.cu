@@ -44,7 +44,7 @@ namespace moai
     Ct Evaluator::clone(const Ct &a) const
     {
         Ct r = alloc(a.batch, a.size, a.limbs, a.scale);
-        { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpyAsync(r.d, a.d, (size_t)a.batch * a.size * a.limbs * n() * sizeof(u64),
+        { KernelTimer ktm(c, "k_copy_clone", 1); MOAI_CUDA_CHECK(cudaMemcpyAsync(r.d, a.d, (size_t)a.batch * a.size * a.limbs * n() * sizeof(u64),
                                         cudaMemcpyDeviceToDevice, c->stream)); }
         return r;
     }
@@ -53,7 +53,7 @@ namespace moai
     {
         EV_REQUIRE(src.size == dst.size && src.limbs == dst.limbs && dst_b0 + src.batch <= dst.batch,
                    "copy_into shape mismatch");
-        { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpyAsync(dst.d + (size_t)dst_b0 * dst.size * dst.limbs * n(), src.d,
+        { KernelTimer ktm(c, "k_copy_into", 1); MOAI_CUDA_CHECK(cudaMemcpyAsync(dst.d + (size_t)dst_b0 * dst.size * dst.limbs * n(), src.d,
                                         (size_t)src.batch * src.size * src.limbs * n() * sizeof(u64),
                                         cudaMemcpyDeviceToDevice, c->stream)); }
     }
@@ -245,6 +245,28 @@ namespace moai
             ew_multiply_plain(c, a.d, p.d, r.d, a.batch, a.size, a.limbs,
                               p.count == 1 ? 0 : (long long)a.limbs * (long long)n());
         }
+        return r;
+    }
+
+    Ct Evaluator::lincomb_scalar(const std::vector<Ct> &terms, const std::vector<double> &coefs, int limbs,
+                                 double out_scale) const
+    {
+        EV_REQUIRE(!terms.empty() && terms.size() == coefs.size() && terms.size() <= 8, "1..8 terms expected");
+        std::vector<const u64 *> in;
+        std::vector<int> in_limbs;
+        std::vector<u64> consts;
+        for (size_t j = 0; j < terms.size(); j++)
+        {
+            const Ct &t = terms[j];
+            EV_REQUIRE(t.size == terms[0].size && t.batch == terms[0].batch, "terms must share batch and size");
+            EV_REQUIRE(t.limbs >= limbs, "a term is below the requested level");
+            const Pt k = encode(coefs[j], limbs, out_scale / t.scale); // same constants multiply_plain would use
+            in.push_back(t.d);
+            in_limbs.push_back(t.limbs);
+            consts.insert(consts.end(), k.consts.begin(), k.consts.end());
+        }
+        Ct r = alloc(terms[0].batch, terms[0].size, limbs, out_scale);
+        ew_lincomb_scalar(c, (int)terms.size(), in.data(), in_limbs.data(), consts.data(), r.d, r.batch, r.size, limbs);
         return r;
     }
 

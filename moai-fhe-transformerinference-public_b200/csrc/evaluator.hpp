@@ -129,6 +129,9 @@ namespace moai
         Ct alloc(long long batch, int size, int limbs, double scale) const;
         Ct wrap(u64 *d, long long batch, int size, int limbs, double scale) const; // caller-owned memory
         Ct view(const Ct &a, long long b0, long long count) const;                 // sub-batch, shared storage
+        // sum_j coef[j] * terms[j], each term mod-switched to `limbs` on the fly and its constant encoded at
+        // out_scale / terms[j].scale, in one pass (fused multiply_const + mod_switch_to + add of a polynomial leaf)
+        Ct lincomb_scalar(const std::vector<Ct> &terms, const std::vector<double> &coefs, int limbs, double out_scale) const;
         Ct clone(const Ct &a) const;
         void copy_into(const Ct &src, Ct &dst, long long dst_b0) const;            // dst[dst_b0 ...] = src
         Ct concat(const std::vector<Ct> &parts) const;

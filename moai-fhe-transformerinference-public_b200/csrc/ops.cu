@@ -145,6 +145,46 @@ namespace moai
             out[i] = x;
         }
 
+        // out = sum_j in_j * k[j][l]: a linear combination of up to LC_MAX ciphertext batches with per-limb scalar
+        // constants, every input read at ITS OWN limb count (only the first `limbs` limbs are used: the mod-switch to
+        // the output level costs nothing).  One pass instead of a copy + multiply + add per term — the leaves
+        // sum_j c_j T_j of the Chebyshev evaluation in EvalMod (M/source/bootstrapping/common/Polynomial.cpp:322-495
+        // does them with multiply_const + add per term).
+        constexpr int LC_MAX = 8;
+        struct LinCombArgs
+        {
+            const ulonglong2 *in[LC_MAX];
+            int in_limbs[LC_MAX];
+            int n_terms;
+        };
+        __global__ void k_lincomb(LinCombArgs a, const Twiddle *__restrict__ consts, ulonglong2 *__restrict__ out,
+                                  long long total2, int log_n2, int limbs, const LimbConst *__restrict__ lcs)
+        {
+            long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; // over [batch * polys][limbs][n/2]
+            if (i >= total2)
+            {
+                return;
+            }
+            const long long lp = i >> log_n2;
+            const int limb = (int)(lp % limbs);
+            const long long bp = lp / limbs;
+            const long long within = i & (((long long)1 << log_n2) - 1);
+            const u64 q = lcs[limb].q;
+            ulonglong2 acc{ 0, 0 };
+#pragma unroll
+            for (int j = 0; j < LC_MAX; j++)
+            {
+                if (j < a.n_terms)
+                {
+                    const ulonglong2 v = a.in[j][((bp * a.in_limbs[j] + limb) << log_n2) + within];
+                    const Twiddle k = consts[j * limbs + limb];
+                    acc.x = addmod(acc.x, mul_shoup(v.x, k.w, k.wq, q), q);
+                    acc.y = addmod(acc.y, mul_shoup(v.y, k.w, k.wq, q), q);
+                }
+            }
+            out[i] = acc;
+        }
+
         // (a0, a1) x (b0, b1) -> (a0 b0, a0 b1 + a1 b0, a1 b1); one thread per coefficient pair of a limb
         __global__ void k_multiply(const ulonglong2 *__restrict__ a, const ulonglong2 *__restrict__ b,
                                    ulonglong2 *__restrict__ out, long long total2, int log_n2, int limbs,
@@ -240,7 +280,7 @@ namespace moai
             const int targets = limbs_in - 1;
             Scratch t(P * n * sizeof(u64), c->stream);
             Scratch u((size_t)P * targets * n * sizeof(u64), c->stream);
-            { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(t.p, n * sizeof(u64), in + (size_t)targets * n,
+            { KernelTimer ktm(c, "k_copy_last_limb", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(t.p, n * sizeof(u64), in + (size_t)targets * n,
                                               (size_t)limbs_in * n * sizeof(u64), n * sizeof(u64), (size_t)P,
                                               cudaMemcpyDeviceToDevice, c->stream)); }
             ntt_inverse(c, t.as<u64>(), P, c->d_ids + last_id, 1);
@@ -597,6 +637,40 @@ namespace moai
         MOAI_CUDA_CHECK(cudaGetLastError());
     }
 
+    void ew_lincomb_scalar(Context *c, int n_terms, const u64 *const *in, const int *in_limbs, const u64 *h_consts,
+                           u64 *out, long long batch, int polys, int limbs)
+    {
+        MOAI_REQUIRE(n_terms >= 1 && n_terms <= LC_MAX, "1..8 terms per linear combination");
+        const long long total2 = batch * polys * limbs * (long long)(c->n / 2);
+        if (!total2)
+        {
+            return;
+        }
+        LinCombArgs a{};
+        a.n_terms = n_terms;
+        std::vector<Twiddle> h((size_t)n_terms * limbs);
+        for (int j = 0; j < n_terms; j++)
+        {
+            MOAI_REQUIRE(in_limbs[j] >= limbs, "a term is below the output level");
+            a.in[j] = reinterpret_cast<const ulonglong2 *>(in[j]);
+            a.in_limbs[j] = in_limbs[j];
+            for (int l = 0; l < limbs; l++)
+            {
+                const u64 k = h_consts[(size_t)j * limbs + l];
+                MOAI_REQUIRE(k < c->q[l], "scalar constant must be reduced");
+                h[(size_t)j * limbs + l].w = k;
+                h[(size_t)j * limbs + l].wq = (u64)((((unsigned __int128)k) << 64) / c->q[l]);
+            }
+        }
+        Scratch d(h.size() * sizeof(Twiddle), c->stream);
+        MOAI_CUDA_CHECK(cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(Twiddle), cudaMemcpyHostToDevice, c->stream));
+        KernelTimer kt(c, "k_lincomb", 1);
+        k_lincomb<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(a, d.as<Twiddle>(), reinterpret_cast<ulonglong2 *>(out),
+                                                                  total2, c->log_n - 1, limbs, c->d_limb);
+        c->launches += 1;
+        MOAI_CUDA_CHECK(cudaGetLastError());
+    }
+
     void ew_multiply_scalar(Context *c, const u64 *ct, const u64 *h_consts, u64 *out, long long batch, int polys,
                             int limbs)
     {
@@ -703,7 +777,7 @@ namespace moai
     {
         MOAI_REQUIRE(limbs_out >= 1 && limbs_out <= limbs_in, "end of modulus switching chain reached");
         const size_t n = c->n;
-        { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(out, (size_t)limbs_out * n * sizeof(u64), in,
+        { KernelTimer ktm(c, "k_copy_mod_switch", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(out, (size_t)limbs_out * n * sizeof(u64), in,
                                           (size_t)limbs_in * n * sizeof(u64), (size_t)limbs_out * n * sizeof(u64),
                                           (size_t)(batch * polys), cudaMemcpyDeviceToDevice, c->stream)); }
     }
@@ -713,7 +787,7 @@ namespace moai
         const size_t n = c->n;
         const long long P = batch * polys;
         Scratch d(P * n * sizeof(u64), c->stream);
-        { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpyAsync(d.p, in, P * n * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream)); }
+        { KernelTimer ktm(c, "k_copy_modraise", 1); MOAI_CUDA_CHECK(cudaMemcpyAsync(d.p, in, P * n * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream)); }
         ntt_inverse(c, d.as<u64>(), P, c->d_ids, 1);
         const long long total2 = P * limbs_out * (long long)(n / 2);
         k_modraise_expand<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
@@ -759,7 +833,7 @@ namespace moai
         }
         Scratch d((size_t)batch * limbs * n * sizeof(u64), c->stream);
         const size_t row = (size_t)limbs * n * sizeof(u64);
-        { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(d.p, row, target, target_stride ? (size_t)target_stride * sizeof(u64) : row,
+        { KernelTimer ktm(c, "k_copy_ks_target", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(d.p, row, target, target_stride ? (size_t)target_stride * sizeof(u64) : row,
                                           row, (size_t)batch, cudaMemcpyDeviceToDevice, c->stream)); }
         ntt_inverse(c, d.as<u64>(), batch * limbs, c->d_ids, limbs);
         // NTT_I(d_I mod q_I) reproduces the target limb itself, so the I == J digits need no
@@ -817,7 +891,7 @@ namespace moai
         const int *ids_ks = c->d_ids_ks + (size_t)limbs * (c->kl + 1);
         Scratch d((size_t)batch * limbs * n * sizeof(u64), c->stream);
         const size_t row = (size_t)limbs * n * sizeof(u64);
-        { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(d.p, row, target, target_stride ? (size_t)target_stride * sizeof(u64) : row, row,
+        { KernelTimer ktm(c, "k_copy_ks_target", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(d.p, row, target, target_stride ? (size_t)target_stride * sizeof(u64) : row, row,
                                           (size_t)batch, cudaMemcpyDeviceToDevice, c->stream)); }
         ntt_inverse(c, d.as<u64>(), batch * limbs, c->d_ids, limbs);
         NttPrologue pro;
@@ -1048,9 +1122,9 @@ namespace moai
                 }
                 else
                 {
-                    { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)max_limbs * n * sizeof(u64),
+                    { KernelTimer ktm(c, "k_copy_key_prepare", 1); MOAI_CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)max_limbs * n * sizeof(u64),
                                                     cudaMemcpyDeviceToDevice, c->stream)); }
-                    { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpyAsync(dst + (size_t)max_limbs * n, src + (size_t)(c->kl - 1) * n,
+                    { KernelTimer ktm(c, "k_copy_key_prepare", 1); MOAI_CUDA_CHECK(cudaMemcpyAsync(dst + (size_t)max_limbs * n, src + (size_t)(c->kl - 1) * n,
                                                     n * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream)); }
                 }
             }
@@ -1062,10 +1136,10 @@ namespace moai
         const size_t n = c->n;
         const size_t poly = (size_t)limbs * n;
         // out2 <- (c0, c1) ; target <- c2
-        { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(out2, 2 * poly * sizeof(u64), in3, 3 * poly * sizeof(u64),
+        { KernelTimer ktm(c, "k_copy_relin_c0c1", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(out2, 2 * poly * sizeof(u64), in3, 3 * poly * sizeof(u64),
                                           2 * poly * sizeof(u64), (size_t)batch, cudaMemcpyDeviceToDevice, c->stream)); }
         Scratch tg((size_t)batch * poly * sizeof(u64), c->stream);
-        { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(tg.p, poly * sizeof(u64), in3 + 2 * poly, 3 * poly * sizeof(u64),
+        { KernelTimer ktm(c, "k_copy_relin_c2", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(tg.p, poly * sizeof(u64), in3 + 2 * poly, 3 * poly * sizeof(u64),
                                           poly * sizeof(u64), (size_t)batch, cudaMemcpyDeviceToDevice, c->stream)); }
         switch_key(c, out2, tg.as<u64>(), batch, limbs, ksk, key_kl);
     }
@@ -1080,10 +1154,10 @@ namespace moai
         Scratch perm((size_t)batch * 2 * poly * sizeof(u64), c->stream);
         apply_galois_ntt(c, in, perm.as<u64>(), batch * 2 * limbs, elt);
         Scratch tg((size_t)batch * poly * sizeof(u64), c->stream);
-        { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(tg.p, poly * sizeof(u64), perm.as<u64>() + poly, 2 * poly * sizeof(u64),
+        { KernelTimer ktm(c, "k_copy_galois", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(tg.p, poly * sizeof(u64), perm.as<u64>() + poly, 2 * poly * sizeof(u64),
                                           poly * sizeof(u64), (size_t)batch, cudaMemcpyDeviceToDevice, c->stream)); }
-        { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)batch * 2 * poly * sizeof(u64), c->stream)); }
-        { KernelTimer ktm(c, "k_memcpy_d2d", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(out, 2 * poly * sizeof(u64), perm.p, 2 * poly * sizeof(u64),
+        { KernelTimer ktm(c, "k_copy_galois", 1); MOAI_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)batch * 2 * poly * sizeof(u64), c->stream)); }
+        { KernelTimer ktm(c, "k_copy_galois", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(out, 2 * poly * sizeof(u64), perm.p, 2 * poly * sizeof(u64),
                                           poly * sizeof(u64), (size_t)batch, cudaMemcpyDeviceToDevice, c->stream)); }
         switch_key(c, out, tg.as<u64>(), batch, limbs, ksk, key_kl);
     }

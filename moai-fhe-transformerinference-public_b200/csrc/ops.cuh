@@ -28,6 +28,10 @@ namespace moai
     void ew_multiply_scalar(Context *c, const u64 *ct, const u64 *h_consts, u64 *out, long long batch, int polys,
                             int limbs);
     void ew_add_scalar(Context *c, const u64 *ct, const u64 *h_consts, u64 *out, long long batch, int polys, int limbs);
+    // out = sum_j in[j] * k[j][l] over n_terms <= 8 batches; in[j] has in_limbs[j] >= limbs limbs per polynomial and
+    // only its first `limbs` are read; h_consts is [n_terms][limbs] (host)
+    void ew_lincomb_scalar(Context *c, int n_terms, const u64 *const *in, const int *in_limbs, const u64 *h_consts,
+                           u64 *out, long long batch, int polys, int limbs);
     void ew_multiply(Context *c, const u64 *a, const u64 *b, u64 *out3, long long batch, int limbs, bool accumulate,
                      bool b_broadcast = false);
     void ew_square(Context *c, const u64 *a, u64 *out3, long long batch, int limbs);

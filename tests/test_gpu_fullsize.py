@@ -29,6 +29,9 @@ NUM_BATCH = 256
 TOK = 5
 SCALE = 2.0 ** 46
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "layer0_activations.npz")
+# what the reference's own encrypted modules output for those activations (decrypted; oracle/_ref, real SEAL):
+# tests/golden/make_layer0_reference_outputs.py (N = 8192) and make_gelu_reference_fullsize.py (N = 65536)
+GOLDEN_REF = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "layer0_reference_decrypted.npz")
 
 
 @pytest.fixture(scope="module")
@@ -52,7 +55,8 @@ def env(pkg):
     mask = np.zeros(SLOTS, dtype=np.int32)
     for k in range(TOK):
         mask[k * NUM_BATCH] = 1                           # bias_vec(input_len = {5, 0, ...}), Batch_encode_encrypt.hpp:39-49
-    yield {"o": o, "be": be, "kg": kg, "boot": boot, "keys": keys, "mask": mask, "g": np.load(GOLDEN)}
+    yield {"o": o, "be": be, "kg": kg, "boot": boot, "keys": keys, "mask": mask, "g": np.load(GOLDEN),
+           "ref": np.load(GOLDEN_REF)}
     del keys, fast
     be.close()
 
@@ -206,12 +210,15 @@ def test_bootstrap_real_pairs_fullsize(pkg, env):
     assert err.max() < 1e-4
 
 
-@pytest.mark.parametrize("name,variant,tol_abs,tol_rel", [("ln1", 1, 2e-3, 1e-3), ("ln2", 2, 0.25, 0.1)])
-def test_layernorm_golden(pkg, env, name, variant, tol_abs, tol_rel):
-    """layernorm / layernorm2 (layernorm.hpp:157-547) on layer 0's residual sums vs real_self_output.csv /
-    real_final_output.csv.  The reference's own code is 4.4e-4 (ln1) and 0.13 max-abs / 5.7 % rel (ln2: its inverse
-    square root is a low-degree iteration) away from these CSVs; tolerances: ln1 2e-3 abs / 1e-3 rel, ln2 0.25 abs /
-    0.1 rel (rel = |err| / max(1, |expected|))."""
+@pytest.mark.parametrize("name,variant,tol_abs,tol_rel,tol_ref", [("ln1", 1, 2e-3, 1e-3, 1e-4), ("ln2", 2, 0.25, 0.1, 5e-3)])
+def test_layernorm_golden(pkg, env, name, variant, tol_abs, tol_rel, tol_ref):
+    """layernorm / layernorm2 (layernorm.hpp:157-547) on layer 0's residual sums.
+    (a) vs the REFERENCE'S decrypted output of the same module on the same activations (oracle/_ref, N = 8192):
+        rel <= 1e-4 (ln1) / 5e-3 (ln2), rel = |err| / max(1, |expected|) (the modules' forced scale resets make the
+        result depend on the primes, hence on the ring degree, at that level);
+    (b) vs real_self_output.csv / real_final_output.csv: the reference's own code is 4.5e-4 (ln1) and 0.13 max-abs /
+        5.7 % rel (ln2: its inverse square root is a low-degree iteration) away from these; tolerances ln1 2e-3 abs /
+        1e-3 rel, ln2 0.25 abs / 0.1 rel."""
     be, keys, g = env["be"], env["keys"], env["g"]
     x = encrypt_cols(env, pack_rows(g[name + "_in"]), 21)
     out, osc = be.layernorm(keys, x, SCALE, g[name + "_gamma"], g[name + "_beta"], env["mask"], variant=variant)
@@ -221,45 +228,80 @@ def test_layernorm_golden(pkg, env, name, variant, tol_abs, tol_rel):
     exp = g[name + "_out"]
     err = np.abs(got - exp)
     rel = (err / np.maximum(1.0, np.abs(exp))).max()
-    print("%s golden: max-abs %.3g, rel %.3g" % (name, err.max(), rel))
-    assert err.max() < tol_abs and rel < tol_rel
+    want = env["ref"][name + "_ref"]
+    rel_ref = (np.abs(got - want) / np.maximum(1.0, np.abs(want))).max()
+    print("%s golden: vs reference decrypted rel %.3g (max-abs %.3g); vs CSV max-abs %.3g, rel %.3g"
+          % (name, rel_ref, np.abs(got - want).max(), err.max(), rel))
+    assert rel_ref < tol_ref and err.max() < tol_abs and rel < tol_rel
 
 
 def test_gelu_golden(pkg, env):
-    """gelu_v2 (gelu_others.hpp:4-154) on all 3072 intermediate features of layer 0 vs real_intermediate_output.csv.
-    The reference's degree-24 polynomial is itself up to 0.03 away (inputs reach -15.4); tolerance 0.06 max-abs."""
-    be, keys, g = env["be"], env["keys"], env["g"]
+    """gelu_v2 (gelu_others.hpp:4-154) on all 3072 intermediate features of layer 0.
+    (a) vs the REFERENCE'S decrypted gelu_v2 output: every entry with |x| <= 9 against the N = 8192 run (2e-3), and the
+        17 columns of the N = 65536 run — all columns with an input beyond |x| = 9 plus the first eight — entry by entry
+        (2e-3).  The second set matters: gelu_v2's forced scale resets leave an error that depends on the primes and
+        that its degree-24 polynomial amplifies where |0.1 x| > 1 (reference at x = -14.7: 0.37 from the true GELU at
+        N = 65536, 0.08 at N = 8192), and a faithful implementation reproduces exactly that.
+    (b) vs real_intermediate_output.csv for |x| <= 9: 0.05 max-abs (the reference is up to 0.04 away there)."""
+    be, keys, g, ref = env["be"], env["keys"], env["g"], env["ref"]
     V = pack_rows(g["gelu_in"])
-    errs = []
+    got = np.zeros((TOK, 3072))
     for c0 in range(0, 3072, 256):
         x = encrypt_cols(env, V[c0:c0 + 256], 9)
         out, osc = be.gelu_v2(keys, x, SCALE)
         del x
         assert out.shape[2] == 2
-        got = slot_values(env, out, osc, VALID).real.T
-        errs.append(np.abs(got - g["gelu_out"][:, c0:c0 + 256]).max())
+        got[:, c0:c0 + 256] = slot_values(env, out, osc, VALID).real.T
         del out
-    print("gelu_v2 golden: max-abs %.3g" % max(errs))
-    assert max(errs) < 0.06
+    mod = np.abs(g["gelu_in"]) <= 9.0
+    e_ref = np.abs(got - ref["gelu_ref"])[mod].max()
+    e_csv = np.abs(got - g["gelu_out"])[mod].max()
+    cols = ref["gelu_cols65536"]
+    e_full = np.abs(got[:, cols] - ref["gelu_ref65536"]).max()
+    worst = np.abs(got - g["gelu_out"]).max()
+    print("gelu_v2 golden: |x| <= 9: vs reference decrypted (N = 8192) %.3g, vs CSV %.3g; the %d extreme columns vs the "
+          "reference at N = 65536: %.3g (they are up to %.3g from the true GELU, as the reference is)"
+          % (e_ref, e_csv, len(cols), e_full, worst))
+    assert e_ref < 2e-3 and e_full < 2e-3 and e_csv < 0.05
+
+
+def softmax_scale_drift(q, s0=SCALE):
+    """The reference's modules overwrite the scale after rescaling (`x.scale() = scale`).  The value a
+    ciphertext decrypts to is then off by (true scale / 2^46), a factor fixed by the primes.  For softmax_boot:
+    f_exp (exp + mask, softmax.hpp:9-47, 407-467), f_inv (inverse, :49-82, reset at :545) and f_out (:565-576)."""
+    lv = 12
+    s = s0 * s0 / q[lv]
+    lv -= 1
+    for _ in range(7):
+        s = s * s / q[lv]
+        lv -= 1
+    s = s * s / q[lv]
+    f_exp = s / s0
+    sy, sr, ly = s0, s0, 20
+    for _ in range(16):
+        sy = sy * sy / q[ly]
+        ly -= 1
+        sr = sr * sy / q[ly]
+    return f_exp, sr / s0, (s0 * s0 / q[ly - 1]) / s0
 
 
 def test_softmax_golden(pkg, env):
-    """softmax_boot (softmax.hpp:308-581, one bootstrapping inside) on layer 0's scores, all 12 heads, vs
-    aftsoftmax.csv (true softmax).  The module computes exp as (1 + x / 128)^128 after subtracting the layer's
-    constant 7.5 (:324), bootstraps the row sums and normalises with a 16-step Goldschmidt inverse; the float64 model of
-    exactly that is evaluated beside it.  With these scores the row sums of exp(S - 7.5) are as small as 1e-3, and the
-    bootstrapping error eps on a row sum (8e-6 max-abs at this size, test_bootstrap_fullsize_per_phase) comes back
-    multiplied by 1 / sum: |P - model| <= eps / sum per row.  The reference behaves the same way (oracle/_ref at
-    N = 8192, eps = 3e-6: 4.6e-4 ... 1.1e-3 from the model, 1.4e-2 ... 2.0e-2 from the CSV on heads 0, 1, 2, 5).
-    Tolerances: per row 1e-3 + 2e-5 / sum against the model; 4e-2 max-abs against the CSV (the (1 + x/128)^128
-    approximation of exp itself is 1.4e-2 ... 2e-2 away)."""
+    """softmax_boot (softmax.hpp:308-581, one bootstrapping inside) on layer 0's scores, all 12 heads.
+    (a) vs the float64 model of exactly what the module computes: exp as (1 + (x - 7.5) / 128)^128 (:324), a 16-step
+        Goldschmidt inverse of the bootstrapped row sums, and the forced scale resets, which at this ring's primes
+        inflate every probability by f_inv = 1 + 9.2e-3 (1 + 1.1e-3 at N = 8192: the reference's decrypted output
+        from oracle/_ref matches the same model with its own primes to 1.1e-4).  Per row the bootstrapping error on the
+        row sum (8e-6 at this size) comes back multiplied by 1 / sum (sums are as small as 2e-3):
+        tolerance 2e-4 + 2e-5 / sum.
+    (b) vs aftsoftmax.csv (true softmax): 4e-2 max-abs; the reference is 1.2e-2 ... 2.3e-2 away (its exp)."""
     be, kg, boot, keys, g = env["be"], env["kg"], env["boot"], env["keys"], env["g"]
+    f_exp, f_inv, f_out = softmax_scale_drift([float(p) for p in be.primes])
     worst_csv, worst_model, worst_ratio = 0.0, 0.0, 0.0
     for h in range(12):
         S = g["QKT"][:, 5 * h:5 * h + 5]
         want = g["aftsoftmax"][:, 5 * h:5 * h + 5]
         E = (1 + (S - 7.5) / 128.0) ** 128
-        model = E / (E.sum(axis=1, keepdims=True) + 1e-5)
+        model = E * f_exp / ((E * f_exp).sum(axis=1, keepdims=True) + 1e-5) * f_inv * f_out
         V = np.zeros((128, SLOTS))
         for i in range(128):
             for k in range(TOK):
@@ -277,10 +319,11 @@ def test_softmax_golden(pkg, env):
                     P[k, (k + i) % 128] = got[i, k]
         worst_csv = max(worst_csv, np.abs(P - want).max())
         worst_model = max(worst_model, np.abs(P - model).max())
-        row_tol = 1e-3 + 2e-5 / E.sum(axis=1)
+        row_tol = 2e-4 + 2e-5 / E.sum(axis=1)
         worst_ratio = max(worst_ratio, (np.abs(P - model).max(axis=1) / row_tol).max())
-    print("softmax_boot golden (12 heads): max-abs vs float64 model %.3g (worst row at %.2f of its bound "
-          "1e-3 + 2e-5 / sum), vs aftsoftmax.csv %.3g" % (worst_model, worst_ratio, worst_csv))
+    print("softmax_boot golden (12 heads): max-abs vs the float64 model %.3g (worst row at %.2f of its bound "
+          "2e-4 + 2e-5 / sum; scale drift f_inv - 1 = %.3g), vs aftsoftmax.csv %.3g"
+          % (worst_model, worst_ratio, f_inv - 1, worst_csv))
     assert worst_ratio < 1.0 and worst_csv < 4e-2
 
 

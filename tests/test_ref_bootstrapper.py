@@ -115,3 +115,33 @@ def test_golden_layer0_activations_are_consistent():
     ge = 0.5 * gi * (1 + np.vectorize(math.erf)(gi / math.sqrt(2)))
     assert np.abs(ge - g["gelu_out"]).max() < 1e-5
     assert g["selfoutput_linear"].shape == (5, 768)
+
+
+def test_softmax_scale_drift_model_matches_reference_decrypted_golden():
+    """tests/golden/layer0_reference_decrypted.npz holds what the reference's softmax_boot decrypts to for layer 0's
+    scores (oracle/_ref, N = 8192).  The float64 model used by the full-size GPU gate — (1 + x/128)^128, Goldschmidt
+    inverse, and the forced scale resets turned into the factors of softmax_scale_drift() for THAT ring's primes —
+    reproduces it to 2e-4 (without the drift factors the gap is 1.1e-3), which is what licenses using the same model
+    with the N = 65536 primes on the GPU."""
+    from oracle import Oracle, MOAI_BITS
+    from test_gpu_fullsize import softmax_scale_drift
+    g = np.load(os.path.join(HERE, "golden", "layer0_activations.npz"))
+    ref = np.load(os.path.join(HERE, "golden", "layer0_reference_decrypted.npz"))
+    q = [float(x) for x in Oracle(13, MOAI_BITS).q]
+    f_exp, f_inv, f_out = softmax_scale_drift(q)
+    assert 1e-3 < f_inv - 1 < 1.3e-3
+    worst, worst_plain = 0.0, 0.0
+    for h in range(12):
+        S = g["QKT"][:, 5 * h:5 * h + 5]
+        E = (1 + (S - 7.5) / 128.0) ** 128
+        model = E * f_exp / ((E * f_exp).sum(axis=1, keepdims=True) + 1e-5) * f_inv * f_out
+        plain = E / (E.sum(axis=1, keepdims=True) + 1e-5)
+        got = ref["softmax_ref"][:, 5 * h:5 * h + 5]
+        worst = max(worst, np.abs(got - model).max())
+        worst_plain = max(worst_plain, np.abs(got - plain).max())
+    assert worst < 2e-4 and 5e-4 < worst_plain < 2e-3
+    # and the other reference-decrypted fixtures sit where the test docstrings say they do
+    assert np.abs(ref["ln1_ref"] - g["ln1_out"]).max() < 5e-4
+    assert 0.1 < np.abs(ref["ln2_ref"] - g["ln2_out"]).max() < 0.15
+    assert np.abs(ref["gelu_ref"] - g["gelu_out"]).max() < 0.09
+    assert 1.0 < np.abs(ref["gelu_ref65536"] - g["gelu_out"][:, ref["gelu_cols65536"]]).max() < 1.2

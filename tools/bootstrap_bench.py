@@ -71,6 +71,8 @@ def main():
     dump = be.profile_dump()
     phases = {k: round(v[0] / args.batch, 2) for k, v in dump.items() if k.startswith("boot_")}
     phases["allocator"] = {k: (round(v[0], 1), v[1]) for k, v in dump.items() if k.startswith("alloc_")}
+    # live per-kernel device time of that call (deferred CUDA-event pairs around every launch): [ms, units]
+    kernels = {k: [round(v[0], 2), v[1]] for k, v in sorted(dump.items(), key=lambda kv: -kv[1][0]) if k.startswith("k_")}
     be.profile(False)
     ms = e0.elapsed_time(e1) / args.iters
     per_ct = ms / args.batch
@@ -81,6 +83,7 @@ def main():
                       "projected_bootstrap_s_per_layer": round(per_layer_s, 1),
                       "projected_bootstrap_s_per_input_12_layers": round(per_layer_s * 12 / 256, 2),
                       "reference_bootstrap_s_per_input_12_layers": 384.8,
+                      "kernels_ms_one_call": kernels,
                       "gpu_mem_GiB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}))
     be.close()
 
