@@ -64,6 +64,23 @@ int32_t moai_keys_add_galois(moai_keys *keys, uint32_t galois_elt, const uint64_
 int32_t moai_key_prepare(moai_context *ctx, const uint64_t *ksk_in, uint32_t galois_elt, int32_t max_limbs,
                          int32_t pre_permute, uint64_t *ksk_out);
 int32_t moai_keys_add_galois_fast(moai_keys *keys, uint32_t galois_elt, const uint64_t *ksk_pre, int32_t key_limbs);
+/* Grouped-digit keys (csrc/ksgroup.hpp): the fast-mode replacement of SEAL's one-digit-per-prime key switch
+ * (S/evaluator.cpp:2724-3021, l (l + 1) forward NTTs at l limbs).  K_G = sum_{J in G} K_J of a stock SEAL key is a
+ * hybrid key-switching key for the special modulus P' = p * (the k_extra top data primes, unused by a ciphertext at
+ * l <= L - k_extra limbs): digits * (l + k_extra + 1) NTTs with digits ~ l / (k_extra + 1).  Same plaintext, different
+ * (negligible) noise; derived on the device from the keys the client already ships.
+ *   moai_ksg_best_extra      the k_extra the library's cost model prefers at `limbs` (0 = SEAL's digits)
+ *   moai_ksg_key_shape       layout of a grouped key: [digits][2][key_limbs = max_limbs + k_extra + 1][N]
+ *   moai_key_prepare_grouped SEAL-layout key -> grouped key usable at every level <= max_limbs (pre_permute as in
+ *                            moai_key_prepare; 0 for the relinearisation key)
+ *   moai_keys_add_grouped    registers it: galois_elt = 0 for a relinearisation key.  Several variants per element
+ *                            may coexist; every key switch picks the cheapest one that covers its level.          */
+int32_t moai_ksg_best_extra(moai_context *ctx, int32_t limbs, int32_t *k_extra);
+int32_t moai_ksg_key_shape(moai_context *ctx, int32_t k_extra, int32_t max_limbs, int32_t *digits, int32_t *key_limbs);
+int32_t moai_key_prepare_grouped(moai_context *ctx, const uint64_t *ksk_in, uint32_t galois_elt, int32_t k_extra,
+                                 int32_t max_limbs, int32_t pre_permute, uint64_t *ksk_out);
+int32_t moai_keys_add_grouped(moai_keys *keys, uint32_t galois_elt, const uint64_t *ksk_grouped, int32_t k_extra,
+                              int32_t max_limbs);
 /* SEAL-exact rotations with a level-truncated key (moai_key_prepare with pre_permute = 0): the residues are
  * SEAL's bit for bit — a key switch at l limbs never reads digits or limbs beyond l — at (L/35)^2 of the
  * memory; a rotation above L limbs with such a key is rejected.                                    */
@@ -118,6 +135,16 @@ int32_t moai_bootstrapper_destroy(moai_bootstrapper *b);
  * call before moai_bootstrapper_required_steps and register the keys with moai_keys_add_galois_fast */
 int32_t moai_bootstrapper_set_hoisting(moai_bootstrapper *b, int32_t on);
 int32_t moai_bootstrapper_required_steps(moai_bootstrapper *b, int32_t *steps, int32_t capacity, int32_t *count);
+/* the same steps with the level (limb count) each is used at; step 0 = the complex conjugation
+ * (Evaluator::complex_conjugate, S/evaluator.cpp:2635-2657): what a level-truncated or grouped key must cover */
+int32_t moai_bootstrapper_required_step_levels(moai_bootstrapper *b, int32_t *steps, int32_t *limbs, int32_t capacity,
+                                               int32_t *count);
+/* Evaluator::relinearize (S/evaluator.cpp:1345-1400) / complex_conjugate through a key handle: SEAL-layout key, or the
+ * cheapest fast-mode key registered for the level */
+int32_t moai_relinearize_keys(moai_context *ctx, moai_keys *keys, const uint64_t *in3, uint64_t *out2, int64_t batch,
+                              int32_t limbs);
+int32_t moai_complex_conjugate_keys(moai_context *ctx, moai_keys *keys, const uint64_t *in, uint64_t *out, int64_t batch,
+                                    int32_t limbs);
 int32_t moai_bootstrap(moai_context *ctx, moai_bootstrapper *b, moai_keys *keys, const uint64_t *in, int64_t batch,
                        double scale, uint64_t *out, int32_t *out_limbs, double *out_scale);
 /* Bootstrapping of REAL-slot messages (all of MOAI's activations), two per bootstrapping: z = a + i b is one

@@ -386,11 +386,12 @@ class Backend:
         return out[0] if single else out
 
     # ---- evaluation keys + MOAI modules (B4-B9)
-    def make_keys(self, relin=None, galois=None, galois_fast=None):
+    def make_keys(self, relin=None, galois=None, galois_fast=None, grouped=None):
         """relin: device key tensor; galois: dict galois_elt -> device key tensor (SEAL layout,
         bit-exact rotations); galois_fast: dict galois_elt -> tensor or list of tensors produced by
-        key_prepare(pre_permute=True), shaped [L, 2, L + 1, n] (hoisted fast-mode rotations).  The
-        returned handle keeps the tensors alive."""
+        key_prepare(pre_permute=True), shaped [L, 2, L + 1, n] (hoisted fast-mode rotations);
+        grouped: dict galois_elt (0 = relinearisation key) -> list of GroupedKey from key_prepare_grouped.
+        The returned handle keeps the tensors alive."""
         h = C.c_void_p()
         self._chk(self.lib.moai_keys_create(self.h, C.byref(h)))
         keep = []
@@ -407,7 +408,58 @@ class Backend:
             for t in (ts if isinstance(ts, (list, tuple)) else [ts]):
                 self._chk(self.lib.moai_keys_add_galois_fast(h, C.c_uint32(elt), _ptr(t), C.c_int32(t.shape[2])))
                 keep.append(t)
+        for elt, gks in (grouped or {}).items():
+            for gk in (gks if isinstance(gks, (list, tuple)) else [gks]):
+                self._chk(self.lib.moai_keys_add_grouped(h, C.c_uint32(elt), _ptr(gk.t), C.c_int32(gk.k_extra),
+                                                         C.c_int32(gk.max_limbs)))
+                keep.append(gk.t)
         return _KeysHandle(self.lib, h, keep)
+
+    def ksg_best_extra(self, limbs):
+        """Extra primes the library's cost model prefers for a key switch at `limbs` (0 = SEAL's digits)."""
+        k = C.c_int32()
+        self._chk(self.lib.moai_ksg_best_extra(self.h, C.c_int32(limbs), C.byref(k)))
+        return k.value
+
+    def ksg_key_shape(self, k_extra, max_limbs):
+        d, kl = C.c_int32(), C.c_int32()
+        self._chk(self.lib.moai_ksg_key_shape(self.h, C.c_int32(k_extra), C.c_int32(max_limbs), C.byref(d), C.byref(kl)))
+        return d.value, kl.value
+
+    def ksg_plan(self, levels):
+        """Grouped-key variants that give every level in `levels` its preferred digit layout: dict k_extra ->
+        max_limbs (one key per distinct k, truncated to the highest level that wants it; levels that prefer SEAL's
+        digits are left to the SEAL-layout / pre-permuted key)."""
+        plan = {}
+        for lv in levels:
+            k = self.ksg_best_extra(lv)
+            if k:
+                plan[k] = max(plan.get(k, 0), lv)
+        return plan
+
+    def random_grouped_key(self, k_extra, max_limbs, generator=None):
+        """Uniformly random residues in the layout of a grouped key (timing runs: a key switch's time does not depend
+        on key values)."""
+        d, gkl = self.ksg_key_shape(k_extra, max_limbs)
+        t = self.torch.empty((d, 2, gkl, self.n), dtype=self.torch.int64, device=self.device)
+        ids = list(range(max_limbs)) + list(range(self.kl - 1 - k_extra, self.kl - 1)) + [self.kl - 1]
+        for j, pid in enumerate(ids):
+            t[:, :, j, :] = self.torch.randint(0, int(self.primes[pid]), (d, 2, self.n), generator=generator,
+                                               device=self.device, dtype=self.torch.int64)
+        return GroupedKey(t, k_extra, max_limbs)
+
+    def key_prepare_grouped(self, ksk, elt, max_limbs, k_extra=None, pre_permute=True):
+        """SEAL-layout key [kl-1, 2, kl, n] -> grouped-digit key [digits, 2, max_limbs + k + 1, n] for the fast-mode
+        key switch at levels <= max_limbs (include/moai_b200_modules.h); elt = 0 with pre_permute=False for the
+        relinearisation key.  Returns None when the cost model prefers SEAL's digits (k = 0) at this level."""
+        k = self.ksg_best_extra(max_limbs) if k_extra is None else k_extra
+        if k == 0:
+            return None
+        d, kl = self.ksg_key_shape(k, max_limbs)
+        out = self.empty(d, 2, kl, self.n)
+        self._chk(self.lib.moai_key_prepare_grouped(self.h, _ptr(ksk), C.c_uint32(elt), C.c_int32(k), C.c_int32(max_limbs),
+                                                    C.c_int32(int(pre_permute)), _ptr(out)))
+        return GroupedKey(out, k, max_limbs)
 
     def key_prepare(self, ksk, elt, max_limbs=None, pre_permute=True):
         """SEAL-layout Galois key [kl-1, 2, kl, n] -> level-truncated (and pre-permuted) key
@@ -425,6 +477,18 @@ class Backend:
         out = self.torch.empty_like(a)
         self._chk(self.lib.moai_rotate_vector(self.h, keys.h, _ptr(a), _ptr(out), C.c_int64(bt), C.c_int32(l),
                                               C.c_int32(steps)))
+        return out
+
+    def relinearize_keys(self, keys, a3):
+        bt, p, l, n = a3.shape
+        out = self.empty(bt, 2, l, n)
+        self._chk(self.lib.moai_relinearize_keys(self.h, keys.h, _ptr(a3), _ptr(out), C.c_int64(bt), C.c_int32(l)))
+        return out
+
+    def complex_conjugate_keys(self, keys, a):
+        bt, p, l, n = a.shape
+        out = self.torch.empty_like(a)
+        self._chk(self.lib.moai_complex_conjugate_keys(self.h, keys.h, _ptr(a), _ptr(out), C.c_int64(bt), C.c_int32(l)))
         return out
 
     def rotate_many(self, keys, a, steps):
@@ -530,6 +594,17 @@ class Bootstrapper:
         self.be._chk(self.be.lib.moai_bootstrapper_required_steps(self.h, buf, C.c_int32(1024), C.byref(cnt)))
         return [int(buf[i]) for i in range(cnt.value)]
 
+    def required_step_levels(self):
+        """dict step -> sorted list of levels (limb counts) the rotation key is used at; step 0 = conjugation."""
+        cap = 1024
+        st, lv = (C.c_int32 * cap)(), (C.c_int32 * cap)()
+        cnt = C.c_int32()
+        self.be._chk(self.be.lib.moai_bootstrapper_required_step_levels(self.h, st, lv, C.c_int32(cap), C.byref(cnt)))
+        out = {}
+        for i in range(cnt.value):
+            out.setdefault(st[i], []).append(lv[i])
+        return {k: sorted(set(v)) for k, v in out.items()}
+
     def bootstrap_3(self, keys, x, scale):
         """x: [batch, 2, 1, n] at chain_index 0 -> ([batch, 2, total_limbs - 14, n], final_scale)."""
         be = self.be
@@ -630,6 +705,13 @@ class Bootstrapper:
             self.be.lib.moai_bootstrapper_destroy(self.h)
         except Exception:
             pass
+
+
+class GroupedKey:
+    """A grouped-digit key-switching key on the device (csrc/ksgroup.hpp)."""
+
+    def __init__(self, t, k_extra, max_limbs):
+        self.t, self.k_extra, self.max_limbs = t, k_extra, max_limbs
 
 
 class _KeysHandle:

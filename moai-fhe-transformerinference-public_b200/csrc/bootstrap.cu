@@ -372,6 +372,36 @@ namespace moai
         return std::vector<int>(steps.begin(), steps.end());
     }
 
+    std::vector<std::pair<int, int>> Bootstrapper::required_step_levels() const
+    {
+        const int n = slots();
+        std::set<std::pair<int, int>> out;
+        for (int dir = 0; dir < 2; dir++)
+        {
+            for (int s = 0; s < 3; s++)
+            {
+                const LinearStage &st = dir == 0 ? cts_[s] : stc_[s];
+                for (int j : st.baby)
+                {
+                    if (j)
+                    {
+                        out.insert({ ((j * st.stride) % n + n) % n, st.limbs });
+                    }
+                }
+                for (int i : st.giants)
+                {
+                    if (i)
+                    {
+                        out.insert({ (int)(((long long)i * st.giant * st.stride % n + n) % n), st.limbs });
+                    }
+                }
+            }
+        }
+        out.insert({ 0, cts_[2].limbs - 1 });       // conjugation after CoeffToSlot
+        out.insert({ 0, prm.total_limbs - 14 });    // separation of the two real-slot messages
+        return std::vector<std::pair<int, int>>(out.begin(), out.end());
+    }
+
     void Bootstrapper::encode_stage(const Evaluator &ev, LinearStage &st, double pt_scale)
     {
         const int n = slots();

@@ -69,6 +69,8 @@ namespace moai
         // re-plan the linear stages for hoisted (pre-permuted-key) rotations; call before required_steps()
         void set_hoisting(bool on);
         std::vector<int> required_steps() const; // rotation steps (normalised to [0, slots)) the BSGS plans use
+        // (step, limbs) for every rotation key and level it is used at; step 0 = the complex conjugation
+        std::vector<std::pair<int, int>> required_step_levels() const;
         // in: batch of size-2 ciphertexts at 1 limb (chain_index 0); returns them at
         // total_limbs - 14 limbs with scale final_scale
         // stop_after (diagnostics, moai_bootstrap_phase_debug): 0 = the whole bootstrapping; 1 = return after ModRaise

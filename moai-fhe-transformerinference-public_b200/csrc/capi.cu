@@ -596,6 +596,54 @@ extern "C"
         API_END
     }
 
+    // ---- grouped-digit keys (csrc/ksgroup.hpp) ----------------------------------------------------
+    int32_t moai_ksg_best_extra(moai_context *ctx, int32_t limbs, int32_t *k_extra)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(k_extra && limbs >= 1 && limbs <= c->kl - 1, "bad argument");
+        *k_extra = ksg_best_k(c, limbs);
+        API_END
+    }
+
+    int32_t moai_ksg_key_shape(moai_context *ctx, int32_t k_extra, int32_t max_limbs, int32_t *digits, int32_t *key_limbs)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(digits && key_limbs, "null argument");
+        *digits = ksg_digits(c, k_extra, max_limbs);
+        *key_limbs = ksg_key_kl(k_extra, max_limbs);
+        API_END
+    }
+
+    int32_t moai_key_prepare_grouped(moai_context *ctx, const uint64_t *ksk_in, uint32_t galois_elt, int32_t k_extra,
+                                     int32_t max_limbs, int32_t pre_permute, uint64_t *ksk_out)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(ksk_in && ksk_out, "null argument");
+        ksg_key_prepare(c, CU(ksk_in), galois_elt, k_extra, max_limbs, pre_permute != 0, U(ksk_out));
+        API_END
+    }
+
+    int32_t moai_keys_add_grouped(moai_keys *keys, uint32_t galois_elt, const uint64_t *ksk_grouped, int32_t k_extra,
+                                  int32_t max_limbs)
+    {
+        API_BEGIN
+        MOAI_REQUIRE(keys && ksk_grouped, "null argument");
+        MOAI_REQUIRE(k_extra >= 1 && max_limbs >= 1 && max_limbs + k_extra <= keys->kl - 1, "bad grouped-key shape");
+        const KeyRef ref{ CU(ksk_grouped), ksg_key_kl(k_extra, max_limbs), k_extra };
+        if (galois_elt == 0)
+        {
+            keys->k.relin_fast.push_back(ref);
+        }
+        else
+        {
+            keys->k.galois_fast[galois_elt].push_back(ref);
+        }
+        API_END
+    }
+
     static const Keys &getk(moai_keys *keys)
     {
         if (!keys)
@@ -785,6 +833,52 @@ extern "C"
             steps[i] = v[i];
         }
         *count = (int32_t)v.size();
+        API_END
+    }
+
+    int32_t moai_bootstrapper_required_step_levels(moai_bootstrapper *b, int32_t *steps, int32_t *limbs, int32_t capacity,
+                                                   int32_t *count)
+    {
+        API_BEGIN
+        MOAI_REQUIRE(b && steps && limbs && count, "null argument");
+        auto v = b->b->required_step_levels();
+        MOAI_REQUIRE((int)v.size() <= capacity, "steps buffer too small");
+        for (size_t i = 0; i < v.size(); i++)
+        {
+            steps[i] = v[i].first;
+            limbs[i] = v[i].second;
+        }
+        *count = (int32_t)v.size();
+        API_END
+    }
+
+    int32_t moai_relinearize_keys(moai_context *ctx, moai_keys *keys, const uint64_t *in3, uint64_t *out2, int64_t batch,
+                                  int32_t limbs)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(in3 && out2, "null argument");
+        check_shape(c, batch, 3, limbs);
+        Evaluator ev(c);
+        Ct r = ev.relinearize(ev.wrap(const_cast<u64 *>(CU(in3)), batch, 3, limbs, 1.0), getk(keys));
+        MOAI_CUDA_CHECK(cudaMemcpyAsync(out2, r.d, (size_t)batch * 2 * limbs * c->n * sizeof(u64), cudaMemcpyDeviceToDevice,
+                                        c->stream));
+        MOAI_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        API_END
+    }
+
+    int32_t moai_complex_conjugate_keys(moai_context *ctx, moai_keys *keys, const uint64_t *in, uint64_t *out, int64_t batch,
+                                        int32_t limbs)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(in && out && in != out, "null or aliased argument");
+        check_shape(c, batch, 2, limbs);
+        Evaluator ev(c);
+        Ct r = ev.complex_conjugate(ev.wrap(const_cast<u64 *>(CU(in)), batch, 2, limbs, 1.0), getk(keys));
+        MOAI_CUDA_CHECK(cudaMemcpyAsync(out, r.d, (size_t)batch * 2 * limbs * c->n * sizeof(u64), cudaMemcpyDeviceToDevice,
+                                        c->stream));
+        MOAI_CUDA_CHECK(cudaStreamSynchronize(c->stream));
         API_END
     }
 

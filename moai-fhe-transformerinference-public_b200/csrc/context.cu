@@ -487,6 +487,7 @@ namespace moai
         {
             cudaFree(kv.second);
         }
+        ksg_release(this);
     }
 
     uint32_t Context::elt_from_step(int step) const

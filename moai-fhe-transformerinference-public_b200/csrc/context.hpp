@@ -126,6 +126,9 @@ namespace moai
 
         std::mutex galois_mu;
         std::map<uint32_t, uint32_t *> galois_tables; // elt -> device [n]
+        // grouped-digit key switching (csrc/ksgroup.cu): conversion tables per (extra primes, level)
+        std::mutex ksg_mu;
+        std::map<std::pair<int, int>, void *> ksg_cache;
 
         ~Context();
         const uint32_t *galois_table(uint32_t elt);
@@ -133,6 +136,7 @@ namespace moai
     };
 
     Context *context_create(int log_n, const u64 *primes, int kl, int device);
+    void ksg_release(Context *c); // csrc/ksgroup.cu
 
     // RAII device timer around a kernel (only active when Context::profiling is set): records
     // CUDA events on the launching stream and accumulates the elapsed time under `name`.

@@ -301,9 +301,10 @@ namespace moai
     {
         // S/evaluator.cpp:1345-1400
         EV_REQUIRE(a3.size == 3, "relinearize expects a size-3 ciphertext");
-        EV_REQUIRE(k.relin.p != nullptr, "not enough relinearization keys");
+        const KeyRef *rk = k.relin_at(c, a3.limbs);
+        EV_REQUIRE(rk != nullptr, "not enough relinearization keys");
         Ct r = alloc(a3.batch, 2, a3.limbs, a3.scale);
-        moai::relinearize(c, a3.d, r.d, a3.batch, a3.limbs, k.relin.p, k.relin.key_kl);
+        moai::relinearize(c, a3.d, r.d, a3.batch, a3.limbs, rk->p, rk->key_kl, rk->k_extra);
         return r;
     }
 
@@ -346,7 +347,7 @@ namespace moai
             apply_galois(c, a.d, r.d, a.batch, a.limbs, elt, it->second.p, it->second.key_kl);
             return r;
         }
-        if (const KeyRef *fk = k.fast(elt, a.limbs))
+        if (const KeyRef *fk = k.fast(c, elt, a.limbs))
         {
             return rotate_fast(a, elt, *fk);
         }
@@ -383,7 +384,7 @@ namespace moai
         auto it = k.galois.find(elt);
         if (it == k.galois.end())
         {
-            const KeyRef *fk = k.fast(elt, a.limbs);
+            const KeyRef *fk = k.fast(c, elt, a.limbs);
             EV_REQUIRE(fk != nullptr, "Galois key not present");
             return rotate_fast(a, elt, *fk);
         }
@@ -395,14 +396,22 @@ namespace moai
     // ---------------------------------------------------------------- hoisted rotations (fast mode)
     bool Evaluator::has_fast_key(int steps, int limbs, const Keys &k) const
     {
-        return steps == 0 || k.fast(c->elt_from_step(steps), limbs) != nullptr;
+        return steps == 0 || k.fast(c, c->elt_from_step(steps), limbs) != nullptr;
     }
 
-    Hoisted Evaluator::hoist(const Ct &a) const
+    Hoisted Evaluator::hoist(const Ct &a, int k_extra) const
     {
         EV_REQUIRE(a.size == 2, "encrypted size must be 2");
         Hoisted h;
         h.src = a;
+        h.k_extra = k_extra;
+        if (k_extra > 0)
+        {
+            h.ext = std::make_shared<DevBuf>((size_t)a.batch * ksg_ext_bytes_per_ct(c, a.limbs, k_extra), c->stream);
+            ksg_decompose(c, a.d + (size_t)a.limbs * n(), a.batch, a.limbs, k_extra, reinterpret_cast<u64 *>(h.ext->p),
+                          2LL * a.limbs * (long long)n(), 3);
+            return h;
+        }
         h.ext = std::make_shared<DevBuf>((size_t)a.batch * ks_ext_bytes_per_ct(c, a.limbs), c->stream);
         ks_decompose(c, a.d + (size_t)a.limbs * n(), a.batch, a.limbs, reinterpret_cast<u64 *>(h.ext->p),
                      2LL * a.limbs * (long long)n());
@@ -417,9 +426,16 @@ namespace moai
             return a;
         }
         const uint32_t elt = c->elt_from_step(steps);
-        const KeyRef *fk = k.fast(elt, a.limbs);
+        const KeyRef *fk = k.fast(c, elt, a.limbs, h.k_extra);
         EV_REQUIRE(fk != nullptr, "pre-permuted Galois key not present");
         Ct r = alloc(a.batch, 2, a.limbs, a.scale);
+        if (h.k_extra > 0)
+        {
+            u64 *outp = r.d;
+            ksg_rotate_hoisted_multi(c, a.d, reinterpret_cast<const u64 *>(h.ext->p), a.batch, a.limbs, h.k_extra, 1, &elt,
+                                     &fk->p, &fk->key_kl, &outp);
+            return r;
+        }
         moai::rotate_hoisted(c, a.d, reinterpret_cast<const u64 *>(h.ext->p), a.batch, a.limbs, elt, fk->p, fk->key_kl,
                              r.d);
         return r;
@@ -428,7 +444,7 @@ namespace moai
     Ct Evaluator::rotate_fast(const Ct &a, uint32_t elt, const KeyRef &key) const
     {
         Ct r = alloc(a.batch, 2, a.limbs, a.scale);
-        rotate_prepermuted(c, a.d, a.batch, a.limbs, elt, key.p, key.key_kl, r.d);
+        rotate_prepermuted(c, a.d, a.batch, a.limbs, elt, key.p, key.key_kl, r.d, key.k_extra);
         return r;
     }
 
@@ -450,16 +466,48 @@ namespace moai
             }
             return out;
         }
+        // all rotations share one decomposition, hence one digit layout: the cheapest number of extra primes for
+        // which EVERY step has a key (0 = SEAL's per-prime digits)
+        int kx = -1;
+        {
+            double best_cost = 0;
+            for (int cand = 0; a.limbs + cand <= c->kl - 1; cand++)
+            {
+                bool ok = true;
+                for (int s : steps)
+                {
+                    ok = ok && (s == 0 || k.fast(c, c->elt_from_step(s), a.limbs, cand) != nullptr);
+                }
+                const double cost = ok ? ksg_cost(c, a.limbs, cand) : 0;
+                if (ok && (kx < 0 || cost < best_cost))
+                {
+                    kx = cand;
+                    best_cost = cost;
+                }
+            }
+        }
+        if (kx < 0) // keys exist for every step, but with different digit layouts
+        {
+            for (size_t i = 0; i < steps.size(); i++)
+            {
+                out[i] = rotate_vector(a, steps[i], k);
+            }
+            return out;
+        }
         for (size_t i = 0; i < steps.size(); i++)
         {
             out[i] = steps[i] == 0 ? a : alloc(a.batch, 2, a.limbs, a.scale);
         }
         // the decomposition of a chunk is shared by all rotations; ~4 GiB of extended digits at a time
-        const long long chunk = ks_chunk(c, a.limbs, a.batch, ks_ext_budget());
+        long long chunk = ks_chunk(c, a.limbs, a.batch, ks_ext_budget());
+        if (kx > 0)
+        {
+            chunk = std::max<long long>(1, std::min<long long>(a.batch, (long long)(ks_ext_budget() / ksg_ext_bytes_per_ct(c, a.limbs, kx))));
+        }
         for (long long b0 = 0; b0 < a.batch; b0 += chunk)
         {
             const long long nb = std::min(chunk, a.batch - b0);
-            Hoisted h = hoist(view(a, b0, nb));
+            Hoisted h = hoist(view(a, b0, nb), kx);
             const u64 *extp = reinterpret_cast<const u64 *>(h.ext->p);
             std::vector<size_t> todo;
             for (size_t i = 0; i < steps.size(); i++)
@@ -470,7 +518,7 @@ namespace moai
                 }
             }
             size_t g0 = 0;
-            if (ks_multi_enabled(c, a.limbs))
+            if (kx > 0 || ks_multi_enabled(c, a.limbs))
             {
                 // up to KSM_R rotations share one pass over the extended digits
                 for (; g0 < todo.size(); g0 += KSM_R)
@@ -484,19 +532,26 @@ namespace moai
                     {
                         const size_t i = todo[g0 + r];
                         elts[r] = c->elt_from_step(steps[i]);
-                        const KeyRef *fk = k.fast(elts[r], a.limbs);
+                        const KeyRef *fk = k.fast(c, elts[r], a.limbs, kx);
                         kp[r] = fk->p;
                         kkl[r] = fk->key_kl;
                         outs[r] = out[i].d + (size_t)b0 * 2 * a.limbs * n();
                     }
-                    rotate_hoisted_multi(c, h.src.d, extp, nb, a.limbs, cnt, elts, kp, kkl, outs);
+                    if (kx > 0)
+                    {
+                        ksg_rotate_hoisted_multi(c, h.src.d, extp, nb, a.limbs, kx, cnt, elts, kp, kkl, outs);
+                    }
+                    else
+                    {
+                        rotate_hoisted_multi(c, h.src.d, extp, nb, a.limbs, cnt, elts, kp, kkl, outs);
+                    }
                 }
             }
             for (; g0 < todo.size(); g0++)
             {
                 const size_t i = todo[g0];
                 const uint32_t elt = c->elt_from_step(steps[i]);
-                const KeyRef *fk = k.fast(elt, a.limbs);
+                const KeyRef *fk = k.fast(c, elt, a.limbs, kx);
                 moai::rotate_hoisted(c, h.src.d, extp, nb, a.limbs, elt, fk->p, fk->key_kl,
                                      out[i].d + (size_t)b0 * 2 * a.limbs * n());
             }

@@ -10,6 +10,7 @@
 #pragma once
 #include "ntt.cuh"
 #include "ops.cuh"
+#include "ksgroup.hpp"
 #include <cmath>
 #include <complex>
 #include <map>
@@ -67,13 +68,15 @@ namespace moai
     // One key-switching key on the device.  key_kl = limbs stored per key polynomial: the
     // context's kl for SEAL's layout [kl-1][2][kl][n] (S/kswitchkeys.h:335-340), L + 1 for a key
     // truncated to its first L digits / data limbs (+ the special prime) by key_prepare.
+    // k_extra > 0: a grouped-digit key of ksg_key_prepare (csrc/ksgroup.hpp), [digits][2][max_limbs + k_extra + 1][n].
     struct KeyRef
     {
         const u64 *p = nullptr;
         int key_kl = 0;
+        int k_extra = 0;
         int max_limbs() const
         {
-            return key_kl - 1;
+            return key_kl - 1 - k_extra;
         }
     };
 
@@ -81,25 +84,46 @@ namespace moai
     //  * galois      : keys exactly as SEAL generates them -> SEAL-bit-exact rotations.
     //  * galois_fast : pre-permuted keys K' = sigma^-1(K) (key_prepare), possibly several level
     //                  truncations per element -> hoisted rotations (same plaintext, different noise).
+    //  * relin_fast  : grouped-digit variants of the relinearisation key (fast mode).
     struct Keys
     {
         KeyRef relin;
+        std::vector<KeyRef> relin_fast;
         std::map<uint32_t, KeyRef> galois;
         std::map<uint32_t, std::vector<KeyRef>> galois_fast;
-        // smallest pre-permuted key of `elt` that covers `limbs` levels (nullptr when none)
-        const KeyRef *fast(uint32_t elt, int limbs) const
+        // cheapest (ksg_cost) pre-permuted key of `elt` that covers `limbs` levels (nullptr when none);
+        // only_k >= 0 restricts the choice to keys with that many extra primes
+        const KeyRef *fast(Context *c, uint32_t elt, int limbs, int only_k = -1) const
         {
             auto it = galois_fast.find(elt);
-            if (it == galois_fast.end())
+            return it == galois_fast.end() ? nullptr : pick(c, it->second, limbs, only_k);
+        }
+        // cheapest relinearisation key at this level: a grouped variant, else SEAL's
+        const KeyRef *relin_at(Context *c, int limbs) const
+        {
+            const KeyRef *g = pick(c, relin_fast, limbs, -1);
+            if (g && (!relin.p || ksg_cost(c, limbs, g->k_extra) < ksg_cost(c, limbs, 0)))
             {
-                return nullptr;
+                return g;
             }
+            return relin.p ? &relin : nullptr;
+        }
+        static const KeyRef *pick(Context *c, const std::vector<KeyRef> &cands, int limbs, int only_k)
+        {
             const KeyRef *best = nullptr;
-            for (auto &k : it->second)
+            double best_cost = 0;
+            for (auto &k : cands)
             {
-                if (k.max_limbs() >= limbs && (!best || k.key_kl < best->key_kl))
+                if (k.max_limbs() < limbs || (only_k >= 0 && k.k_extra != only_k) ||
+                    (k.k_extra > 0 && limbs + k.k_extra > c->kl - 1))
+                {
+                    continue;
+                }
+                const double cost = ksg_cost(c, limbs, k.k_extra);
+                if (!best || cost < best_cost || (cost == best_cost && k.key_kl < best->key_kl))
                 {
                     best = &k;
+                    best_cost = cost;
                 }
             }
             return best;
@@ -110,7 +134,8 @@ namespace moai
     struct Hoisted
     {
         Ct src;                      // the unrotated ciphertexts (shared storage)
-        std::shared_ptr<DevBuf> ext; // [batch][limbs + 1][limbs][n]
+        std::shared_ptr<DevBuf> ext; // [batch][limbs + 1][limbs][n]; grouped digits: [batch][limbs + k + 1][digits][n]
+        int k_extra = 0;
     };
 
     class Evaluator
@@ -161,7 +186,7 @@ namespace moai
         Ct complex_conjugate(const Ct &a, const Keys &k) const;
         // fast mode: one decomposition, many rotations.  Needs pre-permuted keys.
         bool has_fast_key(int steps, int limbs, const Keys &k) const;
-        Hoisted hoist(const Ct &a) const;
+        Hoisted hoist(const Ct &a, int k_extra = 0) const;
         Ct rotate_hoisted(const Hoisted &h, int steps, const Keys &k) const;
         Ct rotate_fast(const Ct &a, uint32_t elt, const KeyRef &key) const; // chunked hoist + rotate
         // rotations of one batch by several steps: hoisted when every key is pre-permuted, else one by one

@@ -1,0 +1,596 @@
+// Grouped-digit key switching (design and derivation: ksgroup.hpp).
+#include "ksgroup.hpp"
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+namespace moai
+{
+    namespace
+    {
+        typedef unsigned __int128 u128h;
+
+        u64 h_mulmod(u64 a, u64 b, u64 q)
+        {
+            return (u64)((u128h)a * b % q);
+        }
+        u64 h_powmod(u64 a, u64 e, u64 q)
+        {
+            u64 r = 1 % q;
+            a %= q;
+            while (e)
+            {
+                if (e & 1)
+                {
+                    r = h_mulmod(r, a, q);
+                }
+                a = h_mulmod(a, a, q);
+                e >>= 1;
+            }
+            return r;
+        }
+        u64 h_invmod(u64 a, u64 q) // q prime
+        {
+            return h_powmod(a % q, q - 2, q);
+        }
+        Twiddle h_shoup(u64 w, u64 q)
+        {
+            Twiddle t;
+            t.w = w;
+            t.wq = (u64)(((u128h)w << 64) / q);
+            return t;
+        }
+        double h_centred(u64 v, u64 q)
+        {
+            return v > q / 2 ? -(double)(q - v) : (double)v;
+        }
+
+        // consecutive groups of the data primes 0 .. L-k-1, each with prod(G) <= p * prod(E) (bit-length sums)
+        std::vector<int> group_starts(const Context *c, int k)
+        {
+            const int L = c->kl - 1;
+            double cap = std::log2((double)c->q[c->kl - 1]);
+            for (int i = L - k; i < L; i++)
+            {
+                cap += std::log2((double)c->q[i]);
+            }
+            std::vector<int> st{ 0 };
+            double bits = 0;
+            int cnt = 0;
+            for (int J = 0; J < L - k; J++)
+            {
+                const double b = std::log2((double)c->q[J]);
+                if (cnt > 0 && (bits + b > cap || cnt >= CONV_MAX))
+                {
+                    st.push_back(J);
+                    bits = 0;
+                    cnt = 0;
+                }
+                bits += b;
+                cnt++;
+            }
+            st.push_back(L - k);
+            return st;
+        }
+
+        struct KsgTables
+        {
+            int k = 0, limbs = 0, rns = 0, digits = 0;
+            KsShape shape;
+            ConvTab dec, md;
+            const Twiddle *d_yconst = nullptr; // [limbs]  prod(E) (Q_g / q_J)^-1 mod q_J
+            const Twiddle *d_zconst = nullptr; // [k + 1]  (P' / p_i)^-1 mod p_i
+            const Twiddle *d_pinv = nullptr;   // [limbs]  P'^-1 mod q_j
+            const int *d_ids = nullptr;        // [rns]
+            void *blob = nullptr;
+        };
+
+        struct Blob
+        {
+            std::vector<unsigned char> bytes;
+            size_t put(const void *p, size_t n)
+            {
+                const size_t off = (bytes.size() + 15) & ~(size_t)15;
+                bytes.resize(off + n);
+                std::memcpy(bytes.data() + off, p, n);
+                return off;
+            }
+            template <class T>
+            size_t put(const std::vector<T> &v)
+            {
+                return put(v.data(), v.size() * sizeof(T));
+            }
+        };
+
+        // conversion tables of ONE source set (`src` prime indices, grouped by s0 / cnt) into `tgt` prime indices
+        struct ConvOffsets
+        {
+            size_t s0, cnt, invq, wide, B, B26, Bd, B26d, negQ, negQd;
+            int src_limbs;
+        };
+        ConvOffsets build_conv(const Context *c, Blob &bl, const std::vector<int> &src, const std::vector<int> &s0,
+                               const std::vector<int> &cnt, const std::vector<int> &tgt)
+        {
+            const int digits = (int)s0.size(), rns = (int)tgt.size();
+            std::vector<double> invq(src.size());
+            std::vector<unsigned char> wide(src.size());
+            for (size_t j = 0; j < src.size(); j++)
+            {
+                invq[j] = 1.0 / (double)c->q[src[j]];
+                wide[j] = (c->q[src[j]] >> 52) != 0;
+            }
+            std::vector<u64> B((size_t)digits * rns * CONV_MAX, 0), B26(B.size(), 0), negQ((size_t)digits * rns, 0);
+            std::vector<double> Bd(B.size(), 0.0), B26d(B.size(), 0.0), negQd(negQ.size(), 0.0);
+            for (int g = 0; g < digits; g++)
+            {
+                for (int I = 0; I < rns; I++)
+                {
+                    const u64 m = c->q[tgt[I]];
+                    u64 Qg = 1 % m;
+                    for (int j = 0; j < cnt[g]; j++)
+                    {
+                        Qg = h_mulmod(Qg, c->q[src[s0[g] + j]] % m, m);
+                        u64 b = 1 % m; // (Q_g / q_j) mod m as a product (no big integers needed)
+                        for (int j2 = 0; j2 < cnt[g]; j2++)
+                        {
+                            if (j2 != j)
+                            {
+                                b = h_mulmod(b, c->q[src[s0[g] + j2]] % m, m);
+                            }
+                        }
+                        const size_t at = ((size_t)g * rns + I) * CONV_MAX + j;
+                        B[at] = b;
+                        B26[at] = h_mulmod(b, ((u64)1 << 26) % m, m);
+                        Bd[at] = h_centred(B[at], m);
+                        B26d[at] = h_centred(B26[at], m);
+                    }
+                    negQ[(size_t)g * rns + I] = Qg ? m - Qg : 0;
+                    negQd[(size_t)g * rns + I] = h_centred(negQ[(size_t)g * rns + I], m);
+                }
+            }
+            ConvOffsets o;
+            o.s0 = bl.put(s0);
+            o.cnt = bl.put(cnt);
+            o.invq = bl.put(invq);
+            o.wide = bl.put(wide);
+            o.B = bl.put(B);
+            o.B26 = bl.put(B26);
+            o.Bd = bl.put(Bd);
+            o.B26d = bl.put(B26d);
+            o.negQ = bl.put(negQ);
+            o.negQd = bl.put(negQd);
+            o.src_limbs = (int)src.size();
+            return o;
+        }
+        ConvTab bind_conv(const ConvOffsets &o, const unsigned char *base)
+        {
+            ConvTab t;
+            t.s0 = reinterpret_cast<const int *>(base + o.s0);
+            t.cnt = reinterpret_cast<const int *>(base + o.cnt);
+            t.invq = reinterpret_cast<const double *>(base + o.invq);
+            t.wide = base + o.wide;
+            t.B = reinterpret_cast<const u64 *>(base + o.B);
+            t.B26 = reinterpret_cast<const u64 *>(base + o.B26);
+            t.Bd = reinterpret_cast<const double *>(base + o.Bd);
+            t.B26d = reinterpret_cast<const double *>(base + o.B26d);
+            t.negQ = reinterpret_cast<const u64 *>(base + o.negQ);
+            t.negQd = reinterpret_cast<const double *>(base + o.negQd);
+            t.src_limbs = o.src_limbs;
+            return t;
+        }
+
+        const KsgTables &tables(Context *c, int k, int limbs)
+        {
+            std::lock_guard<std::mutex> lk(c->ksg_mu);
+            auto it = c->ksg_cache.find({ k, limbs });
+            if (it != c->ksg_cache.end())
+            {
+                return *static_cast<KsgTables *>(it->second);
+            }
+            const int L = c->kl - 1;
+            MOAI_REQUIRE(k >= 1 && limbs >= 1 && limbs + k <= L, "no spare primes for grouped digits at this level");
+            KsgTables *t = new KsgTables();
+            t->k = k;
+            t->limbs = limbs;
+            t->rns = limbs + k + 1;
+            // targets: own data primes, the k borrowed top primes, the special prime
+            std::vector<int> ids;
+            for (int i = 0; i < limbs; i++)
+            {
+                ids.push_back(i);
+            }
+            for (int i = L - k; i < L; i++)
+            {
+                ids.push_back(i);
+            }
+            ids.push_back(L);
+            // digits: the key's fixed groups cut at `limbs`
+            const std::vector<int> st = group_starts(c, k);
+            std::vector<int> s0, cnt;
+            for (size_t g = 0; g + 1 < st.size() && st[g] < limbs; g++)
+            {
+                s0.push_back(st[g]);
+                cnt.push_back(std::min(st[g + 1], limbs) - st[g]);
+            }
+            t->digits = (int)s0.size();
+            std::vector<int> src_dec(limbs);
+            for (int i = 0; i < limbs; i++)
+            {
+                src_dec[i] = i;
+            }
+            Blob bl;
+            const size_t o_ids = bl.put(ids);
+            const ConvOffsets o_dec = build_conv(c, bl, src_dec, s0, cnt, ids);
+            // y_J = c_J * prod(E) * (Q_g / q_J)^-1 mod q_J
+            std::vector<Twiddle> yconst(limbs);
+            for (int g = 0; g < t->digits; g++)
+            {
+                for (int j = 0; j < cnt[g]; j++)
+                {
+                    const int J = s0[g] + j;
+                    const u64 q = c->q[J];
+                    u64 v = 1;
+                    for (int j2 = 0; j2 < cnt[g]; j2++)
+                    {
+                        if (j2 != j)
+                        {
+                            v = h_mulmod(v, c->q[s0[g] + j2] % q, q);
+                        }
+                    }
+                    v = h_invmod(v, q);
+                    for (int i = L - k; i < L; i++)
+                    {
+                        v = h_mulmod(v, c->q[i] % q, q);
+                    }
+                    yconst[J] = h_shoup(v, q);
+                }
+            }
+            const size_t o_y = bl.put(yconst);
+            // mod-down by P' = prod(E) * p: one group of k + 1 source limbs into the data primes
+            std::vector<int> src_md(ids.begin() + limbs, ids.end()), tgt_md(ids.begin(), ids.begin() + limbs);
+            const ConvOffsets o_md = build_conv(c, bl, src_md, std::vector<int>{ 0 }, std::vector<int>{ k + 1 }, tgt_md);
+            std::vector<Twiddle> zconst(k + 1), pinv(limbs);
+            for (int i = 0; i <= k; i++)
+            {
+                const u64 q = c->q[src_md[i]];
+                u64 v = 1;
+                for (int i2 = 0; i2 <= k; i2++)
+                {
+                    if (i2 != i)
+                    {
+                        v = h_mulmod(v, c->q[src_md[i2]] % q, q);
+                    }
+                }
+                zconst[i] = h_shoup(h_invmod(v, q), q);
+            }
+            for (int j = 0; j < limbs; j++)
+            {
+                const u64 q = c->q[j];
+                u64 v = 1;
+                for (int i = 0; i <= k; i++)
+                {
+                    v = h_mulmod(v, c->q[src_md[i]] % q, q);
+                }
+                pinv[j] = h_shoup(h_invmod(v, q), q);
+            }
+            const size_t o_z = bl.put(zconst), o_p = bl.put(pinv);
+            MOAI_CUDA_CHECK(cudaMalloc(&t->blob, bl.bytes.size()));
+            MOAI_CUDA_CHECK(cudaMemcpy(t->blob, bl.bytes.data(), bl.bytes.size(), cudaMemcpyHostToDevice));
+            const unsigned char *base = static_cast<const unsigned char *>(t->blob);
+            t->d_ids = reinterpret_cast<const int *>(base + o_ids);
+            t->dec = bind_conv(o_dec, base);
+            t->md = bind_conv(o_md, base);
+            t->d_yconst = reinterpret_cast<const Twiddle *>(base + o_y);
+            t->d_zconst = reinterpret_cast<const Twiddle *>(base + o_z);
+            t->d_pinv = reinterpret_cast<const Twiddle *>(base + o_p);
+            t->shape.digits = t->digits;
+            t->shape.rns = t->rns;
+            t->shape.n_data = limbs;
+            t->shape.ids = t->d_ids;
+            c->ksg_cache[{ k, limbs }] = t;
+            return *t;
+        }
+
+        // data[p][slot][n] *= consts[slot]  (mod the prime ids[slot])
+        __global__ void k_scale_slots(ulonglong2 *data, long long total2, int log_n2, int slots,
+                                      const int *__restrict__ ids, const Twiddle *__restrict__ consts,
+                                      const LimbConst *__restrict__ lcs)
+        {
+            const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= total2)
+            {
+                return;
+            }
+            const int slot = (int)((i >> log_n2) % slots);
+            const u64 q = lcs[ids[slot]].q;
+            const Twiddle w = consts[slot];
+            ulonglong2 v = data[i];
+            v.x = mul_shoup(v.x, w.w, w.wq, q);
+            v.y = mul_shoup(v.y, w.w, w.wq, q);
+            data[i] = v;
+        }
+
+        void scale_slots(Context *c, u64 *data, long long polys, int slots, const int *d_ids, const Twiddle *d_consts)
+        {
+            const long long total2 = polys * slots * (long long)(c->n / 2);
+            KernelTimer kt(c, "k_scale_slots", 1);
+            k_scale_slots<<<(unsigned)((total2 + 255) / 256), 256, 0, c->stream>>>(
+                reinterpret_cast<ulonglong2 *>(data), total2, c->log_n - 1, slots, d_ids, d_consts, c->d_limb);
+            c->launches += 1;
+            MOAI_CUDA_CHECK(cudaGetLastError());
+        }
+
+        // out[G][k][I] = sum_{J in G} in[J][k][prime(I)]   (16-byte lanes; <= CONV_MAX terms below 2^61 each)
+        struct KeySumArgs
+        {
+            const ulonglong2 *src[CONV_MAX];
+            int cnt;
+        };
+        __global__ void k_key_group_sum(KeySumArgs a, ulonglong2 *out, long long n2, u64 q)
+        {
+            const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= n2)
+            {
+                return;
+            }
+            ulonglong2 s = a.src[0][i];
+            for (int j = 1; j < a.cnt; j++)
+            {
+                const ulonglong2 v = a.src[j][i];
+                s.x = addmod(s.x, v.x, q);
+                s.y = addmod(s.y, v.y, q);
+            }
+            out[i] = s;
+        }
+
+        size_t ksg_ext_budget_bytes()
+        {
+            return ks_ext_budget();
+        }
+    } // namespace
+
+    void ksg_release(Context *c)
+    {
+        for (auto &kv : c->ksg_cache)
+        {
+            KsgTables *t = static_cast<KsgTables *>(kv.second);
+            cudaFree(t->blob);
+            delete t;
+        }
+        c->ksg_cache.clear();
+    }
+
+    int ksg_max_limbs(Context *c, int k)
+    {
+        return c->kl - 1 - k;
+    }
+
+    int ksg_digits(Context *c, int k, int lmax)
+    {
+        MOAI_REQUIRE(k >= 1 && lmax >= 1 && lmax + k <= c->kl - 1, "no spare primes for grouped digits at this level");
+        const std::vector<int> st = group_starts(c, k);
+        int d = 0;
+        for (size_t g = 0; g + 1 < st.size() && st[g] < lmax; g++)
+        {
+            d++;
+        }
+        return d;
+    }
+
+    size_t ksg_key_words(Context *c, int k, int lmax)
+    {
+        return (size_t)ksg_digits(c, k, lmax) * 2 * ksg_key_kl(k, lmax) * c->n;
+    }
+
+    // Cost model in microseconds per ciphertext at N = 65536 (limb-transform 0.5, inverse 0.6, one source limb of a
+    // base conversion into one target limb 0.035, one (digit, target) pair of the evk inner product 0.06, one
+    // element-wise pass over a limb 0.08); only the ORDER of the candidates matters.
+    double ksg_cost(Context *c, int limbs, int k)
+    {
+        const double NTT = 0.5, INTT = 0.6, CONV = 0.035, MAC = 0.06, EW = 0.08;
+        if (k == 0)
+        {
+            return limbs * INTT + (double)limbs * (limbs + 1) * (NTT + MAC) + 2 * (INTT + limbs * NTT + limbs * EW);
+        }
+        const int digits = ksg_digits(c, k, limbs), m = limbs + k + 1;
+        const double dec = limbs * (INTT + EW) + (double)digits * m * NTT + (double)limbs * m * CONV;
+        const double mac = (double)digits * m * MAC;
+        const double md = 2 * ((k + 1) * (INTT + EW) + limbs * NTT + (double)(k + 1) * limbs * CONV + limbs * EW);
+        return dec + mac + md;
+    }
+
+    int ksg_best_k(Context *c, int limbs)
+    {
+        int best = 0;
+        double bc = ksg_cost(c, limbs, 0);
+        for (int k = 1; limbs + k <= c->kl - 1 && k + 1 <= CONV_MAX; k++)
+        {
+            const double v = ksg_cost(c, limbs, k);
+            if (v < bc)
+            {
+                bc = v;
+                best = k;
+            }
+        }
+        return best;
+    }
+
+    void ksg_key_prepare(Context *c, const u64 *in, uint32_t elt, int k, int lmax, bool pre_permute, u64 *out)
+    {
+        const int L = c->kl - 1;
+        MOAI_REQUIRE(k >= 1 && lmax >= 1 && lmax + k <= L, "no spare primes for grouped digits at this level");
+        MOAI_REQUIRE(k + 1 <= CONV_MAX, "too many extra primes");
+        MOAI_REQUIRE(in != out, "key preparation is out of place");
+        const size_t n = c->n;
+        const int okl = ksg_key_kl(k, lmax);
+        const std::vector<int> st = group_starts(c, k);
+        const int digits = ksg_digits(c, k, lmax);
+        uint32_t inv = 1;
+        if (pre_permute)
+        {
+            const uint64_t m = 2 * (uint64_t)n;
+            uint64_t x = elt;
+            for (int i = 0; i < 6; i++)
+            {
+                x = (x * (2 + m * 4 - (uint64_t)elt * x % m)) % m;
+            }
+            MOAI_REQUIRE((uint64_t)elt * x % m == 1, "Galois element is not invertible");
+            inv = (uint32_t)x;
+        }
+        Scratch tmp(n * sizeof(u64), c->stream);
+        const long long n2 = (long long)(n / 2);
+        for (int g = 0; g < digits; g++)
+        {
+            // the WHOLE group of the key (also the primes at or above lmax: their F_J vanish on the basis in use)
+            const int j0 = st[g], j1 = st[g + 1];
+            for (int kk = 0; kk < 2; kk++)
+            {
+                for (int ol = 0; ol < okl; ol++)
+                {
+                    const int prime = ol < lmax ? ol : (ol < lmax + k ? L - k + (ol - lmax) : L);
+                    KeySumArgs a;
+                    a.cnt = j1 - j0;
+                    for (int j = 0; j < a.cnt; j++)
+                    {
+                        a.src[j] = reinterpret_cast<const ulonglong2 *>(in + (((size_t)(j0 + j) * 2 + kk) * c->kl + prime) * n);
+                    }
+                    u64 *dst = out + (((size_t)g * 2 + kk) * okl + ol) * n;
+                    u64 *sum = pre_permute ? tmp.as<u64>() : dst;
+                    {
+                        KernelTimer kt(c, "k_key_group_sum", 1);
+                        k_key_group_sum<<<(unsigned)((n2 + 255) / 256), 256, 0, c->stream>>>(
+                            a, reinterpret_cast<ulonglong2 *>(sum), n2, c->q[prime]);
+                        c->launches += 1;
+                    }
+                    if (pre_permute)
+                    {
+                        apply_galois_ntt(c, sum, dst, 1, inv);
+                    }
+                }
+            }
+        }
+        MOAI_CUDA_CHECK(cudaGetLastError());
+    }
+
+    size_t ksg_ext_bytes_per_ct(Context *c, int limbs, int k)
+    {
+        return (size_t)(limbs + k + 1) * ksg_digits(c, k, limbs) * c->n * sizeof(u64);
+    }
+
+    void ksg_decompose(Context *c, const u64 *target, long long batch, int limbs, int k, u64 *ext,
+                       long long target_stride, int passes)
+    {
+        const KsgTables &t = tables(c, k, limbs);
+        const size_t n = c->n;
+        Scratch d((size_t)batch * limbs * n * sizeof(u64), c->stream);
+        const size_t row = (size_t)limbs * n * sizeof(u64);
+        {
+            KernelTimer ktm(c, "k_copy_ks_target", 1);
+            MOAI_CUDA_CHECK(cudaMemcpy2DAsync(d.p, row, target, target_stride ? (size_t)target_stride * sizeof(u64) : row,
+                                              row, (size_t)batch, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        ntt_inverse(c, d.as<u64>(), batch * limbs, c->d_ids, limbs);
+        scale_slots(c, d.as<u64>(), batch, limbs, c->d_ids, t.d_yconst);
+        NttPrologue pro;
+        pro.src = d.as<u64>();
+        pro.mode = 3;
+        pro.conv = &t.dec;
+        ntt_forward(c, ext, batch * t.rns * t.digits, t.d_ids, t.rns, t.digits, &pro, passes);
+    }
+
+    void ksg_moddown(Context *c, const u64 *acc, long long polys, int limbs, int k, const u64 *addend,
+                     bool addend_even_only, u64 *out)
+    {
+        const KsgTables &t = tables(c, k, limbs);
+        const size_t n = c->n;
+        const int np = k + 1;
+        Scratch r((size_t)polys * np * n * sizeof(u64), c->stream);
+        {
+            KernelTimer ktm(c, "k_copy_last_limb", 1);
+            MOAI_CUDA_CHECK(cudaMemcpy2DAsync(r.p, (size_t)np * n * sizeof(u64), acc + (size_t)limbs * n,
+                                              (size_t)t.rns * n * sizeof(u64), (size_t)np * n * sizeof(u64), (size_t)polys,
+                                              cudaMemcpyDeviceToDevice, c->stream));
+        }
+        ntt_inverse(c, r.as<u64>(), polys * np, t.d_ids + limbs, np);
+        scale_slots(c, r.as<u64>(), polys, np, t.d_ids + limbs, t.d_zconst);
+        Scratch u((size_t)polys * limbs * n * sizeof(u64), c->stream);
+        NttPrologue pro;
+        pro.src = r.as<u64>();
+        pro.mode = 3;
+        pro.conv = &t.md;
+        ntt_forward(c, u.as<u64>(), polys * limbs, c->d_ids, limbs, 1, &pro);
+        divround_finish(c, acc, u.as<u64>(), addend, out, polys, limbs, t.rns, t.d_pinv, addend_even_only);
+    }
+
+    // inner products of the integer-path target moduli (the special prime): plain pass B + 128-bit MAC
+    static void ksg_int_targets(Context *c, const KsgTables &t, u64 *ext, long long batch, const u64 *ksk, int key_kl,
+                                u64 *acc, bool need_pass_b)
+    {
+        const size_t n = c->n;
+        for (int I = 0; I < t.rns; I++)
+        {
+            const int prime = I < t.limbs ? I : (I < t.limbs + t.k ? c->kl - 1 - t.k + (I - t.limbs) : c->kl - 1);
+            if (c->h_limb[prime].fp_class != 0)
+            {
+                continue;
+            }
+            if (need_pass_b)
+            {
+                ntt_forward_pass_b_strided(c, ext + (size_t)I * t.digits * n, batch, t.digits, (long long)t.rns * t.digits,
+                                           c->d_ids + prime);
+            }
+            ks_mac_int(c, ext, ksk, acc, batch, t.shape, key_kl, I);
+        }
+    }
+
+    void ksg_switch(Context *c, const u64 *target, long long batch, int limbs, int k, const u64 *ksk, int key_kl,
+                    const u64 *addend, u64 *out, long long target_stride, bool addend_c0_only)
+    {
+        const KsgTables &t = tables(c, k, limbs);
+        MOAI_REQUIRE(key_kl >= t.rns, "grouped key does not cover this level");
+        const size_t n = c->n;
+        const size_t per_ext = ksg_ext_bytes_per_ct(c, limbs, k);
+        long long chunk = (long long)(ksg_ext_budget_bytes() / per_ext);
+        chunk = chunk < 1 ? 1 : (chunk > batch ? batch : chunk);
+        Scratch ext((size_t)chunk * per_ext, c->stream);
+        Scratch acc((size_t)chunk * 2 * t.rns * n * sizeof(u64), c->stream);
+        const size_t tstride = target_stride ? (size_t)target_stride : (size_t)limbs * n;
+        for (long long b0 = 0; b0 < batch; b0 += chunk)
+        {
+            const long long nb = std::min(chunk, batch - b0);
+            ksg_decompose(c, target + (size_t)b0 * tstride, nb, limbs, k, ext.as<u64>(), target_stride, /*passes=*/1);
+            ks_passb_mac(c, ext.as<u64>(), nb, t.shape, ksk, key_kl, acc.as<u64>());
+            ksg_int_targets(c, t, ext.as<u64>(), nb, ksk, key_kl, acc.as<u64>(), true);
+            const size_t off = (size_t)b0 * 2 * limbs * n;
+            ksg_moddown(c, acc.as<u64>(), nb * 2, limbs, k, addend ? addend + off : nullptr, addend_c0_only, out + off);
+        }
+    }
+
+    void ksg_rotate_hoisted_multi(Context *c, const u64 *ct, const u64 *ext, long long batch, int limbs, int k, int n_rot,
+                                  const uint32_t *elts, const u64 *const *ksk_pre, const int *key_kl, u64 *const *outs)
+    {
+        MOAI_REQUIRE(n_rot >= 1 && n_rot <= KSM_R, "too many rotations for one multi-key pass");
+        const KsgTables &t = tables(c, k, limbs);
+        const size_t n = c->n;
+        const size_t acc_words = (size_t)batch * 2 * t.rns * n;
+        Scratch acc(acc_words * n_rot * sizeof(u64), c->stream);
+        u64 *accp[KSM_R];
+        for (int r = 0; r < n_rot; r++)
+        {
+            accp[r] = acc.as<u64>() + acc_words * r;
+            MOAI_REQUIRE(key_kl[r] >= t.rns, "grouped key does not cover this level");
+        }
+        ks_mac_multi(c, ext, batch, t.shape, n_rot, ksk_pre, key_kl, accp);
+        for (int r = 0; r < n_rot; r++)
+        {
+            ksg_int_targets(c, t, const_cast<u64 *>(ext), batch, ksk_pre[r], key_kl[r], accp[r], false);
+        }
+        Scratch tmp((size_t)batch * 2 * limbs * n * sizeof(u64), c->stream);
+        for (int r = 0; r < n_rot; r++)
+        {
+            ksg_moddown(c, accp[r], batch * 2, limbs, k, ct, true, tmp.as<u64>());
+            apply_galois_ntt(c, tmp.as<u64>(), outs[r], batch * 2 * limbs, elts[r]);
+        }
+    }
+} // namespace moai

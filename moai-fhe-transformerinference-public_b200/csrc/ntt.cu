@@ -303,11 +303,14 @@ namespace moai
         };
 
         template <int LOGR, class F>
+        __device__ __forceinline__ void fwd_pass_a_stages(const F &f, typename F::elem (&x)[16], u64 *base, u64 *sm, int t,
+                                                          int tb);
+
+        template <int LOGR, class F>
         __device__ __forceinline__ void fwd_pass_a_body(const F &f, u64 *base, u64 *sm, int t, int tb, const ProArgs &pa)
         {
             constexpr int R = 1 << LOGR, T1 = R / 16;
             typename F::elem x[16];
-            typename F::elem *smf = reinterpret_cast<typename F::elem *>(sm);
 #pragma unroll
             for (int k = 0; k < 16; k++)
             {
@@ -322,6 +325,15 @@ namespace moai
                     x[k] = f.pro_reduce(x[k]);
                 }
             }
+            fwd_pass_a_stages<LOGR>(f, x, base, sm, t, tb);
+        }
+
+        template <int LOGR, class F>
+        __device__ __forceinline__ void fwd_pass_a_stages(const F &f, typename F::elem (&x)[16], u64 *base, u64 *sm, int t,
+                                                          int tb)
+        {
+            constexpr int R = 1 << LOGR, T1 = R / 16;
+            typename F::elem *smf = reinterpret_cast<typename F::elem *>(sm);
             f.phase_begin_fwd(x);
             // stages 0..3 pair the top four bits of a (k): root index 2^s + block
             ct_stage<8>(f, x, 1);
@@ -623,6 +635,172 @@ namespace moai
 
 
         // =====================================================================================
+        // Pass A with the fast base conversion of ConvTab (ntt.cuh) as its prologue: the 16 residues a thread
+        // starts from are computed from up to CONV_MAX source limbs instead of being loaded.  FP64-path targets
+        // use the exact FP64 products of the NTT (terms <= 1.125 p, reduced every 2 (51-bit class) / 8 (46-bit
+        // class) terms, so sums stay below 2^53); integer-path targets accumulate 128-bit sums (<= 16 products of
+        // 61-bit factors) and reduce once.  v = rint(sum y_j / q_j) is computed with the same FP64 instruction
+        // sequence in both versions, so every target modulus sees the same integer digit.
+        // =====================================================================================
+        __device__ __forceinline__ double conv_y_double(u64 y)
+        {
+            return __ull2double_rn(y);
+        }
+        __device__ __forceinline__ double conv_rint(double v)
+        {
+            const double M = 6755399441055744.0;
+            return __dadd_rn(__dadd_rn(v, M), -M);
+        }
+
+        template <bool WIDE>
+        __device__ __forceinline__ void conv_prologue(const FpField<WIDE> &f, const NttArgs &a, double (&x)[16],
+                                                      const u64 *src0, size_t row_stride, int g, int I, int rns)
+        {
+            const ConvTab &cv = a.conv;
+            const int s0 = cv.s0[g], cnt = cv.cnt[g];
+            const size_t trow = ((size_t)g * rns + I) * CONV_MAX;
+            double vs[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+            {
+                x[k] = 0.0;
+                vs[k] = 0.0;
+            }
+            const int red_every = WIDE ? 2 : 8;
+            int since = 0;
+            for (int j = 0; j < cnt; j++)
+            {
+                const double iq = cv.invq[s0 + j];
+                const double bd = cv.Bd[trow + j];
+                const u64 *sj = src0 + ((size_t)j << a.log_n);
+                u64 y[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                {
+                    y[k] = sj[(size_t)k * row_stride];
+                }
+                if (cv.wide[s0 + j])
+                {
+                    const double b26 = cv.B26d[trow + j];
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                    {
+                        vs[k] = __fma_rn(conv_y_double(y[k]), iq, vs[k]);
+                        const double hi = f.in_outer(y[k] >> 26), lo = f.in_outer(y[k] & 0x3FFFFFFull);
+                        x[k] = __dadd_rn(x[k], __dadd_rn(f.mul_lazy(hi, b26), f.mul_lazy(lo, bd)));
+                    }
+                    since += 2;
+                }
+                else
+                {
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                    {
+                        vs[k] = __fma_rn(conv_y_double(y[k]), iq, vs[k]);
+                        x[k] = __dadd_rn(x[k], f.mul_lazy(f.in_outer(y[k]), bd));
+                    }
+                    since += 1;
+                }
+                if (since >= red_every)
+                {
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                    {
+                        x[k] = f.red(x[k]);
+                    }
+                    since = 0;
+                }
+            }
+            const double nq = cv.negQd[(size_t)g * rns + I];
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+            {
+                x[k] = f.red(__dadd_rn(x[k], f.mul_lazy(conv_rint(vs[k]), nq)));
+            }
+        }
+
+        __device__ __forceinline__ void conv_prologue(const IntField &f, const NttArgs &a, u64 (&x)[16], const u64 *src0,
+                                                      size_t row_stride, int g, int I, int rns, const LimbConst &lc,
+                                                      const Twiddle &t64)
+        {
+            const ConvTab &cv = a.conv;
+            const int s0 = cv.s0[g], cnt = cv.cnt[g];
+            const size_t trow = ((size_t)g * rns + I) * CONV_MAX;
+            double vs[16];
+            u128 acc[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+            {
+                acc[k].lo = 0;
+                acc[k].hi = 0;
+                vs[k] = 0.0;
+            }
+            for (int j = 0; j < cnt; j++)
+            {
+                const double iq = cv.invq[s0 + j];
+                const u64 bj = cv.B[trow + j];
+                const u64 *sj = src0 + ((size_t)j << a.log_n);
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                {
+                    const u64 y = sj[(size_t)k * row_stride];
+                    vs[k] = __fma_rn(conv_y_double(y), iq, vs[k]);
+                    mac_wide(acc[k], y, bj);
+                }
+            }
+            const u64 nq = cv.negQ[(size_t)g * rns + I];
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+            {
+                const u64 v = (u64)__double2ll_rn(conv_rint(vs[k]));
+                mac_wide(acc[k], v, nq);
+                x[k] = barrett_reduce_acc(acc[k], lc, t64.w, t64.wq);
+            }
+            (void)f;
+        }
+
+        template <int LOGR>
+        __global__ void __launch_bounds__((1 << LOGR) / 16 * TB) ntt_fwd_pass_a_conv(NttArgs a, const Twiddle *two64)
+        {
+            __shared__ u64 sm[(1 << LOGR) * TB];
+            constexpr int T1 = (1 << LOGR) / 16;
+            const int tb = threadIdx.x & (TB - 1), t = threadIdx.x >> 4;
+            const long long poly = blockIdx.x / (256 / TB);
+            const int tile = blockIdx.x % (256 / TB);
+            const int I = (int)((poly / a.div) % a.period);
+            const int g = (int)(poly % a.div);
+            const long long b = poly / ((long long)a.period * a.div);
+            const int limb = a.limb_ids[I];
+            const LimbConst lc = a.limb[limb];
+            u64 *base = a.data + ((size_t)poly << a.log_n) + tile * TB + tb;
+            // element k of this thread: row t + T1 k, column tile * TB + tb, of source limb s0[g] + j of item b
+            const u64 *src0 = a.src + (((size_t)b * a.conv.src_limbs + a.conv.s0[g]) << a.log_n) + (size_t)t * 256 +
+                              tile * TB + tb;
+            const size_t row_stride = (size_t)T1 * 256;
+            if (lc.fp_class == 1)
+            {
+                const FpField<false> f(a, limb, lc);
+                double x[16];
+                conv_prologue(f, a, x, src0, row_stride, g, I, a.period);
+                fwd_pass_a_stages<LOGR>(f, x, base, sm, t, tb);
+            }
+            else if (lc.fp_class == 2)
+            {
+                const FpField<true> f(a, limb, lc);
+                double x[16];
+                conv_prologue(f, a, x, src0, row_stride, g, I, a.period);
+                fwd_pass_a_stages<LOGR>(f, x, base, sm, t, tb);
+            }
+            else
+            {
+                const IntField f(a, limb, lc);
+                u64 x[16];
+                conv_prologue(f, a, x, src0, row_stride, g, I, a.period, lc, two64[limb]);
+                fwd_pass_a_stages<LOGR>(f, x, base, sm, t, tb);
+            }
+        }
+
+        // =====================================================================================
         // Fused key-switch kernel: pass B of the digit-extension NTT + inner product with the evk.
         //
         // One CTA owns FR rows (FR x 256 output coefficients) of ONE target modulus I of ONE
@@ -659,13 +837,13 @@ namespace moai
 
         struct KsFusedArgs
         {
-            const u64 *mid;         // [batch][rns][limbs][n]: pass-A output of the extended digits
-            const u64 *ksk;         // [limbs..][2][key_kl][n]
+            const u64 *mid;         // [batch][rns][digits][n]: pass-A output of the extended digits
+            const u64 *ksk;         // [digits..][2][key_kl][n]
             u64 *acc;               // [batch][2][rns][n] canonical
             const double *tw_fp;    // [kl][n]
             const LimbConst *limb;  // [kl]
             const int *ids_ks;      // [rns]: prime index of target modulus I
-            int limbs, rns, key_kl, log_n;
+            int limbs, rns, n_data, key_kl, log_n; // limbs = digits (KsShape, ntt.cuh)
         };
 
         template <bool WIDE>
@@ -681,7 +859,7 @@ namespace moai
             double2 *tw1 = reinterpret_cast<double2 *>(smem + KS_SM_ROWS + KS_SM_TW2) + r * 8;
             ulonglong2 *kst = reinterpret_cast<ulonglong2 *>(smem + KS_SM_ROWS + KS_SM_TW2 + KS_SM_TW1) + tid;
 
-            const int key_limb = I == a.limbs ? a.key_kl - 1 : I;
+            const int key_limb = I < a.n_data ? I : I + a.key_kl - a.rns;
             const u64 *mid0 = a.mid + (((size_t)b * a.rns + I) * a.limbs << a.log_n) + (size_t)row * 256;
             const u64 *key0 = a.ksk + ((size_t)key_limb << a.log_n) + (size_t)row * 256 + 16 * t;
             const size_t key_poly = (size_t)a.key_kl << a.log_n; // stride between key[J][0] and key[J][1]
@@ -1036,13 +1214,13 @@ namespace moai
         // =====================================================================================
         struct KsMacMultiArgs
         {
-            const u64 *ext;          // [batch][rns][limbs][n] NTT form, canonical
+            const u64 *ext;          // [batch][rns][digits][n] NTT form, canonical
             const u64 *ksk[KSM_R];
             u64 *acc[KSM_R];         // each [batch][2][rns][n]
             int key_kl[KSM_R];
             const LimbConst *limb;
             const int *ids_ks;
-            int limbs, rns, log_n;
+            int limbs, rns, n_data, log_n; // limbs = digits (KsShape, ntt.cuh)
         };
 
         // Streams of one digit J for a CTA: the extended digit and key[J][0], key[J][1] of each of the R keys,
@@ -1068,7 +1246,7 @@ namespace moai
 #pragma unroll
             for (int r = 0; r < R; r++)
             {
-                const int key_limb = I == a.limbs ? a.key_kl[r] - 1 : I;
+                const int key_limb = I < a.n_data ? I : I + a.key_kl[r] - a.rns;
                 kp[r] = reinterpret_cast<const ulonglong2 *>(a.ksk[r]) + (long long)key_limb * n2 + within;
                 kpoly[r] = (long long)a.key_kl[r] * n2;  // key[J][0] -> key[J][1]
                 kstep[r] = 2 * kpoly[r];                 // key[J] -> key[J + 1]
@@ -1178,9 +1356,16 @@ namespace moai
         {
             if (do_a)
             {
-                KernelTimer kt(c, "k_ntt_fwd_pass_a", a.count);
+                KernelTimer kt(c, a.src_mode == 3 ? "k_ntt_fwd_pass_a_conv" : "k_ntt_fwd_pass_a", a.count);
                 const long long ctas_a = a.count * (256 / TB);
-                ntt_fwd_pass_a<LOGR><<<(unsigned)ctas_a, (1 << LOGR) / 16 * TB, 0, s>>>(a);
+                if (a.src_mode == 3)
+                {
+                    ntt_fwd_pass_a_conv<LOGR><<<(unsigned)ctas_a, (1 << LOGR) / 16 * TB, 0, s>>>(a, c->d_two64);
+                }
+                else
+                {
+                    ntt_fwd_pass_a<LOGR><<<(unsigned)ctas_a, (1 << LOGR) / 16 * TB, 0, s>>>(a);
+                }
             }
             if (do_b)
             {
@@ -1231,6 +1416,11 @@ namespace moai
             a.last_id = pro->last_id;
             a.kl = c->kl;
             a.half_mod = c->d_half_mod;
+            if (pro->mode == 3)
+            {
+                MOAI_REQUIRE(pro->conv != nullptr, "base-conversion prologue without tables");
+                a.conv = *pro->conv;
+            }
         }
         switch (c->log_n)
         {
@@ -1257,7 +1447,17 @@ namespace moai
         }
     } // namespace
 
-    void ks_mac_multi(Context *c, const u64 *ext, long long batch, int limbs, int n_keys, const u64 *const *ksk,
+    KsShape ks_shape_seal(Context *c, int limbs)
+    {
+        KsShape sh;
+        sh.digits = limbs;
+        sh.rns = limbs + 1;
+        sh.n_data = limbs;
+        sh.ids = c->d_ids_ks + (size_t)limbs * (c->kl + 1);
+        return sh;
+    }
+
+    void ks_mac_multi(Context *c, const u64 *ext, long long batch, const KsShape &sh, int n_keys, const u64 *const *ksk,
                       const int *key_kl, u64 *const *acc)
     {
         MOAI_REQUIRE(n_keys >= 1 && n_keys <= KSM_R, "too many keys for one multi-key inner product");
@@ -1270,12 +1470,13 @@ namespace moai
             a.key_kl[r] = r < n_keys ? key_kl[r] : 0;
         }
         a.limb = c->d_limb;
-        a.ids_ks = c->d_ids_ks + (size_t)limbs * (c->kl + 1);
-        a.limbs = limbs;
-        a.rns = limbs + 1;
+        a.ids_ks = sh.ids;
+        a.limbs = sh.digits;
+        a.rns = sh.rns;
+        a.n_data = sh.n_data;
         a.log_n = c->log_n;
         NttArgs na{ nullptr, c->d_fwd, c->d_fwd_fp, c->d_limb, nullptr, 1, 1, c->log_n, 0 };
-        dim3 grid((unsigned)batch, (unsigned)(limbs + 1), (unsigned)((c->n / 2) / 256));
+        dim3 grid((unsigned)batch, (unsigned)sh.rns, (unsigned)((c->n / 2) / 256));
         KernelTimer kt(c, "k_ks_mac_multi", batch * (long long)n_keys);
         switch (n_keys)
         {
@@ -1305,22 +1506,25 @@ namespace moai
         MOAI_CUDA_CHECK(cudaGetLastError());
     }
 
-    void ks_passb_mac(Context *c, const u64 *mid, long long batch, int limbs, const u64 *ksk, int key_kl, u64 *acc)
+    void ks_passb_mac(Context *c, const u64 *mid, long long batch, const KsShape &sh, const u64 *ksk, int key_kl,
+                      u64 *acc)
     {
+        const int limbs = sh.digits;
         MOAI_REQUIRE(c->log_n >= 12, "unsupported log_n");
         static const cudaError_t attr = cudaFuncSetAttribute(
             ks_passb_mac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KS_FUSED_SMEM);
         (void)attr;
-        const int rns = limbs + 1;
+        const int rns = sh.rns;
         KsFusedArgs a;
         a.mid = mid;
         a.ksk = ksk;
         a.acc = acc;
         a.tw_fp = c->d_fwd_fp;
         a.limb = c->d_limb;
-        a.ids_ks = c->d_ids_ks + (size_t)limbs * (c->kl + 1);
+        a.ids_ks = sh.ids;
         a.limbs = limbs;
         a.rns = rns;
+        a.n_data = sh.n_data;
         a.key_kl = key_kl;
         a.log_n = c->log_n;
         NttArgs na{ nullptr, c->d_fwd, c->d_fwd_fp, c->d_limb, nullptr, 1, 1, c->log_n, 0 };

@@ -30,6 +30,29 @@
 
 namespace moai
 {
+    // Fast base conversion fused into the forward NTT's first pass (NttPrologue mode 3).  Output polynomial
+    // (b, I, g) of an [batch][rns][digits][n] buffer is the conversion of source limbs s0[g] .. s0[g] + cnt[g] - 1
+    // of batch item b (coefficient form, already multiplied by (Q_g / q_j)^-1 mod q_j) into target modulus m_I:
+    //     sum_j y_j * [(Q_g / q_j) mod m_I]  -  v * [Q_g mod m_I],   v = rint(sum_j y_j / q_j)
+    // i.e. the centred CRT lift of the digit, |D| <= Q_g / 2 (the float v is the same for every target modulus:
+    // identical operations on identical inputs).  Used for the grouped digits of the fast-mode key switch and
+    // for its mod-down by several primes (csrc/ksgroup.cu).
+    constexpr int CONV_MAX = 16; // source limbs per digit
+    struct ConvTab
+    {
+        const int *s0 = nullptr;             // [digits]
+        const int *cnt = nullptr;            // [digits]
+        const double *invq = nullptr;        // [src_limbs] 1 / q_src
+        const unsigned char *wide = nullptr; // [src_limbs] 1: residues may reach 2^52 (split 2^26 hi + lo on the FP64 path)
+        const u64 *B = nullptr;              // [digits][rns][CONV_MAX]  (Q_g / q_j) mod m_I
+        const u64 *B26 = nullptr;            // [digits][rns][CONV_MAX]  2^26 (Q_g / q_j) mod m_I   (wide sources)
+        const double *Bd = nullptr;          // the same two tables as centred doubles (FP64-path targets only)
+        const double *B26d = nullptr;
+        const u64 *negQ = nullptr;           // [digits][rns]  (-Q_g) mod m_I
+        const double *negQd = nullptr;       // centred double
+        int src_limbs = 0;
+    };
+
     struct NttArgs
     {
         u64 *data;             // [count][n]
@@ -48,6 +71,8 @@ namespace moai
         //   src_mode 2 (divide-and-round expansion, S/util/rns.cpp:851-880 / S/evaluator.cpp:2966-2990):
         //              polynomial p reads t = src[p / period] (coefficients modulo prime `last_id`) and
         //              forms ((t + half) mod q_last) mod q_i + (q_i - half mod q_i).
+        //   src_mode 3 (fast base conversion, ConvTab above): polynomial p = (b, I, g) with
+        //              b = p / (period*div), I = (p / div) % period, g = p % div.
         // pass B only: logical polynomial p lives at data + ((p / grp_size) * grp_stride + p % grp_size) * n
         // (grp_size = 0: contiguous)
         long long grp_size = 0, grp_stride = 0;
@@ -56,6 +81,7 @@ namespace moai
         int last_id = 0;
         int kl = 0;
         const u64 *half_mod = nullptr; // [kl][kl]
+        ConvTab conv;
     };
 
     struct NttPrologue
@@ -63,7 +89,22 @@ namespace moai
         const u64 *src = nullptr;
         int mode = 0;
         int last_id = 0;
+        const ConvTab *conv = nullptr; // mode 3
     };
+
+    // Shape of a key-switch inner product.  SEAL's per-prime digits (S/evaluator.cpp:2805-2909): digits = limbs,
+    // rns = limbs + 1, n_data = limbs.  Grouped digits (csrc/ksgroup.cu): digits = groups in use, rns = limbs + k + 1.
+    // Key layout [digit][2][key_kl][n]; target I reads key limb I (I < n_data) or I + key_kl - rns (the trailing
+    // extra / special primes sit at the end of a key polynomial).
+    struct KsShape
+    {
+        int digits = 0;
+        int rns = 0;
+        int n_data = 0;
+        const int *ids = nullptr; // device [rns]: prime index of target modulus I
+    };
+    KsShape ks_shape_seal(Context *c, int limbs);
+
 
     // Transforms `count` consecutive polynomials in place; polynomial p lives at data + p*n and
     // uses the prime with index d_limb_ids[(p / div) % period].
@@ -78,12 +119,13 @@ namespace moai
     // in one pass on the FP64 pipe; acc[r][batch][2][limbs+1][n] receives canonical residues for every
     // FP64-path modulus (integer-path moduli are left untouched).
     constexpr int KSM_R = 4;
-    void ks_mac_multi(Context *c, const u64 *ext, long long batch, int limbs, int n_keys, const u64 *const *ksk,
+    void ks_mac_multi(Context *c, const u64 *ext, long long batch, const KsShape &sh, int n_keys, const u64 *const *ksk,
                       const int *key_kl, u64 *const *acc);
     // Fused key-switch kernel (csrc/ntt.cu): pass B of the digit-extension NTT + inner product with
-    // the evk for every FP64-path modulus.  mid = pass-A output [batch][limbs+1][limbs][n];
-    // acc[batch][2][limbs+1][n] receives canonical residues for those moduli (integer-path moduli
+    // the evk for every FP64-path modulus.  mid = pass-A output [batch][rns][digits][n];
+    // acc[batch][2][rns][n] receives canonical residues for those moduli (integer-path moduli
     // are left untouched for the un-fused kernels).
-    void ks_passb_mac(Context *c, const u64 *mid, long long batch, int limbs, const u64 *ksk, int key_kl, u64 *acc);
+    void ks_passb_mac(Context *c, const u64 *mid, long long batch, const KsShape &sh, const u64 *ksk, int key_kl,
+                      u64 *acc);
     void ntt_inverse(Context *c, u64 *data, long long count, const int *d_limb_ids, int period, int div = 1);
 } // namespace moai

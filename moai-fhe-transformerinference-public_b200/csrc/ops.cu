@@ -12,6 +12,7 @@
 // lookup per thread (limb index is uniform per 2-element vector because n is even).
 #include "ntt.cuh"
 #include "ops.cuh"
+#include "ksgroup.hpp"
 #include <cstdlib>
 
 namespace moai
@@ -524,8 +525,8 @@ namespace moai
 
         // acc[b][k][I][n] = sum_J ext[b][I][J][n] * ksk[J][k][ids_ks[I]][n] mod m_I
         __global__ void k_ks_mac(const ulonglong2 *__restrict__ ext, const ulonglong2 *__restrict__ ksk,
-                                 ulonglong2 *__restrict__ acc, long long batch, int log_n2, int limbs, int key_kl,
-                                 const int *__restrict__ ids_ks, const LimbConst *__restrict__ lcs,
+                                 ulonglong2 *__restrict__ acc, long long batch, int log_n2, int limbs, int rns, int n_data,
+                                 int key_kl, const int *__restrict__ ids_ks, const LimbConst *__restrict__ lcs,
                                  const Twiddle *__restrict__ two64, int I0)
         {
             // grid: x = batch item (fastest, so that CTAs sharing a key tile run together and the evk
@@ -534,13 +535,13 @@ namespace moai
             const int I = blockIdx.y + I0; // I0: first target modulus of this launch
             const long long b = blockIdx.x;
             const int prime = ids_ks[I];
-            // position of modulus I inside the key: data limbs first, the special prime last
-            // (a level-truncated key keeps only key_kl - 1 data limbs, see key_prepare)
-            const int key_limb = I == limbs ? key_kl - 1 : I;
+            // position of modulus I inside the key: data limbs first, the extra / special primes last
+            // (a level-truncated key keeps fewer data limbs, see key_prepare; KsShape in ntt.cuh); limbs = digits
+            const int key_limb = I < n_data ? I : I + key_kl - rns;
             const LimbConst lc = lcs[prime];
             const Twiddle t64 = two64[prime];
             const long long n2 = (long long)1 << log_n2;
-            const ulonglong2 *e = ext + ((b * (limbs + 1) + I) * limbs << log_n2) + within;
+            const ulonglong2 *e = ext + ((b * rns + I) * limbs << log_n2) + within;
             u128 a0x{ 0, 0 }, a0y{ 0, 0 }, a1x{ 0, 0 }, a1y{ 0, 0 };
             for (int J = 0; J < limbs; J++)
             {
@@ -557,12 +558,40 @@ namespace moai
             r0.y = barrett_reduce_acc(a0y, lc, t64.w, t64.wq);
             r1.x = barrett_reduce_acc(a1x, lc, t64.w, t64.wq);
             r1.y = barrett_reduce_acc(a1y, lc, t64.w, t64.wq);
-            acc[(((b * 2 + 0) * (limbs + 1) + I) << log_n2) + within] = r0;
-            acc[(((b * 2 + 1) * (limbs + 1) + I) << log_n2) + within] = r1;
+            acc[(((b * 2 + 0) * rns + I) << log_n2) + within] = r0;
+            acc[(((b * 2 + 1) * rns + I) << log_n2) + within] = r1;
         }
     } // namespace
 
     // ====================================================================== launchers
+    // 128-bit integer inner product of target modulus I (integer-path moduli of a key switch of shape `sh`)
+    void ks_mac_int(Context *c, const u64 *ext, const u64 *ksk, u64 *acc, long long batch, const KsShape &sh, int key_kl,
+                    int I)
+    {
+        dim3 grid((unsigned)batch, 1u, (unsigned)((c->n / 2) / EW_THREADS));
+        KernelTimer kt(c, "k_ks_mac", 1);
+        k_ks_mac<<<grid, EW_THREADS, 0, c->stream>>>(reinterpret_cast<const ulonglong2 *>(ext),
+                                                     reinterpret_cast<const ulonglong2 *>(ksk),
+                                                     reinterpret_cast<ulonglong2 *>(acc), batch, c->log_n - 1, sh.digits,
+                                                     sh.rns, sh.n_data, key_kl, sh.ids, c->d_limb, c->d_two64, I);
+        c->launches += 1;
+        MOAI_CUDA_CHECK(cudaGetLastError());
+    }
+
+    // out[P][targets][n] = (in[P][limbs_in][n](limb j < targets) - u[P][targets][n]) * inv[j] mod q_j (+ addend)
+    void divround_finish(Context *c, const u64 *in, const u64 *u, const u64 *addend, u64 *out, long long P, int targets,
+                         int limbs_in, const Twiddle *d_inv, bool addend_even_only)
+    {
+        const long long total2 = P * targets * (long long)(c->n / 2);
+        KernelTimer kt(c, "k_divround_finish", 1);
+        k_divround_finish<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
+            reinterpret_cast<const ulonglong2 *>(in), reinterpret_cast<const ulonglong2 *>(u),
+            reinterpret_cast<const ulonglong2 *>(addend), reinterpret_cast<ulonglong2 *>(out), total2, c->log_n - 1,
+            targets, limbs_in, 0, 0, c->d_limb, d_inv, addend_even_only ? 1 : 0);
+        c->launches += 1;
+        MOAI_CUDA_CHECK(cudaGetLastError());
+    }
+
     void ew_addsub(Context *c, int op, const u64 *a, const u64 *b, u64 *out, long long batch, int polys, int limbs,
                    bool b_broadcast)
     {
@@ -872,7 +901,8 @@ namespace moai
         KernelTimer kt12(c, "k_ks_mac", 1);
         k_ks_mac<<<grid, EW_THREADS, 0, c->stream>>>(reinterpret_cast<const ulonglong2 *>(ext),
                                                      reinterpret_cast<const ulonglong2 *>(ksk), acc.as<ulonglong2>(),
-                                                     batch, c->log_n - 1, limbs, key_kl, ids_ks, c->d_limb, c->d_two64, 0);
+                                                     batch, c->log_n - 1, limbs, rns, limbs, key_kl, ids_ks, c->d_limb,
+                                                     c->d_two64, 0);
         c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
         divide_round_last(c, acc.as<u64>(), batch * 2, rns, c->kl - 1, addend, out, addend_c0_only);
@@ -899,7 +929,7 @@ namespace moai
         pro.mode = 1;
         ntt_forward(c, ext, batch * rns * limbs, ids_ks, rns, limbs, &pro, /*passes=*/1);
         Scratch acc((size_t)batch * 2 * rns * n * sizeof(u64), c->stream);
-        ks_passb_mac(c, ext, batch, limbs, ksk, key_kl, acc.as<u64>());
+        ks_passb_mac(c, ext, batch, ks_shape_seal(c, limbs), ksk, key_kl, acc.as<u64>());
         for (int I = 0; I < rns; I++)
         {
             const int prime = I == limbs ? c->kl - 1 : I;
@@ -913,8 +943,8 @@ namespace moai
             KernelTimer kt13(c, "k_ks_mac", 1);
             k_ks_mac<<<grid, EW_THREADS, 0, c->stream>>>(reinterpret_cast<const ulonglong2 *>(ext),
                                                          reinterpret_cast<const ulonglong2 *>(ksk),
-                                                         acc.as<ulonglong2>(), batch, c->log_n - 1, limbs, key_kl,
-                                                         ids_ks, c->d_limb, c->d_two64, I);
+                                                         acc.as<ulonglong2>(), batch, c->log_n - 1, limbs, rns, limbs,
+                                                         key_kl, ids_ks, c->d_limb, c->d_two64, I);
             c->launches += 1;
             MOAI_CUDA_CHECK(cudaGetLastError());
         }
@@ -926,10 +956,18 @@ namespace moai
     // One rotation with a pre-permuted key and its own digit decomposition (giant steps, conjugation):
     // out = sigma((c0, 0) + keyswitch(c1; K')), through the fused key-switch kernel when the primes allow.
     void rotate_prepermuted(Context *c, const u64 *ct, long long batch, int limbs, uint32_t elt, const u64 *ksk_pre,
-                            int key_kl, u64 *out)
+                            int key_kl, u64 *out, int k_extra)
     {
         const size_t n = c->n;
         const size_t per_ct = (size_t)2 * limbs * n;
+        if (k_extra > 0)
+        {
+            Scratch tmpg((size_t)batch * per_ct * sizeof(u64), c->stream);
+            ksg_switch(c, ct + (size_t)limbs * n, batch, limbs, k_extra, ksk_pre, key_kl, ct, tmpg.as<u64>(),
+                       (long long)per_ct, true);
+            apply_galois_ntt(c, tmpg.as<u64>(), out, batch * 2 * limbs, elt);
+            return;
+        }
         const long long chunk = ks_chunk(c, limbs, batch, ks_ext_budget());
         const bool fused = ks_can_fuse(c, limbs);
         Scratch ext((size_t)chunk * ks_ext_bytes_per_ct(c, limbs), c->stream);
@@ -991,10 +1029,16 @@ namespace moai
         return chunk < 1 ? 1 : (chunk > batch ? batch : chunk);
     }
 
-    void switch_key(Context *c, u64 *ct, const u64 *target, long long batch, int limbs, const u64 *ksk, int key_kl)
+    void switch_key(Context *c, u64 *ct, const u64 *target, long long batch, int limbs, const u64 *ksk, int key_kl,
+                    int k_extra)
     {
         MOAI_REQUIRE(limbs >= 1 && limbs <= c->kl - 1, "limb count out of range");
         const size_t n = c->n;
+        if (k_extra > 0)
+        {
+            ksg_switch(c, target, batch, limbs, k_extra, ksk, key_kl, ct, ct, 0, false);
+            return;
+        }
         if (key_kl <= 0)
         {
             key_kl = c->kl;
@@ -1050,7 +1094,7 @@ namespace moai
             accp[r] = acc.as<u64>() + acc_words * r;
             MOAI_REQUIRE(key_kl[r] >= limbs + 1 && key_kl[r] <= c->kl, "key does not cover this level");
         }
-        ks_mac_multi(c, ext, batch, limbs, n_rot, ksk_pre, key_kl, accp);
+        ks_mac_multi(c, ext, batch, ks_shape_seal(c, limbs), n_rot, ksk_pre, key_kl, accp);
         for (int I = 0; I < rns; I++)
         {
             const int prime = I == limbs ? c->kl - 1 : I;
@@ -1065,7 +1109,7 @@ namespace moai
                 k_ks_mac<<<grid, EW_THREADS, 0, c->stream>>>(reinterpret_cast<const ulonglong2 *>(ext),
                                                              reinterpret_cast<const ulonglong2 *>(ksk_pre[r]),
                                                              reinterpret_cast<ulonglong2 *>(accp[r]), batch, c->log_n - 1,
-                                                             limbs, key_kl[r], ids_ks, c->d_limb, c->d_two64, I);
+                                                             limbs, rns, limbs, key_kl[r], ids_ks, c->d_limb, c->d_two64, I);
                 c->launches += 1;
             }
             MOAI_CUDA_CHECK(cudaGetLastError());
@@ -1131,7 +1175,8 @@ namespace moai
         }
     }
 
-    void relinearize(Context *c, const u64 *in3, u64 *out2, long long batch, int limbs, const u64 *ksk, int key_kl)
+    void relinearize(Context *c, const u64 *in3, u64 *out2, long long batch, int limbs, const u64 *ksk, int key_kl,
+                     int k_extra)
     {
         const size_t n = c->n;
         const size_t poly = (size_t)limbs * n;
@@ -1141,7 +1186,7 @@ namespace moai
         Scratch tg((size_t)batch * poly * sizeof(u64), c->stream);
         { KernelTimer ktm(c, "k_copy_relin_c2", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(tg.p, poly * sizeof(u64), in3 + 2 * poly, 3 * poly * sizeof(u64),
                                           poly * sizeof(u64), (size_t)batch, cudaMemcpyDeviceToDevice, c->stream)); }
-        switch_key(c, out2, tg.as<u64>(), batch, limbs, ksk, key_kl);
+        switch_key(c, out2, tg.as<u64>(), batch, limbs, ksk, key_kl, k_extra);
     }
 
     void apply_galois(Context *c, const u64 *in, u64 *out, long long batch, int limbs, uint32_t elt, const u64 *ksk,

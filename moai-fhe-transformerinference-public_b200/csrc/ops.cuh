@@ -49,9 +49,11 @@ namespace moai
     void apply_galois_ntt(Context *c, const u64 *in, u64 *out, long long count_polys_limbs, uint32_t elt);
     // key_kl = limbs stored per key polynomial: 0 / c->kl for SEAL's layout [kl-1][2][kl][n], L + 1 for
     // a key truncated to L levels by key_prepare ([L][2][L+1][n])
-    void switch_key(Context *c, u64 *ct, const u64 *target, long long batch, int limbs, const u64 *ksk, int key_kl = 0);
+    // k_extra > 0: `ksk` is a grouped-digit key of ksg_key_prepare (csrc/ksgroup.hpp; fast mode, not SEAL's residues)
+    void switch_key(Context *c, u64 *ct, const u64 *target, long long batch, int limbs, const u64 *ksk, int key_kl = 0,
+                    int k_extra = 0);
     void relinearize(Context *c, const u64 *in3, u64 *out2, long long batch, int limbs, const u64 *ksk,
-                     int key_kl = 0);
+                     int key_kl = 0, int k_extra = 0);
     void apply_galois(Context *c, const u64 *in, u64 *out, long long batch, int limbs, uint32_t elt, const u64 *ksk,
                       int key_kl = 0);
     // the two halves of a key switch, exposed for hoisting (one decomposition, many rotations)
@@ -65,7 +67,13 @@ namespace moai
                         const u64 *ksk_pre, int key_kl, u64 *out);
     // one rotation with a pre-permuted key and its own decomposition (fused key-switch kernel)
     void rotate_prepermuted(Context *c, const u64 *ct, long long batch, int limbs, uint32_t elt, const u64 *ksk_pre,
-                            int key_kl, u64 *out);
+                            int key_kl, u64 *out, int k_extra = 0);
+    // pieces shared with csrc/ksgroup.cu
+    struct KsShape;
+    void ks_mac_int(Context *c, const u64 *ext, const u64 *ksk, u64 *acc, long long batch, const KsShape &sh, int key_kl,
+                    int I);
+    void divround_finish(Context *c, const u64 *in, const u64 *u, const u64 *addend, u64 *out, long long P, int targets,
+                         int limbs_in, const Twiddle *d_inv, bool addend_even_only);
     // up to KSM_R (csrc/ntt.cuh) hoisted rotations in one pass over the extended digits
     bool ks_multi_enabled(Context *c, int limbs);
     void rotate_hoisted_multi(Context *c, const u64 *ct, const u64 *ext, long long batch, int limbs, int n_rot,

@@ -26,7 +26,11 @@ def main():
     ap.add_argument("--fast", action="store_true", help="hoisted baby steps with pre-permuted keys (fast mode)")
     ap.add_argument("--real", action="store_true", help="real-slot messages, two per bootstrapping (moai_bootstrap_real); "
                                                         "--batch counts ciphertexts, so batch/2 bootstrappings run")
+    ap.add_argument("--grouped", action="store_true", help="fast mode with grouped-digit keys (csrc/ksgroup.hpp): every "
+                                                           "Galois key in the digit layout its level prefers, the "
+                                                           "relinearisation key in one variant per layout")
     args = ap.parse_args()
+    args.fast = args.fast or args.grouped
     pkg = importlib.import_module("moai-fhe-transformerinference-public_b200")
     primes = bench.moai_primes()
     be = pkg.Backend(16, primes)
@@ -51,7 +55,26 @@ def main():
     for st in steps + [0]:
         gal[be.galois_elt_from_step(st)] = rand_key()
     # random residues stand in for key material; a pre-permuted key is the same size and layout
-    keys = be.make_keys(relin=rand_key(), galois_fast=gal) if args.fast else be.make_keys(relin=rand_key(), galois=gal)
+    key_bytes = 0
+    if args.grouped:
+        gal, grouped = {}, {}
+        for st, lvs in boot.required_step_levels().items():
+            e = be.galois_elt_from_step(st)
+            for lv in lvs:
+                k = be.ksg_best_extra(lv)
+                if k == 0:   # no spare prime at this level: SEAL's digits, level-truncated
+                    t = rand_key()[:lv, :, :lv + 1, :].contiguous()
+                    gal.setdefault(e, []).append(t)
+                    key_bytes += t.numel() * 8
+                else:
+                    gk = be.random_grouped_key(k, lv, g)
+                    grouped.setdefault(e, []).append(gk)
+                    key_bytes += gk.t.numel() * 8
+        grouped[0] = [be.random_grouped_key(k, lv, g) for k, lv in sorted(be.ksg_plan(range(1, 35)).items())]
+        key_bytes += sum(gk.t.numel() * 8 for gk in grouped[0])
+        keys = be.make_keys(relin=rand_key(), galois_fast=gal, grouped=grouped)
+    else:
+        keys = be.make_keys(relin=rand_key(), galois_fast=gal) if args.fast else be.make_keys(relin=rand_key(), galois=gal)
     x = torch.randint(0, primes[0], (args.batch, 2, 1, n), generator=g, device="cuda", dtype=torch.int64)
     run = (lambda: boot.bootstrap_real(keys, x, 2.0 ** 46, chunk_pairs=32)) if args.real else \
         (lambda: boot.bootstrap_3(keys, x, 2.0 ** 46))
@@ -77,7 +100,8 @@ def main():
     ms = e0.elapsed_time(e1) / args.iters
     per_ct = ms / args.batch
     per_layer_s = per_ct * 3084 / 1000.0
-    print(json.dumps({"op": "bootstrap_real (two real-slot ciphertexts per bootstrapping)" if args.real else "bootstrap_3", "batch": args.batch, "keys": args.keys, "mode": "fast (hoisted)" if args.fast else "exact (SEAL key switch)",
+    print(json.dumps({"op": "bootstrap_real (two real-slot ciphertexts per bootstrapping)" if args.real else "bootstrap_3", "batch": args.batch, "keys": args.keys, "mode": ("fast (hoisted, grouped digits)" if args.grouped else "fast (hoisted)") if args.fast else "exact (SEAL key switch)",
+                      "grouped_key_GiB": round(key_bytes / 2 ** 30, 2),
                       "galois_keys": len(gal), "clocks": clocks,
                       "ms_per_batch": round(ms, 2), "ms_per_ciphertext": round(per_ct, 2), "phase_ms_per_ciphertext": phases,
                       "projected_bootstrap_s_per_layer": round(per_layer_s, 1),
