@@ -426,7 +426,8 @@ def run_layer(args):
     device = torch.device("cuda", local_rank)
     part_a = args.partition == "A" and world > 1
     # replicas: every rank has its own packed batch (own seed); partitioning A: ONE packed batch, identical on every rank
-    st = layer_bench.setup(layer_bench.Args(1, "fast"), device=local_rank, seed=11 + (0 if part_a else rank))
+    st = layer_bench.setup(layer_bench.Args(1, os.environ.get("MOAI_LAYER_MODE", "grouped")), device=local_rank,
+                           seed=11 + (0 if part_a else rank))
     be, boot, keys, w, x, mask = st["be"], st["boot"], st["keys"], st["w"], st["x"], st["mask"]
     if part_a:
         be.comm_init(dist)

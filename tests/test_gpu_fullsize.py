@@ -34,8 +34,10 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lay
 GOLDEN_REF = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "layer0_reference_decrypted.npz")
 
 
-@pytest.fixture(scope="module")
-def env(pkg):
+@pytest.fixture(scope="module", params=["grouped", "fast"])
+def env(pkg, request):
+    """Both fast-mode key layouts: "grouped" (grouped-digit keys derived from the stock keys, csrc/ksgroup.hpp — what
+    bench.py times) and "fast" (SEAL's per-prime digits, pre-permuted)."""
     import torch
     from devkeygen import DeviceKeyGen
     from oracle import Oracle, MOAI_BITS
@@ -44,21 +46,40 @@ def env(pkg):
     kg = DeviceKeyGen(pkg, be, hamming_weight=192, seed=20250991)
     boot = pkg.Bootstrapper(be, total_limbs=35)
     boot.set_hoisting(True)
-    fast = {}
-    for st in boot.required_steps() + [0]:
-        e = be.galois_elt_from_step(st)
-        k = kg.galois_key(e)
-        fast.setdefault(e, []).append(be.key_prepare(k, e))
-        del k
-    keys = be.make_keys(relin=kg.relin_key(), galois_fast=fast)
+    fast, grouped = {}, {}
+    if request.param == "grouped":
+        for st, lvs in sorted(boot.required_step_levels().items()):
+            e = be.galois_elt_from_step(st)
+            k = kg.galois_key(e)
+            for lv in lvs:
+                gk = be.key_prepare_grouped(k, e, lv)
+                if gk is None:      # no spare prime at the top level: SEAL's digits
+                    fast.setdefault(e, []).append(be.key_prepare(k, e, max_limbs=lv))
+                else:
+                    grouped.setdefault(e, []).append(gk)
+            del k
+        relin = kg.relin_key()
+        relin4 = relin.reshape(be.kl - 1, 2, be.kl, N)
+        grouped[0] = [be.key_prepare_grouped(relin4, 0, lv, k_extra=k, pre_permute=False)
+                      for k, lv in sorted(be.ksg_plan(range(1, be.kl - 1)).items())]
+        keys = be.make_keys(relin=relin, galois_fast=fast, grouped=grouped)
+    else:
+        for st in boot.required_steps() + [0]:
+            e = be.galois_elt_from_step(st)
+            k = kg.galois_key(e)
+            fast.setdefault(e, []).append(be.key_prepare(k, e))
+            del k
+        keys = be.make_keys(relin=kg.relin_key(), galois_fast=fast)
     torch.cuda.synchronize()
+    print("\n[%s keys: %.1f GiB on the device]" % (request.param, torch.cuda.memory_allocated() / 2 ** 30))
     mask = np.zeros(SLOTS, dtype=np.int32)
     for k in range(TOK):
         mask[k * NUM_BATCH] = 1                           # bias_vec(input_len = {5, 0, ...}), Batch_encode_encrypt.hpp:39-49
     yield {"o": o, "be": be, "kg": kg, "boot": boot, "keys": keys, "mask": mask, "g": np.load(GOLDEN),
            "ref": np.load(GOLDEN_REF)}
-    del keys, fast
+    del keys, fast, grouped
     be.close()
+    torch.cuda.empty_cache()
 
 
 @pytest.fixture(autouse=True)

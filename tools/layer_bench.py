@@ -65,6 +65,31 @@ def setup(args, device=0, seed=11):
                 gal[e] = rand_key(14)
         keys = be.make_keys(relin=rand_key(), galois=gal)
         n_keys = len(gal)
+    elif args.mode == "grouped":
+        # fast mode with grouped-digit keys (csrc/ksgroup.hpp): every Galois key in the digit layout the cost model
+        # prefers at the level it is used at, the relinearisation key in one variant per layout
+        boot.set_hoisting(True)
+        dev = torch.device("cuda", device)
+        gal, grouped = {}, {}
+
+        def add(st, level):
+            e = be.galois_elt_from_step(st)
+            k = be.ksg_best_extra(level)
+            if k == 0:
+                gal.setdefault(e, []).append(rand_key(level))
+            else:
+                grouped.setdefault(e, []).append(be.random_grouped_key(k, level, g))
+
+        for st, lvs in sorted(boot.required_step_levels().items()):
+            for lv in lvs:
+                add(st, lv)
+        att = pkg.attention_rotation_steps(256)
+        for tag, level in (("qk", 14), ("sv", 3)):
+            for st in att[tag]:
+                add(st, level)
+        grouped[0] = [be.random_grouped_key(k, lv, g) for k, lv in sorted(be.ksg_plan(range(1, kl - 1)).items())]
+        keys = be.make_keys(relin=rand_key(), galois_fast=gal, grouped=grouped)
+        n_keys = sum(len(v) for v in gal.values()) + sum(len(v) for v in grouped.values())
     else:
         boot.set_hoisting(True)
         gal = {}
@@ -101,8 +126,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--layers", type=int, default=1,
                     help="encoder layers run back to back on the same packed batch (BASELINE config 5 = 12)")
-    ap.add_argument("--mode", default="fast", choices=["fast", "exact"],
-                    help="fast: hoisted rotations, pre-permuted level-truncated keys; exact: SEAL-identical key switches")
+    ap.add_argument("--mode", default="grouped", choices=["grouped", "fast", "exact"],
+                    help="grouped: fast mode with grouped-digit keys (default); fast: hoisted rotations, pre-permuted "
+                         "level-truncated keys; exact: SEAL-identical key switches")
     args = ap.parse_args()
     st = setup(args)
     be, boot, keys, w, x, mask = st["be"], st["boot"], st["keys"], st["w"], st["x"], st["mask"]
