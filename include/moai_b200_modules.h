@@ -81,6 +81,14 @@ int32_t moai_key_prepare_grouped(moai_context *ctx, const uint64_t *ksk_in, uint
                                  int32_t max_limbs, int32_t pre_permute, uint64_t *ksk_out);
 int32_t moai_keys_add_grouped(moai_keys *keys, uint32_t galois_elt, const uint64_t *ksk_grouped, int32_t k_extra,
                               int32_t max_limbs);
+/* Single-digit keys for rotations of a MOD-RAISED ciphertext (Bootstrapper::modraise_inplace, Bootstrapper.cpp:2938-2992):
+ * its c1 is the centred lift of residues modulo q_0, i.e. as an integer polynomial it is ONE digit below the special
+ * prime, and sum_J K_J encrypts p * s': the key switch needs no decomposition at all (one NTT for the special prime).
+ * moai_key_prepare_single: SEAL-layout key -> [1][2][key_limbs][N]; used by the first CoeffToSlot stage in hoisting
+ * mode 2 (moai_bootstrapper_set_hoisting), which then runs on baby steps only.                                      */
+int32_t moai_key_prepare_single(moai_context *ctx, const uint64_t *ksk_in, uint32_t galois_elt, int32_t pre_permute,
+                                uint64_t *ksk_out);
+int32_t moai_keys_add_single(moai_keys *keys, uint32_t galois_elt, const uint64_t *ksk_single);
 /* SEAL-exact rotations with a level-truncated key (moai_key_prepare with pre_permute = 0): the residues are
  * SEAL's bit for bit — a key switch at l limbs never reads digits or limbs beyond l — at (L/35)^2 of the
  * memory; a rotation above L limbs with such a key is rejected.                                    */
@@ -131,8 +139,11 @@ typedef struct moai_bootstrapper moai_bootstrapper;
 int32_t moai_bootstrapper_create(moai_context *ctx, int32_t total_limbs, double final_scale, int32_t boundary_K,
                                  int32_t deg, int32_t double_angles, int32_t log_width, moai_bootstrapper **out);
 int32_t moai_bootstrapper_destroy(moai_bootstrapper *b);
-/* fast mode: plan the linear stages for hoisted baby steps (16 baby x 4 giant instead of 8 x 8);
- * call before moai_bootstrapper_required_steps and register the keys with moai_keys_add_galois_fast */
+/* fast mode: on = 1 plans the linear stages for hoisted baby steps (16 baby x 4 giant instead of 8 x 8); on = 2
+ * additionally keeps the baby-step rotations in the key-switch basis (one mod-down per giant step instead of one per
+ * baby step) and runs the first CoeffToSlot stage on single-digit keys with baby steps only; call before
+ * moai_bootstrapper_required_steps[_levels] and register the keys with moai_keys_add_galois_fast / _grouped / _single.
+ * moai_bootstrapper_required_step_levels reports the steps that want a single-digit key with limbs = 0.           */
 int32_t moai_bootstrapper_set_hoisting(moai_bootstrapper *b, int32_t on);
 int32_t moai_bootstrapper_required_steps(moai_bootstrapper *b, int32_t *steps, int32_t capacity, int32_t *count);
 /* the same steps with the level (limb count) each is used at; step 0 = the complex conjugation

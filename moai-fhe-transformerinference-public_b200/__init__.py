@@ -386,11 +386,12 @@ class Backend:
         return out[0] if single else out
 
     # ---- evaluation keys + MOAI modules (B4-B9)
-    def make_keys(self, relin=None, galois=None, galois_fast=None, grouped=None):
+    def make_keys(self, relin=None, galois=None, galois_fast=None, grouped=None, single=None):
         """relin: device key tensor; galois: dict galois_elt -> device key tensor (SEAL layout,
         bit-exact rotations); galois_fast: dict galois_elt -> tensor or list of tensors produced by
         key_prepare(pre_permute=True), shaped [L, 2, L + 1, n] (hoisted fast-mode rotations);
-        grouped: dict galois_elt (0 = relinearisation key) -> list of GroupedKey from key_prepare_grouped.
+        grouped: dict galois_elt (0 = relinearisation key) -> list of GroupedKey from key_prepare_grouped;
+        single: dict galois_elt -> tensor [1, 2, kl, n] from key_prepare_single (rotations of mod-raised ciphertexts).
         The returned handle keeps the tensors alive."""
         h = C.c_void_p()
         self._chk(self.lib.moai_keys_create(self.h, C.byref(h)))
@@ -408,6 +409,9 @@ class Backend:
             for t in (ts if isinstance(ts, (list, tuple)) else [ts]):
                 self._chk(self.lib.moai_keys_add_galois_fast(h, C.c_uint32(elt), _ptr(t), C.c_int32(t.shape[2])))
                 keep.append(t)
+        for elt, t in (single or {}).items():
+            self._chk(self.lib.moai_keys_add_single(h, C.c_uint32(elt), _ptr(t)))
+            keep.append(t)
         for elt, gks in (grouped or {}).items():
             for gk in (gks if isinstance(gks, (list, tuple)) else [gks]):
                 self._chk(self.lib.moai_keys_add_grouped(h, C.c_uint32(elt), _ptr(gk.t), C.c_int32(gk.k_extra),
@@ -460,6 +464,13 @@ class Backend:
         self._chk(self.lib.moai_key_prepare_grouped(self.h, _ptr(ksk), C.c_uint32(elt), C.c_int32(k), C.c_int32(max_limbs),
                                                     C.c_int32(int(pre_permute)), _ptr(out)))
         return GroupedKey(out, k, max_limbs)
+
+    def key_prepare_single(self, ksk, elt, pre_permute=True):
+        """SEAL-layout Galois key -> single-digit key [1, 2, kl, n] (sum of all digits, pre-permuted) for rotations of a
+        mod-raised ciphertext (first CoeffToSlot stage, hoisting mode 2)."""
+        out = self.empty(1, 2, self.kl, self.n)
+        self._chk(self.lib.moai_key_prepare_single(self.h, _ptr(ksk), C.c_uint32(elt), C.c_int32(int(pre_permute)), _ptr(out)))
+        return out
 
     def key_prepare(self, ksk, elt, max_limbs=None, pre_permute=True):
         """SEAL-layout Galois key [kl-1, 2, kl, n] -> level-truncated (and pre-permuted) key

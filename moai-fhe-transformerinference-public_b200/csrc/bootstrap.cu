@@ -231,6 +231,7 @@ namespace moai
                     cts_[s].diags[off] = kv.second;
                 }
                 cts_[s].limbs = prm.total_limbs - s;
+                cts_[s].first = s == 0;
                 plan_bsgs(cts_[s]);
             }
         }
@@ -281,7 +282,7 @@ namespace moai
             for (auto &kv : st.diags)
             {
                 const int e = kv.first / stride;
-                const int i = (int)std::floor((double)e / g);
+                const int i = g > 0 ? (int)std::floor((double)e / g) : 0; // g == 0: baby steps only (signed j)
                 bs.insert(e - i * g);
                 gs.insert(i);
             }
@@ -292,7 +293,40 @@ namespace moai
             g++;
         }
         std::set<int> bs, gs;
-        if (prm.hoisting)
+        if (prm.hoisting == 2)
+        {
+            // lazy mod-down: a baby step costs an inner product and one gather-multiply pass, a giant step a full
+            // key switch plus the mod-down of its inner sum: ~1 : 8 (1 : 50 on the first stage, whose baby steps run
+            // on single-digit keys while its giant steps would pay SEAL's 35-digit key switch: baby steps only)
+            double best = 1e300;
+            int best_g = g;
+            const int max_baby = st.first ? 64 : BSGS_MAX_BABY;
+            for (int cand = st.first ? 0 : 1; cand <= 64; cand++)
+            {
+                split(cand, bs, gs);
+                if ((int)bs.size() > max_baby || (int)gs.size() > BSGS_MAX_GIANT)
+                {
+                    continue;
+                }
+                int nb = 0, ng = 0;
+                for (int j : bs)
+                {
+                    nb += j != 0;
+                }
+                for (int i : gs)
+                {
+                    ng += i != 0;
+                }
+                const double cost = nb * 1.0 + ng * (st.first ? 50.0 : 8.0) + (int)gs.size() * (st.first ? 3.0 : 1.0);
+                if (cost < best)
+                {
+                    best = cost;
+                    best_g = cand;
+                }
+            }
+            g = best_g;
+        }
+        else if (prm.hoisting)
         {
             // baby steps share one digit decomposition (hoisted: inner product + mod-down only), giant
             // steps pay a full key switch: weigh them ~1 : 3.5 (measured at 35 limbs) and stay inside
@@ -331,17 +365,42 @@ namespace moai
         st.giants.assign(gs.begin(), gs.end());
     }
 
-    void Bootstrapper::set_hoisting(bool on)
+    void Bootstrapper::set_hoisting(int mode)
     {
-        prm.hoisting = on ? 1 : 0;
+        MOAI_REQUIRE(mode >= 0 && mode <= 2, "hoisting mode must be 0, 1 or 2");
+        prm.hoisting = mode;
         for (int s = 0; s < 3; s++)
         {
+            cts_[s].first = s == 0;
             plan_bsgs(cts_[s]);
             plan_bsgs(stc_[s]);
             cts_[s].pts.clear(); // pre-rotation of the diagonals depends on the plan
             stc_[s].pts.clear();
+            cts_[s].pts_ext.clear();
+            stc_[s].pts_ext.clear();
+            cts_[s].pt_scale = 0;
+            stc_[s].pt_scale = 0;
         }
         stc_encoded_for_scale_ = 0;
+    }
+
+    std::vector<int> Bootstrapper::single_digit_steps() const
+    {
+        std::vector<int> out;
+        if (prm.hoisting != 2)
+        {
+            return out;
+        }
+        const int n = slots();
+        const LinearStage &st = cts_[0];
+        for (int j : st.baby)
+        {
+            if (j)
+            {
+                out.push_back(((j * st.stride) % n + n) % n);
+            }
+        }
+        return out;
     }
 
     std::vector<int> Bootstrapper::required_steps() const
@@ -381,11 +440,12 @@ namespace moai
             for (int s = 0; s < 3; s++)
             {
                 const LinearStage &st = dir == 0 ? cts_[s] : stc_[s];
+                const bool single = prm.hoisting == 2 && dir == 0 && s == 0; // level 0 = single-digit key
                 for (int j : st.baby)
                 {
                     if (j)
                     {
-                        out.insert({ ((j * st.stride) % n + n) % n, st.limbs });
+                        out.insert({ ((j * st.stride) % n + n) % n, single ? 0 : st.limbs });
                     }
                 }
                 for (int i : st.giants)
@@ -402,34 +462,76 @@ namespace moai
         return std::vector<std::pair<int, int>>(out.begin(), out.end());
     }
 
-    void Bootstrapper::encode_stage(const Evaluator &ev, LinearStage &st, double pt_scale)
+    void Bootstrapper::prepare_stage(LinearStage &st, double pt_scale, double diag_factor)
+    {
+        st.pt_scale = pt_scale;
+        st.diag_factor = diag_factor;
+        st.pts.clear();
+        st.pts_ext.clear();
+        st.ext_layout = -99;
+    }
+
+    void Bootstrapper::encode_stage(const Evaluator &ev, LinearStage &st, const std::vector<int> *ids)
     {
         const int n = slots();
-        st.pts.clear();
-        st.pt_scale = pt_scale;
+        MOAI_REQUIRE(st.pt_scale > 0, "linear stage has no plaintext scale yet");
+        auto &dst = ids ? st.pts_ext : st.pts;
+        dst.clear();
         // all pre-rotated diagonals of the stage in one batched device encode
         std::vector<std::pair<int, int>> keys;
         std::vector<cd> vals;
         for (auto &kv : st.diags)
         {
             const int e = kv.first / st.stride;
-            const int i = (int)std::floor((double)e / st.giant);
+            const int i = st.giant > 0 ? (int)std::floor((double)e / st.giant) : 0;
             const int j = e - i * st.giant;
             const long long G = (long long)i * st.giant * st.stride;
             keys.push_back({ i, j });
             // P[p] = diag[(p - G) mod n]
             for (int p = 0; p < n; p++)
             {
-                vals.push_back(kv.second[(((long long)p - G) % n + n) % n]);
+                vals.push_back(kv.second[(((long long)p - G) % n + n) % n] * st.diag_factor);
             }
         }
-        Pt all = ev.encode_batch(vals.data(), (long long)keys.size(), n, st.limbs, pt_scale);
+        Pt all;
+        int per = st.limbs;
+        if (!ids)
+        {
+            all = ev.encode_batch(vals.data(), (long long)keys.size(), n, st.limbs, st.pt_scale);
+        }
+        else
+        {
+            // encode over the whole chain, keep the listed primes: {0 .. l-1} and a trailing run {L-k .. L}
+            const int kl = c_->kl;
+            per = (int)ids->size();
+            int lead = 0;
+            while (lead < per && (*ids)[lead] == lead)
+            {
+                lead++;
+            }
+            for (int t = lead; t < per; t++)
+            {
+                MOAI_REQUIRE((*ids)[t] == kl - (per - t), "key-switch basis is not {0..l-1} + a trailing run of primes");
+            }
+            Pt full = ev.encode_batch(vals.data(), (long long)keys.size(), n, kl, st.pt_scale);
+            all.limbs = per;
+            all.scale = st.pt_scale;
+            all.count = (long long)keys.size();
+            all.buf = std::make_shared<DevBuf>(keys.size() * (size_t)per * c_->n * sizeof(u64), c_->stream);
+            all.d = reinterpret_cast<u64 *>(all.buf->p);
+            const size_t limb_b = c_->n * sizeof(u64);
+            MOAI_CUDA_CHECK(cudaMemcpy2DAsync(all.d, per * limb_b, full.d, kl * limb_b, lead * limb_b, keys.size(),
+                                              cudaMemcpyDeviceToDevice, c_->stream));
+            MOAI_CUDA_CHECK(cudaMemcpy2DAsync(all.d + (size_t)lead * c_->n, per * limb_b,
+                                              full.d + (size_t)(kl - (per - lead)) * c_->n, kl * limb_b,
+                                              (per - lead) * limb_b, keys.size(), cudaMemcpyDeviceToDevice, c_->stream));
+        }
         for (size_t k = 0; k < keys.size(); k++)
         {
             Pt one = all;
-            one.d = all.d + k * (size_t)st.limbs * c_->n;
+            one.d = all.d + k * (size_t)per * c_->n;
             one.count = 1;
-            st.pts[keys[k]] = one;
+            dst[keys[k]] = one;
         }
     }
 
@@ -464,9 +566,45 @@ namespace moai
     }
 
     // ------------------------------------------------------------------------------------ linear transforms
-    Ct Bootstrapper::linear_transform(const Evaluator &ev, const Ct &ct, LinearStage &st, const Keys &keys) const
+    Ct Bootstrapper::finish_giants(const Evaluator &ev, const Ct &ct, LinearStage &st, const Keys &keys,
+                                   const std::vector<int> &gi, std::vector<Ct> &inner) const
+    {
+        const long long n = slots();
+        auto norm = [&](long long step) { return (int)(((step % n) + n) % n); };
+        Ct acc;
+        for (size_t k = 0; k < gi.size(); k++)
+        {
+            const int gstep = norm((long long)gi[k] * st.giant * st.stride);
+            Ct term = gstep != 0 ? ev.rotate_vector(inner[k], gstep, keys) : inner[k];
+            inner[k] = Ct();
+            if (acc.empty())
+            {
+                acc = term;
+            }
+            else
+            {
+                ev.add_inplace(acc, term);
+            }
+        }
+        (void)ct;
+        return ev.rescale_to_next(acc);
+    }
+
+    Ct Bootstrapper::linear_transform(const Evaluator &ev, const Ct &ct, LinearStage &st, const Keys &keys)
     {
         MOAI_REQUIRE(ct.limbs == st.limbs, "linear stage applied at the wrong level");
+        if (prm.hoisting == 2)
+        {
+            Ct r = linear_transform_lazy(ev, ct, st, keys);
+            if (!r.empty())
+            {
+                return r;
+            }
+        }
+        if (st.pts.empty())
+        {
+            encode_stage(ev, st, nullptr);
+        }
         const long long n = slots();
         auto norm = [&](long long step) { return (int)(((step % n) + n) % n); }; // left rotation in [0, slots)
         // baby steps: rotations of the same ciphertexts (hoisted when the keys are pre-permuted)
@@ -475,6 +613,7 @@ namespace moai
         {
             bsteps.push_back(norm((long long)j * st.stride));
         }
+        MOAI_REQUIRE((int)st.baby.size() <= BSGS_MAX_BABY, "BSGS plan exceeds the fused kernel's limits");
         std::vector<Ct> rots = ev.rotate_many(ct, bsteps, keys);
         // every giant step's inner sum  sum_j P[i][j] (.) rot_j  in one fused pass
         const int nb = (int)st.baby.size();
@@ -513,22 +652,202 @@ namespace moai
         }
         bsgs_inner(c_, rp.data(), nb, pts.data(), (int)gi.size(), op.data(), ct.batch, ct.limbs);
         rots.clear();
-        Ct acc;
-        for (size_t k = 0; k < gi.size(); k++)
+        return finish_giants(ev, ct, st, keys, gi, inner);
+    }
+
+    // Lazy mod-down ("double hoisting"): rot_r(ct) P' = sigma_r(acc_r + (P' c0, 0)) stays in the key-switch basis, the
+    // inner sums are formed there (k_bsgs_ext) and every giant step's inner sum is divided by P' ONCE.  The first
+    // CoeffToSlot stage sees the mod-raised ciphertext, whose c1 is a single small digit (ksgroup.hpp): with single-digit
+    // keys its "decomposition" is one NTT and its baby steps cost 2 x 36 limb products each, so the stage is planned
+    // with baby steps only.  Returns an empty Ct when the registered keys do not allow the lazy path.
+    Ct Bootstrapper::linear_transform_lazy(const Evaluator &ev, const Ct &ct, LinearStage &st, const Keys &keys) const
+    {
+        Context *c = c_;
+        const size_t N = c->n;
+        const long long n = slots();
+        const int limbs = ct.limbs;
+        auto norm = [&](long long step) { return (int)(((step % n) + n) % n); };
+        std::vector<uint32_t> elts; // per baby step (0 = the identity)
+        for (int j : st.baby)
         {
-            const int gstep = norm((long long)gi[k] * st.giant * st.stride);
-            Ct term = gstep != 0 ? ev.rotate_vector(inner[k], gstep, keys) : inner[k];
-            inner[k] = Ct();
-            if (acc.empty())
+            const int step = norm((long long)j * st.stride);
+            elts.push_back(step == 0 ? 0u : c->elt_from_step(step));
+        }
+        // digit layout: single-digit keys on the mod-raised input, else the cheapest layout every baby step has a key for
+        int layout = -99;
+        if (st.first)
+        {
+            bool ok = true;
+            for (uint32_t e : elts)
             {
-                acc = term;
+                ok = ok && (e == 0 || keys.galois_single.count(e));
+            }
+            if (ok)
+            {
+                layout = KS_SINGLE;
+            }
+        }
+        if (layout == -99)
+        {
+            double best_cost = 0;
+            for (int cand = 0; limbs + cand <= c->kl - 1; cand++)
+            {
+                bool ok = true;
+                for (uint32_t e : elts)
+                {
+                    ok = ok && (e == 0 || keys.fast(c, e, limbs, cand) != nullptr);
+                }
+                const double cost = ok ? ksg_cost(c, limbs, cand) : 0;
+                if (ok && (layout == -99 || cost < best_cost))
+                {
+                    layout = cand;
+                    best_cost = cost;
+                }
+            }
+        }
+        if (layout == -99)
+        {
+            return Ct();
+        }
+        const KsExtInfo info = layout == KS_SINGLE ? ks_ext_info_single(c, limbs) : ks_ext_info(c, layout, limbs);
+        const KsShape &sh = info.shape;
+        auto *self = const_cast<Bootstrapper *>(this);
+        if (st.pts_ext.empty() || st.ext_layout != layout)
+        {
+            self->encode_stage(ev, st, &info.h_ids);
+            st.ext_layout = layout;
+            st.pts.clear(); // the level-basis copies are not needed on this path
+        }
+        // giant steps present and their plaintext rows (one pointer per baby step)
+        const int nbaby = (int)st.baby.size();
+        std::vector<int> gi;
+        std::vector<const u64 *> pts;
+        for (int i : st.giants)
+        {
+            bool any = false;
+            for (int j : st.baby)
+            {
+                any = any || st.pts_ext.count({ i, j });
+            }
+            if (!any)
+            {
+                continue;
+            }
+            gi.push_back(i);
+            for (int j : st.baby)
+            {
+                auto it = st.pts_ext.find({ i, j });
+                pts.push_back(it == st.pts_ext.end() ? nullptr : it->second.d);
+            }
+        }
+        MOAI_REQUIRE(!gi.empty() && gi.size() <= (size_t)BSGS_MAX_GIANT, "BSGS plan exceeds the fused kernel's limits");
+        const int G = (int)gi.size();
+        std::vector<Ct> inner(G);
+        for (auto &x : inner)
+        {
+            x = ev.alloc(ct.batch, 2, limbs, ct.scale * st.pt_scale);
+        }
+        // keys of the non-identity baby steps
+        std::vector<int> rot_idx; // baby index of every rotation that needs a key switch
+        std::vector<const KeyRef *> rkeys;
+        for (int j = 0; j < nbaby; j++)
+        {
+            if (elts[j] == 0)
+            {
+                continue;
+            }
+            rot_idx.push_back(j);
+            rkeys.push_back(layout == KS_SINGLE ? &keys.galois_single.at(elts[j]) : keys.fast(c, elts[j], limbs, layout));
+        }
+        const int R = (int)rot_idx.size();
+        // chunk: the gathers of k_bsgs_ext hit whole limbs of every acc_r, keep them L2-sized (~96 MiB) and the
+        // workspace below ~6 GiB
+        const size_t acc_words = (size_t)2 * sh.rns * N;
+        const size_t ext_bytes = layout == KS_SINGLE ? ks_single_ext_bytes_per_ct(c, limbs)
+                                 : (layout > 0 ? ksg_ext_bytes_per_ct(c, limbs, layout) : ks_ext_bytes_per_ct(c, limbs));
+        long long chunk = std::max<long long>(1, (long long)(96.0 * 1048576.0 / (std::max(R, 1) * (double)N * 8)));
+        chunk = std::min<long long>(chunk, std::max<long long>(1, (long long)(ks_ext_budget() / ext_bytes)));
+        chunk = std::min<long long>(chunk, ct.batch);
+        Scratch ext((size_t)chunk * ext_bytes, c->stream);
+        Scratch accs((size_t)std::max(R, 1) * chunk * acc_words * sizeof(u64), c->stream);
+        Scratch outs((size_t)G * chunk * acc_words * sizeof(u64), c->stream);
+        Scratch cP((size_t)chunk * 2 * limbs * N * sizeof(u64), c->stream);
+        const size_t per_ct = (size_t)2 * limbs * N;
+        for (long long b0 = 0; b0 < ct.batch; b0 += chunk)
+        {
+            const long long nb = std::min(chunk, ct.batch - b0);
+            const u64 *src = ct.d + (size_t)b0 * per_ct;
+            if (layout == KS_SINGLE)
+            {
+                ks_hoist_modraised(c, src + (size_t)limbs * N, nb, limbs, ext.as<u64>(), (long long)per_ct);
+            }
+            else if (layout > 0)
+            {
+                ksg_decompose(c, src + (size_t)limbs * N, nb, limbs, layout, ext.as<u64>(), (long long)per_ct, 3);
             }
             else
             {
-                ev.add_inplace(acc, term);
+                ks_decompose(c, src + (size_t)limbs * N, nb, limbs, ext.as<u64>(), (long long)per_ct);
+            }
+            ew_multiply_scalar(c, src, info.h_pmod.data(), cP.as<u64>(), nb, 2, limbs);
+            // inner products of every rotation with its key (no mod-down), KSM_R keys per pass over the digits
+            for (int r0 = 0; r0 < R; r0 += KSM_R)
+            {
+                const int cnt = std::min(KSM_R, R - r0);
+                const u64 *kp[KSM_R];
+                int kkl[KSM_R];
+                u64 *accp[KSM_R];
+                for (int r = 0; r < cnt; r++)
+                {
+                    kp[r] = rkeys[r0 + r]->p;
+                    kkl[r] = rkeys[r0 + r]->key_kl;
+                    accp[r] = accs.as<u64>() + (size_t)(r0 + r) * nb * acc_words;
+                    MOAI_REQUIRE(kkl[r] >= sh.rns, "key does not cover this level");
+                }
+                ks_mac_multi(c, ext.as<u64>(), nb, sh, cnt, kp, kkl, accp);
+                for (int r = 0; r < cnt; r++)
+                {
+                    ks_int_targets(c, sh, info.h_ids, ext.as<u64>(), nb, kp[r], kkl[r], accp[r], false);
+                }
+            }
+            // inner sums of every giant step in the key-switch basis, BSGS_MAX_BABY baby steps per pass
+            std::vector<u64 *> op(G);
+            for (int g = 0; g < G; g++)
+            {
+                op[g] = outs.as<u64>() + (size_t)g * nb * acc_words;
+            }
+            int ri = 0;
+            for (int j0 = 0; j0 < nbaby; j0 += BSGS_MAX_BABY)
+            {
+                const int cnt = std::min(BSGS_MAX_BABY, nbaby - j0);
+                std::vector<const u64 *> ap(cnt), pp((size_t)G * cnt);
+                std::vector<const uint32_t *> perm(cnt);
+                for (int j = 0; j < cnt; j++)
+                {
+                    if (elts[j0 + j] == 0)
+                    {
+                        ap[j] = nullptr;
+                        perm[j] = nullptr;
+                    }
+                    else
+                    {
+                        ap[j] = accs.as<u64>() + (size_t)ri * nb * acc_words;
+                        perm[j] = c->galois_table(elts[j0 + j]);
+                        ri++;
+                    }
+                    for (int g = 0; g < G; g++)
+                    {
+                        pp[(size_t)g * cnt + j] = pts[(size_t)g * nbaby + j0 + j];
+                    }
+                }
+                bsgs_ext(c, ap.data(), perm.data(), cnt, pp.data(), G, op.data(), cP.as<u64>(), nb, sh, j0 > 0);
+            }
+            for (int g = 0; g < G; g++)
+            {
+                ks_moddown(c, op[g], nb * 2, limbs, layout > 0 ? layout : 0, nullptr, false, inner[g].d + (size_t)b0 * per_ct);
             }
         }
-        return ev.rescale_to_next(acc);
+        return finish_giants(ev, ct, const_cast<LinearStage &>(st), keys, gi, inner);
     }
 
     // ------------------------------------------------------------------------------------ EvalMod
@@ -690,11 +1009,11 @@ namespace moai
         const int n = slots();
         const double q0 = (double)c_->q[0];
         // plaintexts of the linear stages: encoded once per (stage, input scale)
-        if (cts_[0].pts.empty())
+        if (cts_[0].pt_scale == 0)
         {
             for (int s = 0; s < 3; s++)
             {
-                encode_stage(ev, cts_[s], ev.last_prime(cts_[s].limbs));
+                prepare_stage(cts_[s], ev.last_prime(cts_[s].limbs), 1.0);
             }
         }
         // 1. ModRaise; the plaintext is now t = m + q0 I, declared at scale q0
@@ -738,25 +1057,16 @@ namespace moai
         im = ev.view(both, in.batch, in.batch);
         // 4. SlotToCoeff on re + i im, constants q0 / (2 pi initial_scale) folded into the diagonals
         Ct w = ev.add(re, ev.multiply_plain(im, ev.encode(plus_i, im.limbs, 1.0)));
-        if (stc_encoded_for_scale_ != initial_scale || stc_[0].pts.empty())
+        if (stc_encoded_for_scale_ != initial_scale || stc_[0].pt_scale == 0)
         {
             const double f = std::cbrt(q0 / (2 * PI * initial_scale));
             for (int s = 0; s < 3; s++)
             {
-                LinearStage tmp = stc_[s];
-                for (auto &kv : tmp.diags)
-                {
-                    for (auto &z : kv.second)
-                    {
-                        z *= f;
-                    }
-                }
                 // the last stage's plaintext scale makes the final rescale land exactly on final_scale;
                 // w.scale is invariant through the first two stages (plaintext scale = dropped prime)
-                const double ps = s < 2 ? ev.last_prime(tmp.limbs) : prm.final_scale * ev.last_prime(tmp.limbs) / w.scale;
-                encode_stage(ev, tmp, ps);
-                stc_[s].pts = tmp.pts;
-                stc_[s].pt_scale = ps;
+                const double ps = s < 2 ? ev.last_prime(stc_[s].limbs)
+                                        : prm.final_scale * ev.last_prime(stc_[s].limbs) / w.scale;
+                prepare_stage(stc_[s], ps, f);
             }
             stc_encoded_for_scale_ = initial_scale;
         }

@@ -34,7 +34,11 @@ namespace moai
         int log_width = 10;   // loge                     (:352)
         int total_limbs = 35; // data limbs after ModRaise (:368)
         double final_scale = 70368744177664.0; // 2^46
-        int hoisting = 0;     // 1: plan the BSGS stages for hoisted baby steps (more, cheaper baby steps)
+        // 1: plan the BSGS stages for hoisted baby steps (more, cheaper baby steps);
+        // 2: additionally keep the baby-step rotations in the key-switch basis (lazy mod-down: one mod-down per giant
+        //    step, csrc/ops.cu k_bsgs_ext) and run the first CoeffToSlot stage — whose input is the mod-raised
+        //    ciphertext, a single small digit — with single-digit keys and baby steps only
+        int hoisting = 0;
         // levels the recursive Chebyshev division of the cosine spends: ceil(log2(deg + 1)) (59 -> 6, 31 -> 5).
         // The whole EvalMod spends poly_levels() + double_angles, which must be 8 (output at total_limbs - 14):
         // the reference's (59, 2); (31, 3) also fits the budget but not the precision (fit error 3e-4).
@@ -59,7 +63,13 @@ namespace moai
         std::vector<int> giants;          // i values present
         // encoded, pre-rotated diagonals on the device: key (i, j)
         std::map<std::pair<int, int>, Pt> pts;
-        double pt_scale = 0;              // scale the plaintexts were encoded with
+        double pt_scale = 0;              // scale the plaintexts are encoded with
+        double diag_factor = 1.0;         // constant folded into every diagonal at encode time
+        // the same plaintexts over the key-switch basis of the lazy path (data limbs + extra primes), encoded on first
+        // use for the digit layout the registered keys select (ext_layout: extra primes, or KS_SINGLE)
+        std::map<std::pair<int, int>, Pt> pts_ext;
+        int ext_layout = -99;
+        bool first = false;               // applied to the mod-raised ciphertext (first CoeffToSlot stage)
     };
 
     class Bootstrapper
@@ -67,7 +77,9 @@ namespace moai
     public:
         Bootstrapper(Context *ctx, const BootParams &p);
         // re-plan the linear stages for hoisted (pre-permuted-key) rotations; call before required_steps()
-        void set_hoisting(bool on);
+        void set_hoisting(int mode);
+        // steps of the first CoeffToSlot stage's baby steps when they run on single-digit keys (hoisting mode 2)
+        std::vector<int> single_digit_steps() const;
         std::vector<int> required_steps() const; // rotation steps (normalised to [0, slots)) the BSGS plans use
         // (step, limbs) for every rotation key and level it is used at; step 0 = the complex conjugation
         std::vector<std::pair<int, int>> required_step_levels() const;
@@ -117,9 +129,14 @@ namespace moai
 
         void build_matrices();
         void plan_bsgs(LinearStage &st) const;
-        void encode_stage(const Evaluator &ev, LinearStage &st, double pt_scale);
+        void prepare_stage(LinearStage &st, double pt_scale, double diag_factor);
+        // ids == nullptr: limbs 0 .. st.limbs - 1 into st.pts; else the listed primes into st.pts_ext
+        void encode_stage(const Evaluator &ev, LinearStage &st, const std::vector<int> *ids);
+        Ct linear_transform_lazy(const Evaluator &ev, const Ct &ct, LinearStage &st, const Keys &keys) const;
+        Ct finish_giants(const Evaluator &ev, const Ct &ct, LinearStage &st, const Keys &keys, const std::vector<int> &gi,
+                         std::vector<Ct> &inner) const;
         void fit_cosine();
-        Ct linear_transform(const Evaluator &ev, const Ct &ct, LinearStage &st, const Keys &keys) const;
+        Ct linear_transform(const Evaluator &ev, const Ct &ct, LinearStage &st, const Keys &keys);
         Ct eval_mod(const Evaluator &ev, const Ct &y, const Keys &keys) const;
         Ct eval_cheb(const Evaluator &ev, const std::vector<double> &coef, int target_limbs, double target_scale,
                      const std::map<int, Ct> &T, const Keys &keys) const;

@@ -814,11 +814,29 @@ extern "C"
         API_END
     }
 
+    int32_t moai_key_prepare_single(moai_context *ctx, const uint64_t *ksk_in, uint32_t galois_elt, int32_t pre_permute,
+                                    uint64_t *ksk_out)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(ksk_in && ksk_out, "null argument");
+        ks_key_prepare_single(c, CU(ksk_in), galois_elt, pre_permute != 0, U(ksk_out));
+        API_END
+    }
+
+    int32_t moai_keys_add_single(moai_keys *keys, uint32_t galois_elt, const uint64_t *ksk_single)
+    {
+        API_BEGIN
+        MOAI_REQUIRE(keys && ksk_single, "null argument");
+        keys->k.galois_single[galois_elt] = KeyRef{ CU(ksk_single), keys->kl, KS_SINGLE };
+        API_END
+    }
+
     int32_t moai_bootstrapper_set_hoisting(moai_bootstrapper *b, int32_t on)
     {
         API_BEGIN
         MOAI_REQUIRE(b, "null argument");
-        b->b->set_hoisting(on != 0);
+        b->b->set_hoisting(on);
         API_END
     }
 

@@ -91,6 +91,9 @@ namespace moai
         std::vector<KeyRef> relin_fast;
         std::map<uint32_t, KeyRef> galois;
         std::map<uint32_t, std::vector<KeyRef>> galois_fast;
+        // single-digit keys [1][2][kl][n] = sigma^-1(sum of all digits) for rotations of a MOD-RAISED ciphertext
+        // (ksgroup.hpp): used by the first CoeffToSlot stage of the bootstrapping only
+        std::map<uint32_t, KeyRef> galois_single;
         // cheapest (ksg_cost) pre-permuted key of `elt` that covers `limbs` levels (nullptr when none);
         // only_k >= 0 restricts the choice to keys with that many extra primes
         const KeyRef *fast(Context *c, uint32_t elt, int limbs, int only_k = -1) const

@@ -83,6 +83,8 @@ namespace moai
             const Twiddle *d_zconst = nullptr; // [k + 1]  (P' / p_i)^-1 mod p_i
             const Twiddle *d_pinv = nullptr;   // [limbs]  P'^-1 mod q_j
             const int *d_ids = nullptr;        // [rns]
+            std::vector<u64> h_pmod;           // [limbs]  P' mod q_j
+            std::vector<int> h_ids;            // [rns]
             void *blob = nullptr;
         };
 
@@ -189,7 +191,7 @@ namespace moai
                 return *static_cast<KsgTables *>(it->second);
             }
             const int L = c->kl - 1;
-            MOAI_REQUIRE(k >= 1 && limbs >= 1 && limbs + k <= L, "no spare primes for grouped digits at this level");
+            MOAI_REQUIRE(k >= 0 && limbs >= 1 && limbs + k <= L, "no spare primes for grouped digits at this level");
             KsgTables *t = new KsgTables();
             t->k = k;
             t->limbs = limbs;
@@ -206,12 +208,23 @@ namespace moai
             }
             ids.push_back(L);
             // digits: the key's fixed groups cut at `limbs`
-            const std::vector<int> st = group_starts(c, k);
             std::vector<int> s0, cnt;
-            for (size_t g = 0; g + 1 < st.size() && st[g] < limbs; g++)
+            if (k == 0) // SEAL's digits: one per prime, extended by a plain reduction (no conversion tables)
             {
-                s0.push_back(st[g]);
-                cnt.push_back(std::min(st[g + 1], limbs) - st[g]);
+                for (int i = 0; i < limbs; i++)
+                {
+                    s0.push_back(i);
+                    cnt.push_back(1);
+                }
+            }
+            else
+            {
+                const std::vector<int> st = group_starts(c, k);
+                for (size_t g = 0; g + 1 < st.size() && st[g] < limbs; g++)
+                {
+                    s0.push_back(st[g]);
+                    cnt.push_back(std::min(st[g + 1], limbs) - st[g]);
+                }
             }
             t->digits = (int)s0.size();
             std::vector<int> src_dec(limbs);
@@ -274,6 +287,19 @@ namespace moai
                 }
                 pinv[j] = h_shoup(h_invmod(v, q), q);
             }
+            // P' mod q_j: the factor that lifts an un-switched polynomial into the key-switch basis
+            t->h_pmod.resize(limbs);
+            for (int j = 0; j < limbs; j++)
+            {
+                const u64 q = c->q[j];
+                u64 v = 1;
+                for (int i = 0; i <= k; i++)
+                {
+                    v = h_mulmod(v, c->q[src_md[i]] % q, q);
+                }
+                t->h_pmod[j] = v;
+            }
+            t->h_ids = ids;
             const size_t o_z = bl.put(zconst), o_p = bl.put(pinv);
             MOAI_CUDA_CHECK(cudaMalloc(&t->blob, bl.bytes.size()));
             MOAI_CUDA_CHECK(cudaMemcpy(t->blob, bl.bytes.data(), bl.bytes.size(), cudaMemcpyHostToDevice));
@@ -524,24 +550,179 @@ namespace moai
     }
 
     // inner products of the integer-path target moduli (the special prime): plain pass B + 128-bit MAC
-    static void ksg_int_targets(Context *c, const KsgTables &t, u64 *ext, long long batch, const u64 *ksk, int key_kl,
-                                u64 *acc, bool need_pass_b)
+    void ks_int_targets(Context *c, const KsShape &sh, const std::vector<int> &h_ids, u64 *ext, long long batch,
+                        const u64 *ksk, int key_kl, u64 *acc, bool need_pass_b)
     {
         const size_t n = c->n;
-        for (int I = 0; I < t.rns; I++)
+        for (int I = 0; I < sh.rns; I++)
         {
-            const int prime = I < t.limbs ? I : (I < t.limbs + t.k ? c->kl - 1 - t.k + (I - t.limbs) : c->kl - 1);
+            const int prime = h_ids[I];
             if (c->h_limb[prime].fp_class != 0)
             {
                 continue;
             }
             if (need_pass_b)
             {
-                ntt_forward_pass_b_strided(c, ext + (size_t)I * t.digits * n, batch, t.digits, (long long)t.rns * t.digits,
-                                           c->d_ids + prime);
+                ntt_forward_pass_b_strided(c, ext + (size_t)I * sh.digits * n, batch, sh.digits,
+                                           (long long)sh.rns * sh.digits, c->d_ids + prime);
             }
-            ks_mac_int(c, ext, ksk, acc, batch, t.shape, key_kl, I);
+            ks_mac_int(c, ext, ksk, acc, batch, sh, key_kl, I);
         }
+    }
+    static void ksg_int_targets(Context *c, const KsgTables &t, u64 *ext, long long batch, const u64 *ksk, int key_kl,
+                                u64 *acc, bool need_pass_b)
+    {
+        ks_int_targets(c, t.shape, t.h_ids, ext, batch, ksk, key_kl, acc, need_pass_b);
+    }
+
+    KsExtInfo ks_ext_info(Context *c, int k, int limbs)
+    {
+        const KsgTables &t = tables(c, k, limbs);
+        KsExtInfo e;
+        e.shape = t.shape;
+        e.k = k;
+        e.h_ids = t.h_ids;
+        e.h_pmod = t.h_pmod;
+        return e;
+    }
+
+    KsExtInfo ks_ext_info_single(Context *c, int limbs)
+    {
+        KsExtInfo e = ks_ext_info(c, 0, limbs);
+        e.shape.digits = 1;
+        e.k = KS_SINGLE;
+        return e;
+    }
+
+    void ks_moddown(Context *c, const u64 *acc, long long polys, int limbs, int k, const u64 *addend, bool addend_even_only,
+                    u64 *out)
+    {
+        if (k > 0)
+        {
+            ksg_moddown(c, acc, polys, limbs, k, addend, addend_even_only, out);
+        }
+        else
+        {
+            moddown_special(c, acc, polys, limbs, addend, out, addend_even_only);
+        }
+    }
+
+    // centred lift of coefficients modulo q_0 into the prime `target` (one limb of ModRaise)
+    namespace
+    {
+        __global__ void k_lift_q0(const ulonglong2 *__restrict__ d, ulonglong2 *__restrict__ out, long long total2, u64 q0,
+                                  LimbConst lc)
+        {
+            const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= total2)
+            {
+                return;
+            }
+            const u64 half = q0 >> 1, corr = lc.q - reduce64(q0, lc);
+            const ulonglong2 v = d[i];
+            ulonglong2 r;
+            r.x = reduce64(v.x, lc);
+            r.y = reduce64(v.y, lc);
+            if (v.x > half)
+            {
+                r.x = addmod(r.x, corr, lc.q);
+            }
+            if (v.y > half)
+            {
+                r.y = addmod(r.y, corr, lc.q);
+            }
+            out[i] = r;
+        }
+    } // namespace
+
+    size_t ks_single_ext_bytes_per_ct(Context *c, int limbs)
+    {
+        return (size_t)(limbs + 1) * c->n * sizeof(u64);
+    }
+
+    void ks_hoist_modraised(Context *c, const u64 *c1, long long batch, int limbs, u64 *ext, long long c1_stride)
+    {
+        const size_t n = c->n;
+        const size_t row = (size_t)limbs * n * sizeof(u64);
+        {
+            KernelTimer ktm(c, "k_copy_ks_target", 1);
+            MOAI_CUDA_CHECK(cudaMemcpy2DAsync(ext, row + n * sizeof(u64), c1, c1_stride ? (size_t)c1_stride * sizeof(u64) : row,
+                                              row, (size_t)batch, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        // the special-prime limb: INTT of limb 0 (coefficients modulo q_0), centred lift, NTT
+        Scratch d((size_t)batch * n * sizeof(u64), c->stream);
+        {
+            KernelTimer ktm(c, "k_copy_ks_target", 1);
+            MOAI_CUDA_CHECK(cudaMemcpy2DAsync(d.p, n * sizeof(u64), c1, c1_stride ? (size_t)c1_stride * sizeof(u64) : row,
+                                              n * sizeof(u64), (size_t)batch, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        ntt_inverse(c, d.as<u64>(), batch, c->d_ids, 1);
+        Scratch sp((size_t)batch * n * sizeof(u64), c->stream);
+        const long long total2 = batch * (long long)(n / 2);
+        {
+            KernelTimer kt(c, "k_lift_q0", 1);
+            k_lift_q0<<<(unsigned)((total2 + 255) / 256), 256, 0, c->stream>>>(d.as<ulonglong2>(), sp.as<ulonglong2>(), total2,
+                                                                               c->q[0], c->h_limb[c->kl - 1]);
+            c->launches += 1;
+        }
+        ntt_forward(c, sp.as<u64>(), batch, c->d_ids + (c->kl - 1), 1);
+        {
+            KernelTimer ktm(c, "k_copy_ks_target", 1);
+            MOAI_CUDA_CHECK(cudaMemcpy2DAsync(ext + (size_t)limbs * n, row + n * sizeof(u64), sp.p, n * sizeof(u64),
+                                              n * sizeof(u64), (size_t)batch, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        MOAI_CUDA_CHECK(cudaGetLastError());
+    }
+
+    void ks_key_prepare_single(Context *c, const u64 *in, uint32_t elt, bool pre_permute, u64 *out)
+    {
+        MOAI_REQUIRE(in != out, "key preparation is out of place");
+        const size_t n = c->n;
+        const int L = c->kl - 1;
+        uint32_t inv = 1;
+        if (pre_permute)
+        {
+            const uint64_t m = 2 * (uint64_t)n;
+            uint64_t x = elt;
+            for (int i = 0; i < 6; i++)
+            {
+                x = (x * (2 + m * 4 - (uint64_t)elt * x % m)) % m;
+            }
+            MOAI_REQUIRE((uint64_t)elt * x % m == 1, "Galois element is not invertible");
+            inv = (uint32_t)x;
+        }
+        Scratch tmp(n * sizeof(u64), c->stream);
+        const long long n2 = (long long)(n / 2);
+        for (int kk = 0; kk < 2; kk++)
+        {
+            for (int ol = 0; ol < c->kl; ol++)
+            {
+                u64 *dst = out + ((size_t)kk * c->kl + ol) * n;
+                u64 *sum = pre_permute ? tmp.as<u64>() : dst;
+                for (int j0 = 0; j0 < L; j0 += CONV_MAX - 1)
+                {
+                    KeySumArgs a;
+                    a.cnt = 0;
+                    if (j0 > 0)
+                    {
+                        a.src[a.cnt++] = reinterpret_cast<const ulonglong2 *>(sum); // running sum (same-index read/write)
+                    }
+                    for (int j = j0; j < std::min(L, j0 + CONV_MAX - 1); j++)
+                    {
+                        a.src[a.cnt++] = reinterpret_cast<const ulonglong2 *>(in + (((size_t)j * 2 + kk) * c->kl + ol) * n);
+                    }
+                    KernelTimer kt(c, "k_key_group_sum", 1);
+                    k_key_group_sum<<<(unsigned)((n2 + 255) / 256), 256, 0, c->stream>>>(
+                        a, reinterpret_cast<ulonglong2 *>(sum), n2, c->q[ol]);
+                    c->launches += 1;
+                }
+                if (pre_permute)
+                {
+                    apply_galois_ntt(c, sum, dst, 1, inv);
+                }
+            }
+        }
+        MOAI_CUDA_CHECK(cudaGetLastError());
     }
 
     void ksg_switch(Context *c, const u64 *target, long long batch, int limbs, int k, const u64 *ksk, int key_kl,

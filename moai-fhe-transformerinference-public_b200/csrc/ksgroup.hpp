@@ -23,6 +23,7 @@
 #pragma once
 #include "ntt.cuh"
 #include "ops.cuh"
+#include <vector>
 
 namespace moai
 {
@@ -58,5 +59,27 @@ namespace moai
     // hoisted rotations from one decomposition (up to KSM_R keys per pass)
     void ksg_rotate_hoisted_multi(Context *c, const u64 *ct, const u64 *ext, long long batch, int limbs, int k, int n_rot,
                                   const uint32_t *elts, const u64 *const *ksk_pre, const int *key_kl, u64 *const *outs);
+    // ---- pieces for the lazy (extended-basis) BSGS of the bootstrapping's linear stages -----------------------------
+    constexpr int KS_SINGLE = -1; // digit layout "one digit": the polynomial itself is small (right after ModRaise)
+    struct KsExtInfo
+    {
+        KsShape shape;            // digits / targets of the key-switch basis at this level
+        int k = 0;                // extra primes (0 = SEAL's digits, KS_SINGLE)
+        std::vector<int> h_ids;   // prime index of every target
+        std::vector<u64> h_pmod;  // P' mod q_j for the data limbs
+    };
+    KsExtInfo ks_ext_info(Context *c, int k, int limbs);       // k >= 0
+    KsExtInfo ks_ext_info_single(Context *c, int limbs);
+    void ks_int_targets(Context *c, const KsShape &sh, const std::vector<int> &h_ids, u64 *ext, long long batch,
+                        const u64 *ksk, int key_kl, u64 *acc, bool need_pass_b);
+    void ks_moddown(Context *c, const u64 *acc, long long polys, int limbs, int k, const u64 *addend, bool addend_even_only,
+                    u64 *out); // k == 0: by the special prime alone
+    // Single-digit key switch of a MOD-RAISED ciphertext.  After ModRaise (Bootstrapper.cpp:2938-2992) c1 is the
+    // centred lift of coefficients modulo q_0: as an integer polynomial it is below q_0 / 2 < p, i.e. it IS one
+    // digit, and K_all = sum over ALL J of K_J encrypts p * s' (F = p modulo every prime).  The "decomposition" is the
+    // ciphertext's own limbs plus one NTT for the special prime: ext [batch][limbs + 1][1][n]; key [1][2][kl][n].
+    size_t ks_single_ext_bytes_per_ct(Context *c, int limbs);
+    void ks_hoist_modraised(Context *c, const u64 *c1, long long batch, int limbs, u64 *ext, long long c1_stride);
+    void ks_key_prepare_single(Context *c, const u64 *in, uint32_t elt, bool pre_permute, u64 *out);
     void ksg_release(Context *c);
 } // namespace moai

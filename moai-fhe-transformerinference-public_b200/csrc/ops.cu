@@ -767,6 +767,140 @@ namespace moai
     }
 
 
+    // ------------------------------------------------------------------ BSGS inner sums in the EXTENDED basis
+    // Lazy mod-down ("double hoisting"): the baby-step rotations of a linear stage are left in the key-switch basis
+    // {q_0..q_{l-1}} + extra primes (rns limbs, scaled by the special modulus P'):
+    //     rot_r(ct) * P'  =  sigma_r( acc_r + (P' c0, 0) ),   acc_r = sum_g digit_g (.) K'_{r,g}   (no mod-down),
+    // and the inner sums  out_i = sum_r pt[i][r] (.) sigma_r(...)  are formed there, so that a stage pays ONE mod-down
+    // per giant step instead of one per baby step.  sigma_r is a gather through the NTT-domain permutation table;
+    // the identity rotation contributes P' * ct (zero modulo the extra primes).  128-bit lazy sums like k_bsgs_inner.
+    namespace
+    {
+        struct BsgsExtArgs
+        {
+            const u64 *acc[BSGS_MAX_BABY];                  // [batch][2][rns][n]; nullptr = the identity rotation
+            const uint32_t *perm[BSGS_MAX_BABY];            // [n] permutation of rotation r
+            const u64 *pt[BSGS_MAX_GIANT][BSGS_MAX_BABY];   // [rns][n], nullptr = absent diagonal
+            u64 *out[BSGS_MAX_GIANT];                       // [batch][2][rns][n]
+            const u64 *cP;                                  // [batch][2][n_data][n] = P' * ct
+            const int *ids;                                 // [rns] prime index of limb I
+            int n_baby, n_giant, rns, n_data, accumulate;
+        };
+
+        __global__ void __launch_bounds__(EW_THREADS) k_bsgs_ext(BsgsExtArgs a, long long polys, int log_n2,
+                                                                 const LimbConst *__restrict__ lcs,
+                                                                 const Twiddle *__restrict__ two64)
+        {
+            // same CTA order as k_bsgs_inner: (ciphertext, polynomial) fastest, so the diagonals are streamed once
+            const long long bp = blockIdx.x % polys; // b * 2 + p
+            const long long rest = blockIdx.x / polys;
+            const int cblks = (1 << log_n2) / EW_THREADS;
+            const long long within = (rest % cblks) * EW_THREADS + threadIdx.x;
+            const int I = (int)(rest / cblks);
+            const int prime = a.ids[I];
+            const LimbConst lc = lcs[prime];
+            const Twiddle t64 = two64[prime];
+            const int log_n = log_n2 + 1;
+            const bool data = I < a.n_data;
+            const bool poly0 = (bp & 1) == 0;
+            const u64 *cp_self = a.cP + ((bp * a.n_data + I) << log_n);           // P' * this polynomial
+            const u64 *cp_c0 = a.cP + (((bp & ~1ll) * a.n_data + I) << log_n);    // P' * c0 of this ciphertext
+            ulonglong2 r[BSGS_MAX_BABY];
+#pragma unroll
+            for (int j = 0; j < BSGS_MAX_BABY; j++)
+            {
+                if (j < a.n_baby)
+                {
+                    ulonglong2 v = make_ulonglong2(0, 0);
+                    if (a.acc[j])
+                    {
+                        const uint2 ix = __ldg(reinterpret_cast<const uint2 *>(a.perm[j]) + within);
+                        const u64 *src = a.acc[j] + ((bp * a.rns + I) << log_n);
+                        v.x = src[ix.x];
+                        v.y = src[ix.y];
+                        if (data && poly0)
+                        {
+                            v.x = addmod(v.x, cp_c0[ix.x], lc.q);
+                            v.y = addmod(v.y, cp_c0[ix.y], lc.q);
+                        }
+                    }
+                    else if (data)
+                    {
+                        v = reinterpret_cast<const ulonglong2 *>(cp_self)[within];
+                    }
+                    r[j] = v;
+                }
+            }
+            const long long o = ((bp * a.rns + I) << log_n2) + within;
+            const long long pt_off = ((long long)I << log_n2) + within;
+            for (int g = 0; g < a.n_giant; g++)
+            {
+                u128 sx{ 0, 0 }, sy{ 0, 0 };
+                if (a.accumulate)
+                {
+                    const ulonglong2 prev = reinterpret_cast<const ulonglong2 *>(a.out[g])[o];
+                    sx.lo = prev.x;
+                    sy.lo = prev.y;
+                }
+#pragma unroll
+                for (int j = 0; j < BSGS_MAX_BABY; j++)
+                {
+                    if (j < a.n_baby && a.pt[g][j])
+                    {
+                        const ulonglong2 w = __ldg(reinterpret_cast<const ulonglong2 *>(a.pt[g][j]) + pt_off);
+                        mac_wide(sx, r[j].x, w.x);
+                        mac_wide(sy, r[j].y, w.y);
+                    }
+                }
+                ulonglong2 res;
+                res.x = barrett_reduce_acc(sx, lc, t64.w, t64.wq);
+                res.y = barrett_reduce_acc(sy, lc, t64.w, t64.wq);
+                reinterpret_cast<ulonglong2 *>(a.out[g])[o] = res;
+            }
+        }
+    } // namespace
+
+    void bsgs_ext(Context *c, const u64 *const *acc, const uint32_t *const *perm, int n_baby, const u64 *const *pt,
+                  int n_giant, u64 *const *out, const u64 *cP, long long batch, const KsShape &sh, bool accumulate)
+    {
+        MOAI_REQUIRE(n_baby >= 1 && n_baby <= BSGS_MAX_BABY && n_giant >= 1 && n_giant <= BSGS_MAX_GIANT,
+                     "BSGS plan exceeds the fused kernel's limits");
+        BsgsExtArgs a;
+        a.n_baby = n_baby;
+        a.n_giant = n_giant;
+        a.rns = sh.rns;
+        a.n_data = sh.n_data;
+        a.ids = sh.ids;
+        a.cP = cP;
+        a.accumulate = accumulate ? 1 : 0;
+        for (int j = 0; j < n_baby; j++)
+        {
+            a.acc[j] = acc[j];
+            a.perm[j] = perm[j];
+        }
+        for (int g = 0; g < n_giant; g++)
+        {
+            a.out[g] = out[g];
+            for (int j = 0; j < n_baby; j++)
+            {
+                a.pt[g][j] = pt[g * n_baby + j];
+            }
+        }
+        const long long ctas = batch * 2 * sh.rns * (long long)((c->n / 2) / EW_THREADS);
+        MOAI_REQUIRE((c->n / 2) % EW_THREADS == 0 && ctas < (1ll << 31), "unsupported shape for the fused inner sums");
+        KernelTimer kt(c, "k_bsgs_ext", 1);
+        k_bsgs_ext<<<(unsigned)ctas, EW_THREADS, 0, c->stream>>>(a, batch * 2, c->log_n - 1, c->d_limb, c->d_two64);
+        c->launches += 1;
+        MOAI_CUDA_CHECK(cudaGetLastError());
+    }
+
+    // mod-down by the special prime alone (S/evaluator.cpp:2962-3018): in [P][limbs + 1][n] -> out [P][limbs][n]
+    void moddown_special(Context *c, const u64 *in, long long P, int limbs, const u64 *addend, u64 *out,
+                         bool addend_even_only)
+    {
+        divide_round_last(c, in, P, limbs + 1, c->kl - 1, addend, out, addend_even_only);
+    }
+
     void bsgs_inner(Context *c, const u64 *const *rot, int n_baby, const u64 *const *pt, int n_giant, u64 *const *out,
                     long long batch, int limbs)
     {

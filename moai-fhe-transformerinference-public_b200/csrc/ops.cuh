@@ -42,6 +42,13 @@ namespace moai
     void bsgs_inner(Context *c, const u64 *const *rot, int n_baby, const u64 *const *pt, int n_giant, u64 *const *out,
                     long long batch, int limbs);
 
+    // the same inner sums with the rotations left in the key-switch basis (lazy mod-down; csrc/ops.cu)
+    struct KsShape;
+    void bsgs_ext(Context *c, const u64 *const *acc, const uint32_t *const *perm, int n_baby, const u64 *const *pt,
+                  int n_giant, u64 *const *out, const u64 *cP, long long batch, const KsShape &sh, bool accumulate);
+    void moddown_special(Context *c, const u64 *in, long long P, int limbs, const u64 *addend, u64 *out,
+                         bool addend_even_only);
+
     void rescale(Context *c, const u64 *in, u64 *out, long long batch, int polys, int limbs);
     void mod_switch_drop(Context *c, const u64 *in, u64 *out, long long batch, int polys, int limbs_in, int limbs_out);
     void mod_raise(Context *c, const u64 *in, u64 *out, long long batch, int polys, int limbs_out);
@@ -69,7 +76,6 @@ namespace moai
     void rotate_prepermuted(Context *c, const u64 *ct, long long batch, int limbs, uint32_t elt, const u64 *ksk_pre,
                             int key_kl, u64 *out, int k_extra = 0);
     // pieces shared with csrc/ksgroup.cu
-    struct KsShape;
     void ks_mac_int(Context *c, const u64 *ext, const u64 *ksk, u64 *acc, long long batch, const KsShape &sh, int key_kl,
                     int I);
     void divround_finish(Context *c, const u64 *in, const u64 *u, const u64 *addend, u64 *out, long long P, int targets,

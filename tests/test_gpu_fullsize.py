@@ -36,8 +36,9 @@ GOLDEN_REF = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", 
 
 @pytest.fixture(scope="module", params=["grouped", "fast"])
 def env(pkg, request):
-    """Both fast-mode key layouts: "grouped" (grouped-digit keys derived from the stock keys, csrc/ksgroup.hpp — what
-    bench.py times) and "fast" (SEAL's per-prime digits, pre-permuted)."""
+    """Both fast-mode key layouts: "grouped" (grouped-digit keys derived from the stock keys, lazy mod-down in the linear
+    stages and single-digit keys on the first CoeffToSlot stage: csrc/ksgroup.hpp — what bench.py times) and "fast"
+    (SEAL's per-prime digits, pre-permuted, one mod-down per rotation)."""
     import torch
     from devkeygen import DeviceKeyGen
     from oracle import Oracle, MOAI_BITS
@@ -45,13 +46,16 @@ def env(pkg, request):
     be = pkg.Backend(LOG_N, o.q)
     kg = DeviceKeyGen(pkg, be, hamming_weight=192, seed=20250991)
     boot = pkg.Bootstrapper(be, total_limbs=35)
-    boot.set_hoisting(True)
-    fast, grouped = {}, {}
+    boot.set_hoisting(2 if request.param == "grouped" else 1)
+    fast, grouped, single = {}, {}, {}
     if request.param == "grouped":
         for st, lvs in sorted(boot.required_step_levels().items()):
             e = be.galois_elt_from_step(st)
             k = kg.galois_key(e)
             for lv in lvs:
+                if lv == 0:         # baby step of the first CoeffToSlot stage: single-digit key
+                    single[e] = be.key_prepare_single(k, e)
+                    continue
                 gk = be.key_prepare_grouped(k, e, lv)
                 if gk is None:      # no spare prime at the top level: SEAL's digits
                     fast.setdefault(e, []).append(be.key_prepare(k, e, max_limbs=lv))
@@ -62,7 +66,7 @@ def env(pkg, request):
         relin4 = relin.reshape(be.kl - 1, 2, be.kl, N)
         grouped[0] = [be.key_prepare_grouped(relin4, 0, lv, k_extra=k, pre_permute=False)
                       for k, lv in sorted(be.ksg_plan(range(1, be.kl - 1)).items())]
-        keys = be.make_keys(relin=relin, galois_fast=fast, grouped=grouped)
+        keys = be.make_keys(relin=relin, galois_fast=fast, grouped=grouped, single=single)
     else:
         for st in boot.required_steps() + [0]:
             e = be.galois_elt_from_step(st)
@@ -77,7 +81,7 @@ def env(pkg, request):
         mask[k * NUM_BATCH] = 1                           # bias_vec(input_len = {5, 0, ...}), Batch_encode_encrypt.hpp:39-49
     yield {"o": o, "be": be, "kg": kg, "boot": boot, "keys": keys, "mask": mask, "g": np.load(GOLDEN),
            "ref": np.load(GOLDEN_REF)}
-    del keys, fast, grouped
+    del keys, fast, grouped, single
     be.close()
     torch.cuda.empty_cache()
 

@@ -143,3 +143,57 @@ def test_bootstrap_grouped(pkg, env):
         err = max(err, np.abs(dec - zs[i]).max())
     print("bootstrap on grouped keys: max |out - msg| = %.3g" % err)
     assert err < 2e-3, err
+
+
+def _boot_keys(pkg, o, be, sk, boot, use_grouped, use_single):
+    fast, grouped, single = {}, {}, {}
+    for i, (st, lvs) in enumerate(sorted(boot.required_step_levels().items())):
+        e = o.elt_from_step(st)
+        kk = pkg.to_device(o.gen_galois_key(sk, 1000 + i, e).reshape(o.kl - 1, 2, o.kl, o.n))
+        for lv in lvs:
+            if lv == 0:     # baby step of the first CoeffToSlot stage (hoisting mode 2)
+                if use_single:
+                    single[e] = be.key_prepare_single(kk, e)
+                else:
+                    fast.setdefault(e, []).append(be.key_prepare(kk, e))
+                continue
+            g = be.key_prepare_grouped(kk, e, lv) if use_grouped else None
+            if g is None:
+                fast.setdefault(e, []).append(be.key_prepare(kk, e, max_limbs=lv))
+            else:
+                grouped.setdefault(e, []).append(g)
+    relin = pkg.to_device(o.gen_relin_key(sk, 5))
+    if use_grouped:
+        relin4 = relin.reshape(o.kl - 1, 2, o.kl, o.n)
+        grouped[0] = [be.key_prepare_grouped(relin4, 0, lv, k_extra=k, pre_permute=False)
+                      for k, lv in sorted(be.ksg_plan(range(1, o.kl - 1)).items())]
+    return be.make_keys(relin=relin, galois_fast=fast, grouped=grouped, single=single), (len(fast), len(grouped), len(single))
+
+
+@pytest.mark.parametrize("use_grouped,use_single", [(True, True), (False, False), (False, True)])
+def test_bootstrap_lazy_moddown(pkg, env, use_grouped, use_single):
+    """Hoisting mode 2: baby-step rotations stay in the key-switch basis (one mod-down per giant step, k_bsgs_ext) and
+    the first CoeffToSlot stage runs on single-digit keys with baby steps only (the mod-raised c1 is one small digit).
+    Same tolerance as every other bootstrapping test (2e-3 max-abs); all three key configurations: grouped + single
+    (what bench.py times), SEAL digits everywhere, SEAL digits + single."""
+    o, be, sk = env
+    boot = pkg.Bootstrapper(be, total_limbs=17)
+    boot.set_hoisting(2)
+    levels = boot.required_step_levels()
+    assert any(0 in lv for lv in levels.values())          # first-stage baby steps want single-digit keys
+    keys, counts = _boot_keys(pkg, o, be, sk, boot, use_grouped, use_single)
+    rng = np.random.default_rng(1)
+    B = 3
+    zs = (rng.normal(size=(B, o.n // 2)) + 1j * rng.normal(size=(B, o.n // 2))) * 0.1
+    zs[2] = 0.0
+    cts = np.stack([o.encrypt_sym(sk, 50 + i, o.encode(zs[i], SCALE, 1), 1) for i in range(B)])
+    out, out_scale = boot.bootstrap_3(keys, pkg.to_device(cts.reshape(B, 2, 1, o.n)), SCALE)
+    assert out.shape[2] == 3 and out_scale == SCALE
+    res = pkg.to_host(out)
+    err = 0.0
+    for i in range(B):
+        dec = o.decode(o.decrypt(sk, res[i].reshape(-1), 2, 3), 3, out_scale)
+        err = max(err, np.abs(dec - zs[i]).max())
+    print("lazy bootstrapping (grouped=%s, single=%s; keys fast/grouped/single = %s): max |out - msg| = %.3g"
+          % (use_grouped, use_single, counts, err))
+    assert err < 2e-3, err

@@ -29,7 +29,10 @@ def main():
     ap.add_argument("--grouped", action="store_true", help="fast mode with grouped-digit keys (csrc/ksgroup.hpp): every "
                                                            "Galois key in the digit layout its level prefers, the "
                                                            "relinearisation key in one variant per layout")
+    ap.add_argument("--lazy", action="store_true", help="with --grouped: hoisting mode 2 (baby-step rotations stay in the "
+                                                        "key-switch basis, single-digit keys on the first CoeffToSlot stage)")
     args = ap.parse_args()
+    args.grouped = args.grouped or args.lazy
     args.fast = args.fast or args.grouped
     pkg = importlib.import_module("moai-fhe-transformerinference-public_b200")
     primes = bench.moai_primes()
@@ -46,7 +49,7 @@ def main():
         return k
 
     if args.fast:
-        boot.set_hoisting(True)
+        boot.set_hoisting(2 if args.lazy else 1)
     if args.keys == "required":
         steps = boot.required_steps()
     else:
@@ -57,10 +60,14 @@ def main():
     # random residues stand in for key material; a pre-permuted key is the same size and layout
     key_bytes = 0
     if args.grouped:
-        gal, grouped = {}, {}
+        gal, grouped, single = {}, {}, {}
         for st, lvs in boot.required_step_levels().items():
             e = be.galois_elt_from_step(st)
             for lv in lvs:
+                if lv == 0:   # first CoeffToSlot stage, baby step: single-digit key [1, 2, kl, n]
+                    single[e] = rand_key()[:1].contiguous()
+                    key_bytes += single[e].numel() * 8
+                    continue
                 k = be.ksg_best_extra(lv)
                 if k == 0:   # no spare prime at this level: SEAL's digits, level-truncated
                     t = rand_key()[:lv, :, :lv + 1, :].contiguous()
@@ -72,7 +79,7 @@ def main():
                     key_bytes += gk.t.numel() * 8
         grouped[0] = [be.random_grouped_key(k, lv, g) for k, lv in sorted(be.ksg_plan(range(1, 35)).items())]
         key_bytes += sum(gk.t.numel() * 8 for gk in grouped[0])
-        keys = be.make_keys(relin=rand_key(), galois_fast=gal, grouped=grouped)
+        keys = be.make_keys(relin=rand_key(), galois_fast=gal, grouped=grouped, single=single)
     else:
         keys = be.make_keys(relin=rand_key(), galois_fast=gal) if args.fast else be.make_keys(relin=rand_key(), galois=gal)
     x = torch.randint(0, primes[0], (args.batch, 2, 1, n), generator=g, device="cuda", dtype=torch.int64)
@@ -100,7 +107,7 @@ def main():
     ms = e0.elapsed_time(e1) / args.iters
     per_ct = ms / args.batch
     per_layer_s = per_ct * 3084 / 1000.0
-    print(json.dumps({"op": "bootstrap_real (two real-slot ciphertexts per bootstrapping)" if args.real else "bootstrap_3", "batch": args.batch, "keys": args.keys, "mode": ("fast (hoisted, grouped digits)" if args.grouped else "fast (hoisted)") if args.fast else "exact (SEAL key switch)",
+    print(json.dumps({"op": "bootstrap_real (two real-slot ciphertexts per bootstrapping)" if args.real else "bootstrap_3", "batch": args.batch, "keys": args.keys, "mode": ("fast (hoisted, grouped digits%s)" % (", lazy mod-down + single-digit first stage" if args.lazy else "") if args.grouped else "fast (hoisted)") if args.fast else "exact (SEAL key switch)",
                       "grouped_key_GiB": round(key_bytes / 2 ** 30, 2),
                       "galois_keys": len(gal), "clocks": clocks,
                       "ms_per_batch": round(ms, 2), "ms_per_ciphertext": round(per_ct, 2), "phase_ms_per_ciphertext": phases,

@@ -68,12 +68,15 @@ def setup(args, device=0, seed=11):
     elif args.mode == "grouped":
         # fast mode with grouped-digit keys (csrc/ksgroup.hpp): every Galois key in the digit layout the cost model
         # prefers at the level it is used at, the relinearisation key in one variant per layout
-        boot.set_hoisting(True)
+        boot.set_hoisting(int(os.environ.get("MOAI_HOISTING", "2")))   # 2: lazy mod-down + single-digit first stage
         dev = torch.device("cuda", device)
-        gal, grouped = {}, {}
+        gal, grouped, single = {}, {}, {}
 
         def add(st, level):
             e = be.galois_elt_from_step(st)
+            if level == 0:      # baby step of the first CoeffToSlot stage: single-digit key [1, 2, kl, n]
+                single[e] = rand_key()[:1].contiguous()
+                return
             k = be.ksg_best_extra(level)
             if k == 0:
                 gal.setdefault(e, []).append(rand_key(level))
@@ -88,8 +91,8 @@ def setup(args, device=0, seed=11):
             for st in att[tag]:
                 add(st, level)
         grouped[0] = [be.random_grouped_key(k, lv, g) for k, lv in sorted(be.ksg_plan(range(1, kl - 1)).items())]
-        keys = be.make_keys(relin=rand_key(), galois_fast=gal, grouped=grouped)
-        n_keys = sum(len(v) for v in gal.values()) + sum(len(v) for v in grouped.values())
+        keys = be.make_keys(relin=rand_key(), galois_fast=gal, grouped=grouped, single=single)
+        n_keys = sum(len(v) for v in gal.values()) + sum(len(v) for v in grouped.values()) + len(single)
     else:
         boot.set_hoisting(True)
         gal = {}
