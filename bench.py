@@ -360,7 +360,8 @@ def run_gpu(args):
 # ---------------------------------------------------------------------------------------------------------
 PUBLISHED_12_LAYERS = 574.6   # P:Table 3 total, s per input for 12 layers on a 56-core Xeon 8480+
 LAYER_WORKLOAD = ("C4/C5: BERT-base encoder layer on one packed batch (768 cts @ chain 20, N=65536, 35+1 primes, "
-                  "256 inputs x 128 tokens, all tokens valid), fast mode; step = one bootstrap-delimited quarter of the "
+                  "256 inputs x 128 tokens, all tokens valid), fast mode (grouped-digit keys, lazy mod-down); step = one "
+                  "bootstrap-delimited quarter of the "
                   "layer (4 steps = 1 layer); 12-layer figure = seconds per layer x 12")
 STAGE_NAMES = ["attention+selfoutput+bootstrap_1", "layernorm_1+bootstrap_2", "intermediate+gelu+final+bootstrap_3",
                "layernorm_2+bootstrap_4"]
@@ -513,14 +514,22 @@ def run_layer(args):
             hbm_peak, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
         else:
             hbm_peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
-        ta, ua = prof.get("k_ntt_fwd_pass_a", (0.0, 0))
+        ta0, ua0 = prof.get("k_ntt_fwd_pass_a", (0.0, 0))
+        tac, uac = prof.get("k_ntt_fwd_pass_a_conv", (0.0, 0))
+        ta, ua = ta0 + tac, ua0 + uac       # pass A, plain and with the base-conversion prologue of the grouped digits
         tb, ub = prof.get("k_ntt_fwd_pass_b", (0.0, 0))
+        tf, uf = prof.get("k_ks_passb_mac", (0.0, 0))
         t1, u1 = prof.get("k_ntt_fwd_fused", (0.0, 0))
         # one forward limb-transform = pass A + pass B (or the single fused kernel); pass A also feeds the fused
         # key-switch kernel, so the pair is costed per limb-transform: (ms per unit of A) + (ms per unit of B)
         units = ub + u1
         pair_ms = (ta / ua * ub if ua else 0.0) + tb + t1
         limb_bytes = (1 << LOG_N) * 8
+
+        def krow(ms, u, bytes_per_unit):
+            return {"ms": ms, "units": int(u), "us_per_unit": ms * 1e3 / u if u else None,
+                    "algorithmic_GBps": u * bytes_per_unit / (ms * 1e-3) / 1e9 if ms > 0 else None,
+                    "frac_of_hbm_peak": u * bytes_per_unit / (ms * 1e-3) / 1e9 / hbm_peak if ms > 0 else None}
         achieved = units * 2 * limb_bytes / (pair_ms * 1e-3) / 1e9 if pair_ms > 0 else None
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ntt_fwd_traffic.json")
@@ -556,7 +565,13 @@ def run_layer(args):
                              "algorithmic_bytes_per_limb_transform": 2 * limb_bytes,
                              "us_per_limb_transform": pair_ms * 1e3 / units if units else None,
                              "kernel_ms": {"pass_a": ta, "pass_b": tb, "fused": t1, "pass_a_units": int(ua)},
-                             "kernel_share_of_step": (ta + tb + t1) / sum(dev_ms) if dev_ms else None,
+                             # the four kernels a forward transform is made of, each on its own algorithmic bytes:
+                             # pass A / pass B read and write one limb (1 MiB); the conversion variant of pass A writes one
+                             # limb and reads its source digits from the L2 (0.5 MiB counted); the fused pass-B + key inner
+                             # product reads one limb of pass-A output per unit (0.5 MiB; the evk tiles are shared by the batch)
+                             "ntt_kernels": {"pass_a": krow(ta0, ua0, 2 * limb_bytes), "pass_a_conv": krow(tac, uac, limb_bytes),
+                                             "pass_b": krow(tb, ub, 2 * limb_bytes), "ks_passb_mac": krow(tf, uf, limb_bytes)},
+                             "kernel_share_of_step": (ta + tb + t1 + tf) / sum(dev_ms) if dev_ms else None,
                              "note": "timed live with CUDA events around every launch on the launching stream; `achieved` = "
                                      "algorithmic bytes (1 MiB per limb-transform, SURVEY 8(d)) / time; `traffic` = DRAM bytes per "
                                      "limb-transform from the ncu capture under profiles/"},

@@ -760,13 +760,12 @@ namespace moai
             rkeys.push_back(layout == KS_SINGLE ? &keys.galois_single.at(elts[j]) : keys.fast(c, elts[j], limbs, layout));
         }
         const int R = (int)rot_idx.size();
-        // chunk: the gathers of k_bsgs_ext hit whole limbs of every acc_r, keep them L2-sized (~96 MiB) and the
-        // workspace below ~6 GiB
+        // chunk: bound the workspace (digits + one inner product per rotation + the giants' sums) to the key-switch budget
         const size_t acc_words = (size_t)2 * sh.rns * N;
         const size_t ext_bytes = layout == KS_SINGLE ? ks_single_ext_bytes_per_ct(c, limbs)
                                  : (layout > 0 ? ksg_ext_bytes_per_ct(c, limbs, layout) : ks_ext_bytes_per_ct(c, limbs));
-        long long chunk = std::max<long long>(1, (long long)(96.0 * 1048576.0 / (std::max(R, 1) * (double)N * 8)));
-        chunk = std::min<long long>(chunk, std::max<long long>(1, (long long)(ks_ext_budget() / ext_bytes)));
+        const size_t per_ct_ws = ext_bytes + (size_t)(std::max(R, 1) + G) * acc_words * sizeof(u64);
+        long long chunk = std::max<long long>(1, (long long)(ks_ext_budget() / per_ct_ws));
         chunk = std::min<long long>(chunk, ct.batch);
         Scratch ext((size_t)chunk * ext_bytes, c->stream);
         Scratch accs((size_t)std::max(R, 1) * chunk * acc_words * sizeof(u64), c->stream);

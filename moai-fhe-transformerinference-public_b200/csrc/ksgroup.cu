@@ -510,13 +510,9 @@ namespace moai
         const KsgTables &t = tables(c, k, limbs);
         const size_t n = c->n;
         Scratch d((size_t)batch * limbs * n * sizeof(u64), c->stream);
-        const size_t row = (size_t)limbs * n * sizeof(u64);
-        {
-            KernelTimer ktm(c, "k_copy_ks_target", 1);
-            MOAI_CUDA_CHECK(cudaMemcpy2DAsync(d.p, row, target, target_stride ? (size_t)target_stride * sizeof(u64) : row,
-                                              row, (size_t)batch, cudaMemcpyDeviceToDevice, c->stream));
-        }
-        ntt_inverse(c, d.as<u64>(), batch * limbs, c->d_ids, limbs);
+        MOAI_REQUIRE(target_stride % (long long)n == 0, "target stride must be a whole number of limbs");
+        ntt_inverse_from(c, target, limbs, target_stride ? target_stride / (long long)n : limbs, d.as<u64>(), batch * limbs,
+                         c->d_ids, limbs);
         scale_slots(c, d.as<u64>(), batch, limbs, c->d_ids, t.d_yconst);
         NttPrologue pro;
         pro.src = d.as<u64>();
@@ -526,19 +522,13 @@ namespace moai
     }
 
     void ksg_moddown(Context *c, const u64 *acc, long long polys, int limbs, int k, const u64 *addend,
-                     bool addend_even_only, u64 *out)
+                     bool addend_even_only, u64 *out, int addend_group)
     {
         const KsgTables &t = tables(c, k, limbs);
         const size_t n = c->n;
         const int np = k + 1;
         Scratch r((size_t)polys * np * n * sizeof(u64), c->stream);
-        {
-            KernelTimer ktm(c, "k_copy_last_limb", 1);
-            MOAI_CUDA_CHECK(cudaMemcpy2DAsync(r.p, (size_t)np * n * sizeof(u64), acc + (size_t)limbs * n,
-                                              (size_t)t.rns * n * sizeof(u64), (size_t)np * n * sizeof(u64), (size_t)polys,
-                                              cudaMemcpyDeviceToDevice, c->stream));
-        }
-        ntt_inverse(c, r.as<u64>(), polys * np, t.d_ids + limbs, np);
+        ntt_inverse_from(c, acc + (size_t)limbs * n, np, t.rns, r.as<u64>(), polys * np, t.d_ids + limbs, np);
         scale_slots(c, r.as<u64>(), polys, np, t.d_ids + limbs, t.d_zconst);
         Scratch u((size_t)polys * limbs * n * sizeof(u64), c->stream);
         NttPrologue pro;
@@ -546,7 +536,7 @@ namespace moai
         pro.mode = 3;
         pro.conv = &t.md;
         ntt_forward(c, u.as<u64>(), polys * limbs, c->d_ids, limbs, 1, &pro);
-        divround_finish(c, acc, u.as<u64>(), addend, out, polys, limbs, t.rns, t.d_pinv, addend_even_only);
+        divround_finish(c, acc, u.as<u64>(), addend, out, polys, limbs, t.rns, t.d_pinv, addend_even_only, addend_group);
     }
 
     // inner products of the integer-path target moduli (the special prime): plain pass B + 128-bit MAC
@@ -726,7 +716,7 @@ namespace moai
     }
 
     void ksg_switch(Context *c, const u64 *target, long long batch, int limbs, int k, const u64 *ksk, int key_kl,
-                    const u64 *addend, u64 *out, long long target_stride, bool addend_c0_only)
+                    const u64 *addend, u64 *out, long long target_stride, bool addend_c0_only, int addend_group)
     {
         const KsgTables &t = tables(c, k, limbs);
         MOAI_REQUIRE(key_kl >= t.rns, "grouped key does not cover this level");
@@ -744,7 +734,9 @@ namespace moai
             ks_passb_mac(c, ext.as<u64>(), nb, t.shape, ksk, key_kl, acc.as<u64>());
             ksg_int_targets(c, t, ext.as<u64>(), nb, ksk, key_kl, acc.as<u64>(), true);
             const size_t off = (size_t)b0 * 2 * limbs * n;
-            ksg_moddown(c, acc.as<u64>(), nb * 2, limbs, k, addend ? addend + off : nullptr, addend_c0_only, out + off);
+            ksg_moddown(c, acc.as<u64>(), nb * 2, limbs, k,
+                        addend ? addend + (size_t)b0 * addend_group * limbs * n : nullptr, addend_c0_only, out + off,
+                        addend_group);
         }
     }
 

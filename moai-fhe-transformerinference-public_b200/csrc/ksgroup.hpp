@@ -51,11 +51,12 @@ namespace moai
     void ksg_decompose(Context *c, const u64 *target, long long batch, int limbs, int k, u64 *ext,
                        long long target_stride, int passes);
     // out[P][limbs][n] = round(acc[P][limbs + k + 1][n] / P')  (+ addend; addend_even_only: even polynomials only)
+    // addend_group: polynomials per ciphertext in the addend's layout (2; 3 when relinearize adds (c0, c1) of its input)
     void ksg_moddown(Context *c, const u64 *acc, long long polys, int limbs, int k, const u64 *addend,
-                     bool addend_even_only, u64 *out);
+                     bool addend_even_only, u64 *out, int addend_group = 2);
     // complete key switch: out[b] = addend[b] + keyswitch(target[b]); out / addend are size-2 ciphertexts
     void ksg_switch(Context *c, const u64 *target, long long batch, int limbs, int k, const u64 *ksk, int key_kl,
-                    const u64 *addend, u64 *out, long long target_stride, bool addend_c0_only);
+                    const u64 *addend, u64 *out, long long target_stride, bool addend_c0_only, int addend_group = 2);
     // hoisted rotations from one decomposition (up to KSM_R keys per pass)
     void ksg_rotate_hoisted_multi(Context *c, const u64 *ct, const u64 *ext, long long batch, int limbs, int k, int n_rot,
                                   const uint32_t *elts, const u64 *const *ksk_pre, const int *key_kl, u64 *const *outs);

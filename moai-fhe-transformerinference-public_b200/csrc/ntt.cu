@@ -1,4 +1,5 @@
 #include "ntt.cuh"
+#include "fpfield.cuh"
 #include <cstdlib>
 
 namespace moai
@@ -67,132 +68,6 @@ namespace moai
                 const u64 u = x, v = y;
                 x = mul_shoup_lazy(csub(u + v, two_q), inv_n, inv_n_quo, q);
                 y = mul_shoup_lazy(u + two_q - v, inv_n_w, inv_n_w_quo, q);
-            }
-        };
-
-        // ---- exact FP64 path for primes p < 2^51.
-        // Residues are integer-valued doubles.  With M = 1.5 * 2^52, rnd(y) = (y + M) - M is
-        // round-to-nearest-integer for |y| < 2^51; quot(x) = fma(x, 1/p, M) - M = rnd(x/p).
-        //   red(x)      = x - rnd(x/p) p                 : |x| < 2^53  ->  |red| <= p/2 + 1
-        //   mul(a, w)   : h = fl(a w), l = fma(a, w, -h) (so a w = h + l exactly),
-        //                 r = fma(-rnd(h/p), p, h) + l   : needs |a| < 2^52, |w| <= p/2;
-        //                 |r| <= 1.125 p for p < 2^51 and <= 0.52 p for p < 2^48 (error terms: rounding of
-        //                 h/p, of 1/p, and |l| <= ulp(h)/2); r is an exact integer because h - t p is an
-        //                 integer below 2^53.
-        // WIDE  (2^48 <= p, 2p + 64 < 2^52).  Forward: products are left unreduced (|v| <= 1.125 p) and
-        //        the 16 registers are reduced after every second stage: 0.5p -> 1.625p -> 2.75p (< 2^53),
-        //        multiplier inputs <= 1.625p < 2^52.  Inverse: mul() is followed by red() (|v| <= p/2 + 1)
-        //        and every sum is reduced.
-        // NARROW (p < 2^48): 32p of headroom below 2^53; no intermediate reductions in the forward
-        //        transform (|x| <= 2p + 8 * 0.52p per pass); in the inverse, sums double for at most 4
-        //        stages between the phase reductions.
-        template <bool WIDE>
-        struct FpField
-        {
-            typedef double elem;
-            typedef double tw_t;
-            double p, pinv, inv_n, inv_n_w, pshift;
-            u64 pi;
-            const double *__restrict__ tab;
-
-            __device__ FpField(const NttArgs &a, int limb, const LimbConst &lc)
-                : p(lc.pd), pinv(lc.pinv), inv_n(lc.inv_n_d), inv_n_w(lc.inv_n_w_d),
-                  pshift(lc.pd + 4503599627370496.0), pi(lc.q), tab(a.tw_fp + ((size_t)limb << a.log_n))
-            {}
-            __device__ __forceinline__ tw_t tw(size_t idx) const { return __ldg(tab + idx); }
-            __device__ __forceinline__ elem pro_reduce(elem x) const { return red(x); }
-            // nearest integer to x * pinv: the product is folded into the magic-constant addition (one
-            // FMA, one rounding fewer than mul + add), valid for |x * pinv| < 2^51
-            __device__ __forceinline__ double quot(double x) const
-            {
-                const double M = 6755399441055744.0;
-                return __dadd_rn(__fma_rn(x, pinv, M), -M);
-            }
-            __device__ __forceinline__ double red(double x) const
-            {
-                return __fma_rn(-quot(x), p, x);
-            }
-            // a w mod p without the final reduction: |result| <= 1.125 p (WIDE) / 0.65 p (NARROW)
-            __device__ __forceinline__ double mul_lazy(double a, double w) const
-            {
-                const double h = __dmul_rn(a, w);
-                const double l = __fma_rn(a, w, -h);
-                return __dadd_rn(__fma_rn(-quot(h), p, h), l);
-            }
-            __device__ __forceinline__ double mul(double a, double w) const
-            {
-                const double r = mul_lazy(a, w);
-                return WIDE ? red(r) : r;
-            }
-            // canonical / lazy uint64 below 2^52 -> double, exactly (bit trick, no I2F)
-            __device__ __forceinline__ elem in_outer(u64 v) const
-            {
-                return __dadd_rn(__longlong_as_double((long long)(v | 0x4330000000000000ull)), -4503599627370496.0);
-            }
-            __device__ __forceinline__ elem in_mid(u64 v) const { return __longlong_as_double((long long)v); }
-            __device__ __forceinline__ u64 out_mid(elem x) const { return (u64)__double_as_longlong(x); }
-            // |red(x)| <= p/2 + 1: shift into the positive range in FP64 (one exact add), then finish
-            // with integer compares on the otherwise idle ALU pipe.  2^52 + p + r is an integer in
-            // [2^52, 2^53), so its mantissa field is p + r exactly.
-            __device__ __forceinline__ u64 canon(elem x) const
-            {
-                const double r = __dadd_rn(red(x), pshift);
-                const u64 v = (u64)__double_as_longlong(r) & 0x000FFFFFFFFFFFFFull; // p + red(x) in (p/2 - 2, 3p/2 + 2)
-                return v >= pi ? v - pi : v;
-            }
-            __device__ __forceinline__ u64 out_fwd(elem x) const { return canon(x); }
-            __device__ __forceinline__ u64 out_inv(elem x) const { return canon(x); }
-            // forward: only the WIDE class needs the per-phase reduction; inverse: only NARROW does
-            // (WIDE reduces every sum inside gs()).
-            __device__ __forceinline__ void phase_begin_fwd(elem (&x)[16]) const
-            {
-                if (WIDE)
-                {
-#pragma unroll
-                    for (int k = 0; k < 16; k++)
-                    {
-                        x[k] = red(x[k]);
-                    }
-                }
-            }
-            __device__ __forceinline__ void phase_begin_inv(elem (&x)[16]) const
-            {
-                if (!WIDE)
-                {
-#pragma unroll
-                    for (int k = 0; k < 16; k++)
-                    {
-                        x[k] = red(x[k]);
-                    }
-                }
-            }
-            // forward only: the WIDE class no longer reduces every product; values grow by <= 1.125 p per
-            // stage from <= p/2 + 1 and all 16 registers are reduced after every second stage
-            // (phase_begin_fwd / phase_mid_fwd), so multiplier inputs stay <= 1.625 p < 2^52 and sums
-            // <= 2.75 p < 2^53: 2 x 16 reductions per four stages instead of 16 + 32.
-            __device__ __forceinline__ void phase_mid_fwd(elem (&x)[16]) const
-            {
-                phase_begin_fwd(x);
-            }
-            __device__ __forceinline__ void ct(elem &x, elem &y, const tw_t &w) const
-            {
-                const double v = mul_lazy(y, w);
-                const double u = x;
-                x = __dadd_rn(u, v);
-                y = __dadd_rn(u, -v);
-            }
-            __device__ __forceinline__ void gs(elem &x, elem &y, const tw_t &w) const
-            {
-                const double u = x, v = y;
-                const double s = __dadd_rn(u, v);
-                x = WIDE ? red(s) : s;
-                y = mul(__dadd_rn(u, -v), w);
-            }
-            __device__ __forceinline__ void gs_last(elem &x, elem &y) const
-            {
-                const double u = x, v = y;
-                x = mul(__dadd_rn(u, v), inv_n);
-                y = mul(__dadd_rn(u, -v), inv_n_w);
             }
         };
 
@@ -439,11 +314,12 @@ namespace moai
         }
 
         template <class F>
-        __device__ __forceinline__ void inv_pass_b_body(const F &f, u64 *base, u64 *srow64, int t, size_t row, size_t n)
+        __device__ __forceinline__ void inv_pass_b_body(const F &f, u64 *base, const u64 *in_base, u64 *srow64, int t,
+                                                        size_t row, size_t n)
         {
             typename F::elem x[16];
             typename F::elem *srow = reinterpret_cast<typename F::elem *>(srow64);
-            const ulonglong2 *in = reinterpret_cast<const ulonglong2 *>(base + 16 * t);
+            const ulonglong2 *in = reinterpret_cast<const ulonglong2 *>(in_base + 16 * t);
 #pragma unroll
             for (int k = 0; k < 16; k += 2)
             {
@@ -616,7 +492,14 @@ namespace moai
             const int limb = a.limb_ids[(poly / a.div) % a.period];
             const LimbConst lc = a.limb[limb];
             u64 *base = a.data + ((size_t)poly << a.log_n) + (size_t)row * 256;
-            MOAI_DISPATCH_FIELD(lc, (inv_pass_b_body(f, base, sm + r * ROW_PAD, t, (size_t)row, n)))
+            // optional out-of-place first pass: polynomial p is read from runs of grp_size polynomials grp_stride apart
+            const u64 *in_base = base;
+            if (a.src)
+            {
+                const long long phys = (poly / a.grp_size) * a.grp_stride + poly % a.grp_size;
+                in_base = a.src + ((size_t)phys << a.log_n) + (size_t)row * 256;
+            }
+            MOAI_DISPATCH_FIELD(lc, (inv_pass_b_body(f, base, in_base, sm + r * ROW_PAD, t, (size_t)row, n)))
         }
 
         template <int LOGR>
@@ -642,9 +525,12 @@ namespace moai
         // 61-bit factors) and reduce once.  v = rint(sum y_j / q_j) is computed with the same FP64 instruction
         // sequence in both versions, so every target modulus sees the same integer digit.
         // =====================================================================================
-        __device__ __forceinline__ double conv_y_double(u64 y)
+        // residue -> double for the quotient estimate: exact (and the same value in every instantiation) — the
+        // mantissa trick below 2^52 (one DADD instead of an I2F), the conversion instruction for wider sources
+        __device__ __forceinline__ double conv_y_double(u64 y, bool wide)
         {
-            return __ull2double_rn(y);
+            return wide ? __ull2double_rn(y)
+                        : __dadd_rn(__longlong_as_double((long long)(y | 0x4330000000000000ull)), -4503599627370496.0);
         }
         __device__ __forceinline__ double conv_rint(double v)
         {
@@ -685,7 +571,7 @@ namespace moai
 #pragma unroll
                     for (int k = 0; k < 16; k++)
                     {
-                        vs[k] = __fma_rn(conv_y_double(y[k]), iq, vs[k]);
+                        vs[k] = __fma_rn(conv_y_double(y[k], true), iq, vs[k]);
                         const double hi = f.in_outer(y[k] >> 26), lo = f.in_outer(y[k] & 0x3FFFFFFull);
                         x[k] = __dadd_rn(x[k], __dadd_rn(f.mul_lazy(hi, b26), f.mul_lazy(lo, bd)));
                     }
@@ -696,8 +582,9 @@ namespace moai
 #pragma unroll
                     for (int k = 0; k < 16; k++)
                     {
-                        vs[k] = __fma_rn(conv_y_double(y[k]), iq, vs[k]);
-                        x[k] = __dadd_rn(x[k], f.mul_lazy(f.in_outer(y[k]), bd));
+                        const double yd = conv_y_double(y[k], false); // == f.in_outer(y[k])
+                        vs[k] = __fma_rn(yd, iq, vs[k]);
+                        x[k] = __dadd_rn(x[k], f.mul_lazy(yd, bd));
                     }
                     since += 1;
                 }
@@ -739,12 +626,13 @@ namespace moai
             {
                 const double iq = cv.invq[s0 + j];
                 const u64 bj = cv.B[trow + j];
+                const bool wide = cv.wide[s0 + j] != 0;
                 const u64 *sj = src0 + ((size_t)j << a.log_n);
 #pragma unroll
                 for (int k = 0; k < 16; k++)
                 {
                     const u64 y = sj[(size_t)k * row_stride];
-                    vs[k] = __fma_rn(conv_y_double(y), iq, vs[k]);
+                    vs[k] = __fma_rn(conv_y_double(y, wide), iq, vs[k]);
                     mac_wide(acc[k], y, bj);
                 }
             }
@@ -1539,11 +1427,24 @@ namespace moai
 
     void ntt_inverse(Context *c, u64 *data, long long count, const int *d_limb_ids, int period, int div)
     {
+        ntt_inverse_from(c, nullptr, 0, 0, data, count, d_limb_ids, period, div);
+    }
+
+    void ntt_inverse_from(Context *c, const u64 *src, long long grp_size, long long grp_stride, u64 *data, long long count,
+                          const int *d_limb_ids, int period, int div)
+    {
         if (count <= 0)
         {
             return;
         }
         NttArgs a{ data, c->d_inv, c->d_inv_fp, c->d_limb, d_limb_ids, period, div, c->log_n, count };
+        if (src)
+        {
+            MOAI_REQUIRE(grp_size >= 1 && grp_stride >= grp_size, "bad source layout");
+            a.src = src;
+            a.grp_size = grp_size;
+            a.grp_stride = grp_stride;
+        }
         KernelTimer kt(c, "k_ntt_inv", count);
         switch (c->log_n)
         {

@@ -128,4 +128,9 @@ namespace moai
     void ks_passb_mac(Context *c, const u64 *mid, long long batch, const KsShape &sh, const u64 *ksk, int key_kl,
                       u64 *acc);
     void ntt_inverse(Context *c, u64 *data, long long count, const int *d_limb_ids, int period, int div = 1);
+    // out of place: polynomial p is read from src + ((p / grp_size) * grp_stride + p % grp_size) * n (runs of grp_size
+    // polynomials, grp_stride polynomials apart: one limb range of every ciphertext of a batch) and the coefficients
+    // land contiguously in data — saves the gather copy in front of an in-place transform
+    void ntt_inverse_from(Context *c, const u64 *src, long long grp_size, long long grp_stride, u64 *data, long long count,
+                          const int *d_limb_ids, int period, int div = 1);
 } // namespace moai

@@ -13,6 +13,7 @@
 #include "ntt.cuh"
 #include "ops.cuh"
 #include "ksgroup.hpp"
+#include "fpfield.cuh"
 #include <cstdlib>
 
 namespace moai
@@ -245,7 +246,7 @@ namespace moai
                                           const ulonglong2 *addend, ulonglong2 *out, // may alias each other
                                           long long total2, int log_n2, int targets, int limbs_in, int last_id, int kl,
                                           const LimbConst *__restrict__ lcs, const Twiddle *__restrict__ inv_last,
-                                          int addend_even_only)
+                                          int addend_even_only, int addend_group)
         {
             long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; // over [P][targets][n/2]
             if (i >= total2)
@@ -265,7 +266,9 @@ namespace moai
             r.y = mul_shoup(submod(x.y, y.y, q), inv.w, inv.wq, q);
             if (addend && !(addend_even_only && (p & 1)))
             {
-                ulonglong2 z = addend[i];
+                // the addend's ciphertexts may hold more polynomials than the result's two (relinearize reads c0, c1
+                // straight out of the size-3 input): polynomial p of the result <-> (p / 2) * addend_group + p % 2
+                ulonglong2 z = addend[((((p >> 1) * addend_group + (p & 1)) * targets + limb) << log_n2) + within];
                 r.x = addmod(r.x, z.x, q);
                 r.y = addmod(r.y, z.y, q);
             }
@@ -275,16 +278,13 @@ namespace moai
         // in [P][limbs_in][n] -> out [P][limbs_in-1][n] (+= addend of the same shape when given)
         // addend_even_only: add `addend` only to the even polynomials (c0 of size-2 ciphertexts)
         void divide_round_last(Context *c, const u64 *in, long long P, int limbs_in, int last_id, const u64 *addend,
-                               u64 *out, bool addend_even_only = false)
+                               u64 *out, bool addend_even_only = false, int addend_group = 2)
         {
             const size_t n = c->n;
             const int targets = limbs_in - 1;
             Scratch t(P * n * sizeof(u64), c->stream);
             Scratch u((size_t)P * targets * n * sizeof(u64), c->stream);
-            { KernelTimer ktm(c, "k_copy_last_limb", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(t.p, n * sizeof(u64), in + (size_t)targets * n,
-                                              (size_t)limbs_in * n * sizeof(u64), n * sizeof(u64), (size_t)P,
-                                              cudaMemcpyDeviceToDevice, c->stream)); }
-            ntt_inverse(c, t.as<u64>(), P, c->d_ids + last_id, 1);
+            ntt_inverse_from(c, in + (size_t)targets * n, 1, limbs_in, t.as<u64>(), P, c->d_ids + last_id, 1);
             const long long total2 = P * targets * (long long)(n / 2);
             // expansion (+half, reduce into every target prime, +fix) fused into the NTT's first pass
             NttPrologue pro;
@@ -296,7 +296,7 @@ namespace moai
             k_divround_finish<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
                 reinterpret_cast<const ulonglong2 *>(in), u.as<ulonglong2>(),
                 reinterpret_cast<const ulonglong2 *>(addend), reinterpret_cast<ulonglong2 *>(out), total2, c->log_n - 1,
-                targets, limbs_in, last_id, c->kl, c->d_limb, c->d_inv_last, addend_even_only ? 1 : 0);
+                targets, limbs_in, last_id, c->kl, c->d_limb, c->d_inv_last, addend_even_only ? 1 : 0, addend_group);
             c->launches += 1;
             MOAI_CUDA_CHECK(cudaGetLastError());
         }
@@ -580,14 +580,14 @@ namespace moai
 
     // out[P][targets][n] = (in[P][limbs_in][n](limb j < targets) - u[P][targets][n]) * inv[j] mod q_j (+ addend)
     void divround_finish(Context *c, const u64 *in, const u64 *u, const u64 *addend, u64 *out, long long P, int targets,
-                         int limbs_in, const Twiddle *d_inv, bool addend_even_only)
+                         int limbs_in, const Twiddle *d_inv, bool addend_even_only, int addend_group)
     {
         const long long total2 = P * targets * (long long)(c->n / 2);
         KernelTimer kt(c, "k_divround_finish", 1);
         k_divround_finish<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
             reinterpret_cast<const ulonglong2 *>(in), reinterpret_cast<const ulonglong2 *>(u),
             reinterpret_cast<const ulonglong2 *>(addend), reinterpret_cast<ulonglong2 *>(out), total2, c->log_n - 1,
-            targets, limbs_in, 0, 0, c->d_limb, d_inv, addend_even_only ? 1 : 0);
+            targets, limbs_in, 0, 0, c->d_limb, d_inv, addend_even_only ? 1 : 0, addend_group);
         c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
     }
@@ -787,48 +787,118 @@ namespace moai
             int n_baby, n_giant, rns, n_data, accumulate;
         };
 
+        // value of baby step j at this thread's coefficient pair: sigma_j(acc_j + (P' c0, 0)), or P' ct for the identity
+        __device__ __forceinline__ ulonglong2 bsgs_ext_value(const BsgsExtArgs &a, int j, long long bp, int I, long long within,
+                                                             int log_n, bool data, bool poly0, u64 q)
+        {
+            ulonglong2 v = make_ulonglong2(0, 0);
+            if (a.acc[j])
+            {
+                const uint2 ix = __ldg(reinterpret_cast<const uint2 *>(a.perm[j]) + within);
+                const u64 *src = a.acc[j] + ((bp * a.rns + I) << log_n);
+                v.x = src[ix.x];
+                v.y = src[ix.y];
+                if (data && poly0)
+                {
+                    const u64 *cp_c0 = a.cP + (((bp & ~1ll) * a.n_data + I) << log_n); // P' * c0 of this ciphertext
+                    v.x = addmod(v.x, cp_c0[ix.x], q);
+                    v.y = addmod(v.y, cp_c0[ix.y], q);
+                }
+            }
+            else if (data)
+            {
+                v = reinterpret_cast<const ulonglong2 *>(a.cP + ((bp * a.n_data + I) << log_n))[within];
+            }
+            return v;
+        }
+
+        // FP64-path primes: exact products on the FP64 pipe (fpfield.cuh), sums reduced every 2 / 8 terms
+        template <bool WIDE>
+        __device__ __forceinline__ void bsgs_ext_fp(const FpField<WIDE> &f, const BsgsExtArgs &a, long long bp, int I,
+                                                    long long within, int log_n2, bool data, bool poly0)
+        {
+            double rx[BSGS_MAX_BABY], ry[BSGS_MAX_BABY];
+#pragma unroll
+            for (int j = 0; j < BSGS_MAX_BABY; j++)
+            {
+                if (j < a.n_baby)
+                {
+                    const ulonglong2 v = bsgs_ext_value(a, j, bp, I, within, log_n2 + 1, data, poly0, f.pi);
+                    rx[j] = f.red(f.in_outer(v.x)); // centred: |r| <= p/2 + 1
+                    ry[j] = f.red(f.in_outer(v.y));
+                }
+            }
+            const long long o = ((bp * a.rns + I) << log_n2) + within;
+            const long long pt_off = ((long long)I << log_n2) + within;
+            const int red_every = WIDE ? 2 : 8;
+            for (int g = 0; g < a.n_giant; g++)
+            {
+                double sx = 0.0, sy = 0.0;
+                if (a.accumulate)
+                {
+                    const ulonglong2 prev = reinterpret_cast<const ulonglong2 *>(a.out[g])[o];
+                    sx = f.red(f.in_outer(prev.x));
+                    sy = f.red(f.in_outer(prev.y));
+                }
+                int cnt = 0;
+#pragma unroll
+                for (int j = 0; j < BSGS_MAX_BABY; j++)
+                {
+                    if (j < a.n_baby && a.pt[g][j])
+                    {
+                        const ulonglong2 w = __ldg(reinterpret_cast<const ulonglong2 *>(a.pt[g][j]) + pt_off);
+                        sx = __dadd_rn(sx, f.mul_lazy(f.in_outer(w.x), rx[j]));
+                        sy = __dadd_rn(sy, f.mul_lazy(f.in_outer(w.y), ry[j]));
+                        if (++cnt % red_every == 0)
+                        {
+                            sx = f.red(sx);
+                            sy = f.red(sy);
+                        }
+                    }
+                }
+                ulonglong2 res;
+                res.x = f.canon(sx);
+                res.y = f.canon(sy);
+                reinterpret_cast<ulonglong2 *>(a.out[g])[o] = res;
+            }
+        }
+
         __global__ void __launch_bounds__(EW_THREADS) k_bsgs_ext(BsgsExtArgs a, long long polys, int log_n2,
                                                                  const LimbConst *__restrict__ lcs,
                                                                  const Twiddle *__restrict__ two64)
         {
-            // same CTA order as k_bsgs_inner: (ciphertext, polynomial) fastest, so the diagonals are streamed once
-            const long long bp = blockIdx.x % polys; // b * 2 + p
-            const long long rest = blockIdx.x / polys;
+            // CTA order: coefficient block fastest, then (ciphertext, polynomial), limb slowest.  The gathers of one
+            // (polynomial, limb) scatter over whole limbs of every acc_r (n_baby x 512 KiB) and the diagonals of one limb
+            // (n_giant x n_baby x 512 KiB) are shared by all polynomials: both sets stay L2-resident in this order, so
+            // the diagonals are streamed from HBM once per launch and the gathers never leave the L2.
             const int cblks = (1 << log_n2) / EW_THREADS;
-            const long long within = (rest % cblks) * EW_THREADS + threadIdx.x;
-            const int I = (int)(rest / cblks);
+            const long long within = (blockIdx.x % cblks) * EW_THREADS + threadIdx.x;
+            const long long rest = blockIdx.x / cblks;
+            const long long bp = rest % polys; // b * 2 + p
+            const int I = (int)(rest / polys);
             const int prime = a.ids[I];
             const LimbConst lc = lcs[prime];
-            const Twiddle t64 = two64[prime];
-            const int log_n = log_n2 + 1;
             const bool data = I < a.n_data;
             const bool poly0 = (bp & 1) == 0;
-            const u64 *cp_self = a.cP + ((bp * a.n_data + I) << log_n);           // P' * this polynomial
-            const u64 *cp_c0 = a.cP + (((bp & ~1ll) * a.n_data + I) << log_n);    // P' * c0 of this ciphertext
+            if (lc.fp_class == 1)
+            {
+                bsgs_ext_fp<false>(FpField<false>(lc), a, bp, I, within, log_n2, data, poly0);
+                return;
+            }
+            if (lc.fp_class == 2)
+            {
+                bsgs_ext_fp<true>(FpField<true>(lc), a, bp, I, within, log_n2, data, poly0);
+                return;
+            }
+            // integer-path primes (the 58-bit special prime): 128-bit lazy sums
+            const Twiddle t64 = two64[prime];
             ulonglong2 r[BSGS_MAX_BABY];
 #pragma unroll
             for (int j = 0; j < BSGS_MAX_BABY; j++)
             {
                 if (j < a.n_baby)
                 {
-                    ulonglong2 v = make_ulonglong2(0, 0);
-                    if (a.acc[j])
-                    {
-                        const uint2 ix = __ldg(reinterpret_cast<const uint2 *>(a.perm[j]) + within);
-                        const u64 *src = a.acc[j] + ((bp * a.rns + I) << log_n);
-                        v.x = src[ix.x];
-                        v.y = src[ix.y];
-                        if (data && poly0)
-                        {
-                            v.x = addmod(v.x, cp_c0[ix.x], lc.q);
-                            v.y = addmod(v.y, cp_c0[ix.y], lc.q);
-                        }
-                    }
-                    else if (data)
-                    {
-                        v = reinterpret_cast<const ulonglong2 *>(cp_self)[within];
-                    }
-                    r[j] = v;
+                    r[j] = bsgs_ext_value(a, j, bp, I, within, log_n2 + 1, data, poly0, lc.q);
                 }
             }
             const long long o = ((bp * a.rns + I) << log_n2) + within;
@@ -995,10 +1065,9 @@ namespace moai
             fuse_expand = fuse_expand && (c->q[l] >> 52) == 0;
         }
         Scratch d((size_t)batch * limbs * n * sizeof(u64), c->stream);
-        const size_t row = (size_t)limbs * n * sizeof(u64);
-        { KernelTimer ktm(c, "k_copy_ks_target", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(d.p, row, target, target_stride ? (size_t)target_stride * sizeof(u64) : row,
-                                          row, (size_t)batch, cudaMemcpyDeviceToDevice, c->stream)); }
-        ntt_inverse(c, d.as<u64>(), batch * limbs, c->d_ids, limbs);
+        MOAI_REQUIRE(target_stride % (long long)n == 0, "target stride must be a whole number of limbs");
+        ntt_inverse_from(c, target, limbs, target_stride ? target_stride / (long long)n : limbs, d.as<u64>(), batch * limbs,
+                         c->d_ids, limbs);
         // NTT_I(d_I mod q_I) reproduces the target limb itself, so the I == J digits need no
         // special case (S/evaluator.cpp:2831-2836 takes the NTT-form input there: same residues)
         if (fuse_expand)
@@ -1048,16 +1117,15 @@ namespace moai
     // and the integer inner-product kernel.  Same residues as ks_decompose + ks_mac_moddown.
     static void ks_fused(Context *c, const u64 *target, long long batch, int limbs, u64 *ext, const u64 *ksk,
                          int key_kl, const u64 *addend, u64 *out, long long target_stride = 0,
-                         bool addend_c0_only = false)
+                         bool addend_c0_only = false, int addend_group = 2)
     {
         const size_t n = c->n;
         const int rns = limbs + 1;
         const int *ids_ks = c->d_ids_ks + (size_t)limbs * (c->kl + 1);
         Scratch d((size_t)batch * limbs * n * sizeof(u64), c->stream);
-        const size_t row = (size_t)limbs * n * sizeof(u64);
-        { KernelTimer ktm(c, "k_copy_ks_target", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(d.p, row, target, target_stride ? (size_t)target_stride * sizeof(u64) : row, row,
-                                          (size_t)batch, cudaMemcpyDeviceToDevice, c->stream)); }
-        ntt_inverse(c, d.as<u64>(), batch * limbs, c->d_ids, limbs);
+        MOAI_REQUIRE(target_stride % (long long)n == 0, "target stride must be a whole number of limbs");
+        ntt_inverse_from(c, target, limbs, target_stride ? target_stride / (long long)n : limbs, d.as<u64>(), batch * limbs,
+                         c->d_ids, limbs);
         NttPrologue pro;
         pro.src = d.as<u64>();
         pro.mode = 1;
@@ -1082,7 +1150,7 @@ namespace moai
             c->launches += 1;
             MOAI_CUDA_CHECK(cudaGetLastError());
         }
-        divide_round_last(c, acc.as<u64>(), batch * 2, rns, c->kl - 1, addend, out, addend_c0_only);
+        divide_round_last(c, acc.as<u64>(), batch * 2, rns, c->kl - 1, addend, out, addend_c0_only, addend_group);
     }
 
     static bool ks_can_fuse(Context *c, int limbs);
@@ -1314,6 +1382,29 @@ namespace moai
     {
         const size_t n = c->n;
         const size_t poly = (size_t)limbs * n;
+        if (key_kl <= 0)
+        {
+            key_kl = c->kl;
+        }
+        // out2 = (c0, c1) + keyswitch(c2): the fused / grouped paths read c2 and add (c0, c1) straight out of the
+        // size-3 input (strided target, addend_group = 3) instead of splitting it into two copies first
+        if (k_extra > 0)
+        {
+            ksg_switch(c, in3 + 2 * poly, batch, limbs, k_extra, ksk, key_kl, in3, out2, (long long)(3 * poly), false, 3);
+            return;
+        }
+        if (ks_can_fuse(c, limbs))
+        {
+            const long long chunk = ks_chunk(c, limbs, batch, ks_ext_budget());
+            Scratch ext((size_t)chunk * ks_ext_bytes_per_ct(c, limbs), c->stream);
+            for (long long b0 = 0; b0 < batch; b0 += chunk)
+            {
+                const long long nb = (batch - b0) < chunk ? (batch - b0) : chunk;
+                ks_fused(c, in3 + (size_t)b0 * 3 * poly + 2 * poly, nb, limbs, ext.as<u64>(), ksk, key_kl,
+                         in3 + (size_t)b0 * 3 * poly, out2 + (size_t)b0 * 2 * poly, (long long)(3 * poly), false, 3);
+            }
+            return;
+        }
         // out2 <- (c0, c1) ; target <- c2
         { KernelTimer ktm(c, "k_copy_relin_c0c1", 1); MOAI_CUDA_CHECK(cudaMemcpy2DAsync(out2, 2 * poly * sizeof(u64), in3, 3 * poly * sizeof(u64),
                                           2 * poly * sizeof(u64), (size_t)batch, cudaMemcpyDeviceToDevice, c->stream)); }

@@ -79,7 +79,7 @@ namespace moai
     void ks_mac_int(Context *c, const u64 *ext, const u64 *ksk, u64 *acc, long long batch, const KsShape &sh, int key_kl,
                     int I);
     void divround_finish(Context *c, const u64 *in, const u64 *u, const u64 *addend, u64 *out, long long P, int targets,
-                         int limbs_in, const Twiddle *d_inv, bool addend_even_only);
+                         int limbs_in, const Twiddle *d_inv, bool addend_even_only, int addend_group = 2);
     // up to KSM_R (csrc/ntt.cuh) hoisted rotations in one pass over the extended digits
     bool ks_multi_enabled(Context *c, int limbs);
     void rotate_hoisted_multi(Context *c, const u64 *ct, const u64 *ext, long long batch, int limbs, int n_rot,
