@@ -85,7 +85,8 @@ int32_t moai_keys_add_grouped(moai_keys *keys, uint32_t galois_elt, const uint64
  * its c1 is the centred lift of residues modulo q_0, i.e. as an integer polynomial it is ONE digit below the special
  * prime, and sum_J K_J encrypts p * s': the key switch needs no decomposition at all (one NTT for the special prime).
  * moai_key_prepare_single: SEAL-layout key -> [1][2][key_limbs][N]; used by the first CoeffToSlot stage in hoisting
- * mode 2 (moai_bootstrapper_set_hoisting), which then runs on baby steps only.                                      */
+ * mode 2 (moai_bootstrapper_set_hoisting), which then runs on baby steps only.  Register keys prepared with
+ * pre_permute = 0: the stage's fused kernel forms sigma(ext) (.) K by gathering the digit, not by permuting the key. */
 int32_t moai_key_prepare_single(moai_context *ctx, const uint64_t *ksk_in, uint32_t galois_elt, int32_t pre_permute,
                                 uint64_t *ksk_out);
 int32_t moai_keys_add_single(moai_keys *keys, uint32_t galois_elt, const uint64_t *ksk_single);

@@ -465,9 +465,10 @@ class Backend:
                                                     C.c_int32(int(pre_permute)), _ptr(out)))
         return GroupedKey(out, k, max_limbs)
 
-    def key_prepare_single(self, ksk, elt, pre_permute=True):
-        """SEAL-layout Galois key -> single-digit key [1, 2, kl, n] (sum of all digits, pre-permuted) for rotations of a
-        mod-raised ciphertext (first CoeffToSlot stage, hoisting mode 2)."""
+    def key_prepare_single(self, ksk, elt, pre_permute=False):
+        """SEAL-layout Galois key -> single-digit key [1, 2, kl, n] (sum of all digits, NATURAL order: the fused
+        first-stage kernel gathers the digit instead of permuting the key) for rotations of a mod-raised ciphertext
+        (first CoeffToSlot stage, hoisting mode 2)."""
         out = self.empty(1, 2, self.kl, self.n)
         self._chk(self.lib.moai_key_prepare_single(self.h, _ptr(ksk), C.c_uint32(elt), C.c_int32(int(pre_permute)), _ptr(out)))
         return out

@@ -760,15 +760,19 @@ namespace moai
             rkeys.push_back(layout == KS_SINGLE ? &keys.galois_single.at(elts[j]) : keys.fast(c, elts[j], limbs, layout));
         }
         const int R = (int)rot_idx.size();
+        if (layout == KS_SINGLE && G != 1)
+        {
+            return Ct(); // the single-digit stage is planned with baby steps only
+        }
         // chunk: bound the workspace (digits + one inner product per rotation + the giants' sums) to the key-switch budget
         const size_t acc_words = (size_t)2 * sh.rns * N;
         const size_t ext_bytes = layout == KS_SINGLE ? ks_single_ext_bytes_per_ct(c, limbs)
                                  : (layout > 0 ? ksg_ext_bytes_per_ct(c, limbs, layout) : ks_ext_bytes_per_ct(c, limbs));
-        const size_t per_ct_ws = ext_bytes + (size_t)(std::max(R, 1) + G) * acc_words * sizeof(u64);
+        const size_t per_ct_ws = ext_bytes + (size_t)((layout == KS_SINGLE ? 0 : std::max(R, 1)) + G) * acc_words * sizeof(u64);
         long long chunk = std::max<long long>(1, (long long)(ks_ext_budget() / per_ct_ws));
         chunk = std::min<long long>(chunk, ct.batch);
         Scratch ext((size_t)chunk * ext_bytes, c->stream);
-        Scratch accs((size_t)std::max(R, 1) * chunk * acc_words * sizeof(u64), c->stream);
+        Scratch accs((size_t)(layout == KS_SINGLE ? 1 : std::max(R, 1) * chunk * acc_words) * sizeof(u64), c->stream);
         Scratch outs((size_t)G * chunk * acc_words * sizeof(u64), c->stream);
         Scratch cP((size_t)chunk * 2 * limbs * N * sizeof(u64), c->stream);
         const size_t per_ct = (size_t)2 * limbs * N;
@@ -789,6 +793,30 @@ namespace moai
                 ks_decompose(c, src + (size_t)limbs * N, nb, limbs, ext.as<u64>(), (long long)per_ct);
             }
             ew_multiply_scalar(c, src, info.h_pmod.data(), cP.as<u64>(), nb, 2, limbs);
+            if (layout == KS_SINGLE)
+            {
+                // one fused pass per BSGS_MAX_BABY rotations: gather of the digit, product with the natural-order key,
+                // product with the diagonal (k_bsgs_single)
+                u64 *o = outs.as<u64>();
+                int ri = 0;
+                for (int j0 = 0; j0 < nbaby; j0 += BSGS_MAX_BABY)
+                {
+                    const int cnt = std::min(BSGS_MAX_BABY, nbaby - j0);
+                    std::vector<const u64 *> kp(cnt), pp(cnt);
+                    std::vector<const uint32_t *> perm(cnt);
+                    for (int j = 0; j < cnt; j++)
+                    {
+                        const bool ident = elts[j0 + j] == 0;
+                        kp[j] = ident ? nullptr : rkeys[ri]->p;
+                        perm[j] = ident ? nullptr : c->galois_table(elts[j0 + j]);
+                        ri += ident ? 0 : 1;
+                        pp[j] = pts[j0 + j];
+                    }
+                    bsgs_single(c, ext.as<u64>(), kp.data(), perm.data(), pp.data(), cnt, c->kl, o, cP.as<u64>(), nb, sh, j0 > 0);
+                }
+                ks_moddown(c, o, nb * 2, limbs, 0, nullptr, false, inner[0].d + (size_t)b0 * per_ct);
+                continue;
+            }
             // inner products of every rotation with its key (no mod-down), KSM_R keys per pass over the digits
             for (int r0 = 0; r0 < R; r0 += KSM_R)
             {

@@ -82,6 +82,9 @@ namespace moai
             const Twiddle *d_yconst = nullptr; // [limbs]  prod(E) (Q_g / q_J)^-1 mod q_J
             const Twiddle *d_zconst = nullptr; // [k + 1]  (P' / p_i)^-1 mod p_i
             const Twiddle *d_pinv = nullptr;   // [limbs]  P'^-1 mod q_j
+            const Twiddle *d_qe = nullptr;     // [limbs]  prod(E) mod q_j
+            const int *d_own = nullptr;        // [rns]    digit whose group holds target I (FP64-path data primes), else -1
+            int n_own = 0;
             const int *d_ids = nullptr;        // [rns]
             std::vector<u64> h_pmod;           // [limbs]  P' mod q_j
             std::vector<int> h_ids;            // [rns]
@@ -300,6 +303,33 @@ namespace moai
                 t->h_pmod[j] = v;
             }
             t->h_ids = ids;
+            std::vector<Twiddle> qe(limbs);
+            for (int j = 0; j < limbs; j++)
+            {
+                const u64 q = c->q[j];
+                u64 v = 1;
+                for (int i = L - k; i < L; i++)
+                {
+                    v = h_mulmod(v, c->q[i] % q, q);
+                }
+                qe[j] = h_shoup(v, q);
+            }
+            std::vector<int> own(t->rns, -1);
+            for (int g = 0; g < t->digits; g++)
+            {
+                for (int j = 0; j < cnt[g]; j++)
+                {
+                    if (c->h_limb[s0[g] + j].fp_class != 0)
+                    {
+                        own[s0[g] + j] = g;
+                    }
+                }
+            }
+            for (int v : own)
+            {
+                t->n_own += v >= 0;
+            }
+            const size_t o_qe = bl.put(qe), o_own = bl.put(own);
             const size_t o_z = bl.put(zconst), o_p = bl.put(pinv);
             MOAI_CUDA_CHECK(cudaMalloc(&t->blob, bl.bytes.size()));
             MOAI_CUDA_CHECK(cudaMemcpy(t->blob, bl.bytes.data(), bl.bytes.size(), cudaMemcpyHostToDevice));
@@ -310,6 +340,8 @@ namespace moai
             t->d_yconst = reinterpret_cast<const Twiddle *>(base + o_y);
             t->d_zconst = reinterpret_cast<const Twiddle *>(base + o_z);
             t->d_pinv = reinterpret_cast<const Twiddle *>(base + o_p);
+            t->d_qe = reinterpret_cast<const Twiddle *>(base + o_qe);
+            t->d_own = reinterpret_cast<const int *>(base + o_own);
             t->shape.digits = t->digits;
             t->shape.rns = t->rns;
             t->shape.n_data = limbs;
@@ -335,6 +367,27 @@ namespace moai
             v.x = mul_shoup(v.x, w.w, w.wq, q);
             v.y = mul_shoup(v.y, w.w, w.wq, q);
             data[i] = v;
+        }
+
+        // out[b][l][n] = src[b * stride + l * n ...] * consts[l]  (mod q_l): prod(E) * c1 in NTT form
+        __global__ void k_scale_from(const ulonglong2 *__restrict__ src, long long stride2, ulonglong2 *__restrict__ out,
+                                     long long total2, int log_n2, int limbs, const Twiddle *__restrict__ consts,
+                                     const LimbConst *__restrict__ lcs)
+        {
+            const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= total2)
+            {
+                return;
+            }
+            const long long per = (long long)limbs << log_n2;
+            const long long b = i / per, rest = i % per;
+            const int l = (int)(rest >> log_n2);
+            const u64 q = lcs[l].q;
+            const Twiddle w = consts[l];
+            ulonglong2 v = src[b * stride2 + rest];
+            v.x = mul_shoup(v.x, w.w, w.wq, q);
+            v.y = mul_shoup(v.y, w.w, w.wq, q);
+            out[i] = v;
         }
 
         void scale_slots(Context *c, u64 *data, long long polys, int slots, const int *d_ids, const Twiddle *d_consts)
@@ -504,6 +557,20 @@ namespace moai
         return (size_t)(limbs + k + 1) * ksg_digits(c, k, limbs) * c->n * sizeof(u64);
     }
 
+    // prod(E) * target in NTT form, [batch][limbs][n]: the residues of every digit modulo its OWN primes
+    static void ksg_direct(Context *c, const KsgTables &t, const u64 *target, long long batch, long long target_stride,
+                           u64 *direct)
+    {
+        const long long total2 = batch * t.limbs * (long long)(c->n / 2);
+        const long long stride2 = (target_stride ? target_stride : (long long)t.limbs * (long long)c->n) / 2;
+        KernelTimer kt(c, "k_scale_slots", 1);
+        k_scale_from<<<(unsigned)((total2 + 255) / 256), 256, 0, c->stream>>>(
+            reinterpret_cast<const ulonglong2 *>(target), stride2, reinterpret_cast<ulonglong2 *>(direct), total2,
+            c->log_n - 1, t.limbs, t.d_qe, c->d_limb);
+        c->launches += 1;
+        MOAI_CUDA_CHECK(cudaGetLastError());
+    }
+
     void ksg_decompose(Context *c, const u64 *target, long long batch, int limbs, int k, u64 *ext,
                        long long target_stride, int passes)
     {
@@ -517,7 +584,12 @@ namespace moai
         NttPrologue pro;
         pro.src = d.as<u64>();
         pro.mode = 3;
-        pro.conv = &t.dec;
+        ConvTab dec = t.dec;
+        // pass A alone feeds the fused key-switch kernel, which takes every digit's residue modulo its own primes
+        // directly (ksg_direct): those polynomials are skipped
+        dec.own = passes == 1 ? t.d_own : nullptr;
+        pro.skipped = passes == 1 ? batch * t.n_own : 0;
+        pro.conv = &dec;
         ntt_forward(c, ext, batch * t.rns * t.digits, t.d_ids, t.rns, t.digits, &pro, passes);
     }
 
@@ -726,12 +798,14 @@ namespace moai
         chunk = chunk < 1 ? 1 : (chunk > batch ? batch : chunk);
         Scratch ext((size_t)chunk * per_ext, c->stream);
         Scratch acc((size_t)chunk * 2 * t.rns * n * sizeof(u64), c->stream);
+        Scratch direct((size_t)chunk * limbs * n * sizeof(u64), c->stream);
         const size_t tstride = target_stride ? (size_t)target_stride : (size_t)limbs * n;
         for (long long b0 = 0; b0 < batch; b0 += chunk)
         {
             const long long nb = std::min(chunk, batch - b0);
             ksg_decompose(c, target + (size_t)b0 * tstride, nb, limbs, k, ext.as<u64>(), target_stride, /*passes=*/1);
-            ks_passb_mac(c, ext.as<u64>(), nb, t.shape, ksk, key_kl, acc.as<u64>());
+            ksg_direct(c, t, target + (size_t)b0 * tstride, nb, target_stride, direct.as<u64>());
+            ks_passb_mac(c, ext.as<u64>(), nb, t.shape, ksk, key_kl, acc.as<u64>(), direct.as<u64>(), t.d_own);
             ksg_int_targets(c, t, ext.as<u64>(), nb, ksk, key_kl, acc.as<u64>(), true);
             const size_t off = (size_t)b0 * 2 * limbs * n;
             ksg_moddown(c, acc.as<u64>(), nb * 2, limbs, k,

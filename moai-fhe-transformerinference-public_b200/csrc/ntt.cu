@@ -658,6 +658,10 @@ namespace moai
             const int I = (int)((poly / a.div) % a.period);
             const int g = (int)(poly % a.div);
             const long long b = poly / ((long long)a.period * a.div);
+            if (a.conv.own && a.conv.own[I] == g)
+            {
+                return; // the digit's residue modulo its own primes is taken directly by the fused key-switch kernel
+            }
             const int limb = a.limb_ids[I];
             const LimbConst lc = a.limb[limb];
             u64 *base = a.data + ((size_t)poly << a.log_n) + tile * TB + tb;
@@ -731,6 +735,8 @@ namespace moai
             const double *tw_fp;    // [kl][n]
             const LimbConst *limb;  // [kl]
             const int *ids_ks;      // [rns]: prime index of target modulus I
+            const u64 *direct;      // [batch][n_data][n] or nullptr (see ks_passb_mac)
+            const int *own;         // [rns] or nullptr
             int limbs, rns, n_data, key_kl, log_n; // limbs = digits (KsShape, ntt.cuh)
         };
 
@@ -770,9 +776,15 @@ namespace moai
                     cp_async16(kst + (8 + u) * FT, src + key_poly + 2 * u);
                 }
             };
-            issue_data(0);
+            const int own = a.own ? a.own[I] : -1; // digit taken from a.direct instead of being transformed
+            // digit order: the direct one first (its plain loads then overlap the twiddle loads below), the others in order
+            auto digit_at = [&](int i) { return own < 0 ? i : (i == 0 ? own : (i <= own ? i - 1 : i)); };
+            if (own < 0)
+            {
+                issue_data(0);
+            }
             cp_async_commit();
-            issue_keys(0);
+            issue_keys(digit_at(0));
             cp_async_commit();
 
             // twiddles, loaded once for all digits: the 15 row-uniform ones of the first four stages
@@ -809,10 +821,31 @@ namespace moai
             auto key_d = [&](u64 v) { return f.in_outer(v); };
             const int red_every = WIDE ? 2 : 8; // |acc| <= 0.5 p + 8 * 0.65 p  /  0.5 p + 2 * 1.125 p
 
-            for (int J = 0; J < a.limbs; J++)
+            for (int it = 0; it < a.limbs; it++)
             {
+                const int J = digit_at(it), Jn = digit_at(it + 1);
                 double x[16];
                 cp_async_wait_1(); // data(J) has landed (keys(J) may still be in flight)
+                if (J == own)
+                {
+                    // NTT_I(D_J mod q_I) = prod(E) * c_I is the input limb itself: no transform
+                    const ulonglong2 *dp = reinterpret_cast<const ulonglong2 *>(
+                        a.direct + (((size_t)b * a.n_data + I) << a.log_n) + (size_t)row * 256 + 16 * t);
+#pragma unroll
+                    for (int k = 0; k < 16; k += 2)
+                    {
+                        const ulonglong2 v = __ldg(dp + (k >> 1));
+                        x[k] = f.red(f.in_outer(v.x));
+                        x[k + 1] = f.red(f.in_outer(v.y));
+                    }
+                    if (it + 1 < a.limbs)
+                    {
+                        issue_data(Jn); // the row tile is idle
+                    }
+                    cp_async_commit();
+                }
+                else
+                {
                 __syncwarp();      // a row is half a warp: its 16 threads' copies are now visible to each other
 #pragma unroll
                 for (int k = 0; k < 16; k++)
@@ -846,9 +879,9 @@ namespace moai
                     x[k] = srow[17 * t + k];
                 }
                 __syncwarp();
-                if (J + 1 < a.limbs)
+                if (it + 1 < a.limbs)
                 {
-                    issue_data(J + 1); // lands in the row tile while the last stages and the MAC run
+                    issue_data(Jn); // lands in the row tile while the last stages and the MAC run
                 }
                 cp_async_commit();
                 f.phase_begin_fwd(x);
@@ -873,6 +906,7 @@ namespace moai
                         x[k] = f.red(x[k]); // multiplier input below 2^52
                     }
                 }
+                } // J != own
                 cp_async_wait_1(); // keys(J) have landed
 #pragma unroll
                 for (int u = 0; u < 8; u++)
@@ -883,12 +917,12 @@ namespace moai
                     acc1[2 * u] = __dadd_rn(acc1[2 * u], f.mul_lazy(x[2 * u], key_d(k1.x)));
                     acc1[2 * u + 1] = __dadd_rn(acc1[2 * u + 1], f.mul_lazy(x[2 * u + 1], key_d(k1.y)));
                 }
-                if (J + 1 < a.limbs)
+                if (it + 1 < a.limbs)
                 {
-                    issue_keys(J + 1);
+                    issue_keys(Jn);
                 }
                 cp_async_commit();
-                if ((J + 1) % red_every == 0)
+                if ((it + 1) % red_every == 0)
                 {
 #pragma unroll
                     for (int k = 0; k < 16; k++)
@@ -1244,7 +1278,7 @@ namespace moai
         {
             if (do_a)
             {
-                KernelTimer kt(c, a.src_mode == 3 ? "k_ntt_fwd_pass_a_conv" : "k_ntt_fwd_pass_a", a.count);
+                KernelTimer kt(c, a.src_mode == 3 ? "k_ntt_fwd_pass_a_conv" : "k_ntt_fwd_pass_a", a.count - a.skipped);
                 const long long ctas_a = a.count * (256 / TB);
                 if (a.src_mode == 3)
                 {
@@ -1308,6 +1342,7 @@ namespace moai
             {
                 MOAI_REQUIRE(pro->conv != nullptr, "base-conversion prologue without tables");
                 a.conv = *pro->conv;
+                a.skipped = pro->skipped;
             }
         }
         switch (c->log_n)
@@ -1395,7 +1430,7 @@ namespace moai
     }
 
     void ks_passb_mac(Context *c, const u64 *mid, long long batch, const KsShape &sh, const u64 *ksk, int key_kl,
-                      u64 *acc)
+                      u64 *acc, const u64 *direct, const int *own)
     {
         const int limbs = sh.digits;
         MOAI_REQUIRE(c->log_n >= 12, "unsupported log_n");
@@ -1413,13 +1448,16 @@ namespace moai
         a.limbs = limbs;
         a.rns = rns;
         a.n_data = sh.n_data;
+        a.direct = direct;
+        a.own = direct ? own : nullptr;
         a.key_kl = key_kl;
         a.log_n = c->log_n;
         NttArgs na{ nullptr, c->d_fwd, c->d_fwd_fp, c->d_limb, nullptr, 1, 1, c->log_n, 0 };
         const int R = 1 << (c->log_n - 8);
         dim3 grid((unsigned)batch, (unsigned)(R / FR), (unsigned)rns);
         // units: limb-transforms finished inside the kernel (one per (ciphertext, digit, target modulus))
-        KernelTimer kt(c, "k_ks_passb_mac", batch * (long long)limbs * rns);
+        // (with `direct`, one digit per FP64-path data target needs no transform: n_data of them at most)
+        KernelTimer kt(c, "k_ks_passb_mac", batch * ((long long)limbs * rns - (direct ? sh.n_data : 0)));
         ks_passb_mac_kernel<<<grid, FT, KS_FUSED_SMEM, c->stream>>>(a, na);
         c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());

@@ -50,6 +50,9 @@ namespace moai
         const double *B26d = nullptr;
         const u64 *negQ = nullptr;           // [digits][rns]  (-Q_g) mod m_I
         const double *negQd = nullptr;       // centred double
+        // [rns] or nullptr: digit whose group CONTAINS target I (its residue modulo q_I is the input limb itself,
+        // times a constant): the fused key-switch kernel takes that product directly and the polynomial is skipped
+        const int *own = nullptr;
         int src_limbs = 0;
     };
 
@@ -82,6 +85,7 @@ namespace moai
         int kl = 0;
         const u64 *half_mod = nullptr; // [kl][kl]
         ConvTab conv;
+        long long skipped = 0;
     };
 
     struct NttPrologue
@@ -90,6 +94,7 @@ namespace moai
         int mode = 0;
         int last_id = 0;
         const ConvTab *conv = nullptr; // mode 3
+        long long skipped = 0;         // polynomials the pass-A kernel skips (ConvTab::own): not counted as work units
     };
 
     // Shape of a key-switch inner product.  SEAL's per-prime digits (S/evaluator.cpp:2805-2909): digits = limbs,
@@ -125,8 +130,10 @@ namespace moai
     // the evk for every FP64-path modulus.  mid = pass-A output [batch][rns][digits][n];
     // acc[batch][2][rns][n] receives canonical residues for those moduli (integer-path moduli
     // are left untouched for the un-fused kernels).
+    // direct / own (optional, grouped digits): own[I] = digit whose NTT-form residue modulo target I is
+    // direct[batch][n_data][n] (no transform needed; mid holds nothing for it)
     void ks_passb_mac(Context *c, const u64 *mid, long long batch, const KsShape &sh, const u64 *ksk, int key_kl,
-                      u64 *acc);
+                      u64 *acc, const u64 *direct = nullptr, const int *own = nullptr);
     void ntt_inverse(Context *c, u64 *data, long long count, const int *d_limb_ids, int period, int div = 1);
     // out of place: polynomial p is read from src + ((p / grp_size) * grp_stride + p % grp_size) * n (runs of grp_size
     // polynomials, grp_stride polynomials apart: one limb range of every ciphertext of a batch) and the coefficients

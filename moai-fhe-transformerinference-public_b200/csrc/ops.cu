@@ -794,15 +794,21 @@ namespace moai
             ulonglong2 v = make_ulonglong2(0, 0);
             if (a.acc[j])
             {
-                const uint2 ix = __ldg(reinterpret_cast<const uint2 *>(a.perm[j]) + within);
-                const u64 *src = a.acc[j] + ((bp * a.rns + I) << log_n);
-                v.x = src[ix.x];
-                v.y = src[ix.y];
+                // The NTT-domain automorphism maps the aligned pair (2w, 2w + 1) onto an aligned pair (j, j ^ 1): the two
+                // positions differ in the top bit of the bit-reversed index, i.e. by N in the exponent, and N e = N
+                // (mod 2N) for odd e.  One 16-byte gather per pair, swapped when the image starts at the odd slot.
+                const unsigned ix = __ldg(a.perm[j] + 2 * within);
+                const long long at = (long long)(ix >> 1);
+                const bool swap = (ix & 1u) != 0;
+                const ulonglong2 w = reinterpret_cast<const ulonglong2 *>(a.acc[j] + ((bp * a.rns + I) << log_n))[at];
+                v.x = swap ? w.y : w.x;
+                v.y = swap ? w.x : w.y;
                 if (data && poly0)
                 {
-                    const u64 *cp_c0 = a.cP + (((bp & ~1ll) * a.n_data + I) << log_n); // P' * c0 of this ciphertext
-                    v.x = addmod(v.x, cp_c0[ix.x], q);
-                    v.y = addmod(v.y, cp_c0[ix.y], q);
+                    // P' * c0 of this ciphertext
+                    const ulonglong2 z = reinterpret_cast<const ulonglong2 *>(a.cP + (((bp & ~1ll) * a.n_data + I) << log_n))[at];
+                    v.x = addmod(v.x, swap ? z.y : z.x, q);
+                    v.y = addmod(v.y, swap ? z.x : z.y, q);
                 }
             }
             else if (data)
@@ -813,56 +819,80 @@ namespace moai
         }
 
         // FP64-path primes: exact products on the FP64 pipe (fpfield.cuh), sums reduced every 2 / 8 terms
-        template <bool WIDE>
+        template <bool WIDE, int GM>
         __device__ __forceinline__ void bsgs_ext_fp(const FpField<WIDE> &f, const BsgsExtArgs &a, long long bp, int I,
                                                     long long within, int log_n2, bool data, bool poly0)
         {
-            double rx[BSGS_MAX_BABY], ry[BSGS_MAX_BABY];
-#pragma unroll
-            for (int j = 0; j < BSGS_MAX_BABY; j++)
-            {
-                if (j < a.n_baby)
-                {
-                    const ulonglong2 v = bsgs_ext_value(a, j, bp, I, within, log_n2 + 1, data, poly0, f.pi);
-                    rx[j] = f.red(f.in_outer(v.x)); // centred: |r| <= p/2 + 1
-                    ry[j] = f.red(f.in_outer(v.y));
-                }
-            }
+            // the baby steps are taken 8 at a time (8 gathers in flight per thread, 8 x 2 live values), the giants' sums
+            // stay in registers across the groups
+            constexpr int HALF = 8;
             const long long o = ((bp * a.rns + I) << log_n2) + within;
             const long long pt_off = ((long long)I << log_n2) + within;
             const int red_every = WIDE ? 2 : 8;
-            for (int g = 0; g < a.n_giant; g++)
+            double sx[GM], sy[GM];
+#pragma unroll
+            for (int g = 0; g < GM; g++)
             {
-                double sx = 0.0, sy = 0.0;
-                if (a.accumulate)
+                sx[g] = 0.0;
+                sy[g] = 0.0;
+                if (g < a.n_giant && a.accumulate)
                 {
                     const ulonglong2 prev = reinterpret_cast<const ulonglong2 *>(a.out[g])[o];
-                    sx = f.red(f.in_outer(prev.x));
-                    sy = f.red(f.in_outer(prev.y));
+                    sx[g] = f.red(f.in_outer(prev.x));
+                    sy[g] = f.red(f.in_outer(prev.y));
                 }
-                int cnt = 0;
+            }
+            for (int j0 = 0; j0 < a.n_baby; j0 += HALF)
+            {
+                double rx[HALF], ry[HALF];
 #pragma unroll
-                for (int j = 0; j < BSGS_MAX_BABY; j++)
+                for (int j = 0; j < HALF; j++)
                 {
-                    if (j < a.n_baby && a.pt[g][j])
+                    if (j0 + j < a.n_baby)
                     {
-                        const ulonglong2 w = __ldg(reinterpret_cast<const ulonglong2 *>(a.pt[g][j]) + pt_off);
-                        sx = __dadd_rn(sx, f.mul_lazy(f.in_outer(w.x), rx[j]));
-                        sy = __dadd_rn(sy, f.mul_lazy(f.in_outer(w.y), ry[j]));
-                        if (++cnt % red_every == 0)
+                        const ulonglong2 v = bsgs_ext_value(a, j0 + j, bp, I, within, log_n2 + 1, data, poly0, f.pi);
+                        rx[j] = f.red(f.in_outer(v.x)); // centred: |r| <= p/2 + 1
+                        ry[j] = f.red(f.in_outer(v.y));
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < GM; g++)
+                {
+                    if (g < a.n_giant)
+                    {
+#pragma unroll
+                        for (int j = 0; j < HALF; j++)
                         {
-                            sx = f.red(sx);
-                            sy = f.red(sy);
+                            if (j0 + j < a.n_baby && a.pt[g][j0 + j])
+                            {
+                                const ulonglong2 w = __ldg(reinterpret_cast<const ulonglong2 *>(a.pt[g][j0 + j]) + pt_off);
+                                sx[g] = __dadd_rn(sx[g], f.mul_lazy(f.in_outer(w.x), rx[j]));
+                                sy[g] = __dadd_rn(sy[g], f.mul_lazy(f.in_outer(w.y), ry[j]));
+                                // at most red_every terms since the last reduction (absent diagonals only make it earlier)
+                                if ((j + 1) % red_every == 0)
+                                {
+                                    sx[g] = f.red(sx[g]);
+                                    sy[g] = f.red(sy[g]);
+                                }
+                            }
                         }
                     }
                 }
-                ulonglong2 res;
-                res.x = f.canon(sx);
-                res.y = f.canon(sy);
-                reinterpret_cast<ulonglong2 *>(a.out[g])[o] = res;
+            }
+#pragma unroll
+            for (int g = 0; g < GM; g++)
+            {
+                if (g < a.n_giant)
+                {
+                    ulonglong2 res;
+                    res.x = f.canon(sx[g]);
+                    res.y = f.canon(sy[g]);
+                    reinterpret_cast<ulonglong2 *>(a.out[g])[o] = res;
+                }
             }
         }
 
+        template <int GM> // giants' sums kept in registers: GM >= n_giant
         __global__ void __launch_bounds__(EW_THREADS) k_bsgs_ext(BsgsExtArgs a, long long polys, int log_n2,
                                                                  const LimbConst *__restrict__ lcs,
                                                                  const Twiddle *__restrict__ two64)
@@ -882,25 +912,18 @@ namespace moai
             const bool poly0 = (bp & 1) == 0;
             if (lc.fp_class == 1)
             {
-                bsgs_ext_fp<false>(FpField<false>(lc), a, bp, I, within, log_n2, data, poly0);
+                bsgs_ext_fp<false, GM>(FpField<false>(lc), a, bp, I, within, log_n2, data, poly0);
                 return;
             }
             if (lc.fp_class == 2)
             {
-                bsgs_ext_fp<true>(FpField<true>(lc), a, bp, I, within, log_n2, data, poly0);
+                bsgs_ext_fp<true, GM>(FpField<true>(lc), a, bp, I, within, log_n2, data, poly0);
                 return;
             }
-            // integer-path primes (the 58-bit special prime): 128-bit lazy sums
+            // integer-path primes (the 58-bit special prime, 1 limb in 36): 128-bit lazy sums, one giant step at a time
+            // (the rotations' values are gathered again for every giant step: few CTAs take this path, and it keeps the
+            // kernel's register count at the FP64 path's)
             const Twiddle t64 = two64[prime];
-            ulonglong2 r[BSGS_MAX_BABY];
-#pragma unroll
-            for (int j = 0; j < BSGS_MAX_BABY; j++)
-            {
-                if (j < a.n_baby)
-                {
-                    r[j] = bsgs_ext_value(a, j, bp, I, within, log_n2 + 1, data, poly0, lc.q);
-                }
-            }
             const long long o = ((bp * a.rns + I) << log_n2) + within;
             const long long pt_off = ((long long)I << log_n2) + within;
             for (int g = 0; g < a.n_giant; g++)
@@ -912,14 +935,14 @@ namespace moai
                     sx.lo = prev.x;
                     sy.lo = prev.y;
                 }
-#pragma unroll
-                for (int j = 0; j < BSGS_MAX_BABY; j++)
+                for (int j = 0; j < a.n_baby; j++)
                 {
-                    if (j < a.n_baby && a.pt[g][j])
+                    if (a.pt[g][j])
                     {
+                        const ulonglong2 v = bsgs_ext_value(a, j, bp, I, within, log_n2 + 1, data, poly0, lc.q);
                         const ulonglong2 w = __ldg(reinterpret_cast<const ulonglong2 *>(a.pt[g][j]) + pt_off);
-                        mac_wide(sx, r[j].x, w.x);
-                        mac_wide(sy, r[j].y, w.y);
+                        mac_wide(sx, v.x, w.x);
+                        mac_wide(sy, v.y, w.y);
                     }
                 }
                 ulonglong2 res;
@@ -959,7 +982,227 @@ namespace moai
         const long long ctas = batch * 2 * sh.rns * (long long)((c->n / 2) / EW_THREADS);
         MOAI_REQUIRE((c->n / 2) % EW_THREADS == 0 && ctas < (1ll << 31), "unsupported shape for the fused inner sums");
         KernelTimer kt(c, "k_bsgs_ext", 1);
-        k_bsgs_ext<<<(unsigned)ctas, EW_THREADS, 0, c->stream>>>(a, batch * 2, c->log_n - 1, c->d_limb, c->d_two64);
+        if (n_giant == 1)
+        {
+            k_bsgs_ext<1><<<(unsigned)ctas, EW_THREADS, 0, c->stream>>>(a, batch * 2, c->log_n - 1, c->d_limb, c->d_two64);
+        }
+        else if (n_giant <= 4)
+        {
+            k_bsgs_ext<4><<<(unsigned)ctas, EW_THREADS, 0, c->stream>>>(a, batch * 2, c->log_n - 1, c->d_limb, c->d_two64);
+        }
+        else
+        {
+            k_bsgs_ext<BSGS_MAX_GIANT><<<(unsigned)ctas, EW_THREADS, 0, c->stream>>>(a, batch * 2, c->log_n - 1, c->d_limb,
+                                                                                    c->d_two64);
+        }
+        c->launches += 1;
+        MOAI_CUDA_CHECK(cudaGetLastError());
+    }
+
+    // ------------------------------------------------------------------ single-digit stage (mod-raised input)
+    // The first CoeffToSlot stage of the bootstrapping: the mod-raised c1 is ONE small digit (ksgroup.hpp), so the
+    // key-switch inner product of rotation r is a single product per limb and is formed on the fly:
+    //     out[b][k] = sum_r pt_r (.) sigma_r( ext[b] (.) K'_r[k] + (P c0, 0) )
+    //               = sum_r pt_r (.) ( sigma_r(ext[b]) (.) K_r[k] + sigma_r(P c0, 0) ),     K_r in NATURAL order
+    // (sigma_r is a ring automorphism: it distributes over the product, and sigma_r(K'_r) = K_r), i.e. one gather of the
+    // 36 limbs of ext per rotation instead of materialising 2 x 36 limbs of inner product per rotation and ciphertext.
+    namespace
+    {
+        struct BsgsSingleArgs
+        {
+            const u64 *ext;                       // [batch][rns][n]
+            const u64 *key[BSGS_MAX_BABY];        // [2][key_kl][n] natural order; nullptr = the identity rotation
+            const uint32_t *perm[BSGS_MAX_BABY];
+            const u64 *pt[BSGS_MAX_BABY];         // [rns][n]
+            u64 *out;                             // [batch][2][rns][n]
+            const u64 *cP;                        // [batch][2][n_data][n] = P * ct
+            const int *ids;
+            int n_rot, rns, n_data, key_kl, accumulate;
+        };
+
+        template <bool WIDE>
+        __device__ __forceinline__ void bsgs_single_fp(const FpField<WIDE> &f, const BsgsSingleArgs &a, long long bp, int I,
+                                                       long long within, int log_n2, bool data, bool poly0)
+        {
+            const int log_n = log_n2 + 1;
+            const long long b = bp >> 1;
+            const int k = (int)(bp & 1);
+            const int key_limb = I < a.n_data ? I : I + a.key_kl - a.rns;
+            const long long o = ((bp * a.rns + I) << log_n2) + within;
+            const long long lo = ((long long)I << log_n2) + within;
+            const ulonglong2 *ext = reinterpret_cast<const ulonglong2 *>(a.ext + ((b * a.rns + I) << log_n));
+            const ulonglong2 *cp0 = reinterpret_cast<const ulonglong2 *>(a.cP + (((b * 2) * a.n_data + I) << log_n));
+            double sx = 0.0, sy = 0.0;
+            if (a.accumulate)
+            {
+                const ulonglong2 prev = reinterpret_cast<const ulonglong2 *>(a.out)[o];
+                sx = f.red(f.in_outer(prev.x));
+                sy = f.red(f.in_outer(prev.y));
+            }
+            const int red_every = WIDE ? 2 : 8;
+            int terms = 0;
+#pragma unroll 4
+            for (int r = 0; r < a.n_rot; r++)
+            {
+                if (!a.pt[r])
+                {
+                    continue;
+                }
+                double tx, ty;
+                if (a.key[r])
+                {
+                    const unsigned ix = __ldg(a.perm[r] + 2 * within);
+                    const long long at = (long long)(ix >> 1);
+                    const bool swap = (ix & 1u) != 0;
+                    const ulonglong2 e = ext[at];
+                    const ulonglong2 kv = __ldg(reinterpret_cast<const ulonglong2 *>(a.key[r]) +
+                                                (((long long)k * a.key_kl + key_limb) << log_n2) + within);
+                    const double ex = f.red(f.in_outer(swap ? e.y : e.x)), ey = f.red(f.in_outer(swap ? e.x : e.y));
+                    tx = f.mul_lazy(f.in_outer(kv.x), ex);
+                    ty = f.mul_lazy(f.in_outer(kv.y), ey);
+                    if (data && poly0)
+                    {
+                        const ulonglong2 z = cp0[at];
+                        tx = __dadd_rn(tx, f.in_outer(swap ? z.y : z.x));
+                        ty = __dadd_rn(ty, f.in_outer(swap ? z.x : z.y));
+                    }
+                    tx = f.red(tx);
+                    ty = f.red(ty);
+                }
+                else
+                {
+                    if (!data)
+                    {
+                        continue;
+                    }
+                    const ulonglong2 z = reinterpret_cast<const ulonglong2 *>(a.cP + ((bp * a.n_data + I) << log_n))[within];
+                    tx = f.red(f.in_outer(z.x));
+                    ty = f.red(f.in_outer(z.y));
+                }
+                const ulonglong2 w = __ldg(reinterpret_cast<const ulonglong2 *>(a.pt[r]) + lo);
+                sx = __dadd_rn(sx, f.mul_lazy(f.in_outer(w.x), tx));
+                sy = __dadd_rn(sy, f.mul_lazy(f.in_outer(w.y), ty));
+                if (++terms % red_every == 0)
+                {
+                    sx = f.red(sx);
+                    sy = f.red(sy);
+                }
+            }
+            ulonglong2 res;
+            res.x = f.canon(sx);
+            res.y = f.canon(sy);
+            reinterpret_cast<ulonglong2 *>(a.out)[o] = res;
+        }
+
+        __global__ void __launch_bounds__(EW_THREADS) k_bsgs_single(BsgsSingleArgs a, long long polys, int log_n2,
+                                                                    const LimbConst *__restrict__ lcs,
+                                                                    const Twiddle *__restrict__ two64)
+        {
+            // CTA order as in k_bsgs_ext: coefficient block fastest, then (ciphertext, polynomial), limb slowest
+            const int cblks = (1 << log_n2) / EW_THREADS;
+            const long long within = (blockIdx.x % cblks) * EW_THREADS + threadIdx.x;
+            const long long rest = blockIdx.x / cblks;
+            const long long bp = rest % polys;
+            const int I = (int)(rest / polys);
+            const int prime = a.ids[I];
+            const LimbConst lc = lcs[prime];
+            const bool data = I < a.n_data;
+            const bool poly0 = (bp & 1) == 0;
+            if (lc.fp_class == 1)
+            {
+                bsgs_single_fp<false>(FpField<false>(lc), a, bp, I, within, log_n2, data, poly0);
+                return;
+            }
+            if (lc.fp_class == 2)
+            {
+                bsgs_single_fp<true>(FpField<true>(lc), a, bp, I, within, log_n2, data, poly0);
+                return;
+            }
+            // integer path (the special prime)
+            const Twiddle t64 = two64[prime];
+            const int log_n = log_n2 + 1;
+            const long long b = bp >> 1;
+            const int k = (int)(bp & 1);
+            const int key_limb = I < a.n_data ? I : I + a.key_kl - a.rns;
+            const long long o = ((bp * a.rns + I) << log_n2) + within;
+            const long long lo = ((long long)I << log_n2) + within;
+            const ulonglong2 *ext = reinterpret_cast<const ulonglong2 *>(a.ext + ((b * a.rns + I) << log_n));
+            u128 sx{ 0, 0 }, sy{ 0, 0 };
+            if (a.accumulate)
+            {
+                const ulonglong2 prev = reinterpret_cast<const ulonglong2 *>(a.out)[o];
+                sx.lo = prev.x;
+                sy.lo = prev.y;
+            }
+            for (int r = 0; r < a.n_rot; r++)
+            {
+                if (!a.pt[r])
+                {
+                    continue;
+                }
+                u64 tx, ty;
+                if (a.key[r])
+                {
+                    const unsigned ix = __ldg(a.perm[r] + 2 * within);
+                    const long long at = (long long)(ix >> 1);
+                    const bool swap = (ix & 1u) != 0;
+                    const ulonglong2 e = ext[at];
+                    const ulonglong2 kv = __ldg(reinterpret_cast<const ulonglong2 *>(a.key[r]) +
+                                                (((long long)k * a.key_kl + key_limb) << log_n2) + within);
+                    tx = mulmod(swap ? e.y : e.x, kv.x, lc);
+                    ty = mulmod(swap ? e.x : e.y, kv.y, lc);
+                    if (data && poly0)
+                    {
+                        const ulonglong2 z = reinterpret_cast<const ulonglong2 *>(a.cP + (((b * 2) * a.n_data + I) << log_n))[at];
+                        tx = addmod(tx, swap ? z.y : z.x, lc.q);
+                        ty = addmod(ty, swap ? z.x : z.y, lc.q);
+                    }
+                }
+                else
+                {
+                    if (!data)
+                    {
+                        continue;
+                    }
+                    const ulonglong2 z = reinterpret_cast<const ulonglong2 *>(a.cP + ((bp * a.n_data + I) << log_n))[within];
+                    tx = z.x;
+                    ty = z.y;
+                }
+                const ulonglong2 w = __ldg(reinterpret_cast<const ulonglong2 *>(a.pt[r]) + lo);
+                mac_wide(sx, tx, w.x);
+                mac_wide(sy, ty, w.y);
+            }
+            ulonglong2 res;
+            res.x = barrett_reduce_acc(sx, lc, t64.w, t64.wq);
+            res.y = barrett_reduce_acc(sy, lc, t64.w, t64.wq);
+            reinterpret_cast<ulonglong2 *>(a.out)[o] = res;
+        }
+    } // namespace
+
+    void bsgs_single(Context *c, const u64 *ext, const u64 *const *key, const uint32_t *const *perm, const u64 *const *pt,
+                     int n_rot, int key_kl, u64 *out, const u64 *cP, long long batch, const KsShape &sh, bool accumulate)
+    {
+        MOAI_REQUIRE(n_rot >= 1 && n_rot <= BSGS_MAX_BABY && sh.digits == 1, "bad single-digit stage");
+        BsgsSingleArgs a;
+        a.ext = ext;
+        a.out = out;
+        a.cP = cP;
+        a.ids = sh.ids;
+        a.n_rot = n_rot;
+        a.rns = sh.rns;
+        a.n_data = sh.n_data;
+        a.key_kl = key_kl;
+        a.accumulate = accumulate ? 1 : 0;
+        for (int r = 0; r < n_rot; r++)
+        {
+            a.key[r] = key[r];
+            a.perm[r] = perm[r];
+            a.pt[r] = pt[r];
+        }
+        const long long ctas = batch * 2 * sh.rns * (long long)((c->n / 2) / EW_THREADS);
+        MOAI_REQUIRE((c->n / 2) % EW_THREADS == 0 && ctas < (1ll << 31), "unsupported shape for the fused inner sums");
+        KernelTimer kt(c, "k_bsgs_single", 1);
+        k_bsgs_single<<<(unsigned)ctas, EW_THREADS, 0, c->stream>>>(a, batch * 2, c->log_n - 1, c->d_limb, c->d_two64);
         c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
     }

@@ -46,6 +46,9 @@ namespace moai
     struct KsShape;
     void bsgs_ext(Context *c, const u64 *const *acc, const uint32_t *const *perm, int n_baby, const u64 *const *pt,
                   int n_giant, u64 *const *out, const u64 *cP, long long batch, const KsShape &sh, bool accumulate);
+    // the first CoeffToSlot stage on single-digit keys in natural order (one fused pass per 16 rotations; csrc/ops.cu)
+    void bsgs_single(Context *c, const u64 *ext, const u64 *const *key, const uint32_t *const *perm, const u64 *const *pt,
+                     int n_rot, int key_kl, u64 *out, const u64 *cP, long long batch, const KsShape &sh, bool accumulate);
     void moddown_special(Context *c, const u64 *in, long long P, int limbs, const u64 *addend, u64 *out,
                          bool addend_even_only);
 
