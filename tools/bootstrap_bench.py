@@ -65,7 +65,7 @@ def main():
             e = be.galois_elt_from_step(st)
             for lv in lvs:
                 if lv == 0:   # first CoeffToSlot stage, baby step: single-digit key [1, 2, kl, n]
-                    single[e] = rand_key()[:1].contiguous()
+                    single[e] = rand_key()[:1].clone()
                     key_bytes += single[e].numel() * 8
                     continue
                 k = be.ksg_best_extra(lv)

@@ -75,7 +75,7 @@ def setup(args, device=0, seed=11):
         def add(st, level):
             e = be.galois_elt_from_step(st)
             if level == 0:      # baby step of the first CoeffToSlot stage: single-digit key [1, 2, kl, n]
-                single[e] = rand_key()[:1].contiguous()
+                single[e] = rand_key()[:1].clone()
                 return
             k = be.ksg_best_extra(level)
             if k == 0:
