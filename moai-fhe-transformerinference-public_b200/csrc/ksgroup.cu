@@ -83,6 +83,8 @@ namespace moai
             const Twiddle *d_zconst = nullptr; // [k + 1]  (P' / p_i)^-1 mod p_i
             const Twiddle *d_pinv = nullptr;   // [limbs]  P'^-1 mod q_j
             const Twiddle *d_qe = nullptr;     // [limbs]  prod(E) mod q_j
+            const NttScale *d_yscale = nullptr; // [limbs]  yconst folded into the inverse transform's N^-1
+            const NttScale *d_zscale = nullptr; // [k + 1]  zconst likewise
             const int *d_own = nullptr;        // [rns]    digit whose group holds target I (FP64-path data primes), else -1
             int n_own = 0;
             const int *d_ids = nullptr;        // [rns]
@@ -329,6 +331,16 @@ namespace moai
             {
                 t->n_own += v >= 0;
             }
+            std::vector<NttScale> yscale(limbs), zscale(k + 1);
+            for (int j = 0; j < limbs; j++)
+            {
+                yscale[j] = ntt_scale_make(c, j, yconst[j].w);
+            }
+            for (int i = 0; i <= k; i++)
+            {
+                zscale[i] = ntt_scale_make(c, src_md[i], zconst[i].w);
+            }
+            const size_t o_ys = bl.put(yscale), o_zs = bl.put(zscale);
             const size_t o_qe = bl.put(qe), o_own = bl.put(own);
             const size_t o_z = bl.put(zconst), o_p = bl.put(pinv);
             MOAI_CUDA_CHECK(cudaMalloc(&t->blob, bl.bytes.size()));
@@ -341,6 +353,8 @@ namespace moai
             t->d_zconst = reinterpret_cast<const Twiddle *>(base + o_z);
             t->d_pinv = reinterpret_cast<const Twiddle *>(base + o_p);
             t->d_qe = reinterpret_cast<const Twiddle *>(base + o_qe);
+            t->d_yscale = reinterpret_cast<const NttScale *>(base + o_ys);
+            t->d_zscale = reinterpret_cast<const NttScale *>(base + o_zs);
             t->d_own = reinterpret_cast<const int *>(base + o_own);
             t->shape.digits = t->digits;
             t->shape.rns = t->rns;
@@ -348,25 +362,6 @@ namespace moai
             t->shape.ids = t->d_ids;
             c->ksg_cache[{ k, limbs }] = t;
             return *t;
-        }
-
-        // data[p][slot][n] *= consts[slot]  (mod the prime ids[slot])
-        __global__ void k_scale_slots(ulonglong2 *data, long long total2, int log_n2, int slots,
-                                      const int *__restrict__ ids, const Twiddle *__restrict__ consts,
-                                      const LimbConst *__restrict__ lcs)
-        {
-            const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-            if (i >= total2)
-            {
-                return;
-            }
-            const int slot = (int)((i >> log_n2) % slots);
-            const u64 q = lcs[ids[slot]].q;
-            const Twiddle w = consts[slot];
-            ulonglong2 v = data[i];
-            v.x = mul_shoup(v.x, w.w, w.wq, q);
-            v.y = mul_shoup(v.y, w.w, w.wq, q);
-            data[i] = v;
         }
 
         // out[b][l][n] = src[b * stride + l * n ...] * consts[l]  (mod q_l): prod(E) * c1 in NTT form
@@ -388,16 +383,6 @@ namespace moai
             v.x = mul_shoup(v.x, w.w, w.wq, q);
             v.y = mul_shoup(v.y, w.w, w.wq, q);
             out[i] = v;
-        }
-
-        void scale_slots(Context *c, u64 *data, long long polys, int slots, const int *d_ids, const Twiddle *d_consts)
-        {
-            const long long total2 = polys * slots * (long long)(c->n / 2);
-            KernelTimer kt(c, "k_scale_slots", 1);
-            k_scale_slots<<<(unsigned)((total2 + 255) / 256), 256, 0, c->stream>>>(
-                reinterpret_cast<ulonglong2 *>(data), total2, c->log_n - 1, slots, d_ids, d_consts, c->d_limb);
-            c->launches += 1;
-            MOAI_CUDA_CHECK(cudaGetLastError());
         }
 
         // out[G][k][I] = sum_{J in G} in[J][k][prime(I)]   (16-byte lanes; <= CONV_MAX terms below 2^61 each)
@@ -578,9 +563,9 @@ namespace moai
         const size_t n = c->n;
         Scratch d((size_t)batch * limbs * n * sizeof(u64), c->stream);
         MOAI_REQUIRE(target_stride % (long long)n == 0, "target stride must be a whole number of limbs");
+        // y_J = c_J * prod(E) (Q_g / q_J)^-1: the constant rides on the inverse transform's N^-1
         ntt_inverse_from(c, target, limbs, target_stride ? target_stride / (long long)n : limbs, d.as<u64>(), batch * limbs,
-                         c->d_ids, limbs);
-        scale_slots(c, d.as<u64>(), batch, limbs, c->d_ids, t.d_yconst);
+                         c->d_ids, limbs, 1, t.d_yscale);
         NttPrologue pro;
         pro.src = d.as<u64>();
         pro.mode = 3;
@@ -600,14 +585,25 @@ namespace moai
         const size_t n = c->n;
         const int np = k + 1;
         Scratch r((size_t)polys * np * n * sizeof(u64), c->stream);
-        ntt_inverse_from(c, acc + (size_t)limbs * n, np, t.rns, r.as<u64>(), polys * np, t.d_ids + limbs, np);
-        scale_slots(c, r.as<u64>(), polys, np, t.d_ids + limbs, t.d_zconst);
+        ntt_inverse_from(c, acc + (size_t)limbs * n, np, t.rns, r.as<u64>(), polys * np, t.d_ids + limbs, np, 1,
+                         t.d_zscale);
         Scratch u((size_t)polys * limbs * n * sizeof(u64), c->stream);
         NttPrologue pro;
         pro.src = r.as<u64>();
         pro.mode = 3;
         pro.conv = &t.md;
-        ntt_forward(c, u.as<u64>(), polys * limbs, c->d_ids, limbs, 1, &pro);
+        FinishEpi fin;
+        fin.in = acc;
+        fin.addend = addend;
+        fin.out = out;
+        fin.inv = t.d_pinv;
+        fin.limbs_in = t.rns;
+        fin.addend_even_only = addend_even_only ? 1 : 0;
+        fin.addend_group = addend_group;
+        if (ntt_forward(c, u.as<u64>(), polys * limbs, c->d_ids, limbs, 1, &pro, 3, &fin))
+        {
+            return;
+        }
         divround_finish(c, acc, u.as<u64>(), addend, out, polys, limbs, t.rns, t.d_pinv, addend_even_only, addend_group);
     }
 

@@ -510,8 +510,19 @@ namespace moai
             const size_t n = (size_t)1 << a.log_n;
             const long long poly = blockIdx.x / (256 / TB);
             const int tile = blockIdx.x % (256 / TB);
-            const int limb = a.limb_ids[(poly / a.div) % a.period];
-            const LimbConst lc = a.limb[limb];
+            const int slot = (int)((poly / a.div) % a.period);
+            const int limb = a.limb_ids[slot];
+            LimbConst lc = a.limb[limb];
+            if (a.scale) // a per-limb constant folded into the N^-1 of the last stage
+            {
+                const NttScale sc = a.scale[slot];
+                lc.inv_n = sc.inv_n;
+                lc.inv_n_quo = sc.inv_n_quo;
+                lc.inv_n_w = sc.inv_n_w;
+                lc.inv_n_w_quo = sc.inv_n_w_quo;
+                lc.inv_n_d = sc.inv_n_d;
+                lc.inv_n_w_d = sc.inv_n_w_d;
+            }
             u64 *base = a.data + ((size_t)poly << a.log_n) + tile * TB + tb;
             MOAI_DISPATCH_FIELD(lc, (inv_pass_a_body<LOGR>(f, base, sm, t, tb, n)))
         }
@@ -1080,6 +1091,39 @@ namespace moai
                     ct_stage_tw<2>(f, x, t2);
                     ct_stage_tw<1>(f, x, t1);
                 }
+                if (a.fin.out)
+                {
+                    // divide-and-round tail (FinishEpi): q is the polynomial index P, slot the target limb
+                    const FinishEpi &e = a.fin;
+                    const size_t off = (size_t)row * 256 + 16 * t;
+                    const ulonglong2 *in = reinterpret_cast<const ulonglong2 *>(
+                        e.in + (((size_t)q * e.limbs_in + slot) << a.log_n) + off);
+                    ulonglong2 *o = reinterpret_cast<ulonglong2 *>(e.out + (((size_t)q * a.period + slot) << a.log_n) + off);
+                    const ulonglong2 *ad = nullptr;
+                    if (e.addend && !(e.addend_even_only && (q & 1)))
+                    {
+                        ad = reinterpret_cast<const ulonglong2 *>(
+                            e.addend + (((size_t)((q >> 1) * e.addend_group + (q & 1)) * a.period + slot) << a.log_n) + off);
+                    }
+                    const Twiddle inv = e.inv[slot];
+                    const u64 qq = f.pi;
+#pragma unroll
+                    for (int k = 0; k < 16; k += 2)
+                    {
+                        const ulonglong2 c0 = in[k >> 1];
+                        ulonglong2 v;
+                        v.x = mul_shoup(submod(c0.x, f.out_fwd(x[k]), qq), inv.w, inv.wq, qq);
+                        v.y = mul_shoup(submod(c0.y, f.out_fwd(x[k + 1]), qq), inv.w, inv.wq, qq);
+                        if (ad)
+                        {
+                            const ulonglong2 z = ad[k >> 1];
+                            v.x = addmod(v.x, z.x, qq);
+                            v.y = addmod(v.y, z.y, qq);
+                        }
+                        o[k >> 1] = v;
+                    }
+                    continue;
+                }
                 ulonglong2 *out = reinterpret_cast<ulonglong2 *>(poly_ptr(q) + 16 * t);
 #pragma unroll
                 for (int k = 0; k < 16; k += 2)
@@ -1273,9 +1317,11 @@ namespace moai
         }
 
         // KernelTimer names: "k_ntt_fwd_pass_a" / "k_ntt_fwd_pass_b" with units = limb-transforms (bench.py's roofline)
+        // returns true when the FinishEpi epilogue was applied
         template <int LOGR>
-        void launch_fwd(Context *c, const NttArgs &a, cudaStream_t s, bool do_a = true, bool do_b = true)
+        bool launch_fwd(Context *c, NttArgs a, cudaStream_t s, bool do_a = true, bool do_b = true)
         {
+            bool fin_applied = false;
             if (do_a)
             {
                 KernelTimer kt(c, a.src_mode == 3 ? "k_ntt_fwd_pass_a_conv" : "k_ntt_fwd_pass_a", a.count - a.skipped);
@@ -1301,15 +1347,18 @@ namespace moai
                 if (grouped_on && !a.grp_size && a.count % ((long long)a.period * a.div) == 0 && seq_len >= 4 &&
                     a.period <= 65535)
                 {
+                    fin_applied = a.fin.out != nullptr;
                     dim3 grid((unsigned)((seq_len + GS - 1) / GS), (unsigned)((1 << LOGR) / FR), (unsigned)a.period);
                     ntt_fwd_pass_b_grouped<<<grid, FT, GROUPED_SMEM, s>>>(a, seq_len);
                 }
                 else
                 {
+                    a.fin = FinishEpi();
                     const long long ctas_b = a.count * ((1 << LOGR) / ROWS);
                     ntt_fwd_pass_b<<<(unsigned)ctas_b, ROWS * 16, 0, s>>>(a);
                 }
             }
+            return fin_applied;
         }
 
         template <int LOGR>
@@ -1322,12 +1371,12 @@ namespace moai
         }
     } // namespace
 
-    void ntt_forward(Context *c, u64 *data, long long count, const int *d_limb_ids, int period, int div,
-                     const NttPrologue *pro, int passes)
+    bool ntt_forward(Context *c, u64 *data, long long count, const int *d_limb_ids, int period, int div,
+                     const NttPrologue *pro, int passes, const FinishEpi *fin)
     {
         if (count <= 0)
         {
-            return;
+            return false;
         }
         const bool do_a = (passes & 1) != 0, do_b = (passes & 2) != 0;
         NttArgs a{ data, c->d_fwd, c->d_fwd_fp, c->d_limb, d_limb_ids, period, div, c->log_n, count };
@@ -1345,17 +1394,36 @@ namespace moai
                 a.skipped = pro->skipped;
             }
         }
+        if (fin && do_b && div == 1)
+        {
+            // only FP64-path target primes take the grouped kernel's FP64 body (the integer body stores in place)
+            bool all_fp = d_limb_ids == c->d_ids;
+            for (int l = 0; all_fp && l < period; l++)
+            {
+                all_fp = c->h_limb[l].fp_class != 0;
+            }
+            static const bool fuse_on = [] {
+                const char *e = getenv("MOAI_FUSE_FINISH");
+                return !e || atoi(e) != 0;
+            }();
+            if (all_fp && fuse_on)
+            {
+                a.fin = *fin;
+            }
+        }
+        bool applied = false;
         switch (c->log_n)
         {
-        case 12: launch_fwd<4>(c, a, c->stream, do_a, do_b); break;
-        case 13: launch_fwd<5>(c, a, c->stream, do_a, do_b); break;
-        case 14: launch_fwd<6>(c, a, c->stream, do_a, do_b); break;
-        case 15: launch_fwd<7>(c, a, c->stream, do_a, do_b); break;
-        case 16: launch_fwd<8>(c, a, c->stream, do_a, do_b); break;
+        case 12: applied = launch_fwd<4>(c, a, c->stream, do_a, do_b); break;
+        case 13: applied = launch_fwd<5>(c, a, c->stream, do_a, do_b); break;
+        case 14: applied = launch_fwd<6>(c, a, c->stream, do_a, do_b); break;
+        case 15: applied = launch_fwd<7>(c, a, c->stream, do_a, do_b); break;
+        case 16: applied = launch_fwd<8>(c, a, c->stream, do_a, do_b); break;
         default: throw StatusError{ INVALID_ARGUMENT, "unsupported log_n" };
         }
         c->launches += (do_a ? 1 : 0) + (do_b ? 1 : 0);
         MOAI_CUDA_CHECK(cudaGetLastError());
+        return applied;
     }
 
     namespace
@@ -1465,17 +1533,34 @@ namespace moai
 
     void ntt_inverse(Context *c, u64 *data, long long count, const int *d_limb_ids, int period, int div)
     {
-        ntt_inverse_from(c, nullptr, 0, 0, data, count, d_limb_ids, period, div);
+        ntt_inverse_from(c, nullptr, 0, 0, data, count, d_limb_ids, period, div, nullptr);
+    }
+
+    NttScale ntt_scale_make(Context *c, int prime, u64 constant)
+    {
+        typedef unsigned __int128 u128h;
+        const LimbConst &lc = c->h_limb[prime];
+        const u64 q = lc.q;
+        auto mk = [&](u64 base, u64 &w, u64 &wq, double &d) {
+            w = (u64)((u128h)base * (constant % q) % q);
+            wq = (u64)(((u128h)w << 64) / q);
+            d = w > q / 2 ? -(double)(q - w) : (double)w;
+        };
+        NttScale s;
+        mk(lc.inv_n, s.inv_n, s.inv_n_quo, s.inv_n_d);
+        mk(lc.inv_n_w, s.inv_n_w, s.inv_n_w_quo, s.inv_n_w_d);
+        return s;
     }
 
     void ntt_inverse_from(Context *c, const u64 *src, long long grp_size, long long grp_stride, u64 *data, long long count,
-                          const int *d_limb_ids, int period, int div)
+                          const int *d_limb_ids, int period, int div, const NttScale *d_scale)
     {
         if (count <= 0)
         {
             return;
         }
         NttArgs a{ data, c->d_inv, c->d_inv_fp, c->d_limb, d_limb_ids, period, div, c->log_n, count };
+        a.scale = d_scale;
         if (src)
         {
             MOAI_REQUIRE(grp_size >= 1 && grp_stride >= grp_size, "bad source layout");

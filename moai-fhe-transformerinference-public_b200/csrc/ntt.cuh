@@ -56,6 +56,29 @@ namespace moai
         int src_limbs = 0;
     };
 
+    // Optional constant folded into the inverse transform: the last stage multiplies by N^-1 (and by the last root);
+    // with scale[slot] it multiplies by c * N^-1 instead, so "INTT then scale by a per-limb constant" is one pass
+    // (slot = (p / div) % period, as for the limb ids).
+    struct NttScale
+    {
+        u64 inv_n, inv_n_quo, inv_n_w, inv_n_w_quo; // c N^-1 and c w N^-1 mod q with Shoup quotients
+        double inv_n_d, inv_n_w_d;                  // the same two as centred doubles
+    };
+    NttScale ntt_scale_make(Context *c, int prime, u64 constant);
+
+    // Optional epilogue of the forward transform's grouped pass B: the tail of a divide-and-round
+    // (S/util/rns.cpp:881-901, S/evaluator.cpp:2990-3018).  Polynomial p = (P, j) (period = targets, div = 1) is not
+    // stored; instead  out[P][j] = (in[P][j] - NTT(u)[P][j]) * inv[j] (+ addend)  is written, so the transformed
+    // correction never travels through HBM.
+    struct FinishEpi
+    {
+        const u64 *in = nullptr;     // [P][limbs_in][n]
+        const u64 *addend = nullptr; // polynomial P <-> (P / 2) * addend_group + P % 2 of [..][targets][n]
+        u64 *out = nullptr;          // [P][targets][n]
+        const Twiddle *inv = nullptr; // [targets]
+        int limbs_in = 0, addend_even_only = 0, addend_group = 2;
+    };
+
     struct NttArgs
     {
         u64 *data;             // [count][n]
@@ -86,6 +109,8 @@ namespace moai
         const u64 *half_mod = nullptr; // [kl][kl]
         ConvTab conv;
         long long skipped = 0;
+        const NttScale *scale = nullptr; // inverse transform only
+        FinishEpi fin;                   // forward transform, grouped pass B only
     };
 
     struct NttPrologue
@@ -114,8 +139,10 @@ namespace moai
     // Transforms `count` consecutive polynomials in place; polynomial p lives at data + p*n and
     // uses the prime with index d_limb_ids[(p / div) % period].
     // passes: bit 0 = pass A (row-pairing stages, + prologue), bit 1 = pass B (in-row stages)
-    void ntt_forward(Context *c, u64 *data, long long count, const int *d_limb_ids, int period, int div = 1,
-                     const NttPrologue *pro = nullptr, int passes = 3);
+    // fin: fuse the divide-and-round tail into pass B when the launch allows it (grouped pass B, FP64-path primes);
+    // returns true when it was applied (the caller then skips its finish kernel)
+    bool ntt_forward(Context *c, u64 *data, long long count, const int *d_limb_ids, int period, int div = 1,
+                     const NttPrologue *pro = nullptr, int passes = 3, const FinishEpi *fin = nullptr);
     // pass B of `groups` runs of `grp_size` consecutive polynomials, run g starting at
     // data + g * grp_stride * n, all modulo the single prime *d_limb_id
     void ntt_forward_pass_b_strided(Context *c, u64 *data, long long groups, long long grp_size, long long grp_stride,
@@ -139,5 +166,5 @@ namespace moai
     // polynomials, grp_stride polynomials apart: one limb range of every ciphertext of a batch) and the coefficients
     // land contiguously in data — saves the gather copy in front of an in-place transform
     void ntt_inverse_from(Context *c, const u64 *src, long long grp_size, long long grp_stride, u64 *data, long long count,
-                          const int *d_limb_ids, int period, int div = 1);
+                          const int *d_limb_ids, int period, int div = 1, const NttScale *d_scale = nullptr);
 } // namespace moai

@@ -291,7 +291,19 @@ namespace moai
             pro.src = t.as<u64>();
             pro.mode = 2;
             pro.last_id = last_id;
-            ntt_forward(c, u.as<u64>(), P * targets, c->d_ids, targets, 1, &pro);
+            // (c - u) q_last^-1 (+ addend) rides on the transform's second pass when the launch allows it
+            FinishEpi fin;
+            fin.in = in;
+            fin.addend = addend;
+            fin.out = out;
+            fin.inv = c->d_inv_last + (size_t)last_id * c->kl;
+            fin.limbs_in = limbs_in;
+            fin.addend_even_only = addend_even_only ? 1 : 0;
+            fin.addend_group = addend_group;
+            if (ntt_forward(c, u.as<u64>(), P * targets, c->d_ids, targets, 1, &pro, 3, &fin))
+            {
+                return;
+            }
             KernelTimer kt1(c, "k_divround_finish", 1);
             k_divround_finish<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
                 reinterpret_cast<const ulonglong2 *>(in), u.as<ulonglong2>(),
