@@ -30,6 +30,66 @@ namespace moai
     } // namespace
 
     // ------------------------------------------------------------------------------------ GELU
+    // Fast mode (grouped relinearisation keys registered, i.e. the caller accepts results that match the reference by
+    // tolerance): the SAME degree-24 polynomial g(u), u = 0.1 x, evaluated baby-step / giant-step
+    //     g = [A0 + u^4 A1 + u^8 (A2 + u^4 A3)] + u^16 [A4 + u^4 A5 + u^8 c24],   A_a = c_4a + c_4a+1 u + c_4a+2 u^2 + c_4a+3 u^3,
+    // with every plaintext constant encoded at the scale that makes the following rescale land EXACTLY on its target
+    // (like the Chebyshev evaluation of EvalMod): 9 relinearizations instead of the 23 of the reference's
+    // all-powers evaluation (gelu_others.hpp:22-121), one level less.  The result is switched down to the level the
+    // reference's output has, so the callers see no difference.
+    static Ct gelu_bsgs(const Evaluator &ev, const Ct &x, const Keys &keys, const double (&coeff)[25])
+    {
+        const double D = x.scale;
+        const int L0 = x.limbs;
+        MOAI_REQUIRE(L0 >= 8, "gelu needs 7 levels");
+        auto q = [&](int limbs) { return ev.last_prime(limbs); };
+        auto c = [&](int i) { return coeff[24 - i]; }; // coefficient of u^i
+        auto rr = [&](const Ct &a3) { return ev.rescale_to_next(ev.relinearize(a3, keys)); };
+        Ct u = ev.rescale_to_next(ev.multiply_plain(x, ev.encode(0.1, L0, D)));                   // L0-1
+        Ct u2 = rr(ev.square(u));                                                                   // L0-2
+        Ct u3 = rr(ev.multiply(ev.mod_switch_to(u, L0 - 2), u2));                                   // L0-3
+        Ct u4 = rr(ev.square(u2));                                                                  // L0-3
+        Ct u8 = rr(ev.square(u4));                                                                  // L0-4
+        Ct u16 = rr(ev.square(u8));                                                                 // L0-5
+        // A_a evaluated to exactly (limbs, scale): one fused linear combination at limbs + 1, rescale, add the constant
+        auto A = [&](int a, int limbs, double scale) {
+            Ct r = ev.rescale_to_next(ev.lincomb_scalar({ u, u2, u3 }, { c(4 * a + 1), c(4 * a + 2), c(4 * a + 3) }, limbs + 1,
+                                                         scale * q(limbs + 1)));
+            r.scale = scale;
+            return ev.add_plain(r, ev.encode(c(4 * a), limbs, scale));
+        };
+        // scales, backwards from the result R (limbs L0-6, scale D)
+        const double S_B1 = D * q(L0 - 5) / u16.scale;          // u16 * B1 / q(L0-5) = D
+        const double S_N = D * q(L0 - 5) / u8.scale;            // u8 * N / q(L0-5) = D
+        const double S_A1 = D * q(L0 - 5) / u4.scale;           // u4 * A1 / q(L0-5) = D
+        const double S_A5 = S_B1 * q(L0 - 4) / u4.scale;        // u4 * A5 / q(L0-4) = S_B1
+        const double S_A3 = S_N * q(L0 - 4) / u4.scale;         // u4 * A3 / q(L0-4) = S_N
+        const Ct u4a = ev.mod_switch_to(u4, L0 - 4), u4b = ev.mod_switch_to(u4, L0 - 5), u8b = ev.mod_switch_to(u8, L0 - 5);
+        // B1 = A4 + u^4 A5 + c24 u^8          at (L0-5, S_B1)
+        Ct B1 = rr(ev.multiply(u4a, A(5, L0 - 4, S_A5)));
+        B1.scale = S_B1;
+        {
+            Ct t = ev.rescale_to_next(ev.multiply_plain(u8, ev.encode(c(24), L0 - 4, S_B1 * q(L0 - 4) / u8.scale)));
+            t.scale = S_B1;
+            ev.add_inplace(B1, t);
+            ev.add_inplace(B1, A(4, L0 - 5, S_B1));
+        }
+        // N = A2 + u^4 A3                     at (L0-5, S_N)
+        Ct N = rr(ev.multiply(u4a, A(3, L0 - 4, S_A3)));
+        N.scale = S_N;
+        ev.add_inplace(N, A(2, L0 - 5, S_N));
+        // R = A0 + [u^4 A1 + u^8 N + u^16 B1] : three products at the same level and scale, ONE relinearization
+        Ct acc3 = ev.multiply(u4b, A(1, L0 - 5, S_A1));
+        acc3.scale = D * q(L0 - 5);
+        // (the scales agree by construction up to the last bits of the double arithmetic: accumulate on the residues)
+        ew_multiply(ev.c, u8b.d, N.d, acc3.d, acc3.batch, acc3.limbs, true);
+        ew_multiply(ev.c, u16.d, B1.d, acc3.d, acc3.batch, acc3.limbs, true);
+        Ct R = rr(acc3);
+        R.scale = D;
+        ev.add_inplace(R, A(0, L0 - 6, D));
+        return ev.mod_switch_to(R, L0 - 7);
+    }
+
     // gelu_v2: M/source/non_linear_func/gelu_others.hpp:4-154 — degree-24 polynomial in 0.1*x.
     Ct gelu_v2(const Evaluator &ev, const Ct &x, const Keys &keys)
     {
@@ -45,6 +105,14 @@ namespace moai
         {
             coeff[i] *= t;
             t *= inv_s0;
+        }
+        static const bool bsgs_on = [] {
+            const char *e = getenv("MOAI_GELU_BSGS");
+            return !e || atoi(e) != 0;
+        }();
+        if (bsgs_on && !keys.relin_fast.empty())
+        {
+            return gelu_bsgs(ev, x, keys, coeff);
         }
         std::vector<Ct> p(25);
         p[1] = ev.rescale_to_next(ev.multiply_plain(x, ev.encode(s0, x.limbs, x.scale)));
