@@ -43,7 +43,53 @@ namespace moai
         const int L0 = x.limbs;
         MOAI_REQUIRE(L0 >= 8, "gelu needs 7 levels");
         auto q = [&](int limbs) { return ev.last_prime(limbs); };
-        auto c = [&](int i) { return coeff[24 - i]; }; // coefficient of u^i
+        // The reference multiplies every power p_i = u^i (tracked scale s_i) by a constant encoded at s_i, rescales and then
+        // DECLARES the result to be at the input scale (gelu_others.hpp:123-150): term i is off by the factor
+        // f_i = s_i^2 / (q D), a deterministic function of the prime chain (|f_i - 1| ~ 1e-3).  Where the polynomial
+        // cancels heavily (|x| > 9: coefficients ~1e4 against a result of O(1)) that drift dominates the reference's
+        // output, so it is part of what "the reference's decrypted output" means: replay the reference's level / scale
+        // bookkeeping and fold f_i into the coefficients.
+        double f[25];
+        {
+            struct LS
+            {
+                int l;
+                double s;
+            };
+            LS p[25];
+            auto sq = [&](LS a) { return LS{ a.l - 1, a.s * a.s / q(a.l) }; };
+            auto mul = [&](LS a, LS b) { return LS{ b.l - 1, a.s * b.s / q(b.l) }; };
+            p[1] = LS{ L0 - 1, D * D / q(L0) };
+            p[2] = sq(p[1]);
+            p[4] = sq(p[2]);
+            p[8] = sq(p[4]);
+            p[16] = sq(p[8]);
+            for (int i = 2; i < 17; i *= 2)
+            {
+                p[i + 1] = mul(p[1], p[i]);
+            }
+            for (int k = 2; k <= 3; k++)
+            {
+                for (int i = 4; i < 17; i *= 2)
+                {
+                    p[i + k] = mul(p[k], p[i]);
+                }
+            }
+            for (int k = 4; k <= 7; k++)
+            {
+                for (int i = 8; i < 17; i *= 2)
+                {
+                    p[i + k] = mul(p[k], p[i]);
+                }
+            }
+            p[24] = mul(p[8], p[16]);
+            f[0] = 1.0;
+            for (int i = 1; i < 25; i++)
+            {
+                f[i] = p[i].s * p[i].s / (q(p[24].l) * D);
+            }
+        }
+        auto c = [&](int i) { return coeff[24 - i] * f[i]; }; // coefficient of u^i as the reference applies it
         auto rr = [&](const Ct &a3) { return ev.rescale_to_next(ev.relinearize(a3, keys)); };
         Ct u = ev.rescale_to_next(ev.multiply_plain(x, ev.encode(0.1, L0, D)));                   // L0-1
         Ct u2 = rr(ev.square(u));                                                                   // L0-2
