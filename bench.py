@@ -436,8 +436,14 @@ def run_layer(args):
     aux = torch.empty_like(x)
     aux.copy_(x)
     # host side of the e2e arm: both activation buffers in pinned memory
-    hx = torch.empty(x.shape, dtype=torch.int64, pin_memory=True)
-    haux = torch.empty(x.shape, dtype=torch.int64, pin_memory=True)
+    pinned = True
+    try:
+        hx = torch.empty(x.shape, dtype=torch.int64, pin_memory=True)
+        haux = torch.empty(x.shape, dtype=torch.int64, pin_memory=True)
+    except RuntimeError:        # 2 x 15.75 GiB of page-locked memory per rank may not be available at 8 ranks
+        pinned = False
+        hx = torch.empty(x.shape, dtype=torch.int64)
+        haux = torch.empty(x.shape, dtype=torch.int64)
     hx.copy_(x)
     haux.copy_(aux)
     boot_chunk = int(os.environ.get("MOAI_BOOT_CHUNK", "32"))
@@ -514,14 +520,17 @@ def run_layer(args):
             hbm_peak, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
         else:
             hbm_peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
-        ta0, ua0 = prof.get("k_ntt_fwd_pass_a", (0.0, 0))
+        ta, ua = prof.get("k_ntt_fwd_pass_a", (0.0, 0))
         tac, uac = prof.get("k_ntt_fwd_pass_a_conv", (0.0, 0))
-        ta, ua = ta0 + tac, ua0 + uac       # pass A, plain and with the base-conversion prologue of the grouped digits
         tb, ub = prof.get("k_ntt_fwd_pass_b", (0.0, 0))
+        tbf, ubf = prof.get("k_ntt_fwd_pass_b_finish", (0.0, 0))
         tf, uf = prof.get("k_ks_passb_mac", (0.0, 0))
         t1, u1 = prof.get("k_ntt_fwd_fused", (0.0, 0))
-        # one forward limb-transform = pass A + pass B (or the single fused kernel); pass A also feeds the fused
-        # key-switch kernel, so the pair is costed per limb-transform: (ms per unit of A) + (ms per unit of B)
+        ta0, ua0 = ta, ua
+        # `roofline` = the forward limb-transform VERDICT r1 names: plain pass A + plain pass B (the single fused kernel
+        # if there were one).  Pass A also feeds other kernels, so the pair is costed per limb-transform:
+        # (ms per unit of A) + (ms per unit of B).  The kernels that carry a transform half PLUS fused work (base
+        # conversion, divide-and-round tail, evk inner product) are listed beside it in `ntt_kernels` on their own bytes.
         units = ub + u1
         pair_ms = (ta / ua * ub if ua else 0.0) + tb + t1
         limb_bytes = (1 << LOG_N) * 8
@@ -555,7 +564,7 @@ def run_layer(args):
                            "boot_chunk": boot_chunk, "evaluation_keys_GiB": round(st["key_gib"], 1)},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "s/input", "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": nbytes},
+                        "d2h_bytes_per_step": nbytes, "host_buffers": "pinned" if pinned else "pageable"},
                 "gpu_launches": int(launches),
                 "roofline": {"kernel": "forward NTT passes: ntt_fwd_pass_a + ntt_fwd_pass_b[_grouped] (one limb-transform = "
                                        "both passes)",
@@ -565,13 +574,21 @@ def run_layer(args):
                              "algorithmic_bytes_per_limb_transform": 2 * limb_bytes,
                              "us_per_limb_transform": pair_ms * 1e3 / units if units else None,
                              "kernel_ms": {"pass_a": ta, "pass_b": tb, "fused": t1, "pass_a_units": int(ua)},
-                             # the four kernels a forward transform is made of, each on its own algorithmic bytes:
+                             # the kernels a forward transform is made of, each on its own algorithmic bytes:
                              # pass A / pass B read and write one limb (1 MiB); the conversion variant of pass A writes one
-                             # limb and reads its source digits from the L2 (0.5 MiB counted); the fused pass-B + key inner
-                             # product reads one limb of pass-A output per unit (0.5 MiB; the evk tiles are shared by the batch)
+                             # limb and reads its source digits from the L2 (0.5 MiB counted); pass B with the
+                             # divide-and-round tail reads two limbs and writes one (1.5 MiB; 2 with an addend); the fused
+                             # pass-B + key inner product reads one limb of pass-A output per unit (0.5 MiB; evk tiles shared)
                              "ntt_kernels": {"pass_a": krow(ta0, ua0, 2 * limb_bytes), "pass_a_conv": krow(tac, uac, limb_bytes),
-                                             "pass_b": krow(tb, ub, 2 * limb_bytes), "ks_passb_mac": krow(tf, uf, limb_bytes)},
-                             "kernel_share_of_step": (ta + tb + t1 + tf) / sum(dev_ms) if dev_ms else None,
+                                             "pass_b": krow(tb, ub, 2 * limb_bytes),
+                                             "pass_b_finish": krow(tbf, ubf, 3 * limb_bytes),
+                                             "ks_passb_mac": krow(tf, uf, limb_bytes)},
+                             "bound_note": "pass A / pass B stream one limb in and out and sit at 0.55-0.60 of the HBM roof "
+                                           "each on their own bytes (two passes: 0.29 on the transform's algorithmic MiB); the "
+                                           "dominant kernel by time, pass_a_conv (base conversion of the grouped digits fused "
+                                           "into pass A), is FP64-pipe-bound: 63-66 % of the FP64 issue rate, DRAM 12 % "
+                                           "(profiles/ncu_r2_grouped_ks_kernels.csv)",
+                             "kernel_share_of_step": (ta + tac + tb + tbf + t1 + tf) / sum(dev_ms) if dev_ms else None,
                              "note": "timed live with CUDA events around every launch on the launching stream; `achieved` = "
                                      "algorithmic bytes (1 MiB per limb-transform, SURVEY 8(d)) / time; `traffic` = DRAM bytes per "
                                      "limb-transform from the ncu capture under profiles/"},

@@ -1337,23 +1337,28 @@ namespace moai
             }
             if (do_b)
             {
-                KernelTimer kt(c, "k_ntt_fwd_pass_b", a.count);
                 // polynomials sharing a prime: count / period of them per limb slot
                 const long long seq_len = a.count / a.period;
                 static const bool grouped_on = [] {
                     const char *e = getenv("MOAI_NTT_GROUPED");
                     return !e || atoi(e) != 0;
                 }();
-                if (grouped_on && !a.grp_size && a.count % ((long long)a.period * a.div) == 0 && seq_len >= 4 &&
-                    a.period <= 65535)
+                const bool grouped = grouped_on && !a.grp_size && a.count % ((long long)a.period * a.div) == 0 &&
+                                     seq_len >= 4 && a.period <= 65535;
+                if (!grouped)
                 {
-                    fin_applied = a.fin.out != nullptr;
+                    a.fin = FinishEpi();
+                }
+                fin_applied = a.fin.out != nullptr;
+                // (with the divide-and-round tail as its epilogue the kernel moves 1.5-2 MiB per unit, not 1: own timer)
+                KernelTimer kt(c, fin_applied ? "k_ntt_fwd_pass_b_finish" : "k_ntt_fwd_pass_b", a.count);
+                if (grouped)
+                {
                     dim3 grid((unsigned)((seq_len + GS - 1) / GS), (unsigned)((1 << LOGR) / FR), (unsigned)a.period);
                     ntt_fwd_pass_b_grouped<<<grid, FT, GROUPED_SMEM, s>>>(a, seq_len);
                 }
                 else
                 {
-                    a.fin = FinishEpi();
                     const long long ctas_b = a.count * ((1 << LOGR) / ROWS);
                     ntt_fwd_pass_b<<<(unsigned)ctas_b, ROWS * 16, 0, s>>>(a);
                 }

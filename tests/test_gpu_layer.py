@@ -3,8 +3,11 @@
 tokens) with the repo's exact 36-prime chain shape.  These stages contain bootstrapping, so parity
 is by TOLERANCE against a float64 model that applies the same approximations the reference uses
 (exp = (1 + x/128)^128, Goldschmidt inverse, Newton/Goldschmidt inverse square root, degree-24
-GELU polynomial).  Stated tolerances: attention head 3e-2 max-abs, encoder layer 0.15 max-abs on
-LayerNorm-normalised outputs (O(1) values); the reference prints its own layer outputs to 1e-3."""
+GELU polynomial).  Stated tolerances: attention head 5e-3 max-abs (measured 6.5e-4), encoder layer 0.15 max-abs on
+LayerNorm-normalised outputs (O(1) values; measured 0.124 = the reference's own approximation error on these inputs).
+The two fast key modes — "fast" (pre-permuted SEAL digits) and "grouped" (what bench.py times) — are additionally
+compared with the SEAL-exact run on the same inputs and secret key: 1e-5 (attention) and 1e-4 (whole layer, four
+bootstrapping rounds; measured 6e-6)."""
 import numpy as np
 import pytest
 
@@ -16,11 +19,16 @@ NUM_BATCH = 16          # slots / 128 at N = 4096
 TOK = 5                 # valid tokens per input (the reference run uses 5)
 
 
-@pytest.fixture(scope="module", params=["exact", "fast"])
+RESULTS = {}            # decrypted outputs per (test, key mode): the fast modes are compared with the SEAL-exact run
+
+
+@pytest.fixture(scope="module", params=["exact", "fast", "grouped"])
 def env(pkg, request):
     """exact: SEAL-layout keys (the bootstrapping steps + the driver's powers of two, NAF fallback for
     the rest) -> every key switch is SEAL's.  fast: hoisted rotations with pre-permuted keys for the
-    exact steps the pipeline takes, truncated to the level they are used at."""
+    exact steps the pipeline takes, truncated to the level they are used at.  grouped: what
+    bench.py times — grouped-digit keys, lazy mod-down, single-digit first CoeffToSlot stage (hoisting mode 2), GELU by
+    baby-step / giant-step evaluation."""
     from oracle import Oracle
     o = Oracle(12, BITS)
     be = pkg.Backend(12, o.q)
@@ -38,6 +46,34 @@ def env(pkg, request):
             steps |= {1 << k, (o.n // 2) - (1 << k)}
         gal = dict(gen(i, st) for i, st in enumerate(sorted(steps) + [0]))
         keys = be.make_keys(relin=relin, galois=gal)
+    elif request.param == "grouped":
+        boot.set_hoisting(2)
+        fast, grouped, single = {}, {}, {}
+
+        def add(i, st, level):
+            e, k = gen(i, st)
+            if level == 0:
+                single[e] = be.key_prepare_single(k, e)
+                return
+            g = be.key_prepare_grouped(k, e, level)
+            if g is None:
+                fast.setdefault(e, []).append(be.key_prepare(k, e, max_limbs=level))
+            else:
+                grouped.setdefault(e, []).append(g)
+
+        i = 0
+        for st, lvs in sorted(boot.required_step_levels().items()):
+            for lv in lvs:
+                add(i, st, lv)
+                i += 1
+        att = pkg.attention_rotation_steps(NUM_BATCH)
+        for tag, level in (("qk", 14), ("sv", 3)):
+            for j, st in enumerate(att[tag]):
+                add(500 + 100 * level + j, st, level)
+        relin4 = relin.reshape(o.kl - 1, 2, o.kl, o.n)
+        grouped[0] = [be.key_prepare_grouped(relin4, 0, lv, k_extra=k, pre_permute=False)
+                      for k, lv in sorted(be.ksg_plan(range(1, o.kl - 1)).items())]
+        keys = be.make_keys(relin=relin, galois_fast=fast, grouped=grouped, single=single)
     else:
         boot.set_hoisting(True)
         fast = {}
@@ -53,7 +89,7 @@ def env(pkg, request):
     mask = np.zeros(o.n // 2, dtype=np.int32)
     for k in range(TOK):
         mask[k * NUM_BATCH:(k + 1) * NUM_BATCH] = 1
-    return o, be, boot, sk, keys, mask
+    return o, be, boot, sk, keys, mask, request.param
 
 
 def pack_encrypt(o, sk, X, limbs, seed):
@@ -100,8 +136,18 @@ def attention_model(X, WQ, WK, WV, bQ, bK, bV, c_shift, iters=16):
     return np.einsum("btu,ubc->tbc", P, V)               # [tok, inp, col]
 
 
+def _versus_exact(name, mode, got, tol):
+    """Fast modes against the SEAL-exact run of the same test (same inputs, same secret key): the only differences are
+    key-switching noise and, for GELU, the evaluation order."""
+    RESULTS[(name, mode)] = got
+    if mode != "exact" and (name, "exact") in RESULTS:
+        d = np.abs(got - RESULTS[(name, "exact")]).max()
+        print("%s: %s vs exact keys, max-abs difference of the decrypted outputs %.3g (tolerance %.0e)" % (name, mode, d, tol))
+        assert d < tol, d
+
+
 def test_single_att_block_matches_float_model(pkg, env):
-    o, be, boot, sk, keys, mask = env
+    o, be, boot, sk, keys, mask, mode = env
     rng = np.random.default_rng(1)
     hidden, col_W = 48, 8                                 # reduced widths; the pipeline is width-agnostic
     X = np.zeros((128, NUM_BATCH, hidden))
@@ -122,8 +168,10 @@ def test_single_att_block_matches_float_model(pkg, env):
     got = decrypt_cols(o, sk, pkg, out, out_scale)
     exp = attention_model(X, WQ, WK, WV, bQ, bK, bV, 7.5)
     err = np.abs(got[:TOK] - exp).max()
-    assert err < 3e-2, err
-    assert np.abs(got[TOK:]).max() < 3e-2                 # padding tokens stay (approximately) zero
+    print("attention head (%s keys): max-abs vs the float64 model %.3g" % (mode, err))
+    assert err < 5e-3, err                                # measured 6.5e-4 in all three key modes
+    assert np.abs(got[TOK:]).max() < 5e-3                 # padding tokens stay (approximately) zero
+    _versus_exact("att", mode, got, 1e-5)                 # measured 9.4e-7 (fast), 6.3e-7 (grouped)
 
 
 def layer_model(X, w, iters=16):
@@ -156,7 +204,7 @@ def layer_model(X, w, iters=16):
 
 def test_encoder_layer_end_to_end(pkg, env):
     """One full encoder layer (4 x 768 bootstrappings, 12 heads) at N = 4096, hidden = 768."""
-    o, be, boot, sk, keys, mask = env
+    o, be, boot, sk, keys, mask, mode = env
     rng = np.random.default_rng(2)
     hidden, heads, hd, inter = 768, 12, 64, 3072
     X = np.zeros((128, NUM_BATCH, hidden))
@@ -186,5 +234,10 @@ def test_encoder_layer_end_to_end(pkg, env):
     got = decrypt_cols(o, sk, pkg, out, out_scale)
     exp = layer_model(X, w)
     err = np.abs(got[:TOK] - exp).max()
+    print("encoder layer (%s keys): max-abs vs the float64 model %.3g on O(1) outputs" % (mode, err))
     assert np.isfinite(got).all()
+    # 0.124 in all three key modes: the error of the reference's OWN approximations (degree-24 GELU, Newton inverse square
+    # root of LayerNorm, Goldschmidt softmax) against exact float64 functions on these inputs, not of the arithmetic —
+    # the arithmetic is what the comparison with the SEAL-exact run below isolates
     assert err < 0.15, err
+    _versus_exact("layer", mode, got, 1e-4)               # measured 6.2e-6 (fast), 5.9e-6 (grouped)
