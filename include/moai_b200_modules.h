@@ -64,6 +64,16 @@ int32_t moai_keys_add_galois(moai_keys *keys, uint32_t galois_elt, const uint64_
 int32_t moai_key_prepare(moai_context *ctx, const uint64_t *ksk_in, uint32_t galois_elt, int32_t max_limbs,
                          int32_t pre_permute, uint64_t *ksk_out);
 int32_t moai_keys_add_galois_fast(moai_keys *keys, uint32_t galois_elt, const uint64_t *ksk_pre, int32_t key_limbs);
+/* Seeded components.  A stock client ships the uniform half `a` of every key-switching-key digit
+ * and of a symmetric ciphertext as a 64-byte seed (Serializable<T>::save; S/keygenerator.cpp:164-232,
+ * S/util/rlwe.cpp:328-368); SEAL's loader regenerates it with sample_poly_uniform(Blake2xbPRNG(seed))
+ * (S/util/rlwe.cpp:137-166, S/randomgen.cpp:176-211).  moai_expand_seeds does that on the device, bit for bit:
+ * seeds = count x 8 uint64 (HOST memory, prng_seed_type), out[i] = device [limbs][N] residues modulo the first `limbs`
+ * primes of the key-level list, consecutive polynomials out_stride_words apart (so the `a` halves of all digits of a
+ * key can be written straight into its [digits][2][key_limbs][N] buffer). */
+int32_t moai_expand_seeds(moai_context *ctx, const uint64_t *seeds, int64_t count, int32_t limbs, uint64_t *out,
+                          int64_t out_stride_words);
+
 /* Grouped-digit keys (csrc/ksgroup.hpp): the fast-mode replacement of SEAL's one-digit-per-prime key switch
  * (S/evaluator.cpp:2724-3021, l (l + 1) forward NTTs at l limbs).  K_G = sum_{J in G} K_J of a stock SEAL key is a
  * hybrid key-switching key for the special modulus P' = p * (the k_extra top data primes, unused by a ciphertext at

@@ -430,6 +430,15 @@ class Backend:
         self._chk(self.lib.moai_ksg_key_shape(self.h, C.c_int32(k_extra), C.c_int32(max_limbs), C.byref(d), C.byref(kl)))
         return d.value, kl.value
 
+    def expand_seeds(self, seeds, limbs):
+        """seeds: [count, 8] uint64 (numpy) -> device [count, limbs, n]: SEAL's sample_poly_uniform(Blake2xbPRNG(seed))
+        regenerated on the device (the uniform half of a seeded key digit / ciphertext)."""
+        s = np.ascontiguousarray(seeds, dtype=np.uint64).reshape(-1, 8)
+        out = self.empty(s.shape[0], limbs, self.n)
+        self._chk(self.lib.moai_expand_seeds(self.h, s.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_int64(s.shape[0]),
+                                             C.c_int32(limbs), _ptr(out), C.c_int64(limbs * self.n)))
+        return out
+
     def ksg_plan(self, levels):
         """Grouped-key variants that give every level in `levels` its preferred digit layout: dict k_extra ->
         max_limbs (one key per distinct k, truncated to the highest level that wants it; levels that prefer SEAL's

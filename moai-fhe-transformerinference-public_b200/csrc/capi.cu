@@ -596,6 +596,18 @@ extern "C"
         API_END
     }
 
+    // ---- seeded components (csrc/seedexpand.cu) ---------------------------------------------------
+    int32_t moai_expand_seeds(moai_context *ctx, const uint64_t *seeds, int64_t count, int32_t limbs, uint64_t *out,
+                              int64_t out_stride_words)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(seeds && out && count >= 1, "null argument");
+        MOAI_REQUIRE(out_stride_words >= (int64_t)limbs * (int64_t)c->n, "output polynomials overlap");
+        expand_seeds(c, CU(seeds), count, limbs, U(out), out_stride_words);
+        API_END
+    }
+
     // ---- grouped-digit keys (csrc/ksgroup.hpp) ----------------------------------------------------
     int32_t moai_ksg_best_extra(moai_context *ctx, int32_t limbs, int32_t *k_extra)
     {

@@ -88,6 +88,8 @@ namespace moai
     void rotate_hoisted_multi(Context *c, const u64 *ct, const u64 *ext, long long batch, int limbs, int n_rot,
                               const uint32_t *elts, const u64 *const *ksk_pre, const int *key_kl, u64 *const *outs);
     void key_prepare(Context *c, const u64 *in, uint32_t elt, int max_limbs, bool pre_permute, u64 *out);
+    // seeded key / ciphertext components regenerated on the device (csrc/seedexpand.cu); h_seeds: count x 8 words (host)
+    void expand_seeds(Context *c, const u64 *h_seeds, long long count, int limbs, u64 *d_out, long long out_stride);
 
     // fused module: out[C][2][limbs-1][n] = rescale(sum_j X[j] * encode_scalar(W[j][i]))
     void ct_pt_matmul_scalar(Context *c, const u64 *X, const double *h_W, int K, int C, int limbs, double scale,

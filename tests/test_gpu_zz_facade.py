@@ -241,3 +241,27 @@ def test_reference_program_seal_ckks_test_runs_unmodified():
     assert "Exact scale in PI*x^3: 1099512659965.7514648438" in text     # SEAL's own printed values
     assert "Exact scale in  0.4*x: 1099511775231.0197753906" in text
     assert "Modulus chain index for x3_encrypted: 0" in text and "coeff_modulus size: 200 (60 + 40 + 40 + 60) bits" in text
+
+
+@pytest.mark.parametrize("log_n,bits", [(12, [40, 30, 30, 40]), (16, [51] + [46] * 20 + [51] * 14 + [58])])
+def test_seed_expansion_on_device(pkg, log_n, bits):
+    """moai_expand_seeds (csrc/seedexpand.cu): the uniform half of a seeded key digit / ciphertext regenerated on the
+    device — BLAKE2Xb buffers in parallel, rejected words replaced in scan order — equals SEAL's
+    sample_poly_uniform(Blake2xbPRNG(seed)) bit for bit (S/util/rlwe.cpp:137-166, S/randomgen.cpp:176-211; here through the
+    facade's host restatement, which tests/test_facade.py pins to the real library), including the repo's chain with its
+    58-bit special prime (~1000 rejections per polynomial)."""
+    import facade_harness as facade
+    if not facade.available(mock=False):
+        pytest.skip("oracle/_ref/libfacade_driver*.so not built (needs /root/reference at build time)")
+    d = facade.FacadeDriver(log_n, bits=bits, mock=False)
+    be = pkg.Backend(log_n, d.primes)
+    rng = np.random.default_rng(5)
+    seeds = rng.integers(0, 2 ** 63, size=(3, 8), dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+    got = pkg.to_host(be.expand_seeds(seeds, d.kl)).reshape(3, -1)
+    for i in range(3):
+        exp = d.sample_uniform(seeds[i])
+        assert (got[i] == exp).all(), (i, int((got[i] != exp).sum()))
+    # fewer limbs than the key level (a ciphertext's c1 at its own level)
+    got2 = pkg.to_host(be.expand_seeds(seeds[:1], 2)).reshape(-1)
+    assert got2.shape[0] == 2 * (1 << log_n)
+    be.close()
