@@ -732,15 +732,52 @@ namespace sealapi
         // One serialized Ciphertext / PublicKey (S/ciphertext.cpp:190-330) -> host residues [size][limbs][N].
         // A seeded object stores c0 and a PRNG seed; c1 is expanded at the object's own level
         // (Ciphertext::expand_seed, S/ciphertext.cpp:118-136).
+        // Seeded key digits are expanded ON THE DEVICE (moai_expand_seeds, csrc/seedexpand.cu) when the bound library is
+        // the CUDA backend: the loader then leaves c1 zero, hands the seeds to the uploader, and the uploader expands
+        // them straight into the key's device buffer.  (The CPU test double of the C ABI, moai_version() < 0, and
+        // MOAI_FACADE_HOST_SEEDS=1 keep SEAL's host-side expansion.)
+        inline bool device_seed_expansion()
+        {
+            static const bool on = [] {
+                const char *e = std::getenv("MOAI_FACADE_HOST_SEEDS");
+                return moai_version() >= 100 && !(e && e[0] == '1');
+            }();
+            return on;
+        }
+        struct PendingSeeds
+        {
+            std::vector<std::uint64_t> seeds;  // 8 words per seeded digit
+            std::vector<std::size_t> digits;   // which digits of the key they belong to
+            // dev: the key's device buffer [digits][2][kl][N]
+            void expand(const ContextPtr &c, std::uint64_t *dev) const
+            {
+                const std::size_t kl = c->key_limbs(), per = 2 * kl * c->n;
+                Lock lk(c->mu);
+                std::size_t i = 0;
+                while (i < digits.size())
+                {
+                    std::size_t run = 1; // consecutive digits go in one call
+                    while (i + run < digits.size() && digits[i + run] == digits[i] + run)
+                    {
+                        run++;
+                    }
+                    chk(moai_expand_seeds(c->h, seeds.data() + 8 * i, std::int64_t(run), std::int32_t(kl),
+                                          dev + digits[i] * per + kl * c->n, std::int64_t(per)));
+                    i += run;
+                }
+            }
+        };
+
         struct LoadedCiphertext
         {
             parms_id_type parms_id;
-            bool is_ntt_form = true, was_seeded = false;
+            bool is_ntt_form = true, was_seeded = false, seed_deferred = false;
+            prng_seed_type seed{};
             std::size_t size = 0, limbs = 0;
             double scale = 1.0;
             std::vector<std::uint64_t> data;
         };
-        inline LoadedCiphertext load_ciphertext_stream(const ContextImpl &c, std::istream &in)
+        inline LoadedCiphertext load_ciphertext_stream(const ContextImpl &c, std::istream &in, bool defer_seed = false)
         {
             LoadedCiphertext r;
             (void)get_header(in);
@@ -780,9 +817,17 @@ namespace sealapi
                 {
                     throw std::runtime_error("I/O error");
                 }
-                std::vector<std::uint64_t> primes(c.primes.begin(), c.primes.begin() + r.limbs);
-                util::sample_poly_uniform(UniformRandomGeneratorInfo(type, seed).make_prng(), primes, c.n,
-                                          r.data.data() + total / 2);
+                if (defer_seed && type == prng_type::blake2xb && device_seed_expansion())
+                {
+                    r.seed = seed; // c1 stays zero: the uploader expands the seed on the device
+                    r.seed_deferred = true;
+                }
+                else
+                {
+                    std::vector<std::uint64_t> primes(c.primes.begin(), c.primes.begin() + r.limbs);
+                    util::sample_poly_uniform(UniformRandomGeneratorInfo(type, seed).make_prng(), primes, c.n,
+                                              r.data.data() + total / 2);
+                }
                 r.was_seeded = true;
             }
             return r;
@@ -1278,6 +1323,12 @@ namespace sealapi
                 set_ = std::make_shared<detail::KeySet>(ctx.impl());
             }
         }
+        // seeds of the key being loaded whose uniform halves are still to be expanded on the device (load_entries)
+        static detail::PendingSeeds &pending_ref()
+        {
+            static thread_local detail::PendingSeeds p;
+            return p;
+        }
         // KSwitchKeys::load_members (S/kswitchkeys.cpp:86-150): parms_id, then a vector (by key index) of vectors
         // (one PublicKey per decomposition digit).  Calls `sink(index, host [digits][2][kl][N])` per present key.
         // Seeded entries — what `keygen.create_relin_keys()` / `create_galois_keys(...)` return for shipping —
@@ -1308,21 +1359,37 @@ namespace sealapi
                     throw std::logic_error("KSwitchKeys data is invalid");
                 }
                 std::vector<std::uint64_t> key(std::size_t(dim2) * per);
+                pending_ref() = detail::PendingSeeds();
                 for (std::uint64_t j = 0; j < dim2; j++)
                 {
-                    detail::LoadedCiphertext r = detail::load_ciphertext_stream(c, stream);
+                    detail::LoadedCiphertext r = detail::load_ciphertext_stream(c, stream, /*defer_seed=*/true);
                     if (r.size != 2 || r.limbs != kl || !r.is_ntt_form)
                     {
                         throw std::logic_error("KSwitchKeys data is invalid");
                     }
                     seeded += r.was_seeded;
+                    if (r.seed_deferred)
+                    {
+                        pending_ref().seeds.insert(pending_ref().seeds.end(), r.seed.begin(), r.seed.end());
+                        pending_ref().digits.push_back(std::size_t(j));
+                    }
                     std::copy(r.data.begin(), r.data.end(), key.begin() + std::size_t(j) * per);
                 }
-                sink(static_cast<std::size_t>(index), key.data());
+                sink(static_cast<std::size_t>(index), key.data()); // the uploaders below consume pending_ref()
+                pending_ref() = detail::PendingSeeds();
             }
             return seeded;
         }
         std::shared_ptr<detail::KeySet> set_;
+        void expand_pending(std::uint64_t *dev)
+        {
+            if (!pending_ref().digits.empty())
+            {
+                pending_ref().expand(set_->c, dev);
+                detail::Lock lk(set_->c->mu);
+                detail::chk(moai_synchronize(set_->c->h));
+            }
+        }
     };
 
     class RelinKeys : public KSwitchKeys
@@ -1333,6 +1400,7 @@ namespace sealapi
         {
             need(ctx);
             set_->relin = set_->store(host);
+            expand_pending(const_cast<std::uint64_t *>(set_->relin));
             detail::Lock lk(set_->c->mu);
             detail::chk(moai_keys_set_relin(set_->h, set_->relin));
         }
@@ -1366,6 +1434,7 @@ namespace sealapi
         {
             need(ctx);
             const std::uint64_t *p = set_->store(host);
+            expand_pending(const_cast<std::uint64_t *>(p));
             set_->galois[galois_elt] = p;
             detail::Lock lk(set_->c->mu);
             detail::chk(moai_keys_add_galois(set_->h, galois_elt, p));
@@ -1382,8 +1451,12 @@ namespace sealapi
             full.ensure(c, words);
             set_->blocks.emplace_back(new detail::DeviceBlock());
             set_->blocks.back()->ensure(c, std::size_t(max_limbs) * 2 * (max_limbs + 1) * c->n);
+            {
+                detail::Lock lk0(c->mu);
+                detail::chk(moai_memcpy_h2d(c->h, full.ptr(), host, words * sizeof(std::uint64_t)));
+            }
+            expand_pending(full.ptr());
             detail::Lock lk(c->mu);
-            detail::chk(moai_memcpy_h2d(c->h, full.ptr(), host, words * sizeof(std::uint64_t)));
             detail::chk(moai_key_prepare(c->h, full.ptr(), galois_elt, max_limbs, 1, set_->blocks.back()->ptr()));
             detail::chk(moai_keys_add_galois_fast(set_->h, galois_elt, set_->blocks.back()->ptr(), max_limbs + 1));
             detail::chk(moai_synchronize(c->h));

@@ -416,6 +416,11 @@ GPU_ONLY_MODULE(moai_single_att_block, moai_context *c, moai_keys *k, moai_boots
                 int32_t li, uint64_t *o, int32_t *ol, double *os)
 
 /* ---- not needed by the CPU host-logic tests ---- */
+int32_t moai_expand_seeds(moai_context *c, const uint64_t *s, int64_t n, int32_t l, uint64_t *o, int64_t st)
+{
+    (void)c; (void)s; (void)n; (void)l; (void)o; (void)st;
+    UNSUPPORTED("moai_expand_seeds"); /* the facade expands seeds on the host when bound to the test double */
+}
 int32_t moai_key_prepare(moai_context *c, const uint64_t *a, uint32_t e, int32_t m, int32_t p, uint64_t *o)
 {
     (void)c; (void)a; (void)e; (void)m; (void)p; (void)o;

@@ -254,7 +254,7 @@ def test_seed_expansion_on_device(pkg, log_n, bits):
     if not facade.available(mock=False):
         pytest.skip("oracle/_ref/libfacade_driver*.so not built (needs /root/reference at build time)")
     d = facade.FacadeDriver(log_n, bits=bits, mock=False)
-    be = pkg.Backend(log_n, d.primes)
+    be = pkg.Backend(log_n, [int(v) for v in d.q])
     rng = np.random.default_rng(5)
     seeds = rng.integers(0, 2 ** 63, size=(3, 8), dtype=np.uint64) * np.uint64(2) + np.uint64(1)
     got = pkg.to_host(be.expand_seeds(seeds, d.kl)).reshape(3, -1)
