@@ -369,3 +369,59 @@ def test_c1_selfoutput_linear_with_reference_mask(pkg, env):
     print("C1 masked matmul: max-abs %.3g (max |XW| %.3g), masked-out slots %.3g" % (err, np.abs(exp).max(), np.abs(got[TOK:]).max()))
     assert err < 1e-4 * max(1.0, np.abs(exp).max())
     assert np.abs(got[TOK:]).max() < 1e-6                 # other inputs' slots stay zero
+
+
+GOLDEN_REST = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "layers_1_11_activations.npz")
+# measured max errors of this repo's modules against the reference's plaintext CSVs, layer by layer (grouped keys;
+# profiles/fullsize_golden_r2_layers.log), and the bound asserted for each stage.  The bounds are those of layer 0:
+# what they measure is the REFERENCE'S approximation (Newton inverse square root, degree-24 GELU polynomial), which this
+# repo reproduces operation for operation (bit for bit in exact mode, tests/test_gpu_modules.py).
+LN1_TOL_ABS, GELU_TOL_ABS, LN2_TOL_REL = 2e-3, 0.05, 0.1
+
+
+@pytest.mark.parametrize("layer", list(range(1, 12)))
+def test_layers_1_to_11_golden(pkg, env, request, layer):
+    """The LayerNorm / GELU / LayerNorm2 stages of encoder layers 1..11 on the reference's own activations
+    (tests/golden/layers_1_11_activations.npz from /root/reference/data/layer_k/**/allresults/*.csv), against the CSV
+    outputs: LayerNorm 2e-3 max-abs (measured 2.6e-5 ... 1.6e-3), gelu_v2 0.05 max-abs (measured 0.030 ... 0.037) on the
+    ciphertexts — columns: the 5 tokens of a feature share one ciphertext — all of whose inputs lie inside the
+    polynomial's domain |x| <= 9, LayerNorm2 0.1 relative (|err| / max(1, |expected|); measured 0.03 ... 0.08) — the same
+    bounds as layer 0, where the reference's own decrypted outputs show that these distances are its approximations'
+    and not the arithmetic's.  Where the reference's algorithm leaves its own domain the gate only reports:
+    * gelu_v2 columns with an input beyond |x| = 9 (up to |x| = 123 in layer 10): the degree-24 polynomial in 0.1 x
+      reaches 1e18 and wraps around the ciphertext modulus, which destroys every slot of that ciphertext — in the
+      reference's encrypted run exactly as here;
+    * LayerNorm2 of layers 10 and 11 (residual sums up to 955 / variance beyond the initial guess of its Newton inverse
+      square root, layernorm.hpp:18-24): measured 1.95 and 0.126 relative.
+    Run in the benchmarked key mode only."""
+    if "grouped" not in request.node.name:
+        pytest.skip("layers 1..11 are gated in the benchmarked key mode")
+    be, keys = env["be"], env["keys"]
+    g = np.load(GOLDEN_REST)
+    p = "l%d_" % layer
+    get = lambda n: g[p + n].astype(np.float64)
+    res = {}
+    for name, variant in (("ln1", 1), ("ln2", 2)):
+        x = encrypt_cols(env, pack_rows(get(name + "_in")), 21)
+        out, osc = be.layernorm(keys, x, SCALE, get(name + "_gamma"), get(name + "_beta"), env["mask"], variant=variant)
+        del x
+        got = slot_values(env, out, osc, VALID).real.T
+        del out
+        exp = get(name + "_out")
+        res[name] = (np.abs(got - exp).max(), (np.abs(got - exp) / np.maximum(1.0, np.abs(exp))).max())
+    V = pack_rows(get("gelu_in"))
+    got = np.zeros((TOK, 3072))
+    for c0 in range(0, 3072, 512):
+        x = encrypt_cols(env, V[c0:c0 + 512], 9)
+        out, osc = be.gelu_v2(keys, x, SCALE)
+        del x
+        got[:, c0:c0 + 512] = slot_values(env, out, osc, VALID).real.T
+        del out
+    cols = (np.abs(get("gelu_in")) <= 9.0).all(axis=0)     # ciphertexts whose five inputs all are inside the domain
+    e_gelu = np.abs(got - get("gelu_out"))[:, cols].max()
+    print("layer %d golden: ln1 max-abs %.3g (rel %.3g); gelu_v2 on the %d of 3072 in-domain columns %.3g; ln2 max-abs %.3g, "
+          "rel %.3g" % (layer, res["ln1"][0], res["ln1"][1], int(cols.sum()), e_gelu, res["ln2"][0], res["ln2"][1]))
+    assert res["ln1"][0] < LN1_TOL_ABS and e_gelu < GELU_TOL_ABS
+    assert np.isfinite(res["ln2"][1])
+    if layer <= 9:
+        assert res["ln2"][1] < LN2_TOL_REL
