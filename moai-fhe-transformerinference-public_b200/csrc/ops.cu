@@ -838,23 +838,18 @@ namespace moai
         __device__ __forceinline__ void bsgs_ext_fp(const FpField<WIDE> &f, const BsgsExtArgs &a, long long bp, int I,
                                                     long long within, int log_n2, bool data, bool poly0)
         {
-            // the baby steps are taken 8 at a time (8 gathers in flight per thread, 8 x 2 live values), the giants' sums
-            // stay in registers across the groups
-            constexpr int HALF = 8;
-            // the gathers are the long pole (ncu: 17 warps per issue stalled on the scoreboard at 19 % of the DRAM
-            // rate): start every rotation's 16-byte line on its way to the L2 now, 8 demand loads at a time follow
-            for (int j = 0; j < a.n_baby; j++)
-            {
-                if (a.acc[j])
-                {
-                    const unsigned ix = __ldg(a.perm[j] + 2 * within);
-                    const u64 *ptr = a.acc[j] + ((bp * a.rns + I) << (log_n2 + 1)) + (size_t)(ix & ~1u);
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-                }
-            }
+            // Rotation-outer software pipeline.  ncu of the first version (values of 8 rotations fetched, then used):
+            // 17 warps per issue stalled on the scoreboard at 19 % of the DRAM rate — the dependent chain
+            // permutation index -> 16-byte gather -> diagonals was exposed.  Now the gathers run two rotations ahead of
+            // their use (all indices first: they are L2 hits), the diagonals of a rotation are requested before its
+            // value is converted, and the giants' sums stay in registers.
+            const int log_n = log_n2 + 1;
             const long long o = ((bp * a.rns + I) << log_n2) + within;
             const long long pt_off = ((long long)I << log_n2) + within;
             const int red_every = WIDE ? 2 : 8;
+            const u64 qq = f.pi;
+            const bool add_c0 = data && poly0;
+            const ulonglong2 *cp0 = reinterpret_cast<const ulonglong2 *>(a.cP + (((bp & ~1ll) * a.n_data + I) << log_n));
             double sx[GM], sy[GM];
 #pragma unroll
             for (int g = 0; g < GM; g++)
@@ -868,41 +863,84 @@ namespace moai
                     sy[g] = f.red(f.in_outer(prev.y));
                 }
             }
-            for (int j0 = 0; j0 < a.n_baby; j0 += HALF)
-            {
-                double rx[HALF], ry[HALF];
+            // all permutation indices up front (L2 hits), parked in shared memory: the rotation loop below is NOT
+            // unrolled (registers), so they are indexed dynamically
+            __shared__ unsigned s_ix[BSGS_MAX_BABY][EW_THREADS];
+            unsigned(*ix)[EW_THREADS] = s_ix;
+            const int tx = threadIdx.x;
 #pragma unroll
-                for (int j = 0; j < HALF; j++)
+            for (int j = 0; j < BSGS_MAX_BABY; j++)
+            {
+                ix[j][tx] = (j < a.n_baby && a.acc[j]) ? __ldg(a.perm[j] + 2 * within) : 0u;
+            }
+            // raw operands of rotation j: the gathered pair of acc_j (and of P' c0), or P' * this polynomial for the identity
+            auto issue = [&](int j, ulonglong2 &w, ulonglong2 &z) {
+                w = make_ulonglong2(0, 0);
+                z = make_ulonglong2(0, 0);
+                if (j >= a.n_baby)
                 {
-                    if (j0 + j < a.n_baby)
+                    return;
+                }
+                if (a.acc[j])
+                {
+                    const long long at = (long long)(ix[j][tx] >> 1);
+                    w = reinterpret_cast<const ulonglong2 *>(a.acc[j] + ((bp * a.rns + I) << log_n))[at];
+                    if (add_c0)
                     {
-                        const ulonglong2 v = bsgs_ext_value(a, j0 + j, bp, I, within, log_n2 + 1, data, poly0, f.pi);
-                        rx[j] = f.red(f.in_outer(v.x)); // centred: |r| <= p/2 + 1
-                        ry[j] = f.red(f.in_outer(v.y));
+                        z = cp0[at];
                     }
                 }
+                else if (data)
+                {
+                    w = reinterpret_cast<const ulonglong2 *>(a.cP + ((bp * a.n_data + I) << log_n))[within];
+                }
+            };
+            auto step = [&](int j, ulonglong2 &w, ulonglong2 &z) {
+                // diagonals of this rotation first (independent loads), then the value
+                ulonglong2 pw[GM];
 #pragma unroll
                 for (int g = 0; g < GM; g++)
                 {
-                    if (g < a.n_giant)
+                    pw[g] = make_ulonglong2(0, 0);
+                    if (g < a.n_giant && a.pt[g][j])
                     {
-#pragma unroll
-                        for (int j = 0; j < HALF; j++)
-                        {
-                            if (j0 + j < a.n_baby && a.pt[g][j0 + j])
-                            {
-                                const ulonglong2 w = __ldg(reinterpret_cast<const ulonglong2 *>(a.pt[g][j0 + j]) + pt_off);
-                                sx[g] = __dadd_rn(sx[g], f.mul_lazy(f.in_outer(w.x), rx[j]));
-                                sy[g] = __dadd_rn(sy[g], f.mul_lazy(f.in_outer(w.y), ry[j]));
-                                // at most red_every terms since the last reduction (absent diagonals only make it earlier)
-                                if ((j + 1) % red_every == 0)
-                                {
-                                    sx[g] = f.red(sx[g]);
-                                    sy[g] = f.red(sy[g]);
-                                }
-                            }
-                        }
+                        pw[g] = __ldg(reinterpret_cast<const ulonglong2 *>(a.pt[g][j]) + pt_off);
                     }
+                }
+                const bool swap = a.acc[j] && (ix[j][tx] & 1u);
+                const u64 vx = addmod(swap ? w.y : w.x, swap ? z.y : z.x, qq);
+                const u64 vy = addmod(swap ? w.x : w.y, swap ? z.x : z.y, qq);
+                const double rx = f.red(f.in_outer(vx)), ry = f.red(f.in_outer(vy)); // centred: |r| <= p/2 + 1
+                issue(j + 2, w, z); // this slot is free again: rotation j + 2 goes on its way
+#pragma unroll
+                for (int g = 0; g < GM; g++)
+                {
+                    if (g < a.n_giant && a.pt[g][j])
+                    {
+                        sx[g] = __dadd_rn(sx[g], f.mul_lazy(f.in_outer(pw[g].x), rx));
+                        sy[g] = __dadd_rn(sy[g], f.mul_lazy(f.in_outer(pw[g].y), ry));
+                    }
+                }
+                if ((j + 1) % red_every == 0) // at most red_every terms per sum since the last reduction
+                {
+#pragma unroll
+                    for (int g = 0; g < GM; g++)
+                    {
+                        sx[g] = f.red(sx[g]);
+                        sy[g] = f.red(sy[g]);
+                    }
+                }
+            };
+            ulonglong2 w0, z0, w1, z1;
+            issue(0, w0, z0);
+            issue(1, w1, z1);
+#pragma unroll 1
+            for (int j = 0; j < a.n_baby; j += 2)
+            {
+                step(j, w0, z0);
+                if (j + 1 < a.n_baby)
+                {
+                    step(j + 1, w1, z1);
                 }
             }
 #pragma unroll
