@@ -718,7 +718,7 @@ namespace sealapi
             {
                 throw std::logic_error("loaded SEALHeader is invalid");
             }
-            if (vmaj != 4 && vmaj != 3)
+            if (vmaj != 4) // version 3 streams have no correction_factor field; the parser below reads the v4 layout only
             {
                 throw std::logic_error("incompatible version");
             }
@@ -805,6 +805,15 @@ namespace sealapi
             if (!in)
             {
                 throw std::runtime_error("I/O error");
+            }
+            // is_data_valid_for (S/valcheck.cpp:201-260): every residue below its prime — the kernels assume canonical
+            // input (x + q - y, FP64 NTT inputs below 2^52), so a malformed stream must be refused here
+            for (std::uint64_t w = 0; w < count; w++)
+            {
+                if (r.data[w] >= c.primes[(w / c.n) % r.limbs])
+                {
+                    throw std::logic_error("ciphertext data is invalid");
+                }
             }
             if (count != total)
             {
@@ -1345,6 +1354,10 @@ namespace sealapi
                 throw std::logic_error("KSwitchKeys data is invalid");
             }
             const auto dim1 = detail::get<std::uint64_t>(stream);
+            if (dim1 > c.n) // at most one key per Galois element (S/galoiskeys.h:52-56: index = (elt - 1) / 2 < N)
+            {
+                throw std::logic_error("KSwitchKeys data is invalid");
+            }
             const std::size_t kl = c.key_limbs(), per = 2 * kl * c.n;
             std::size_t seeded = 0;
             for (std::uint64_t index = 0; index < dim1; index++)

@@ -772,6 +772,25 @@ namespace moai
     void inner_product(Context *c, const u64 *a, const u64 *b, u64 *out3, long long batch, int limbs, int mode)
     {
         MOAI_REQUIRE(batch <= 1024, "inner product batch too large for the lazy accumulator");
+        {
+            // the 128-bit lazy sums hold 2 * batch products of two residues: 2 batch q^2 < 2^128 for the widest prime in use
+            int bits = 0;
+            for (int l = 0; l < limbs; l++)
+            {
+                int b = 0;
+                while ((c->q[l] >> b) != 0)
+                {
+                    b++;
+                }
+                bits = b > bits ? b : bits;
+            }
+            int lb = 0;
+            while ((1ll << lb) < 2 * batch)
+            {
+                lb++;
+            }
+            MOAI_REQUIRE(2 * bits + lb <= 127, "inner product batch too large for primes of this size");
+        }
         const long long total2 = (long long)limbs * (long long)(c->n / 2);
         KernelTimer kt8(c, "k_inner_product", 1);
         k_inner_product<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
