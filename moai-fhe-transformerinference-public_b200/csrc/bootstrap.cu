@@ -941,7 +941,7 @@ namespace moai
         }
         const int lv = target_limbs + 1;
         const double ql = ev.last_prime(lv);
-        Ct tg = ev.mod_switch_to(T.at(g), lv);
+        const Ct &tgh = T.at(g); // read at level lv in place (no mod-switch copy)
         bool q_const = true;
         for (size_t i = 1; i < q.size(); i++)
         {
@@ -950,13 +950,15 @@ namespace moai
         Ct prod2; // a constant quotient needs no ciphertext product
         if (q_const)
         {
+            Ct tg = ev.mod_switch_to(tgh, lv);
             prod2 = ev.rescale_to_next(ev.multiply_plain(tg, ev.encode(q[0], lv, target_scale * ql / tg.scale)));
             prod2.scale = target_scale;
         }
         else
         {
-            Ct qc = eval_cheb(ev, q, lv, target_scale * ql / tg.scale, T, keys);
-            Ct prod3 = ev.multiply(qc, tg);
+            Ct qc = eval_cheb(ev, q, lv, target_scale * ql / tgh.scale, T, keys);
+            MOAI_REQUIRE(qc.limbs == lv && tgh.limbs >= lv, "level bookkeeping of the Chebyshev division");
+            Ct prod3 = ev.multiply_lowered(qc, tgh);
             prod3.scale = target_scale * ql; // qc was evaluated to exactly target_scale * ql / tg.scale
             if (acc3.empty())
             {
@@ -1002,7 +1004,8 @@ namespace moai
         auto t_sum = [&](int a, int b) {                                       // T_{a+b} = 2 T_a T_b - T_{a-b}, a > b
             Ct ta = T.at(a), tb = T.at(b);
             const int lv = std::min(ta.limbs, tb.limbs);
-            Ct p = ev.rescale_to_next(ev.relinearize(ev.multiply(ev.mod_switch_to(ta, lv), ev.mod_switch_to(tb, lv)), keys));
+            (void)lv;
+            Ct p = ev.rescale_to_next(ev.relinearize(ev.multiply_lowered(ta, tb), keys));
             ev.double_inplace(p);
             return ev.sub_reduced_error(p, T.at(a - b));
         };

@@ -281,6 +281,16 @@ namespace moai
         return r;
     }
 
+    Ct Evaluator::multiply_lowered(const Ct &a, const Ct &b) const
+    {
+        EV_REQUIRE(a.size == 2 && b.size == 2, "multiply expects size-2 ciphertexts");
+        EV_REQUIRE(a.batch == b.batch || b.batch == 1, "batch mismatch");
+        const int limbs = std::min(a.limbs, b.limbs);
+        Ct r = alloc(a.batch, 3, limbs, a.scale * b.scale);
+        ew_multiply(c, a.d, b.d, r.d, a.batch, limbs, false, b.batch == 1 && a.batch != 1, a.limbs, b.limbs);
+        return r;
+    }
+
     Ct Evaluator::square(const Ct &a) const
     {
         EV_REQUIRE(a.size == 2, "square expects a size-2 ciphertext");

@@ -176,6 +176,8 @@ namespace moai
         Ct sub_plain(const Ct &a, const Pt &p) const;
         Ct multiply_plain(const Ct &a, const Pt &p) const;
         Ct multiply(const Ct &a, const Ct &b) const;     // size 2 x size 2 -> size 3
+        // multiply(mod_switch_to(a, l), mod_switch_to(b, l)) with l = min(a.limbs, b.limbs), without the copies
+        Ct multiply_lowered(const Ct &a, const Ct &b) const;
         Ct square(const Ct &a) const;
         void multiply_accumulate(Ct &acc3, const Ct &a, const Ct &b) const; // acc3 += a x b (size 3)
         Ct relinearize(const Ct &a3, const Keys &k) const;

@@ -93,7 +93,7 @@ namespace moai
         auto rr = [&](const Ct &a3) { return ev.rescale_to_next(ev.relinearize(a3, keys)); };
         Ct u = ev.rescale_to_next(ev.multiply_plain(x, ev.encode(0.1, L0, D)));                   // L0-1
         Ct u2 = rr(ev.square(u));                                                                   // L0-2
-        Ct u3 = rr(ev.multiply(ev.mod_switch_to(u, L0 - 2), u2));                                   // L0-3
+        Ct u3 = rr(ev.multiply_lowered(u, u2));                                                     // L0-3
         Ct u4 = rr(ev.square(u2));                                                                  // L0-3
         Ct u8 = rr(ev.square(u4));                                                                  // L0-4
         Ct u16 = rr(ev.square(u8));                                                                 // L0-5
@@ -110,9 +110,9 @@ namespace moai
         const double S_A1 = D * q(L0 - 5) / u4.scale;           // u4 * A1 / q(L0-5) = D
         const double S_A5 = S_B1 * q(L0 - 4) / u4.scale;        // u4 * A5 / q(L0-4) = S_B1
         const double S_A3 = S_N * q(L0 - 4) / u4.scale;         // u4 * A3 / q(L0-4) = S_N
-        const Ct u4a = ev.mod_switch_to(u4, L0 - 4), u4b = ev.mod_switch_to(u4, L0 - 5), u8b = ev.mod_switch_to(u8, L0 - 5);
+        // (operands at a higher level are read in place: multiply_lowered / ew_multiply with the operand's own stride)
         // B1 = A4 + u^4 A5 + c24 u^8          at (L0-5, S_B1)
-        Ct B1 = rr(ev.multiply(u4a, A(5, L0 - 4, S_A5)));
+        Ct B1 = rr(ev.multiply_lowered(u4, A(5, L0 - 4, S_A5)));
         B1.scale = S_B1;
         {
             Ct t = ev.rescale_to_next(ev.multiply_plain(u8, ev.encode(c(24), L0 - 4, S_B1 * q(L0 - 4) / u8.scale)));
@@ -121,14 +121,14 @@ namespace moai
             ev.add_inplace(B1, A(4, L0 - 5, S_B1));
         }
         // N = A2 + u^4 A3                     at (L0-5, S_N)
-        Ct N = rr(ev.multiply(u4a, A(3, L0 - 4, S_A3)));
+        Ct N = rr(ev.multiply_lowered(u4, A(3, L0 - 4, S_A3)));
         N.scale = S_N;
         ev.add_inplace(N, A(2, L0 - 5, S_N));
         // R = A0 + [u^4 A1 + u^8 N + u^16 B1] : three products at the same level and scale, ONE relinearization
-        Ct acc3 = ev.multiply(u4b, A(1, L0 - 5, S_A1));
+        Ct acc3 = ev.multiply_lowered(u4, A(1, L0 - 5, S_A1));
         acc3.scale = D * q(L0 - 5);
         // (the scales agree by construction up to the last bits of the double arithmetic: accumulate on the residues)
-        ew_multiply(ev.c, u8b.d, N.d, acc3.d, acc3.batch, acc3.limbs, true);
+        ew_multiply(ev.c, u8.d, N.d, acc3.d, acc3.batch, acc3.limbs, true, false, u8.limbs, N.limbs);
         ew_multiply(ev.c, u16.d, B1.d, acc3.d, acc3.batch, acc3.limbs, true);
         Ct R = rr(acc3);
         R.scale = D;

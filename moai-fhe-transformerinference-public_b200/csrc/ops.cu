@@ -193,8 +193,11 @@ namespace moai
         // (a0, a1) x (b0, b1) -> (a0 b0, a0 b1 + a1 b0, a1 b1); one thread per coefficient pair of a limb
         __global__ void k_multiply(const ulonglong2 *__restrict__ a, const ulonglong2 *__restrict__ b,
                                    ulonglong2 *__restrict__ out, long long total2, int log_n2, int limbs,
-                                   const LimbConst *__restrict__ lcs, int accumulate, int square, int b_bcast)
+                                   const LimbConst *__restrict__ lcs, int accumulate, int square, int b_bcast,
+                                   int a_limbs, int b_limbs)
         {
+            // a_limbs / b_limbs >= limbs: limbs stored per polynomial of a / b (an operand at a higher level is read in
+            // place, which IS its mod-switch: S/evaluator.cpp:1583-1652 drops the trailing limbs)
             long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; // over [batch][limbs][n/2]
             if (i >= total2)
             {
@@ -206,11 +209,12 @@ namespace moai
             const LimbConst lc = lcs[limb];
             const long long within = i & (((long long)1 << log_n2) - 1);
             const long long poly2 = (long long)limbs << log_n2;
-            const long long off_in = bt * 2 * poly2 + ((long long)limb << log_n2) + within;
+            const long long apoly2 = (long long)a_limbs << log_n2, bpoly2 = (long long)b_limbs << log_n2;
+            const long long off_a = bt * 2 * apoly2 + ((long long)limb << log_n2) + within;
             const long long off_out = bt * 3 * poly2 + ((long long)limb << log_n2) + within;
-            ulonglong2 a0 = a[off_in], a1 = a[off_in + poly2];
-            const long long off_b = b_bcast ? ((long long)limb << log_n2) + within : off_in;
-            ulonglong2 b0 = square ? a0 : b[off_b], b1 = square ? a1 : b[off_b + poly2];
+            ulonglong2 a0 = a[off_a], a1 = a[off_a + apoly2];
+            const long long off_b = (b_bcast ? 0 : bt * 2 * bpoly2) + ((long long)limb << log_n2) + within;
+            ulonglong2 b0 = square ? a0 : b[off_b], b1 = square ? a1 : b[off_b + bpoly2];
             ulonglong2 r0, r1, r2;
             r0.x = mulmod(a0.x, b0.x, lc);
             r0.y = mulmod(a0.y, b0.y, lc);
@@ -727,8 +731,11 @@ namespace moai
     }
 
     void ew_multiply(Context *c, const u64 *a, const u64 *b, u64 *out3, long long batch, int limbs, bool accumulate,
-                     bool b_broadcast)
+                     bool b_broadcast, int a_limbs, int b_limbs)
     {
+        a_limbs = a_limbs > 0 ? a_limbs : limbs;
+        b_limbs = b_limbs > 0 ? b_limbs : limbs;
+        MOAI_REQUIRE(a_limbs >= limbs && b_limbs >= limbs, "operand below the product's level");
         const long long total2 = batch * limbs * (long long)(c->n / 2);
         if (!total2)
         {
@@ -738,7 +745,7 @@ namespace moai
         k_multiply<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
             reinterpret_cast<const ulonglong2 *>(a), reinterpret_cast<const ulonglong2 *>(b),
             reinterpret_cast<ulonglong2 *>(out3), total2, c->log_n - 1, limbs, c->d_limb, accumulate ? 1 : 0, 0,
-            b_broadcast ? 1 : 0);
+            b_broadcast ? 1 : 0, a_limbs, b_limbs);
         c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
     }
@@ -753,7 +760,7 @@ namespace moai
         KernelTimer kt6(c, "k_multiply", 1);
         k_multiply<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
             reinterpret_cast<const ulonglong2 *>(a), reinterpret_cast<const ulonglong2 *>(a),
-            reinterpret_cast<ulonglong2 *>(out3), total2, c->log_n - 1, limbs, c->d_limb, 0, 1, 0);
+            reinterpret_cast<ulonglong2 *>(out3), total2, c->log_n - 1, limbs, c->d_limb, 0, 1, 0, limbs, limbs);
         c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
     }

@@ -32,8 +32,10 @@ namespace moai
     // only its first `limbs` are read; h_consts is [n_terms][limbs] (host)
     void ew_lincomb_scalar(Context *c, int n_terms, const u64 *const *in, const int *in_limbs, const u64 *h_consts,
                            u64 *out, long long batch, int polys, int limbs);
+    // a_limbs / b_limbs (0 = limbs): limbs stored per polynomial of the operands; an operand at a higher level is read
+    // in place (its implicit mod-switch)
     void ew_multiply(Context *c, const u64 *a, const u64 *b, u64 *out3, long long batch, int limbs, bool accumulate,
-                     bool b_broadcast = false);
+                     bool b_broadcast = false, int a_limbs = 0, int b_limbs = 0);
     void ew_square(Context *c, const u64 *a, u64 *out3, long long batch, int limbs);
 
     // fused BSGS inner sums of one linear stage: out[g] = sum_j pt[g * n_baby + j] (.) rot[j]
