@@ -165,6 +165,12 @@ int32_t moai_bootstrapper_required_step_levels(moai_bootstrapper *b, int32_t *st
  * cheapest fast-mode key registered for the level */
 int32_t moai_relinearize_keys(moai_context *ctx, moai_keys *keys, const uint64_t *in3, uint64_t *out2, int64_t batch,
                               int32_t limbs);
+/* rescale_to_next(relinearize(in3)) — the pair every module function ends a ciphertext product with
+ * (S/evaluator.cpp:1345-1400 then :1402-1481) — out2 at limbs - 1.  With a grouped-digit relinearisation key (fast mode)
+ * the key switch's division by P' and the rescale's division by q_last are ONE division by P' q_last
+ * (csrc/ksgroup.cu: ksg_moddown_rescale); with SEAL's key it is the two exact calls. */
+int32_t moai_relin_rescale_keys(moai_context *ctx, moai_keys *keys, const uint64_t *in3, uint64_t *out2, int64_t batch,
+                                int32_t limbs);
 int32_t moai_complex_conjugate_keys(moai_context *ctx, moai_keys *keys, const uint64_t *in, uint64_t *out, int64_t batch,
                                     int32_t limbs);
 int32_t moai_bootstrap(moai_context *ctx, moai_bootstrapper *b, moai_keys *keys, const uint64_t *in, int64_t batch,

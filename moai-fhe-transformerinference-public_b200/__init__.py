@@ -506,6 +506,13 @@ class Backend:
         self._chk(self.lib.moai_relinearize_keys(self.h, keys.h, _ptr(a3), _ptr(out), C.c_int64(bt), C.c_int32(l)))
         return out
 
+    def relin_rescale_keys(self, keys, a3):
+        """rescale_to_next(relinearize(a3)); one merged division with a grouped-digit key (fast mode)."""
+        bt, p, l, n = a3.shape
+        out = self.empty(bt, 2, l - 1, n)
+        self._chk(self.lib.moai_relin_rescale_keys(self.h, keys.h, _ptr(a3), _ptr(out), C.c_int64(bt), C.c_int32(l)))
+        return out
+
     def complex_conjugate_keys(self, keys, a):
         bt, p, l, n = a.shape
         out = self.torch.empty_like(a)

@@ -1,4 +1,5 @@
 // Full-slot CKKS bootstrapping (see bootstrap.hpp for the design and the reference pointers).
+#include <cstdlib>
 #include "bootstrap.hpp"
 #include <algorithm>
 #include <set>
@@ -742,11 +743,42 @@ namespace moai
         }
         MOAI_REQUIRE(!gi.empty() && gi.size() <= (size_t)BSGS_MAX_GIANT, "BSGS plan exceeds the fused kernel's limits");
         const int G = (int)gi.size();
-        std::vector<Ct> inner(G);
+        // Lazy giant steps: the giants' key switches stay in the key-switch basis too.  Only the c1 of a giant's inner
+        // sum is divided by P' (it has to be decomposed again); its c0 and the giant's key-switch sums are rotated and
+        // added in the extended basis, and the stage's ONE remaining division is by P' q_last — the rescale that ends
+        // the stage rides on it (ksg_moddown_rescale).  Per stage with 4 giants: 5 polynomial mod-downs instead of
+        // 14 + 2 rescales.  Needs grouped keys of the stage's layout for every giant step (MOAI_LAZY_GIANTS=0 disables).
+        static const bool lazy_giants_on = [] {
+            const char *e = std::getenv("MOAI_LAZY_GIANTS");
+            return !(e && e[0] == '0');
+        }();
+        std::vector<uint32_t> gelts(G, 0);
+        std::vector<const KeyRef *> gkeys(G, nullptr);
+        int n_gsw = 0; // giants that need a key switch
+        bool lazy_giants = lazy_giants_on && limbs >= 2 && (layout > 0 || (layout == KS_SINGLE && G == 1));
+        for (int g = 0; g < G && lazy_giants; g++)
+        {
+            const int gstep = norm((long long)gi[g] * st.giant * st.stride);
+            if (gstep == 0)
+            {
+                continue;
+            }
+            gelts[g] = c->elt_from_step(gstep);
+            gkeys[g] = layout > 0 ? keys.fast(c, gelts[g], limbs, layout) : nullptr;
+            lazy_giants = gkeys[g] != nullptr;
+            n_gsw++;
+        }
+        std::vector<Ct> inner(lazy_giants ? 0 : G);
         for (auto &x : inner)
         {
             x = ev.alloc(ct.batch, 2, limbs, ct.scale * st.pt_scale);
         }
+        Ct lazy_out;
+        if (lazy_giants)
+        {
+            lazy_out = ev.alloc(ct.batch, 2, limbs - 1, ct.scale * st.pt_scale / ev.last_prime(limbs));
+        }
+        const size_t per_out = (size_t)2 * (limbs - 1) * N;
         // keys of the non-identity baby steps
         std::vector<int> rot_idx; // baby index of every rotation that needs a key switch
         std::vector<const KeyRef *> rkeys;
@@ -768,11 +800,12 @@ namespace moai
         const size_t acc_words = (size_t)2 * sh.rns * N;
         const size_t ext_bytes = layout == KS_SINGLE ? ks_single_ext_bytes_per_ct(c, limbs)
                                  : (layout > 0 ? ksg_ext_bytes_per_ct(c, limbs, layout) : ks_ext_bytes_per_ct(c, limbs));
-        const size_t per_ct_ws = ext_bytes + (size_t)((layout == KS_SINGLE ? 0 : std::max(R, 1)) + G) * acc_words * sizeof(u64);
+        const int acc_slots = layout == KS_SINGLE ? 0 : std::max(std::max(R, 1), lazy_giants ? n_gsw + 1 : 0);
+        const size_t per_ct_ws = ext_bytes + (size_t)(acc_slots + G) * acc_words * sizeof(u64);
         long long chunk = std::max<long long>(1, (long long)(ks_ext_budget() / per_ct_ws));
         chunk = std::min<long long>(chunk, ct.batch);
         Scratch ext((size_t)chunk * ext_bytes, c->stream);
-        Scratch accs((size_t)(layout == KS_SINGLE ? 1 : std::max(R, 1) * chunk * acc_words) * sizeof(u64), c->stream);
+        Scratch accs((size_t)(layout == KS_SINGLE ? 1 : acc_slots * chunk * acc_words) * sizeof(u64), c->stream);
         Scratch outs((size_t)G * chunk * acc_words * sizeof(u64), c->stream);
         Scratch cP((size_t)chunk * 2 * limbs * N * sizeof(u64), c->stream);
         const size_t per_ct = (size_t)2 * limbs * N;
@@ -813,6 +846,11 @@ namespace moai
                         pp[j] = pts[j0 + j];
                     }
                     bsgs_single(c, ext.as<u64>(), kp.data(), perm.data(), pp.data(), cnt, c->kl, o, cP.as<u64>(), nb, sh, j0 > 0);
+                }
+                if (lazy_giants) // no giant rotation: mod-down and the stage's rescale in one division
+                {
+                    ksg_moddown_rescale(c, o, nb * 2, limbs, 0, nullptr, false, lazy_out.d + (size_t)b0 * per_out);
+                    continue;
                 }
                 ks_moddown(c, o, nb * 2, limbs, 0, nullptr, false, inner[0].d + (size_t)b0 * per_ct);
                 continue;
@@ -869,10 +907,42 @@ namespace moai
                 }
                 bsgs_ext(c, ap.data(), perm.data(), cnt, pp.data(), G, op.data(), cP.as<u64>(), nb, sh, j0 > 0);
             }
+            if (lazy_giants)
+            {
+                // the baby steps' workspaces are free again: digits -> ext, (c1, direct) -> cP, sums -> accs
+                u64 *c1buf = cP.as<u64>(), *direct = cP.as<u64>() + (size_t)nb * limbs * N;
+                const u64 *accp[BSGS_MAX_GIANT], *extra[BSGS_MAX_GIANT];
+                const uint32_t *perm[BSGS_MAX_GIANT];
+                int slot = 0;
+                for (int g = 0; g < G; g++)
+                {
+                    if (gelts[g] == 0)
+                    {
+                        accp[g] = op[g];
+                        extra[g] = nullptr;
+                        perm[g] = nullptr;
+                        continue;
+                    }
+                    ksg_moddown(c, op[g] + (size_t)sh.rns * N, nb, limbs, layout, nullptr, false, c1buf, 2, 2);
+                    u64 *acc_g = accs.as<u64>() + (size_t)slot++ * nb * acc_words;
+                    ksg_switch_acc(c, c1buf, nb, limbs, layout, gkeys[g]->p, gkeys[g]->key_kl, ext.as<u64>(), direct, acc_g, 0);
+                    accp[g] = acc_g;
+                    extra[g] = op[g];
+                    perm[g] = c->galois_table(gelts[g]);
+                }
+                u64 *total = accs.as<u64>() + (size_t)slot * nb * acc_words;
+                ksg_giants_sum(c, G, accp, extra, perm, total, nb, limbs, layout);
+                ksg_moddown_rescale(c, total, nb * 2, limbs, layout, nullptr, false, lazy_out.d + (size_t)b0 * per_out);
+                continue;
+            }
             for (int g = 0; g < G; g++)
             {
                 ks_moddown(c, op[g], nb * 2, limbs, layout > 0 ? layout : 0, nullptr, false, inner[g].d + (size_t)b0 * per_ct);
             }
+        }
+        if (lazy_giants)
+        {
+            return lazy_out;
         }
         return finish_giants(ev, ct, const_cast<LinearStage &>(st), keys, gi, inner);
     }
@@ -985,7 +1055,7 @@ namespace moai
         {
             return rest;
         }
-        Ct prod = ev.rescale_to_next(ev.relinearize(acc3, keys));
+        Ct prod = ev.relin_rescale(acc3, keys);
         prod.scale = target_scale;
         return ev.add(prod, rest);
     }
@@ -996,7 +1066,7 @@ namespace moai
         std::map<int, Ct> T;
         T[1] = y;
         auto dbl_minus_one = [&](const Ct &sq) {
-            Ct r = ev.rescale_to_next(ev.relinearize(sq, keys));
+            Ct r = ev.relin_rescale(sq, keys);
             ev.double_inplace(r);
             return ev.add_const(r, -1.0);
         };
@@ -1005,7 +1075,7 @@ namespace moai
             Ct ta = T.at(a), tb = T.at(b);
             const int lv = std::min(ta.limbs, tb.limbs);
             (void)lv;
-            Ct p = ev.rescale_to_next(ev.relinearize(ev.multiply_lowered(ta, tb), keys));
+            Ct p = ev.relin_rescale(ev.multiply_lowered(ta, tb), keys);
             ev.double_inplace(p);
             return ev.sub_reduced_error(p, T.at(a - b));
         };

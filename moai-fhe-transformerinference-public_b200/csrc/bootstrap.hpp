@@ -120,6 +120,8 @@ namespace moai
         }
 
         BootParams prm;
+        // softmax_boot's masked plaintext batches, encoded once per (mask, shift constant, level, scale) (csrc/modules.cu)
+        std::map<std::string, Pt> mask_pts;
 
     private:
         Context *c_;

@@ -897,6 +897,22 @@ extern "C"
         API_END
     }
 
+    int32_t moai_relin_rescale_keys(moai_context *ctx, moai_keys *keys, const uint64_t *in3, uint64_t *out2, int64_t batch,
+                                    int32_t limbs)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(in3 && out2, "null argument");
+        MOAI_REQUIRE(limbs >= 2, "end of modulus switching chain reached");
+        check_shape(c, batch, 3, limbs);
+        Evaluator ev(c);
+        Ct r = ev.relin_rescale(ev.wrap(const_cast<u64 *>(CU(in3)), batch, 3, limbs, 1.0), getk(keys));
+        MOAI_CUDA_CHECK(cudaMemcpyAsync(out2, r.d, (size_t)batch * 2 * (limbs - 1) * c->n * sizeof(u64),
+                                        cudaMemcpyDeviceToDevice, c->stream));
+        MOAI_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        API_END
+    }
+
     int32_t moai_complex_conjugate_keys(moai_context *ctx, moai_keys *keys, const uint64_t *in, uint64_t *out, int64_t batch,
                                         int32_t limbs)
     {

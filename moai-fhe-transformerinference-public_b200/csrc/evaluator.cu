@@ -1,5 +1,6 @@
 // Implementation of the batched host-side Evaluator (see evaluator.hpp).  Every method keeps
 // SEAL's metadata semantics; the cited lines are where the reference defines them.
+#include <cstdlib>
 #include "evaluator.hpp"
 #include <algorithm>
 #include <cstring>
@@ -315,6 +316,31 @@ namespace moai
         EV_REQUIRE(rk != nullptr, "not enough relinearization keys");
         Ct r = alloc(a3.batch, 2, a3.limbs, a3.scale);
         moai::relinearize(c, a3.d, r.d, a3.batch, a3.limbs, rk->p, rk->key_kl, rk->k_extra);
+        return r;
+    }
+
+    static bool merge_rescale_enabled()
+    {
+        static const bool on = [] {
+            const char *e = std::getenv("MOAI_MERGE_RESCALE");
+            return !(e && e[0] == '0');
+        }();
+        return on;
+    }
+
+    Ct Evaluator::relin_rescale(const Ct &a3, const Keys &k) const
+    {
+        // rescale_to_next(relinearize(a3)); with a grouped-digit key (fast mode) the two divisions are one
+        // (ksg_moddown_rescale, csrc/ksgroup.cu): same plaintext, one rounding instead of two
+        EV_REQUIRE(a3.size == 3, "relinearize expects a size-3 ciphertext");
+        const KeyRef *rk = k.relin_at(c, a3.limbs);
+        EV_REQUIRE(rk != nullptr, "not enough relinearization keys");
+        if (rk->k_extra <= 0 || a3.limbs < 2 || !merge_rescale_enabled())
+        {
+            return rescale_to_next(relinearize(a3, k));
+        }
+        Ct r = alloc(a3.batch, 2, a3.limbs - 1, a3.scale / last_prime(a3.limbs));
+        moai::relinearize_rescale(c, a3.d, r.d, a3.batch, a3.limbs, rk->p, rk->key_kl, rk->k_extra);
         return r;
     }
 

@@ -182,6 +182,8 @@ namespace moai
         void multiply_accumulate(Ct &acc3, const Ct &a, const Ct &b) const; // acc3 += a x b (size 3)
         Ct relinearize(const Ct &a3, const Keys &k) const;
         Ct rescale_to_next(const Ct &a) const;
+        // rescale_to_next(relinearize(a3)); one merged division with grouped-digit keys (MOAI_MERGE_RESCALE=0 disables)
+        Ct relin_rescale(const Ct &a3, const Keys &k) const;
         Ct mod_switch_to(const Ct &a, int limbs) const;
         Ct mod_switch_to_next(const Ct &a) const
         {

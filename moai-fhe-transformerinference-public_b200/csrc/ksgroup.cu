@@ -82,6 +82,12 @@ namespace moai
             const Twiddle *d_yconst = nullptr; // [limbs]  prod(E) (Q_g / q_J)^-1 mod q_J
             const Twiddle *d_zconst = nullptr; // [k + 1]  (P' / p_i)^-1 mod p_i
             const Twiddle *d_pinv = nullptr;   // [limbs]  P'^-1 mod q_j
+            // merged mod-down + rescale (divide by P'' = P' q_{limbs-1} in one go; limbs >= 2)
+            ConvTab mdr;                         // sources q_{limbs-1}, E, p  ->  targets q_0 .. q_{limbs-2}
+            const NttScale *d_zscale_r = nullptr; // [k + 2]  (P'' / p_i)^-1 mod p_i folded into the inverse transform
+            const Twiddle *d_pinv_r = nullptr;   // [limbs - 1]  P''^-1 mod q_j
+            const Twiddle *d_qlinv = nullptr;    // [limbs - 1]  q_{limbs-1}^-1 mod q_j
+            Twiddle pmod_last;                   // P' mod q_{limbs-1}
             const Twiddle *d_qe = nullptr;     // [limbs]  prod(E) mod q_j
             const NttScale *d_yscale = nullptr; // [limbs]  yconst folded into the inverse transform's N^-1
             const NttScale *d_zscale = nullptr; // [k + 1]  zconst likewise
@@ -341,6 +347,44 @@ namespace moai
                 zscale[i] = ntt_scale_make(c, src_md[i], zconst[i].w);
             }
             const size_t o_ys = bl.put(yscale), o_zs = bl.put(zscale);
+            // merged mod-down + rescale: one more source limb (the level's last data prime), one target fewer
+            ConvOffsets o_mdr{};
+            size_t o_zsr = 0, o_pr = 0, o_ql = 0;
+            if (limbs >= 2)
+            {
+                std::vector<int> src_r(ids.begin() + limbs - 1, ids.end()), tgt_r(ids.begin(), ids.begin() + limbs - 1);
+                o_mdr = build_conv(c, bl, src_r, std::vector<int>{ 0 }, std::vector<int>{ k + 2 }, tgt_r);
+                std::vector<NttScale> zscale_r(k + 2);
+                for (int i = 0; i < k + 2; i++)
+                {
+                    const u64 q = c->q[src_r[i]];
+                    u64 v = 1;
+                    for (int i2 = 0; i2 < k + 2; i2++)
+                    {
+                        if (i2 != i)
+                        {
+                            v = h_mulmod(v, c->q[src_r[i2]] % q, q);
+                        }
+                    }
+                    zscale_r[i] = ntt_scale_make(c, src_r[i], h_invmod(v, q));
+                }
+                std::vector<Twiddle> pinv_r(limbs - 1), qlinv(limbs - 1);
+                for (int j = 0; j < limbs - 1; j++)
+                {
+                    const u64 q = c->q[j];
+                    u64 v = 1;
+                    for (int i = 0; i < k + 2; i++)
+                    {
+                        v = h_mulmod(v, c->q[src_r[i]] % q, q);
+                    }
+                    pinv_r[j] = h_shoup(h_invmod(v, q), q);
+                    qlinv[j] = h_shoup(h_invmod(c->q[limbs - 1] % q, q), q);
+                }
+                o_zsr = bl.put(zscale_r);
+                o_pr = bl.put(pinv_r);
+                o_ql = bl.put(qlinv);
+                t->pmod_last = h_shoup(t->h_pmod[limbs - 1], c->q[limbs - 1]);
+            }
             const size_t o_qe = bl.put(qe), o_own = bl.put(own);
             const size_t o_z = bl.put(zconst), o_p = bl.put(pinv);
             MOAI_CUDA_CHECK(cudaMalloc(&t->blob, bl.bytes.size()));
@@ -355,6 +399,13 @@ namespace moai
             t->d_qe = reinterpret_cast<const Twiddle *>(base + o_qe);
             t->d_yscale = reinterpret_cast<const NttScale *>(base + o_ys);
             t->d_zscale = reinterpret_cast<const NttScale *>(base + o_zs);
+            if (limbs >= 2)
+            {
+                t->mdr = bind_conv(o_mdr, base);
+                t->d_zscale_r = reinterpret_cast<const NttScale *>(base + o_zsr);
+                t->d_pinv_r = reinterpret_cast<const Twiddle *>(base + o_pr);
+                t->d_qlinv = reinterpret_cast<const Twiddle *>(base + o_ql);
+            }
             t->d_own = reinterpret_cast<const int *>(base + o_own);
             t->shape.digits = t->digits;
             t->shape.rns = t->rns;
@@ -406,6 +457,28 @@ namespace moai
                 s.y = addmod(s.y, v.y, q);
             }
             out[i] = s;
+        }
+
+        // merged mod-down + rescale: acc[P][rns][n] (limb `limb`) += (P' mod q_limb) * addend[(P/2)*group + P%2][limbs][n] (limb `limb`)
+        __global__ void k_add_scaled_limb(ulonglong2 *acc, const ulonglong2 *__restrict__ addend, long long total2, int log_n2,
+                                          int rns, int limbs, int limb, int addend_group, int even_only, Twiddle w, u64 q)
+        {
+            const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; // over [P][n/2]
+            if (i >= total2)
+            {
+                return;
+            }
+            const long long P = i >> log_n2, within = i & (((long long)1 << log_n2) - 1);
+            if (even_only && (P & 1))
+            {
+                return;
+            }
+            ulonglong2 *a = acc + (((P * rns + limb) << log_n2) + within);
+            const ulonglong2 z = addend[((((P >> 1) * addend_group + (P & 1)) * limbs + limb) << log_n2) + within];
+            ulonglong2 v = *a;
+            v.x = addmod(v.x, mul_shoup(z.x, w.w, w.wq, q), q);
+            v.y = addmod(v.y, mul_shoup(z.y, w.w, w.wq, q), q);
+            *a = v;
         }
 
         size_t ksg_ext_budget_bytes()
@@ -578,14 +651,62 @@ namespace moai
         ntt_forward(c, ext, batch * t.rns * t.digits, t.d_ids, t.rns, t.digits, &pro, passes);
     }
 
+    // out[P][limbs - 1][n] = round((acc + P' addend) / (P' q_{limbs-1})): the rescale that follows a key switch, taken
+    // in the same division (the level's last data prime is one more prime of the special modulus): 2 (limbs - 1) + 2
+    // transforms fewer than mod-down + rescale_to_next (S/evaluator.cpp:1402-1481 after :2910-3018), one rounding
+    // instead of two.  acc's limb limbs - 1 is modified in place.
+    void ksg_moddown_rescale(Context *c, u64 *acc, long long polys, int limbs, int k, const u64 *addend,
+                             bool addend_even_only, u64 *out, int addend_group)
+    {
+        const KsgTables &t = tables(c, k, limbs);
+        MOAI_REQUIRE(limbs >= 2, "end of modulus switching chain reached");
+        const size_t n = c->n;
+        const int np = k + 2, targets = limbs - 1;
+        if (addend)
+        {
+            const long long total2 = polys * (long long)(n / 2);
+            KernelTimer kt(c, "k_addsub", 1);
+            k_add_scaled_limb<<<(unsigned)((total2 + 255) / 256), 256, 0, c->stream>>>(
+                reinterpret_cast<ulonglong2 *>(acc), reinterpret_cast<const ulonglong2 *>(addend), total2, c->log_n - 1,
+                t.rns, limbs, limbs - 1, addend_group, addend_even_only ? 1 : 0, t.pmod_last, c->q[limbs - 1]);
+            c->launches += 1;
+            MOAI_CUDA_CHECK(cudaGetLastError());
+        }
+        Scratch r((size_t)polys * np * n * sizeof(u64), c->stream);
+        ntt_inverse_from(c, acc + (size_t)targets * n, np, t.rns, r.as<u64>(), polys * np, t.d_ids + targets, np, 1,
+                         t.d_zscale_r);
+        Scratch u((size_t)polys * targets * n * sizeof(u64), c->stream);
+        NttPrologue pro;
+        pro.src = r.as<u64>();
+        pro.mode = 3;
+        pro.conv = &t.mdr;
+        FinishEpi fin;
+        fin.in = acc;
+        fin.addend = addend;
+        fin.out = out;
+        fin.inv = t.d_pinv_r;
+        fin.limbs_in = t.rns;
+        fin.addend_even_only = addend_even_only ? 1 : 0;
+        fin.addend_group = addend_group;
+        fin.addend_mul = t.d_qlinv;
+        fin.addend_limbs = limbs;
+        if (ntt_forward(c, u.as<u64>(), polys * targets, c->d_ids, targets, 1, &pro, 3, &fin))
+        {
+            return;
+        }
+        divround_finish(c, acc, u.as<u64>(), addend, out, polys, targets, t.rns, t.d_pinv_r, addend_even_only, addend_group,
+                        t.d_qlinv, limbs);
+    }
+
     void ksg_moddown(Context *c, const u64 *acc, long long polys, int limbs, int k, const u64 *addend,
-                     bool addend_even_only, u64 *out, int addend_group)
+                     bool addend_even_only, u64 *out, int addend_group, int in_stride)
     {
         const KsgTables &t = tables(c, k, limbs);
         const size_t n = c->n;
         const int np = k + 1;
+        const int rns_in = t.rns * in_stride; // limbs between consecutive input polynomials
         Scratch r((size_t)polys * np * n * sizeof(u64), c->stream);
-        ntt_inverse_from(c, acc + (size_t)limbs * n, np, t.rns, r.as<u64>(), polys * np, t.d_ids + limbs, np, 1,
+        ntt_inverse_from(c, acc + (size_t)limbs * n, np, rns_in, r.as<u64>(), polys * np, t.d_ids + limbs, np, 1,
                          t.d_zscale);
         Scratch u((size_t)polys * limbs * n * sizeof(u64), c->stream);
         NttPrologue pro;
@@ -597,14 +718,14 @@ namespace moai
         fin.addend = addend;
         fin.out = out;
         fin.inv = t.d_pinv;
-        fin.limbs_in = t.rns;
+        fin.limbs_in = rns_in;
         fin.addend_even_only = addend_even_only ? 1 : 0;
         fin.addend_group = addend_group;
         if (ntt_forward(c, u.as<u64>(), polys * limbs, c->d_ids, limbs, 1, &pro, 3, &fin))
         {
             return;
         }
-        divround_finish(c, acc, u.as<u64>(), addend, out, polys, limbs, t.rns, t.d_pinv, addend_even_only, addend_group);
+        divround_finish(c, acc, u.as<u64>(), addend, out, polys, limbs, rns_in, t.d_pinv, addend_even_only, addend_group);
     }
 
     // inner products of the integer-path target moduli (the special prime): plain pass B + 128-bit MAC
@@ -783,8 +904,84 @@ namespace moai
         MOAI_CUDA_CHECK(cudaGetLastError());
     }
 
+    void ksg_switch_acc(Context *c, const u64 *target, long long batch, int limbs, int k, const u64 *ksk, int key_kl,
+                        u64 *ext, u64 *direct, u64 *acc, long long target_stride)
+    {
+        const KsgTables &t = tables(c, k, limbs);
+        MOAI_REQUIRE(key_kl >= t.rns, "grouped key does not cover this level");
+        ksg_decompose(c, target, batch, limbs, k, ext, target_stride, /*passes=*/1);
+        ksg_direct(c, t, target, batch, target_stride, direct);
+        ks_passb_mac(c, ext, batch, t.shape, ksk, key_kl, acc, direct, t.d_own);
+        ksg_int_targets(c, t, ext, batch, ksk, key_kl, acc, true);
+    }
+
+    namespace
+    {
+        struct GiantSumArgs
+        {
+            const u64 *acc[BSGS_MAX_GIANT];      // [batch][2][rns][n]: key-switch sums of a giant step (or its inner sums)
+            const u64 *extra[BSGS_MAX_GIANT];    // [batch][2][rns][n] or nullptr: polynomial 0 is added before the rotation
+            const uint32_t *perm[BSGS_MAX_GIANT]; // Galois table of the giant step (nullptr = identity)
+            int n;
+        };
+        // total[b][p][I][.] = sum_g sigma_g(acc_g[b][p][I][.] + (p == 0 ? extra_g[b][0][I][.] : 0))   (mod m_I)
+        __global__ void k_giants_sum(GiantSumArgs a, ulonglong2 *total, long long total2, int log_n, int rns,
+                                     const int *__restrict__ ids, const LimbConst *__restrict__ lcs)
+        {
+            const long long i2 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            if (i2 >= total2)
+            {
+                return;
+            }
+            const long long i = i2 * 2;
+            const long long pl = i >> log_n; // (b * 2 + p) * rns + I
+            const int I = (int)(pl % rns);
+            const bool even = ((pl / rns) & 1) == 0;
+            const u64 q = lcs[ids[I]].q;
+            const long long base = pl << log_n;
+            const uint32_t within = (uint32_t)(i & (((long long)1 << log_n) - 1));
+            u64 sx = 0, sy = 0;
+            for (int g = 0; g < a.n; g++)
+            {
+                const uint32_t *tb = a.perm[g];
+                const long long jx = base + (tb ? tb[within] : within), jy = base + (tb ? tb[within + 1] : within + 1);
+                u64 vx = a.acc[g][jx], vy = a.acc[g][jy];
+                if (even && a.extra[g])
+                {
+                    vx = addmod(vx, a.extra[g][jx], q);
+                    vy = addmod(vy, a.extra[g][jy], q);
+                }
+                sx = addmod(sx, vx, q);
+                sy = addmod(sy, vy, q);
+            }
+            total[i2] = make_ulonglong2(sx, sy);
+        }
+    } // namespace
+
+    void ksg_giants_sum(Context *c, int n_giants, const u64 *const *acc, const u64 *const *extra,
+                        const uint32_t *const *perm, u64 *total, long long batch, int limbs, int k)
+    {
+        const KsgTables &t = tables(c, k, limbs);
+        MOAI_REQUIRE(n_giants >= 1 && n_giants <= BSGS_MAX_GIANT, "too many giant steps for one pass");
+        GiantSumArgs a;
+        a.n = n_giants;
+        for (int g = 0; g < n_giants; g++)
+        {
+            a.acc[g] = acc[g];
+            a.extra[g] = extra[g];
+            a.perm[g] = perm[g];
+        }
+        const long long total2 = batch * 2 * t.rns * (long long)(c->n / 2);
+        KernelTimer kt(c, "k_giants_sum", 1);
+        k_giants_sum<<<(unsigned)((total2 + 255) / 256), 256, 0, c->stream>>>(a, reinterpret_cast<ulonglong2 *>(total), total2,
+                                                                              c->log_n, t.rns, t.d_ids, c->d_limb);
+        c->launches += 1;
+        MOAI_CUDA_CHECK(cudaGetLastError());
+    }
+
     void ksg_switch(Context *c, const u64 *target, long long batch, int limbs, int k, const u64 *ksk, int key_kl,
-                    const u64 *addend, u64 *out, long long target_stride, bool addend_c0_only, int addend_group)
+                    const u64 *addend, u64 *out, long long target_stride, bool addend_c0_only, int addend_group,
+                    bool rescale)
     {
         const KsgTables &t = tables(c, k, limbs);
         MOAI_REQUIRE(key_kl >= t.rns, "grouped key does not cover this level");
@@ -803,10 +1000,15 @@ namespace moai
             ksg_direct(c, t, target + (size_t)b0 * tstride, nb, target_stride, direct.as<u64>());
             ks_passb_mac(c, ext.as<u64>(), nb, t.shape, ksk, key_kl, acc.as<u64>(), direct.as<u64>(), t.d_own);
             ksg_int_targets(c, t, ext.as<u64>(), nb, ksk, key_kl, acc.as<u64>(), true);
+            const u64 *ad = addend ? addend + (size_t)b0 * addend_group * limbs * n : nullptr;
+            if (rescale)
+            {
+                ksg_moddown_rescale(c, acc.as<u64>(), nb * 2, limbs, k, ad, addend_c0_only,
+                                    out + (size_t)b0 * 2 * (limbs - 1) * n, addend_group);
+                continue;
+            }
             const size_t off = (size_t)b0 * 2 * limbs * n;
-            ksg_moddown(c, acc.as<u64>(), nb * 2, limbs, k,
-                        addend ? addend + (size_t)b0 * addend_group * limbs * n : nullptr, addend_c0_only, out + off,
-                        addend_group);
+            ksg_moddown(c, acc.as<u64>(), nb * 2, limbs, k, ad, addend_c0_only, out + off, addend_group);
         }
     }
 

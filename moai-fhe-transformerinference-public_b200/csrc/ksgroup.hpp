@@ -52,11 +52,24 @@ namespace moai
                        long long target_stride, int passes);
     // out[P][limbs][n] = round(acc[P][limbs + k + 1][n] / P')  (+ addend; addend_even_only: even polynomials only)
     // addend_group: polynomials per ciphertext in the addend's layout (2; 3 when relinearize adds (c0, c1) of its input)
+    // in_stride: input polynomial P sits at acc + P * in_stride * (limbs + k + 1) * n (2 with acc + rns * n: the c1's only)
     void ksg_moddown(Context *c, const u64 *acc, long long polys, int limbs, int k, const u64 *addend,
-                     bool addend_even_only, u64 *out, int addend_group = 2);
+                     bool addend_even_only, u64 *out, int addend_group = 2, int in_stride = 1);
+    // key switch WITHOUT the mod-down: acc[batch][2][limbs + k + 1][n] = sum_G D_G (.) K_G; workspaces
+    // ext (ksg_ext_bytes_per_ct per item) and direct ([batch][limbs][n])
+    void ksg_switch_acc(Context *c, const u64 *target, long long batch, int limbs, int k, const u64 *ksk, int key_kl,
+                        u64 *ext, u64 *direct, u64 *acc, long long target_stride);
+    // total = sum_g sigma_g(acc_g + (extra_g.c0, 0)) in the key-switch basis (giant steps of the lazy BSGS)
+    void ksg_giants_sum(Context *c, int n_giants, const u64 *const *acc, const u64 *const *extra,
+                        const uint32_t *const *perm, u64 *total, long long batch, int limbs, int k);
     // complete key switch: out[b] = addend[b] + keyswitch(target[b]); out / addend are size-2 ciphertexts
     void ksg_switch(Context *c, const u64 *target, long long batch, int limbs, int k, const u64 *ksk, int key_kl,
-                    const u64 *addend, u64 *out, long long target_stride, bool addend_c0_only, int addend_group = 2);
+                    const u64 *addend, u64 *out, long long target_stride, bool addend_c0_only, int addend_group = 2,
+                    bool rescale = false);
+    // out[P][limbs - 1][n] = round((acc + P' addend) / (P' q_{limbs-1})): mod-down and the rescale after it in one
+    // division (fast mode; acc's limb limbs - 1 is modified in place)
+    void ksg_moddown_rescale(Context *c, u64 *acc, long long polys, int limbs, int k, const u64 *addend,
+                             bool addend_even_only, u64 *out, int addend_group = 2);
     // hoisted rotations from one decomposition (up to KSM_R keys per pass)
     void ksg_rotate_hoisted_multi(Context *c, const u64 *ct, const u64 *ext, long long batch, int limbs, int k, int n_rot,
                                   const uint32_t *elts, const u64 *const *ksk_pre, const int *key_kl, u64 *const *outs);

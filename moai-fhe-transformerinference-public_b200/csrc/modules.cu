@@ -90,7 +90,7 @@ namespace moai
             }
         }
         auto c = [&](int i) { return coeff[24 - i] * f[i]; }; // coefficient of u^i as the reference applies it
-        auto rr = [&](const Ct &a3) { return ev.rescale_to_next(ev.relinearize(a3, keys)); };
+        auto rr = [&](const Ct &a3) { return ev.relin_rescale(a3, keys); };
         Ct u = ev.rescale_to_next(ev.multiply_plain(x, ev.encode(0.1, L0, D)));                   // L0-1
         Ct u2 = rr(ev.square(u));                                                                   // L0-2
         Ct u3 = rr(ev.multiply_lowered(u, u2));                                                     // L0-3
@@ -162,10 +162,10 @@ namespace moai
         }
         std::vector<Ct> p(25);
         p[1] = ev.rescale_to_next(ev.multiply_plain(x, ev.encode(s0, x.limbs, x.scale)));
-        auto sq = [&](const Ct &a) { return ev.rescale_to_next(ev.relinearize(ev.square(a), keys)); };
+        auto sq = [&](const Ct &a) { return ev.relin_rescale(ev.square(a), keys); };
         auto mul = [&](const Ct &a, const Ct &b) {
             // mod_switch the first factor to the second's level, multiply, relinearize, rescale
-            return ev.rescale_to_next(ev.relinearize(ev.multiply(ev.mod_switch_to(a, b.limbs), b), keys));
+            return ev.relin_rescale(ev.multiply(ev.mod_switch_to(a, b.limbs), b), keys);
         };
         p[2] = sq(p[1]);
         p[4] = sq(p[2]);
@@ -232,7 +232,7 @@ namespace moai
             const double scale = x.scale;
             for (int i = 0; i < iter; ++i)
             {
-                Ct res_sq = ev.rescale_to_next(ev.relinearize(ev.square(res), keys));
+                Ct res_sq = ev.relin_rescale(ev.square(res), keys);
                 Ct res_x = ev.rescale_to_next(ev.multiply_plain(x, ev.encode(-0.5, x.limbs, scale)));
                 if (res.limbs < res_x.limbs)
                 {
@@ -242,9 +242,9 @@ namespace moai
                 {
                     res = ev.mod_switch_to(res, res_x.limbs);
                 }
-                res_x = ev.rescale_to_next(ev.relinearize(ev.multiply(res_x, res), keys));
+                res_x = ev.relin_rescale(ev.multiply(res_x, res), keys);
                 res_sq = ev.mod_switch_to(res_sq, res_x.limbs);
-                res_x = ev.rescale_to_next(ev.relinearize(ev.multiply(res_x, res_sq), keys));
+                res_x = ev.relin_rescale(ev.multiply(res_x, res_sq), keys);
                 res = ev.rescale_to_next(ev.multiply_plain(res, ev.encode(1.5, res.limbs, scale)));
                 res = ev.mod_switch_to(res, res_x.limbs);
                 res_x.scale = scale;
@@ -259,23 +259,23 @@ namespace moai
         {
             const double scale = y.scale;
             v = ev.mod_switch_to(v, y.limbs);
-            Ct x = ev.rescale_to_next(ev.relinearize(ev.multiply(v, y), keys));
+            Ct x = ev.relin_rescale(ev.multiply(v, y), keys);
             Ct h = ev.rescale_to_next(ev.multiply_plain(y, ev.encode(0.5, y.limbs, scale)));
             for (int i = 0; i < d; ++i)
             {
-                Ct r = ev.rescale_to_next(ev.relinearize(ev.multiply(x, h), keys));
+                Ct r = ev.relin_rescale(ev.multiply(x, h), keys);
                 r.scale = scale;
                 r = ev.add_plain(ev.negate(r), ev.encode(0.5, r.limbs, scale));
                 // x = x + x*r
                 x = ev.mod_switch_to(x, r.limbs);
-                Ct tmp = ev.rescale_to_next(ev.relinearize(ev.multiply(x, r), keys));
+                Ct tmp = ev.relin_rescale(ev.multiply(x, r), keys);
                 x.scale = scale;
                 tmp.scale = scale;
                 x = ev.mod_switch_to(x, tmp.limbs);
                 x = ev.add(x, tmp);
                 // h = h + h*r
                 h = ev.mod_switch_to(h, r.limbs);
-                tmp = ev.rescale_to_next(ev.relinearize(ev.multiply(h, r), keys));
+                tmp = ev.relin_rescale(ev.multiply(h, r), keys);
                 h.scale = scale;
                 tmp.scale = scale;
                 h = ev.mod_switch_to(h, tmp.limbs);
@@ -321,13 +321,13 @@ namespace moai
         ave_x = ev.mod_switch_to(ave_x, nx.limbs);
         ave_x.scale = scale;
         // var = sum_i (nx_i - u)^2 accumulated at size 3, ONE relinearization (layernorm.hpp:245-266)
-        Ct var = ev.rescale_to_next(ev.relinearize(ev.sum_sub_square(nx, ave_x), keys));
+        Ct var = ev.relin_rescale(ev.sum_sub_square(nx, ave_x), keys);
         const double inv_n = variant == 1 ? 1 / (nd * nd) : 1 / (nd * nd * nd);
         var = ev.rescale_to_next(ev.multiply_plain(var, ev.encode(masked(bias_vec, inv_n), var.limbs, var.scale)));
         Ct inv_sqrt_var = invert_sqrt(ev, var, 4, 2, keys);
         ave_x = ev.mod_switch_to(ave_x, inv_sqrt_var.limbs);
         Ct out = ev.sub(ev.mod_switch_to(nx, inv_sqrt_var.limbs), ave_x);
-        out = ev.rescale_to_next(ev.relinearize(ev.multiply(out, inv_sqrt_var), keys));
+        out = ev.relin_rescale(ev.multiply(out, inv_sqrt_var), keys);
         // per-ciphertext masked gamma' and beta plaintexts, encoded as one batch
         const size_t slots = bias_vec.size();
         std::vector<std::complex<double>> vals((size_t)num_ct * slots, 0.0);
@@ -362,7 +362,7 @@ namespace moai
         out = ev.add_plain(out, ev.encode(1.0, out.limbs, out.scale));
         for (int i = 0; i < 7; ++i) // i < log2(128)
         {
-            out = ev.rescale_to_next(ev.relinearize(ev.square(out), keys));
+            out = ev.relin_rescale(ev.square(out), keys);
         }
         return out;
     }
@@ -375,10 +375,10 @@ namespace moai
         Ct res = ev.add_plain(y, one);
         for (int i = 0; i < iter; ++i)
         {
-            y = ev.rescale_to_next(ev.relinearize(ev.square(y), keys));
+            y = ev.relin_rescale(ev.square(y), keys);
             Ct tmp = ev.add_plain(y, ev.encode(1.0, y.limbs, y.scale));
             res = ev.mod_switch_to(res, tmp.limbs);
-            res = ev.rescale_to_next(ev.relinearize(ev.multiply(res, tmp), keys));
+            res = ev.relin_rescale(ev.multiply(res, tmp), keys);
         }
         return res;
     }
@@ -435,7 +435,7 @@ namespace moai
             }
             rotW.clear();
             rotX.clear();
-            Ct out = ev.rescale_to_next(ev.relinearize(acc, keys));
+            Ct out = ev.relin_rescale(acc, keys);
             out.scale = scale;
             for (int a0 = inner; a0 < row_X; a0 += inner)
             {
@@ -454,7 +454,7 @@ namespace moai
                 ev.copy_into(s, acc, i);
             }
         }
-        Ct out = ev.rescale_to_next(ev.relinearize(acc, keys));
+        Ct out = ev.relin_rescale(acc, keys);
         out.scale = scale;
         return out;
     }
@@ -521,7 +521,7 @@ namespace moai
                     ev.multiply_accumulate(acc, c_g[k], xk);
                 }
             }
-            Ct o = ev.rescale_to_next(ev.relinearize(acc, keys));
+            Ct o = ev.relin_rescale(acc, keys);
             o.scale = scale;
             if (j == 0)
             {
@@ -625,14 +625,36 @@ namespace moai
             }
             return vals;
         };
+        // The two masked plaintext batches (num vectors each) depend on the token mask, the layer's shift constant and the
+        // level only: the 12 heads of a layer — and every later call with the same mask — reuse them instead of
+        // rebuilding 2 x num x slots values on the host and encoding them again (same plaintexts, bit for bit).
+        auto cached = [&](double v, int limbs, double pt_scale) -> Pt {
+            unsigned long long h = 1469598103934665603ull; // FNV-1a over the mask
+            for (int b : bias_vec)
+            {
+                h = (h ^ (unsigned long long)(b & 0xff)) * 1099511628211ull;
+            }
+            char key[160];
+            snprintf(key, sizeof key, "%016llx|%d|%d|%d|%.17g|%.17g", h, num, input_num, limbs, v, pt_scale);
+            auto it = boot.mask_pts.find(key);
+            if (it != boot.mask_pts.end())
+            {
+                return it->second;
+            }
+            auto vals = pattern(v);
+            Pt p = ev.encode_batch(vals.data(), num, slot_count, limbs, pt_scale);
+            if (boot.mask_pts.size() >= 8) // a layer uses two entries; keep a few layers' worth
+            {
+                boot.mask_pts.clear();
+            }
+            boot.mask_pts[key] = p;
+            return p;
+        };
         // x - max on the valid slots
-        auto minus = pattern(minus_index);
-        Ct x_minus = ev.sub_plain(X, ev.encode_batch(minus.data(), num, slot_count, X.limbs, X.scale));
+        Ct x_minus = ev.sub_plain(X, cached(minus_index, X.limbs, X.scale));
         // exp, then zero the invalid slots
         Ct exp_x = exp_128(ev, x_minus, keys);
-        auto ones = pattern(1.0);
-        exp_x = ev.rescale_to_next(
-            ev.multiply_plain(exp_x, ev.encode_batch(ones.data(), num, slot_count, exp_x.limbs, exp_x.scale)));
+        exp_x = ev.rescale_to_next(ev.multiply_plain(exp_x, cached(1.0, exp_x.limbs, exp_x.scale)));
         exp_x.scale = scale;
         // sum, + 1e-5, down to the last level, bootstrap
         Ct sum = ev.sum_batch(exp_x);
@@ -654,7 +676,7 @@ namespace moai
         {
             exp_x = ev.mod_switch_to(exp_x, inv_sum.limbs);
         }
-        Ct out = ev.rescale_to_next(ev.relinearize(ev.multiply(exp_x, inv_sum), keys));
+        Ct out = ev.relin_rescale(ev.multiply(exp_x, inv_sum), keys);
         out.scale = scale;
         return out;
     }

@@ -1103,9 +1103,11 @@ namespace moai
                     if (e.addend && !(e.addend_even_only && (q & 1)))
                     {
                         ad = reinterpret_cast<const ulonglong2 *>(
-                            e.addend + (((size_t)((q >> 1) * e.addend_group + (q & 1)) * a.period + slot) << a.log_n) + off);
+                            e.addend + (((size_t)((q >> 1) * e.addend_group + (q & 1)) *
+                                             (e.addend_limbs ? e.addend_limbs : a.period) + slot) << a.log_n) + off);
                     }
                     const Twiddle inv = e.inv[slot];
+                    const Twiddle am = e.addend_mul ? e.addend_mul[slot] : Twiddle{ 0, 0 };
                     const u64 qq = f.pi;
 #pragma unroll
                     for (int k = 0; k < 16; k += 2)
@@ -1116,7 +1118,12 @@ namespace moai
                         v.y = mul_shoup(submod(c0.y, f.out_fwd(x[k + 1]), qq), inv.w, inv.wq, qq);
                         if (ad)
                         {
-                            const ulonglong2 z = ad[k >> 1];
+                            ulonglong2 z = ad[k >> 1];
+                            if (e.addend_mul)
+                            {
+                                z.x = mul_shoup(z.x, am.w, am.wq, qq);
+                                z.y = mul_shoup(z.y, am.w, am.wq, qq);
+                            }
                             v.x = addmod(v.x, z.x, qq);
                             v.y = addmod(v.y, z.y, qq);
                         }

@@ -77,6 +77,10 @@ namespace moai
         u64 *out = nullptr;          // [P][targets][n]
         const Twiddle *inv = nullptr; // [targets]
         int limbs_in = 0, addend_even_only = 0, addend_group = 2;
+        // merged mod-down + rescale (csrc/ksgroup.cu): the addend is multiplied by addend_mul[j] (q_last^-1 mod q_j)
+        // and its polynomials hold addend_limbs limbs (0: as many as there are targets)
+        const Twiddle *addend_mul = nullptr;
+        int addend_limbs = 0;
     };
 
     struct NttArgs

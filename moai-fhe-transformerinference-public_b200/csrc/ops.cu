@@ -253,7 +253,8 @@ namespace moai
                                           const ulonglong2 *addend, ulonglong2 *out, // may alias each other
                                           long long total2, int log_n2, int targets, int limbs_in, int last_id, int kl,
                                           const LimbConst *__restrict__ lcs, const Twiddle *__restrict__ inv_last,
-                                          int addend_even_only, int addend_group)
+                                          int addend_even_only, int addend_group,
+                                          const Twiddle *__restrict__ addend_mul = nullptr, int addend_limbs = 0)
         {
             long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; // over [P][targets][n/2]
             if (i >= total2)
@@ -275,7 +276,16 @@ namespace moai
             {
                 // the addend's ciphertexts may hold more polynomials than the result's two (relinearize reads c0, c1
                 // straight out of the size-3 input): polynomial p of the result <-> (p / 2) * addend_group + p % 2
-                ulonglong2 z = addend[((((p >> 1) * addend_group + (p & 1)) * targets + limb) << log_n2) + within];
+                // merged mod-down + rescale: the addend's polynomials hold addend_limbs limbs and are multiplied by
+                // addend_mul[limb] = q_last^-1 mod q_limb
+                ulonglong2 z = addend[((((p >> 1) * addend_group + (p & 1)) * (addend_limbs ? addend_limbs : targets) + limb)
+                                       << log_n2) + within];
+                if (addend_mul)
+                {
+                    const Twiddle am = addend_mul[limb];
+                    z.x = mul_shoup(z.x, am.w, am.wq, q);
+                    z.y = mul_shoup(z.y, am.w, am.wq, q);
+                }
                 r.x = addmod(r.x, z.x, q);
                 r.y = addmod(r.y, z.y, q);
             }
@@ -599,14 +609,15 @@ namespace moai
 
     // out[P][targets][n] = (in[P][limbs_in][n](limb j < targets) - u[P][targets][n]) * inv[j] mod q_j (+ addend)
     void divround_finish(Context *c, const u64 *in, const u64 *u, const u64 *addend, u64 *out, long long P, int targets,
-                         int limbs_in, const Twiddle *d_inv, bool addend_even_only, int addend_group)
+                         int limbs_in, const Twiddle *d_inv, bool addend_even_only, int addend_group,
+                         const Twiddle *d_addend_mul, int addend_limbs)
     {
         const long long total2 = P * targets * (long long)(c->n / 2);
         KernelTimer kt(c, "k_divround_finish", 1);
         k_divround_finish<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(
             reinterpret_cast<const ulonglong2 *>(in), reinterpret_cast<const ulonglong2 *>(u),
             reinterpret_cast<const ulonglong2 *>(addend), reinterpret_cast<ulonglong2 *>(out), total2, c->log_n - 1,
-            targets, limbs_in, 0, 0, c->d_limb, d_inv, addend_even_only ? 1 : 0, addend_group);
+            targets, limbs_in, 0, 0, c->d_limb, d_inv, addend_even_only ? 1 : 0, addend_group, d_addend_mul, addend_limbs);
         c->launches += 1;
         MOAI_CUDA_CHECK(cudaGetLastError());
     }
@@ -1708,6 +1719,17 @@ namespace moai
                 }
             }
         }
+    }
+
+    void relinearize_rescale(Context *c, const u64 *in3, u64 *out2, long long batch, int limbs, const u64 *ksk, int key_kl,
+                             int k_extra)
+    {
+        // fast mode, grouped keys only: out2[batch][2][limbs - 1][n] = rescale(relinearize(in3)) with the rescale taken
+        // inside the key switch's mod-down (ksg_moddown_rescale)
+        MOAI_REQUIRE(k_extra > 0 && limbs >= 2, "merged relinearize + rescale needs a grouped-digit key");
+        const size_t poly = (size_t)limbs * c->n;
+        ksg_switch(c, in3 + 2 * poly, batch, limbs, k_extra, ksk, key_kl, in3, out2, (long long)(3 * poly), false, 3,
+                   /*rescale=*/true);
     }
 
     void relinearize(Context *c, const u64 *in3, u64 *out2, long long batch, int limbs, const u64 *ksk, int key_kl,

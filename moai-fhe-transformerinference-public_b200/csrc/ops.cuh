@@ -66,6 +66,9 @@ namespace moai
                     int k_extra = 0);
     void relinearize(Context *c, const u64 *in3, u64 *out2, long long batch, int limbs, const u64 *ksk,
                      int key_kl = 0, int k_extra = 0);
+    // grouped keys (k_extra > 0) only: rescale_to_next(relinearize(in3)) in one division, out2 at limbs - 1
+    void relinearize_rescale(Context *c, const u64 *in3, u64 *out2, long long batch, int limbs, const u64 *ksk, int key_kl,
+                             int k_extra);
     void apply_galois(Context *c, const u64 *in, u64 *out, long long batch, int limbs, uint32_t elt, const u64 *ksk,
                       int key_kl = 0);
     // the two halves of a key switch, exposed for hoisting (one decomposition, many rotations)
@@ -84,7 +87,8 @@ namespace moai
     void ks_mac_int(Context *c, const u64 *ext, const u64 *ksk, u64 *acc, long long batch, const KsShape &sh, int key_kl,
                     int I);
     void divround_finish(Context *c, const u64 *in, const u64 *u, const u64 *addend, u64 *out, long long P, int targets,
-                         int limbs_in, const Twiddle *d_inv, bool addend_even_only, int addend_group = 2);
+                         int limbs_in, const Twiddle *d_inv, bool addend_even_only, int addend_group = 2,
+                         const Twiddle *d_addend_mul = nullptr, int addend_limbs = 0);
     // up to KSM_R (csrc/ntt.cuh) hoisted rotations in one pass over the extended digits
     bool ks_multi_enabled(Context *c, int limbs);
     void rotate_hoisted_multi(Context *c, const u64 *ct, const u64 *ext, long long batch, int limbs, int n_rot,

@@ -106,6 +106,32 @@ def test_grouped_conjugation_and_relinearisation(pkg, env):
     assert np.abs(decrypt_batch(o, sk, pkg, out) - np.conj(zc)).max() < 1e-6
 
 
+def test_merged_relinearize_rescale(pkg, env):
+    """rescale_to_next(relinearize(x)) with a grouped key divides by P' q_last ONCE (ksg_moddown_rescale): decrypted
+    at the lower level it matches the two SEAL-exact calls (S/evaluator.cpp:1345-1400, :1402-1481) to 1e-6 (measured
+    ~1e-9), and with SEAL's key the entry point IS the two exact calls, bit for bit."""
+    o, be, sk = env
+    rng = np.random.default_rng(91)
+    relin = pkg.to_device(o.gen_relin_key(sk, 5))
+    relin4 = relin.reshape(o.kl - 1, 2, o.kl, o.n)
+    k_exact = be.make_keys(relin=relin)
+    for limbs, key_limbs, k in [(12, 12, None), (9, 12, 5), (4, 6, 3), (16, 16, 1), (2, 8, 3)]:
+        zx, cx = encrypt_batch(o, sk, rng, 3, limbs)
+        zy, cy = encrypt_batch(o, sk, rng, 3, limbs)
+        prod3 = be.multiply(pkg.to_device(cx), pkg.to_device(cy))
+        exact = be.rescale_to_next(be.relinearize_keys(k_exact, prod3))
+        assert (be.relin_rescale_keys(k_exact, prod3) == exact).all()
+        gk = be.key_prepare_grouped(relin4, 0, key_limbs, k_extra=k, pre_permute=False)
+        k_grp = be.make_keys(grouped={0: [gk]})
+        merged = be.relin_rescale_keys(k_grp, prod3)
+        assert merged.shape == exact.shape and not (merged == exact).all()
+        sc = SCALE * SCALE / float(o.q[limbs - 1])
+        de, dg = decrypt_batch(o, sk, pkg, exact, sc), decrypt_batch(o, sk, pkg, merged, sc)
+        assert np.abs(de - zx * zy).max() < 1e-6
+        assert np.abs(dg - zx * zy).max() < 1e-6, (limbs, np.abs(dg - zx * zy).max())
+        print("merged relin+rescale limbs", limbs, "k", k, "err", np.abs(dg - zx * zy).max(), "exact", np.abs(de - zx * zy).max())
+
+
 def test_bootstrap_grouped(pkg, env):
     """The whole bootstrapping on grouped keys (every Galois key prepared for the level it is used at, the
     relinearisation key in several variants): same tolerance as the SEAL-key pipeline, 2e-3 max-abs."""
@@ -187,7 +213,12 @@ def test_bootstrap_lazy_moddown(pkg, env, use_grouped, use_single):
     zs = (rng.normal(size=(B, o.n // 2)) + 1j * rng.normal(size=(B, o.n // 2))) * 0.1
     zs[2] = 0.0
     cts = np.stack([o.encrypt_sym(sk, 50 + i, o.encode(zs[i], SCALE, 1), 1) for i in range(B)])
+    be.profile(True)
     out, out_scale = boot.bootstrap_3(keys, pkg.to_device(cts.reshape(B, 2, 1, o.n)), SCALE)
+    prof = be.profile_dump()
+    be.profile(False)
+    # grouped keys: the giant steps stay in the key-switch basis as well (k_giants_sum, one division per stage)
+    assert ("k_giants_sum" in prof) == use_grouped, sorted(prof)
     assert out.shape[2] == 3 and out_scale == SCALE
     res = pkg.to_host(out)
     err = 0.0
