@@ -119,11 +119,22 @@ namespace moai
         // conversion tables of ONE source set (`src` prime indices, grouped by s0 / cnt) into `tgt` prime indices
         struct ConvOffsets
         {
-            size_t s0, cnt, invq, wide, B, B26, Bd, B26d, negQ, negQd;
+            size_t s0, cnt, invq, wide, B, B26, Bd, B26d, negQ, negQd, BT, c32d;
             int src_limbs;
+            bool mma;
         };
+        // the conversion's tensor-core form (ConvTab::BT) needs whole warps in the pass-A CTA (N >= 2^13) and a free
+        // top byte in every group's first source.  OPT-IN (MOAI_CONV_MMA=1, read when a level's tables are first built):
+        // it takes the FP64 pipe from 61-68 % to 18-22 % busy but is issue- / latency-bound in all three variants
+        // measured (relinearize + rescale, 64 ciphertexts at 28 limbs: FP64 products 7.14 ms; fragments straight from
+        // global memory 2x slower; cp.async staging 8.22 ms; bulk copies + mbarriers 10.06 ms — profiles/conv_mma_r2.md)
+        bool conv_mma_enabled(const Context *c)
+        {
+            const char *e = std::getenv("MOAI_CONV_MMA");
+            return e && e[0] == '1' && c->log_n >= 13;
+        }
         ConvOffsets build_conv(const Context *c, Blob &bl, const std::vector<int> &src, const std::vector<int> &s0,
-                               const std::vector<int> &cnt, const std::vector<int> &tgt)
+                               const std::vector<int> &cnt, const std::vector<int> &tgt, bool want_mma = true)
         {
             const int digits = (int)s0.size(), rns = (int)tgt.size();
             std::vector<double> invq(src.size());
@@ -162,7 +173,60 @@ namespace moai
                     negQd[(size_t)g * rns + I] = h_centred(negQ[(size_t)g * rns + I], m);
                 }
             }
+            // B fragments of mma.sync m16n8k32 (u8): k = 8 (source within the k-step) + byte of the residue, n = byte of the
+            // constant C(j, a, I) = 2^(8a) (Q_g / q_j) mod m_I; the v slot (first source, byte 7) holds (-Q_g) mod m_I
+            bool mma = want_mma && conv_mma_enabled(c);
+            for (int g = 0; g < digits; g++)
+            {
+                mma = mma && (c->q[src[s0[g]]] >> 56) == 0;
+            }
+            std::vector<uint32_t> BT(mma ? (size_t)digits * rns * CONV_KSTEPS * 64 : 0, 0u);
+            std::vector<double> c32d(rns, 0.0);
+            for (int I = 0; I < rns; I++)
+            {
+                c32d[I] = h_centred(((u64)1 << 32) % c->q[tgt[I]], c->q[tgt[I]]);
+            }
+            for (int g = 0; mma && g < digits; g++)
+            {
+                for (int I = 0; I < rns; I++)
+                {
+                    const u64 m = c->q[tgt[I]];
+                    u64 cst_tab[CONV_MAX][8];
+                    for (int j = 0; j < cnt[g]; j++)
+                    {
+                        u64 v = B[((size_t)g * rns + I) * CONV_MAX + j];
+                        for (int ab = 0; ab < 8; ab++)
+                        {
+                            cst_tab[j][ab] = v;
+                            v = h_mulmod(v, 256 % m, m);
+                        }
+                    }
+                    cst_tab[0][7] = negQ[(size_t)g * rns + I];
+                    for (int sI = 0; sI < CONV_KSTEPS; sI++)
+                    {
+                        for (int lane = 0; lane < 32; lane++)
+                        {
+                            const int g8 = lane >> 2, c4 = lane & 3;
+                            for (int r = 0; r < 2; r++)
+                            {
+                                uint32_t word = 0;
+                                for (int e = 0; e < 4; e++)
+                                {
+                                    // lane c4 of a quad holds source c4 of the k-step: bytes 0-3 in register 0, 4-7 in 1
+                                    const int j = 4 * sI + c4, ab = 4 * r + e;
+                                    const u64 cst = j < cnt[g] ? cst_tab[j][ab] : 0;
+                                    word |= (uint32_t)((cst >> (8 * g8)) & 0xFF) << (8 * e);
+                                }
+                                BT[((((size_t)g * rns + I) * CONV_KSTEPS + sI) * 32 + lane) * 2 + r] = word;
+                            }
+                        }
+                    }
+                }
+            }
             ConvOffsets o;
+            o.mma = mma;
+            o.BT = bl.put(BT);
+            o.c32d = bl.put(c32d);
             o.s0 = bl.put(s0);
             o.cnt = bl.put(cnt);
             o.invq = bl.put(invq);
@@ -190,6 +254,8 @@ namespace moai
             t.negQ = reinterpret_cast<const u64 *>(base + o.negQ);
             t.negQd = reinterpret_cast<const double *>(base + o.negQd);
             t.src_limbs = o.src_limbs;
+            t.BT = o.mma ? reinterpret_cast<const uint32_t *>(base + o.BT) : nullptr;
+            t.c32d = reinterpret_cast<const double *>(base + o.c32d);
             return t;
         }
 
@@ -245,7 +311,7 @@ namespace moai
             }
             Blob bl;
             const size_t o_ids = bl.put(ids);
-            const ConvOffsets o_dec = build_conv(c, bl, src_dec, s0, cnt, ids);
+            const ConvOffsets o_dec = build_conv(c, bl, src_dec, s0, cnt, ids, /*want_mma=*/k > 0);
             // y_J = c_J * prod(E) * (Q_g / q_J)^-1 mod q_J
             std::vector<Twiddle> yconst(limbs);
             for (int g = 0; g < t->digits; g++)
@@ -639,6 +705,10 @@ namespace moai
         // y_J = c_J * prod(E) (Q_g / q_J)^-1: the constant rides on the inverse transform's N^-1
         ntt_inverse_from(c, target, limbs, target_stride ? target_stride / (long long)n : limbs, d.as<u64>(), batch * limbs,
                          c->d_ids, limbs, 1, t.d_yscale);
+        if (t.dec.BT)
+        {
+            conv_quotient(c, d.as<u64>(), batch, t.dec, t.digits);
+        }
         NttPrologue pro;
         pro.src = d.as<u64>();
         pro.mode = 3;
@@ -675,6 +745,10 @@ namespace moai
         Scratch r((size_t)polys * np * n * sizeof(u64), c->stream);
         ntt_inverse_from(c, acc + (size_t)targets * n, np, t.rns, r.as<u64>(), polys * np, t.d_ids + targets, np, 1,
                          t.d_zscale_r);
+        if (t.mdr.BT)
+        {
+            conv_quotient(c, r.as<u64>(), polys, t.mdr, 1);
+        }
         Scratch u((size_t)polys * targets * n * sizeof(u64), c->stream);
         NttPrologue pro;
         pro.src = r.as<u64>();
@@ -708,6 +782,10 @@ namespace moai
         Scratch r((size_t)polys * np * n * sizeof(u64), c->stream);
         ntt_inverse_from(c, acc + (size_t)limbs * n, np, rns_in, r.as<u64>(), polys * np, t.d_ids + limbs, np, 1,
                          t.d_zscale);
+        if (t.md.BT)
+        {
+            conv_quotient(c, r.as<u64>(), polys, t.md, 1);
+        }
         Scratch u((size_t)polys * limbs * n * sizeof(u64), c->stream);
         NttPrologue pro;
         pro.src = r.as<u64>();

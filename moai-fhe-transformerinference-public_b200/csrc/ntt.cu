@@ -642,8 +642,19 @@ namespace moai
 #pragma unroll
                 for (int k = 0; k < 16; k++)
                 {
-                    const u64 y = sj[(size_t)k * row_stride];
-                    vs[k] = __fma_rn(conv_y_double(y, wide), iq, vs[k]);
+                    u64 y = sj[(size_t)k * row_stride];
+                    if (cv.BT) // conv_quotient() left v in byte 7 of the first source
+                    {
+                        if (j == 0)
+                        {
+                            vs[k] = (double)(y >> 56);
+                            y &= 0x00FFFFFFFFFFFFFFull;
+                        }
+                    }
+                    else
+                    {
+                        vs[k] = __fma_rn(conv_y_double(y, wide), iq, vs[k]);
+                    }
                     mac_wide(acc[k], y, bj);
                 }
             }
@@ -658,10 +669,225 @@ namespace moai
             (void)f;
         }
 
+        __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+        {
+            const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+        }
+        __device__ __forceinline__ void cp_async_commit()
+        {
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        __device__ __forceinline__ void cp_async_wait_1()
+        {
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        }
+
+        // ---- the conversion on the tensor cores (ConvTab::BT, ntt.cuh) ----------------------------------------------
+        __device__ __forceinline__ void mma_u8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+        {
+            asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+        }
+
+        // CTA tile = R rows x 16 columns; one m16 tile = the 16 columns of one row (mma row g <-> column 2g, row g + 8 <->
+        // column 2g + 1, and lane c of a quad holds source c of the k-step: one 16-byte shared-memory read is a whole A
+        // fragment).  Four phases of R/4 rows; per phase and k-step (four sources) every thread issues ONE 128-byte bulk
+        // copy (cp.async.bulk -> mbarrier; a row of a source) into a ring of CONV_NBUF staging buffers, so CONV_NBUF - 1
+        // stages of loads are always in flight.  The warps leave four 32-bit partial sums per coefficient
+        // (P_c = S_2c + 2^8 S_2c+1, weight 2^16c) in four swizzled planes and every thread recombines its own 4
+        // coefficients of the phase:   x = red( (P0 + 2^16 P1) + [(P2 + 2^16 P3) * (2^32 mod m)] ).
+        // srcb = first source limb of the group, at this tile's first column.
+        // Shared memory (dynamic): staging ring | planes R x 64 B | mbarriers; the ring's first R x 128 B are the
+        // transpose buffer of the stages that follow.  Source jj of a buffer is skewed by 32 jj bytes (bank spread).
+        constexpr int CONV_NBUF = 3;
+        template <int LOGR>
+        __host__ __device__ constexpr int conv_stage_bytes()
+        {
+            return 4 * ((1 << LOGR) / 4 * 128 + 32);
+        }
+        template <int LOGR>
+        __host__ __device__ constexpr int conv_mma_smem()
+        {
+            return CONV_NBUF * conv_stage_bytes<LOGR>() + (1 << LOGR) * 64 + 8 * CONV_NBUF;
+        }
+        __device__ __forceinline__ unsigned smem_u32(const void *p)
+        {
+            return (unsigned)__cvta_generic_to_shared(p);
+        }
+        __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+        {
+            unsigned done = 0;
+            while (!done)
+            {
+                asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+                             "selp.b32 %0, 1, 0, P1;\n\t}"
+                             : "=r"(done)
+                             : "r"(bar), "r"(parity)
+                             : "memory");
+            }
+        }
+        template <int LOGR, bool WIDE>
+        __device__ __forceinline__ void conv_prologue_mma(const FpField<WIDE> &f, const NttArgs &a, double (&x)[16],
+                                                          const u64 *srcb, int g, int I, int rns, unsigned char *smem, int t,
+                                                          int tb)
+        {
+            constexpr int R = 1 << LOGR, T1 = R / 16, QR = R / 4, PLANE = QR * 16, SRC_B = QR * 128 + 32,
+                          STAGE_B = conv_stage_bytes<LOGR>();
+            const ConvTab &cv = a.conv;
+            const int cnt = cv.cnt[g];
+            const int ksteps = (cnt + 3) >> 2;
+            const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+            const int g8 = lane >> 2, c4 = lane & 3;
+            uint32_t *planes = reinterpret_cast<uint32_t *>(smem + CONV_NBUF * STAGE_B);
+            const unsigned bar0 = smem_u32(smem + CONV_NBUF * STAGE_B + R * 64);
+            if (tid == 0)
+            {
+#pragma unroll
+                for (int i = 0; i < CONV_NBUF; i++)
+                {
+                    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * i));
+                }
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncthreads();
+            uint32_t bf[CONV_KSTEPS][2];
+            {
+                const uint32_t *bt = cv.BT + ((((size_t)g * rns + I) * CONV_KSTEPS) * 32 + lane) * 2;
+#pragma unroll
+                for (int s = 0; s < CONV_KSTEPS; s++)
+                {
+                    bf[s][0] = s < ksteps ? __ldg(bt + s * 64) : 0u;
+                    bf[s][1] = s < ksteps ? __ldg(bt + s * 64 + 1) : 0u;
+                }
+            }
+            const double c32 = cv.c32d[I];
+            const int n_stages = 4 * ksteps; // stage u = (phase u / ksteps, k-step u % ksteps), buffer u % CONV_NBUF
+            // this thread's row of a stage: source tid / QR of the k-step, row tid % QR of the phase
+            const int my_jj = tid / QR, my_rr = tid % QR;
+            const u64 *my_src = srcb + (size_t)my_rr * 256;
+            const unsigned my_dst = smem_u32(smem) + my_jj * SRC_B + my_rr * 128;
+            int iu = 0, ip = 0, is = 0, ib = 0; // next stage to issue: index, phase, k-step, buffer
+            auto issue = [&]() {
+                const int j = 4 * is + my_jj;
+                const unsigned bar = bar0 + 8 * ib;
+                if (tid == 0)
+                {
+                    const int nvalid = cnt - 4 * is < 4 ? cnt - 4 * is : 4;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nvalid * QR * 128)
+                                 : "memory");
+                }
+                if (j < cnt)
+                {
+                    const u64 *src = my_src + ((size_t)j << a.log_n) + (size_t)ip * (QR * 256);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(my_dst + ib * STAGE_B), "l"(src), "r"(128), "r"(bar)
+                                 : "memory");
+                }
+                iu++;
+                if (++is == ksteps)
+                {
+                    is = 0;
+                    ip++;
+                }
+                if (++ib == CONV_NBUF)
+                {
+                    ib = 0;
+                }
+            };
+            for (int i = 0; i < CONV_NBUF - 1 && iu < n_stages; i++)
+            {
+                issue();
+            }
+            int acc[8][4];
+            int p = 0, sI = 0, cb = 0;
+            unsigned cpar = 0; // parity of the current buffer's mbarrier phase
+            const unsigned char *frag = smem + c4 * SRC_B + (warp * 8) * 128 + g8 * 16;
+            for (int u = 0; u < n_stages; u++)
+            {
+                if (iu < n_stages)
+                {
+                    issue(); // into the buffer every thread finished reading before the last __syncthreads
+                }
+                mbar_wait(bar0 + 8 * cb, cpar);
+                if (sI == 0)
+                {
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                    {
+                        acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0;
+                    }
+                }
+                uint32_t bb0 = bf[0][0], bb1 = bf[0][1];
+#pragma unroll
+                for (int s2 = 1; s2 < CONV_KSTEPS; s2++)
+                {
+                    if (sI == s2)
+                    {
+                        bb0 = bf[s2][0];
+                        bb1 = bf[s2][1];
+                    }
+                }
+                // sources beyond cnt: their B rows are zero, whatever the staging buffer still holds there
+                const unsigned char *fb = frag + cb * STAGE_B;
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                {
+                    const uint4 w = *reinterpret_cast<const uint4 *>(fb + i * 128);
+                    const uint32_t af[4] = { w.x, w.z, w.y, w.w };
+                    mma_u8(acc[i], af, bb0, bb1);
+                }
+                if (sI == ksteps - 1)
+                {
+                    uint32_t *pl = planes + c4 * PLANE;
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                    {
+                        const int rr = warp * 8 + i;
+                        uint2 v;
+                        v.x = (uint32_t)acc[i][0] + ((uint32_t)acc[i][1] << 8);
+                        v.y = (uint32_t)acc[i][2] + ((uint32_t)acc[i][3] << 8);
+                        *reinterpret_cast<uint2 *>(pl + ((rr * 16 + 2 * g8) ^ (8 * c4))) = v;
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                    {
+                        const int idx = (t + T1 * k) * 16 + tb; // row t + T1 (4 p + k) - p QR
+                        const u64 p0 = planes[idx], p1 = planes[PLANE + (idx ^ 8)], p2 = planes[2 * PLANE + (idx ^ 16)],
+                                  p3 = planes[3 * PLANE + (idx ^ 24)];
+                        const double lo = f.in_outer(p0 + (p1 << 16)), hi = f.in_outer(p2 + (p3 << 16));
+                        const double v = f.red(__dadd_rn(lo, f.mul_lazy(hi, c32)));
+#pragma unroll
+                        for (int pp = 0; pp < 4; pp++)
+                        {
+                            if (pp == p)
+                            {
+                                x[4 * pp + k] = v;
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                if (++sI == ksteps)
+                {
+                    sI = 0;
+                    p++;
+                }
+                if (++cb == CONV_NBUF)
+                {
+                    cb = 0;
+                    cpar ^= 1;
+                }
+            }
+        }
+
         template <int LOGR>
         __global__ void __launch_bounds__((1 << LOGR) / 16 * TB) ntt_fwd_pass_a_conv(NttArgs a, const Twiddle *two64)
         {
-            __shared__ u64 sm[(1 << LOGR) * TB];
+            extern __shared__ __align__(16) unsigned char conv_smem[]; // R x 128 B, or conv_mma_smem (ConvTab::BT)
+            u64 *sm = reinterpret_cast<u64 *>(conv_smem);
             constexpr int T1 = (1 << LOGR) / 16;
             const int tb = threadIdx.x & (TB - 1), t = threadIdx.x >> 4;
             const long long poly = blockIdx.x / (256 / TB);
@@ -680,18 +906,47 @@ namespace moai
             const u64 *src0 = a.src + (((size_t)b * a.conv.src_limbs + a.conv.s0[g]) << a.log_n) + (size_t)t * 256 +
                               tile * TB + tb;
             const size_t row_stride = (size_t)T1 * 256;
+            const u64 *srcb = a.src + (((size_t)b * a.conv.src_limbs + a.conv.s0[g]) << a.log_n) + tile * TB;
             if (lc.fp_class == 1)
             {
                 const FpField<false> f(a, limb, lc);
                 double x[16];
-                conv_prologue(f, a, x, src0, row_stride, g, I, a.period);
+                if constexpr (LOGR >= 5)
+                {
+                    if (a.conv.BT)
+                    {
+                        conv_prologue_mma<LOGR>(f, a, x, srcb, g, I, a.period, conv_smem, t, tb);
+                    }
+                    else
+                    {
+                        conv_prologue(f, a, x, src0, row_stride, g, I, a.period);
+                    }
+                }
+                else
+                {
+                    conv_prologue(f, a, x, src0, row_stride, g, I, a.period);
+                }
                 fwd_pass_a_stages<LOGR>(f, x, base, sm, t, tb);
             }
             else if (lc.fp_class == 2)
             {
                 const FpField<true> f(a, limb, lc);
                 double x[16];
-                conv_prologue(f, a, x, src0, row_stride, g, I, a.period);
+                if constexpr (LOGR >= 5)
+                {
+                    if (a.conv.BT)
+                    {
+                        conv_prologue_mma<LOGR>(f, a, x, srcb, g, I, a.period, conv_smem, t, tb);
+                    }
+                    else
+                    {
+                        conv_prologue(f, a, x, src0, row_stride, g, I, a.period);
+                    }
+                }
+                else
+                {
+                    conv_prologue(f, a, x, src0, row_stride, g, I, a.period);
+                }
                 fwd_pass_a_stages<LOGR>(f, x, base, sm, t, tb);
             }
             else
@@ -723,20 +978,6 @@ namespace moai
         constexpr int KS_SM_ROWS = FR * ROW_PAD * 8, KS_SM_TW2 = FT * 8 * 16, KS_SM_TW1 = FR * 16 * 8,
                       KS_SM_KEYS = FT * 16 * 16;
         constexpr int KS_FUSED_SMEM = KS_SM_ROWS + KS_SM_TW2 + KS_SM_TW1 + KS_SM_KEYS; // 67584 B: 3 CTAs / SM
-
-        __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
-        {
-            const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
-        }
-        __device__ __forceinline__ void cp_async_commit()
-        {
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        }
-        __device__ __forceinline__ void cp_async_wait_1()
-        {
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        }
 
         struct KsFusedArgs
         {
@@ -1335,7 +1576,15 @@ namespace moai
                 const long long ctas_a = a.count * (256 / TB);
                 if (a.src_mode == 3)
                 {
-                    ntt_fwd_pass_a_conv<LOGR><<<(unsigned)ctas_a, (1 << LOGR) / 16 * TB, 0, s>>>(a, c->d_two64);
+                    constexpr int smem_max = LOGR >= 5 ? conv_mma_smem<LOGR>() : (1 << LOGR) * TB * 8;
+                    static const bool attr_set = [] {
+                        MOAI_CUDA_CHECK(cudaFuncSetAttribute(ntt_fwd_pass_a_conv<LOGR>,
+                                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+                        return true;
+                    }();
+                    (void)attr_set;
+                    const int smem = a.conv.BT ? smem_max : (1 << LOGR) * TB * 8;
+                    ntt_fwd_pass_a_conv<LOGR><<<(unsigned)ctas_a, (1 << LOGR) / 16 * TB, smem, s>>>(a, c->d_two64);
                 }
                 else
                 {
@@ -1382,6 +1631,52 @@ namespace moai
             ntt_inv_pass_a<LOGR><<<(unsigned)ctas_a, (1 << LOGR) / 16 * TB, 0, s>>>(a);
         }
     } // namespace
+
+    namespace
+    {
+        // v = rint(sum_j y_j / q_j) of every (item, digit, coefficient), written into byte 7 of the digit's first source
+        __global__ void k_conv_quot(ulonglong2 *src, long long total2, int log_n2, int digits, int src_limbs, ConvTab cv)
+        {
+            const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; // over [batch][digits][n/2]
+            if (i >= total2)
+            {
+                return;
+            }
+            const long long within = i & (((long long)1 << log_n2) - 1);
+            const long long bg = i >> log_n2;
+            const int g = (int)(bg % digits);
+            const long long b = bg / digits;
+            const int s0 = cv.s0[g], cnt = cv.cnt[g];
+            ulonglong2 *p0 = src + (((b * src_limbs + s0) << log_n2) + within);
+            double vx = 0.0, vy = 0.0;
+            ulonglong2 first = *p0;
+            for (int j = 0; j < cnt; j++)
+            {
+                const ulonglong2 y = j == 0 ? first : p0[(long long)j << log_n2];
+                const double iq = cv.invq[s0 + j];
+                const bool wide = cv.wide[s0 + j] != 0;
+                vx = __fma_rn(conv_y_double(y.x, wide), iq, vx);
+                vy = __fma_rn(conv_y_double(y.y, wide), iq, vy);
+            }
+            first.x |= (u64)__double2ll_rn(conv_rint(vx)) << 56;
+            first.y |= (u64)__double2ll_rn(conv_rint(vy)) << 56;
+            *p0 = first;
+        }
+    } // namespace
+
+    void conv_quotient(Context *c, u64 *src, long long batch, const ConvTab &tab, int digits)
+    {
+        const long long total2 = batch * digits * (long long)(c->n / 2);
+        if (!total2)
+        {
+            return;
+        }
+        KernelTimer kt(c, "k_conv_quot", 1);
+        k_conv_quot<<<(unsigned)((total2 + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<ulonglong2 *>(src), total2,
+                                                                             c->log_n - 1, digits, tab.src_limbs, tab);
+        c->launches += 1;
+        MOAI_CUDA_CHECK(cudaGetLastError());
+    }
 
     bool ntt_forward(Context *c, u64 *data, long long count, const int *d_limb_ids, int period, int div,
                      const NttPrologue *pro, int passes, const FinishEpi *fin)

@@ -54,7 +54,20 @@ namespace moai
         // times a constant): the fused key-switch kernel takes that product directly and the polynomial is skipped
         const int *own = nullptr;
         int src_limbs = 0;
+        // Tensor-core form of the conversion (FP64-path targets, N >= 2^13; nullptr: FP64 products as above).
+        // The sum over sources is a u8 x u8 GEMM with a constant right-hand side: K = the 8 bytes of every source
+        // residue, N = the 8 bytes of  C(j, a, I) = 2^(8a) (Q_g / q_j) mod m_I,  M = coefficients;
+        //     sum_j y_j B_jI  ==  sum_b 2^(8b) sum_(j,a) y_(j,a) C(j, a, I)_b    (mod m_I)
+        // so the FP64 pipe only recombines four 32-bit partial sums per coefficient (one exact product) instead of
+        // doing 9 operations per source.  v = rint(sum_j y_j / q_j) is computed ONCE per coefficient by conv_quotient()
+        // into byte 7 of the group's first source (free: residues are below 2^56) and rides in the GEMM with the
+        // constant (-Q_g) mod m_I.  BT: mma.sync m16n8k32 B fragments, [digits][rns][CONV_KSTEPS][32 lanes][2].
+        const uint32_t *BT = nullptr;
+        const double *c32d = nullptr; // [rns] centred 2^32 mod m_I
     };
+    constexpr int CONV_KSTEPS = CONV_MAX / 4; // four sources (32 bytes) per mma k-step
+    // writes v into byte 7 of every group's first source limb of src [batch][src_limbs][n] (once, before the transform)
+    void conv_quotient(Context *c, u64 *src, long long batch, const ConvTab &tab, int digits);
 
     // Optional constant folded into the inverse transform: the last stage multiplies by N^-1 (and by the last root);
     // with scale[slot] it multiplies by c * N^-1 instead, so "INTT then scale by a per-limb constant" is one pass

@@ -132,6 +132,67 @@ def test_merged_relinearize_rescale(pkg, env):
         print("merged relin+rescale limbs", limbs, "k", k, "err", np.abs(dg - zx * zy).max(), "exact", np.abs(de - zx * zy).max())
 
 
+@pytest.fixture(scope="module", params=["0", "1"], ids=["fp64", "mma"])
+def env13(pkg, request):
+    """N = 2^13 with the base conversion as FP64 products (default) and as the opt-in tensor-core GEMM (MOAI_CONV_MMA=1,
+    read when a level's conversion tables are first built, i.e. per context)."""
+    import os
+    from oracle import Oracle
+    old = os.environ.get("MOAI_CONV_MMA")
+    os.environ["MOAI_CONV_MMA"] = request.param
+    o = Oracle(13, BITS)
+    be = pkg.Backend(13, o.q)
+    sk = o.gen_secret(3, hamming_weight=64)
+    yield o, be, sk
+    if old is None:
+        os.environ.pop("MOAI_CONV_MMA", None)
+    else:
+        os.environ["MOAI_CONV_MMA"] = old
+
+
+@pytest.mark.parametrize("limbs,k,key_limbs", [(15, 2, 15), (9, 5, 12), (9, 8, 9), (3, 1, 16), (12, 3, 14)])
+def test_conversion_on_tensor_cores(pkg, env13, limbs, k, key_limbs):
+    """From N = 2^13 on the base conversions of the grouped key switch (digit extension, mod-down) run as a u8 GEMM on
+    the tensor cores (ConvTab::BT, csrc/ntt.cuh; 1, 2 and 3 k-steps of four sources here).  Same integers as the FP64
+    products, so the decrypted rotation / relinearisation must match the SEAL-exact operation as at N = 2^12 (1e-6),
+    hoisted and un-hoisted rotations agree bit for bit, and so does the merged relinearize + rescale."""
+    o, be, sk = env13
+    import os
+    mma = os.environ.get("MOAI_CONV_MMA") == "1"
+    be.profile(True)
+    rng = np.random.default_rng(limbs * 10 + k)
+    steps = [1, 64, o.n // 2 - 3]
+    zs, cts = encrypt_batch(o, sk, rng, 2, limbs)
+    d = pkg.to_device(cts)
+    exact, grouped = {}, {}
+    for i, st in enumerate(steps):
+        e = o.elt_from_step(st)
+        kk = pkg.to_device(o.gen_galois_key(sk, 400 + i, e).reshape(o.kl - 1, 2, o.kl, o.n))
+        exact[e] = kk
+        grouped[e] = [be.key_prepare_grouped(kk, e, key_limbs, k_extra=k)]
+    k_exact = be.make_keys(galois=exact)
+    relin = pkg.to_device(o.gen_relin_key(sk, 5))
+    grouped[0] = [be.key_prepare_grouped(relin.reshape(o.kl - 1, 2, o.kl, o.n), 0, key_limbs, k_extra=k, pre_permute=False)]
+    k_grp = be.make_keys(grouped=grouped)
+    many = be.rotate_many(k_grp, d, steps)
+    for i, st in enumerate(steps):
+        single = be.rotate_vector_keys(k_grp, d, st)
+        assert (single == many[i]).all()
+        got = decrypt_batch(o, sk, pkg, many[i])
+        want = np.roll(zs, -st, axis=1)
+        assert np.abs(got - want).max() < 1e-6, (st, np.abs(got - want).max())
+    zy, cy = encrypt_batch(o, sk, rng, 2, limbs)
+    prod3 = be.multiply(d, pkg.to_device(cy))
+    if limbs >= 2:
+        merged = be.relin_rescale_keys(k_grp, prod3)
+        sc = SCALE * SCALE / float(o.q[limbs - 1])
+        err = np.abs(decrypt_batch(o, sk, pkg, merged, sc) - zs * zy).max()
+        assert err < 1e-6, err
+    prof = be.profile_dump()
+    be.profile(False)
+    assert ("k_conv_quot" in prof) == mma, sorted(prof)   # the variant under test is the one that ran
+
+
 def test_bootstrap_grouped(pkg, env):
     """The whole bootstrapping on grouped keys (every Galois key prepared for the level it is used at, the
     relinearisation key in several variants): same tolerance as the SEAL-key pipeline, 2e-3 max-abs."""

@@ -16,7 +16,7 @@ import bench  # noqa: E402
 def main():
     import torch
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["gelu", "relin", "rotate", "rescale"])
+    ap.add_argument("what", choices=["gelu", "relin", "relin_rescale", "rotate", "rescale"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--limbs", type=int, default=9)
     ap.add_argument("--iters", type=int, default=3)
@@ -60,6 +60,9 @@ def main():
     elif args.what == "relin":
         x = rand_ct(3, args.limbs)
         run = lambda: be.relinearize_keys(keys, x)
+    elif args.what == "relin_rescale":
+        x = rand_ct(3, args.limbs)
+        run = lambda: be.relin_rescale_keys(keys, x)
     elif args.what == "rescale":
         x = rand_ct(2, args.limbs)
         run = lambda: be.rescale_to_next(x)
