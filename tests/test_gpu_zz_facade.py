@@ -126,6 +126,19 @@ def test_bootstrapper_facade_preserves_message():
     for i in range(3):
         dec = o.decode(o.decrypt(sk, outs[i].reshape(-1), 2, 3), 3, scale)
         assert np.abs(dec - vs[i]).max() < 2e-3, (i, np.abs(dec - vs[i]).max())
+    # the request combiner on the device: 12 ciphertexts, one bootstrap_3 call each from an OpenMP loop like the reference's
+    # driver (test_full_scheme.hpp:654-660); concurrent callers are collected into batched, paired device calls
+    import os
+    vs = rng.normal(size=(12, o.n // 2)) * 0.1
+    cts = np.stack([o.encrypt_sym(sk, 120 + i, o.encode(vs[i].astype(np.complex128), scale, 1), 1) for i in range(12)])
+    outs, calls = d.boot_combined(cts.reshape(-1), 12, scale, max_limbs=3, real_slots=True, max_batch=64, linger_us=5000)
+    assert outs.shape == (12, 2, 3, o.n) and 1 <= calls <= 12
+    if (os.cpu_count() or 1) >= 4:
+        assert calls < 12, "concurrent bootstrap_3 calls were not combined"
+    for i in range(12):
+        dec = o.decode(o.decrypt(sk, outs[i].reshape(-1), 2, 3), 3, scale)
+        assert np.abs(dec - vs[i]).max() < 2e-3, (i, np.abs(dec - vs[i]).max())
+    print("request combiner on the GPU: 12 bootstrap_3 calls from an OpenMP loop -> %d device calls" % calls)
     import ctypes as C
     two = np.zeros(2 * 2 * o.n, dtype=np.uint64)
     with pytest.raises(facade.FacadeError, match="lowest level"):
