@@ -990,11 +990,13 @@ namespace moai
             const u64 *direct;      // [batch][n_data][n] or nullptr (see ks_passb_mac)
             const int *own;         // [rns] or nullptr
             int limbs, rns, n_data, key_kl, log_n; // limbs = digits (KsShape, ntt.cuh)
+            long long batch;
+            int items; // ciphertexts per CTA
         };
 
         template <bool WIDE>
         __device__ __forceinline__ void ks_fused_body(const FpField<WIDE> &f, const KsFusedArgs &a, int I, long long b,
-                                                      int rb, unsigned char *smem)
+                                                      int n_items, int rb, unsigned char *smem)
         {
             const int tid = threadIdx.x, t = tid & 15, r = tid >> 4;
             const int R = 1 << (a.log_n - 8);
@@ -1006,13 +1008,18 @@ namespace moai
             ulonglong2 *kst = reinterpret_cast<ulonglong2 *>(smem + KS_SM_ROWS + KS_SM_TW2 + KS_SM_TW1) + tid;
 
             const int key_limb = I < a.n_data ? I : I + a.key_kl - a.rns;
-            const u64 *mid0 = a.mid + (((size_t)b * a.rns + I) * a.limbs << a.log_n) + (size_t)row * 256;
             const u64 *key0 = a.ksk + ((size_t)key_limb << a.log_n) + (size_t)row * 256 + 16 * t;
             const size_t key_poly = (size_t)a.key_kl << a.log_n; // stride between key[J][0] and key[J][1]
+            const int own = a.own ? a.own[I] : -1; // digit taken from a.direct instead of being transformed
+            const int digits = a.limbs;
+            // digit order within an item: the direct one first, the others in order
+            auto digit_at = [&](int i) { return own < 0 ? i : (i == 0 ? own : (i <= own ? i - 1 : i)); };
 
-            // the row's 256 residues of digit J, natural order, 16 bytes per copy (coalesced)
-            auto issue_data = [&](int J) {
-                const u64 *src = mid0 + ((size_t)J << a.log_n);
+            // the row's 256 residues of digit J of item bb, natural order, 16 bytes per copy (coalesced).  The digit a
+            // target owns comes from a.direct (prod(E) * c_I in NTT form: no transform) through the same tile.
+            auto issue_data = [&](long long bb, int J) {
+                const u64 *src = J == own ? a.direct + (((size_t)bb * a.n_data + I) << a.log_n) + (size_t)row * 256
+                                          : a.mid + ((((size_t)bb * a.rns + I) * digits + J) << a.log_n) + (size_t)row * 256;
 #pragma unroll
                 for (int j = 0; j < 8; j++)
                 {
@@ -1028,19 +1035,13 @@ namespace moai
                     cp_async16(kst + (8 + u) * FT, src + key_poly + 2 * u);
                 }
             };
-            const int own = a.own ? a.own[I] : -1; // digit taken from a.direct instead of being transformed
-            // digit order: the direct one first (its plain loads then overlap the twiddle loads below), the others in order
-            auto digit_at = [&](int i) { return own < 0 ? i : (i == 0 ? own : (i <= own ? i - 1 : i)); };
-            if (own < 0)
-            {
-                issue_data(0);
-            }
+            issue_data(b, digit_at(0));
             cp_async_commit();
             issue_keys(digit_at(0));
             cp_async_commit();
 
-            // twiddles, loaded once for all digits: the 15 row-uniform ones of the first four stages
-            // (tw1: [0] = 2^0 block, [1..2], [3..6], [7..14]) and this thread's 15 of the last four
+            // twiddles, loaded once for all digits AND all items of this CTA: the 15 row-uniform ones of the first four
+            // stages (tw1: [0] = 2^0 block, [1..2], [3..6], [7..14]) and this thread's 15 of the last four
             if (t < 15)
             {
                 const int lvl = t == 0 ? 0 : (t < 3 ? 1 : (t < 7 ? 2 : 3));
@@ -1073,39 +1074,29 @@ namespace moai
             auto key_d = [&](u64 v) { return f.in_outer(v); };
             const int red_every = WIDE ? 2 : 8; // |acc| <= 0.5 p + 8 * 0.65 p  /  0.5 p + 2 * 1.125 p
 
-            for (int it = 0; it < a.limbs; it++)
+            // (item, digit) steps of this CTA flattened into one software pipeline: the next step's row tile and key tiles
+            // are in flight while the current one computes, across item boundaries too
+            long long bb = b;
+            int it = 0;
+            const long long total = (long long)n_items * digits;
+            for (long long sq = 0; sq < total; sq++)
             {
-                const int J = digit_at(it), Jn = digit_at(it + 1);
+                const int J = digit_at(it);
+                const bool last_digit = it + 1 == digits;
+                const long long bn = last_digit ? bb + 1 : bb;
+                const int Jn = digit_at(last_digit ? 0 : it + 1);
+                const bool more = sq + 1 < total;
                 double x[16];
                 cp_async_wait_1(); // data(J) has landed (keys(J) may still be in flight)
-                if (J == own)
-                {
-                    // NTT_I(D_J mod q_I) = prod(E) * c_I is the input limb itself: no transform
-                    const ulonglong2 *dp = reinterpret_cast<const ulonglong2 *>(
-                        a.direct + (((size_t)b * a.n_data + I) << a.log_n) + (size_t)row * 256 + 16 * t);
-#pragma unroll
-                    for (int k = 0; k < 16; k += 2)
-                    {
-                        const ulonglong2 v = __ldg(dp + (k >> 1));
-                        x[k] = f.red(f.in_outer(v.x));
-                        x[k + 1] = f.red(f.in_outer(v.y));
-                    }
-                    if (it + 1 < a.limbs)
-                    {
-                        issue_data(Jn); // the row tile is idle
-                    }
-                    cp_async_commit();
-                }
-                else
-                {
                 __syncwarp();      // a row is half a warp: its 16 threads' copies are now visible to each other
 #pragma unroll
                 for (int k = 0; k < 16; k++)
                 {
                     x[k] = srow[t + 16 * k];
                 }
-                f.phase_begin_fwd(x);
+                if (J != own)
                 {
+                    f.phase_begin_fwd(x);
                     const double2 w0 = tw1[0], w1 = tw1[1], w2 = tw1[2], w3 = tw1[3], w4 = tw1[4], w5 = tw1[5],
                                   w6 = tw1[6], w7 = tw1[7];
                     const double t8[1] = { w0.x };
@@ -1131,13 +1122,14 @@ namespace moai
                     x[k] = srow[17 * t + k];
                 }
                 __syncwarp();
-                if (it + 1 < a.limbs)
+                if (more)
                 {
-                    issue_data(Jn); // lands in the row tile while the last stages and the MAC run
+                    issue_data(bn, Jn); // lands in the row tile while the last stages and the MAC run
                 }
                 cp_async_commit();
-                f.phase_begin_fwd(x);
+                if (J != own)
                 {
+                    f.phase_begin_fwd(x);
                     const double2 a0 = tws[0 * FT], a1 = tws[1 * FT], a2 = tws[2 * FT], a3 = tws[3 * FT];
                     const double2 b0 = tws[4 * FT], b1 = tws[5 * FT], c0 = tws[6 * FT], d0 = tws[7 * FT];
                     const double t8[1] = { d0.x };
@@ -1149,16 +1141,24 @@ namespace moai
                     f.phase_mid_fwd(x);
                     ct_stage_tw<2>(f, x, t2);
                     ct_stage_tw<1>(f, x, t1);
+                    if (WIDE)
+                    {
+#pragma unroll
+                        for (int k = 0; k < 16; k++)
+                        {
+                            x[k] = f.red(x[k]); // multiplier input below 2^52
+                        }
+                    }
                 }
-                if (WIDE)
+                else
                 {
+                    // prod(E) * c_I arrives as canonical residues (the bit pattern in_mid / in_outer expect differ)
 #pragma unroll
                     for (int k = 0; k < 16; k++)
                     {
-                        x[k] = f.red(x[k]); // multiplier input below 2^52
+                        x[k] = f.red(f.in_outer((u64)__double_as_longlong(x[k])));
                     }
                 }
-                } // J != own
                 cp_async_wait_1(); // keys(J) have landed
 #pragma unroll
                 for (int u = 0; u < 8; u++)
@@ -1169,40 +1169,53 @@ namespace moai
                     acc1[2 * u] = __dadd_rn(acc1[2 * u], f.mul_lazy(x[2 * u], key_d(k1.x)));
                     acc1[2 * u + 1] = __dadd_rn(acc1[2 * u + 1], f.mul_lazy(x[2 * u + 1], key_d(k1.y)));
                 }
-                if (it + 1 < a.limbs)
+                if (more)
                 {
                     issue_keys(Jn);
                 }
                 cp_async_commit();
-                if ((it + 1) % red_every == 0)
+                if (last_digit)
                 {
+                    u64 *o0 = a.acc + ((((size_t)bb * 2 + 0) * a.rns + I) << a.log_n) + (size_t)row * 256 + 16 * t;
+                    u64 *o1 = a.acc + ((((size_t)bb * 2 + 1) * a.rns + I) << a.log_n) + (size_t)row * 256 + 16 * t;
 #pragma unroll
-                    for (int k = 0; k < 16; k++)
+                    for (int k = 0; k < 16; k += 2)
                     {
-                        acc0[k] = f.red(acc0[k]);
-                        acc1[k] = f.red(acc1[k]);
+                        ulonglong2 v;
+                        v.x = f.canon(acc0[k]);
+                        v.y = f.canon(acc0[k + 1]);
+                        reinterpret_cast<ulonglong2 *>(o0)[k >> 1] = v;
+                        v.x = f.canon(acc1[k]);
+                        v.y = f.canon(acc1[k + 1]);
+                        reinterpret_cast<ulonglong2 *>(o1)[k >> 1] = v;
+                        acc0[k] = acc0[k + 1] = acc1[k] = acc1[k + 1] = 0.0;
                     }
+                    bb++;
+                    it = 0;
                 }
-            }
-            u64 *o0 = a.acc + ((((size_t)b * 2 + 0) * a.rns + I) << a.log_n) + (size_t)row * 256 + 16 * t;
-            u64 *o1 = a.acc + ((((size_t)b * 2 + 1) * a.rns + I) << a.log_n) + (size_t)row * 256 + 16 * t;
+                else
+                {
+                    if ((it + 1) % red_every == 0)
+                    {
 #pragma unroll
-            for (int k = 0; k < 16; k += 2)
-            {
-                ulonglong2 v;
-                v.x = f.canon(acc0[k]);
-                v.y = f.canon(acc0[k + 1]);
-                reinterpret_cast<ulonglong2 *>(o0)[k >> 1] = v;
-                v.x = f.canon(acc1[k]);
-                v.y = f.canon(acc1[k + 1]);
-                reinterpret_cast<ulonglong2 *>(o1)[k >> 1] = v;
+                        for (int k = 0; k < 16; k++)
+                        {
+                            acc0[k] = f.red(acc0[k]);
+                            acc1[k] = f.red(acc1[k]);
+                        }
+                    }
+                    it++;
+                }
             }
         }
 
         __global__ void __launch_bounds__(FT, 3) ks_passb_mac_kernel(KsFusedArgs a, NttArgs na)
         {
             extern __shared__ __align__(16) unsigned char ks_smem[];
-            const long long b = blockIdx.x;
+            // a CTA owns up to a.items consecutive ciphertexts of one (row block, target modulus): twiddles loaded once,
+            // one software pipeline across them (the start-up latency of a 3-digit item is a third of its run time)
+            const long long b = (long long)blockIdx.x * a.items;
+            const int n_items = (int)(a.batch - b < a.items ? a.batch - b : a.items);
             const int rb = blockIdx.y;
             const int I = blockIdx.z;
             const int limb = a.ids_ks[I];
@@ -1210,12 +1223,12 @@ namespace moai
             if (lc.fp_class == 1)
             {
                 const FpField<false> f(na, limb, lc);
-                ks_fused_body<false>(f, a, I, b, rb, ks_smem);
+                ks_fused_body<false>(f, a, I, b, n_items, rb, ks_smem);
             }
             else if (lc.fp_class == 2)
             {
                 const FpField<true> f(na, limb, lc);
-                ks_fused_body<true>(f, a, I, b, rb, ks_smem);
+                ks_fused_body<true>(f, a, I, b, n_items, rb, ks_smem);
             }
             // integer-path moduli (the 58-bit special prime) are handled by the un-fused kernels
         }
@@ -1829,7 +1842,20 @@ namespace moai
         a.log_n = c->log_n;
         NttArgs na{ nullptr, c->d_fwd, c->d_fwd_fp, c->d_limb, nullptr, 1, 1, c->log_n, 0 };
         const int R = 1 << (c->log_n - 8);
-        dim3 grid((unsigned)batch, (unsigned)(R / FR), (unsigned)rns);
+        // ciphertexts per CTA: as many as keep >= 8 waves of CTAs on the GPU (3 CTAs per SM), at most 8
+        static const int items_max = [] {
+            const char *e = getenv("MOAI_KS_ITEMS");
+            return e ? atoi(e) : 8;
+        }();
+        long long items = batch * (R / FR) * rns / ((long long)c->sm_count * 3 * 8);
+        items = items < 1 ? 1 : (items > items_max ? items_max : items);
+        if (limbs >= 12) // long digit loops amortise the start-up by themselves (measured: 17 digits, 9.6 vs 9.95 ms)
+        {
+            items = 1;
+        }
+        a.batch = batch;
+        a.items = (int)items;
+        dim3 grid((unsigned)((batch + items - 1) / items), (unsigned)(R / FR), (unsigned)rns);
         // units: limb-transforms finished inside the kernel (one per (ciphertext, digit, target modulus))
         // (with `direct`, one digit per FP64-path data target needs no transform: n_data of them at most)
         KernelTimer kt(c, "k_ks_passb_mac", batch * ((long long)limbs * rns - (direct ? sh.n_data : 0)));
