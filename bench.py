@@ -446,7 +446,7 @@ def run_layer(args):
         haux = torch.empty(x.shape, dtype=torch.int64)
     hx.copy_(x)
     haux.copy_(aux)
-    boot_chunk = int(os.environ.get("MOAI_BOOT_CHUNK", "32"))
+    boot_chunk = int(os.environ.get("MOAI_BOOT_CHUNK", "64"))
     nbytes = int(x.numel() * 8)
     reads = {0: [(x, hx)], 1: [(x, hx), (aux, haux)], 2: [(x, hx)], 3: [(x, hx), (aux, haux)]}   # stage -> inputs
     writes = {0: (aux, haux), 1: (x, hx), 2: (aux, haux), 3: (x, hx)}                           # stage -> result

@@ -804,6 +804,10 @@ namespace moai
         const size_t per_ct_ws = ext_bytes + (size_t)(acc_slots + G) * acc_words * sizeof(u64);
         long long chunk = std::max<long long>(1, (long long)(ks_ext_budget() / per_ct_ws));
         chunk = std::min<long long>(chunk, ct.batch);
+        {
+            const long long parts = (ct.batch + chunk - 1) / chunk;
+            chunk = (ct.batch + parts - 1) / parts; // equal chunks, no short tail
+        }
         Scratch ext((size_t)chunk * ext_bytes, c->stream);
         Scratch accs((size_t)(layout == KS_SINGLE ? 1 : acc_slots * chunk * acc_words) * sizeof(u64), c->stream);
         Scratch outs((size_t)G * chunk * acc_words * sizeof(u64), c->stream);

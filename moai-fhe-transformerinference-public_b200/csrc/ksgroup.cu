@@ -1067,6 +1067,7 @@ namespace moai
         const size_t per_ext = ksg_ext_bytes_per_ct(c, limbs, k);
         long long chunk = (long long)(ksg_ext_budget_bytes() / per_ext);
         chunk = chunk < 1 ? 1 : (chunk > batch ? batch : chunk);
+        chunk = (batch + (batch + chunk - 1) / chunk - 1) / ((batch + chunk - 1) / chunk); // equal chunks, no short tail
         Scratch ext((size_t)chunk * per_ext, c->stream);
         Scratch acc((size_t)chunk * 2 * t.rns * n * sizeof(u64), c->stream);
         Scratch direct((size_t)chunk * limbs * n * sizeof(u64), c->stream);

@@ -1292,6 +1292,20 @@ namespace moai
             for (long long q = q0; q < q1; q++)
             {
                 double x[16];
+                if (a.fin.out)
+                {
+                    // the epilogue's operands (this thread's 128-byte line of the input limb and of the addend) are
+                    // pulled into L2 now: by the time the 8 stages are done the loads below are L2 hits
+                    const FinishEpi &e = a.fin;
+                    const size_t off = (size_t)row * 256 + 16 * t;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(e.in + (((size_t)q * e.limbs_in + slot) << a.log_n) + off));
+                    if (e.addend && !(e.addend_even_only && (q & 1)))
+                    {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(
+                            e.addend + (((size_t)((q >> 1) * e.addend_group + (q & 1)) *
+                                             (e.addend_limbs ? e.addend_limbs : a.period) + slot) << a.log_n) + off));
+                    }
+                }
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
                 __syncwarp(); // a row is half a warp
 #pragma unroll
