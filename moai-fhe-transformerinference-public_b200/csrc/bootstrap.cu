@@ -951,6 +951,16 @@ namespace moai
         return finish_giants(ev, ct, const_cast<LinearStage &>(st), keys, gi, inner);
     }
 
+    // MOAI_EVALMOD_FOLD=0: remainders and T_{a-b} take their own rescale (the pre-fold schedule)
+    static bool fold_leaves()
+    {
+        static const bool on = [] {
+            const char *e = std::getenv("MOAI_EVALMOD_FOLD");
+            return !(e && e[0] == '0');
+        }();
+        return on;
+    }
+
     // ------------------------------------------------------------------------------------ EvalMod
     // Chebyshev series sum coef[k] T_k evaluated to exactly (target_limbs, target_scale).
     // Recursive division p = q * T_g + r (g the largest giant <= deg p).  The remainder r is evaluated to the same
@@ -991,6 +1001,15 @@ namespace moai
                 acc = ev.lincomb_scalar(terms, cs, lv, target_scale * ql);
             }
             MOAI_REQUIRE(!acc.empty(), "degenerate polynomial leaf");
+            if (!acc3.empty() && fold_leaves())
+            {
+                // the chain's products wait at (lv, target_scale * ql) for their one relinearize + rescale: the remainder
+                // joins them there instead of paying a rescale of its own
+                ev.add_plain_inplace(acc, ev.encode(coef[0], lv, target_scale * ql));
+                ev.add_into3(acc3, acc);
+                rest = Ct();
+                return;
+            }
             Ct r = ev.rescale_to_next(acc);
             r.scale = target_scale;
             rest = ev.add_plain(r, ev.encode(coef[0], r.limbs, target_scale));
@@ -1046,7 +1065,7 @@ namespace moai
         eval_cheb_parts(ev, r, target_limbs, target_scale, T, keys, acc3, rest);
         if (q_const)
         {
-            rest = ev.add(rest, prod2);
+            rest = rest.empty() ? prod2 : ev.add(rest, prod2);
         }
     }
 
@@ -1061,7 +1080,7 @@ namespace moai
         }
         Ct prod = ev.relin_rescale(acc3, keys);
         prod.scale = target_scale;
-        return ev.add(prod, rest);
+        return rest.empty() ? prod : ev.add(prod, rest);
     }
 
     Ct Bootstrapper::eval_mod(const Evaluator &ev, const Ct &y, const Keys &keys) const
@@ -1071,15 +1090,28 @@ namespace moai
         T[1] = y;
         auto dbl_minus_one = [&](const Ct &sq) {
             Ct r = ev.relin_rescale(sq, keys);
-            ev.double_inplace(r);
-            return ev.add_const(r, -1.0);
+            ev.double_add_const_inplace(r, -1.0); // one pass: 2 r - 1
+            return r;
         };
         auto t_even = [&](int a) { return dbl_minus_one(ev.square(T.at(a))); }; // T_2a = 2 T_a^2 - 1
         auto t_sum = [&](int a, int b) {                                       // T_{a+b} = 2 T_a T_b - T_{a-b}, a > b
             Ct ta = T.at(a), tb = T.at(b);
             const int lv = std::min(ta.limbs, tb.limbs);
-            (void)lv;
-            Ct p = ev.relin_rescale(ev.multiply_lowered(ta, tb), keys);
+            Ct prod3 = ev.multiply_lowered(ta, tb);
+            if (fold_leaves())
+            {
+                // 2 (T_a T_b - T_{a-b} / 2): the subtrahend joins the product BEFORE its relinearize + rescale, read at
+                // its own (higher) level with the constant -1/2 encoded at prod.scale / T_{a-b}.scale — instead of the
+                // multiply_const + rescale + mod-switch of sub_reduced_error (S/evaluator.cpp:478-534) afterwards
+                const Ct &td = T.at(a - b);
+                MOAI_REQUIRE(td.limbs >= lv, "level bookkeeping of the Chebyshev basis");
+                Ct half = ev.lincomb_scalar({ td }, { -0.5 }, lv, prod3.scale);
+                ev.add_into3(prod3, half);
+                Ct p = ev.relin_rescale(prod3, keys);
+                ev.double_inplace(p);
+                return p;
+            }
+            Ct p = ev.relin_rescale(prod3, keys);
             ev.double_inplace(p);
             return ev.sub_reduced_error(p, T.at(a - b));
         };

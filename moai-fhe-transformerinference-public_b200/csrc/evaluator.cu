@@ -147,6 +147,19 @@ namespace moai
         ew_addsub(c, EW_ADD, a.d, a.d, a.d, a.batch, a.size, a.limbs, false);
     }
 
+    void Evaluator::double_add_const_inplace(Ct &a, double value) const
+    {
+        const Pt p = encode(value, a.limbs, a.scale);
+        ew_double_add_scalar(c, a.d, p.consts.data(), a.d, a.batch, a.size, a.limbs);
+    }
+
+    void Evaluator::add_into3(Ct &acc3, const Ct &x2) const
+    {
+        check_same(acc3, x2, true);
+        EV_REQUIRE(acc3.size == 3 && x2.size == 2 && acc3.batch == x2.batch, "add_into3 expects sizes 3 and 2");
+        ew_add_into3(c, acc3.d, x2.d, acc3.batch, acc3.limbs);
+    }
+
     Ct Evaluator::sum_batch(const Ct &a) const
     {
         Ct r = alloc(1, a.size, a.limbs, a.scale);

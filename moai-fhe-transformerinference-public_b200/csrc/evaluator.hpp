@@ -218,6 +218,9 @@ namespace moai
         Ct sub_reduced_error(const Ct &a, const Ct &b) const;
         Ct multiply_reduced_error(const Ct &a, const Ct &b, const Keys &k) const;
         void double_inplace(Ct &a) const;
+        // a = 2 a + value (double_inplace + add_const in one pass), and acc3 (size 3) += x2 (size 2)
+        void double_add_const_inplace(Ct &a, double value) const;
+        void add_into3(Ct &acc3, const Ct &x2) const;
 
         // ---- Bootstrapper::modraise_inplace -----------------------------------------------------
         Ct mod_raise(const Ct &a, int limbs_out) const;

@@ -120,7 +120,7 @@ namespace moai
             out[i] = x;
         }
 
-        // mode 0: out = ct * k[l] (all polys);  mode 1: out = ct + k[l] on poly 0
+        // mode 0: out = ct * k[l] (all polys);  mode 1: out = ct + k[l] on poly 0;  mode 2: out = 2 ct (+ k[l] on poly 0)
         // ct and out may alias (add_plain_inplace with a scalar plaintext)
         __global__ void k_scalar(int mode, const ulonglong2 *ct, const Twiddle *__restrict__ consts,
                                  ulonglong2 *out, long long total2, int log_n2, int polys, int limbs,
@@ -142,12 +142,42 @@ namespace moai
                 x.x = mul_shoup(x.x, k.w, k.wq, q);
                 x.y = mul_shoup(x.y, k.w, k.wq, q);
             }
-            else if (p == 0)
+            else
             {
-                x.x = addmod(x.x, k.w, q);
-                x.y = addmod(x.y, k.w, q);
+                if (mode == 2)
+                {
+                    x.x = addmod(x.x, x.x, q);
+                    x.y = addmod(x.y, x.y, q);
+                }
+                if (p == 0)
+                {
+                    x.x = addmod(x.x, k.w, q);
+                    x.y = addmod(x.y, k.w, q);
+                }
             }
             out[i] = x;
+        }
+
+        // acc3[b][p][l][.] += x2[b][p][l][.] for p < 2: a size-2 ciphertext added into a size-3 one (SEAL's add pads the
+        // smaller operand, S/evaluator.cpp:190-212)
+        __global__ void k_add_into3(ulonglong2 *acc3, const ulonglong2 *__restrict__ x2, long long total2, int log_n2, int limbs,
+                                    const LimbConst *__restrict__ lcs)
+        {
+            const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; // over [batch][2][limbs][n/2]
+            if (i >= total2)
+            {
+                return;
+            }
+            const long long lp = i >> log_n2;
+            const int limb = (int)(lp % limbs);
+            const long long bp = lp / limbs, b = bp >> 1, p = bp & 1;
+            const u64 q = lcs[limb].q;
+            ulonglong2 *dst = acc3 + ((((b * 3 + p) * limbs + limb) << log_n2) + (i & (((long long)1 << log_n2) - 1)));
+            const ulonglong2 v = x2[i];
+            ulonglong2 a = *dst;
+            a.x = addmod(a.x, v.x, q);
+            a.y = addmod(a.y, v.y, q);
+            *dst = a;
         }
 
         // out = sum_j in_j * k[j][l]: a linear combination of up to LC_MAX ciphertext batches with per-limb scalar
@@ -734,6 +764,26 @@ namespace moai
                             int limbs)
     {
         scalar_op(c, 0, ct, h_consts, out, batch, polys, limbs);
+    }
+
+    void ew_double_add_scalar(Context *c, const u64 *ct, const u64 *h_consts, u64 *out, long long batch, int polys, int limbs)
+    {
+        scalar_op(c, 2, ct, h_consts, out, batch, polys, limbs);
+    }
+
+    void ew_add_into3(Context *c, u64 *acc3, const u64 *x2, long long batch, int limbs)
+    {
+        const long long total2 = batch * 2 * limbs * (long long)(c->n / 2);
+        if (!total2)
+        {
+            return;
+        }
+        KernelTimer kt(c, "k_addsub", 1);
+        k_add_into3<<<grid_for(total2), EW_THREADS, 0, c->stream>>>(reinterpret_cast<ulonglong2 *>(acc3),
+                                                                    reinterpret_cast<const ulonglong2 *>(x2), total2,
+                                                                    c->log_n - 1, limbs, c->d_limb);
+        c->launches += 1;
+        MOAI_CUDA_CHECK(cudaGetLastError());
     }
 
     void ew_add_scalar(Context *c, const u64 *ct, const u64 *h_consts, u64 *out, long long batch, int polys, int limbs)

@@ -28,6 +28,10 @@ namespace moai
     void ew_multiply_scalar(Context *c, const u64 *ct, const u64 *h_consts, u64 *out, long long batch, int polys,
                             int limbs);
     void ew_add_scalar(Context *c, const u64 *ct, const u64 *h_consts, u64 *out, long long batch, int polys, int limbs);
+    // out = 2 ct (+ consts on poly 0): double_inplace + add_const in one pass
+    void ew_double_add_scalar(Context *c, const u64 *ct, const u64 *h_consts, u64 *out, long long batch, int polys, int limbs);
+    // acc3 (size 3) += x2 (size 2) on the first two polynomials
+    void ew_add_into3(Context *c, u64 *acc3, const u64 *x2, long long batch, int limbs);
     // out = sum_j in[j] * k[j][l] over n_terms <= 8 batches; in[j] has in_limbs[j] >= limbs limbs per polynomial and
     // only its first `limbs` are read; h_consts is [n_terms][limbs] (host)
     void ew_lincomb_scalar(Context *c, int n_terms, const u64 *const *in, const int *in_limbs, const u64 *h_consts,
