@@ -1,3 +1,4 @@
+#include <algorithm>
 #include "ntt.cuh"
 #include "fpfield.cuh"
 #include <cstdlib>
@@ -487,7 +488,7 @@ namespace moai
             const int R = 1 << (a.log_n - 8);
             const size_t n = (size_t)1 << a.log_n;
             const int ctas_per_poly = R / ROWS;
-            const long long poly = blockIdx.x / ctas_per_poly;
+            const long long poly = a.p_base + blockIdx.x / ctas_per_poly;
             const int row = (blockIdx.x % ctas_per_poly) * ROWS + r;
             const int limb = a.limb_ids[(poly / a.div) % a.period];
             const LimbConst lc = a.limb[limb];
@@ -508,7 +509,7 @@ namespace moai
             __shared__ u64 sm[(1 << LOGR) * TB];
             const int tb = threadIdx.x & (TB - 1), t = threadIdx.x >> 4;
             const size_t n = (size_t)1 << a.log_n;
-            const long long poly = blockIdx.x / (256 / TB);
+            const long long poly = a.p_base + blockIdx.x / (256 / TB);
             const int tile = blockIdx.x % (256 / TB);
             const int slot = (int)((poly / a.div) % a.period);
             const int limb = a.limb_ids[slot];
@@ -1649,13 +1650,30 @@ namespace moai
             return fin_applied;
         }
 
+        // The two passes run over chunks small enough for pass B's output to still be in L2 when pass A reads it
+        // (MOAI_NTT_L2_LIMBS polynomials per chunk, default 96 = 48 MiB at N = 65536; 0 = one launch pair)
         template <int LOGR>
-        void launch_inv(const NttArgs &a, cudaStream_t s)
+        void launch_inv(const NttArgs &a0, cudaStream_t s)
         {
-            const long long ctas_b = a.count * ((1 << LOGR) / ROWS);
-            ntt_inv_pass_b<<<(unsigned)ctas_b, ROWS * 16, 0, s>>>(a);
-            const long long ctas_a = a.count * (256 / TB);
-            ntt_inv_pass_a<LOGR><<<(unsigned)ctas_a, (1 << LOGR) / 16 * TB, 0, s>>>(a);
+            static const long long l2_limbs = [] {
+                const char *e = getenv("MOAI_NTT_L2_LIMBS");
+                return e ? atoll(e) : 96ll;
+            }();
+            long long chunk = l2_limbs > 0 ? std::max<long long>(1, (l2_limbs << 16) >> a0.log_n) : a0.count;
+            if (chunk * 2 > a0.count)
+            {
+                chunk = a0.count; // not worth splitting
+            }
+            for (long long p0 = 0; p0 < a0.count; p0 += chunk)
+            {
+                NttArgs a = a0;
+                a.p_base = p0;
+                const long long cnt = std::min(chunk, a0.count - p0);
+                const long long ctas_b = cnt * ((1 << LOGR) / ROWS);
+                ntt_inv_pass_b<<<(unsigned)ctas_b, ROWS * 16, 0, s>>>(a);
+                const long long ctas_a = cnt * (256 / TB);
+                ntt_inv_pass_a<LOGR><<<(unsigned)ctas_a, (1 << LOGR) / 16 * TB, 0, s>>>(a);
+            }
         }
     } // namespace
 

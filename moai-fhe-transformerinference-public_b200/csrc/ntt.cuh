@@ -127,6 +127,7 @@ namespace moai
         ConvTab conv;
         long long skipped = 0;
         const NttScale *scale = nullptr; // inverse transform only
+        long long p_base = 0;            // inverse transform only: first polynomial of this launch (L2-sized chunks)
         FinishEpi fin;                   // forward transform, grouped pass B only
     };
 
