@@ -83,6 +83,8 @@ namespace moai
         }
         __device__ __forceinline__ u64 out_fwd(elem x) const { return canon(x); }
         __device__ __forceinline__ u64 out_inv(elem x) const { return canon(x); }
+        // the residue as a CENTRED double (|r| <= p/2 + 1), bit pattern: what the base-conversion prologue multiplies
+        __device__ __forceinline__ u64 out_fp(elem x) const { return (u64)__double_as_longlong(red(x)); }
         // forward: only the WIDE class needs the per-phase reduction; inverse: only NARROW does
         // (WIDE reduces every sum inside gs()).
         __device__ __forceinline__ void phase_begin_fwd(elem (&x)[16]) const

@@ -119,9 +119,9 @@ namespace moai
         // conversion tables of ONE source set (`src` prime indices, grouped by s0 / cnt) into `tgt` prime indices
         struct ConvOffsets
         {
-            size_t s0, cnt, invq, wide, B, B26, Bd, B26d, negQ, negQd, BT, c32d;
+            size_t s0, cnt, invq, wide, B, B26, Bd, B26d, negQ, negQd, BT, c32d, fpsrc, srcq;
             int src_limbs;
-            bool mma;
+            bool mma, fp;
         };
         // the conversion's tensor-core form (ConvTab::BT) needs whole warps in the pass-A CTA (N >= 2^13) and a free
         // top byte in every group's first source.  OPT-IN (MOAI_CONV_MMA=1, read when a level's tables are first built):
@@ -223,7 +223,23 @@ namespace moai
                     }
                 }
             }
+            // FP64-path sources as centred doubles with precomputed quotients: OPT-IN (MOAI_CONV_FPSRC=1).  It removes 2 of
+            // the 9 FP64 operations per (source, target), but the conversion pass A only gets 4 % faster (7.19 -> 6.90 ms
+            // at 28 limbs, 64 ciphertexts) and the quotient pre-pass costs 0.34 ms: no net gain (relin_rescale 16.03 vs
+            // 16.05 ms; 33 limbs 27.5 vs 27.9; 22 limbs 11.14 vs 11.21)
+            const char *efp = std::getenv("MOAI_CONV_FPSRC");
+            const bool fp = !mma && efp && efp[0] == '1';
+            std::vector<unsigned char> fpsrc(src.size(), 0);
+            std::vector<u64> srcq(src.size());
+            for (size_t j = 0; j < src.size(); j++)
+            {
+                fpsrc[j] = fp && c->h_limb[src[j]].fp_class != 0;
+                srcq[j] = c->q[src[j]];
+            }
             ConvOffsets o;
+            o.fp = fp;
+            o.fpsrc = bl.put(fpsrc);
+            o.srcq = bl.put(srcq);
             o.mma = mma;
             o.BT = bl.put(BT);
             o.c32d = bl.put(c32d);
@@ -256,6 +272,8 @@ namespace moai
             t.src_limbs = o.src_limbs;
             t.BT = o.mma ? reinterpret_cast<const uint32_t *>(base + o.BT) : nullptr;
             t.c32d = reinterpret_cast<const double *>(base + o.c32d);
+            t.fpsrc = o.fp ? base + o.fpsrc : nullptr;
+            t.srcq = reinterpret_cast<const u64 *>(base + o.srcq);
             return t;
         }
 
@@ -704,12 +722,18 @@ namespace moai
         MOAI_REQUIRE(target_stride % (long long)n == 0, "target stride must be a whole number of limbs");
         // y_J = c_J * prod(E) (Q_g / q_J)^-1: the constant rides on the inverse transform's N^-1
         ntt_inverse_from(c, target, limbs, target_stride ? target_stride / (long long)n : limbs, d.as<u64>(), batch * limbs,
-                         c->d_ids, limbs, 1, t.d_yscale);
+                         c->d_ids, limbs, 1, t.d_yscale, t.dec.fpsrc != nullptr);
         if (t.dec.BT)
         {
             conv_quotient(c, d.as<u64>(), batch, t.dec, t.digits);
         }
+        Scratch vq(t.dec.fpsrc ? (size_t)batch * t.digits * n * sizeof(double) : 0, c->stream);
         NttPrologue pro;
+        if (t.dec.fpsrc)
+        {
+            conv_quotient_fp(c, d.as<u64>(), batch, t.dec, t.digits, vq.as<double>());
+            pro.conv_v = vq.as<double>();
+        }
         pro.src = d.as<u64>();
         pro.mode = 3;
         ConvTab dec = t.dec;
@@ -744,13 +768,19 @@ namespace moai
         }
         Scratch r((size_t)polys * np * n * sizeof(u64), c->stream);
         ntt_inverse_from(c, acc + (size_t)targets * n, np, t.rns, r.as<u64>(), polys * np, t.d_ids + targets, np, 1,
-                         t.d_zscale_r);
+                         t.d_zscale_r, t.mdr.fpsrc != nullptr);
         if (t.mdr.BT)
         {
             conv_quotient(c, r.as<u64>(), polys, t.mdr, 1);
         }
         Scratch u((size_t)polys * targets * n * sizeof(u64), c->stream);
+        Scratch vq(t.mdr.fpsrc ? (size_t)polys * n * sizeof(double) : 0, c->stream);
         NttPrologue pro;
+        if (t.mdr.fpsrc)
+        {
+            conv_quotient_fp(c, r.as<u64>(), polys, t.mdr, 1, vq.as<double>());
+            pro.conv_v = vq.as<double>();
+        }
         pro.src = r.as<u64>();
         pro.mode = 3;
         pro.conv = &t.mdr;
@@ -781,13 +811,19 @@ namespace moai
         const int rns_in = t.rns * in_stride; // limbs between consecutive input polynomials
         Scratch r((size_t)polys * np * n * sizeof(u64), c->stream);
         ntt_inverse_from(c, acc + (size_t)limbs * n, np, rns_in, r.as<u64>(), polys * np, t.d_ids + limbs, np, 1,
-                         t.d_zscale);
+                         t.d_zscale, t.md.fpsrc != nullptr);
         if (t.md.BT)
         {
             conv_quotient(c, r.as<u64>(), polys, t.md, 1);
         }
         Scratch u((size_t)polys * limbs * n * sizeof(u64), c->stream);
+        Scratch vq(t.md.fpsrc ? (size_t)polys * n * sizeof(double) : 0, c->stream);
         NttPrologue pro;
+        if (t.md.fpsrc)
+        {
+            conv_quotient_fp(c, r.as<u64>(), polys, t.md, 1, vq.as<double>());
+            pro.conv_v = vq.as<double>();
+        }
         pro.src = r.as<u64>();
         pro.mode = 3;
         pro.conv = &t.md;

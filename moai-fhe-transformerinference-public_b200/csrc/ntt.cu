@@ -48,6 +48,7 @@ namespace moai
             __device__ __forceinline__ u64 out_mid(elem x) const { return x; }
             __device__ __forceinline__ u64 out_fwd(elem x) const { return csub(csub(x, two_q), q); } // [0,4q)->[0,q)
             __device__ __forceinline__ u64 out_inv(elem x) const { return csub(x, q); }              // [0,2q)->[0,q)
+            __device__ __forceinline__ u64 out_fp(elem x) const { return csub(x, q); } // integer-path limbs stay residues
             __device__ __forceinline__ void phase_begin_fwd(elem (&)[16]) const {}
             __device__ __forceinline__ void phase_mid_fwd(elem (&)[16]) const {}
             __device__ __forceinline__ void phase_begin_inv(elem (&)[16]) const {}
@@ -359,7 +360,8 @@ namespace moai
         }
 
         template <int LOGR, class F>
-        __device__ __forceinline__ void inv_pass_a_body(const F &f, u64 *base, u64 *sm, int t, int tb, size_t n)
+        __device__ __forceinline__ void inv_pass_a_body(const F &f, u64 *base, u64 *sm, int t, int tb, size_t n,
+                                                        bool fp_out = false)
         {
             constexpr int R = 1 << LOGR, T1 = R / 16;
             typename F::elem x[16];
@@ -411,7 +413,7 @@ namespace moai
             for (int k = 0; k < 16; k++)
             {
                 const int row = (LOGR == 4) ? (16 * t + k) : (t + T1 * k);
-                base[(size_t)row * 256] = f.out_inv(x[k]);
+                base[(size_t)row * 256] = fp_out ? f.out_fp(x[k]) : f.out_inv(x[k]);
             }
         }
 
@@ -525,7 +527,7 @@ namespace moai
                 lc.inv_n_w_d = sc.inv_n_w_d;
             }
             u64 *base = a.data + ((size_t)poly << a.log_n) + tile * TB + tb;
-            MOAI_DISPATCH_FIELD(lc, (inv_pass_a_body<LOGR>(f, base, sm, t, tb, n)))
+            MOAI_DISPATCH_FIELD(lc, (inv_pass_a_body<LOGR>(f, base, sm, t, tb, n, a.fp_out != 0)))
         }
 
 
@@ -566,6 +568,7 @@ namespace moai
             }
             const int red_every = WIDE ? 2 : 8;
             int since = 0;
+            const bool pre_v = a.conv_v != nullptr; // quotients precomputed (conv_quotient_fp)
             for (int j = 0; j < cnt; j++)
             {
                 const double iq = cv.invq[s0 + j];
@@ -577,13 +580,31 @@ namespace moai
                 {
                     y[k] = sj[(size_t)k * row_stride];
                 }
-                if (cv.wide[s0 + j])
+                if (cv.fpsrc && cv.fpsrc[s0 + j])
+                {
+                    // centred doubles straight from the inverse transform: 7 FP64 operations per (source, target)
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                    {
+                        const double yd = __longlong_as_double((long long)y[k]);
+                        if (!pre_v)
+                        {
+                            vs[k] = __fma_rn(yd, iq, vs[k]);
+                        }
+                        x[k] = __dadd_rn(x[k], f.mul_lazy(yd, bd));
+                    }
+                    since += 1;
+                }
+                else if (cv.wide[s0 + j])
                 {
                     const double b26 = cv.B26d[trow + j];
 #pragma unroll
                     for (int k = 0; k < 16; k++)
                     {
-                        vs[k] = __fma_rn(conv_y_double(y[k], true), iq, vs[k]);
+                        if (!pre_v)
+                        {
+                            vs[k] = __fma_rn(conv_y_double(y[k], true), iq, vs[k]);
+                        }
                         const double hi = f.in_outer(y[k] >> 26), lo = f.in_outer(y[k] & 0x3FFFFFFull);
                         x[k] = __dadd_rn(x[k], __dadd_rn(f.mul_lazy(hi, b26), f.mul_lazy(lo, bd)));
                     }
@@ -611,10 +632,22 @@ namespace moai
                 }
             }
             const double nq = cv.negQd[(size_t)g * rns + I];
+            if (pre_v)
+            {
+                // v[b][digits][n]: item b and the element offset follow from src0 = a.src + ((b src_limbs + s0) << log_n) + off
+                const size_t diff = (size_t)(src0 - a.src);
+                const size_t bq = (diff >> a.log_n) / (size_t)cv.src_limbs, eoff = diff & (((size_t)1 << a.log_n) - 1);
+                const double *vp = a.conv_v + (((bq * (size_t)a.div + (size_t)g) << a.log_n) + eoff);
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                {
+                    vs[k] = vp[(size_t)k * row_stride];
+                }
+            }
 #pragma unroll
             for (int k = 0; k < 16; k++)
             {
-                x[k] = f.red(__dadd_rn(x[k], f.mul_lazy(conv_rint(vs[k]), nq)));
+                x[k] = f.red(__dadd_rn(x[k], f.mul_lazy(pre_v ? vs[k] : conv_rint(vs[k]), nq)));
             }
         }
 
@@ -627,6 +660,7 @@ namespace moai
             const size_t trow = ((size_t)g * rns + I) * CONV_MAX;
             double vs[16];
             u128 acc[16];
+            const bool pre_v = a.conv_v != nullptr;
 #pragma unroll
             for (int k = 0; k < 16; k++)
             {
@@ -652,7 +686,24 @@ namespace moai
                             y &= 0x00FFFFFFFFFFFFFFull;
                         }
                     }
-                    else
+                    else if (cv.fpsrc && cv.fpsrc[s0 + j])
+                    {
+                        // a centred double: its canonical residue is y + q for negative y, and every such wrap adds
+                        // one Q_g to the sum, i.e. one to the quotient (counted in vs)
+                        const double yd = __longlong_as_double((long long)y);
+                        long long yi = __double2ll_rn(yd);
+                        if (!pre_v)
+                        {
+                            vs[k] = __fma_rn(yd, iq, vs[k]);
+                        }
+                        if (yi < 0)
+                        {
+                            yi += (long long)cv.srcq[s0 + j];
+                            vs[k] = __dadd_rn(vs[k], 1.0);
+                        }
+                        y = (u64)yi;
+                    }
+                    else if (!pre_v)
                     {
                         vs[k] = __fma_rn(conv_y_double(y, wide), iq, vs[k]);
                     }
@@ -660,9 +711,22 @@ namespace moai
                 }
             }
             const u64 nq = cv.negQ[(size_t)g * rns + I];
+            if (pre_v)
+            {
+                const size_t diff = (size_t)(src0 - a.src);
+                const size_t bq = (diff >> a.log_n) / (size_t)cv.src_limbs, eoff = diff & (((size_t)1 << a.log_n) - 1);
+                const double *vp = a.conv_v + (((bq * (size_t)a.div + (size_t)g) << a.log_n) + eoff);
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                {
+                    vs[k] = __dadd_rn(vs[k], vp[(size_t)k * row_stride]);
+                }
+            }
 #pragma unroll
             for (int k = 0; k < 16; k++)
             {
+                // canonical sources: the quotient of the canonical sum = the centred one + the number of wrapped sources
+                // (vs holds both)
                 const u64 v = (u64)__double2ll_rn(conv_rint(vs[k]));
                 mac_wide(acc[k], v, nq);
                 x[k] = barrett_reduce_acc(acc[k], lc, t64.w, t64.wq);
@@ -885,7 +949,7 @@ namespace moai
         }
 
         template <int LOGR>
-        __global__ void __launch_bounds__((1 << LOGR) / 16 * TB) ntt_fwd_pass_a_conv(NttArgs a, const Twiddle *two64)
+        __global__ void __launch_bounds__((1 << LOGR) / 16 * TB, 2) ntt_fwd_pass_a_conv(NttArgs a, const Twiddle *two64)
         {
             extern __shared__ __align__(16) unsigned char conv_smem[]; // R x 128 B, or conv_mma_smem (ConvTab::BT)
             u64 *sm = reinterpret_cast<u64 *>(conv_smem);
@@ -1651,13 +1715,14 @@ namespace moai
         }
 
         // The two passes run over chunks small enough for pass B's output to still be in L2 when pass A reads it
-        // (MOAI_NTT_L2_LIMBS polynomials per chunk, default 96 = 48 MiB at N = 65536; 0 = one launch pair)
+        // (MOAI_NTT_L2_LIMBS polynomials per chunk; default 0 = one launch pair: the serialised tails of the small launches
+        // cost more than the L2 hits save — relin_rescale at 28 limbs, 64 ciphertexts)
         template <int LOGR>
         void launch_inv(const NttArgs &a0, cudaStream_t s)
         {
             static const long long l2_limbs = [] {
                 const char *e = getenv("MOAI_NTT_L2_LIMBS");
-                return e ? atoll(e) : 96ll;
+                return e ? atoll(e) : 0ll; // measured: chunks of 48 / 96 / 192 limbs cost 2.70 / 2.21 / 2.03 ms against 1.76 ms in one launch pair
             }();
             long long chunk = l2_limbs > 0 ? std::max<long long>(1, (l2_limbs << 16) >> a0.log_n) : a0.count;
             if (chunk * 2 > a0.count)
@@ -1709,6 +1774,58 @@ namespace moai
         }
     } // namespace
 
+    namespace
+    {
+        __global__ void k_conv_quot_fp(const ulonglong2 *__restrict__ src, double2 *__restrict__ v, long long total2, int log_n2,
+                                       int digits, int src_limbs, ConvTab cv)
+        {
+            const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; // over [batch][digits][n/2]
+            if (i >= total2)
+            {
+                return;
+            }
+            const long long within = i & (((long long)1 << log_n2) - 1);
+            const long long bg = i >> log_n2;
+            const int g = (int)(bg % digits);
+            const long long b = bg / digits;
+            const int s0 = cv.s0[g], cnt = cv.cnt[g];
+            const ulonglong2 *p0 = src + (((b * src_limbs + s0) << log_n2) + within);
+            double vx = 0.0, vy = 0.0;
+            for (int j = 0; j < cnt; j++)
+            {
+                const ulonglong2 y = p0[(long long)j << log_n2];
+                const double iq = cv.invq[s0 + j];
+                if (cv.fpsrc[s0 + j])
+                {
+                    vx = __fma_rn(__longlong_as_double((long long)y.x), iq, vx);
+                    vy = __fma_rn(__longlong_as_double((long long)y.y), iq, vy);
+                }
+                else
+                {
+                    const bool wide = cv.wide[s0 + j] != 0;
+                    vx = __fma_rn(conv_y_double(y.x, wide), iq, vx);
+                    vy = __fma_rn(conv_y_double(y.y, wide), iq, vy);
+                }
+            }
+            v[i] = make_double2(conv_rint(vx), conv_rint(vy));
+        }
+    } // namespace
+
+    void conv_quotient_fp(Context *c, const u64 *src, long long batch, const ConvTab &tab, int digits, double *v)
+    {
+        const long long total2 = batch * digits * (long long)(c->n / 2);
+        if (!total2)
+        {
+            return;
+        }
+        KernelTimer kt(c, "k_conv_quot_fp", 1);
+        k_conv_quot_fp<<<(unsigned)((total2 + 255) / 256), 256, 0, c->stream>>>(
+            reinterpret_cast<const ulonglong2 *>(src), reinterpret_cast<double2 *>(v), total2, c->log_n - 1, digits,
+            tab.src_limbs, tab);
+        c->launches += 1;
+        MOAI_CUDA_CHECK(cudaGetLastError());
+    }
+
     void conv_quotient(Context *c, u64 *src, long long batch, const ConvTab &tab, int digits)
     {
         const long long total2 = batch * digits * (long long)(c->n / 2);
@@ -1744,6 +1861,7 @@ namespace moai
                 MOAI_REQUIRE(pro->conv != nullptr, "base-conversion prologue without tables");
                 a.conv = *pro->conv;
                 a.skipped = pro->skipped;
+                a.conv_v = pro->conv_v;
             }
         }
         if (fin && do_b && div == 1)
@@ -1918,7 +2036,7 @@ namespace moai
     }
 
     void ntt_inverse_from(Context *c, const u64 *src, long long grp_size, long long grp_stride, u64 *data, long long count,
-                          const int *d_limb_ids, int period, int div, const NttScale *d_scale)
+                          const int *d_limb_ids, int period, int div, const NttScale *d_scale, bool fp_out)
     {
         if (count <= 0)
         {
@@ -1926,6 +2044,7 @@ namespace moai
         }
         NttArgs a{ data, c->d_inv, c->d_inv_fp, c->d_limb, d_limb_ids, period, div, c->log_n, count };
         a.scale = d_scale;
+        a.fp_out = fp_out ? 1 : 0;
         if (src)
         {
             MOAI_REQUIRE(grp_size >= 1 && grp_stride >= grp_size, "bad source layout");

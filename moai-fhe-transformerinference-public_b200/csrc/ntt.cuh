@@ -64,10 +64,17 @@ namespace moai
         // constant (-Q_g) mod m_I.  BT: mma.sync m16n8k32 B fragments, [digits][rns][CONV_KSTEPS][32 lanes][2].
         const uint32_t *BT = nullptr;
         const double *c32d = nullptr; // [rns] centred 2^32 mod m_I
+        // [src_limbs] or nullptr: 1 = this source limb arrives as CENTRED DOUBLES (the inverse transform wrote them,
+        // NttArgs::fp_out): the prologue multiplies them as they are — no conversion per (source, target) — and the
+        // quotient v comes precomputed from conv_quotient_fp (NttPrologue::conv_v) instead of one FMA per (source, target)
+        const unsigned char *fpsrc = nullptr;
+        const u64 *srcq = nullptr; // [src_limbs] the source primes (integer-path targets canonicalise the doubles)
     };
     constexpr int CONV_KSTEPS = CONV_MAX / 4; // four sources (32 bytes) per mma k-step
     // writes v into byte 7 of every group's first source limb of src [batch][src_limbs][n] (once, before the transform)
     void conv_quotient(Context *c, u64 *src, long long batch, const ConvTab &tab, int digits);
+    // v[batch][digits][n] (doubles) = rint(sum_j y_j / q_j) from sources that are centred doubles (fpsrc) or residues
+    void conv_quotient_fp(Context *c, const u64 *src, long long batch, const ConvTab &tab, int digits, double *v);
 
     // Optional constant folded into the inverse transform: the last stage multiplies by N^-1 (and by the last root);
     // with scale[slot] it multiplies by c * N^-1 instead, so "INTT then scale by a per-limb constant" is one pass
@@ -128,6 +135,8 @@ namespace moai
         long long skipped = 0;
         const NttScale *scale = nullptr; // inverse transform only
         long long p_base = 0;            // inverse transform only: first polynomial of this launch (L2-sized chunks)
+        int fp_out = 0;                  // inverse transform only: FP64-path limbs are stored as centred doubles
+        const double *conv_v = nullptr;  // src_mode 3: precomputed quotients [batch][div][n] (ConvTab::fpsrc)
         FinishEpi fin;                   // forward transform, grouped pass B only
     };
 
@@ -138,6 +147,7 @@ namespace moai
         int last_id = 0;
         const ConvTab *conv = nullptr; // mode 3
         long long skipped = 0;         // polynomials the pass-A kernel skips (ConvTab::own): not counted as work units
+        const double *conv_v = nullptr; // mode 3 with ConvTab::fpsrc
     };
 
     // Shape of a key-switch inner product.  SEAL's per-prime digits (S/evaluator.cpp:2805-2909): digits = limbs,
@@ -183,6 +193,8 @@ namespace moai
     // out of place: polynomial p is read from src + ((p / grp_size) * grp_stride + p % grp_size) * n (runs of grp_size
     // polynomials, grp_stride polynomials apart: one limb range of every ciphertext of a batch) and the coefficients
     // land contiguously in data — saves the gather copy in front of an in-place transform
+    // fp_out: FP64-path limbs are written as centred doubles (bit patterns) for the base-conversion prologue
     void ntt_inverse_from(Context *c, const u64 *src, long long grp_size, long long grp_stride, u64 *data, long long count,
-                          const int *d_limb_ids, int period, int div = 1, const NttScale *d_scale = nullptr);
+                          const int *d_limb_ids, int period, int div = 1, const NttScale *d_scale = nullptr,
+                          bool fp_out = false);
 } // namespace moai

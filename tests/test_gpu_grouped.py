@@ -132,18 +132,21 @@ def test_merged_relinearize_rescale(pkg, env):
         print("merged relin+rescale limbs", limbs, "k", k, "err", np.abs(dg - zx * zy).max(), "exact", np.abs(de - zx * zy).max())
 
 
-@pytest.fixture(scope="module", params=["0", "1"], ids=["fp64", "mma"])
+@pytest.fixture(scope="module", params=["0", "1", "fpsrc"], ids=["fp64", "mma", "fpsrc"])
 def env13(pkg, request):
-    """N = 2^13 with the base conversion as FP64 products (default) and as the opt-in tensor-core GEMM (MOAI_CONV_MMA=1,
-    read when a level's conversion tables are first built, i.e. per context)."""
+    """N = 2^13 with the base conversion as FP64 products (default), as the opt-in tensor-core GEMM (MOAI_CONV_MMA=1)
+    and with the opt-in centred-double sources + precomputed quotients (MOAI_CONV_FPSRC=1); both switches are read when
+    a level's conversion tables are first built, i.e. per context."""
     import os
     from oracle import Oracle
     old = os.environ.get("MOAI_CONV_MMA")
-    os.environ["MOAI_CONV_MMA"] = request.param
+    os.environ["MOAI_CONV_MMA"] = "1" if request.param == "1" else "0"
+    os.environ["MOAI_CONV_FPSRC"] = "1" if request.param == "fpsrc" else "0"
     o = Oracle(13, BITS)
     be = pkg.Backend(13, o.q)
     sk = o.gen_secret(3, hamming_weight=64)
     yield o, be, sk
+    os.environ.pop("MOAI_CONV_FPSRC", None)
     if old is None:
         os.environ.pop("MOAI_CONV_MMA", None)
     else:
@@ -191,6 +194,7 @@ def test_conversion_on_tensor_cores(pkg, env13, limbs, k, key_limbs):
     prof = be.profile_dump()
     be.profile(False)
     assert ("k_conv_quot" in prof) == mma, sorted(prof)   # the variant under test is the one that ran
+    assert ("k_conv_quot_fp" in prof) == (os.environ.get("MOAI_CONV_FPSRC") == "1"), sorted(prof)
 
 
 def test_bootstrap_grouped(pkg, env):
