@@ -72,7 +72,7 @@ public:
     Bootstrapper &operator=(const Bootstrapper &) = delete;
     ~Bootstrapper()
     {
-        seal::detail::Lock lk(context.impl()->mu);
+        seal::detail::RootLock lk(context.impl()->mu);
         if (keys_)
         {
             moai_keys_destroy(keys_);
@@ -97,7 +97,7 @@ public:
         hoisting_ = on;
         if (h_)
         {
-            seal::detail::Lock lk(context.impl()->mu);
+            seal::detail::RootLock lk(context.impl()->mu);
             seal::detail::chk(moai_bootstrapper_set_hoisting(h_, on ? 1 : 0));
         }
     }
@@ -115,7 +115,7 @@ public:
         std::vector<std::int32_t> steps(4096);
         std::int32_t count = 0;
         {
-            seal::detail::Lock lk(context.impl()->mu);
+            seal::detail::RootLock lk(context.impl()->mu);
             seal::detail::chk(moai_bootstrapper_required_steps(h_, steps.data(), static_cast<std::int32_t>(steps.size()), &count));
         }
         for (std::int32_t i = 0; i < count; i++)
@@ -178,7 +178,7 @@ public:
         std::int32_t got_limbs = 0;
         double got_scale = 0.0;
         {
-            seal::detail::Lock lk(context.impl()->mu);
+            seal::detail::RootLock lk(context.impl()->mu);
             seal::detail::chk(moai_bootstrap(context.handle(), h_, keys_, cipher.data(), 1, cipher.scale(), out.data(),
                                              &got_limbs, &got_scale));
         }
@@ -318,7 +318,7 @@ private:
                 std::int32_t got_limbs = 0;
                 double got_scale = 0.0;
                 {
-                    seal::detail::Lock lk(c->mu);
+                    seal::detail::RootLock lk(c->mu);
                     for (std::size_t k = 0; k < B; k++)
                     {
                         seal::detail::chk(moai_memcpy_d2d(c->h, in.ptr() + k * 2 * n, batch[group[k]]->in->data(),
@@ -348,7 +348,7 @@ private:
                     r.scale() = got_scale;
                     r.is_ntt_form() = true;
                     {
-                        seal::detail::Lock lk(c->mu);
+                        seal::detail::RootLock lk(c->mu);
                         seal::detail::chk(moai_memcpy_d2d(c->h, r.data(), out.ptr() + k * 2 * out_limbs * n,
                                                           2 * out_limbs * n * sizeof(std::uint64_t)));
                     }
@@ -372,7 +372,7 @@ private:
         {
             return;
         }
-        seal::detail::Lock lk(context.impl()->mu);
+        seal::detail::RootLock lk(context.impl()->mu);
         seal::detail::chk(moai_bootstrapper_create(context.handle(), static_cast<std::int32_t>(L + 1), final_scale,
                                                    static_cast<std::int32_t>(boundary_K), static_cast<std::int32_t>(sin_cos_deg),
                                                    static_cast<std::int32_t>(scale_factor), static_cast<std::int32_t>(loge), &h_));
@@ -390,7 +390,7 @@ private:
         {
             return;
         }
-        seal::detail::Lock lk(context.impl()->mu);
+        seal::detail::RootLock lk(context.impl()->mu);
         if (keys_)
         {
             moai_keys_destroy(keys_);

@@ -46,6 +46,13 @@ int32_t moai_version(void);
 int32_t moai_context_create(int32_t log_n, const uint64_t *primes, int32_t n_key_limbs, int32_t device,
                             moai_context **out);
 int32_t moai_context_destroy(moai_context *ctx);
+/* A LANE of `ctx` for one more host thread: same tables (shared, immutable), its own CUDA stream and therefore its own
+ * arena.  SEAL's Evaluator is called from many OpenMP threads at once (M/test/test_full_scheme.hpp:654-660 and every
+ * module header's `#pragma omp parallel for`); with one lane per thread those calls are issued concurrently instead of
+ * queueing on one stream.  Key handles and device buffers may be used from any lane; a buffer written on one lane must
+ * be complete (moai_synchronize on that lane) before another lane reads it.  Destroy lanes (moai_context_destroy)
+ * before their parent. */
+int32_t moai_context_fork(moai_context *ctx, moai_context **lane);
 int32_t moai_set_stream(moai_context *ctx, void *cuda_stream);
 int32_t moai_synchronize(moai_context *ctx);
 

@@ -50,7 +50,7 @@ namespace fused
         const std::size_t per = 2 * limbs * c->n;
         detail::DeviceBlock blk;
         blk.ensure(c, per * count);
-        detail::Lock lk(c->mu);
+        detail::RootLock lk(c->mu);
         for (std::size_t i = 0; i < count; i++)
         {
             if (v[i].size() != 2 || v[i].coeff_modulus_size() != limbs || v[i].context() != c)
@@ -70,7 +70,7 @@ namespace fused
         const std::size_t per = 2 * limbs * c->n;
         const parms_id_type &id = ctx.parms_id_for_limbs(limbs);
         std::vector<Ciphertext> out(count);
-        detail::Lock lk(c->mu);
+        detail::RootLock lk(c->mu);
         for (std::size_t i = 0; i < count; i++)
         {
             out[i].resize(ctx, id, 2);
@@ -105,7 +105,7 @@ namespace fused
     public:
         KeyBundle(const SEALContext &ctx, const RelinKeys *rk, const GaloisKeys *gk) : c_(ctx.impl())
         {
-            detail::Lock lk(c_->mu);
+            detail::RootLock lk(c_->mu);
             detail::chk(moai_keys_create(c_->h, &h_));
             if (rk && rk->has_key(2))
             {
@@ -130,7 +130,7 @@ namespace fused
         {
             if (h_)
             {
-                detail::Lock lk(c_->mu);
+                detail::RootLock lk(c_->mu);
                 moai_keys_destroy(h_);
             }
         }
@@ -170,7 +170,7 @@ namespace fused
         detail::DeviceBlock out;
         out.ensure(c, std::size_t(col_W) * 2 * (limbs - 1) * c->n);
         {
-            detail::Lock lk(c->mu);
+            detail::RootLock lk(c->mu);
             if (bias_vec)
             {
                 if (bias_vec->size() < c->n / 2)
@@ -199,7 +199,7 @@ namespace fused
         std::int32_t out_limbs = 0;
         double out_scale = 0.0;
         {
-            detail::Lock lk(c->mu);
+            detail::RootLock lk(c->mu);
             detail::chk(f(c->h, out.ptr(), &out_limbs, &out_scale));
         }
         return unpack(ctx, out.ptr(), out_count, std::size_t(out_limbs), out_scale);

@@ -57,6 +57,8 @@
 #include <limits>
 #include <map>
 #include <memory>
+#include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <ostream>
 #include <sstream>
@@ -347,16 +349,68 @@ namespace sealapi
         }
 
         // one per SEALContext; shared by every object that owns device memory of that context
+        struct ContextImpl;
+        struct CtxMutex : std::recursive_mutex
+        {
+            const ContextImpl *owner = nullptr;
+        };
         struct ContextImpl
         {
-            moai_context *h = nullptr;
+            moai_context *h = nullptr; // the root context (its stream serves the batched entry points)
             int log_n = 0;
             std::size_t n = 0;
             std::vector<std::uint64_t> primes; // key level: data primes then the special prime
-            mutable std::recursive_mutex mu;
+            mutable CtxMutex mu;
+            // Thread lanes (one CUDA stream per calling host thread).  Off: every call is serialised by `mu`
+            // onto the root stream.  On (SEALContext::set_thread_lanes(true) or MOAI_FACADE_LANES=1): each host thread
+            // gets its own lane of the context (moai_context_fork: shared tables, own stream and arena), calls are
+            // issued WITHOUT the mutex and every call synchronises its lane before it returns — SEAL's calls are
+            // synchronous, so an object produced by one thread is complete before another thread can touch it.
+            mutable std::atomic<bool> lanes{ false };
+            mutable std::mutex lanes_mu;
+            mutable std::vector<moai_context *> lane_list;
+            const std::uint64_t uid = next_uid();
+
+            ContextImpl()
+            {
+                mu.owner = this;
+                const char *e = std::getenv("MOAI_FACADE_LANES");
+                lanes = e && e[0] == '1';
+            }
+            static std::uint64_t next_uid()
+            {
+                static std::atomic<std::uint64_t> n{ 1 };
+                return n++;
+            }
+            // the context handle the CALLING THREAD issues work on
+            moai_context *cur() const
+            {
+                if (!lanes.load(std::memory_order_relaxed))
+                {
+                    return h;
+                }
+                thread_local std::map<std::uint64_t, moai_context *> mine; // by context uid: survives address reuse
+                auto it = mine.find(uid);
+                if (it != mine.end())
+                {
+                    return it->second;
+                }
+                moai_context *lane = nullptr;
+                chk(moai_context_fork(h, &lane));
+                {
+                    std::lock_guard<std::mutex> lk(lanes_mu);
+                    lane_list.push_back(lane);
+                }
+                mine[uid] = lane;
+                return lane;
+            }
 
             ~ContextImpl()
             {
+                for (moai_context *l : lane_list)
+                {
+                    moai_context_destroy(l);
+                }
                 if (h)
                 {
                     moai_context_destroy(h);
@@ -372,7 +426,60 @@ namespace sealapi
             }
         };
         using ContextPtr = std::shared_ptr<ContextImpl>;
-        using Lock = std::lock_guard<std::recursive_mutex>;
+        // Scope of one facade call.  Lanes off: holds the context's mutex.  Lanes on: holds nothing and, on the way out,
+        // waits for the calling thread's lane (the call's results are complete when it returns, like SEAL's).
+        class Lock
+        {
+        public:
+            explicit Lock(CtxMutex &m) : m_(m), locked_(!m.owner->lanes.load(std::memory_order_relaxed))
+            {
+                if (locked_)
+                {
+                    m_.lock();
+                }
+            }
+            ~Lock()
+            {
+                if (locked_)
+                {
+                    m_.unlock();
+                }
+                else
+                {
+                    moai_synchronize(m_.owner->cur());
+                }
+            }
+            Lock(const Lock &) = delete;
+            Lock &operator=(const Lock &) = delete;
+
+        private:
+            CtxMutex &m_;
+            bool locked_;
+        };
+        // Scope of a call that runs on the ROOT stream whatever the lane mode (the batched module / bootstrapping entry
+        // points, whose handles keep per-context caches): always the mutex; with lanes on it also drains the root stream
+        // before returning so that other threads' lanes see complete results.
+        class RootLock
+        {
+        public:
+            explicit RootLock(CtxMutex &m) : m_(m)
+            {
+                m_.lock();
+            }
+            ~RootLock()
+            {
+                if (m_.owner->lanes.load(std::memory_order_relaxed))
+                {
+                    moai_synchronize(m_.owner->h);
+                }
+                m_.unlock();
+            }
+            RootLock(const RootLock &) = delete;
+            RootLock &operator=(const RootLock &) = delete;
+
+        private:
+            CtxMutex &m_;
+        };
 
         // stream-ordered device block from the library's arena (the role of S/util/mempool.h)
         class DeviceBlock
@@ -409,7 +516,7 @@ namespace sealapi
                 if (p_ && c_)
                 {
                     Lock lk(c_->mu);
-                    moai_free(c_->h, p_);
+                    moai_free(c_->cur(), p_);
                 }
                 p_ = nullptr;
                 words_ = 0;
@@ -431,7 +538,7 @@ namespace sealapi
                 {
                     Lock lk(c->mu);
                     void *p = nullptr;
-                    chk(moai_malloc(c->h, words * sizeof(std::uint64_t), &p));
+                    chk(moai_malloc(c->cur(), words * sizeof(std::uint64_t), &p));
                     p_ = static_cast<std::uint64_t *>(p);
                 }
                 words_ = words;
@@ -650,7 +757,18 @@ namespace sealapi
         void synchronize() const
         {
             detail::Lock lk(impl_->mu);
+            detail::chk(moai_synchronize(impl_->cur()));
+        }
+        // one CUDA stream (lane) per calling host thread instead of one mutex for all of them; switch it while no other
+        // thread is inside a facade call (e.g. right after constructing the context)
+        void set_thread_lanes(bool on) const
+        {
             detail::chk(moai_synchronize(impl_->h));
+            impl_->lanes = on;
+        }
+        bool thread_lanes() const
+        {
+            return impl_->lanes;
         }
 
     private:
@@ -761,7 +879,7 @@ namespace sealapi
                     {
                         run++;
                     }
-                    chk(moai_expand_seeds(c->h, seeds.data() + 8 * i, std::int64_t(run), std::int32_t(kl),
+                    chk(moai_expand_seeds(c->cur(), seeds.data() + 8 * i, std::int64_t(run), std::int32_t(kl),
                                           dev + digits[i] * per + kl * c->n, std::int64_t(per)));
                     i += run;
                 }
@@ -874,7 +992,7 @@ namespace sealapi
                 auto c = o.mem_.context();
                 mem_.ensure(c, limbs_ * c->n);
                 detail::Lock lk(c->mu);
-                detail::chk(moai_memcpy_d2d(c->h, mem_.ptr(), o.mem_.ptr(), limbs_ * c->n * sizeof(std::uint64_t)));
+                detail::chk(moai_memcpy_d2d(c->cur(), mem_.ptr(), o.mem_.ptr(), limbs_ * c->n * sizeof(std::uint64_t)));
             }
             else
             {
@@ -935,8 +1053,8 @@ namespace sealapi
             set_vector(ctx, limbs, scale);
             auto &c = ctx.impl();
             detail::Lock lk(c->mu);
-            detail::chk(moai_memcpy_h2d(c->h, mem_.ptr(), host, limbs * c->n * sizeof(std::uint64_t)));
-            detail::chk(moai_synchronize(c->h));
+            detail::chk(moai_memcpy_h2d(c->cur(), mem_.ptr(), host, limbs * c->n * sizeof(std::uint64_t)));
+            detail::chk(moai_synchronize(c->cur()));
         }
         void download(std::uint64_t *host) const
         {
@@ -946,7 +1064,7 @@ namespace sealapi
                 throw std::logic_error("plaintext holds no residue array");
             }
             detail::Lock lk(c->mu);
-            detail::chk(moai_memcpy_d2h(c->h, host, mem_.ptr(), limbs_ * c->n * sizeof(std::uint64_t)));
+            detail::chk(moai_memcpy_d2h(c->cur(), host, mem_.ptr(), limbs_ * c->n * sizeof(std::uint64_t)));
         }
 
         // used by CKKSEncoder / Evaluator / Decryptor
@@ -1026,7 +1144,7 @@ namespace sealapi
             {
                 mem_.ensure(c, o.words());
                 detail::Lock lk(c->mu);
-                detail::chk(moai_memcpy_d2d(c->h, mem_.ptr(), o.mem_.ptr(), o.words() * sizeof(std::uint64_t)));
+                detail::chk(moai_memcpy_d2d(c->cur(), mem_.ptr(), o.mem_.ptr(), o.words() * sizeof(std::uint64_t)));
             }
             else
             {
@@ -1116,8 +1234,8 @@ namespace sealapi
             ntt_ = true;
             auto &c = ctx.impl();
             detail::Lock lk(c->mu);
-            detail::chk(moai_memcpy_h2d(c->h, mem_.ptr(), host, words() * sizeof(std::uint64_t)));
-            detail::chk(moai_synchronize(c->h));
+            detail::chk(moai_memcpy_h2d(c->cur(), mem_.ptr(), host, words() * sizeof(std::uint64_t)));
+            detail::chk(moai_synchronize(c->cur()));
         }
         void download(std::uint64_t *host) const
         {
@@ -1127,7 +1245,7 @@ namespace sealapi
                 throw std::logic_error("ciphertext is empty");
             }
             detail::Lock lk(c->mu);
-            detail::chk(moai_memcpy_d2h(c->h, host, mem_.ptr(), words() * sizeof(std::uint64_t)));
+            detail::chk(moai_memcpy_d2h(c->cur(), host, mem_.ptr(), words() * sizeof(std::uint64_t)));
         }
 
         // ---- SEAL's wire format (Ciphertext::save / load with compr_mode_type::none, S/ciphertext.cpp:153-330):
@@ -1221,8 +1339,8 @@ namespace sealapi
             mem_ = std::make_shared<detail::DeviceBlock>();
             mem_->ensure(c, 2 * c->key_limbs() * c->n);
             detail::Lock lk(c->mu);
-            detail::chk(moai_memcpy_h2d(c->h, mem_->ptr(), host, 2 * c->key_limbs() * c->n * sizeof(std::uint64_t)));
-            detail::chk(moai_synchronize(c->h));
+            detail::chk(moai_memcpy_h2d(c->cur(), mem_->ptr(), host, 2 * c->key_limbs() * c->n * sizeof(std::uint64_t)));
+            detail::chk(moai_synchronize(c->cur()));
         }
         // what PublicKey::save writes (a Ciphertext stream; seeded form accepted)
         void load(const SEALContext &ctx, std::istream &stream)
@@ -1259,8 +1377,8 @@ namespace sealapi
             mem_ = std::make_shared<detail::DeviceBlock>();
             mem_->ensure(c, c->key_limbs() * c->n);
             detail::Lock lk(c->mu);
-            detail::chk(moai_memcpy_h2d(c->h, mem_->ptr(), host, c->key_limbs() * c->n * sizeof(std::uint64_t)));
-            detail::chk(moai_synchronize(c->h));
+            detail::chk(moai_memcpy_h2d(c->cur(), mem_->ptr(), host, c->key_limbs() * c->n * sizeof(std::uint64_t)));
+            detail::chk(moai_synchronize(c->cur()));
         }
         const std::uint64_t *data() const noexcept
         {
@@ -1291,7 +1409,7 @@ namespace sealapi
             explicit KeySet(const ContextPtr &ctx) : c(ctx)
             {
                 Lock lk(c->mu);
-                chk(moai_keys_create(c->h, &h));
+                chk(moai_keys_create(c->cur(), &h));
             }
             ~KeySet()
             {
@@ -1309,8 +1427,8 @@ namespace sealapi
                 blocks.emplace_back(new DeviceBlock());
                 blocks.back()->ensure(c, words);
                 Lock lk(c->mu);
-                chk(moai_memcpy_h2d(c->h, blocks.back()->ptr(), host, words * sizeof(std::uint64_t)));
-                chk(moai_synchronize(c->h));
+                chk(moai_memcpy_h2d(c->cur(), blocks.back()->ptr(), host, words * sizeof(std::uint64_t)));
+                chk(moai_synchronize(c->cur()));
                 return blocks.back()->ptr();
             }
         };
@@ -1400,7 +1518,7 @@ namespace sealapi
             {
                 pending_ref().expand(set_->c, dev);
                 detail::Lock lk(set_->c->mu);
-                detail::chk(moai_synchronize(set_->c->h));
+                detail::chk(moai_synchronize(set_->c->cur()));
             }
         }
     };
@@ -1466,13 +1584,13 @@ namespace sealapi
             set_->blocks.back()->ensure(c, std::size_t(max_limbs) * 2 * (max_limbs + 1) * c->n);
             {
                 detail::Lock lk0(c->mu);
-                detail::chk(moai_memcpy_h2d(c->h, full.ptr(), host, words * sizeof(std::uint64_t)));
+                detail::chk(moai_memcpy_h2d(c->cur(), full.ptr(), host, words * sizeof(std::uint64_t)));
             }
             expand_pending(full.ptr());
             detail::Lock lk(c->mu);
-            detail::chk(moai_key_prepare(c->h, full.ptr(), galois_elt, max_limbs, 1, set_->blocks.back()->ptr()));
+            detail::chk(moai_key_prepare(c->cur(), full.ptr(), galois_elt, max_limbs, 1, set_->blocks.back()->ptr()));
             detail::chk(moai_keys_add_galois_fast(set_->h, galois_elt, set_->blocks.back()->ptr(), max_limbs + 1));
-            detail::chk(moai_synchronize(c->h));
+            detail::chk(moai_synchronize(c->cur()));
             set_->fast.push_back({ galois_elt, set_->blocks.back()->ptr(), max_limbs + 1 });
         }
         const std::shared_ptr<detail::KeySet> &key_set() const
@@ -1543,11 +1661,11 @@ namespace sealapi
             std::vector<std::complex<double>> one(1);
             const std::complex<double> *src = values.empty() ? one.data() : values.data();
             detail::Lock lk(c->mu);
-            detail::chk(moai_memcpy_h2d(c->h, dv.ptr(), src, 2 * count * sizeof(double)));
-            detail::chk(moai_encode_vector(c->h, reinterpret_cast<const double *>(dv.ptr()), 1,
+            detail::chk(moai_memcpy_h2d(c->cur(), dv.ptr(), src, 2 * count * sizeof(double)));
+            detail::chk(moai_encode_vector(c->cur(), reinterpret_cast<const double *>(dv.ptr()), 1,
                                            static_cast<std::int32_t>(count), scale, static_cast<std::int32_t>(limbs),
                                            destination.data()));
-            detail::chk(moai_synchronize(c->h)); // `src` may be a temporary
+            detail::chk(moai_synchronize(c->cur())); // `src` may be a temporary
         }
         void encode(const std::vector<double> &values, const parms_id_type &id, double scale, Plaintext &destination) const
         {
@@ -1568,7 +1686,7 @@ namespace sealapi
             auto &c = ctx_.impl();
             {
                 detail::Lock lk(c->mu);
-                detail::chk(moai_encode_scalar_consts(c->h, value, scale, static_cast<std::int32_t>(limbs), consts.data()));
+                detail::chk(moai_encode_scalar_consts(c->cur(), value, scale, static_cast<std::int32_t>(limbs), consts.data()));
             }
             destination.set_scalar(ctx_, std::move(consts), scale);
         }
@@ -1609,9 +1727,9 @@ namespace sealapi
                 detail::DeviceBlock tmp;
                 tmp.ensure(c, limbs * n);
                 detail::Lock lk(c->mu);
-                detail::chk(moai_memcpy_d2d(c->h, tmp.ptr(), plain.data(), limbs * n * sizeof(std::uint64_t)));
-                detail::chk(moai_ntt_inverse(c->h, tmp.ptr(), 1, 1, static_cast<std::int32_t>(limbs)));
-                detail::chk(moai_memcpy_d2h(c->h, res.data(), tmp.ptr(), limbs * n * sizeof(std::uint64_t)));
+                detail::chk(moai_memcpy_d2d(c->cur(), tmp.ptr(), plain.data(), limbs * n * sizeof(std::uint64_t)));
+                detail::chk(moai_ntt_inverse(c->cur(), tmp.ptr(), 1, 1, static_cast<std::int32_t>(limbs)));
+                detail::chk(moai_memcpy_d2h(c->cur(), res.data(), tmp.ptr(), limbs * n * sizeof(std::uint64_t)));
             }
             std::vector<std::complex<double>> a(n);
             compose_centered(*c, res, limbs, plain.scale(), a);
@@ -2231,7 +2349,7 @@ namespace sealapi
         {
             auto &c = ctx_.impl();
             detail::Lock lk(c->mu);
-            detail::chk(f(c->h));
+            detail::chk(f(c->cur()));
         }
         void valid(const Ciphertext &a, const char *name) const
         {
@@ -2437,9 +2555,9 @@ namespace sealapi
             sk_host_.resize(kl * n);
             {
                 detail::Lock lk(c->mu);
-                detail::chk(moai_memcpy_h2d(c->h, d.ptr(), s.data(), s.size() * sizeof(std::uint64_t)));
-                detail::chk(moai_ntt_forward(c->h, d.ptr(), 1, 1, static_cast<std::int32_t>(kl)));
-                detail::chk(moai_memcpy_d2h(c->h, sk_host_.data(), d.ptr(), s.size() * sizeof(std::uint64_t)));
+                detail::chk(moai_memcpy_h2d(c->cur(), d.ptr(), s.data(), s.size() * sizeof(std::uint64_t)));
+                detail::chk(moai_ntt_forward(c->cur(), d.ptr(), 1, 1, static_cast<std::int32_t>(kl)));
+                detail::chk(moai_memcpy_d2h(c->cur(), sk_host_.data(), d.ptr(), s.size() * sizeof(std::uint64_t)));
             }
             sk_.upload(ctx_, sk_host_.data());
         }
@@ -2457,7 +2575,7 @@ namespace sealapi
             std::vector<std::uint64_t> host(2 * c->key_limbs() * c->n);
             {
                 detail::Lock lk(c->mu);
-                detail::chk(moai_memcpy_d2h(c->h, host.data(), pk.ptr(), host.size() * sizeof(std::uint64_t)));
+                detail::chk(moai_memcpy_d2h(c->cur(), host.data(), pk.ptr(), host.size() * sizeof(std::uint64_t)));
             }
             destination.upload(ctx_, host.data());
         }
@@ -2469,7 +2587,7 @@ namespace sealapi
             s2.ensure(c, c->key_limbs() * c->n);
             {
                 detail::Lock lk(c->mu); // s^2 (compute_secret_key_array, S/keygenerator.cpp:232-290)
-                detail::chk(moai_multiply_plain(c->h, sk_.data(), sk_.data(), s2.ptr(), 1, 1, kl, 0));
+                detail::chk(moai_multiply_plain(c->cur(), sk_.data(), sk_.data(), s2.ptr(), 1, 1, kl, 0));
             }
             std::vector<std::uint64_t> key = one_kswitch_key(s2.ptr());
             destination.upload(ctx_, key.data());
@@ -2505,8 +2623,8 @@ namespace sealapi
                 d.ensure(c, kl * n);
                 {
                     detail::Lock lk(c->mu);
-                    detail::chk(moai_memcpy_h2d(c->h, d.ptr(), rot.data(), rot.size() * sizeof(std::uint64_t)));
-                    detail::chk(moai_synchronize(c->h));
+                    detail::chk(moai_memcpy_h2d(c->cur(), d.ptr(), rot.data(), rot.size() * sizeof(std::uint64_t)));
+                    detail::chk(moai_synchronize(c->cur()));
                 }
                 std::vector<std::uint64_t> key = one_kswitch_key(d.ptr());
                 fresh.upload(ctx_, elt, key.data());
@@ -2521,7 +2639,7 @@ namespace sealapi
             for (int st : steps)
             {
                 std::uint32_t e = 0;
-                detail::chk(moai_galois_elt_from_step(c->h, st, &e));
+                detail::chk(moai_galois_elt_from_step(c->cur(), st, &e));
                 elts.push_back(e);
             }
             create_galois_keys(elts, destination);
@@ -2572,13 +2690,13 @@ namespace sealapi
             de.ensure(c, kl * n);
             std::uint64_t *c0 = dst, *c1 = dst + kl * n;
             detail::Lock lk(c->mu);
-            detail::chk(moai_memcpy_h2d(c->h, c1, a.data(), a.size() * sizeof(std::uint64_t)));
-            detail::chk(moai_memcpy_h2d(c->h, de.ptr(), e.data(), e.size() * sizeof(std::uint64_t)));
-            detail::chk(moai_ntt_forward(c->h, de.ptr(), 1, 1, l32));
-            detail::chk(moai_multiply_plain(c->h, c1, sk_.data(), c0, 1, 1, l32, 0)); // a s
-            detail::chk(moai_add(c->h, de.ptr(), c0, c0, 1, 1, l32));                  // + e
-            detail::chk(moai_negate(c->h, c0, c0, 1, 1, l32));                         // -(a s + e)
-            detail::chk(moai_synchronize(c->h));
+            detail::chk(moai_memcpy_h2d(c->cur(), c1, a.data(), a.size() * sizeof(std::uint64_t)));
+            detail::chk(moai_memcpy_h2d(c->cur(), de.ptr(), e.data(), e.size() * sizeof(std::uint64_t)));
+            detail::chk(moai_ntt_forward(c->cur(), de.ptr(), 1, 1, l32));
+            detail::chk(moai_multiply_plain(c->cur(), c1, sk_.data(), c0, 1, 1, l32, 0)); // a s
+            detail::chk(moai_add(c->cur(), de.ptr(), c0, c0, 1, 1, l32));                  // + e
+            detail::chk(moai_negate(c->cur(), c0, c0, 1, 1, l32));                         // -(a s + e)
+            detail::chk(moai_synchronize(c->cur()));
         }
         // generate_one_kswitch_key (S/keygenerator.cpp:292-336): host copy [digits][2][kl][N]
         std::vector<std::uint64_t> one_kswitch_key(const std::uint64_t *new_key_dev) const
@@ -2600,12 +2718,12 @@ namespace sealapi
                 std::vector<std::uint64_t> consts(kl, 0);
                 consts[i] = c->primes[kl - 1] % c->primes[i]; // P mod q_i
                 detail::Lock lk(c->mu);
-                detail::chk(moai_multiply_scalar(c->h, new_key_dev, consts.data(), tmp.ptr(), 1, 1, l32));
-                detail::chk(moai_add(c->h, dst, tmp.ptr(), dst, 1, 1, l32));
+                detail::chk(moai_multiply_scalar(c->cur(), new_key_dev, consts.data(), tmp.ptr(), 1, 1, l32));
+                detail::chk(moai_add(c->cur(), dst, tmp.ptr(), dst, 1, 1, l32));
             }
             std::vector<std::uint64_t> host(digits * per);
             detail::Lock lk(c->mu);
-            detail::chk(moai_memcpy_d2h(c->h, host.data(), all.ptr(), host.size() * sizeof(std::uint64_t)));
+            detail::chk(moai_memcpy_d2h(c->cur(), host.data(), all.ptr(), host.size() * sizeof(std::uint64_t)));
             return host;
         }
 
@@ -2659,30 +2777,30 @@ namespace sealapi
             wide.ensure(c, 2 * le * n);
             const std::int32_t l32 = static_cast<std::int32_t>(le);
             detail::Lock lk(c->mu);
-            detail::chk(moai_memcpy_h2d(c->h, du.ptr(), u.data(), u.size() * sizeof(std::uint64_t)));
-            detail::chk(moai_memcpy_h2d(c->h, de.ptr(), e.data(), e.size() * sizeof(std::uint64_t)));
+            detail::chk(moai_memcpy_h2d(c->cur(), du.ptr(), u.data(), u.size() * sizeof(std::uint64_t)));
+            detail::chk(moai_memcpy_h2d(c->cur(), de.ptr(), e.data(), e.size() * sizeof(std::uint64_t)));
             // the first `le` limbs of each public-key polynomial (all of them at the key level)
             const std::size_t kl = c->key_limbs();
             for (int j = 0; j < 2; j++)
             {
-                detail::chk(moai_memcpy_d2d(c->h, pk.ptr() + j * le * n, pk_.data() + j * kl * n,
+                detail::chk(moai_memcpy_d2d(c->cur(), pk.ptr() + j * le * n, pk_.data() + j * kl * n,
                                             le * n * sizeof(std::uint64_t)));
             }
-            detail::chk(moai_ntt_forward(c->h, du.ptr(), 1, 1, l32));
-            detail::chk(moai_multiply_plain(c->h, pk.ptr(), du.ptr(), wide.ptr(), 1, 2, l32, 0));
-            detail::chk(moai_ntt_forward(c->h, de.ptr(), 1, 2, l32));
-            detail::chk(moai_add(c->h, wide.ptr(), de.ptr(), wide.ptr(), 1, 2, l32));
+            detail::chk(moai_ntt_forward(c->cur(), du.ptr(), 1, 1, l32));
+            detail::chk(moai_multiply_plain(c->cur(), pk.ptr(), du.ptr(), wide.ptr(), 1, 2, l32, 0));
+            detail::chk(moai_ntt_forward(c->cur(), de.ptr(), 1, 2, l32));
+            detail::chk(moai_add(c->cur(), wide.ptr(), de.ptr(), wide.ptr(), 1, 2, l32));
             destination.resize(ctx_, id, 2);
             if (le == limbs)
             {
-                detail::chk(moai_memcpy_d2d(c->h, destination.data(), wide.ptr(), 2 * le * n * sizeof(std::uint64_t)));
+                detail::chk(moai_memcpy_d2d(c->cur(), destination.data(), wide.ptr(), 2 * le * n * sizeof(std::uint64_t)));
             }
             else
             {
                 // divide_and_round_q_last_ntt_inplace (S/util/rns.cpp:830-901) == the rescaling kernel
-                detail::chk(moai_rescale_to_next(c->h, wide.ptr(), destination.data(), 1, 2, l32));
+                detail::chk(moai_rescale_to_next(c->cur(), wide.ptr(), destination.data(), 1, 2, l32));
             }
-            detail::chk(moai_synchronize(c->h)); // the host vectors go out of scope
+            detail::chk(moai_synchronize(c->cur())); // the host vectors go out of scope
             destination.is_ntt_form() = true;
             destination.scale() = 1.0;
         }
@@ -2706,11 +2824,11 @@ namespace sealapi
             detail::Lock lk(c->mu);
             if (plain.is_scalar())
             {
-                detail::chk(moai_add_scalar(c->h, destination.data(), plain.scalar_consts().data(), destination.data(), 1, 2, limbs));
+                detail::chk(moai_add_scalar(c->cur(), destination.data(), plain.scalar_consts().data(), destination.data(), 1, 2, limbs));
             }
             else
             {
-                detail::chk(moai_add_plain(c->h, destination.data(), plain.data(), destination.data(), 1, 2, limbs, 0));
+                detail::chk(moai_add_plain(c->cur(), destination.data(), plain.data(), destination.data(), 1, 2, limbs, 0));
             }
             destination.scale() = plain.scale();
         }
@@ -2752,16 +2870,16 @@ namespace sealapi
             if (a.size() == 3)
             {
                 // (c2 s + c1) s + c0
-                detail::chk(moai_multiply_plain(c->h, a.data(2), sk_.data(), tmp.ptr(), 1, 1, l, 0));
-                detail::chk(moai_add(c->h, tmp.ptr(), a.data(1), tmp.ptr(), 1, 1, l));
-                detail::chk(moai_multiply_plain(c->h, tmp.ptr(), sk_.data(), tmp.ptr(), 1, 1, l, 0));
+                detail::chk(moai_multiply_plain(c->cur(), a.data(2), sk_.data(), tmp.ptr(), 1, 1, l, 0));
+                detail::chk(moai_add(c->cur(), tmp.ptr(), a.data(1), tmp.ptr(), 1, 1, l));
+                detail::chk(moai_multiply_plain(c->cur(), tmp.ptr(), sk_.data(), tmp.ptr(), 1, 1, l, 0));
             }
             else
             {
-                detail::chk(moai_multiply_plain(c->h, a.data(1), sk_.data(), tmp.ptr(), 1, 1, l, 0));
+                detail::chk(moai_multiply_plain(c->cur(), a.data(1), sk_.data(), tmp.ptr(), 1, 1, l, 0));
             }
-            detail::chk(moai_add(c->h, tmp.ptr(), a.data(0), destination.data(), 1, 1, l));
-            detail::chk(moai_synchronize(c->h));
+            detail::chk(moai_add(c->cur(), tmp.ptr(), a.data(0), destination.data(), 1, 1, l));
+            detail::chk(moai_synchronize(c->cur()));
         }
 
     private:

@@ -90,6 +90,14 @@ extern "C"
         API_END
     }
 
+    int32_t moai_context_fork(moai_context *ctx, moai_context **lane)
+    {
+        API_BEGIN
+        MOAI_REQUIRE(ctx && ctx->c && lane, "null argument");
+        *lane = new moai_context{ context_fork(ctx->c) };
+        API_END
+    }
+
     int32_t moai_context_destroy(moai_context *ctx)
     {
         API_BEGIN
@@ -98,9 +106,16 @@ extern "C"
             if (ctx->c)
             {
                 cudaSetDevice(ctx->c->device);
-                cudaDeviceSynchronize();
-                device_release_cached();
-                delete ctx->c;
+                if (ctx->c->parent)
+                {
+                    delete ctx->c; // a lane: drains and destroys its own stream only
+                }
+                else
+                {
+                    cudaDeviceSynchronize();
+                    device_release_cached();
+                    delete ctx->c;
+                }
             }
             delete ctx;
         }

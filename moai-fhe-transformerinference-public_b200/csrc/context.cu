@@ -471,6 +471,15 @@ namespace moai
         {
             cudaEventDestroy(e);
         }
+        if (owns_stream && stream)
+        {
+            cudaStreamSynchronize(stream);
+            cudaStreamDestroy(stream);
+        }
+        if (parent)
+        {
+            return; // a lane: every table belongs to the parent
+        }
         cudaFree(d_limb);
         cudaFree(d_fwd);
         cudaFree(d_inv);
@@ -514,6 +523,10 @@ namespace moai
 
     const uint32_t *Context::galois_table(uint32_t elt)
     {
+        if (parent)
+        {
+            return parent->galois_table(elt);
+        }
         std::lock_guard<std::mutex> lk(galois_mu);
         auto it = galois_tables.find(elt);
         if (it != galois_tables.end())
@@ -535,6 +548,45 @@ namespace moai
         uint32_t *d = to_device(h);
         galois_tables[elt] = d;
         return d;
+    }
+
+    Context *context_fork(Context *parent)
+    {
+        MOAI_REQUIRE(parent != nullptr, "null context");
+        Context *r = parent->root();
+        MOAI_CUDA_CHECK(cudaSetDevice(r->device));
+        Context *c = new Context();
+        c->parent = r;
+        c->device = r->device;
+        c->log_n = r->log_n;
+        c->n = r->n;
+        c->kl = r->kl;
+        c->q = r->q;
+        c->sm_count = r->sm_count;
+        c->d_limb = r->d_limb;
+        c->d_fwd = r->d_fwd;
+        c->d_inv = r->d_inv;
+        c->d_fwd_fp = r->d_fwd_fp;
+        c->d_inv_fp = r->d_inv_fp;
+        c->d_inv_last = r->d_inv_last;
+        c->d_half_mod = r->d_half_mod;
+        c->d_two64 = r->d_two64;
+        c->d_ids = r->d_ids;
+        c->d_ids_ks = r->d_ids_ks;
+        c->d_fft_inv_roots = r->d_fft_inv_roots;
+        c->d_index_map = r->d_index_map;
+        c->h_fft_inv_roots = r->h_fft_inv_roots;
+        c->h_index_map = r->h_index_map;
+        c->h_limb = r->h_limb;
+        cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess)
+        {
+            c->parent = r; // nothing owned yet
+            delete c;
+            MOAI_CUDA_CHECK(e);
+        }
+        c->owns_stream = true;
+        return c;
     }
 
     Context *context_create(int log_n, const u64 *primes, int kl, int device)

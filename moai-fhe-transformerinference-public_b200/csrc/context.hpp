@@ -130,12 +130,24 @@ namespace moai
         std::mutex ksg_mu;
         std::map<std::pair<int, int>, void *> ksg_cache;
 
+        // A LANE of another context (context_fork): shares every immutable table of `parent` (twiddles, limb constants,
+        // encoder tables, Galois permutations, grouped-digit conversion tables) and owns only what is per caller — its
+        // CUDA stream (hence its arena: the allocator is keyed by (device, stream)), timers and counters.  One lane per
+        // host thread lets threads issue work concurrently (one stream per calling thread).
+        Context *parent = nullptr;
+        bool owns_stream = false;
+        Context *root()
+        {
+            return parent ? parent : this;
+        }
+
         ~Context();
         const uint32_t *galois_table(uint32_t elt);
         uint32_t elt_from_step(int step) const;
     };
 
     Context *context_create(int log_n, const u64 *primes, int kl, int device);
+    Context *context_fork(Context *parent); // a lane with its own non-blocking stream; must not outlive `parent`
     void ksg_release(Context *c); // csrc/ksgroup.cu
 
     // RAII device timer around a kernel (only active when Context::profiling is set): records

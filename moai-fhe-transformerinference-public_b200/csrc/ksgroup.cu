@@ -277,8 +277,9 @@ namespace moai
             return t;
         }
 
-        const KsgTables &tables(Context *c, int k, int limbs)
+        const KsgTables &tables(Context *lane, int k, int limbs)
         {
+            Context *c = lane->root(); // the tables are immutable: every lane of a context shares the root's cache
             std::lock_guard<std::mutex> lk(c->ksg_mu);
             auto it = c->ksg_cache.find({ k, limbs });
             if (it != c->ksg_cache.end())

@@ -16,6 +16,7 @@
 #include <iostream>
 #include <memory>
 #include <omp.h>
+#include <set>
 #include <sstream>
 #include <string>
 #include <sys/time.h>
@@ -992,6 +993,66 @@ extern "C"
             rtn[i].download(out + size_t(i) * 2 * rtn[i].coeff_modulus_size() * d->n);
         }
         *device_calls = int(d->boot->combined_device_calls() - before);
+        FD_CATCH(d)
+    }
+
+    // Thread lanes (SEALContext::set_thread_lanes): n ciphertexts processed one per iteration of an OpenMP loop, the way
+    // every module header of the reference calls its shared Evaluator (`#pragma omp parallel for`), here with a chain
+    // that produces, hands over and frees objects across calls:  out[i] = rescale(relin(x[i]^2) + x[i] * x[(i+1) % n]
+    // relinearized) rotated by one step.  x: [n][2][limbs][N] -> out: [n][2][limbs-1][N].  *threads = OpenMP threads
+    // that took part.
+    int fd_parallel_chain(void *h, const uint64_t *x, int n_cts, int limbs, double scale, int lanes, int with_rotation,
+                          uint64_t *out, int *threads)
+    {
+        auto d = static_cast<Drv *>(h);
+        FD_TRY
+        d->ctx->set_thread_lanes(lanes != 0);
+        vector<Ciphertext> in(n_cts), rtn(n_cts);
+        const size_t per = size_t(2) * limbs * d->n;
+        for (int i = 0; i < n_cts; i++)
+        {
+            load_ct(*d, x + size_t(i) * per, 2, limbs, scale, in[i]);
+        }
+        vector<string> errors(n_cts);
+        vector<int> tids(n_cts, 0);
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int i = 0; i < n_cts; i++)
+        {
+            try
+            {
+                tids[i] = omp_get_thread_num();
+                Ciphertext sq, pr;
+                d->evaluator->square(in[i], sq);
+                d->evaluator->relinearize_inplace(sq, d->rlk);
+                d->evaluator->multiply(in[i], in[(i + 1) % n_cts], pr);
+                d->evaluator->relinearize_inplace(pr, d->rlk);
+                d->evaluator->add_inplace(sq, pr);
+                d->evaluator->rescale_to_next_inplace(sq);
+                if (with_rotation)
+                {
+                    d->evaluator->rotate_vector(sq, 1, d->glk, rtn[i]);
+                }
+                else
+                {
+                    rtn[i] = sq;
+                }
+            }
+            catch (const exception &e)
+            {
+                errors[i] = e.what();
+            }
+        }
+        d->ctx->set_thread_lanes(false);
+        set<int> used(tids.begin(), tids.end());
+        *threads = int(used.size());
+        for (int i = 0; i < n_cts; i++)
+        {
+            if (!errors[i].empty())
+            {
+                throw logic_error("item " + to_string(i) + ": " + errors[i]);
+            }
+            rtn[i].download(out + size_t(i) * 2 * (limbs - 1) * d->n);
+        }
         FD_CATCH(d)
     }
 

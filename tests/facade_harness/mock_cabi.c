@@ -92,6 +92,12 @@ int32_t moai_context_create(int32_t log_n, const uint64_t *primes, int32_t n_key
     *out = c;
     return MOAI_OK;
 }
+int32_t moai_context_fork(moai_context *c, moai_context **lane)
+{
+    /* the test double has no streams: a lane is an independent context over the same primes (thread-safe by construction) */
+    REQ(c && lane, "bad arguments");
+    return moai_context_create(c->log_n, c->q, c->kl, 0, lane);
+}
 int32_t moai_context_destroy(moai_context *c)
 {
     if (c)

@@ -205,6 +205,38 @@ def test_reference_main_program_builds_unmodified_and_fails_loudly_without_gpu(t
     assert "no CPU fallback" in res.stderr
 
 
+def test_thread_lanes_match_the_serialised_facade():
+    """SEALContext::set_thread_lanes(true): every OpenMP thread works on its own lane of the context
+    (moai_context_fork: its own stream and arena) instead of queueing on one mutex.  A chain that creates, hands over
+    and frees ciphertexts across calls (square, multiply with the neighbour, relinearize, add, rescale, rotate) from an
+    OpenMP loop gives the same residues, bit for bit, as the serialised facade — here on the CPU test double of the
+    C ABI, in tests/test_gpu_zz_facade.py on the B200."""
+    import facade_harness as facade
+    from oracle import Oracle
+    if not facade.available(mock=True):
+        pytest.skip("facade driver not built")
+    o = Oracle(12, [40, 30, 30, 30, 40])
+    d = facade.FacadeDriver(12, primes=o.q, mock=True)
+    sk = o.gen_secret(3)
+    d.set_relin(o.gen_relin_key(sk, 5))
+    e = o.elt_from_step(1)
+    d.add_galois(e, o.gen_galois_key(sk, 9, e))
+    rng = np.random.default_rng(3)
+    n_cts, limbs, scale = 12, 3, 2.0 ** 30
+    zs = (rng.normal(size=(n_cts, o.n // 2)) + 1j * rng.normal(size=(n_cts, o.n // 2))) * 0.5
+    x = np.stack([o.encrypt_sym(sk, 20 + i, o.encode(zs[i], scale, limbs), limbs) for i in range(n_cts)])
+    serial, _ = d.parallel_chain(x.reshape(-1), n_cts, limbs, scale, lanes=False)
+    lanes, threads = d.parallel_chain(x.reshape(-1), n_cts, limbs, scale, lanes=True)
+    assert (serial == lanes).all()
+    assert threads >= 1
+    # and the chain computes what it says: rot_1(x_i^2 + x_i x_{i+1}) at scale^2 / q_2
+    sc = scale * scale / float(o.q[limbs - 1])
+    for i in range(n_cts):
+        dec = o.decode(o.decrypt(sk, lanes[i].reshape(-1), 2, limbs - 1), limbs - 1, sc)
+        want = np.roll(zs[i] * zs[i] + zs[i] * zs[(i + 1) % n_cts], -1)
+        assert np.abs(dec - want).max() < 1e-3          # 30-bit scale
+
+
 @pytest.mark.parametrize("real_slots", [True, False])
 def test_bootstrapper_request_combining_routes_every_ciphertext(real_slots):
     """Opt-in combining of concurrent bootstrap_3 calls (include/facade/Bootstrapper.h): 40 ciphertexts bootstrapped from

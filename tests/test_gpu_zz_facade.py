@@ -145,6 +145,37 @@ def test_bootstrapper_facade_preserves_message():
         d._chk(d.lib.fd_bootstrap_limbs(d.h, two.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_int(2), C.c_double(scale)))
 
 
+def test_thread_lanes_on_the_device():
+    """One lane (CUDA stream + arena) per OpenMP thread on the B200: the reference-style parallel loop over a shared
+    Evaluator gives the same residues as the mutex-serialised facade, bit for bit, and the decrypted values are right.
+    With the 58-bit special prime of the repo's chain shape so that the grouped / fused key-switch kernels run."""
+    import facade_harness as facade
+    from oracle import Oracle
+    if not facade.available(mock=False):
+        pytest.skip("oracle/_ref/libfacade_driver.so not built")
+    bits = [51] + [46] * 2 + [51] * 3 + [58]
+    o = Oracle(12, bits)
+    d = facade.FacadeDriver(12, primes=o.q, mock=False)
+    sk = o.gen_secret(3, hamming_weight=64)
+    d.set_relin(o.gen_relin_key(sk, 5))
+    e = o.elt_from_step(1)
+    d.add_galois(e, o.gen_galois_key(sk, 9, e))
+    rng = np.random.default_rng(3)
+    n_cts, limbs, scale = 24, 5, 2.0 ** 46
+    zs = (rng.normal(size=(n_cts, o.n // 2)) + 1j * rng.normal(size=(n_cts, o.n // 2))) * 0.5
+    x = np.stack([o.encrypt_sym(sk, 20 + i, o.encode(zs[i], scale, limbs), limbs) for i in range(n_cts)])
+    serial, _ = d.parallel_chain(x.reshape(-1), n_cts, limbs, scale, lanes=False)
+    for rep in range(3):                      # races do not show every time
+        lanes, threads = d.parallel_chain(x.reshape(-1), n_cts, limbs, scale, lanes=True)
+        assert (serial == lanes).all(), rep
+    sc = scale * scale / float(o.q[limbs - 1])
+    for i in range(n_cts):
+        dec = o.decode(o.decrypt(sk, lanes[i].reshape(-1), 2, limbs - 1), limbs - 1, sc)
+        want = np.roll(zs[i] * zs[i] + zs[i] * zs[(i + 1) % n_cts], -1)
+        assert np.abs(dec - want).max() < 1e-6
+    print("thread lanes on the B200: %d OpenMP threads, %d ciphertexts, bit-identical to the serialised facade" % (threads, n_cts))
+
+
 # ---- include/facade_fused first on the include path: the same module functions as fused device pipelines ----
 @pytest.fixture(scope="module")
 def small_fused(sealref_small):
