@@ -304,9 +304,11 @@ class FacadeDriver:
         """square / multiply / relinearize / add / rescale (/ rotate) on n ciphertexts from an OpenMP loop, with one lane
         per thread (lanes=True) or the context mutex (lanes=False); returns ([n][2][limbs-1][N], threads used)."""
         out = np.zeros(n_cts * 2 * (limbs - 1) * self.n, dtype=np.uint64)
-        th = C.c_int(0)
+        th, ms = C.c_int(0), C.c_double(0)
         self._chk(self.lib.fd_parallel_chain(self.h, _p(x), C.c_int(n_cts), C.c_int(limbs), C.c_double(scale),
-                                             C.c_int(int(lanes)), C.c_int(int(with_rotation)), _p(out), C.byref(th)))
+                                             C.c_int(int(lanes)), C.c_int(int(with_rotation)), _p(out), C.byref(th),
+                                             C.byref(ms)))
+        self.last_loop_ms = ms.value
         return out.reshape(n_cts, 2, limbs - 1, self.n), th.value
 
     def softmax_boot(self, x, num, limbs, scale, bias_vec, input_num, iters, layer_id, max_limbs):

@@ -1002,7 +1002,7 @@ extern "C"
     // relinearized) rotated by one step.  x: [n][2][limbs][N] -> out: [n][2][limbs-1][N].  *threads = OpenMP threads
     // that took part.
     int fd_parallel_chain(void *h, const uint64_t *x, int n_cts, int limbs, double scale, int lanes, int with_rotation,
-                          uint64_t *out, int *threads)
+                          uint64_t *out, int *threads, double *loop_ms)
     {
         auto d = static_cast<Drv *>(h);
         FD_TRY
@@ -1015,6 +1015,8 @@ extern "C"
         }
         vector<string> errors(n_cts);
         vector<int> tids(n_cts, 0);
+        d->ctx->synchronize();
+        const auto t0 = chrono::steady_clock::now();
 #pragma omp parallel for schedule(dynamic, 1)
         for (int i = 0; i < n_cts; i++)
         {
@@ -1042,6 +1044,7 @@ extern "C"
                 errors[i] = e.what();
             }
         }
+        *loop_ms = chrono::duration<double, milli>(chrono::steady_clock::now() - t0).count(); // every call has drained
         d->ctx->set_thread_lanes(false);
         set<int> used(tids.begin(), tids.end());
         *threads = int(used.size());
