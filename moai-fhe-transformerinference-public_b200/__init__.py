@@ -370,6 +370,20 @@ class Backend:
             C.c_int32(K), C.c_int32(Cc), C.c_int32(K), C.c_int32(l), C.c_double(scale), _ptr(out)))
         return out
 
+    def ct_pt_matrix_mul_wo_pre_w_mask_fast(self, enc_X, W, bias_vec, scale, out=None):
+        """Fast-mode masked matmul: one tensor-core GEMM times ONE mask plaintext (tolerance, not bit-exact)."""
+        K, p, l, n = enc_X.shape
+        W = np.ascontiguousarray(W, dtype=np.float64)
+        mask = np.ascontiguousarray(bias_vec, dtype=np.int32)
+        if W.shape[0] != K or mask.size != n // 2:
+            raise MoaiError(1, "bad dimensions of X or W")
+        Cc = W.shape[1]
+        out = self.empty(Cc, 2, l - 1, n) if out is None else out
+        self._chk(self.lib.moai_ct_pt_matrix_mul_wo_pre_w_mask_fast(
+            self.h, _ptr(enc_X), W.ctypes.data_as(C.POINTER(C.c_double)), mask.ctypes.data_as(C.POINTER(C.c_int32)),
+            C.c_int32(K), C.c_int32(Cc), C.c_int32(K), C.c_int32(l), C.c_double(scale), _ptr(out)))
+        return out
+
     # ---- vector encoder (A12)
     def encode(self, values, scale, limbs):
         """CKKSEncoder::encode for a batch: values [count, n_vals] (or [n_vals]) real/complex ->

@@ -539,6 +539,19 @@ extern "C"
         API_END
     }
 
+    int32_t moai_ct_pt_matrix_mul_wo_pre_w_mask_fast(moai_context *ctx, const uint64_t *enc_X, const double *W,
+                                                     const int32_t *bias_vec, int32_t col_X, int32_t col_W, int32_t row_W,
+                                                     int32_t limbs, double scale, uint64_t *out)
+    {
+        API_BEGIN
+        Context *c = get(ctx);
+        MOAI_REQUIRE(col_X == row_W, "bad dimensions of X or W");
+        MOAI_REQUIRE(enc_X && W && bias_vec && out, "null argument");
+        MOAI_REQUIRE(ct_pt_matmul_masked_fast_ok(scale), "scale too small for the factorised masked matmul (needs >= 2^44)");
+        ct_pt_matmul_masked_fast(c, CU(enc_X), W, reinterpret_cast<const int *>(bias_vec), row_W, col_W, limbs, scale, U(out));
+        API_END
+    }
+
     int32_t moai_encode_vector(moai_context *ctx, const double *values, int64_t count, int32_t n_vals, double scale,
                                int32_t limbs, uint64_t *out)
     {

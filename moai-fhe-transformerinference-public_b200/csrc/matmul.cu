@@ -585,8 +585,10 @@ namespace moai
 
     // X: [K][2][limbs][n] device; W: host row-major K x C doubles; out: [C][2][limbs-1][n] device
     void ct_pt_matmul_scalar(Context *c, const u64 *X, const double *h_W, int K, int C, int limbs, double scale,
-                             u64 *out)
+                             u64 *out, const u64 *post_pt)
     {
+        // post_pt (optional, [limbs][n]): every pre-rescale output column is multiplied by this plaintext before the
+        // rescale (the factorised masked matmul below)
         MOAI_REQUIRE(K >= 1 && C >= 1, "bad dimensions of X or W");
         MOAI_REQUIRE(limbs >= 2 && limbs <= c->kl - 1, "end of modulus switching chain reached");
         MOAI_REQUIRE(K <= 4096, "K too large for the 128-bit lazy accumulator");
@@ -631,6 +633,10 @@ namespace moai
                     PhaseTimer pt(c, "ctpt_gemm");
                     tc5_gemm(c, X, dBp.as<unsigned char>(), Y.as<u64>(), K, C, c0, cn, np, limbs, 0, 2 * limbs, c->stream);
                 }
+                if (post_pt)
+                {
+                    ew_multiply_plain(c, Y.as<u64>(), post_pt, Y.as<u64>(), cn, 2, limbs, 0);
+                }
                 rescale(c, Y.as<u64>(), out + (size_t)c0 * 2 * (limbs - 1) * n, cn, 2, limbs);
             }
             return;
@@ -657,6 +663,10 @@ namespace moai
                                 0, 2 * limbs, c->stream);
                 }
                 MOAI_CUDA_CHECK(cudaGetLastError());
+                if (post_pt)
+                {
+                    ew_multiply_plain(c, Y.as<u64>(), post_pt, Y.as<u64>(), cn, 2, limbs, 0);
+                }
                 rescale(c, Y.as<u64>(), out + (size_t)c0 * 2 * (limbs - 1) * n, cn, 2, limbs);
             }
             return;
@@ -695,6 +705,10 @@ namespace moai
             }
             c->launches += 1;
             MOAI_CUDA_CHECK(cudaGetLastError());
+            if (post_pt)
+            {
+                ew_multiply_plain(c, Y.as<u64>(), post_pt, Y.as<u64>(), cn, 2, limbs, 0);
+            }
             rescale(c, Y.as<u64>(), out + (size_t)c0 * 2 * (limbs - 1) * n, cn, 2, limbs);
         }
     }
@@ -906,5 +920,35 @@ namespace moai
             }
         }
         rescale(c, Y.as<u64>(), out, C, 2, limbs);
+    }
+    // Fast-mode ct_pt_matrix_mul_wo_pre_w_mask: the reference encodes one plaintext per weight,
+    // encode(w_ji * mask) at `scale` (Ct_pt_matrix_mul.hpp:127-134) — K * C encodings and K * C * limbs transforms, which
+    // is what ct_pt_matmul_masked reproduces bit for bit (2.8 s for 768 x 768 at N = 65536).  Encoding is linear up to
+    // its rounding, so   sum_j X_j (.) encode(w_ji mask)  ~  [sum_j round(w_ji s_w) X_j] (.) encode(mask at 2^28),
+    // s_w = scale / 2^28:  ONE scalar GEMM on the tensor cores with integer weights at scale s_w, ONE plaintext, the same
+    // output scale (s_w 2^28 = scale exactly) and the same single rescale.  Error against the exact path: weights
+    // quantised to 1 / s_w (2^-18 at scale 2^46) and the mask's coefficients rounded at 2^28 (slot error ~ sqrt(N) 0.29 /
+    // 2^28 of the output value).  Measured on C1 (768 x 768, N = 65536, max |XW| = 25): 1.15e-4 max-abs with the mask at
+    // 2^26, against 1.7e-5 for the exact path and a stated tolerance of 2.5e-3; 15 ms against 2.8 s
+    // (tests/test_gpu_fullsize.py).  Needs scale >= 2^44 (16 bits for the weights).
+    constexpr double MASK_PT_SCALE = 268435456.0; // 2^28
+    bool ct_pt_matmul_masked_fast_ok(double scale)
+    {
+        return scale >= MASK_PT_SCALE * 65536.0;
+    }
+    void ct_pt_matmul_masked_fast(Context *c, const u64 *X, const double *h_W, const int *h_mask, int K, int C, int limbs,
+                                  double scale, u64 *out)
+    {
+        MOAI_REQUIRE(ct_pt_matmul_masked_fast_ok(scale), "scale too small for the factorised masked matmul");
+        const size_t n = c->n;
+        Scratch dmask((n / 2) * sizeof(int), c->stream);
+        Scratch done(sizeof(double), c->stream);
+        Scratch V((size_t)limbs * n * sizeof(u64), c->stream);
+        const double one = 1.0;
+        MOAI_CUDA_CHECK(cudaMemcpyAsync(dmask.p, h_mask, (n / 2) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        MOAI_CUDA_CHECK(cudaMemcpyAsync(done.p, &one, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        MOAI_CUDA_CHECK(cudaStreamSynchronize(c->stream)); // `one` is a stack variable
+        encode_masked_weights(c, done.as<double>(), dmask.as<int>(), 1, MASK_PT_SCALE, limbs, V.as<u64>());
+        ct_pt_matmul_scalar(c, X, h_W, K, C, limbs, scale / MASK_PT_SCALE, out, V.as<u64>());
     }
 } // namespace moai

@@ -714,7 +714,7 @@ namespace moai
     namespace
     {
         Ct masked_matmul(const Evaluator &ev, const Ct &X, const std::vector<double> &W, const std::vector<int> &bias_vec,
-                         int col_W)
+                         int col_W, bool fast = false)
         {
             // ct_pt_matrix_mul_wo_pre_w_mask (Ct_pt_matrix_mul.hpp:103-170)
             bool all_ones = true;
@@ -726,6 +726,11 @@ namespace moai
             if (all_ones)
             {
                 ct_pt_matmul_scalar(ev.c, X.d, W.data(), (int)X.batch, col_W, X.limbs, X.scale, out.d);
+            }
+            else if (fast && ct_pt_matmul_masked_fast_ok(X.scale))
+            {
+                // fast mode: one tensor-core GEMM times ONE mask plaintext instead of K * C encodings (csrc/matmul.cu)
+                ct_pt_matmul_masked_fast(ev.c, X.d, W.data(), bias_vec.data(), (int)X.batch, col_W, X.limbs, X.scale, out.d);
             }
             else
             {
@@ -841,7 +846,7 @@ namespace moai
             Ct so;
             {
                 PhaseTimer t(c, "selfoutput_matmul");
-                so = add_masked_bias(ev, masked_matmul(ev, att_out, w.selfoutput, bias_vec, hidden), w.selfoutput_bias,
+                so = add_masked_bias(ev, masked_matmul(ev, att_out, w.selfoutput, bias_vec, hidden, !keys.relin_fast.empty()), w.selfoutput_bias,
                                      bias_vec, scale);
                 att_out = Ct();
             }
@@ -919,7 +924,7 @@ namespace moai
             Ct fin;
             {
                 PhaseTimer t(c, "final_matmul");
-                fin = add_masked_bias(ev, masked_matmul(ev, inter, w.final_weight, bias_vec, hidden), w.final_bias,
+                fin = add_masked_bias(ev, masked_matmul(ev, inter, w.final_weight, bias_vec, hidden, !keys.relin_fast.empty()), w.final_bias,
                                       bias_vec, scale);
                 inter = Ct();
             }

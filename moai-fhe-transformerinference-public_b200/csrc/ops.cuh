@@ -103,7 +103,7 @@ namespace moai
 
     // fused module: out[C][2][limbs-1][n] = rescale(sum_j X[j] * encode_scalar(W[j][i]))
     void ct_pt_matmul_scalar(Context *c, const u64 *X, const double *h_W, int K, int C, int limbs, double scale,
-                             u64 *out);
+                             u64 *out, const u64 *post_pt = nullptr);
 
     // tcgen05 (5th-generation tensor core) version of the byte-plane GEMM (csrc/matmul_tc5.cu)
     size_t tc5_packed_weight_bytes(int K, int C, int limbs, int np);
@@ -123,4 +123,8 @@ namespace moai
     // out[C][2][limbs-1][n] = rescale(sum_j X[j] * encode_vector(W[j][i] * mask))  (exact general-mask path)
     void ct_pt_matmul_masked(Context *c, const u64 *X, const double *h_W, const int *h_mask, int K, int C, int limbs,
                              double scale, u64 *out);
+    // fast mode: one scalar GEMM with weights at scale / 2^26 times ONE mask plaintext at 2^26 (csrc/matmul.cu)
+    bool ct_pt_matmul_masked_fast_ok(double scale);
+    void ct_pt_matmul_masked_fast(Context *c, const u64 *X, const double *h_W, const int *h_mask, int K, int C, int limbs,
+                                  double scale, u64 *out);
 } // namespace moai

@@ -361,7 +361,37 @@ def test_c1_selfoutput_linear_with_reference_mask(pkg, env):
     rng = np.random.default_rng(20250991)
     W = rng.normal(size=(768, 768)) * 0.04
     x = encrypt_cols(env, pack_rows(X), 2)
+    import time
+    import torch
     out = be.ct_pt_matrix_mul_wo_pre_w_mask(x, W, env["mask"], SCALE)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = be.ct_pt_matrix_mul_wo_pre_w_mask(x, W, env["mask"], SCALE)
+    torch.cuda.synchronize()
+    ms_masked = (time.perf_counter() - t0) * 1e3
+    ones = np.ones_like(env["mask"])
+    be.ct_pt_matrix_mul_wo_pre_w_mask(x, W, ones, SCALE)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    be.ct_pt_matrix_mul_wo_pre_w_mask(x, W, ones, SCALE)
+    torch.cuda.synchronize()
+    ms_all = (time.perf_counter() - t0) * 1e3
+    # the exact masked path encodes one plaintext per (weight, limb) like the reference; the all-valid mask is the scalar
+    # case and takes the tensor-core GEMM
+    # fast mode: [sum_j round(w s_w) X_j] (.) encode(mask at 2^28) — one GEMM, one plaintext
+    fast = be.ct_pt_matrix_mul_wo_pre_w_mask_fast(x, W, env["mask"], SCALE)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    fast = be.ct_pt_matrix_mul_wo_pre_w_mask_fast(x, W, env["mask"], SCALE)
+    torch.cuda.synchronize()
+    ms_fast = (time.perf_counter() - t0) * 1e3
+    print("C1 768 x 768 at 2 limbs, second call: reference's 5-token mask %.1f ms exact / %.1f ms factorised, all-valid "
+          "mask %.1f ms" % (ms_masked, ms_fast, ms_all))
+    gotf = slot_values(env, fast, SCALE, VALID + [1, 257]).real.T
+    errf = np.abs(gotf[:TOK] - X @ W).max()
+    print("C1 masked matmul, factorised: max-abs %.3g, masked-out slots %.3g" % (errf, np.abs(gotf[TOK:]).max()))
+    assert errf < 1e-4 * max(1.0, np.abs(X @ W).max())
+    assert np.abs(gotf[TOK:]).max() < 1e-6
     assert out.shape == (768, 2, 1, N)
     got = slot_values(env, out, SCALE, VALID + [1, 257]).real.T
     exp = X @ W
