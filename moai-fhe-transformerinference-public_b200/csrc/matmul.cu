@@ -931,10 +931,15 @@ namespace moai
     // 2^28 of the output value).  Measured on C1 (768 x 768, N = 65536, max |XW| = 25): 1.15e-4 max-abs with the mask at
     // 2^26, against 1.7e-5 for the exact path and a stated tolerance of 2.5e-3; 15 ms against 2.8 s
     // (tests/test_gpu_fullsize.py).  Needs scale >= 2^44 (16 bits for the weights).
-    constexpr double MASK_PT_SCALE = 268435456.0; // 2^28
+    // bits of the mask plaintext's scale: its slot error grows like sqrt(N) / 2^t, the weights' like sqrt(K) / 2^(46 - t);
+    // t = 20 + log2(N) / 2 balances them (28 at N = 65536)
+    static double mask_pt_scale(const Context *c)
+    {
+        return std::ldexp(1.0, 20 + c->log_n / 2);
+    }
     bool ct_pt_matmul_masked_fast_ok(double scale)
     {
-        return scale >= MASK_PT_SCALE * 65536.0;
+        return scale >= 17592186044416.0; // 2^44: at least 16 bits for the weights
     }
     void ct_pt_matmul_masked_fast(Context *c, const u64 *X, const double *h_W, const int *h_mask, int K, int C, int limbs,
                                   double scale, u64 *out)
@@ -948,7 +953,8 @@ namespace moai
         MOAI_CUDA_CHECK(cudaMemcpyAsync(dmask.p, h_mask, (n / 2) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
         MOAI_CUDA_CHECK(cudaMemcpyAsync(done.p, &one, sizeof(double), cudaMemcpyHostToDevice, c->stream));
         MOAI_CUDA_CHECK(cudaStreamSynchronize(c->stream)); // `one` is a stack variable
-        encode_masked_weights(c, done.as<double>(), dmask.as<int>(), 1, MASK_PT_SCALE, limbs, V.as<u64>());
-        ct_pt_matmul_scalar(c, X, h_W, K, C, limbs, scale / MASK_PT_SCALE, out, V.as<u64>());
+        const double vs = mask_pt_scale(c);
+        encode_masked_weights(c, done.as<double>(), dmask.as<int>(), 1, vs, limbs, V.as<u64>());
+        ct_pt_matmul_scalar(c, X, h_W, K, C, limbs, scale / vs, out, V.as<u64>());
     }
 } // namespace moai
