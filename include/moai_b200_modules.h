@@ -40,7 +40,7 @@ int32_t moai_ct_pt_matrix_mul_wo_pre_w_mask(moai_context *ctx, const uint64_t *e
 /* Fast-mode variant of the same module (same arguments and output level / scale; needs scale >= 2^44).  The reference
  * encodes one plaintext per weight, encode(w * mask) (Ct_pt_matrix_mul.hpp:127-134): K * C encodings, which the entry
  * point above reproduces bit for bit (2.8 s for 768 x 768 at N = 65536).  This one factorises it — [sum_j round(w_ji
- * scale / 2^28) X_j] (.) encode(mask at 2^28) — into ONE tensor-core GEMM and ONE plaintext: 15 ms, decrypted result
+ * scale / 2^26) X_j] (.) encode(mask at 2^26) — into ONE tensor-core GEMM and ONE plaintext: 15-30 ms, decrypted result
  * within 1e-4 relative of the float64 product like the exact path (tests/test_gpu_fullsize.py). */
 int32_t moai_ct_pt_matrix_mul_wo_pre_w_mask_fast(moai_context *ctx, const uint64_t *enc_X, const double *W,
                                                  const int32_t *bias_vec, int32_t col_X, int32_t col_W, int32_t row_W,

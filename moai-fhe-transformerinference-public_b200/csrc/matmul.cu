@@ -924,18 +924,19 @@ namespace moai
     // Fast-mode ct_pt_matrix_mul_wo_pre_w_mask: the reference encodes one plaintext per weight,
     // encode(w_ji * mask) at `scale` (Ct_pt_matrix_mul.hpp:127-134) — K * C encodings and K * C * limbs transforms, which
     // is what ct_pt_matmul_masked reproduces bit for bit (2.8 s for 768 x 768 at N = 65536).  Encoding is linear up to
-    // its rounding, so   sum_j X_j (.) encode(w_ji mask)  ~  [sum_j round(w_ji s_w) X_j] (.) encode(mask at 2^28),
-    // s_w = scale / 2^28:  ONE scalar GEMM on the tensor cores with integer weights at scale s_w, ONE plaintext, the same
-    // output scale (s_w 2^28 = scale exactly) and the same single rescale.  Error against the exact path: weights
-    // quantised to 1 / s_w (2^-18 at scale 2^46) and the mask's coefficients rounded at 2^28 (slot error ~ sqrt(N) 0.29 /
-    // 2^28 of the output value).  Measured on C1 (768 x 768, N = 65536, max |XW| = 25): 1.15e-4 max-abs with the mask at
-    // 2^26, against 1.7e-5 for the exact path and a stated tolerance of 2.5e-3; 15 ms against 2.8 s
-    // (tests/test_gpu_fullsize.py).  Needs scale >= 2^44 (16 bits for the weights).
-    // bits of the mask plaintext's scale: its slot error grows like sqrt(N) / 2^t, the weights' like sqrt(K) / 2^(46 - t);
-    // t = 20 + log2(N) / 2 balances them (28 at N = 65536)
-    static double mask_pt_scale(const Context *c)
+    // its rounding, so   sum_j X_j (.) encode(w_ji mask)  ~  [sum_j round(w_ji s_w) X_j] (.) encode(mask at 2^26),
+    // s_w = scale / 2^26:  ONE scalar GEMM on the tensor cores with integer weights at scale s_w, ONE plaintext, the same
+    // output scale (s_w 2^26 = scale exactly) and the same single rescale.  Error against the exact path: weights
+    // quantised to 1 / s_w (2^-20 at scale 2^46) and the mask's coefficients rounded at 2^26 (slot error ~ sqrt(N) 0.29 /
+    // 2^26 of the output value).  Measured on C1 (768 x 768, N = 65536, max |XW| = 25): 1.15e-4 max-abs, against 1.7e-5
+    // for the exact path and a stated tolerance of 2.5e-3; 15 ms against 2.8 s (tests/test_gpu_fullsize.py).
+    // Needs scale >= 2^44.
+    // bits of the mask plaintext's scale: its slot error grows like sqrt(N) / 2^t, the weights' like sqrt(K) |x| / 2^(46 - t).
+    // Measured on C1 at N = 65536 (max |XW| = 25): t = 26 -> 1.15e-4 max-abs, t = 28 -> 4.2e-4 (the weights dominate);
+    // encoder layer at N = 4096, fast vs SEAL-exact keys: t = 26 -> 1.6e-5, t = 28 -> 5.6e-5.
+    static double mask_pt_scale(const Context *)
     {
-        return std::ldexp(1.0, 20 + c->log_n / 2);
+        return 67108864.0; // 2^26
     }
     bool ct_pt_matmul_masked_fast_ok(double scale)
     {

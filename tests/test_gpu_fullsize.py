@@ -378,7 +378,7 @@ def test_c1_selfoutput_linear_with_reference_mask(pkg, env):
     ms_all = (time.perf_counter() - t0) * 1e3
     # the exact masked path encodes one plaintext per (weight, limb) like the reference; the all-valid mask is the scalar
     # case and takes the tensor-core GEMM
-    # fast mode: [sum_j round(w s_w) X_j] (.) encode(mask at 2^28) — one GEMM, one plaintext
+    # fast mode: [sum_j round(w s_w) X_j] (.) encode(mask at 2^26) — one GEMM, one plaintext
     fast = be.ct_pt_matrix_mul_wo_pre_w_mask_fast(x, W, env["mask"], SCALE)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
