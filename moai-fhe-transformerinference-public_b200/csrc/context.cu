@@ -3,6 +3,7 @@
 // prime); the tables below are the same mathematical objects SEAL builds in
 // NTTTables::initialize (S/util/ntt.cpp:241-300), RNSTool::initialize (S/util/rns.cpp:578-787),
 // GaloisTool (S/util/galois.cpp:18-95) and CKKSEncoder::CKKSEncoder (S/ckks.cpp:20-75).
+#include <memory>
 #include "context.hpp"
 #include <chrono>
 #include "comm.hpp"
@@ -594,7 +595,8 @@ namespace moai
         MOAI_REQUIRE(log_n >= 12 && log_n <= 16, "log_n must be in [12, 16]");
         MOAI_REQUIRE(kl >= 2 && kl <= 64, "need 2..64 primes (data primes + special prime)");
         MOAI_CUDA_CHECK(cudaSetDevice(device));
-        Context *c = new Context();
+        std::unique_ptr<Context> owner(new Context()); // freed if a later check throws
+        Context *c = owner.get();
         c->device = device;
         c->log_n = log_n;
         c->n = (size_t)1 << log_n;
@@ -771,6 +773,6 @@ namespace moai
         MOAI_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
         uint64_t thresh = UINT64_MAX;
         MOAI_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
-        return c;
+        return owner.release();
     }
 } // namespace moai

@@ -738,13 +738,54 @@ namespace moai
             wmax = std::fmax(wmax, std::fabs(h_W[i]));
         }
         MOAI_REQUIRE(wmax * scale < 9.0e18, "encoded value is too large");
-        cudaStream_t s_in, s_out;
-        MOAI_CUDA_CHECK(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-        MOAI_CUDA_CHECK(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        // side streams and events: destroyed on EVERY exit path, after the streams have drained (a check that throws
+        // midway must neither leak them nor hand the device buffers back to the arena while a copy still uses them)
+        struct SideResources
+        {
+            cudaStream_t s_in = nullptr, s_out = nullptr;
+            std::vector<cudaEvent_t> events;
+            cudaEvent_t event()
+            {
+                cudaEvent_t e = nullptr;
+                MOAI_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                events.push_back(e);
+                return e;
+            }
+            void drain() const
+            {
+                if (s_in)
+                {
+                    cudaStreamSynchronize(s_in);
+                }
+                if (s_out)
+                {
+                    cudaStreamSynchronize(s_out);
+                }
+            }
+            ~SideResources()
+            {
+                drain();
+                for (cudaEvent_t e : events)
+                {
+                    cudaEventDestroy(e);
+                }
+                if (s_in)
+                {
+                    cudaStreamDestroy(s_in);
+                }
+                if (s_out)
+                {
+                    cudaStreamDestroy(s_out);
+                }
+            }
+        } side;
+        MOAI_CUDA_CHECK(cudaStreamCreateWithFlags(&side.s_in, cudaStreamNonBlocking));
+        MOAI_CUDA_CHECK(cudaStreamCreateWithFlags(&side.s_out, cudaStreamNonBlocking));
+        cudaStream_t s_in = side.s_in, s_out = side.s_out;
         std::vector<cudaEvent_t> landed(2 * limbs);
         for (auto &e : landed)
         {
-            MOAI_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            e = side.event();
         }
         const int Kp = (K + 31) / 32 * 32, Cp = (C + IM_TILE_N - 1) / IM_TILE_N * IM_TILE_N, np = 7;
         const size_t ct_words = (size_t)2 * limbs * n;
@@ -758,6 +799,16 @@ namespace moai
             Scratch dX((size_t)K * ct_words * sizeof(u64), c->stream);
             Scratch Y((size_t)C * ct_words * sizeof(u64), c->stream);
             Scratch dOut((size_t)C * 2 * (limbs - 1) * n * sizeof(u64), c->stream);
+            struct DrainFirst // declared after the buffers: runs before they are released, also while unwinding
+            {
+                const SideResources &r;
+                cudaStream_t main;
+                ~DrainFirst()
+                {
+                    r.drain();
+                    cudaStreamSynchronize(main);
+                }
+            } drain_first{ side, c->stream };
             MOAI_CUDA_CHECK(cudaMemcpyAsync(dW.p, h_W, kc * sizeof(double), cudaMemcpyHostToDevice, c->stream));
             if (tc5)
             {
@@ -771,8 +822,7 @@ namespace moai
                 c->launches += 1;
             }
             // the buffers come from the stream-ordered arena of c->stream: order the side streams after it
-            cudaEvent_t ready;
-            MOAI_CUDA_CHECK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+            cudaEvent_t ready = side.event();
             MOAI_CUDA_CHECK(cudaEventRecord(ready, c->stream));
             MOAI_CUDA_CHECK(cudaStreamWaitEvent(s_in, ready, 0));
             MOAI_CUDA_CHECK(cudaStreamWaitEvent(s_out, ready, 0));
@@ -807,7 +857,7 @@ namespace moai
             {
                 const int cn = std::min(out_chunk, C - c0);
                 rescale(c, Y.as<u64>() + (size_t)c0 * ct_words, dOut.as<u64>() + (size_t)c0 * out_ct, cn, 2, limbs);
-                MOAI_CUDA_CHECK(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+                done[k] = side.event();
                 MOAI_CUDA_CHECK(cudaEventRecord(done[k], c->stream));
                 MOAI_CUDA_CHECK(cudaStreamWaitEvent(s_out, done[k], 0));
                 MOAI_CUDA_CHECK(cudaMemcpyAsync(h_out + (size_t)c0 * out_ct, dOut.as<u64>() + (size_t)c0 * out_ct,
@@ -815,18 +865,7 @@ namespace moai
             }
             MOAI_CUDA_CHECK(cudaStreamSynchronize(s_out));
             MOAI_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-            for (auto &e : done)
-            {
-                cudaEventDestroy(e);
-            }
-            cudaEventDestroy(ready);
-        } // device buffers return to the arena after every stream has drained
-        for (auto &e : landed)
-        {
-            cudaEventDestroy(e);
-        }
-        cudaStreamDestroy(s_in);
-        cudaStreamDestroy(s_out);
+        } // device buffers return to the arena after every stream has drained (DrainFirst); `side` frees the handles
     }
 
     namespace
