@@ -446,7 +446,13 @@ namespace sealapi
                 }
                 else
                 {
-                    moai_synchronize(m_.owner->cur());
+                    try
+                    {
+                        moai_synchronize(m_.owner->cur()); // the lane exists already unless the call never reached the device
+                    }
+                    catch (...)
+                    {
+                    }
                 }
             }
             Lock(const Lock &) = delete;
