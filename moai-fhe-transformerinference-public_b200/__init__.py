@@ -87,6 +87,17 @@ class Backend:
         self.h = h
         self.use_torch_stream()
 
+    def fork(self):
+        """A lane of this context (moai_context_fork): the same tables, its own CUDA stream and arena — one per host thread.
+        Close lanes before their parent; results of a lane are complete after lane.synchronize()."""
+        lane = object.__new__(Backend)
+        lane.torch, lane.lib = self.torch, self.lib
+        lane.log_n, lane.n, lane.primes, lane.kl, lane.device = self.log_n, self.n, self.primes, self.kl, self.device
+        h = C.c_void_p()
+        self._chk(self.lib.moai_context_fork(self.h, C.byref(h)))
+        lane.h = h
+        return lane
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.moai_context_destroy(self.h)

@@ -264,3 +264,65 @@ def test_error_codes(pkg, backend_small, oracle_small):
     assert ei.value.code == 1
     empty = be.empty(0, 2, 3, o.n)
     assert be.add(empty, empty).shape[0] == 0  # empty batch is a no-op
+
+
+def test_context_lanes_from_threads(pkg):
+    """moai_context_fork: four host threads, each with its own lane (stream + arena) of one context, run NTT ->
+    multiply_plain -> rescale -> rotation chains concurrently; every lane's result equals the root context's, bit for
+    bit (the tables — twiddles, Galois permutations — are shared and immutable)."""
+    import threading
+    import torch
+    from oracle import Oracle
+    o = Oracle(12, [40, 30, 30, 40])
+    be = pkg.Backend(12, o.q)
+    rng = np.random.default_rng(5)
+    limbs = 3
+
+    def rnd(size, batch=4):
+        out = np.empty((batch, size, limbs, o.n), dtype=np.uint64)
+        for l in range(limbs):
+            out[:, :, l, :] = rng.integers(0, int(o.q[l]), (batch, size, o.n), dtype=np.uint64)
+        return out
+
+    xs = [pkg.to_device(rnd(2)) for _ in range(4)]
+    pt = pkg.to_device(rnd(1, 1)[0, 0])
+    ksk = np.empty((o.kl - 1, 2, o.kl, o.n), dtype=np.uint64)
+    for l in range(o.kl):
+        ksk[:, :, l, :] = rng.integers(0, int(o.q[l]), (o.kl - 1, 2, o.n), dtype=np.uint64)
+    dk = pkg.to_device(ksk)
+    elt = be.galois_elt_from_step(3)
+    torch.cuda.synchronize()
+
+    def chain(b, x):
+        # the tensors are torch allocations (torch's own stream-ordered pool, not the lane's arena): drain the lane before
+        # an intermediate is dropped
+        y = b.multiply_plain(x, pt)
+        z = b.rescale_to_next(y)
+        r = b.apply_galois(z, elt, dk)
+        b.synchronize()
+        return r
+
+    want = [chain(be, x) for x in xs]
+    be.synchronize()
+    lanes = [be.fork() for _ in range(4)]
+    got, errs = [None] * 4, []
+
+    def work(i):
+        try:
+            for _ in range(5):
+                got[i] = chain(lanes[i], xs[i])
+            lanes[i].synchronize()
+        except Exception as e:   # noqa: BLE001
+            errs.append(repr(e))
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for i in range(4):
+        assert (got[i] == want[i]).all()
+    for ln in lanes:
+        ln.close()
+    be.close()
